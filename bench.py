@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""bench.py -- voxelize + SVO build throughput on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+A "step" is one pass of the hot path (partition -> voxelize -> build, incl. the
+sparse clear that re-arms the bit-grid) over the workload.  N = 1 runs
+BASELINE.json configs[1]: `svo_builder_binary -s 1024` on a synthetic 2 M-triangle
+displaced sphere.  N > 1 (torchrun, one rank per GPU) runs the sharded path: a
+(2*1024)^3 grid whose 8 logical partitions are 1024^3 each; N of the octants hold
+one displaced sphere each, rank r voxelizes and builds the partitions it owns,
+the subtree sizes are all-gathered over NCCL and the shared upper levels are
+merged (weak scaling: per-GPU work fixed).
+
+`value` is triangles/s with inputs resident in HBM; `e2e` is the same metric
+through the C-ABI call svo_run() with HOST buffers (H2D + D2H inside the timed
+region).  The reference arm (--impl reference) times the unmodified reference
+CPU binary from oracle/_ref (1 thread: the reference is single threaded).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import shutil
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "voxelize+SVO build throughput"
+UNIT = "triangles/s"
+WORKLOAD = "svo_builder_binary -s 1024, synthetic 2M-triangle displaced sphere (BASELINE.json configs[1])"
+GRID = 1024
+SPHERE_N = 1000  # 1000 x 1000 quads -> 2,000,000 triangles
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+def make_mesh():
+    from ooc_svo_builder_b200 import meshgen
+    return meshgen.displaced_sphere(SPHERE_N, SPHERE_N, seed=1)
+
+
+# ----------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md recipe)
+# ----------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0: float, t1: float) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=3)
+        except Exception:
+            self.proc.kill()
+        sm, smmax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        allsm = []
+        for ts, line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                allsm.append(float(f[1]))
+                if t0 <= ts <= t1 + 0.2:
+                    sm.append(float(f[1])); smmax.append(float(f[2]))
+                    for i, n in enumerate(names):
+                        if f[5 + i].lower().startswith("active"):
+                            reasons.add(n)
+            except ValueError:
+                continue
+        if not sm:
+            sm = allsm
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(smmax) if smmax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------
+# reference arm / cpu baseline: the unmodified reference CLI on the host CPU
+# ----------------------------------------------------------------------------
+def run_reference_cpu(mesh, gridsize: int, steps: int, warmup: int):
+    """Returns (triangles/s, voxels/s, info). One step = one full run of the reference
+    CPU binary (partition + voxelize + build + its own file IO, page cache warm)."""
+    from oracle import oracle as O
+    from ooc_svo_builder_b200 import meshgen
+    d = tempfile.mkdtemp(prefix="svo_bench_ref_")
+    try:
+        hdr = meshgen.write_tri(os.path.join(d, "m"), mesh)
+        times, nvox = [], None
+        if O.ref_available():
+            kind = "reference"
+            exe = O.ref_exe(False)
+            t_begin = time.perf_counter()
+            for i in range(warmup + steps):
+                if times and time.perf_counter() - t_begin > 150.0:
+                    break                                   # bounded: the whole arm ends within a few minutes
+                t = time.perf_counter()
+                p = subprocess.run([exe, "-f", hdr, "-s", str(gridsize)], capture_output=True, text=True)
+                dt = time.perf_counter() - t
+                if i >= warmup:
+                    times.append(dt)
+                for line in p.stdout.splitlines():
+                    if line.startswith("Total amount of voxels:"):
+                        nvox = int(line.split(":")[1])
+        else:
+            kind = "port"
+            for i in range(warmup + steps):
+                t = time.perf_counter()
+                r = O.build(mesh.tris, mesh.length, gridsize)
+                dt = time.perf_counter() - t
+                nvox = r.n_voxels
+                if i >= warmup:
+                    times.append(dt)
+        best = min(times)
+        mean = sum(times) / len(times)
+        return mesh.n_triangles / mean, (nvox or 0) / mean, {
+            "kind": kind, "cores": 1, "host_cores": os.cpu_count(), "mean_s": mean, "best_s": best, "runs": len(times), "n_voxels": nvox,
+            "sample": "whole workload (%d triangles, -s %d), %d run(s) of the %s, wall clock incl. its file IO, page cache warm"
+                      % (mesh.n_triangles, gridsize, len(times), "unmodified reference CLI (oracle/_ref/svo_builder_binary)" if kind == "reference" else "C restatement (oracle/liboracle.so)")}
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    mesh = make_mesh()
+    tps, vps, info = run_reference_cpu(mesh, GRID, max(1, args.steps), max(0, min(args.warmup, 1)))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": tps, "unit": UNIT, "n_gpus": args.gpus, "steps": info["runs"],
+        "warmup": min(args.warmup, 1), "ms_per_step": info["mean_s"] * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "voxels_per_s": vps,
+        "config": {"workload": WORKLOAD, "gridsize": GRID, "n_triangles": mesh.n_triangles, "n_voxels": info["n_voxels"]},
+        "cpu_baseline": {"value": tps, "unit": UNIT, "cores": 1, "kind": info["kind"], "sample": info["sample"], "host_cores": info["host_cores"]},
+        "e2e": {"value": tps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------
+def ours(args):
+    import torch
+    from ooc_svo_builder_b200 import SvoBuilder, PinnedBuffer
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    peak, peak_src = load_peaks()
+
+    if world > 1:
+        from ooc_svo_builder_b200 import sharded
+        return sharded.bench(args, rank, world, local, dist, peak, peak_src, ClockSampler)
+
+    mesh = make_mesh()
+    T = mesh.n_triangles
+    sb = SvoBuilder(local)
+    stream = torch.cuda.Stream()
+    sb.set_stream(stream.cuda_stream)
+    prm = sb.make_params(mesh.length, GRID, False)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")     # > 126 MB L2
+
+    with torch.cuda.stream(stream):
+        d_tris = torch.from_numpy(mesh.tris).cuda()
+        torch.cuda.synchronize()
+        sb.set_triangles(d_tris)
+
+        def step():
+            sb.partition(prm)
+            sb.voxelize()
+            return sb.build()
+
+        for _ in range(max(args.warmup, 3)):
+            flush.zero_()
+            nv, nn, nd = step()
+        torch.cuda.synchronize()
+        sampler = ClockSampler(local)
+        sampler.start()
+        time.sleep(0.3)
+        t_wall0 = time.time()
+        evs, per_stage = [], []
+        for _ in range(args.steps):
+            flush.zero_()                                  # L2 flush between timed iterations (outside the event pair)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            nv, nn, nd = step()
+            e1.record(stream)
+            evs.append((e0, e1))
+            per_stage.append(sb.stats())
+        torch.cuda.synchronize()
+        t_wall1 = time.time()
+        step_ms = [a.elapsed_time(b) for a, b in evs]
+        clocks = sampler.stop(t_wall0, t_wall1)
+    total_ms = sum(step_ms)
+    ms_per_step = total_ms / len(step_ms)
+    value = T / (ms_per_step * 1e-3)
+
+    def avg(k):
+        return sum(s[k] for s in per_stage) / len(per_stage)
+
+    st = per_stage[-1]
+    launches = st["kernel_launches"]
+    # ---- roofline of the dominant kernel (CUDA events inside the library, on its launch stream) ----
+    n_leafrec = None
+    kern = {
+        "k_vox_small": {"ms": avg("ms_vox_small"), "bytes": T * 36 + 8 * 0},
+        "k_emit_leaf": {"ms": avg("ms_emit_leaf"), "bytes": 8 * nv + 24 * nn},
+    }
+    dom = max(kern, key=lambda k: kern[k]["ms"])
+    if dom == "k_emit_leaf":
+        alg_bytes = 8 * nv + 24 * nn
+        note = "octree build: 8*N voxels read + 24*N_nodes written (SURVEY.md §8d), divided by k_emit_leaf time"
+    else:
+        alg_bytes = T * 36 + (GRID ** 3) // 8 * 0 + 8 * nv
+        note = "voxelizer: T*36 B triangle records read + 8 B per occupied voxel of bit-grid traffic, divided by k_vox_small time"
+    achieved = alg_bytes / (kern[dom]["ms"] * 1e-3) / 1e9 if kern[dom]["ms"] > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src, "algorithmic_bytes": alg_bytes, "kernel_ms": kern[dom]["ms"], "note": note,
+                "octree_build": {"kernel": "k_emit_leaf", "ms": kern["k_emit_leaf"]["ms"], "algorithmic_bytes": 8 * nv + 24 * nn,
+                                 "achieved": (8 * nv + 24 * nn) / max(kern["k_emit_leaf"]["ms"], 1e-9) / 1e6,
+                                 "frac": (8 * nv + 24 * nn) / max(kern["k_emit_leaf"]["ms"], 1e-9) / 1e6 / peak}}
+
+    # ---- e2e: one C-ABI call with HOST (pinned) buffers ----
+    h_tris = PinnedBuffer(mesh.tris.nbytes)
+    h_tris.array[:] = mesh.tris.view(np.uint8).reshape(-1)
+    h_nodes = PinnedBuffer(nn * 24)
+    h_data = PinnedBuffer(nd * 32)
+    tris_view = h_tris.array.view(np.float32).reshape(T, 9)
+    e2e_times = []
+    for i in range(max(args.warmup, 3) + args.steps):
+        sb.synchronize()
+        t = time.perf_counter()
+        sb.run_host(prm, tris_view, h_nodes.array, h_data.array)
+        dt = time.perf_counter() - t
+        if i >= max(args.warmup, 3):
+            e2e_times.append(dt)
+    e2e_s = sum(e2e_times) / len(e2e_times)
+    e2e = {"value": T / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(mesh.tris.nbytes), "d2h_bytes_per_step": int(nn * 24 + nd * 32),
+           "ms_per_step": e2e_s * 1e3, "api": "svo_run (C ABI, pinned host buffers in/out, wall clock)"}
+
+    # ---- CPU baseline: the reference itself on this box's host cores (bounded: one run, ~10 s) ----
+    cpu_tps, cpu_vps, info = run_reference_cpu(mesh, GRID, 1, 0)
+    cpu_baseline = {"value": cpu_tps, "unit": UNIT, "cores": 1, "kind": info["kind"], "sample": info["sample"],
+                    "host_cores": info["host_cores"], "voxels_per_s": cpu_vps, "seconds": info["mean_s"]}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "voxels_per_s": nv / (ms_per_step * 1e-3),
+        "config": {"workload": WORKLOAD, "gridsize": GRID, "n_triangles": T, "n_voxels": nv, "n_nodes": nn, "partitions": st["n_partitions"],
+                   "l2": "flushed between timed iterations (256 MB write)", "parallelism": "1 GPU"},
+        "stage_ms": {k: avg(k) for k in ("ms_partition", "ms_voxelize", "ms_vox_small", "ms_compact", "ms_build", "ms_emit", "ms_emit_leaf", "ms_clear")},
+        "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
+        "gpu_launches": int(launches) * args.steps, "gpu_launches_per_step": int(launches),
+        "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+    sb.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,180 @@
+/* svo_b200.h -- C ABI of the B200-native voxelize-and-build path.
+ *
+ * Drop-in boundary for Forceflow/ooc_svo_builder's hot path. The reference has
+ * no plugin / FFI interface; its in-process seams are the four
+ * calls main() makes (src/svo_builder/main.cpp:298-389). Each entry point below
+ * replaces one of them and cites it. All reference paths are relative to
+ * /root/reference/.
+ *
+ * Conventions: extern "C", plain pointers and sizes, int status (0 = ok, see
+ * SVO_E_*), svo_last_error() for the message. The library owns device memory
+ * and streams; callers own every host buffer they pass. A context is bound to
+ * one CUDA device and is not thread-safe; use one context per device. There is
+ * NO CPU fallback: every compute entry point fails with SVO_E_CUDA when no
+ * sm_100 device is usable.
+ */
+#ifndef SVO_B200_H_
+#define SVO_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SVO_OK            0
+#define SVO_E_INVALID     1   /* bad argument / call order                         */
+#define SVO_E_CUDA        2   /* CUDA runtime error or no usable device            */
+#define SVO_E_NOMEM       3   /* device or host allocation failed                  */
+#define SVO_E_RANGE       4   /* destination buffer too small / range out of bounds*/
+
+/* main.cpp:23 `enum ColorType`, selected by `-c` (main.cpp:152-178). */
+#define SVO_COLOR_MODEL   0
+#define SVO_COLOR_FIXED   1
+#define SVO_COLOR_LINEAR  2
+#define SVO_COLOR_NORMAL  3
+
+#define SVO_NODE_BYTES    24  /* octree_io.h:62-66: u64 data, u64 children_base, i8 children_offset[8] */
+#define SVO_DATA_BYTES    32  /* VoxelData.h:10-17: u64 morton, f32 color[3], f32 normal[3]            */
+
+typedef struct svo_ctx svo_ctx;
+
+/* The program parameters of main.cpp:28-36 that reach the hot path. */
+typedef struct svo_params {
+    uint64_t gridsize;          /* -s, power of two >= 2                       (main.cpp:30)  */
+    uint64_t memory_limit_mb;   /* -l, decides the logical partition count     (main.cpp:31)  */
+    float    bbox_min0;         /* .tri header bbox.min[0]                     (tri_tools.h:109) */
+    float    bbox_max0;         /* .tri header bbox.max[0]; only the x extent is used (main.cpp:311) */
+    int32_t  payload;           /* 0 = svo_builder_binary (9 floats / triangle),
+                                   1 = svo_builder        (21 floats / triangle)  (tri_util.h:7-11) */
+    int32_t  generate_levels;   /* -levels                                     (main.cpp:35)  */
+    int32_t  color_mode;        /* -c, SVO_COLOR_*                             (main.cpp:33)  */
+    float    sparseness_limit;  /* -d as a fraction; accepted for CLI compatibility. It only
+                                   switches the reference between two routes that produce the
+                                   same files (voxelizer.cpp:176-186, main.cpp:355-368).       */
+} svo_params;
+
+/* Counters and device-side stage timings (CUDA events) of the last run. */
+typedef struct svo_stats {
+    uint64_t n_partitions;      /* logical partitions P = 8^k                                  */
+    uint64_t n_pairs;           /* sum of per-partition triangle counts                        */
+    uint64_t n_voxels;          /* "Total amount of voxels" (main.cpp:391)                     */
+    uint64_t n_nodes;           /* .octree n_nodes                                             */
+    uint64_t n_data;            /* .octree n_data                                              */
+    uint64_t n_small, n_medium, n_large; /* triangle/partition pairs per bbox work class       */
+    float ms_upload;            /* host -> device triangle copy                                */
+    float ms_partition;         /* binning pass                                                */
+    float ms_voxelize;          /* Schwarz-Seidel kernels (all classes) + payload owner pass   */
+    float ms_build;             /* pyramid compaction + subtree sizes + node/data emission     */
+    float ms_emit;              /* the node emission kernels alone (subset of ms_build)        */
+    float ms_clear;             /* sparse clear of the bit-grid pyramid for the next run       */
+    float ms_download;          /* device -> host copies issued by svo_fetch_*                 */
+    float ms_vox_small;         /* k_vox_small alone (subset of ms_voxelize)                   */
+    float ms_emit_leaf;         /* k_emit_leaf alone (subset of ms_emit)                       */
+    float ms_compact;           /* level counts + top-down tile-list expansion + subtree sizes */
+    uint32_t kernel_launches;   /* kernels launched by the last run                            */
+} svo_stats;
+
+/* ---- lifetime ------------------------------------------------------------ */
+
+/* Creates a context on CUDA device `device`. Fails (SVO_E_CUDA) if the device is
+ * missing or is not compute capability 10.x. */
+int  svo_ctx_create(int device, svo_ctx** out);
+void svo_ctx_destroy(svo_ctx* ctx);
+/* Makes ctx issue all its work on `cuda_stream` (a cudaStream_t of ctx's device,
+ * e.g. the caller's framework stream) instead of its own stream; NULL restores
+ * the context's own stream. The caller keeps the stream alive. */
+int  svo_ctx_set_stream(svo_ctx* ctx, void* cuda_stream);
+/* Message of the last failure on `ctx`; ctx may be NULL for svo_ctx_create failures. */
+const char* svo_last_error(const svo_ctx* ctx);
+const char* svo_version(void);
+
+/* ---- partitioner --------------------------------------------------------- */
+
+/* Replaces `size_t estimate_partitions(gridsize, memory_limit)`
+ * (src/svo_builder/partitioner.cpp:12-28). Pure host arithmetic. */
+uint64_t svo_estimate_partitions(uint64_t gridsize, uint64_t memory_limit_mb);
+
+/* Replaces the .trip text round trip main.cpp applies to the bbox before it
+ * computes the voxelizer's unit length (trip_tools.h:110-111 written, :78 read,
+ * main.cpp:304-311): formats like `ostream << float`, parses like `istream >> float`. */
+float svo_text_roundtrip_float(float v);
+
+/* Stages the triangle records. Replaces TriReader's 8192-triangle fread loop
+ * (src/libs/libtri/include/TriReader.h:41-79). `tris` is n_tris * (9 or 21)
+ * packed little-endian float32 (tri_util.h:29-55).
+ *   svo_set_triangles        : `tris` is HOST memory (pageable or pinned); copied to the device.
+ *   svo_set_triangles_device : `tris` is DEVICE memory on ctx's device; borrowed, not copied,
+ *                              and must stay valid until the next svo_set_triangles* call. */
+int svo_set_triangles(svo_ctx* ctx, const float* tris, uint64_t n_tris, int floats_per_tri);
+int svo_set_triangles_device(svo_ctx* ctx, const float* tris, uint64_t n_tris, int floats_per_tri);
+
+/* Replaces `TripInfo partition(tri_info, n_partitions, gridsize)`
+ * (partitioner.cpp:101-149, BBoxBuffer.h:70-84, intersection.h:50-53): bins every
+ * triangle into every logical partition whose world box its bbox touches
+ * (inclusive float test). Produces device index lists instead of .tripdata
+ * files. `part_tricounts` (may be NULL) receives n_partitions counts -- the
+ * values the reference writes to the .trip header (trip_tools.h:118-120). */
+int svo_partition(svo_ctx* ctx, const svo_params* params,
+                  uint64_t* n_partitions, uint64_t* part_tricounts, uint64_t tricounts_capacity);
+
+/* ---- voxelizer ----------------------------------------------------------- */
+
+/* Replaces the per-partition loop around `voxelize_schwarz_method(...)`
+ * (main.cpp:329-352, voxelizer.cpp:138-307) for ALL partitions: conservative
+ * Schwarz-Seidel triangle/box overlap into a Morton-ordered bit-grid. Requires
+ * svo_partition. n_voxels may be NULL (the count is final after svo_build). */
+int svo_voxelize(svo_ctx* ctx);
+
+/* ---- octree builder ------------------------------------------------------ */
+
+/* Replaces OctreeBuilder::addVoxel x N + finalizeTree (OctreeBuilder.cpp:34-168,
+ * main.cpp:354-389): builds the node array (and the payload data array) on the
+ * device in the reference's file order. Outputs the record counts that go into
+ * the .octree header (octree_io.h:74-83). */
+int svo_build(svo_ctx* ctx, uint64_t* n_voxels, uint64_t* n_nodes, uint64_t* n_data);
+
+/* Replaces writeNode / writeVoxelData (octree_io.h:49-66): copies records
+ * [first, first+count) of the .octreenodes / .octreedata image into caller
+ * memory (count * 24 resp. count * 32 bytes). Chunk the calls to stream the
+ * result within a host memory budget (-l). */
+int svo_fetch_nodes(svo_ctx* ctx, uint64_t first, uint64_t count, void* dst);
+int svo_fetch_data(svo_ctx* ctx, uint64_t first, uint64_t count, void* dst);
+
+/* Device-resident views of the same images (valid until the next svo_partition /
+ * svo_build on ctx) for callers that keep the octree on the GPU. */
+int svo_device_nodes(svo_ctx* ctx, const void** dev_ptr, uint64_t* n_nodes);
+int svo_device_data(svo_ctx* ctx, const void** dev_ptr, uint64_t* n_data);
+
+/* Ascending Morton codes of the filled voxels (the stream the reference feeds to
+ * addVoxel, main.cpp:355-368). dst holds `capacity` uint64; *n_written <= capacity. */
+int svo_fetch_voxel_codes(svo_ctx* ctx, uint64_t* dst, uint64_t capacity, uint64_t* n_written);
+
+/* ---- whole path ---------------------------------------------------------- */
+
+/* main.cpp:298-389 in one call: partition + voxelize + build from HOST triangle
+ * records, results copied into caller buffers when they are non-NULL
+ * (nodes_capacity / data_capacity in records; SVO_E_RANGE if too small -- the
+ * counts are still returned so the caller can retry with larger buffers via
+ * svo_fetch_*). */
+int svo_run(svo_ctx* ctx, const svo_params* params,
+            const float* host_tris, uint64_t n_tris,
+            void* nodes_dst, uint64_t nodes_capacity,
+            void* data_dst, uint64_t data_capacity,
+            svo_stats* stats);
+
+int svo_get_stats(svo_ctx* ctx, svo_stats* stats);
+
+/* Blocks until all work queued on ctx's stream has finished. */
+int svo_synchronize(svo_ctx* ctx);
+
+/* Pinned host memory helpers (cudaHostAlloc / cudaFreeHost) for callers that
+ * want svo_set_triangles / svo_fetch_* to run at full PCIe speed. */
+void* svo_host_alloc(size_t bytes);
+void  svo_host_free(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SVO_B200_H_ */

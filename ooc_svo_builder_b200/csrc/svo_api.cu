@@ -1,0 +1,703 @@
+// svo_api.cu -- C ABI (include/svo_b200.h) and host-side orchestration of the
+// sm_100a kernels in svo_kernels.cuh. No CPU fallback: every compute entry
+// point needs a compute-capability 10.x device.
+#include "../../include/svo_b200.h"
+#include "svo_kernels.cuh"
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace svo;
+typedef unsigned long long ull;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        size_t want = bytes + bytes / 8 + 256;      // a little slack so steady-state runs never reallocate
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { (void)cudaGetLastError(); e = cudaMalloc(&p, bytes); want = bytes; }
+        if (e == cudaSuccess) cap = want; else p = nullptr;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return static_cast<T*>(p); }
+};
+
+struct LevelBufs {
+    DevBuf key, mask, fc, ps, base;
+    ull n = 0;
+    Level view() const {
+        Level L;
+        L.key = key.as<ull>(); L.mask = mask.as<ull>(); L.fc = fc.as<ull>(); L.ps = ps.as<ull>(); L.base = base.as<ull>();
+        L.n = n;
+        return L;
+    }
+};
+
+enum { EV_UP0, EV_UP1, EV_PART0, EV_PART1, EV_VOX0, EV_VOX1, EV_BUILD0, EV_EMIT0, EV_EMIT1, EV_BUILD1, EV_VS0, EV_VS1, EV_EL0, EV_EL1, EV_CMP1, EV_CLR0, EV_CLR1, EV_DN0, EV_DN1, EV_COUNT };
+
+}  // namespace
+
+struct svo_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    cudaStream_t own_stream = nullptr;
+    std::string err;
+    cudaEvent_t ev[EV_COUNT];
+    bool ev_set[EV_COUNT];
+    ull* h_pinned = nullptr;          // 64 u64 of pinned scratch for small read-backs
+
+    // triangles
+    DevBuf tri_own;
+    const float* d_tris = nullptr;
+    uint64_t n_tris = 0;
+    int fpt = 0;
+    bool have_tris = false;
+
+    // job
+    svo_params prm;
+    bool partitioned = false, voxelized = false, built = false;
+    int D = 0, nl = 0, k = 0;
+    uint64_t P = 1;
+    uint32_t side = 0;
+    float unit_vox = 0, unit_div = 0;
+
+    // dense pyramid
+    DevBuf dense[MAX_LEVELS];
+    ull nwords[MAX_LEVELS];
+    uint64_t dense_grid = 0;          // gridsize the pyramid is allocated for
+    bool dense_clean = false;
+    DevBuf d_lvlptrs, d_nwords, d_counts;
+
+    // partition lists
+    DevBuf part_counts, part_cursor, part_off, pair_tri;
+    uint64_t n_pairs = 0;
+    std::vector<uint64_t> h_part_counts;
+
+    // work queues
+    DevBuf queue[2], qcount;
+
+    // compact levels
+    LevelBufs lv[MAX_LEVELS];
+    DevBuf scan_tmp;
+
+    // outputs
+    DevBuf nodes, data, owner, tileidx, codes;
+    uint64_t n_voxels = 0, n_nodes = 0, n_data = 0;
+
+    svo_stats stats;
+    uint32_t launches = 0;
+};
+
+namespace {
+
+int fail(svo_ctx* c, int code, const std::string& msg) {
+    if (c) c->err = msg; else g_create_error = msg;
+    return code;
+}
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            (void)cudaGetLastError();                                                              \
+            return fail(c, e_ == cudaErrorMemoryAllocation ? SVO_E_NOMEM : SVO_E_CUDA,             \
+                        std::string(#call) + ": " + cudaGetErrorString(e_));                       \
+        }                                                                                          \
+    } while (0)
+
+#define LAUNCHED()                                                                                 \
+    do {                                                                                           \
+        c->launches++;                                                                             \
+        CK(cudaGetLastError());                                                                    \
+    } while (0)
+
+inline unsigned blocks_for(ull n, unsigned per) { return (unsigned)((n + per - 1) / per); }
+
+void mark(svo_ctx* c, int e) {
+    cudaEventRecord(c->ev[e], c->stream);
+    c->ev_set[e] = true;
+}
+float span(svo_ctx* c, int a, int b) {
+    float ms = 0.f;
+    if (c->ev_set[a] && c->ev_set[b] && cudaEventElapsedTime(&ms, c->ev[a], c->ev[b]) == cudaSuccess) return ms;
+    (void)cudaGetLastError();
+    return 0.f;
+}
+
+template <class F>
+int exscan(svo_ctx* c, F f, ull n, ull* out) {
+    if (n == 0) {
+        CK(cudaMemsetAsync(out, 0, sizeof(ull), c->stream));
+        return SVO_OK;
+    }
+    const ull nt = (n + SCAN_TILE - 1) / SCAN_TILE;
+    CK(c->scan_tmp.ensure((nt + 1) * sizeof(ull)));
+    ull* tmp = c->scan_tmp.as<ull>();
+    k_scan_reduce<<<(unsigned)nt, SCAN_THREADS, 0, c->stream>>>(f, n, tmp); LAUNCHED();
+    k_scan_tiles<<<1, 1024, 0, c->stream>>>(tmp, nt); LAUNCHED();
+    k_scan_final<<<(unsigned)nt, SCAN_THREADS, 0, c->stream>>>(f, n, tmp, out); LAUNCHED();
+    return SVO_OK;
+}
+
+int ilog2u(uint64_t v) { int r = -1; while (v) { v >>= 1; r++; } return r; }
+
+// Allocates (and zeroes) the dense pyramid for gridsize g.
+int ensure_pyramid(svo_ctx* c) {
+    const uint64_t g = c->prm.gridsize;
+    if (c->dense_grid != g) {
+        size_t total = 0;
+        for (int j = 0; j < c->nl; j++) total += (size_t)c->nwords[j] * 8;
+        size_t free_b = 0, total_b = 0;
+        CK(cudaMemGetInfo(&free_b, &total_b));
+        size_t have = 0;
+        for (int j = 0; j < MAX_LEVELS; j++) have += c->dense[j].cap;
+        if (total > free_b + have) {
+            char m[256];
+            snprintf(m, sizeof m, "bit-grid pyramid for gridsize %llu needs %.1f GiB, device has %.1f GiB free",
+                     (ull)g, total / 1073741824.0, (free_b + have) / 1073741824.0);
+            return fail(c, SVO_E_NOMEM, m);
+        }
+        for (int j = 0; j < MAX_LEVELS; j++) c->dense[j].release();
+        for (int j = 0; j < c->nl; j++) CK(c->dense[j].ensure((size_t)c->nwords[j] * 8));
+        c->dense_grid = g;
+        c->dense_clean = false;
+        ull* ptrs[MAX_LEVELS] = { nullptr };
+        for (int j = 0; j < c->nl; j++) ptrs[j] = c->dense[j].as<ull>();
+        CK(c->d_lvlptrs.ensure(sizeof ptrs));
+        CK(c->d_nwords.ensure(sizeof c->nwords));
+        CK(c->d_counts.ensure(MAX_LEVELS * sizeof(ull)));
+        CK(cudaMemcpyAsync(c->d_lvlptrs.p, ptrs, sizeof ptrs, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(c->d_nwords.p, c->nwords, sizeof c->nwords, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaStreamSynchronize(c->stream));      // ptrs / nwords are stack / member memory
+    }
+    if (!c->dense_clean) {
+        for (int j = 0; j < c->nl; j++) CK(cudaMemsetAsync(c->dense[j].p, 0, (size_t)c->nwords[j] * 8, c->stream));
+        c->dense_clean = true;
+    }
+    return SVO_OK;
+}
+
+VoxJob make_voxjob(svo_ctx* c) {
+    VoxJob J;
+    memset(&J, 0, sizeof J);
+    J.tris = c->d_tris;
+    J.fpt = (uint32_t)c->fpt;
+    J.n_pairs = c->n_pairs;
+    J.pair_tri = c->P == 1 ? nullptr : c->pair_tri.as<uint32_t>();
+    J.part_off = c->P == 1 ? nullptr : c->part_off.as<uint64_t>();
+    J.P = (uint32_t)c->P;
+    J.k = (uint32_t)c->k;
+    J.side = c->side;
+    J.g = (uint32_t)c->prm.gridsize;
+    J.u = c->unit_vox;
+    J.unit_div = c->unit_div;
+    J.nl = c->nl;
+    for (int j = 0; j < c->nl; j++) J.lvl[j] = c->dense[j].as<ull>();
+    J.queue[0] = c->queue[0].as<ull>();
+    J.queue[1] = c->queue[1].as<ull>();
+    J.qcount = c->qcount.as<ull>();
+    J.small_max = 128;
+    J.medium_max = 32768;
+    if (const char* e = getenv("SVO_SMALL_MAX")) J.small_max = strtoull(e, nullptr, 10);
+    if (const char* e = getenv("SVO_MEDIUM_MAX")) J.medium_max = strtoull(e, nullptr, 10);
+    J.tileidx = c->tileidx.as<uint32_t>();
+    J.leafprefix = c->lv[0].fc.as<ull>();
+    J.owner = c->owner.as<uint32_t>();
+    return J;
+}
+
+template <bool OWNER>
+int launch_voxelizer(svo_ctx* c) {
+    if (c->n_pairs == 0) return SVO_OK;
+    VoxJob J = make_voxjob(c);
+    const size_t smem = J.pair_tri ? 0 : (size_t)VOX_BLOCK * c->fpt * sizeof(float);
+    if (!OWNER) mark(c, EV_VS0);
+    k_vox_small<OWNER><<<blocks_for(c->n_pairs, VOX_BLOCK), VOX_BLOCK, smem, c->stream>>>(J); LAUNCHED();
+    if (!OWNER) mark(c, EV_VS1);
+    const unsigned grid = (unsigned)c->sm_count * 4;
+    k_vox_medium<OWNER><<<grid, WARPS_PER_BLOCK * 32, 0, c->stream>>>(J); LAUNCHED();
+    k_vox_large<OWNER><<<grid, WARPS_PER_BLOCK * 32, 0, c->stream>>>(J); LAUNCHED();
+    return SVO_OK;
+}
+
+int validate_params(svo_ctx* c, const svo_params* p) {
+    if (!p) return fail(c, SVO_E_INVALID, "params is NULL");
+    const uint64_t g = p->gridsize;
+    if (g < 2 || (g & (g - 1)) != 0) return fail(c, SVO_E_INVALID, "gridsize must be a power of two >= 2");
+    if (g > (1ull << 20)) return fail(c, SVO_E_INVALID, "gridsize above 2^20 is not supported");
+    if (p->memory_limit_mb < 1) return fail(c, SVO_E_INVALID, "memory_limit_mb must be >= 1");
+    if (!(p->bbox_max0 > p->bbox_min0)) return fail(c, SVO_E_INVALID, "bbox_max0 must exceed bbox_min0");
+    if (p->color_mode < 0 || p->color_mode > 3) return fail(c, SVO_E_INVALID, "unknown color_mode");
+    if (p->generate_levels) return fail(c, SVO_E_INVALID, "-levels (generate_levels) is not implemented on the device path yet");
+    return SVO_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* svo_version(void) { return "ooc_svo_builder_b200 0.1 (reference ooc_svo_builder 1.6.4 byte layout)"; }
+
+const char* svo_last_error(const svo_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int svo_ctx_create(int device, svo_ctx** out) {
+    svo_ctx* c = nullptr;
+    if (!out) return fail(c, SVO_E_INVALID, "out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        (void)cudaGetLastError();
+        return fail(c, SVO_E_CUDA, std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                                       " (this library has no CPU fallback)");
+    }
+    if (device < 0 || device >= ndev) return fail(c, SVO_E_INVALID, "device index out of range");
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        char m[160];
+        snprintf(m, sizeof m, "device %d (%s) is sm_%d%d; this library is built for sm_100a only", device, prop.name, prop.major, prop.minor);
+        return fail(c, SVO_E_CUDA, m);
+    }
+    CK(cudaSetDevice(device));
+    svo_ctx* n = new svo_ctx();
+    n->device = device;
+    n->sm_count = prop.multiProcessorCount;
+    memset(&n->stats, 0, sizeof n->stats);
+    memset(&n->prm, 0, sizeof n->prm);
+    memset(n->nwords, 0, sizeof n->nwords);
+    for (int i = 0; i < EV_COUNT; i++) n->ev_set[i] = false;
+    c = n;
+    cudaError_t e2 = cudaStreamCreateWithFlags(&n->own_stream, cudaStreamNonBlocking);
+    n->stream = n->own_stream;
+    for (int i = 0; i < EV_COUNT && e2 == cudaSuccess; i++) e2 = cudaEventCreate(&n->ev[i]);
+    if (e2 == cudaSuccess) e2 = cudaHostAlloc((void**)&n->h_pinned, 64 * sizeof(ull), cudaHostAllocDefault);
+    if (e2 != cudaSuccess) {
+        std::string m = std::string("context setup: ") + cudaGetErrorString(e2);
+        delete n;
+        return fail(nullptr, SVO_E_CUDA, m);
+    }
+    *out = n;
+    return SVO_OK;
+}
+
+void svo_ctx_destroy(svo_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    c->tri_own.release();
+    for (int j = 0; j < MAX_LEVELS; j++) {
+        c->dense[j].release();
+        c->lv[j].key.release(); c->lv[j].mask.release(); c->lv[j].fc.release(); c->lv[j].ps.release(); c->lv[j].base.release();
+    }
+    c->d_lvlptrs.release(); c->d_nwords.release(); c->d_counts.release();
+    c->part_counts.release(); c->part_cursor.release(); c->part_off.release(); c->pair_tri.release();
+    c->queue[0].release(); c->queue[1].release(); c->qcount.release();
+    c->scan_tmp.release(); c->nodes.release(); c->data.release(); c->owner.release(); c->tileidx.release(); c->codes.release();
+    for (int i = 0; i < EV_COUNT; i++) cudaEventDestroy(c->ev[i]);
+    if (c->h_pinned) cudaFreeHost(c->h_pinned);
+    cudaStreamDestroy(c->own_stream);
+    delete c;
+}
+
+int svo_ctx_set_stream(svo_ctx* c, void* cuda_stream) {
+    if (!c) return SVO_E_INVALID;
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
+    return SVO_OK;
+}
+
+uint64_t svo_estimate_partitions(uint64_t gridsize, uint64_t memory_limit) {
+    // partitioner.cpp:12-28
+    uint64_t required = (gridsize * gridsize * gridsize) / 1024 / 1024;
+    if (required <= memory_limit) return 1;
+    uint64_t numpartitions = 1, required_partition = required;
+    while (required_partition > memory_limit) {
+        required_partition /= 8;
+        numpartitions *= 8;
+    }
+    return numpartitions;
+}
+
+float svo_text_roundtrip_float(float v) {
+    char buf[64];
+    snprintf(buf, sizeof buf, "%g", (double)v);
+    return strtof(buf, nullptr);
+}
+
+void* svo_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
+    return p;
+}
+void svo_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+int svo_synchronize(svo_ctx* c) {
+    if (!c) return SVO_E_INVALID;
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    return SVO_OK;
+}
+
+static int set_tris_common(svo_ctx* c, uint64_t n_tris, int fpt) {
+    if (fpt != 9 && fpt != 21) return fail(c, SVO_E_INVALID, "floats_per_tri must be 9 (binary) or 21 (payload)");
+    if (n_tris > 0xffffffffULL) return fail(c, SVO_E_INVALID, "more than 2^32-1 triangles");
+    c->n_tris = n_tris;
+    c->fpt = fpt;
+    c->have_tris = true;
+    c->partitioned = c->voxelized = c->built = false;
+    return SVO_OK;
+}
+
+int svo_set_triangles(svo_ctx* c, const float* tris, uint64_t n_tris, int fpt) {
+    if (!c) return SVO_E_INVALID;
+    if (n_tris && !tris) return fail(c, SVO_E_INVALID, "tris is NULL");
+    CK(cudaSetDevice(c->device));
+    int rc = set_tris_common(c, n_tris, fpt);
+    if (rc) return rc;
+    const size_t bytes = (size_t)n_tris * fpt * sizeof(float);
+    CK(c->tri_own.ensure(bytes ? bytes : 16));
+    for (int i = 0; i < EV_COUNT; i++) c->ev_set[i] = false;
+    mark(c, EV_UP0);
+    if (bytes) CK(cudaMemcpyAsync(c->tri_own.p, tris, bytes, cudaMemcpyHostToDevice, c->stream));
+    mark(c, EV_UP1);
+    c->d_tris = c->tri_own.as<float>();
+    return SVO_OK;
+}
+
+int svo_set_triangles_device(svo_ctx* c, const float* tris, uint64_t n_tris, int fpt) {
+    if (!c) return SVO_E_INVALID;
+    if (n_tris && !tris) return fail(c, SVO_E_INVALID, "tris is NULL");
+    if (((uintptr_t)tris & 15) != 0) return fail(c, SVO_E_INVALID, "device triangle pointer must be 16-byte aligned");
+    CK(cudaSetDevice(c->device));
+    int rc = set_tris_common(c, n_tris, fpt);
+    if (rc) return rc;
+    for (int i = 0; i < EV_COUNT; i++) c->ev_set[i] = false;
+    c->d_tris = tris;
+    return SVO_OK;
+}
+
+int svo_partition(svo_ctx* c, const svo_params* params, uint64_t* n_partitions, uint64_t* part_tricounts, uint64_t cap) {
+    if (!c) return SVO_E_INVALID;
+    int rc = validate_params(c, params);
+    if (rc) return rc;
+    if (!c->have_tris) return fail(c, SVO_E_INVALID, "svo_partition before svo_set_triangles");
+    if ((params->payload ? 21 : 9) != c->fpt) return fail(c, SVO_E_INVALID, "params.payload does not match floats_per_tri");
+    CK(cudaSetDevice(c->device));
+    c->prm = *params;
+    c->voxelized = c->built = false;
+    c->launches = 0;
+    const uint64_t g = params->gridsize;
+    c->D = ilog2u(g);
+    c->nl = (c->D + 1) / 2;
+    for (int j = 0; j < MAX_LEVELS; j++) {
+        const int sh = 3 * c->D - 6 * (j + 1);
+        c->nwords[j] = j < c->nl ? (sh >= 0 ? (1ULL << sh) : 1ULL) : 0ULL;
+    }
+    c->P = svo_estimate_partitions(g, params->memory_limit_mb);               // main.cpp:298
+    c->k = ilog2u(c->P) / 3;
+    if (c->k > 5) return fail(c, SVO_E_INVALID, "more than 8^5 logical partitions are not supported");
+    c->side = (uint32_t)(g >> c->k);
+    // main.cpp:304-311: the voxelizer's unit length comes from the bbox re-read from the .trip text header
+    const float rmin = svo_text_roundtrip_float(params->bbox_min0), rmax = svo_text_roundtrip_float(params->bbox_max0);
+    c->unit_vox = (rmax - rmin) / (float)g;
+    c->unit_div = 1.0f / c->unit_vox;                                          // voxelizer.cpp:164
+    c->h_part_counts.assign(c->P, 0);
+    mark(c, EV_PART0);
+    if (c->P == 1) {
+        // partition_one, partitioner.cpp:80-98: the single partition holds every triangle, untested
+        c->n_pairs = c->n_tris;
+        c->h_part_counts[0] = c->n_tris;
+    } else {
+        BinJob B;
+        memset(&B, 0, sizeof B);
+        B.tris = c->d_tris; B.fpt = (uint32_t)c->fpt; B.n_tris = c->n_tris; B.k = (uint32_t)c->k; B.P = (uint32_t)c->P;
+        const float unit_part = (params->bbox_max0 - params->bbox_min0) / (float)g;   // partitioner.cpp:45
+        for (uint32_t i = 0; i < (1u << c->k); i++) {
+            B.bmin[i] = (float)(uint32_t)(i * c->side) * unit_part;                    // :54-56
+            B.bmax[i] = (float)(uint32_t)((i + 1) * c->side - 1 + 1u) * unit_part;     // :57-59
+        }
+        CK(c->part_counts.ensure(c->P * sizeof(ull)));
+        CK(c->part_cursor.ensure(c->P * sizeof(ull)));
+        CK(c->part_off.ensure((c->P + 1) * sizeof(ull)));
+        CK(cudaMemsetAsync(c->part_counts.p, 0, c->P * sizeof(ull), c->stream));
+        CK(cudaMemsetAsync(c->part_cursor.p, 0, c->P * sizeof(ull), c->stream));
+        B.counts = c->part_counts.as<ull>(); B.cursor = c->part_cursor.as<ull>(); B.off = c->part_off.as<ull>();
+        if (c->n_tris) {
+            const size_t smem = c->P <= 4096 ? c->P * sizeof(unsigned) : 0;
+            k_bin<false><<<blocks_for(c->n_tris, 256), 256, smem, c->stream>>>(B); LAUNCHED();
+        }
+        CountOp op{ c->part_counts.as<ull>() };
+        rc = exscan(c, op, c->P, c->part_off.as<ull>());
+        if (rc) return rc;
+        std::vector<ull> off(c->P + 1);
+        CK(cudaMemcpyAsync(off.data(), c->part_off.p, (c->P + 1) * sizeof(ull), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        for (uint64_t i = 0; i < c->P; i++) c->h_part_counts[i] = off[i + 1] - off[i];
+        c->n_pairs = off[c->P];
+        CK(c->pair_tri.ensure((c->n_pairs ? c->n_pairs : 1) * sizeof(uint32_t)));
+        B.pair_tri = c->pair_tri.as<uint32_t>();
+        if (c->n_tris) { k_bin<true><<<blocks_for(c->n_tris, 256), 256, 0, c->stream>>>(B); LAUNCHED(); }
+    }
+    mark(c, EV_PART1);
+    c->partitioned = true;
+    if (n_partitions) *n_partitions = c->P;
+    if (part_tricounts) {
+        if (cap < c->P) return fail(c, SVO_E_RANGE, "part_tricounts capacity is smaller than the partition count");
+        for (uint64_t i = 0; i < c->P; i++) part_tricounts[i] = c->h_part_counts[i];
+    }
+    return SVO_OK;
+}
+
+int svo_voxelize(svo_ctx* c) {
+    if (!c) return SVO_E_INVALID;
+    if (!c->partitioned) return fail(c, SVO_E_INVALID, "svo_voxelize before svo_partition");
+    CK(cudaSetDevice(c->device));
+    int rc = ensure_pyramid(c);
+    if (rc) return rc;
+    CK(c->qcount.ensure(4 * sizeof(ull)));
+    CK(cudaMemsetAsync(c->qcount.p, 0, 4 * sizeof(ull), c->stream));
+    const size_t qbytes = (c->n_pairs ? c->n_pairs : 1) * sizeof(ull);
+    CK(c->queue[0].ensure(qbytes));
+    CK(c->queue[1].ensure(qbytes));
+    mark(c, EV_VOX0);
+    c->dense_clean = false;
+    rc = launch_voxelizer<false>(c);
+    if (rc) return rc;
+    mark(c, EV_VOX1);
+    c->voxelized = true;
+    c->built = false;
+    return SVO_OK;
+}
+
+int svo_build(svo_ctx* c, uint64_t* n_voxels, uint64_t* n_nodes, uint64_t* n_data) {
+    if (!c) return SVO_E_INVALID;
+    if (!c->voxelized) return fail(c, SVO_E_INVALID, "svo_build before svo_voxelize");
+    CK(cudaSetDevice(c->device));
+    const int nl = c->nl, top = nl - 1;
+    const bool payload = c->prm.payload != 0;
+    mark(c, EV_BUILD0);
+    // ---- sync #1: how many non-zero words does every level hold? ----
+    CK(cudaMemsetAsync(c->d_counts.p, 0, MAX_LEVELS * sizeof(ull), c->stream));
+    if (nl > 1) {
+        dim3 grid(64, (unsigned)(nl - 1));
+        k_level_counts<<<grid, 256, 0, c->stream>>>((ull* const*)c->d_lvlptrs.p, c->d_nwords.as<ull>(), nl, c->d_counts.as<ull>()); LAUNCHED();
+    }
+    CK(cudaMemcpyAsync(c->h_pinned, c->d_counts.p, MAX_LEVELS * sizeof(ull), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(c->h_pinned + 16, c->dense[top].p, sizeof(ull), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    const ull top_word = c->h_pinned[16];
+    for (int j = 0; j < nl; j++) c->lv[j].n = (j == top) ? (top_word ? 1 : 0) : c->h_pinned[j + 1];
+    for (int j = 0; j < nl; j++) {
+        const ull n = c->lv[j].n;
+        CK(c->lv[j].key.ensure((n + 1) * sizeof(ull)));
+        CK(c->lv[j].mask.ensure((n + 1) * sizeof(ull)));
+        CK(c->lv[j].fc.ensure((n + 2) * sizeof(ull)));
+        CK(c->lv[j].ps.ensure((n + 2) * sizeof(ull)));
+        CK(c->lv[j].base.ensure((n + 1) * sizeof(ull)));
+    }
+    if (payload) CK(c->tileidx.ensure((size_t)c->nwords[0] * sizeof(uint32_t)));
+    // ---- top-down: compact tile lists ----
+    CK(cudaMemsetAsync(c->lv[top].key.p, 0, sizeof(ull), c->stream));
+    CK(cudaMemsetAsync(c->lv[top].base.p, 0, sizeof(ull), c->stream));
+    CK(cudaMemcpyAsync(c->lv[top].mask.p, c->dense[top].p, sizeof(ull), cudaMemcpyDeviceToDevice, c->stream));
+    if (payload && nl == 1) CK(cudaMemsetAsync(c->tileidx.p, 0, sizeof(uint32_t), c->stream));
+    for (int j = top; j >= 0; j--) {
+        PopcOp op{ c->lv[j].mask.as<ull>() };
+        int rc = exscan(c, op, c->lv[j].n, c->lv[j].fc.as<ull>());
+        if (rc) return rc;
+        if (j > 0 && c->lv[j].n) {
+            k_expand<<<blocks_for(c->lv[j].n, WARPS_PER_BLOCK), WARPS_PER_BLOCK * 32, 0, c->stream>>>(
+                c->lv[j].view(), c->lv[j - 1].view(), c->dense[j - 1].as<ull>(), (payload && j == 1) ? c->tileidx.as<uint32_t>() : nullptr); LAUNCHED();
+        }
+    }
+    // ---- bottom-up: subtree sizes ----
+    for (int j = 0; j < nl; j++) {
+        SizeOp op{ c->lv[j].mask.as<ull>(), c->lv[j].fc.as<ull>(), j ? c->lv[j - 1].ps.as<ull>() : nullptr };
+        int rc = exscan(c, op, c->lv[j].n, c->lv[j].ps.as<ull>());
+        if (rc) return rc;
+    }
+    mark(c, EV_CMP1);
+    // ---- sync #2: record counts ----
+    CK(cudaMemcpyAsync(c->h_pinned + 32, c->lv[0].fc.as<ull>() + c->lv[0].n, sizeof(ull), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(c->h_pinned + 33, c->lv[top].ps.as<ull>() + c->lv[top].n, sizeof(ull), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->n_voxels = c->h_pinned[32];
+    const ull s_top = c->h_pinned[33];
+    const bool d_even = (c->D % 2) == 0;
+    c->n_nodes = c->n_voxels == 0 ? 1 : s_top + (d_even ? 1 : 0);
+    c->n_data = payload ? 1 + c->n_voxels : 2;          // OctreeBuilder.cpp:25-29
+    CK(c->nodes.ensure((size_t)c->n_nodes * SVO_NODE_BYTES));
+    CK(c->data.ensure((size_t)c->n_data * SVO_DATA_BYTES));
+    // ---- emit ----
+    mark(c, EV_EMIT0);
+    if (c->n_voxels == 0) {
+        // empty grid: finalizeTree pads everything and writes a null root (OctreeBuilder.cpp:36-42)
+        static const ull null_root[3] = { 0ULL, 0ULL, ~0ULL };
+        CK(cudaMemcpyAsync(c->nodes.p, null_root, sizeof null_root, cudaMemcpyHostToDevice, c->stream));
+    } else {
+        EmitJob E;
+        E.nodes = c->nodes.as<ull>();
+        E.leaf_data_mode = payload ? 1 : 0;
+        for (int j = top; j >= 1; j--) {
+            E.is_top = (j == top);
+            E.root_here = (j == top) && d_even;
+            k_emit_upper<<<blocks_for(c->lv[j].n, WARPS_PER_BLOCK), WARPS_PER_BLOCK * 32, 0, c->stream>>>(c->lv[j].view(), c->lv[j - 1].view(), E); LAUNCHED();
+        }
+        E.is_top = (top == 0);
+        E.root_here = (top == 0) && d_even;
+        mark(c, EV_EL0);
+        k_emit_leaf<<<blocks_for(c->lv[0].n, WARPS_PER_BLOCK), WARPS_PER_BLOCK * 32, 0, c->stream>>>(c->lv[0].view(), E); LAUNCHED();
+        mark(c, EV_EL1);
+    }
+    mark(c, EV_EMIT1);
+    // ---- data records ----
+    if (!payload) {
+        static const uint32_t white[16] = { 0, 0, 0, 0, 0, 0, 0, 0,                         // record 0: NULL
+                                            0, 0, 0x3f800000u, 0x3f800000u, 0x3f800000u, 0, 0, 0 };  // record 1: white voxel
+        CK(cudaMemcpyAsync(c->data.p, white, sizeof white, cudaMemcpyHostToDevice, c->stream));
+    } else {
+        CK(cudaMemsetAsync(c->data.p, 0, SVO_DATA_BYTES, c->stream));
+        if (c->n_voxels) {
+            CK(c->owner.ensure((size_t)c->n_voxels * sizeof(uint32_t)));
+            CK(cudaMemsetAsync(c->owner.p, 0xff, (size_t)c->n_voxels * sizeof(uint32_t), c->stream));
+            int rc = launch_voxelizer<true>(c);
+            if (rc) return rc;
+            PayloadJob Pj;
+            Pj.tris = c->d_tris; Pj.owner = c->owner.as<uint32_t>(); Pj.data = c->data.as<float>();
+            Pj.unit_div = c->unit_div; Pj.gridsize_f = (float)c->prm.gridsize; Pj.color_mode = c->prm.color_mode;
+            k_payload<<<blocks_for(c->lv[0].n, WARPS_PER_BLOCK), WARPS_PER_BLOCK * 32, 0, c->stream>>>(c->lv[0].view(), Pj); LAUNCHED();
+        }
+    }
+    mark(c, EV_BUILD1);
+    // ---- leave a clean pyramid behind: zero exactly the words that were set ----
+    mark(c, EV_CLR0);
+    for (int j = 0; j < nl; j++) {
+        if (c->lv[j].n) { k_sparse_clear<<<blocks_for(c->lv[j].n, 256), 256, 0, c->stream>>>(c->lv[j].key.as<ull>(), c->lv[j].n, c->dense[j].as<ull>()); LAUNCHED(); }
+    }
+    c->dense_clean = true;
+    mark(c, EV_CLR1);
+    // queue statistics
+    CK(cudaMemcpyAsync(c->h_pinned + 40, c->qcount.p, 2 * sizeof(ull), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->built = true;
+    c->stats.n_partitions = c->P; c->stats.n_pairs = c->n_pairs;
+    c->stats.n_voxels = c->n_voxels; c->stats.n_nodes = c->n_nodes; c->stats.n_data = c->n_data;
+    c->stats.n_medium = c->h_pinned[40]; c->stats.n_large = c->h_pinned[41];
+    c->stats.n_small = c->n_pairs - c->stats.n_medium - c->stats.n_large;
+    c->stats.ms_upload = span(c, EV_UP0, EV_UP1);
+    c->stats.ms_partition = span(c, EV_PART0, EV_PART1);
+    c->stats.ms_voxelize = span(c, EV_VOX0, EV_VOX1);
+    c->stats.ms_build = span(c, EV_BUILD0, EV_BUILD1);
+    c->stats.ms_emit = span(c, EV_EMIT0, EV_EMIT1);
+    c->stats.ms_clear = span(c, EV_CLR0, EV_CLR1);
+    c->stats.ms_download = 0.f;
+    c->stats.ms_vox_small = span(c, EV_VS0, EV_VS1);
+    c->stats.ms_emit_leaf = c->n_voxels ? span(c, EV_EL0, EV_EL1) : 0.f;
+    c->stats.ms_compact = span(c, EV_BUILD0, EV_CMP1);
+    c->stats.kernel_launches = c->launches;
+    if (n_voxels) *n_voxels = c->n_voxels;
+    if (n_nodes) *n_nodes = c->n_nodes;
+    if (n_data) *n_data = c->n_data;
+    return SVO_OK;
+}
+
+static int fetch_common(svo_ctx* c, const DevBuf& src, uint64_t total, uint64_t rec, uint64_t first, uint64_t count, void* dst) {
+    if (!c->built) return fail(c, SVO_E_INVALID, "fetch before svo_build");
+    if (first > total || count > total - first) return fail(c, SVO_E_RANGE, "record range out of bounds");
+    if (count && !dst) return fail(c, SVO_E_INVALID, "dst is NULL");
+    CK(cudaSetDevice(c->device));
+    mark(c, EV_DN0);
+    if (count) CK(cudaMemcpyAsync(dst, (const char*)src.p + first * rec, count * rec, cudaMemcpyDeviceToHost, c->stream));
+    mark(c, EV_DN1);
+    CK(cudaStreamSynchronize(c->stream));
+    c->stats.ms_download += span(c, EV_DN0, EV_DN1);
+    return SVO_OK;
+}
+
+int svo_fetch_nodes(svo_ctx* c, uint64_t first, uint64_t count, void* dst) {
+    if (!c) return SVO_E_INVALID;
+    return fetch_common(c, c->nodes, c->n_nodes, SVO_NODE_BYTES, first, count, dst);
+}
+int svo_fetch_data(svo_ctx* c, uint64_t first, uint64_t count, void* dst) {
+    if (!c) return SVO_E_INVALID;
+    return fetch_common(c, c->data, c->n_data, SVO_DATA_BYTES, first, count, dst);
+}
+
+int svo_device_nodes(svo_ctx* c, const void** p, uint64_t* n) {
+    if (!c) return SVO_E_INVALID;
+    if (!c->built) return fail(c, SVO_E_INVALID, "svo_device_nodes before svo_build");
+    if (p) *p = c->nodes.p;
+    if (n) *n = c->n_nodes;
+    return SVO_OK;
+}
+int svo_device_data(svo_ctx* c, const void** p, uint64_t* n) {
+    if (!c) return SVO_E_INVALID;
+    if (!c->built) return fail(c, SVO_E_INVALID, "svo_device_data before svo_build");
+    if (p) *p = c->data.p;
+    if (n) *n = c->n_data;
+    return SVO_OK;
+}
+
+int svo_fetch_voxel_codes(svo_ctx* c, uint64_t* dst, uint64_t capacity, uint64_t* n_written) {
+    if (!c) return SVO_E_INVALID;
+    if (!c->built) return fail(c, SVO_E_INVALID, "svo_fetch_voxel_codes before svo_build");
+    CK(cudaSetDevice(c->device));
+    const uint64_t n = c->n_voxels < capacity ? c->n_voxels : capacity;
+    if (n_written) *n_written = n;
+    if (n == 0) return SVO_OK;
+    if (!dst) return fail(c, SVO_E_INVALID, "dst is NULL");
+    CK(c->codes.ensure((size_t)n * sizeof(ull)));
+    k_voxel_codes<<<blocks_for(c->lv[0].n, WARPS_PER_BLOCK), WARPS_PER_BLOCK * 32, 0, c->stream>>>(c->lv[0].view(), c->codes.as<ull>(), n); LAUNCHED();
+    CK(cudaMemcpyAsync(dst, c->codes.p, (size_t)n * sizeof(ull), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return SVO_OK;
+}
+
+int svo_get_stats(svo_ctx* c, svo_stats* s) {
+    if (!c || !s) return SVO_E_INVALID;
+    *s = c->stats;
+    return SVO_OK;
+}
+
+int svo_run(svo_ctx* c, const svo_params* params, const float* host_tris, uint64_t n_tris,
+            void* nodes_dst, uint64_t nodes_cap, void* data_dst, uint64_t data_cap, svo_stats* stats) {
+    if (!c) return SVO_E_INVALID;
+    if (!params) return fail(c, SVO_E_INVALID, "params is NULL");
+    int rc = svo_set_triangles(c, host_tris, n_tris, params->payload ? 21 : 9);
+    if (rc) return rc;
+    rc = svo_partition(c, params, nullptr, nullptr, 0);
+    if (rc) return rc;
+    rc = svo_voxelize(c);
+    if (rc) return rc;
+    uint64_t nv, nn, nd;
+    rc = svo_build(c, &nv, &nn, &nd);
+    if (rc) return rc;
+    int short_rc = SVO_OK;
+    if (nodes_dst) {
+        if (nodes_cap < nn) short_rc = fail(c, SVO_E_RANGE, "nodes_dst too small");
+        else if ((rc = svo_fetch_nodes(c, 0, nn, nodes_dst))) return rc;
+    }
+    if (data_dst) {
+        if (data_cap < nd) short_rc = fail(c, SVO_E_RANGE, "data_dst too small");
+        else if ((rc = svo_fetch_data(c, 0, nd, data_dst))) return rc;
+    }
+    if (stats) *stats = c->stats;
+    return short_rc;
+}
+
+}  // extern "C"

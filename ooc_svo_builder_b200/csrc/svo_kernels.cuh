@@ -1,0 +1,735 @@
+// svo_kernels.cuh -- the sm_100a kernels of the voxelize-and-build path.
+//
+// Data layout in HBM:
+//   * triangles: the .tridata image as-is (AoS, 36 B or 84 B records)
+//   * bit-grid pyramid: level 0 is the Morton-ordered occupancy bit-grid, one
+//     64-bit word per 4x4x4 brick (= one octree node at depth D-2: its 8 bytes are
+//     the child masks of its depth D-1 children). Level j+1 has one bit per
+//     level-j word (non-zero), so a level-j word is the octree node at depth
+//     D-2(j+1) with two tree levels packed in it. The pyramid is kept dense; the
+//     voxelizer maintains the upper levels with the return value of its atomicOr.
+//   * compact tile lists per level (key, mask, child prefix, subtree-size prefix,
+//     file base), built top-down from the pyramid, so every pass after the
+//     voxelizer is O(occupied), never O(grid).
+#pragma once
+#include "svo_device.cuh"
+
+namespace svo {
+
+constexpr int MAX_LEVELS = 12;        // ceil(D/2), D <= 21 (libmorton's 21 bits per axis)
+constexpr int VOX_BLOCK = 128;        // threads per block of the small-bbox voxelizer
+constexpr int WARPS_PER_BLOCK = 8;
+
+struct VoxJob {
+    const float* tris;                // .tridata image
+    uint32_t fpt;                     // floats per triangle: 9 or 21
+    uint64_t n_pairs;                 // triangle/partition pairs
+    const uint32_t* pair_tri;         // per-partition index lists, concatenated; NULL = identity (P == 1)
+    const uint64_t* part_off;         // P+1 list offsets (NULL when P == 1)
+    uint32_t P, k;                    // logical partitions P = 8^k
+    uint32_t side;                    // partition side in voxels = g >> k
+    uint32_t g;
+    float u, unit_div;                // unit length, 1/u (voxelizer.cpp:164)
+    int nl;                           // pyramid levels
+    unsigned long long* lvl[MAX_LEVELS];
+    unsigned long long* queue[2];     // medium / large work queues: (part << 32 | tri)
+    unsigned long long* qcount;       // [0] medium, [1] large, [2] small (statistics)
+    unsigned long long small_max, medium_max;
+    // payload owner pass
+    const uint32_t* tileidx;          // dense: level-0 word -> compact tile index
+    const unsigned long long* leafprefix;  // exclusive popcount prefix over level-0 tiles
+    uint32_t* owner;                  // per leaf: min triangle index that covers it
+};
+
+// ---------------------------------------------------------------------------
+// hit sinks
+// ---------------------------------------------------------------------------
+// Binary pass: 64-bit atomicOr into the brick word; the thread that turns a word
+// from zero to non-zero propagates one bit to the level above, and so on.
+__device__ __forceinline__ void sink_fill(const VoxJob& J, uint64_t w, uint64_t mask) {
+    unsigned long long old = atomicOr(&J.lvl[0][w], (unsigned long long)mask);
+    int j = 0;
+    while (old == 0ULL && ++j < J.nl) {
+        const unsigned long long bit = 1ULL << (w & 63);
+        w >>= 6;
+        old = atomicOr(&J.lvl[j][w], bit);
+    }
+}
+// Payload owner pass: the reference's first-triangle-wins rule (voxelizer.cpp:263)
+// made order independent: owner = min triangle index over all triangles passing.
+__device__ __forceinline__ void sink_owner_bit(const VoxJob& J, uint64_t w, int bit, uint32_t tri) {
+    const unsigned long long W = J.lvl[0][w];
+    const unsigned long long r = J.leafprefix[J.tileidx[w]] + __popcll(W & lowmask(bit));
+    atomicMin(&J.owner[r], tri);
+}
+
+// ---------------------------------------------------------------------------
+// pair decoding
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t pair_partition(const VoxJob& J, uint64_t q) {
+    if (J.P == 1) return 0;
+    uint32_t lo = 0, hi = J.P;            // find last p with off[p] <= q
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (J.part_off[mid] <= q) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+__device__ __forceinline__ void partition_origin(const VoxJob& J, uint32_t part, int& px, int& py, int& pz) {
+    px = (int)(compact3(part) * J.side);          // voxelizer.cpp:149: decode(morton_start) -> (x, y, z)
+    py = (int)(compact3(part >> 1) * J.side);
+    pz = (int)(compact3(part >> 2) * J.side);
+}
+__device__ __forceinline__ void load_vertices(const VoxJob& J, uint32_t tri, float* v) {
+    const float* t = J.tris + (size_t)tri * J.fpt;
+#pragma unroll
+    for (int i = 0; i < 9; i++) v[i] = __ldg(t + i);
+}
+
+// Warp-aggregated queue push; must be called by all 32 lanes.
+__device__ __forceinline__ void warp_push(unsigned long long* counter, unsigned long long* q, bool pred, unsigned long long val) {
+    const unsigned m = __ballot_sync(0xffffffffu, pred);
+    if (m == 0) return;
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(m) - 1;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(counter, (unsigned long long)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (pred) q[base + __popc(m & ((1u << lane) - 1u))] = val;
+}
+
+// ---------------------------------------------------------------------------
+// Voxelizer, small bounding boxes: one thread per triangle/partition pair.
+// OWNER = false: fill the bit-grid and route bigger pairs to the queues.
+// OWNER = true : payload owner pass over the same pairs (queues already built).
+// Identity lists (P == 1) stage the block's triangle records through shared
+// memory with float4 loads; gathered lists read the vertices directly.
+// ---------------------------------------------------------------------------
+template <bool OWNER>
+__global__ void __launch_bounds__(VOX_BLOCK) k_vox_small(VoxJob J) {
+    extern __shared__ float4 s_stage4[];
+    float* s_stage = reinterpret_cast<float*>(s_stage4);
+    const uint64_t q0 = (uint64_t)blockIdx.x * VOX_BLOCK;
+    const uint64_t q = q0 + threadIdx.x;
+    const bool active = q < J.n_pairs;
+    float v[9];
+    uint32_t tri = 0, part = 0;
+    if (J.pair_tri == nullptr) {
+        // block-contiguous records [q0, q0 + VOX_BLOCK): VOX_BLOCK * fpt floats, 16-byte aligned
+        const uint64_t nrec = (J.n_pairs - q0 < VOX_BLOCK) ? (J.n_pairs - q0) : VOX_BLOCK;
+        const uint64_t nfl = nrec * J.fpt;
+        const float* src = J.tris + q0 * J.fpt;
+        const uint64_t n4 = nfl >> 2;
+        const float4* src4 = reinterpret_cast<const float4*>(src);
+        for (uint64_t i = threadIdx.x; i < n4; i += VOX_BLOCK) s_stage4[i] = __ldg(src4 + i);
+        for (uint64_t i = (n4 << 2) + threadIdx.x; i < nfl; i += VOX_BLOCK) s_stage[i] = __ldg(src + i);
+        __syncthreads();
+        tri = (uint32_t)q;
+        if (active) {
+#pragma unroll
+            for (int i = 0; i < 9; i++) v[i] = s_stage[threadIdx.x * J.fpt + i];
+        }
+    } else if (active) {
+        tri = J.pair_tri[q];
+        part = pair_partition(J, q);
+        load_vertices(J, tri, v);
+    }
+    int cls = -1;
+    GridBox b = { 0, -1, 0, -1, 0, -1 };
+    if (active) {
+        int px, py, pz;
+        partition_origin(J, part, px, py, pz);
+        b = clamped_box(v, J.unit_div, px, py, pz, (int)J.side);
+        const unsigned long long vol = (unsigned long long)(b.x1 - b.x0 + 1) * (unsigned long long)(b.y1 - b.y0 + 1) *
+                                       (unsigned long long)(b.z1 - b.z0 + 1);
+        cls = vol <= J.small_max ? 0 : (vol <= J.medium_max ? 1 : 2);
+    }
+    if (!OWNER) {
+        const unsigned long long e = ((unsigned long long)part << 32) | tri;
+        warp_push(&J.qcount[0], J.queue[0], cls == 1, e);
+        warp_push(&J.qcount[1], J.queue[1], cls == 2, e);
+    }
+    if (cls != 0) return;
+
+    TriSetup s;
+    tri_setup(v, J.u, s);
+    const float u = J.u;
+    // brick-major traversal: one atomic per touched brick
+    for (int bz = b.z0 >> 2; bz <= (b.z1 >> 2); bz++) {
+        const int za = max(b.z0, bz << 2), zb = min(b.z1, (bz << 2) + 3);
+        for (int by = b.y0 >> 2; by <= (b.y1 >> 2); by++) {
+            const int ya = max(b.y0, by << 2), yb = min(b.y1, (by << 2) + 3);
+            for (int bx = b.x0 >> 2; bx <= (b.x1 >> 2); bx++) {
+                const int xa = max(b.x0, bx << 2), xb = min(b.x1, (bx << 2) + 3);
+                unsigned long long mask = 0;
+                for (int x = xa; x <= xb; x++) {
+                    const float px = fmul((float)x, u);
+                    for (int y = ya; y <= yb; y++) {
+                        const float py = fmul((float)y, u);
+                        // the XY edge functions do not depend on z: test once per column
+                        if (!edge_pass(s, 0, px, py) || !edge_pass(s, 1, px, py) || !edge_pass(s, 2, px, py)) continue;
+                        for (int z = za; z <= zb; z++) {
+                            const float pz = fmul((float)z, u);
+                            if (!plane_pass(s, px, py, pz)) continue;
+                            if (!edge_pass(s, 3, py, pz) || !edge_pass(s, 4, py, pz) || !edge_pass(s, 5, py, pz)) continue;
+                            if (!edge_pass(s, 6, pz, px) || !edge_pass(s, 7, pz, px) || !edge_pass(s, 8, pz, px)) continue;
+                            mask |= 1ULL << brick_bit(x, y, z);
+                        }
+                    }
+                }
+                if (mask) {
+                    const uint64_t w = morton3((uint32_t)bx, (uint32_t)by, (uint32_t)bz);
+                    if (!OWNER) {
+                        sink_fill(J, w, mask);
+                    } else {
+                        while (mask) {
+                            const int bit = __ffsll((long long)mask) - 1;
+                            mask &= mask - 1;
+                            sink_owner_bit(J, w, bit, tri);
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Voxelizer, medium and large boxes: warps walk the bricks of the box. 32 bricks
+// are pruned at a time (one per lane, exact box test), the survivors are then
+// evaluated by the whole warp, 64 voxels = 2 per lane, ballots build the word.
+// Medium: one warp owns a pair. Large: all warps of the grid share each pair.
+// ---------------------------------------------------------------------------
+template <bool OWNER>
+__device__ __forceinline__ void warp_voxelize_box(const VoxJob& J, const TriSetup& s, const GridBox& b, uint32_t tri,
+                                                  unsigned long long chunk0, unsigned long long chunk_stride) {
+    const int lane = threadIdx.x & 31;
+    const int bx0 = b.x0 >> 2, by0 = b.y0 >> 2, bz0 = b.z0 >> 2;
+    const unsigned long long nbx = (unsigned long long)((b.x1 >> 2) - bx0 + 1);
+    const unsigned long long nby = (unsigned long long)((b.y1 >> 2) - by0 + 1);
+    const unsigned long long nbz = (unsigned long long)((b.z1 >> 2) - bz0 + 1);
+    const unsigned long long nb = nbx * nby * nbz;
+    const int dx = (lane & 1) | ((lane >> 2) & 2);          // lane = bit index of the voxel (z bit 1 clear)
+    const int dy = ((lane >> 1) & 1) | ((lane >> 3) & 2);
+    const int dz = (lane >> 2) & 1;
+    const float u = J.u;
+    for (unsigned long long c = chunk0; c * 32ULL < nb; c += chunk_stride) {
+        const unsigned long long bi = c * 32ULL + lane;
+        int bx = 0, by = 0, bz = 0;
+        bool may = false;
+        if (bi < nb) {
+            bx = bx0 + (int)(bi % nbx);
+            const unsigned long long r = bi / nbx;
+            by = by0 + (int)(r % nby);
+            bz = bz0 + (int)(r / nby);
+            may = box_may_pass(s, u, max(b.x0, bx << 2), min(b.x1, (bx << 2) + 3), max(b.y0, by << 2),
+                               min(b.y1, (by << 2) + 3), max(b.z0, bz << 2), min(b.z1, (bz << 2) + 3));
+        }
+        unsigned m = __ballot_sync(0xffffffffu, may);
+        while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            const int sbx = __shfl_sync(0xffffffffu, bx, src);
+            const int sby = __shfl_sync(0xffffffffu, by, src);
+            const int sbz = __shfl_sync(0xffffffffu, bz, src);
+            const int x = (sbx << 2) + dx, y = (sby << 2) + dy, z = (sbz << 2) + dz;
+            bool h0 = false, h1 = false;
+            if (x >= b.x0 && x <= b.x1 && y >= b.y0 && y <= b.y1) {
+                const float px = fmul((float)x, u), py = fmul((float)y, u);
+                if (edge_pass(s, 0, px, py) && edge_pass(s, 1, px, py) && edge_pass(s, 2, px, py)) {
+                    if (z >= b.z0 && z <= b.z1) {
+                        const float pz = fmul((float)z, u);
+                        h0 = plane_pass(s, px, py, pz) && edge_pass(s, 3, py, pz) && edge_pass(s, 4, py, pz) &&
+                             edge_pass(s, 5, py, pz) && edge_pass(s, 6, pz, px) && edge_pass(s, 7, pz, px) &&
+                             edge_pass(s, 8, pz, px);
+                    }
+                    if (z + 2 >= b.z0 && z + 2 <= b.z1) {
+                        const float pz = fmul((float)(z + 2), u);
+                        h1 = plane_pass(s, px, py, pz) && edge_pass(s, 3, py, pz) && edge_pass(s, 4, py, pz) &&
+                             edge_pass(s, 5, py, pz) && edge_pass(s, 6, pz, px) && edge_pass(s, 7, pz, px) &&
+                             edge_pass(s, 8, pz, px);
+                    }
+                }
+            }
+            const unsigned lo = __ballot_sync(0xffffffffu, h0);
+            const unsigned hi = __ballot_sync(0xffffffffu, h1);
+            if (lo | hi) {
+                const uint64_t w = morton3((uint32_t)sbx, (uint32_t)sby, (uint32_t)sbz);
+                if (!OWNER) {
+                    if (lane == 0) sink_fill(J, w, ((unsigned long long)hi << 32) | lo);
+                } else {
+                    if (h0) sink_owner_bit(J, w, lane, tri);
+                    if (h1) sink_owner_bit(J, w, lane + 32, tri);
+                }
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void queued_pair_setup(const VoxJob& J, unsigned long long e, uint32_t& tri, TriSetup& s, GridBox& b) {
+    tri = (uint32_t)(e & 0xffffffffULL);
+    const uint32_t part = (uint32_t)(e >> 32);
+    float v[9];
+    load_vertices(J, tri, v);
+    int px, py, pz;
+    partition_origin(J, part, px, py, pz);
+    b = clamped_box(v, J.unit_div, px, py, pz, (int)J.side);
+    tri_setup(v, J.u, s);
+}
+
+template <bool OWNER>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_vox_medium(VoxJob J) {
+    const unsigned long long n = J.qcount[0];
+    const unsigned long long nwarps = (unsigned long long)gridDim.x * WARPS_PER_BLOCK;
+    for (unsigned long long e = (unsigned long long)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5); e < n; e += nwarps) {
+        uint32_t tri; TriSetup s; GridBox b;
+        queued_pair_setup(J, J.queue[0][e], tri, s, b);
+        warp_voxelize_box<OWNER>(J, s, b, tri, 0ULL, 1ULL);
+    }
+}
+
+template <bool OWNER>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_vox_large(VoxJob J) {
+    const unsigned long long n = J.qcount[1];
+    const unsigned long long nwarps = (unsigned long long)gridDim.x * WARPS_PER_BLOCK;
+    const unsigned long long gw = (unsigned long long)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    for (unsigned long long e = 0; e < n; e++) {
+        uint32_t tri; TriSetup s; GridBox b;
+        queued_pair_setup(J, J.queue[1][e], tri, s, b);
+        warp_voxelize_box<OWNER>(J, s, b, tri, gw, nwarps);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Partitioner: bin triangles into the logical partitions whose world box their
+// bbox touches (partitioner.cpp:43-61, :117-126; BBoxBuffer.h:70-84;
+// intersection.h:50-53). The boxes are a product of per-axis slabs, so the
+// inclusive test separates per axis into a contiguous slab range.
+// ---------------------------------------------------------------------------
+struct BinJob {
+    const float* tris;
+    uint32_t fpt;
+    uint64_t n_tris;
+    uint32_t k, P;
+    float bmin[32], bmax[32];         // world slab [bmin[i], bmax[i]] of slab i (same on every axis)
+    unsigned long long* counts;       // P
+    unsigned long long* cursor;       // P (fill pass)
+    const unsigned long long* off;    // P+1 (fill pass)
+    uint32_t* pair_tri;
+};
+
+__device__ __forceinline__ void slab_range(const BinJob& B, float mn, float mx, int& lo, int& hi) {
+    // partition slab i is kept unless (mx < bmin[i]) or (mn > bmax[i])
+    const int n = 1 << B.k;
+    lo = n; hi = -1;
+    for (int i = 0; i < n; i++) {
+        if (!(mx < B.bmin[i]) && !(mn > B.bmax[i])) { if (i < lo) lo = i; hi = i; }
+    }
+}
+
+template <bool FILL>
+__global__ void __launch_bounds__(256) k_bin(BinJob B) {
+    extern __shared__ unsigned int s_hist[];
+    const bool use_smem = !FILL && B.P <= 4096;
+    if (use_smem) {
+        for (uint32_t i = threadIdx.x; i < B.P; i += blockDim.x) s_hist[i] = 0;
+        __syncthreads();
+    }
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int lx = 1, hx = 0, ly = 1, hy = 0, lz = 1, hz = 0;
+    if (t < B.n_tris) {
+        const float* v = B.tris + t * B.fpt;
+        float c[9];
+#pragma unroll
+        for (int i = 0; i < 9; i++) c[i] = __ldg(v + i);
+        slab_range(B, stdmin(c[0], stdmin(c[3], c[6])), stdmax(c[0], stdmax(c[3], c[6])), lx, hx);
+        slab_range(B, stdmin(c[1], stdmin(c[4], c[7])), stdmax(c[1], stdmax(c[4], c[7])), ly, hy);
+        slab_range(B, stdmin(c[2], stdmin(c[5], c[8])), stdmax(c[2], stdmax(c[5], c[8])), lz, hz);
+    }
+    const int nx = max(hx - lx + 1, 0), ny = max(hy - ly + 1, 0), nz = max(hz - lz + 1, 0);
+    const int mine = nx * ny * nz;
+    if (!FILL) {
+        for (int i = 0; i < mine; i++) {
+            const uint32_t part = (uint32_t)morton3(lx + i % nx, ly + (i / nx) % ny, lz + i / (nx * ny));
+            if (use_smem) atomicAdd(&s_hist[part], 1u); else atomicAdd(&B.counts[part], 1ULL);
+        }
+        if (use_smem) {
+            __syncthreads();
+            for (uint32_t i = threadIdx.x; i < B.P; i += blockDim.x)
+                if (s_hist[i]) atomicAdd(&B.counts[i], (unsigned long long)s_hist[i]);
+        }
+    } else {
+        // warp-uniform trip count so that the match/ballot aggregation is convergent
+        const int most = __reduce_max_sync(0xffffffffu, mine);
+        const int lane = threadIdx.x & 31;
+        for (int i = 0; i < most; i++) {
+            const bool valid = i < mine;
+            uint32_t part = 0xffffffffu;
+            if (valid) part = (uint32_t)morton3(lx + i % nx, ly + (i / nx) % ny, lz + i / (nx * ny));
+            const unsigned peers = __match_any_sync(0xffffffffu, part);
+            const int leader = __ffs(peers) - 1;
+            unsigned long long base = 0;
+            if (valid && lane == leader) base = atomicAdd(&B.cursor[part], (unsigned long long)__popc(peers));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (valid) B.pair_tri[B.off[part] + base + __popc(peers & ((1u << lane) - 1u))] = (uint32_t)t;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Hand-written exclusive scan (no CUB): reduce per tile -> scan tile sums in one
+// block -> rescan tiles with their offset. out has n + 1 entries (out[n] = total).
+// ---------------------------------------------------------------------------
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ unsigned long long warp_incl_scan(unsigned long long v) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned long long t = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= d) v += t;
+    }
+    return v;
+}
+// exclusive scan across the block; returns this thread's exclusive prefix, total via ref
+__device__ __forceinline__ unsigned long long block_excl_scan(unsigned long long v, unsigned long long& total) {
+    __shared__ unsigned long long s_w[32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    const unsigned long long inc = warp_incl_scan(v);
+    __syncthreads();                 // protect s_w across back-to-back calls
+    if (lane == 31) s_w[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        unsigned long long x = lane < nw ? s_w[lane] : 0ULL;
+        x = warp_incl_scan(x);
+        s_w[lane] = x;
+    }
+    __syncthreads();
+    total = s_w[nw - 1];
+    return inc - v + (wid ? s_w[wid - 1] : 0ULL);
+}
+
+template <class F>
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_reduce(F f, unsigned long long n, unsigned long long* tile_sums) {
+    const unsigned long long base = (unsigned long long)blockIdx.x * SCAN_TILE;
+    unsigned long long acc = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; i++) {
+        const unsigned long long idx = base + (unsigned long long)i * SCAN_THREADS + threadIdx.x;
+        if (idx < n) acc += f(idx);
+    }
+    unsigned long long total;
+    block_excl_scan(acc, total);
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+// single block: in-place exclusive scan of tile_sums[0..nt), total to tile_sums[nt]
+__global__ void __launch_bounds__(1024) k_scan_tiles(unsigned long long* tile_sums, unsigned long long nt) {
+    unsigned long long carry = 0;
+    for (unsigned long long b = 0; b < nt; b += blockDim.x) {
+        const unsigned long long idx = b + threadIdx.x;
+        const unsigned long long v = idx < nt ? tile_sums[idx] : 0ULL;
+        unsigned long long total;
+        const unsigned long long ex = block_excl_scan(v, total);
+        if (idx < nt) tile_sums[idx] = carry + ex;
+        carry += total;
+    }
+    if (threadIdx.x == 0) tile_sums[nt] = carry;
+}
+template <class F>
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_final(F f, unsigned long long n, const unsigned long long* tile_sums,
+                                                             unsigned long long* out) {
+    // blocked arrangement: thread t owns SCAN_ITEMS consecutive elements
+    const unsigned long long base = (unsigned long long)blockIdx.x * SCAN_TILE + (unsigned long long)threadIdx.x * SCAN_ITEMS;
+    unsigned long long v[SCAN_ITEMS];
+    unsigned long long acc = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; i++) {
+        v[i] = (base + i < n) ? f(base + i) : 0ULL;
+        acc += v[i];
+    }
+    unsigned long long total;
+    unsigned long long run = block_excl_scan(acc, total) + tile_sums[blockIdx.x];
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; i++) {
+        if (base + i < n) out[base + i] = run;
+        run += v[i];
+    }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) out[n] = tile_sums[gridDim.x];
+}
+
+// ---------------------------------------------------------------------------
+// Pyramid compaction + octree construction
+// ---------------------------------------------------------------------------
+struct Level {
+    unsigned long long* key;      // n      word index at this level (= Morton prefix of the node)
+    unsigned long long* mask;     // n      the 64-bit word
+    unsigned long long* fc;       // n + 1  exclusive prefix of popc(mask): index of first child tile / leaf rank
+    unsigned long long* ps;       // n + 1  exclusive prefix of subtree sizes S
+    unsigned long long* base;     // n      file position of the first record of the tile's subtree region
+    unsigned long long n;
+};
+
+// counts[j] (j >= 1) = number of set bits in dense level j = number of non-zero words of level j-1
+__global__ void __launch_bounds__(256) k_level_counts(unsigned long long* const* lvl, const unsigned long long* nwords, int nl,
+                                                      unsigned long long* counts) {
+    const int j = blockIdx.y + 1;
+    if (j >= nl) return;
+    const unsigned long long n = nwords[j];
+    unsigned long long acc = 0;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x)
+        acc += __popcll(lvl[j][i]);
+    unsigned long long total;
+    block_excl_scan(acc, total);
+    if (threadIdx.x == 0 && total) atomicAdd(&counts[j], total);
+}
+
+struct CountOp {
+    const unsigned long long* cnt;
+    __device__ unsigned long long operator()(unsigned long long i) const { return cnt[i]; }
+};
+struct PopcOp {
+    const unsigned long long* mask;
+    __device__ unsigned long long operator()(unsigned long long i) const { return (unsigned long long)__popcll(mask[i]); }
+};
+// subtree size of tile i: S = popc(W) + popc8(W) + sum of the children's S
+struct SizeOp {
+    const unsigned long long* mask;
+    const unsigned long long* fc;        // this level
+    const unsigned long long* child_ps;  // level below (NULL at level 0)
+    __device__ unsigned long long operator()(unsigned long long i) const {
+        const unsigned long long w = mask[i];
+        unsigned long long s = (unsigned long long)(__popcll(w) + __popc(nonzero_bytes(w)));
+        if (child_ps) s += child_ps[fc[i + 1]] - child_ps[fc[i]];
+        return s;
+    }
+};
+
+// Top-down expansion: one warp per parent tile writes its children's keys and
+// gathers their words from the dense level below.
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_expand(Level parent, Level child, const unsigned long long* dense_child,
+                                                                uint32_t* tileidx) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    if (i >= parent.n) return;
+    const int lane = threadIdx.x & 31;
+    const unsigned long long W = parent.mask[i], key = parent.key[i], fc = parent.fc[i];
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const int bit = lane + 32 * h;
+        if ((W >> bit) & 1ULL) {
+            const unsigned long long c = fc + __popcll(W & lowmask(bit));
+            const unsigned long long ck = (key << 6) | (unsigned long long)bit;
+            child.key[c] = ck;
+            child.mask[c] = dense_child[ck];
+            if (tileidx) tileidx[ck] = (uint32_t)c;
+        }
+    }
+}
+
+struct EmitJob {
+    unsigned long long* nodes;        // n_nodes * 3 u64
+    int is_top;                       // this level holds the single top word
+    int root_here;                    // D even: the top word IS the root -> write its record at S(top)
+    int leaf_data_mode;               // level 0: 0 = binary (data = 1), 1 = payload (data = 1 + leaf rank)
+};
+
+// Upper levels (tile = node at depth d with two packed levels): writes the
+// records of its grandchildren (tiles of the level below) and children, and the
+// file base of every grandchild subtree.
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_emit_upper(Level L, Level C, EmitJob E) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    if (i >= L.n) return;
+    const int lane = threadIdx.x & 31;
+    const unsigned long long W = L.mask[i], fc = L.fc[i], base = L.base[i];
+    const unsigned long long S = L.ps[i + 1] - L.ps[i];
+    const uint32_t nzb = nonzero_bytes(W);
+    const unsigned long long ps0 = C.ps[fc];
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const int bit = lane + 32 * h;
+        if ((W >> bit) & 1ULL) {
+            const int k = bit >> 3;
+            const unsigned long long c = fc + __popcll(W & lowmask(bit));
+            // subtree region of grandchild c
+            const unsigned long long gbase = base + (C.ps[c] - ps0) + __popcll(W & lowmask(8 * k));
+            C.base[c] = gbase;
+            // its record sits in the children block of byte k
+            const unsigned long long blk = base + (C.ps[fc + __popcll(W & lowmask(8 * (k + 1)))] - ps0) + __popcll(W & lowmask(8 * k));
+            const unsigned long long pos = blk + __popcll(W & lowmask(bit) & ~lowmask(8 * k));
+            const unsigned long long gw = C.mask[c];
+            const uint32_t gnz = nonzero_bytes(gw);
+            const unsigned long long gS = C.ps[c + 1] - C.ps[c];
+            unsigned long long* o = E.nodes + pos * 3;
+            o[0] = 0ULL;
+            o[1] = gbase + gS - __popc(gnz);
+            o[2] = child_offsets(gnz);
+        }
+    }
+    if (lane < 8 && ((nzb >> lane) & 1u)) {
+        const int k = lane;
+        const unsigned long long blk = base + (C.ps[fc + __popcll(W & lowmask(8 * (k + 1)))] - ps0) + __popcll(W & lowmask(8 * k));
+        const unsigned long long pos = base + S - __popc(nzb) + __popc(nzb & ((1u << k) - 1u));
+        unsigned long long* o = E.nodes + pos * 3;
+        o[0] = 0ULL;
+        o[1] = blk;
+        o[2] = child_offsets((uint32_t)((W >> (8 * k)) & 0xffULL));
+    }
+    if (E.root_here && lane == 8) {
+        unsigned long long* o = E.nodes + S * 3;
+        o[0] = 0ULL;
+        o[1] = base + S - __popc(nzb);
+        o[2] = child_offsets(nzb);
+    }
+}
+
+// Level 0 (bricks): the whole subtree region of a brick is contiguous in the file:
+// popc(W) leaf records followed by one record per non-zero byte. One warp streams
+// it out as consecutive 8-byte words (fully coalesced stores).
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_emit_leaf(Level L, EmitJob E) {
+    __shared__ unsigned long long s_off[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_off[i] = child_offsets((uint32_t)i);
+    __syncthreads();
+    const unsigned long long i = (unsigned long long)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    if (i >= L.n) return;
+    const int lane = threadIdx.x & 31;
+    const unsigned long long W = L.mask[i], base = L.base[i];
+    const uint32_t nzb = nonzero_bytes(W);
+    const int nleaf = __popcll(W), nch = __popc(nzb);
+    const unsigned long long leaf0 = E.leaf_data_mode ? (1ULL + L.fc[i]) : 1ULL;
+    unsigned long long* out = E.nodes + base * 3;
+    const int total = 3 * (nleaf + nch);
+    for (int q = lane; q < total; q += 32) {
+        const int r = q / 3, f = q - 3 * r;
+        unsigned long long val;
+        if (r < nleaf) {
+            val = f == 0 ? (E.leaf_data_mode ? leaf0 + r : 1ULL) : (f == 1 ? 0ULL : ~0ULL);
+        } else {
+            const int k = __fns(nzb, 0, r - nleaf + 1);
+            val = f == 0 ? 0ULL : (f == 1 ? base + __popcll(W & lowmask(8 * k)) : s_off[(W >> (8 * k)) & 0xffULL]);
+        }
+        out[q] = val;
+    }
+    if (E.root_here && lane == 0) {   // gridsize 4: the single brick is the root
+        unsigned long long* o = E.nodes + (unsigned long long)(nleaf + nch) * 3;
+        o[0] = 0ULL;
+        o[1] = base + nleaf;
+        o[2] = child_offsets(nzb);
+    }
+}
+
+// ascending Morton codes of the filled voxels
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_voxel_codes(Level L, unsigned long long* codes, unsigned long long capacity) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    if (i >= L.n) return;
+    const int lane = threadIdx.x & 31;
+    const unsigned long long W = L.mask[i], key = L.key[i], fc = L.fc[i];
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const int bit = lane + 32 * h;
+        if ((W >> bit) & 1ULL) {
+            const unsigned long long r = fc + __popcll(W & lowmask(bit));
+            if (r < capacity) codes[r] = (key << 6) | (unsigned long long)bit;
+        }
+    }
+}
+
+// zero exactly the words that were set, so the next run starts from a clean pyramid
+__global__ void __launch_bounds__(256) k_sparse_clear(const unsigned long long* key, unsigned long long n, unsigned long long* dense) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dense[key[i]] = 0ULL;
+}
+
+// ---------------------------------------------------------------------------
+// Payload: one data record per leaf, in leaf (= Morton) order
+// (voxelizer.cpp:293-299, BarycentricCoords.h:4-33, main.cpp:371-384).
+// ---------------------------------------------------------------------------
+struct PayloadJob {
+    const float* tris;        // 21-float records
+    const uint32_t* owner;    // per leaf
+    float* data;              // n_data * 8 floats (32-byte records)
+    float unit_div;
+    float gridsize_f;
+    int color_mode;
+};
+
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_payload(Level L, PayloadJob Pj) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    if (i >= L.n) return;
+    const int lane = threadIdx.x & 31;
+    const unsigned long long W = L.mask[i], key = L.key[i], fc = L.fc[i];
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const int bit = lane + 32 * h;
+        if (!((W >> bit) & 1ULL)) continue;
+        const unsigned long long r = fc + __popcll(W & lowmask(bit));
+        const unsigned long long m = (key << 6) | (unsigned long long)bit;
+        const uint32_t cx = compact3(m), cy = compact3(m >> 1), cz = compact3(m >> 2);
+        const float* t = Pj.tris + (size_t)Pj.owner[r] * 21;
+        float v[21];
+#pragma unroll
+        for (int q = 0; q < 21; q++) v[q] = __ldg(t + q);
+        // n = normalize(cross(e0, e1)) exactly as in the voxelizer (voxelizer.cpp:207-210)
+        const float e0x = fsub(v[3], v[0]), e0y = fsub(v[4], v[1]), e0z = fsub(v[5], v[2]);
+        const float e1x = fsub(v[6], v[3]), e1y = fsub(v[7], v[4]), e1z = fsub(v[8], v[5]);
+        const float crx = fsub(fmul(e0y, e1z), fmul(e1y, e0z));
+        const float cry = fsub(fmul(e0z, e1x), fmul(e1z, e0x));
+        const float crz = fsub(fmul(e0x, e1y), fmul(e1x, e0y));
+        const float inv = fdiv(1.0f, fsqrt(dot3(crx, cry, crz, crx, cry, crz)));
+        const float nx = fmul(crx, inv), ny = fmul(cry, inv), nz = fmul(crz, inv);
+        // ComputeBarycentricCoords(t, n, x / unit_div, y / unit_div, z / unit_div)
+        const float vx = fdiv((float)cx, Pj.unit_div), vy = fdiv((float)cy, Pj.unit_div), vz = fdiv((float)cz, Pj.unit_div);
+        const float coeffD = -dot3(v[0], v[1], v[2], nx, ny, nz);
+        const float kk = fdiv(fadd(dot3(vx, vy, vz, nx, ny, nz), coeffD), fadd(fadd(fmul(nx, nx), fmul(ny, ny)), fmul(nz, nz)));
+        const float ptx = fsub(vx, fmul(kk, nx)), pty = fsub(vy, fmul(kk, ny)), ptz = fsub(vz, fmul(kk, nz));
+        // inverse(mat3(v0, v1, v2)) * point, glm compute_inverse<3,3>; m[c][r] = v[3c + r]
+#define M_(c, r) v[3 * (c) + (r)]
+        const float ood = fdiv(1.0f,
+            fadd(fsub(fmul(M_(0, 0), fsub(fmul(M_(1, 1), M_(2, 2)), fmul(M_(2, 1), M_(1, 2)))),
+                      fmul(M_(1, 0), fsub(fmul(M_(0, 1), M_(2, 2)), fmul(M_(2, 1), M_(0, 2))))),
+                 fmul(M_(2, 0), fsub(fmul(M_(0, 1), M_(1, 2)), fmul(M_(1, 1), M_(0, 2))))));
+        const float i00 = fmul(fsub(fmul(M_(1, 1), M_(2, 2)), fmul(M_(2, 1), M_(1, 2))), ood);
+        const float i10 = fmul(-fsub(fmul(M_(1, 0), M_(2, 2)), fmul(M_(2, 0), M_(1, 2))), ood);
+        const float i20 = fmul(fsub(fmul(M_(1, 0), M_(2, 1)), fmul(M_(2, 0), M_(1, 1))), ood);
+        const float i01 = fmul(-fsub(fmul(M_(0, 1), M_(2, 2)), fmul(M_(2, 1), M_(0, 2))), ood);
+        const float i11 = fmul(fsub(fmul(M_(0, 0), M_(2, 2)), fmul(M_(2, 0), M_(0, 2))), ood);
+        const float i21 = fmul(-fsub(fmul(M_(0, 0), M_(2, 1)), fmul(M_(2, 0), M_(0, 1))), ood);
+        const float i02 = fmul(fsub(fmul(M_(0, 1), M_(1, 2)), fmul(M_(1, 1), M_(0, 2))), ood);
+        const float i12 = fmul(-fsub(fmul(M_(0, 0), M_(1, 2)), fmul(M_(1, 0), M_(0, 2))), ood);
+        const float i22 = fmul(fsub(fmul(M_(0, 0), M_(1, 1)), fmul(M_(1, 0), M_(0, 1))), ood);
+#undef M_
+        const float b0 = fadd(fadd(fmul(i00, ptx), fmul(i10, pty)), fmul(i20, ptz));
+        const float b1 = fadd(fadd(fmul(i01, ptx), fmul(i11, pty)), fmul(i21, ptz));
+        const float b2 = fadd(fadd(fmul(i02, ptx), fmul(i12, pty)), fmul(i22, ptz));
+        float col[3];
+#pragma unroll
+        for (int q = 0; q < 3; q++)   // InterpolateValue: b.x * c0 + b.y * c1 + b.z * c2
+            col[q] = fadd(fadd(fmul(b0, v[12 + q]), fmul(b1, v[15 + q])), fmul(b2, v[18 + q]));
+        const float fnx = v[9], fny = v[10], fnz = v[11];     // t.normal from the file (voxelizer.cpp:299)
+        if (Pj.color_mode == 1) {                             // fixed colour, main.cpp:373-374
+            col[0] = col[1] = col[2] = 1.0f;
+        } else if (Pj.color_mode == 2) {                      // mortonToRGB, svo_builder_util.h:14-18
+            col[0] = fdiv((float)cz, Pj.gridsize_f);
+            col[1] = fdiv((float)cy, Pj.gridsize_f);
+            col[2] = fdiv((float)cx, Pj.gridsize_f);
+        } else if (Pj.color_mode == 3) {                      // main.cpp:379-381
+            const float ninv = fdiv(1.0f, fsqrt(dot3(fnx, fny, fnz, fnx, fny, fnz)));
+            col[0] = fdiv(fadd(fmul(fnx, ninv), 1.0f), 2.0f);
+            col[1] = fdiv(fadd(fmul(fny, ninv), 1.0f), 2.0f);
+            col[2] = fdiv(fadd(fmul(fnz, ninv), 1.0f), 2.0f);
+        }
+        // x86 SSE produces the "default NaN" 0xFFC00000 for invalid operations (0*inf, inf-inf, 0/0:
+        // singular vertex matrix, zero normal) and propagates it; CUDA produces 0x7FFFFFFF.
+#pragma unroll
+        for (int q = 0; q < 3; q++) if (col[q] != col[q]) col[q] = __uint_as_float(0xFFC00000u);
+        float4* o = reinterpret_cast<float4*>(Pj.data + (1ULL + r) * 8ULL);
+        float4 a, b;
+        a.x = __uint_as_float((uint32_t)(m & 0xffffffffULL));
+        a.y = __uint_as_float((uint32_t)(m >> 32));
+        a.z = col[0]; a.w = col[1];
+        b.x = col[2]; b.y = fnx; b.z = fny; b.w = fnz;
+        o[0] = a; o[1] = b;
+    }
+}
+
+}  // namespace svo
