@@ -35,11 +35,12 @@ struct DevBuf {
 };
 
 struct LevelBufs {
-    DevBuf key, mask, fc, ps, base;
+    DevBuf key, mask, fc, ps, base, pi, pl, ibase, cache;
     ull n = 0;
     Level view() const {
         Level L;
         L.key = key.as<ull>(); L.mask = mask.as<ull>(); L.fc = fc.as<ull>(); L.ps = ps.as<ull>(); L.base = base.as<ull>();
+        L.pi = pi.as<ull>(); L.pl = pl.as<ull>(); L.ibase = ibase.as<ull>(); L.cache = cache.as<float>();
         L.n = n;
         return L;
     }
@@ -241,7 +242,6 @@ int validate_params(svo_ctx* c, const svo_params* p) {
     if (p->memory_limit_mb < 1) return fail(c, SVO_E_INVALID, "memory_limit_mb must be >= 1");
     if (!(p->bbox_max0 > p->bbox_min0)) return fail(c, SVO_E_INVALID, "bbox_max0 must exceed bbox_min0");
     if (p->color_mode < 0 || p->color_mode > 3) return fail(c, SVO_E_INVALID, "unknown color_mode");
-    if (p->generate_levels) return fail(c, SVO_E_INVALID, "-levels (generate_levels) is not implemented on the device path yet");
     return SVO_OK;
 }
 
@@ -302,6 +302,7 @@ void svo_ctx_destroy(svo_ctx* c) {
     for (int j = 0; j < MAX_LEVELS; j++) {
         c->dense[j].release();
         c->lv[j].key.release(); c->lv[j].mask.release(); c->lv[j].fc.release(); c->lv[j].ps.release(); c->lv[j].base.release();
+        c->lv[j].pi.release(); c->lv[j].pl.release(); c->lv[j].ibase.release(); c->lv[j].cache.release();
     }
     c->d_lvlptrs.release(); c->d_nwords.release(); c->d_counts.release();
     c->part_counts.release(); c->part_cursor.release(); c->part_off.release(); c->pair_tri.release();
@@ -490,6 +491,7 @@ int svo_build(svo_ctx* c, uint64_t* n_voxels, uint64_t* n_nodes, uint64_t* n_dat
     CK(cudaSetDevice(c->device));
     const int nl = c->nl, top = nl - 1;
     const bool payload = c->prm.payload != 0;
+    const bool levels = c->prm.generate_levels != 0;
     mark(c, EV_BUILD0);
     // ---- sync #1: how many non-zero words does every level hold? ----
     CK(cudaMemsetAsync(c->d_counts.p, 0, MAX_LEVELS * sizeof(ull), c->stream));
@@ -509,6 +511,12 @@ int svo_build(svo_ctx* c, uint64_t* n_voxels, uint64_t* n_nodes, uint64_t* n_dat
         CK(c->lv[j].fc.ensure((n + 2) * sizeof(ull)));
         CK(c->lv[j].ps.ensure((n + 2) * sizeof(ull)));
         CK(c->lv[j].base.ensure((n + 1) * sizeof(ull)));
+        if (levels) {
+            CK(c->lv[j].pi.ensure((n + 2) * sizeof(ull)));
+            CK(c->lv[j].pl.ensure((n + 2) * sizeof(ull)));
+            CK(c->lv[j].ibase.ensure((n + 1) * sizeof(ull)));
+            CK(c->lv[j].cache.ensure((n + 1) * 6 * sizeof(float)));
+        }
     }
     if (payload) CK(c->tileidx.ensure((size_t)c->nwords[0] * sizeof(uint32_t)));
     // ---- top-down: compact tile lists ----
@@ -530,6 +538,16 @@ int svo_build(svo_ctx* c, uint64_t* n_voxels, uint64_t* n_nodes, uint64_t* n_dat
         SizeOp op{ c->lv[j].mask.as<ull>(), c->lv[j].fc.as<ull>(), j ? c->lv[j - 1].ps.as<ull>() : nullptr };
         int rc = exscan(c, op, c->lv[j].n, c->lv[j].ps.as<ull>());
         if (rc) return rc;
+        if (levels) {
+            LeafCountOp lop{ c->lv[j].mask.as<ull>(), c->lv[j].fc.as<ull>(), j ? c->lv[j - 1].pl.as<ull>() : nullptr };
+            if ((rc = exscan(c, lop, c->lv[j].n, c->lv[j].pl.as<ull>()))) return rc;
+            InternalOp iop{ c->lv[j].mask.as<ull>(), c->lv[j].fc.as<ull>(), j ? c->lv[j - 1].pi.as<ull>() : nullptr };
+            if ((rc = exscan(c, iop, c->lv[j].n, c->lv[j].pi.as<ull>()))) return rc;
+        }
+    }
+    if (levels) {
+        CK(cudaMemsetAsync(c->lv[top].ibase.p, 0, sizeof(ull), c->stream));
+        CK(cudaMemcpyAsync(c->h_pinned + 34, c->lv[top].pi.as<ull>() + c->lv[top].n, sizeof(ull), cudaMemcpyDeviceToHost, c->stream));
     }
     mark(c, EV_CMP1);
     // ---- sync #2: record counts ----
@@ -541,6 +559,7 @@ int svo_build(svo_ctx* c, uint64_t* n_voxels, uint64_t* n_nodes, uint64_t* n_dat
     const bool d_even = (c->D % 2) == 0;
     c->n_nodes = c->n_voxels == 0 ? 1 : s_top + (d_even ? 1 : 0);
     c->n_data = payload ? 1 + c->n_voxels : 2;          // OctreeBuilder.cpp:25-29
+    if (levels && c->n_voxels) c->n_data += c->h_pinned[34] - (d_even ? 0 : 1);   // one record per internal node (the virtual top word is no node)
     CK(c->nodes.ensure((size_t)c->n_nodes * SVO_NODE_BYTES));
     CK(c->data.ensure((size_t)c->n_data * SVO_DATA_BYTES));
     // ---- emit ----
@@ -553,6 +572,8 @@ int svo_build(svo_ctx* c, uint64_t* n_voxels, uint64_t* n_nodes, uint64_t* n_dat
         EmitJob E;
         E.nodes = c->nodes.as<ull>();
         E.leaf_data_mode = payload ? 1 : 0;
+        E.levels = levels ? 1 : 0;
+        E.virtual_top = d_even ? 0 : 1;
         for (int j = top; j >= 1; j--) {
             E.is_top = (j == top);
             E.root_here = (j == top) && d_even;
@@ -561,7 +582,8 @@ int svo_build(svo_ctx* c, uint64_t* n_voxels, uint64_t* n_nodes, uint64_t* n_dat
         E.is_top = (top == 0);
         E.root_here = (top == 0) && d_even;
         mark(c, EV_EL0);
-        k_emit_leaf<<<blocks_for(c->lv[0].n, WARPS_PER_BLOCK), WARPS_PER_BLOCK * 32, 0, c->stream>>>(c->lv[0].view(), E); LAUNCHED();
+        if (levels) { k_emit_leaf_levels<<<blocks_for(c->lv[0].n, WARPS_PER_BLOCK), WARPS_PER_BLOCK * 32, 0, c->stream>>>(c->lv[0].view(), E); LAUNCHED(); }
+        else { k_emit_leaf<<<blocks_for(c->lv[0].n, WARPS_PER_BLOCK * EMIT_TILES_PER_WARP), WARPS_PER_BLOCK * 32, 0, c->stream>>>(c->lv[0].view(), E); LAUNCHED(); }
         mark(c, EV_EL1);
     }
     mark(c, EV_EMIT1);
@@ -580,7 +602,19 @@ int svo_build(svo_ctx* c, uint64_t* n_voxels, uint64_t* n_nodes, uint64_t* n_dat
             PayloadJob Pj;
             Pj.tris = c->d_tris; Pj.owner = c->owner.as<uint32_t>(); Pj.data = c->data.as<float>();
             Pj.unit_div = c->unit_div; Pj.gridsize_f = (float)c->prm.gridsize; Pj.color_mode = c->prm.color_mode;
+            Pj.levels = levels ? 1 : 0;
             k_payload<<<blocks_for(c->lv[0].n, WARPS_PER_BLOCK), WARPS_PER_BLOCK * 32, 0, c->stream>>>(c->lv[0].view(), Pj); LAUNCHED();
+        }
+    }
+    if (levels && c->n_voxels) {
+        // internal-node data records, bottom-up (needs the leaf records and the ibase values written above)
+        EmitJob E;
+        E.nodes = c->nodes.as<ull>(); E.leaf_data_mode = payload ? 1 : 0; E.levels = 1; E.virtual_top = d_even ? 0 : 1;
+        E.is_top = 0; E.root_here = 0;
+        for (int j = 0; j < nl; j++) {
+            const int real_node = !(j == top && !d_even);
+            k_levels_data<<<blocks_for(c->lv[j].n, 128), 128, 0, c->stream>>>(c->lv[j].view(), j ? c->lv[j - 1].view() : c->lv[j].view(), j, E,
+                                                                               c->data.as<float>(), real_node); LAUNCHED();
         }
     }
     mark(c, EV_BUILD1);

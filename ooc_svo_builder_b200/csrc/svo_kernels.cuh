@@ -468,6 +468,11 @@ struct Level {
     unsigned long long* fc;       // n + 1  exclusive prefix of popc(mask): index of first child tile / leaf rank
     unsigned long long* ps;       // n + 1  exclusive prefix of subtree sizes S
     unsigned long long* base;     // n      file position of the first record of the tile's subtree region
+    // -levels only:
+    unsigned long long* pi;       // n + 1  exclusive prefix of I = internal (non-leaf) nodes in the tile's subtree, itself included
+    unsigned long long* pl;       // n + 1  exclusive prefix of the leaf counts
+    unsigned long long* ibase;    // n      internal nodes completed (post-order) before the tile's subtree begins
+    float* cache;                 // n * 6  averaged colour + normal of the tile's node (Node::data_cache)
     unsigned long long n;
 };
 
@@ -506,6 +511,27 @@ struct SizeOp {
     }
 };
 
+// -levels: leaves / internal nodes below (and including) tile i
+struct LeafCountOp {
+    const unsigned long long* mask;
+    const unsigned long long* fc;
+    const unsigned long long* child_pl;  // NULL at level 0
+    __device__ unsigned long long operator()(unsigned long long i) const {
+        if (!child_pl) return (unsigned long long)__popcll(mask[i]);
+        return child_pl[fc[i + 1]] - child_pl[fc[i]];
+    }
+};
+struct InternalOp {
+    const unsigned long long* mask;
+    const unsigned long long* fc;
+    const unsigned long long* child_pi;  // NULL at level 0
+    __device__ unsigned long long operator()(unsigned long long i) const {
+        unsigned long long s = 1ULL + __popc(nonzero_bytes(mask[i]));
+        if (child_pi) s += child_pi[fc[i + 1]] - child_pi[fc[i]];
+        return s;
+    }
+};
+
 // Top-down expansion: one warp per parent tile writes its children's keys and
 // gathers their words from the dense level below.
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_expand(Level parent, Level child, const unsigned long long* dense_child,
@@ -532,7 +558,16 @@ struct EmitJob {
     int is_top;                       // this level holds the single top word
     int root_here;                    // D even: the top word IS the root -> write its record at S(top)
     int leaf_data_mode;               // level 0: 0 = binary (data = 1), 1 = payload (data = 1 + leaf rank)
+    int levels;                       // -levels: internal nodes carry a data index too
+    int virtual_top;                  // D odd: the top word is not a node (its byte 0 is the root)
 };
+
+// -levels: data index of an internal node = records written before it. Payload mode interleaves the
+// leaf records (written at addVoxel) with the internal ones (written in post-order by groupNodes):
+// 1 + leaves up to the end of its subtree + its post-order rank. Binary mode has no leaf records: 2 + rank.
+__device__ __forceinline__ unsigned long long internal_data_index(const EmitJob& E, unsigned long long leaves_through, unsigned long long rank) {
+    return (E.leaf_data_mode ? 1ULL + leaves_through : 2ULL) + rank;
+}
 
 // Upper levels (tile = node at depth d with two packed levels): writes the
 // records of its grandchildren (tiles of the level below) and children, and the
@@ -560,62 +595,190 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_emit_upper(Level L, Le
             const unsigned long long gw = C.mask[c];
             const uint32_t gnz = nonzero_bytes(gw);
             const unsigned long long gS = C.ps[c + 1] - C.ps[c];
+            unsigned long long gdata = 0ULL;
+            if (E.levels) {
+                const unsigned long long gib = L.ibase[i] + (C.pi[c] - C.pi[fc]) + __popc(nzb & ((1u << k) - 1u));
+                C.ibase[c] = gib;
+                gdata = internal_data_index(E, C.pl[c + 1], gib + (C.pi[c + 1] - C.pi[c]) - 1ULL);
+            }
             unsigned long long* o = E.nodes + pos * 3;
-            o[0] = 0ULL;
+            o[0] = gdata;
             o[1] = gbase + gS - __popc(gnz);
             o[2] = child_offsets(gnz);
         }
     }
     if (lane < 8 && ((nzb >> lane) & 1u)) {
         const int k = lane;
-        const unsigned long long blk = base + (C.ps[fc + __popcll(W & lowmask(8 * (k + 1)))] - ps0) + __popcll(W & lowmask(8 * k));
+        const unsigned long long cend = fc + __popcll(W & lowmask(8 * (k + 1)));
+        const unsigned long long blk = base + (C.ps[cend] - ps0) + __popcll(W & lowmask(8 * k));
         const unsigned long long pos = base + S - __popc(nzb) + __popc(nzb & ((1u << k) - 1u));
+        unsigned long long cdata = 0ULL;
+        if (E.levels) cdata = internal_data_index(E, C.pl[cend], L.ibase[i] + (C.pi[cend] - C.pi[fc]) + __popc(nzb & ((1u << k) - 1u)));
         unsigned long long* o = E.nodes + pos * 3;
-        o[0] = 0ULL;
+        o[0] = cdata;
         o[1] = blk;
         o[2] = child_offsets((uint32_t)((W >> (8 * k)) & 0xffULL));
     }
     if (E.root_here && lane == 8) {
         unsigned long long* o = E.nodes + S * 3;
-        o[0] = 0ULL;
+        o[0] = E.levels ? internal_data_index(E, L.pl[i + 1], L.ibase[i] + (L.pi[i + 1] - L.pi[i]) - 1ULL) : 0ULL;
         o[1] = base + S - __popc(nzb);
         o[2] = child_offsets(nzb);
     }
 }
 
 // Level 0 (bricks): the whole subtree region of a brick is contiguous in the file:
-// popc(W) leaf records followed by one record per non-zero byte. One warp streams
-// it out as consecutive 8-byte words (fully coalesced stores).
+// popc(W) leaf records followed by one record per non-zero byte. A warp takes 32
+// consecutive bricks (one coalesced load of their words and bases), then streams
+// each brick's region out as consecutive 8-byte words: the leaf part is a
+// period-3 pattern, so a store instruction covers 256 contiguous bytes; the
+// child records are written by lanes 0..7.
+constexpr int EMIT_TILES_PER_WARP = 32;
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_emit_leaf(Level L, EmitJob E) {
     __shared__ unsigned long long s_off[256];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) s_off[i] = child_offsets((uint32_t)i);
     __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const unsigned long long t0 = ((unsigned long long)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5)) * EMIT_TILES_PER_WARP;
+    if (t0 >= L.n) return;
+    const int cnt = (int)min((unsigned long long)EMIT_TILES_PER_WARP, L.n - t0);
+    unsigned long long myW = 0, myBase = 0, myFc = 0;
+    if (lane < cnt) {
+        myW = L.mask[t0 + lane];
+        myBase = L.base[t0 + lane];
+        if (E.leaf_data_mode) myFc = L.fc[t0 + lane];
+    }
+    const int f = lane % 3;                        // field of word q = lane + 32 * it: (lane + 2 * it) % 3
+    for (int t = 0; t < cnt; t++) {
+        const unsigned long long W = __shfl_sync(0xffffffffu, myW, t);
+        const unsigned long long base = __shfl_sync(0xffffffffu, myBase, t);
+        const uint32_t nzb = nonzero_bytes(W);
+        const int nleaf = __popcll(W);
+        unsigned long long* out = E.nodes + base * 3;
+        const int total = 3 * nleaf;
+        if (!E.leaf_data_mode) {
+            int ff = f;
+            for (int q = lane; q < total; q += 32) {
+                out[q] = ff == 0 ? 1ULL : (ff == 1 ? 0ULL : ~0ULL);
+                ff += 2; if (ff >= 3) ff -= 3;       // (q + 32) % 3 == (q % 3 + 2) % 3
+            }
+        } else {
+            const unsigned long long leaf0 = 1ULL + __shfl_sync(0xffffffffu, myFc, t);   // data index = 1 + leaf rank
+            int ff = f;
+            for (int q = lane; q < total; q += 32) {
+                out[q] = ff == 0 ? leaf0 + (unsigned)(q / 3) : (ff == 1 ? 0ULL : ~0ULL);
+                ff += 2; if (ff >= 3) ff -= 3;
+            }
+        }
+        if (lane < 8 && ((nzb >> lane) & 1u)) {
+            unsigned long long* o = out + 3 * (nleaf + __popc(nzb & ((1u << lane) - 1u)));
+            o[0] = 0ULL;
+            o[1] = base + __popcll(W & lowmask(8 * lane));
+            o[2] = s_off[(W >> (8 * lane)) & 0xffULL];
+        }
+        if (E.root_here && lane == 8) {   // gridsize 4: the single brick is the root
+            unsigned long long* o = out + 3 * (nleaf + __popc(nzb));
+            o[0] = 0ULL;
+            o[1] = base + nleaf;
+            o[2] = child_offsets(nzb);
+        }
+    }
+}
+
+// -levels variant of the brick emitter (one warp per brick, lanes = voxels): leaf data indices
+// are shifted by the internal records written before them, children carry a data index.
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_emit_leaf_levels(Level L, EmitJob E) {
     const unsigned long long i = (unsigned long long)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
     if (i >= L.n) return;
     const int lane = threadIdx.x & 31;
-    const unsigned long long W = L.mask[i], base = L.base[i];
+    const unsigned long long W = L.mask[i], base = L.base[i], ib = L.ibase[i], lp = L.fc[i];
     const uint32_t nzb = nonzero_bytes(W);
-    const int nleaf = __popcll(W), nch = __popc(nzb);
-    const unsigned long long leaf0 = E.leaf_data_mode ? (1ULL + L.fc[i]) : 1ULL;
-    unsigned long long* out = E.nodes + base * 3;
-    const int total = 3 * (nleaf + nch);
-    for (int q = lane; q < total; q += 32) {
-        const int r = q / 3, f = q - 3 * r;
-        unsigned long long val;
-        if (r < nleaf) {
-            val = f == 0 ? (E.leaf_data_mode ? leaf0 + r : 1ULL) : (f == 1 ? 0ULL : ~0ULL);
-        } else {
-            const int k = __fns(nzb, 0, r - nleaf + 1);
-            val = f == 0 ? 0ULL : (f == 1 ? base + __popcll(W & lowmask(8 * k)) : s_off[(W >> (8 * k)) & 0xffULL]);
+    const int nleaf = __popcll(W);
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const int bit = lane + 32 * h;
+        if ((W >> bit) & 1ULL) {
+            const int r = __popcll(W & lowmask(bit));
+            unsigned long long* o = E.nodes + (base + r) * 3;
+            o[0] = E.leaf_data_mode ? 1ULL + lp + r + ib + __popc(nzb & ((1u << (bit >> 3)) - 1u)) : 1ULL;
+            o[1] = 0ULL;
+            o[2] = ~0ULL;
         }
-        out[q] = val;
     }
-    if (E.root_here && lane == 0) {   // gridsize 4: the single brick is the root
-        unsigned long long* o = E.nodes + (unsigned long long)(nleaf + nch) * 3;
-        o[0] = 0ULL;
+    if (lane < 8 && ((nzb >> lane) & 1u)) {
+        const int k = lane;
+        unsigned long long* o = E.nodes + (base + nleaf + __popc(nzb & ((1u << k) - 1u))) * 3;
+        o[0] = internal_data_index(E, lp + __popcll(W & lowmask(8 * (k + 1))), ib + __popc(nzb & ((1u << k) - 1u)));
+        o[1] = base + __popcll(W & lowmask(8 * k));
+        o[2] = child_offsets((uint32_t)((W >> (8 * k)) & 0xffULL));
+    }
+    if (E.root_here && lane == 8) {   // gridsize 4
+        unsigned long long* o = E.nodes + (base + nleaf + __popc(nzb)) * 3;
+        o[0] = internal_data_index(E, lp + nleaf, ib + __popc(nzb));
         o[1] = base + nleaf;
         o[2] = child_offsets(nzb);
     }
+}
+
+// -levels data records, bottom-up (OctreeBuilder.cpp:82-99): a parent's colour is the sum of its
+// children's cached colours in slot order divided by the number of non-null children, its normal the
+// normalised mean normal. One thread per tile: the 8 byte-children first, then the tile's own node.
+__device__ __forceinline__ float canon_nan(float x) { return (x != x) ? __uint_as_float(0xFFC00000u) : x; }   // x86 default NaN
+__device__ __forceinline__ void finish_average(const float* sum, float notnull, float* out) {
+    out[0] = fdiv(sum[0], notnull); out[1] = fdiv(sum[1], notnull); out[2] = fdiv(sum[2], notnull);
+    const float tx = fdiv(sum[3], notnull), ty = fdiv(sum[4], notnull), tz = fdiv(sum[5], notnull);
+    const float inv = fdiv(1.0f, fsqrt(dot3(tx, ty, tz, tx, ty, tz)));
+    out[3] = fmul(tx, inv); out[4] = fmul(ty, inv); out[5] = fmul(tz, inv);
+}
+__device__ __forceinline__ void write_data_record(float* data, unsigned long long idx, const float* c) {
+    float4* o = reinterpret_cast<float4*>(data + idx * 8ULL);
+    o[0] = make_float4(0.0f, 0.0f, canon_nan(c[0]), canon_nan(c[1]));              // morton 0
+    o[1] = make_float4(canon_nan(c[2]), canon_nan(c[3]), canon_nan(c[4]), canon_nan(c[5]));
+}
+__global__ void __launch_bounds__(128) k_levels_data(Level L, Level C, int level, EmitJob E, float* data, int real_node) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= L.n) return;
+    const unsigned long long W = L.mask[i], fc = L.fc[i], ib = L.ibase[i];
+    const uint32_t nzb = nonzero_bytes(W);
+    float wsum[6] = { 0.f, 0.f, 0.f, 0.f, 0.f, 0.f };
+    float wn = 0.0f;
+    for (int k = 0; k < 8; k++) {
+        const uint32_t byte = (uint32_t)((W >> (8 * k)) & 0xffULL);
+        if (!byte) continue;
+        float csum[6] = { 0.f, 0.f, 0.f, 0.f, 0.f, 0.f };
+        float cn = 0.0f;
+        const unsigned long long before = __popcll(W & lowmask(8 * k));
+        const int krank = __popc(nzb & ((1u << k) - 1u));
+        for (int b = 0; b < 8; b++) {
+            if (!((byte >> b) & 1u)) continue;
+            const unsigned long long c = fc + before + __popc(byte & ((1u << b) - 1u));   // child tile index / leaf rank
+            cn = fadd(cn, 1.0f);
+            if (level == 0) {
+                if (E.leaf_data_mode) {     // payload leaves cache their data record (OctreeBuilder.cpp:160)
+                    const float* rec = data + (1ULL + c + ib + krank) * 8ULL;
+#pragma unroll
+                    for (int q = 0; q < 6; q++) csum[q] = fadd(csum[q], rec[2 + q]);
+                }                           // binary leaves cache zeros (OctreeBuilder.cpp:137-141)
+            } else {
+#pragma unroll
+                for (int q = 0; q < 6; q++) csum[q] = fadd(csum[q], C.cache[c * 6 + q]);
+            }
+        }
+        float cc[6];
+        finish_average(csum, cn, cc);
+        const unsigned long long cend = fc + __popcll(W & lowmask(8 * (k + 1)));
+        const unsigned long long leaves_through = level == 0 ? cend : C.pl[cend];
+        const unsigned long long rank = ib + (level == 0 ? 0ULL : C.pi[cend] - C.pi[fc]) + krank;
+        write_data_record(data, internal_data_index(E, leaves_through, rank), cc);
+        wn = fadd(wn, 1.0f);
+#pragma unroll
+        for (int q = 0; q < 6; q++) wsum[q] = fadd(wsum[q], cc[q]);
+    }
+    float wc[6];
+    finish_average(wsum, wn, wc);
+#pragma unroll
+    for (int q = 0; q < 6; q++) L.cache[i * 6 + q] = wc[q];
+    if (real_node) write_data_record(data, internal_data_index(E, L.pl[i + 1], ib + (L.pi[i + 1] - L.pi[i]) - 1ULL), wc);
 }
 
 // ascending Morton codes of the filled voxels
@@ -651,6 +814,7 @@ struct PayloadJob {
     float unit_div;
     float gridsize_f;
     int color_mode;
+    int levels;               // -levels: leaf records are interleaved with internal ones
 };
 
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_payload(Level L, PayloadJob Pj) {
@@ -722,7 +886,9 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_payload(Level L, Paylo
         // singular vertex matrix, zero normal) and propagates it; CUDA produces 0x7FFFFFFF.
 #pragma unroll
         for (int q = 0; q < 3; q++) if (col[q] != col[q]) col[q] = __uint_as_float(0xFFC00000u);
-        float4* o = reinterpret_cast<float4*>(Pj.data + (1ULL + r) * 8ULL);
+        unsigned long long didx = 1ULL + r;
+        if (Pj.levels) didx += L.ibase[i] + __popc(nonzero_bytes(W) & ((1u << (bit >> 3)) - 1u));
+        float4* o = reinterpret_cast<float4*>(Pj.data + didx * 8ULL);
         float4 a, b;
         a.x = __uint_as_float((uint32_t)(m & 0xffffffffULL));
         a.y = __uint_as_float((uint32_t)(m >> 32));

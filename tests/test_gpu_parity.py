@@ -5,9 +5,14 @@ bytes, same file bytes); payload mode bit-exact index structure and -- because
 the kernels replicate the reference's float operation order without FMA --
 bit-exact floats too (tolerance 0 ulp, asserted on the raw bytes).
 """
+import hashlib
+import json
+import os
+
 import numpy as np
 import pytest
 
+from cases import CASES
 from ooc_svo_builder_b200 import meshgen as mg
 
 pytestmark = pytest.mark.gpu
@@ -32,42 +37,37 @@ def _check(builder, oracle, mesh, gridsize, memory_limit_mb=2048, color="model",
     return got
 
 
-def test_c1_icosphere_256(builder, oracle):
+GOLDEN = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden.json")))
+
+
+@pytest.mark.parametrize("name,factory,g,kw", CASES, ids=[c[0] for c in CASES])
+def test_case_vs_oracle_and_golden(builder, oracle, name, factory, g, kw):
+    mesh = factory()
+    got = _check(builder, oracle, mesh, g, memory_limit_mb=kw.get("memory_limit_mb", 2048),
+                 color=kw.get("color", "model"), levels=kw.get("levels", False))
+    gold = GOLDEN[name]
+    if hashlib.sha256(mesh.tris.tobytes()).hexdigest() == gold["mesh_sha256"]:
+        # digests of the UNMODIFIED reference's output files (tests/golden/make_golden.py)
+        assert got.header.decode() == gold["header"]
+        assert hashlib.sha256(got.nodes.tobytes()).hexdigest() == gold["nodes_sha256"]
+        assert hashlib.sha256(got.data.tobytes()).hexdigest() == gold["data_sha256"]
+        assert got.n_voxels == gold["n_voxels"]
+
+
+def test_known_answers(builder, oracle):
     got = _check(builder, oracle, mg.icosphere(6), 256)
-    assert got.n_voxels == 308581 and got.n_nodes == 411166      # SURVEY.md §8c known answer
-
-
-def test_icosphere_8_partitions(builder, oracle):
-    _check(builder, oracle, mg.icosphere(6), 256, memory_limit_mb=3)
-
-
-@pytest.mark.parametrize("g", [2, 4, 8, 16, 32, 64, 128, 512])
-def test_gridsizes(builder, oracle, g):
-    _check(builder, oracle, mg.icosphere(3), g)
-
-
-def test_f5_partition_plane(builder, oracle):
-    m = mg.single_triangle_on_partition_plane()
+    assert got.n_voxels == 308581 and got.n_nodes == 411166
+    m = mg.single_triangle_on_partition_plane()                   # SURVEY.md F5
     assert _check(builder, oracle, m, 256).n_voxels == 378
     assert _check(builder, oracle, m, 256, memory_limit_mb=3).n_voxels == 756
 
 
-@pytest.mark.parametrize("limit", [2048, 2, 1])
-def test_axis_aligned_box(builder, oracle, limit):
-    _check(builder, oracle, mg.axis_aligned_box(), 128, memory_limit_mb=max(limit, 2) if limit != 1 else 2)
-    _check(builder, oracle, mg.axis_aligned_box(2.0, 0.5, 1.5), 256, memory_limit_mb=3)
-
-
-def test_degenerate(builder, oracle):
-    _check(builder, oracle, mg.degenerate_mix(), 64)
-    _check(builder, oracle, mg.degenerate_mix(), 256, memory_limit_mb=2)
-
-
-def test_empty(builder, oracle):
-    for g in (2, 4, 64, 128):
-        got = _check(builder, oracle, mg.empty_mesh(), g)
-        assert got.n_nodes == 1
-    _check(builder, oracle, mg.empty_mesh(payload=True), 64)
+@pytest.mark.parametrize("g", [2, 4, 8, 16, 64, 128])
+def test_gridsizes_payload_levels(builder, oracle, g):
+    m = mg.icosphere(2)
+    _check(builder, oracle, mg.Mesh(mg.with_payload(m.tris), m.length), g, levels=True)
+    _check(builder, oracle, m, g, levels=True)
+    _check(builder, oracle, mg.empty_mesh(payload=True), g, levels=True)
 
 
 @pytest.mark.parametrize("seed", [0, 1, 2])
@@ -77,32 +77,30 @@ def test_random_soup_all_classes(builder, oracle, seed):
     assert got.stats["n_medium"] > 0 and got.stats["n_large"] > 0
 
 
-def test_random_soup_64_partitions(builder, oracle):
-    _check(builder, oracle, mg.random_soup(1500, seed=11), 512, memory_limit_mb=2)
+def test_huge_triangles(builder, oracle):
+    # two triangles spanning the whole cube diagonal + a quad on a face: exercises the large class and the exact box pruning
+    L = 1.9
+    t = np.array([[0, 0, 0, L, L, 0.3, 0.2, L, L], [L, 0, 0.1, 0, L, 0.7, L, L, L],
+                  [0, 0, L, L, 0, L, L, L, L], [0.05, 0, 0.05, L, 0.02, L, 0.01, L, 0.5]], dtype=np.float32)
+    _check(builder, oracle, mg.Mesh(t, L), 256)
+    _check(builder, oracle, mg.Mesh(t, L), 512, memory_limit_mb=2)
 
 
-def test_displaced_sphere(builder, oracle):
-    _check(builder, oracle, mg.displaced_sphere(200, 200, seed=1), 512)
-
-
-def test_payload_icosphere(builder, oracle):
-    m = mg.icosphere(5)
-    _check(builder, oracle, mg.Mesh(mg.with_payload(m.tris), m.length), 128)
-
-
-def test_payload_partitions(builder, oracle):
-    m = mg.icosphere(5)
-    _check(builder, oracle, mg.Mesh(mg.with_payload(m.tris), m.length), 256, memory_limit_mb=3)
-
-
-@pytest.mark.parametrize("color", ["fixed", "linear", "normal"])
-def test_payload_color_modes(builder, oracle, color):
-    _check(builder, oracle, mg.terrain(60, seed=2), 128, color=color)
-
-
-def test_payload_soup(builder, oracle):
-    _check(builder, oracle, mg.random_soup(1500, seed=4, payload=True), 128, memory_limit_mb=2)
-    _check(builder, oracle, mg.terrain(120, seed=2), 256, memory_limit_mb=3)
+def test_c2_full_size_bit_exact(builder, oracle):
+    """BASELINE.json configs[1] at full size: svo_builder_binary -s 1024 on the 2 M-triangle displaced
+    sphere, bit-exact .octree / .octreenodes / .octreedata against the CPU oracle."""
+    mesh = mg.displaced_sphere(1000, 1000, seed=1)
+    got = builder.run(mesh.tris, mesh.length, 1024)
+    want = oracle.build(mesh.tris, mesh.length, 1024)
+    assert got.header == want.header and got.n_voxels == want.n_voxels
+    assert hashlib.sha256(got.nodes.tobytes()).digest() == hashlib.sha256(want.nodes).digest()
+    assert got.data.tobytes() == want.data
+    # size-independent invariants (SURVEY.md §4)
+    n = np.frombuffer(got.nodes.tobytes(), dtype=np.uint64).reshape(-1, 3)
+    leaf = n[:, 2] == np.uint64(0xFFFFFFFFFFFFFFFF)
+    assert leaf.sum() == got.n_voxels and (n[leaf, 0] == 1).all() and (n[leaf, 1] == 0).all()
+    codes = builder.voxel_codes()
+    assert codes.size == got.n_voxels and (np.diff(codes.astype(np.int64)) > 0).all()
 
 
 def test_voxel_codes_match_oracle(builder, oracle):
