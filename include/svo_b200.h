@@ -151,6 +151,33 @@ int svo_device_data(svo_ctx* ctx, const void** dev_ptr, uint64_t* n_data);
  * addVoxel, main.cpp:355-368). dst holds `capacity` uint64; *n_written <= capacity. */
 int svo_fetch_voxel_codes(svo_ctx* ctx, uint64_t* dst, uint64_t capacity, uint64_t* n_written);
 
+/* ---- multi-GPU: partitions sharded across contexts -------------------------
+ *
+ * One context per GPU (one process per GPU, or several contexts in one process).
+ * Rank r of `world` owns a contiguous Morton range of the grid's 8^dc chunks
+ * (dc >= log8 P), i.e. whole logical partitions when P >= world. It voxelizes and
+ * builds only the subtrees of its range; the only exchange is a small table with
+ * one 4 x u64 entry {mask, subtree size, leaves, internal nodes} per top-of-shard
+ * subtree, which the CALLER sums across ranks (NCCL all-reduce over NVLink; the
+ * entries of different ranks are disjoint). Every rank then merges the shared
+ * upper levels itself and emits its own contiguous range of the output files.
+ *
+ *   svo_shard_configure(rank, world)  before svo_partition
+ *   svo_partition, svo_voxelize       as on one GPU (every rank sees all triangles)
+ *   svo_shard_table_size              u64 count of the table
+ *   svo_shard_count(dev_table)        local build phase; zeroes the table, writes own entries
+ *   <all-reduce(sum) dev_table>       the caller's collective
+ *   svo_shard_emit(dev_table, ...)    merged upper levels + emission; returns GLOBAL counts
+ *   svo_shard_ranges                  [node_lo, node_hi) / [data_lo, data_hi): the records this
+ *                                     context holds; svo_fetch_* take global record positions
+ *                                     inside these ranges. The ranges of all ranks tile the files.
+ * -levels is not supported on the sharded path yet (SVO_E_INVALID). */
+int svo_shard_configure(svo_ctx* ctx, int rank, int world);
+int svo_shard_table_size(svo_ctx* ctx, uint64_t* n_u64);
+int svo_shard_count(svo_ctx* ctx, uint64_t* dev_table);
+int svo_shard_emit(svo_ctx* ctx, const uint64_t* dev_table, uint64_t* n_voxels, uint64_t* n_nodes, uint64_t* n_data);
+int svo_shard_ranges(svo_ctx* ctx, uint64_t* node_lo, uint64_t* node_hi, uint64_t* data_lo, uint64_t* data_hi);
+
 /* ---- whole path ---------------------------------------------------------- */
 
 /* main.cpp:298-389 in one call: partition + voxelize + build from HOST triangle

@@ -28,6 +28,7 @@ ABI_SYMBOLS = [
     "svo_estimate_partitions", "svo_text_roundtrip_float",
     "svo_set_triangles", "svo_set_triangles_device", "svo_partition", "svo_voxelize", "svo_build",
     "svo_fetch_nodes", "svo_fetch_data", "svo_device_nodes", "svo_device_data", "svo_fetch_voxel_codes",
+    "svo_shard_configure", "svo_shard_table_size", "svo_shard_count", "svo_shard_emit", "svo_shard_ranges",
     "svo_run", "svo_get_stats", "svo_synchronize", "svo_host_alloc", "svo_host_free",
 ]
 
@@ -89,6 +90,11 @@ def load_library(path: str | None = None):
     L.svo_device_nodes.restype = i32; L.svo_device_nodes.argtypes = [vp, C.POINTER(vp), C.POINTER(u64)]
     L.svo_device_data.restype = i32; L.svo_device_data.argtypes = [vp, C.POINTER(vp), C.POINTER(u64)]
     L.svo_fetch_voxel_codes.restype = i32; L.svo_fetch_voxel_codes.argtypes = [vp, vp, u64, C.POINTER(u64)]
+    L.svo_shard_configure.restype = i32; L.svo_shard_configure.argtypes = [vp, i32, i32]
+    L.svo_shard_table_size.restype = i32; L.svo_shard_table_size.argtypes = [vp, C.POINTER(u64)]
+    L.svo_shard_count.restype = i32; L.svo_shard_count.argtypes = [vp, vp]
+    L.svo_shard_emit.restype = i32; L.svo_shard_emit.argtypes = [vp, vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
+    L.svo_shard_ranges.restype = i32; L.svo_shard_ranges.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
     L.svo_run.restype = i32; L.svo_run.argtypes = [vp, C.POINTER(Params), vp, u64, vp, u64, vp, u64, C.POINTER(Stats)]
     L.svo_get_stats.restype = i32; L.svo_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.svo_synchronize.restype = i32; L.svo_synchronize.argtypes = [vp]
@@ -232,6 +238,28 @@ class SvoBuilder:
         nv, nn, nd = C.c_uint64(), C.c_uint64(), C.c_uint64()
         self._ck(self._lib.svo_build(self._h, C.byref(nv), C.byref(nn), C.byref(nd)))
         return nv.value, nn.value, nd.value
+
+    # -- sharded (multi-GPU) build: see include/svo_b200.h -------------------
+    def shard_configure(self, rank: int, world: int) -> None:
+        self._ck(self._lib.svo_shard_configure(self._h, rank, world))
+
+    def shard_table_size(self) -> int:
+        n = C.c_uint64()
+        self._ck(self._lib.svo_shard_table_size(self._h, C.byref(n)))
+        return n.value
+
+    def shard_count(self, dev_table_ptr: int) -> None:
+        self._ck(self._lib.svo_shard_count(self._h, dev_table_ptr))
+
+    def shard_emit(self, dev_table_ptr: int) -> tuple[int, int, int]:
+        nv, nn, nd = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self._ck(self._lib.svo_shard_emit(self._h, dev_table_ptr, C.byref(nv), C.byref(nn), C.byref(nd)))
+        return nv.value, nn.value, nd.value
+
+    def shard_ranges(self) -> tuple[int, int, int, int]:
+        a, b, c_, d = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self._ck(self._lib.svo_shard_ranges(self._h, C.byref(a), C.byref(b), C.byref(c_), C.byref(d)))
+        return a.value, b.value, c_.value, d.value
 
     def fetch_nodes(self, first: int, count: int, out: np.ndarray | None = None) -> np.ndarray:
         if out is None:

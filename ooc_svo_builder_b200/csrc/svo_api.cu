@@ -98,6 +98,20 @@ struct svo_ctx {
     DevBuf nodes, data, owner, tileidx, codes;
     uint64_t n_voxels = 0, n_nodes = 0, n_data = 0;
 
+    // sharding / two-phase build
+    int world = 1, rank = 0;
+    int dc = 0, J = 0;
+    ull c0 = 0, c1 = 1, slab_start = 0, slab_end = 0, WJ = 1;
+    ull bias[MAX_LEVELS];
+    int sb_lo[3], sb_hi[3];
+    ull q_begin = 0, q_end = 0;
+    bool want_pl = false, phase_a_done = false;
+    DevBuf table_own, dcol[4];
+    LevelBufs glv;                     // global level-J tile list (sharded / odd depth)
+    std::vector<ull> h_table;
+    ull leaf_offset = 0, n_voxels_local = 0;
+    ull node_lo = 0, node_hi = 0, data_lo = 0, data_hi = 0;
+
     svo_stats stats;
     uint32_t launches = 0;
 };
@@ -155,10 +169,11 @@ int exscan(svo_ctx* c, F f, ull n, ull* out) {
 
 int ilog2u(uint64_t v) { int r = -1; while (v) { v >>= 1; r++; } return r; }
 
-// Allocates (and zeroes) the dense pyramid for gridsize g.
+// Allocates (and zeroes) the dense pyramid for the current geometry (gridsize, shard).
 int ensure_pyramid(svo_ctx* c) {
     const uint64_t g = c->prm.gridsize;
-    if (c->dense_grid != g) {
+    const uint64_t geom_key = (g << 16) | ((uint64_t)c->world << 8) | (uint64_t)c->rank;
+    if (c->dense_grid != geom_key) {
         size_t total = 0;
         for (int j = 0; j < c->nl; j++) total += (size_t)c->nwords[j] * 8;
         size_t free_b = 0, total_b = 0;
@@ -173,7 +188,7 @@ int ensure_pyramid(svo_ctx* c) {
         }
         for (int j = 0; j < MAX_LEVELS; j++) c->dense[j].release();
         for (int j = 0; j < c->nl; j++) CK(c->dense[j].ensure((size_t)c->nwords[j] * 8));
-        c->dense_grid = g;
+        c->dense_grid = geom_key;
         c->dense_clean = false;
         ull* ptrs[MAX_LEVELS] = { nullptr };
         for (int j = 0; j < c->nl; j++) ptrs[j] = c->dense[j].as<ull>();
@@ -185,7 +200,7 @@ int ensure_pyramid(svo_ctx* c) {
         CK(cudaStreamSynchronize(c->stream));      // ptrs / nwords are stack / member memory
     }
     if (!c->dense_clean) {
-        for (int j = 0; j < c->nl; j++) CK(cudaMemsetAsync(c->dense[j].p, 0, (size_t)c->nwords[j] * 8, c->stream));
+        for (int j = 0; j <= c->J; j++) CK(cudaMemsetAsync(c->dense[j].p, 0, (size_t)c->nwords[j] * 8, c->stream));
         c->dense_clean = true;
     }
     return SVO_OK;
@@ -196,7 +211,8 @@ VoxJob make_voxjob(svo_ctx* c) {
     memset(&J, 0, sizeof J);
     J.tris = c->d_tris;
     J.fpt = (uint32_t)c->fpt;
-    J.n_pairs = c->n_pairs;
+    J.q_begin = c->q_begin;
+    J.q_end = c->q_end;
     J.pair_tri = c->P == 1 ? nullptr : c->pair_tri.as<uint32_t>();
     J.part_off = c->P == 1 ? nullptr : c->part_off.as<uint64_t>();
     J.P = (uint32_t)c->P;
@@ -205,8 +221,11 @@ VoxJob make_voxjob(svo_ctx* c) {
     J.g = (uint32_t)c->prm.gridsize;
     J.u = c->unit_vox;
     J.unit_div = c->unit_div;
-    J.nl = c->nl;
-    for (int j = 0; j < c->nl; j++) J.lvl[j] = c->dense[j].as<ull>();
+    J.nl = c->J + 1;                                             // the cascade stops at the top local level
+    for (int j = 0; j <= c->J; j++) J.lvl[j] = c->dense[j].as<ull>() - c->bias[j];   // indexed with global word indices
+    J.w_lo = c->bias[0];
+    J.w_hi = c->bias[0] + c->nwords[0];
+    for (int a = 0; a < 3; a++) { J.sb_lo[a] = c->sb_lo[a]; J.sb_hi[a] = c->sb_hi[a]; }
     J.queue[0] = c->queue[0].as<ull>();
     J.queue[1] = c->queue[1].as<ull>();
     J.qcount = c->qcount.as<ull>();
@@ -214,7 +233,7 @@ VoxJob make_voxjob(svo_ctx* c) {
     J.medium_max = 32768;
     if (const char* e = getenv("SVO_SMALL_MAX")) J.small_max = strtoull(e, nullptr, 10);
     if (const char* e = getenv("SVO_MEDIUM_MAX")) J.medium_max = strtoull(e, nullptr, 10);
-    J.tileidx = c->tileidx.as<uint32_t>();
+    J.tileidx = c->tileidx.p ? c->tileidx.as<uint32_t>() - c->bias[0] : nullptr;
     J.leafprefix = c->lv[0].fc.as<ull>();
     J.owner = c->owner.as<uint32_t>();
     return J;
@@ -222,11 +241,11 @@ VoxJob make_voxjob(svo_ctx* c) {
 
 template <bool OWNER>
 int launch_voxelizer(svo_ctx* c) {
-    if (c->n_pairs == 0) return SVO_OK;
+    if (c->q_end == c->q_begin) return SVO_OK;
     VoxJob J = make_voxjob(c);
     const size_t smem = J.pair_tri ? 0 : (size_t)VOX_BLOCK * c->fpt * sizeof(float);
     if (!OWNER) mark(c, EV_VS0);
-    k_vox_small<OWNER><<<blocks_for(c->n_pairs, VOX_BLOCK), VOX_BLOCK, smem, c->stream>>>(J); LAUNCHED();
+    k_vox_small<OWNER><<<blocks_for(c->q_end - c->q_begin, VOX_BLOCK), VOX_BLOCK, smem, c->stream>>>(J); LAUNCHED();
     if (!OWNER) mark(c, EV_VS1);
     const unsigned grid = (unsigned)c->sm_count * 4;
     k_vox_medium<OWNER><<<grid, WARPS_PER_BLOCK * 32, 0, c->stream>>>(J); LAUNCHED();
@@ -279,6 +298,7 @@ int svo_ctx_create(int device, svo_ctx** out) {
     memset(&n->stats, 0, sizeof n->stats);
     memset(&n->prm, 0, sizeof n->prm);
     memset(n->nwords, 0, sizeof n->nwords);
+    memset(n->bias, 0, sizeof n->bias);
     for (int i = 0; i < EV_COUNT; i++) n->ev_set[i] = false;
     c = n;
     cudaError_t e2 = cudaStreamCreateWithFlags(&n->own_stream, cudaStreamNonBlocking);
@@ -304,6 +324,10 @@ void svo_ctx_destroy(svo_ctx* c) {
         c->lv[j].key.release(); c->lv[j].mask.release(); c->lv[j].fc.release(); c->lv[j].ps.release(); c->lv[j].base.release();
         c->lv[j].pi.release(); c->lv[j].pl.release(); c->lv[j].ibase.release(); c->lv[j].cache.release();
     }
+    c->glv.key.release(); c->glv.mask.release(); c->glv.fc.release(); c->glv.ps.release(); c->glv.base.release();
+    c->glv.pi.release(); c->glv.pl.release(); c->glv.ibase.release(); c->glv.cache.release();
+    c->table_own.release();
+    for (int q = 0; q < 4; q++) c->dcol[q].release();
     c->d_lvlptrs.release(); c->d_nwords.release(); c->d_counts.release();
     c->part_counts.release(); c->part_cursor.release(); c->part_off.release(); c->pair_tri.release();
     c->queue[0].release(); c->queue[1].release(); c->qcount.release();
@@ -392,6 +416,8 @@ int svo_set_triangles_device(svo_ctx* c, const float* tris, uint64_t n_tris, int
     return SVO_OK;
 }
 
+static int setup_geometry(svo_ctx* c);
+
 int svo_partition(svo_ctx* c, const svo_params* params, uint64_t* n_partitions, uint64_t* part_tricounts, uint64_t cap) {
     if (!c) return SVO_E_INVALID;
     int rc = validate_params(c, params);
@@ -405,10 +431,6 @@ int svo_partition(svo_ctx* c, const svo_params* params, uint64_t* n_partitions, 
     const uint64_t g = params->gridsize;
     c->D = ilog2u(g);
     c->nl = (c->D + 1) / 2;
-    for (int j = 0; j < MAX_LEVELS; j++) {
-        const int sh = 3 * c->D - 6 * (j + 1);
-        c->nwords[j] = j < c->nl ? (sh >= 0 ? (1ULL << sh) : 1ULL) : 0ULL;
-    }
     c->P = svo_estimate_partitions(g, params->memory_limit_mb);               // main.cpp:298
     c->k = ilog2u(c->P) / 3;
     if (c->k > 5) return fail(c, SVO_E_INVALID, "more than 8^5 logical partitions are not supported");
@@ -455,11 +477,89 @@ int svo_partition(svo_ctx* c, const svo_params* params, uint64_t* n_partitions, 
         if (c->n_tris) { k_bin<true><<<blocks_for(c->n_tris, 256), 256, 0, c->stream>>>(B); LAUNCHED(); }
     }
     mark(c, EV_PART1);
+    rc = setup_geometry(c);
+    if (rc) return rc;
     c->partitioned = true;
     if (n_partitions) *n_partitions = c->P;
     if (part_tricounts) {
         if (cap < c->P) return fail(c, SVO_E_RANGE, "part_tricounts capacity is smaller than the partition count");
         for (uint64_t i = 0; i < c->P; i++) part_tricounts[i] = c->h_part_counts[i];
+    }
+    return SVO_OK;
+}
+
+int svo_shard_configure(svo_ctx* c, int rank, int world) {
+    if (!c) return SVO_E_INVALID;
+    if (world < 1 || rank < 0 || rank >= world || (world & (world - 1)) != 0)
+        return fail(c, SVO_E_INVALID, "shard world size must be a power of two and 0 <= rank < world");
+    c->world = world;
+    c->rank = rank;
+    c->partitioned = c->voxelized = c->built = false;
+    return SVO_OK;
+}
+
+// Shard geometry: the grid is cut into 8^dc chunks (subtrees at depth dc >= k), rank r owns a contiguous
+// Morton range of them. Pyramid levels 0..J live inside a chunk (local, dense per slab); levels above J are
+// tiny and replicated on every rank.
+static int setup_geometry(svo_ctx* c) {
+    const int D = c->D;
+    int dc = 0;
+    if (c->world > 1) {
+        int need = 0;
+        while ((1 << (3 * need)) < c->world) need++;
+        dc = c->k > need ? c->k : need;
+        if (D - dc < 2) return fail(c, SVO_E_INVALID, "gridsize too small for this many shards");
+        if (c->prm.generate_levels) return fail(c, SVO_E_INVALID, "-levels is not supported on the sharded (multi-GPU) path yet");
+    }
+    c->dc = dc;
+    c->J = (D - dc) / 2 - 1;
+    if (c->J < 0) c->J = 0;                                     // gridsize 2: the single level-0 word is the (virtual) top
+    const ull nchunks = 1ULL << (3 * dc);
+    c->c0 = nchunks * (ull)c->rank / (ull)c->world;
+    c->c1 = nchunks * (ull)(c->rank + 1) / (ull)c->world;
+    const int chunk_bits = 3 * (D - dc);
+    c->slab_start = c->c0 << chunk_bits;
+    c->slab_end = c->c1 << chunk_bits;
+    for (int j = 0; j < MAX_LEVELS; j++) {
+        const int sh = 6 * (j + 1);
+        if (j >= c->nl) { c->nwords[j] = 0; c->bias[j] = 0; continue; }
+        if (j <= c->J) {                                        // local level: the slab's words, global index = local + bias
+            const ull lo = c->slab_start >> sh, hi = c->slab_end >> sh;
+            c->bias[j] = lo;
+            c->nwords[j] = hi > lo ? hi - lo : 1;
+        } else {                                                // replicated upper level
+            c->bias[j] = 0;
+            c->nwords[j] = 3 * D >= sh ? (1ULL << (3 * D - sh)) : 1ULL;
+        }
+    }
+    const int shJ = 6 * (c->J + 1);
+    c->WJ = 3 * D >= shJ ? (1ULL << (3 * D - shJ)) : 1ULL;
+    // voxel bounding box of the slab (exact when the slab is a box, a superset otherwise; the sinks filter by word range)
+    if (c->world == 1) {
+        for (int a = 0; a < 3; a++) { c->sb_lo[a] = 0; c->sb_hi[a] = (int)c->prm.gridsize - 1; }
+    } else {
+        const uint32_t cs = (uint32_t)(c->prm.gridsize >> dc);
+        for (int a = 0; a < 3; a++) { c->sb_lo[a] = 0x7fffffff; c->sb_hi[a] = -1; }
+        for (ull ch = c->c0; ch < c->c1; ch++) {
+            const uint32_t cc[3] = { compact3(ch), compact3(ch >> 1), compact3(ch >> 2) };
+            for (int a = 0; a < 3; a++) {
+                c->sb_lo[a] = std::min(c->sb_lo[a], (int)(cc[a] * cs));
+                c->sb_hi[a] = std::max(c->sb_hi[a], (int)(cc[a] * cs + cs - 1));
+            }
+        }
+    }
+    // pairs of the partitions that intersect the slab
+    if (c->P == 1 || c->world == 1) { c->q_begin = 0; c->q_end = c->n_pairs; }
+    else {
+        const int sh = 3 * (dc - c->k);
+        const ull p_first = c->c0 >> sh, p_last = (c->c1 - 1) >> sh;
+        ull acc = 0;
+        c->q_begin = c->q_end = 0;
+        for (ull p = 0; p < c->P; p++) {
+            if (p == p_first) c->q_begin = acc;
+            acc += c->h_part_counts[p];
+            if (p == p_last) c->q_end = acc;
+        }
     }
     return SVO_OK;
 }
@@ -472,7 +572,8 @@ int svo_voxelize(svo_ctx* c) {
     if (rc) return rc;
     CK(c->qcount.ensure(4 * sizeof(ull)));
     CK(cudaMemsetAsync(c->qcount.p, 0, 4 * sizeof(ull), c->stream));
-    const size_t qbytes = (c->n_pairs ? c->n_pairs : 1) * sizeof(ull);
+    const ull npairs = c->q_end - c->q_begin;
+    const size_t qbytes = (npairs ? npairs : 1) * sizeof(ull);
     CK(c->queue[0].ensure(qbytes));
     CK(c->queue[1].ensure(qbytes));
     mark(c, EV_VOX0);
@@ -485,143 +586,303 @@ int svo_voxelize(svo_ctx* c) {
     return SVO_OK;
 }
 
-int svo_build(svo_ctx* c, uint64_t* n_voxels, uint64_t* n_nodes, uint64_t* n_data) {
-    if (!c) return SVO_E_INVALID;
-    if (!c->voxelized) return fail(c, SVO_E_INVALID, "svo_build before svo_voxelize");
-    CK(cudaSetDevice(c->device));
-    const int nl = c->nl, top = nl - 1;
-    const bool payload = c->prm.payload != 0;
-    const bool levels = c->prm.generate_levels != 0;
+// ---------------------------------------------------------------------------
+// Build, phase A (local): compact tile lists of levels J..0 from the slab's pyramid, subtree sizes
+// bottom-up, and this rank's entries of the exchange table.
+// ---------------------------------------------------------------------------
+static int alloc_level(svo_ctx* c, LevelBufs& L, ull n, bool pl, bool levels) {
+    L.n = n;
+    CK(L.key.ensure((n + 1) * sizeof(ull)));
+    CK(L.mask.ensure((n + 1) * sizeof(ull)));
+    CK(L.fc.ensure((n + 2) * sizeof(ull)));
+    CK(L.ps.ensure((n + 2) * sizeof(ull)));
+    CK(L.base.ensure((n + 1) * sizeof(ull)));
+    if (pl) CK(L.pl.ensure((n + 2) * sizeof(ull)));
+    if (levels) {
+        CK(L.pi.ensure((n + 2) * sizeof(ull)));
+        CK(L.ibase.ensure((n + 1) * sizeof(ull)));
+        CK(L.cache.ensure((n + 1) * 6 * sizeof(float)));
+    }
+    return SVO_OK;
+}
+
+static int size_scans(svo_ctx* c, LevelBufs& L, const LevelBufs* child, bool pl, bool levels) {
+    SizeOp op{ L.mask.as<ull>(), L.fc.as<ull>(), child ? child->ps.as<ull>() : nullptr };
+    int rc = exscan(c, op, L.n, L.ps.as<ull>());
+    if (rc) return rc;
+    if (pl) {
+        LeafCountOp lop{ L.mask.as<ull>(), L.fc.as<ull>(), child ? child->pl.as<ull>() : nullptr };
+        if ((rc = exscan(c, lop, L.n, L.pl.as<ull>()))) return rc;
+    }
+    if (levels) {
+        InternalOp iop{ L.mask.as<ull>(), L.fc.as<ull>(), child ? child->pi.as<ull>() : nullptr };
+        if ((rc = exscan(c, iop, L.n, L.pi.as<ull>()))) return rc;
+    }
+    return SVO_OK;
+}
+
+static int build_phase_a(svo_ctx* c, ull* table) {
+    const int J = c->J;
+    const bool payload = c->prm.payload != 0, levels = c->prm.generate_levels != 0;
+    const bool want_pl = payload || levels || c->world > 1;
+    c->want_pl = want_pl;
     mark(c, EV_BUILD0);
-    // ---- sync #1: how many non-zero words does every level hold? ----
+    // ---- sync #1: how many non-zero words does every local level hold? ----
     CK(cudaMemsetAsync(c->d_counts.p, 0, MAX_LEVELS * sizeof(ull), c->stream));
-    if (nl > 1) {
-        dim3 grid(64, (unsigned)(nl - 1));
-        k_level_counts<<<grid, 256, 0, c->stream>>>((ull* const*)c->d_lvlptrs.p, c->d_nwords.as<ull>(), nl, c->d_counts.as<ull>()); LAUNCHED();
+    {
+        dim3 grid(64, (unsigned)(J + 1));
+        k_level_counts<<<grid, 256, 0, c->stream>>>((ull* const*)c->d_lvlptrs.p, c->d_nwords.as<ull>(), J, c->d_counts.as<ull>()); LAUNCHED();
     }
     CK(cudaMemcpyAsync(c->h_pinned, c->d_counts.p, MAX_LEVELS * sizeof(ull), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaMemcpyAsync(c->h_pinned + 16, c->dense[top].p, sizeof(ull), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
-    const ull top_word = c->h_pinned[16];
-    for (int j = 0; j < nl; j++) c->lv[j].n = (j == top) ? (top_word ? 1 : 0) : c->h_pinned[j + 1];
-    for (int j = 0; j < nl; j++) {
-        const ull n = c->lv[j].n;
-        CK(c->lv[j].key.ensure((n + 1) * sizeof(ull)));
-        CK(c->lv[j].mask.ensure((n + 1) * sizeof(ull)));
-        CK(c->lv[j].fc.ensure((n + 2) * sizeof(ull)));
-        CK(c->lv[j].ps.ensure((n + 2) * sizeof(ull)));
-        CK(c->lv[j].base.ensure((n + 1) * sizeof(ull)));
-        if (levels) {
-            CK(c->lv[j].pi.ensure((n + 2) * sizeof(ull)));
-            CK(c->lv[j].pl.ensure((n + 2) * sizeof(ull)));
-            CK(c->lv[j].ibase.ensure((n + 1) * sizeof(ull)));
-            CK(c->lv[j].cache.ensure((n + 1) * 6 * sizeof(float)));
-        }
+    for (int j = 0; j <= J; j++) {
+        int rc = alloc_level(c, c->lv[j], c->h_pinned[j], want_pl, levels);
+        if (rc) return rc;
     }
     if (payload) CK(c->tileidx.ensure((size_t)c->nwords[0] * sizeof(uint32_t)));
     // ---- top-down: compact tile lists ----
-    CK(cudaMemsetAsync(c->lv[top].key.p, 0, sizeof(ull), c->stream));
-    CK(cudaMemsetAsync(c->lv[top].base.p, 0, sizeof(ull), c->stream));
-    CK(cudaMemcpyAsync(c->lv[top].mask.p, c->dense[top].p, sizeof(ull), cudaMemcpyDeviceToDevice, c->stream));
-    if (payload && nl == 1) CK(cudaMemsetAsync(c->tileidx.p, 0, sizeof(uint32_t), c->stream));
-    for (int j = top; j >= 0; j--) {
+    if (c->lv[J].n) {
+        k_compact_top<<<1, 1024, 0, c->stream>>>(c->dense[J].as<ull>(), c->nwords[J], c->bias[J], c->lv[J].key.as<ull>(), c->lv[J].mask.as<ull>(),
+                                                (payload && J == 0) ? c->tileidx.as<uint32_t>() : nullptr); LAUNCHED();
+    }
+    for (int j = J; j >= 0; j--) {
         PopcOp op{ c->lv[j].mask.as<ull>() };
         int rc = exscan(c, op, c->lv[j].n, c->lv[j].fc.as<ull>());
         if (rc) return rc;
         if (j > 0 && c->lv[j].n) {
             k_expand<<<blocks_for(c->lv[j].n, WARPS_PER_BLOCK), WARPS_PER_BLOCK * 32, 0, c->stream>>>(
-                c->lv[j].view(), c->lv[j - 1].view(), c->dense[j - 1].as<ull>(), (payload && j == 1) ? c->tileidx.as<uint32_t>() : nullptr); LAUNCHED();
+                c->lv[j].view(), c->lv[j - 1].view(), c->dense[j - 1].as<ull>() - c->bias[j - 1],
+                (payload && j == 1) ? c->tileidx.as<uint32_t>() - c->bias[0] : nullptr); LAUNCHED();
         }
     }
-    // ---- bottom-up: subtree sizes ----
-    for (int j = 0; j < nl; j++) {
-        SizeOp op{ c->lv[j].mask.as<ull>(), c->lv[j].fc.as<ull>(), j ? c->lv[j - 1].ps.as<ull>() : nullptr };
-        int rc = exscan(c, op, c->lv[j].n, c->lv[j].ps.as<ull>());
+    // ---- bottom-up: subtree sizes (+ leaf / internal counts) ----
+    for (int j = 0; j <= J; j++) {
+        int rc = size_scans(c, c->lv[j], j ? &c->lv[j - 1] : nullptr, want_pl, levels);
         if (rc) return rc;
-        if (levels) {
-            LeafCountOp lop{ c->lv[j].mask.as<ull>(), c->lv[j].fc.as<ull>(), j ? c->lv[j - 1].pl.as<ull>() : nullptr };
-            if ((rc = exscan(c, lop, c->lv[j].n, c->lv[j].pl.as<ull>()))) return rc;
-            InternalOp iop{ c->lv[j].mask.as<ull>(), c->lv[j].fc.as<ull>(), j ? c->lv[j - 1].pi.as<ull>() : nullptr };
-            if ((rc = exscan(c, iop, c->lv[j].n, c->lv[j].pi.as<ull>()))) return rc;
-        }
     }
-    if (levels) {
-        CK(cudaMemsetAsync(c->lv[top].ibase.p, 0, sizeof(ull), c->stream));
-        CK(cudaMemcpyAsync(c->h_pinned + 34, c->lv[top].pi.as<ull>() + c->lv[top].n, sizeof(ull), cudaMemcpyDeviceToHost, c->stream));
+    // ---- this rank's table entries ----
+    if (table) {
+        CK(cudaMemsetAsync(table, 0, (size_t)c->WJ * 4 * sizeof(ull), c->stream));
+        if (c->lv[J].n) {
+            k_table_fill<<<blocks_for(c->lv[J].n, 256), 256, 0, c->stream>>>(c->lv[J].key.as<ull>(), c->lv[J].mask.as<ull>(), c->lv[J].ps.as<ull>(),
+                                                                               want_pl ? c->lv[J].pl.as<ull>() : nullptr,
+                                                                               levels ? c->lv[J].pi.as<ull>() : nullptr, c->lv[J].n, table); LAUNCHED();
+        }
     }
     mark(c, EV_CMP1);
-    // ---- sync #2: record counts ----
-    CK(cudaMemcpyAsync(c->h_pinned + 32, c->lv[0].fc.as<ull>() + c->lv[0].n, sizeof(ull), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaMemcpyAsync(c->h_pinned + 33, c->lv[top].ps.as<ull>() + c->lv[top].n, sizeof(ull), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    c->n_voxels = c->h_pinned[32];
-    const ull s_top = c->h_pinned[33];
+    c->phase_a_done = true;
+    return SVO_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Build, phase B: replicated upper levels from the (summed) table, file bases top-down, emission.
+// ---------------------------------------------------------------------------
+static int build_phase_b(svo_ctx* c, const ull* table) {
+    const int J = c->J, nl = c->nl, top = nl - 1;
+    const bool payload = c->prm.payload != 0, levels = c->prm.generate_levels != 0;
+    const bool want_pl = c->want_pl;
+    const bool upper = J < top;
     const bool d_even = (c->D % 2) == 0;
+    ull goff = 0, n_gJ = c->lv[J].n;
+    c->leaf_offset = 0;
+    if (upper) {
+        // ---- dense columns of the global level-J words + replicated upper pyramid ----
+        for (int q = 0; q < 4; q++) CK(c->dcol[q].ensure((size_t)c->WJ * sizeof(ull)));
+        for (int j = J + 1; j < nl; j++) CK(cudaMemsetAsync(c->dense[j].p, 0, (size_t)c->nwords[j] * sizeof(ull), c->stream));
+        k_table_unpack<<<blocks_for(c->WJ, 256), 256, 0, c->stream>>>(table, c->WJ, c->dcol[0].as<ull>(), c->dcol[1].as<ull>(), c->dcol[2].as<ull>(),
+                                                                       c->dcol[3].as<ull>(), (ull* const*)c->d_lvlptrs.p, J + 1, nl); LAUNCHED();
+        // the host needs the global tile count of every upper level and this rank's offsets: the table is tiny
+        if (c->world > 1) {
+            c->h_table.resize((size_t)c->WJ * 4);
+            CK(cudaMemcpyAsync(c->h_table.data(), table, (size_t)c->WJ * 4 * sizeof(ull), cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+            n_gJ = 0;
+            const ull wj0 = c->bias[J], wj1 = c->bias[J] + c->nwords[J];
+            for (ull e = 0; e < c->WJ; e++) {
+                if (!c->h_table[e * 4]) continue;
+                if (e < wj0) { goff++; c->leaf_offset += c->h_table[e * 4 + 2]; }
+                (void)wj1;
+                n_gJ++;
+            }
+        }
+        // tile counts of the replicated upper levels
+        if (c->world == 1) {
+            // one GPU has at most ONE upper level: the virtual top word of an odd depth
+            for (int j = J + 1; j < nl; j++) { int rc = alloc_level(c, c->lv[j], c->lv[J].n ? 1 : 0, want_pl, levels); if (rc) return rc; }
+        } else {
+            std::vector<ull> cur((size_t)c->WJ);
+            for (ull e = 0; e < c->WJ; e++) cur[e] = c->h_table[e * 4] ? 1 : 0;
+            for (int j = J + 1; j < nl; j++) {
+                std::vector<ull> nxt((size_t)c->nwords[j], 0);
+                for (size_t e = 0; e < cur.size(); e++) if (cur[e]) nxt[e >> 6] = 1;
+                ull n = 0; for (ull v : nxt) n += v;
+                int rc = alloc_level(c, c->lv[j], n, want_pl, levels); if (rc) return rc;
+                cur.swap(nxt);
+            }
+        }
+        int rc = alloc_level(c, c->glv, n_gJ, want_pl, levels);
+        if (rc) return rc;
+        // ---- upper compact lists (tiny), ending in the GLOBAL level-J list ----
+        for (int j = top; j > J; j--) {
+            if (c->lv[j].n) { k_compact_top<<<1, 1024, 0, c->stream>>>(c->dense[j].as<ull>(), c->nwords[j], 0, c->lv[j].key.as<ull>(), c->lv[j].mask.as<ull>(), nullptr); LAUNCHED(); }
+        }
+        for (int j = top; j > J; j--) {
+            PopcOp op{ c->lv[j].mask.as<ull>() };
+            if ((rc = exscan(c, op, c->lv[j].n, c->lv[j].fc.as<ull>()))) return rc;
+        }
+        // global level-J list: keys and masks from the dense mask column, in key order
+        if (c->glv.n) { k_compact_top<<<1, 1024, 0, c->stream>>>(c->dcol[0].as<ull>(), c->WJ, 0, c->glv.key.as<ull>(), c->glv.mask.as<ull>(), nullptr); LAUNCHED(); }
+        {
+            DenseColOp sop{ c->dcol[1].as<ull>(), c->glv.key.as<ull>() };
+            if ((rc = exscan(c, sop, c->glv.n, c->glv.ps.as<ull>()))) return rc;
+            if (want_pl) { DenseColOp lop{ c->dcol[2].as<ull>(), c->glv.key.as<ull>() }; if ((rc = exscan(c, lop, c->glv.n, c->glv.pl.as<ull>()))) return rc; }
+            if (levels) { DenseColOp iop{ c->dcol[3].as<ull>(), c->glv.key.as<ull>() }; if ((rc = exscan(c, iop, c->glv.n, c->glv.pi.as<ull>()))) return rc; }
+        }
+        for (int j = J + 1; j < nl; j++) {
+            if ((rc = size_scans(c, c->lv[j], j == J + 1 ? &c->glv : &c->lv[j - 1], want_pl, levels))) return rc;
+        }
+    }
+    // ---- sync #2: record counts ----
+    LevelBufs& topL = c->lv[top];
+    CK(cudaMemcpyAsync(c->h_pinned + 32, c->lv[0].fc.as<ull>() + c->lv[0].n, sizeof(ull), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(c->h_pinned + 33, topL.ps.as<ull>() + topL.n, sizeof(ull), cudaMemcpyDeviceToHost, c->stream));
+    if (levels) CK(cudaMemcpyAsync(c->h_pinned + 34, topL.pi.as<ull>() + topL.n, sizeof(ull), cudaMemcpyDeviceToHost, c->stream));
+    if (want_pl) CK(cudaMemcpyAsync(c->h_pinned + 35, topL.pl.as<ull>() + topL.n, sizeof(ull), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->n_voxels_local = c->h_pinned[32];
+    c->n_voxels = (c->world > 1) ? c->h_pinned[35] : c->n_voxels_local;
+    const ull s_top = c->h_pinned[33];
     c->n_nodes = c->n_voxels == 0 ? 1 : s_top + (d_even ? 1 : 0);
     c->n_data = payload ? 1 + c->n_voxels : 2;          // OctreeBuilder.cpp:25-29
     if (levels && c->n_voxels) c->n_data += c->h_pinned[34] - (d_even ? 0 : 1);   // one record per internal node (the virtual top word is no node)
-    CK(c->nodes.ensure((size_t)c->n_nodes * SVO_NODE_BYTES));
-    CK(c->data.ensure((size_t)c->n_data * SVO_DATA_BYTES));
-    // ---- emit ----
+
+    // level-J view of this rank's tiles inside the global list
+    Level LJ = c->lv[J].view();
+    Level GJ = c->glv.view();
+    if (upper) {
+        LJ.key = GJ.key + goff; LJ.mask = GJ.mask + goff; LJ.ps = GJ.ps + goff; LJ.base = GJ.base + goff;
+        LJ.pl = want_pl ? GJ.pl + goff : nullptr;
+        LJ.pi = levels ? GJ.pi + goff : nullptr;
+        LJ.ibase = levels ? GJ.ibase + goff : nullptr;
+        LJ.cache = levels ? GJ.cache + goff * 6 : nullptr;
+    }
     mark(c, EV_EMIT0);
+    EmitJob E;
+    memset(&E, 0, sizeof E);
+    E.leaf_data_mode = payload ? 1 : 0;
+    E.levels = levels ? 1 : 0;
+    E.virtual_top = d_even ? 0 : 1;
+    E.leaf_offset = c->leaf_offset;
+    E.pos_lo = 0; E.pos_hi = ~0ULL;
+    E.write_records = 1;
+    c->node_lo = 0; c->node_hi = c->n_nodes;
+    if (c->n_voxels) {
+        CK(cudaMemsetAsync(topL.base.p, 0, sizeof(ull), c->stream));
+        if (levels) CK(cudaMemsetAsync(topL.ibase.p, 0, sizeof(ull), c->stream));
+    }
+    auto emit_upper_levels = [&](void) -> int {
+        for (int j = top; j > J; j--) {
+            if (!c->lv[j].n) continue;
+            E.is_top = (j == top);
+            E.root_here = (j == top) && d_even;
+            k_emit_upper<<<blocks_for(c->lv[j].n, WARPS_PER_BLOCK), WARPS_PER_BLOCK * 32, 0, c->stream>>>(c->lv[j].view(), j == J + 1 ? GJ : c->lv[j - 1].view(), E); LAUNCHED();
+        }
+        return SVO_OK;
+    };
+    if (c->world > 1 && c->n_voxels) {
+        // first pass over the replicated upper levels only propagates bases; then this rank's file range is known
+        E.write_records = 0;
+        int rc = emit_upper_levels();
+        if (rc) return rc;
+        E.write_records = 1;
+        const ull n_own = c->lv[J].n;
+        if (c->rank > 0 && goff < n_gJ) CK(cudaMemcpyAsync(c->h_pinned + 44, c->glv.base.as<ull>() + goff, sizeof(ull), cudaMemcpyDeviceToHost, c->stream));
+        if (goff + n_own < n_gJ) CK(cudaMemcpyAsync(c->h_pinned + 45, c->glv.base.as<ull>() + goff + n_own, sizeof(ull), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        c->node_lo = c->rank == 0 ? 0 : (goff < n_gJ ? c->h_pinned[44] : c->n_nodes);
+        c->node_hi = (goff + n_own < n_gJ && c->rank != c->world - 1) ? c->h_pinned[45] : c->n_nodes;
+        if (c->rank == c->world - 1) c->node_hi = c->n_nodes;
+    } else if (c->world > 1) {
+        c->node_lo = c->rank == 0 ? 0 : 1; c->node_hi = 1;      // empty grid: rank 0 writes the null root
+        if (c->rank != 0) c->node_lo = c->node_hi = 1;
+    }
+    const ull n_local_nodes = c->node_hi - c->node_lo;
+    CK(c->nodes.ensure((size_t)(n_local_nodes ? n_local_nodes : 1) * SVO_NODE_BYTES));
+    E.nodes = c->nodes.as<ull>() - c->node_lo * 3;
+    E.pos_lo = c->node_lo; E.pos_hi = c->node_hi;
     if (c->n_voxels == 0) {
         // empty grid: finalizeTree pads everything and writes a null root (OctreeBuilder.cpp:36-42)
         static const ull null_root[3] = { 0ULL, 0ULL, ~0ULL };
-        CK(cudaMemcpyAsync(c->nodes.p, null_root, sizeof null_root, cudaMemcpyHostToDevice, c->stream));
+        if (n_local_nodes) CK(cudaMemcpyAsync(c->nodes.p, null_root, sizeof null_root, cudaMemcpyHostToDevice, c->stream));
     } else {
-        EmitJob E;
-        E.nodes = c->nodes.as<ull>();
-        E.leaf_data_mode = payload ? 1 : 0;
-        E.levels = levels ? 1 : 0;
-        E.virtual_top = d_even ? 0 : 1;
-        for (int j = top; j >= 1; j--) {
+        int rc = emit_upper_levels();
+        if (rc) return rc;
+        for (int j = J; j >= 1; j--) {
+            if (!c->lv[j].n) continue;
             E.is_top = (j == top);
             E.root_here = (j == top) && d_even;
-            k_emit_upper<<<blocks_for(c->lv[j].n, WARPS_PER_BLOCK), WARPS_PER_BLOCK * 32, 0, c->stream>>>(c->lv[j].view(), c->lv[j - 1].view(), E); LAUNCHED();
+            k_emit_upper<<<blocks_for(c->lv[j].n, WARPS_PER_BLOCK), WARPS_PER_BLOCK * 32, 0, c->stream>>>(j == J ? LJ : c->lv[j].view(), c->lv[j - 1].view(), E); LAUNCHED();
         }
-        E.is_top = (top == 0);
-        E.root_here = (top == 0) && d_even;
-        mark(c, EV_EL0);
-        if (levels) { k_emit_leaf_levels<<<blocks_for(c->lv[0].n, WARPS_PER_BLOCK), WARPS_PER_BLOCK * 32, 0, c->stream>>>(c->lv[0].view(), E); LAUNCHED(); }
-        else { k_emit_leaf<<<blocks_for(c->lv[0].n, WARPS_PER_BLOCK * EMIT_TILES_PER_WARP), WARPS_PER_BLOCK * 32, 0, c->stream>>>(c->lv[0].view(), E); LAUNCHED(); }
-        mark(c, EV_EL1);
+        if (c->lv[0].n) {
+            E.is_top = (top == 0);
+            E.root_here = (top == 0) && d_even;
+            const Level L0 = (J == 0) ? LJ : c->lv[0].view();
+            mark(c, EV_EL0);
+            if (levels) { k_emit_leaf_levels<<<blocks_for(L0.n, WARPS_PER_BLOCK), WARPS_PER_BLOCK * 32, 0, c->stream>>>(L0, E); LAUNCHED(); }
+            else { k_emit_leaf<<<blocks_for(L0.n, WARPS_PER_BLOCK * EMIT_TILES_PER_WARP), WARPS_PER_BLOCK * 32, 0, c->stream>>>(L0, E); LAUNCHED(); }
+            mark(c, EV_EL1);
+        }
     }
     mark(c, EV_EMIT1);
     // ---- data records ----
     if (!payload) {
+        c->data_lo = 0; c->data_hi = c->n_data;                  // 2 records (+ internal records with -levels), all on rank 0
+        if (c->rank != 0) c->data_lo = c->data_hi = c->n_data;
+        CK(c->data.ensure((size_t)(c->n_data) * SVO_DATA_BYTES));
         static const uint32_t white[16] = { 0, 0, 0, 0, 0, 0, 0, 0,                         // record 0: NULL
                                             0, 0, 0x3f800000u, 0x3f800000u, 0x3f800000u, 0, 0, 0 };  // record 1: white voxel
-        CK(cudaMemcpyAsync(c->data.p, white, sizeof white, cudaMemcpyHostToDevice, c->stream));
+        if (c->rank == 0) CK(cudaMemcpyAsync(c->data.p, white, sizeof white, cudaMemcpyHostToDevice, c->stream));
     } else {
-        CK(cudaMemsetAsync(c->data.p, 0, SVO_DATA_BYTES, c->stream));
-        if (c->n_voxels) {
-            CK(c->owner.ensure((size_t)c->n_voxels * sizeof(uint32_t)));
-            CK(cudaMemsetAsync(c->owner.p, 0xff, (size_t)c->n_voxels * sizeof(uint32_t), c->stream));
+        if (c->world == 1) { c->data_lo = 0; c->data_hi = c->n_data; }
+        else {
+            c->data_lo = c->rank == 0 ? 0 : 1 + c->leaf_offset;
+            c->data_hi = 1 + c->leaf_offset + c->n_voxels_local;
+        }
+        const ull n_local_data = c->data_hi - c->data_lo;
+        CK(c->data.ensure((size_t)(n_local_data ? n_local_data : 1) * SVO_DATA_BYTES));
+        if (c->rank == 0) CK(cudaMemsetAsync(c->data.p, 0, SVO_DATA_BYTES, c->stream));
+        if (c->n_voxels_local) {
+            CK(c->owner.ensure((size_t)c->n_voxels_local * sizeof(uint32_t)));
+            CK(cudaMemsetAsync(c->owner.p, 0xff, (size_t)c->n_voxels_local * sizeof(uint32_t), c->stream));
             int rc = launch_voxelizer<true>(c);
             if (rc) return rc;
             PayloadJob Pj;
-            Pj.tris = c->d_tris; Pj.owner = c->owner.as<uint32_t>(); Pj.data = c->data.as<float>();
+            memset(&Pj, 0, sizeof Pj);
+            Pj.tris = c->d_tris; Pj.owner = c->owner.as<uint32_t>();
+            Pj.data = c->data.as<float>() - c->data_lo * 8;
             Pj.unit_div = c->unit_div; Pj.gridsize_f = (float)c->prm.gridsize; Pj.color_mode = c->prm.color_mode;
             Pj.levels = levels ? 1 : 0;
-            k_payload<<<blocks_for(c->lv[0].n, WARPS_PER_BLOCK), WARPS_PER_BLOCK * 32, 0, c->stream>>>(c->lv[0].view(), Pj); LAUNCHED();
+            Pj.leaf_offset = c->leaf_offset;
+            const Level L0 = (J == 0) ? LJ : c->lv[0].view();
+            k_payload<<<blocks_for(L0.n, WARPS_PER_BLOCK), WARPS_PER_BLOCK * 32, 0, c->stream>>>(L0, Pj); LAUNCHED();
         }
     }
     if (levels && c->n_voxels) {
         // internal-node data records, bottom-up (needs the leaf records and the ibase values written above)
-        EmitJob E;
-        E.nodes = c->nodes.as<ull>(); E.leaf_data_mode = payload ? 1 : 0; E.levels = 1; E.virtual_top = d_even ? 0 : 1;
         E.is_top = 0; E.root_here = 0;
         for (int j = 0; j < nl; j++) {
+            if (!c->lv[j].n) continue;
             const int real_node = !(j == top && !d_even);
-            k_levels_data<<<blocks_for(c->lv[j].n, 128), 128, 0, c->stream>>>(c->lv[j].view(), j ? c->lv[j - 1].view() : c->lv[j].view(), j, E,
-                                                                               c->data.as<float>(), real_node); LAUNCHED();
+            const Level L = (j == J) ? LJ : c->lv[j].view();
+            const Level C = j == 0 ? L : (j - 1 == J ? (upper ? GJ : LJ) : c->lv[j - 1].view());
+            k_levels_data<<<blocks_for(L.n, 128), 128, 0, c->stream>>>(L, C, j, E, c->data.as<float>(), real_node); LAUNCHED();
         }
     }
     mark(c, EV_BUILD1);
     // ---- leave a clean pyramid behind: zero exactly the words that were set ----
     mark(c, EV_CLR0);
-    for (int j = 0; j < nl; j++) {
-        if (c->lv[j].n) { k_sparse_clear<<<blocks_for(c->lv[j].n, 256), 256, 0, c->stream>>>(c->lv[j].key.as<ull>(), c->lv[j].n, c->dense[j].as<ull>()); LAUNCHED(); }
+    for (int j = 0; j <= J; j++) {
+        if (c->lv[j].n) { k_sparse_clear<<<blocks_for(c->lv[j].n, 256), 256, 0, c->stream>>>(c->lv[j].key.as<ull>(), c->lv[j].n, c->dense[j].as<ull>() - c->bias[j]); LAUNCHED(); }
     }
     c->dense_clean = true;
     mark(c, EV_CLR1);
@@ -629,10 +890,11 @@ int svo_build(svo_ctx* c, uint64_t* n_voxels, uint64_t* n_nodes, uint64_t* n_dat
     CK(cudaMemcpyAsync(c->h_pinned + 40, c->qcount.p, 2 * sizeof(ull), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     c->built = true;
-    c->stats.n_partitions = c->P; c->stats.n_pairs = c->n_pairs;
+    c->phase_a_done = false;
+    c->stats.n_partitions = c->P; c->stats.n_pairs = c->q_end - c->q_begin;
     c->stats.n_voxels = c->n_voxels; c->stats.n_nodes = c->n_nodes; c->stats.n_data = c->n_data;
     c->stats.n_medium = c->h_pinned[40]; c->stats.n_large = c->h_pinned[41];
-    c->stats.n_small = c->n_pairs - c->stats.n_medium - c->stats.n_large;
+    c->stats.n_small = c->stats.n_pairs - c->stats.n_medium - c->stats.n_large;
     c->stats.ms_upload = span(c, EV_UP0, EV_UP1);
     c->stats.ms_partition = span(c, EV_PART0, EV_PART1);
     c->stats.ms_voxelize = span(c, EV_VOX0, EV_VOX1);
@@ -641,18 +903,71 @@ int svo_build(svo_ctx* c, uint64_t* n_voxels, uint64_t* n_nodes, uint64_t* n_dat
     c->stats.ms_clear = span(c, EV_CLR0, EV_CLR1);
     c->stats.ms_download = 0.f;
     c->stats.ms_vox_small = span(c, EV_VS0, EV_VS1);
-    c->stats.ms_emit_leaf = c->n_voxels ? span(c, EV_EL0, EV_EL1) : 0.f;
+    c->stats.ms_emit_leaf = c->lv[0].n ? span(c, EV_EL0, EV_EL1) : 0.f;
     c->stats.ms_compact = span(c, EV_BUILD0, EV_CMP1);
     c->stats.kernel_launches = c->launches;
+    return SVO_OK;
+}
+
+int svo_build(svo_ctx* c, uint64_t* n_voxels, uint64_t* n_nodes, uint64_t* n_data) {
+    if (!c) return SVO_E_INVALID;
+    if (!c->voxelized) return fail(c, SVO_E_INVALID, "svo_build before svo_voxelize");
+    if (c->world != 1) return fail(c, SVO_E_INVALID, "sharded context: use svo_shard_count / svo_shard_emit");
+    CK(cudaSetDevice(c->device));
+    const bool upper = c->J < c->nl - 1;
+    if (upper) CK(c->table_own.ensure((size_t)c->WJ * 4 * sizeof(ull)));
+    int rc = build_phase_a(c, upper ? c->table_own.as<ull>() : nullptr);
+    if (rc) return rc;
+    rc = build_phase_b(c, upper ? c->table_own.as<ull>() : nullptr);
+    if (rc) return rc;
     if (n_voxels) *n_voxels = c->n_voxels;
     if (n_nodes) *n_nodes = c->n_nodes;
     if (n_data) *n_data = c->n_data;
     return SVO_OK;
 }
 
-static int fetch_common(svo_ctx* c, const DevBuf& src, uint64_t total, uint64_t rec, uint64_t first, uint64_t count, void* dst) {
+int svo_shard_table_size(svo_ctx* c, uint64_t* n_u64) {
+    if (!c || !n_u64) return SVO_E_INVALID;
+    if (!c->partitioned) return fail(c, SVO_E_INVALID, "svo_shard_table_size before svo_partition");
+    *n_u64 = c->WJ * 4;
+    return SVO_OK;
+}
+
+int svo_shard_count(svo_ctx* c, uint64_t* dev_table) {
+    if (!c) return SVO_E_INVALID;
+    if (!c->voxelized) return fail(c, SVO_E_INVALID, "svo_shard_count before svo_voxelize");
+    if (!dev_table) return fail(c, SVO_E_INVALID, "dev_table is NULL");
+    CK(cudaSetDevice(c->device));
+    return build_phase_a(c, (ull*)dev_table);
+}
+
+int svo_shard_emit(svo_ctx* c, const uint64_t* dev_table, uint64_t* n_voxels, uint64_t* n_nodes, uint64_t* n_data) {
+    if (!c) return SVO_E_INVALID;
+    if (!c->phase_a_done) return fail(c, SVO_E_INVALID, "svo_shard_emit before svo_shard_count");
+    if (!dev_table) return fail(c, SVO_E_INVALID, "dev_table is NULL");
+    CK(cudaSetDevice(c->device));
+    int rc = build_phase_b(c, (const ull*)dev_table);
+    if (rc) return rc;
+    if (n_voxels) *n_voxels = c->n_voxels;
+    if (n_nodes) *n_nodes = c->n_nodes;
+    if (n_data) *n_data = c->n_data;
+    return SVO_OK;
+}
+
+int svo_shard_ranges(svo_ctx* c, uint64_t* node_lo, uint64_t* node_hi, uint64_t* data_lo, uint64_t* data_hi) {
+    if (!c) return SVO_E_INVALID;
+    if (!c->built) return fail(c, SVO_E_INVALID, "svo_shard_ranges before the build finished");
+    if (node_lo) *node_lo = c->node_lo;
+    if (node_hi) *node_hi = c->node_hi;
+    if (data_lo) *data_lo = c->data_lo;
+    if (data_hi) *data_hi = c->data_hi;
+    return SVO_OK;
+}
+
+static int fetch_common(svo_ctx* c, const DevBuf& src, uint64_t lo, uint64_t hi, uint64_t rec, uint64_t first, uint64_t count, void* dst) {
     if (!c->built) return fail(c, SVO_E_INVALID, "fetch before svo_build");
-    if (first > total || count > total - first) return fail(c, SVO_E_RANGE, "record range out of bounds");
+    if (first < lo || first > hi || count > hi - first) return fail(c, SVO_E_RANGE, "record range outside this context's part of the file");
+    first -= lo;
     if (count && !dst) return fail(c, SVO_E_INVALID, "dst is NULL");
     CK(cudaSetDevice(c->device));
     mark(c, EV_DN0);
@@ -665,25 +980,25 @@ static int fetch_common(svo_ctx* c, const DevBuf& src, uint64_t total, uint64_t 
 
 int svo_fetch_nodes(svo_ctx* c, uint64_t first, uint64_t count, void* dst) {
     if (!c) return SVO_E_INVALID;
-    return fetch_common(c, c->nodes, c->n_nodes, SVO_NODE_BYTES, first, count, dst);
+    return fetch_common(c, c->nodes, c->node_lo, c->node_hi, SVO_NODE_BYTES, first, count, dst);
 }
 int svo_fetch_data(svo_ctx* c, uint64_t first, uint64_t count, void* dst) {
     if (!c) return SVO_E_INVALID;
-    return fetch_common(c, c->data, c->n_data, SVO_DATA_BYTES, first, count, dst);
+    return fetch_common(c, c->data, c->data_lo, c->data_hi, SVO_DATA_BYTES, first, count, dst);
 }
 
 int svo_device_nodes(svo_ctx* c, const void** p, uint64_t* n) {
     if (!c) return SVO_E_INVALID;
     if (!c->built) return fail(c, SVO_E_INVALID, "svo_device_nodes before svo_build");
     if (p) *p = c->nodes.p;
-    if (n) *n = c->n_nodes;
+    if (n) *n = c->node_hi - c->node_lo;
     return SVO_OK;
 }
 int svo_device_data(svo_ctx* c, const void** p, uint64_t* n) {
     if (!c) return SVO_E_INVALID;
     if (!c->built) return fail(c, SVO_E_INVALID, "svo_device_data before svo_build");
     if (p) *p = c->data.p;
-    if (n) *n = c->n_data;
+    if (n) *n = c->data_hi - c->data_lo;
     return SVO_OK;
 }
 
@@ -691,7 +1006,8 @@ int svo_fetch_voxel_codes(svo_ctx* c, uint64_t* dst, uint64_t capacity, uint64_t
     if (!c) return SVO_E_INVALID;
     if (!c->built) return fail(c, SVO_E_INVALID, "svo_fetch_voxel_codes before svo_build");
     CK(cudaSetDevice(c->device));
-    const uint64_t n = c->n_voxels < capacity ? c->n_voxels : capacity;
+    const uint64_t nloc = c->world > 1 ? c->n_voxels_local : c->n_voxels;
+    const uint64_t n = nloc < capacity ? nloc : capacity;
     if (n_written) *n_written = n;
     if (n == 0) return SVO_OK;
     if (!dst) return fail(c, SVO_E_INVALID, "dst is NULL");

@@ -23,7 +23,7 @@ constexpr int WARPS_PER_BLOCK = 8;
 struct VoxJob {
     const float* tris;                // .tridata image
     uint32_t fpt;                     // floats per triangle: 9 or 21
-    uint64_t n_pairs;                 // triangle/partition pairs
+    uint64_t q_begin, q_end;          // pair range handled by this context (its partitions)
     const uint32_t* pair_tri;         // per-partition index lists, concatenated; NULL = identity (P == 1)
     const uint64_t* part_off;         // P+1 list offsets (NULL when P == 1)
     uint32_t P, k;                    // logical partitions P = 8^k
@@ -35,6 +35,10 @@ struct VoxJob {
     unsigned long long* queue[2];     // medium / large work queues: (part << 32 | tri)
     unsigned long long* qcount;       // [0] medium, [1] large, [2] small (statistics)
     unsigned long long small_max, medium_max;
+    // sharding: level-0 word range owned by this context and the voxel bounding box of its slab.
+    // lvl[] / tileidx are biased so that they are indexed with GLOBAL word indices.
+    unsigned long long w_lo, w_hi;
+    int sb_lo[3], sb_hi[3];
     // payload owner pass
     const uint32_t* tileidx;          // dense: level-0 word -> compact tile index
     const unsigned long long* leafprefix;  // exclusive popcount prefix over level-0 tiles
@@ -47,6 +51,7 @@ struct VoxJob {
 // Binary pass: 64-bit atomicOr into the brick word; the thread that turns a word
 // from zero to non-zero propagates one bit to the level above, and so on.
 __device__ __forceinline__ void sink_fill(const VoxJob& J, uint64_t w, uint64_t mask) {
+    if (w < J.w_lo || w >= J.w_hi) return;          // another rank's slab
     unsigned long long old = atomicOr(&J.lvl[0][w], (unsigned long long)mask);
     int j = 0;
     while (old == 0ULL && ++j < J.nl) {
@@ -58,6 +63,7 @@ __device__ __forceinline__ void sink_fill(const VoxJob& J, uint64_t w, uint64_t 
 // Payload owner pass: the reference's first-triangle-wins rule (voxelizer.cpp:263)
 // made order independent: owner = min triangle index over all triangles passing.
 __device__ __forceinline__ void sink_owner_bit(const VoxJob& J, uint64_t w, int bit, uint32_t tri) {
+    if (w < J.w_lo || w >= J.w_hi) return;
     const unsigned long long W = J.lvl[0][w];
     const unsigned long long r = J.leafprefix[J.tileidx[w]] + __popcll(W & lowmask(bit));
     atomicMin(&J.owner[r], tri);
@@ -86,6 +92,14 @@ __device__ __forceinline__ void load_vertices(const VoxJob& J, uint32_t tri, flo
     for (int i = 0; i < 9; i++) v[i] = __ldg(t + i);
 }
 
+// Restrict a clamped box to the slab this context owns (no-op on a single GPU). Returns false if empty.
+__device__ __forceinline__ bool restrict_to_slab(const VoxJob& J, GridBox& b) {
+    b.x0 = max(b.x0, J.sb_lo[0]); b.x1 = min(b.x1, J.sb_hi[0]);
+    b.y0 = max(b.y0, J.sb_lo[1]); b.y1 = min(b.y1, J.sb_hi[1]);
+    b.z0 = max(b.z0, J.sb_lo[2]); b.z1 = min(b.z1, J.sb_hi[2]);
+    return b.x0 <= b.x1 && b.y0 <= b.y1 && b.z0 <= b.z1;
+}
+
 // Warp-aggregated queue push; must be called by all 32 lanes.
 __device__ __forceinline__ void warp_push(unsigned long long* counter, unsigned long long* q, bool pred, unsigned long long val) {
     const unsigned m = __ballot_sync(0xffffffffu, pred);
@@ -109,14 +123,14 @@ template <bool OWNER>
 __global__ void __launch_bounds__(VOX_BLOCK) k_vox_small(VoxJob J) {
     extern __shared__ float4 s_stage4[];
     float* s_stage = reinterpret_cast<float*>(s_stage4);
-    const uint64_t q0 = (uint64_t)blockIdx.x * VOX_BLOCK;
+    const uint64_t q0 = J.q_begin + (uint64_t)blockIdx.x * VOX_BLOCK;
     const uint64_t q = q0 + threadIdx.x;
-    const bool active = q < J.n_pairs;
+    const bool active = q < J.q_end;
     float v[9];
     uint32_t tri = 0, part = 0;
     if (J.pair_tri == nullptr) {
         // block-contiguous records [q0, q0 + VOX_BLOCK): VOX_BLOCK * fpt floats, 16-byte aligned
-        const uint64_t nrec = (J.n_pairs - q0 < VOX_BLOCK) ? (J.n_pairs - q0) : VOX_BLOCK;
+        const uint64_t nrec = (J.q_end - q0 < VOX_BLOCK) ? (J.q_end - q0) : VOX_BLOCK;
         const uint64_t nfl = nrec * J.fpt;
         const float* src = J.tris + q0 * J.fpt;
         const uint64_t n4 = nfl >> 2;
@@ -140,9 +154,11 @@ __global__ void __launch_bounds__(VOX_BLOCK) k_vox_small(VoxJob J) {
         int px, py, pz;
         partition_origin(J, part, px, py, pz);
         b = clamped_box(v, J.unit_div, px, py, pz, (int)J.side);
-        const unsigned long long vol = (unsigned long long)(b.x1 - b.x0 + 1) * (unsigned long long)(b.y1 - b.y0 + 1) *
-                                       (unsigned long long)(b.z1 - b.z0 + 1);
-        cls = vol <= J.small_max ? 0 : (vol <= J.medium_max ? 1 : 2);
+        if (restrict_to_slab(J, b)) {
+            const unsigned long long vol = (unsigned long long)(b.x1 - b.x0 + 1) * (unsigned long long)(b.y1 - b.y0 + 1) *
+                                           (unsigned long long)(b.z1 - b.z0 + 1);
+            cls = vol <= J.small_max ? 0 : (vol <= J.medium_max ? 1 : 2);
+        }
     }
     if (!OWNER) {
         const unsigned long long e = ((unsigned long long)part << 32) | tri;
@@ -274,6 +290,7 @@ __device__ __forceinline__ void queued_pair_setup(const VoxJob& J, unsigned long
     int px, py, pz;
     partition_origin(J, part, px, py, pz);
     b = clamped_box(v, J.unit_div, px, py, pz, (int)J.side);
+    restrict_to_slab(J, b);     // queued pairs are non-empty by construction
     tri_setup(v, J.u, s);
 }
 
@@ -476,19 +493,77 @@ struct Level {
     unsigned long long n;
 };
 
-// counts[j] (j >= 1) = number of set bits in dense level j = number of non-zero words of level j-1
-__global__ void __launch_bounds__(256) k_level_counts(unsigned long long* const* lvl, const unsigned long long* nwords, int nl,
+// counts[j] = number of non-zero words of local dense level j, j = 0..J: for j < J that is the number
+// of set bits of level j+1; for the top local level J the words are counted directly.
+__global__ void __launch_bounds__(256) k_level_counts(unsigned long long* const* lvl, const unsigned long long* nwords, int J,
                                                       unsigned long long* counts) {
-    const int j = blockIdx.y + 1;
-    if (j >= nl) return;
-    const unsigned long long n = nwords[j];
+    const int j = blockIdx.y;
+    if (j > J) return;
+    const int src = j < J ? j + 1 : J;
+    const unsigned long long n = nwords[src];
     unsigned long long acc = 0;
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x)
-        acc += __popcll(lvl[j][i]);
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long w = lvl[src][i];
+        acc += j < J ? (unsigned long long)__popcll(w) : (w != 0ULL ? 1ULL : 0ULL);
+    }
     unsigned long long total;
     block_excl_scan(acc, total);
     if (threadIdx.x == 0 && total) atomicAdd(&counts[j], total);
 }
+
+// Top local level: compact the non-zero words of the (small) dense level J into (key, mask). One block.
+__global__ void __launch_bounds__(1024) k_compact_top(const unsigned long long* dense, unsigned long long n, unsigned long long key_bias,
+                                                      unsigned long long* key, unsigned long long* mask, uint32_t* tileidx) {
+    unsigned long long carry = 0;
+    for (unsigned long long b = 0; b < n; b += blockDim.x) {
+        const unsigned long long idx = b + threadIdx.x;
+        const unsigned long long w = idx < n ? dense[idx] : 0ULL;
+        unsigned long long total;
+        const unsigned long long ex = block_excl_scan(w != 0ULL ? 1ULL : 0ULL, total);
+        if (w != 0ULL) {
+            key[carry + ex] = key_bias + idx; mask[carry + ex] = w;
+            if (tileidx) tileidx[idx] = (uint32_t)(carry + ex);     // level 0 only (payload owner pass)
+        }
+        carry += total;
+    }
+}
+
+// The exchange table: one entry of 4 u64 per GLOBAL level-J word: {mask, subtree size S, leaves, internal nodes}.
+// Every rank writes the entries of its own words (all others stay zero), the caller sums the tables of
+// all ranks (NCCL all-reduce; the entries are disjoint, so the sum is the union).
+__global__ void __launch_bounds__(256) k_table_fill(const unsigned long long* key, const unsigned long long* mask, const unsigned long long* ps,
+                                                    const unsigned long long* pl, const unsigned long long* pi, unsigned long long n,
+                                                    unsigned long long* table) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned long long* e = table + key[i] * 4ULL;
+    e[0] = mask[i];
+    e[1] = ps[i + 1] - ps[i];
+    e[2] = pl ? pl[i + 1] - pl[i] : 0ULL;
+    e[3] = pi ? pi[i + 1] - pi[i] : 0ULL;
+}
+// Unpack the summed table into dense columns and rebuild the (tiny, replicated) upper dense levels.
+__global__ void __launch_bounds__(256) k_table_unpack(const unsigned long long* table, unsigned long long n, unsigned long long* dmask,
+                                                      unsigned long long* dS, unsigned long long* dLC, unsigned long long* dI,
+                                                      unsigned long long* const* lvl, int first_upper, int nl) {
+    const unsigned long long e = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const unsigned long long m = table[e * 4ULL];
+    dmask[e] = m; dS[e] = table[e * 4ULL + 1]; dLC[e] = table[e * 4ULL + 2]; dI[e] = table[e * 4ULL + 3];
+    if (m) {
+        unsigned long long w = e;
+        for (int j = first_upper; j < nl; j++) {
+            const unsigned long long bit = 1ULL << (w & 63);
+            w >>= 6;
+            if (atomicOr(&lvl[j][w], bit) != 0ULL) break;
+        }
+    }
+}
+struct DenseColOp {      // value of a dense per-word column at the key of compact tile i
+    const unsigned long long* col;
+    const unsigned long long* key;
+    __device__ unsigned long long operator()(unsigned long long i) const { return col[key[i]]; }
+};
 
 struct CountOp {
     const unsigned long long* cnt;
@@ -560,7 +635,14 @@ struct EmitJob {
     int leaf_data_mode;               // level 0: 0 = binary (data = 1), 1 = payload (data = 1 + leaf rank)
     int levels;                       // -levels: internal nodes carry a data index too
     int virtual_top;                  // D odd: the top word is not a node (its byte 0 is the root)
+    // sharding: `nodes` is biased by -pos_lo records; replicated upper levels only write [pos_lo, pos_hi)
+    unsigned long long pos_lo, pos_hi;
+    unsigned long long leaf_offset;   // leaves in the slabs of lower ranks
+    int write_records;                // 0: only propagate the subtree bases (first pass of the replicated upper levels)
 };
+__device__ __forceinline__ bool emit_here(const EmitJob& E, unsigned long long pos) {
+    return E.write_records && pos >= E.pos_lo && pos < E.pos_hi;
+}
 
 // -levels: data index of an internal node = records written before it. Payload mode interleaves the
 // leaf records (written at addVoxel) with the internal ones (written in post-order by groupNodes):
@@ -601,10 +683,12 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_emit_upper(Level L, Le
                 C.ibase[c] = gib;
                 gdata = internal_data_index(E, C.pl[c + 1], gib + (C.pi[c + 1] - C.pi[c]) - 1ULL);
             }
-            unsigned long long* o = E.nodes + pos * 3;
-            o[0] = gdata;
-            o[1] = gbase + gS - __popc(gnz);
-            o[2] = child_offsets(gnz);
+            if (emit_here(E, pos)) {
+                unsigned long long* o = E.nodes + pos * 3;
+                o[0] = gdata;
+                o[1] = gbase + gS - __popc(gnz);
+                o[2] = child_offsets(gnz);
+            }
         }
     }
     if (lane < 8 && ((nzb >> lane) & 1u)) {
@@ -614,12 +698,14 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_emit_upper(Level L, Le
         const unsigned long long pos = base + S - __popc(nzb) + __popc(nzb & ((1u << k) - 1u));
         unsigned long long cdata = 0ULL;
         if (E.levels) cdata = internal_data_index(E, C.pl[cend], L.ibase[i] + (C.pi[cend] - C.pi[fc]) + __popc(nzb & ((1u << k) - 1u)));
-        unsigned long long* o = E.nodes + pos * 3;
-        o[0] = cdata;
-        o[1] = blk;
-        o[2] = child_offsets((uint32_t)((W >> (8 * k)) & 0xffULL));
+        if (emit_here(E, pos)) {
+            unsigned long long* o = E.nodes + pos * 3;
+            o[0] = cdata;
+            o[1] = blk;
+            o[2] = child_offsets((uint32_t)((W >> (8 * k)) & 0xffULL));
+        }
     }
-    if (E.root_here && lane == 8) {
+    if (E.root_here && lane == 8 && emit_here(E, S)) {
         unsigned long long* o = E.nodes + S * 3;
         o[0] = E.levels ? internal_data_index(E, L.pl[i + 1], L.ibase[i] + (L.pi[i + 1] - L.pi[i]) - 1ULL) : 0ULL;
         o[1] = base + S - __popc(nzb);
@@ -663,7 +749,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_emit_leaf(Level L, Emi
                 ff += 2; if (ff >= 3) ff -= 3;       // (q + 32) % 3 == (q % 3 + 2) % 3
             }
         } else {
-            const unsigned long long leaf0 = 1ULL + __shfl_sync(0xffffffffu, myFc, t);   // data index = 1 + leaf rank
+            const unsigned long long leaf0 = 1ULL + E.leaf_offset + __shfl_sync(0xffffffffu, myFc, t);   // data index = 1 + leaf rank
             int ff = f;
             for (int q = lane; q < total; q += 32) {
                 out[q] = ff == 0 ? leaf0 + (unsigned)(q / 3) : (ff == 1 ? 0ULL : ~0ULL);
@@ -815,6 +901,7 @@ struct PayloadJob {
     float gridsize_f;
     int color_mode;
     int levels;               // -levels: leaf records are interleaved with internal ones
+    unsigned long long leaf_offset;   // sharding: leaves of lower ranks; `data` is biased accordingly
 };
 
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_payload(Level L, PayloadJob Pj) {
@@ -886,7 +973,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_payload(Level L, Paylo
         // singular vertex matrix, zero normal) and propagates it; CUDA produces 0x7FFFFFFF.
 #pragma unroll
         for (int q = 0; q < 3; q++) if (col[q] != col[q]) col[q] = __uint_as_float(0xFFC00000u);
-        unsigned long long didx = 1ULL + r;
+        unsigned long long didx = 1ULL + Pj.leaf_offset + r;
         if (Pj.levels) didx += L.ibase[i] + __popc(nonzero_bytes(W) & ((1u << (bit >> 3)) - 1u));
         float4* o = reinterpret_cast<float4*>(Pj.data + didx * 8ULL);
         float4 a, b;

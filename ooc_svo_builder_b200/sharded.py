@@ -1,0 +1,319 @@
+"""Multi-GPU driver of the sharded build (one context per GPU) and its host-side plan.
+
+The data path has exactly one exchange: the table of top-of-shard subtree records
+(`svo_shard_count` -> all-reduce(sum) -> `svo_shard_emit`, include/svo_b200.h).
+With torch.distributed the all-reduce runs over NCCL / NVLink on the device
+buffer the library filled; nothing else crosses GPUs.  Every rank ends up with a
+contiguous range of the .octreenodes / .octreedata files; the ranges tile them.
+
+`plan()` restates the library's shard geometry in Python so that the host logic
+can be tested without a GPU (tests/test_sharded_cpu.py, gloo, world_size 2).
+"""
+from __future__ import annotations
+
+import math
+import os
+import time
+from dataclasses import dataclass
+
+import numpy as np
+
+from .api import SvoBuilder, header_bytes, estimate_partitions, NODE_BYTES, DATA_BYTES
+
+
+@dataclass
+class ShardPlan:
+    world: int
+    rank: int
+    depth: int            # D = log2(gridsize)
+    k: int                # log8(P)
+    dc: int               # chunk depth
+    top_local_level: int  # J
+    chunk_range: tuple    # [c0, c1) chunks of 8^(D-dc) voxels
+    morton_range: tuple   # [start, end) Morton codes owned
+    partition_range: tuple  # [p_first, p_last] logical partitions that intersect the slab
+    table_entries: int    # WJ: global level-J words = table entries (x4 u64)
+    own_entries: tuple    # [wj0, wj1) entries this rank writes
+
+
+def plan(gridsize: int, n_partitions: int, world: int, rank: int) -> ShardPlan:
+    """Mirror of setup_geometry() in csrc/svo_api.cu."""
+    D = int(math.log2(gridsize))
+    k = int(round(math.log(n_partitions, 8))) if n_partitions > 1 else 0
+    dc = 0
+    if world > 1:
+        need = 0
+        while 8 ** need < world:
+            need += 1
+        dc = max(k, need)
+        if D - dc < 2:
+            raise ValueError("gridsize too small for this many shards")
+    J = max((D - dc) // 2 - 1, 0)
+    nchunks = 8 ** dc
+    c0, c1 = nchunks * rank // world, nchunks * (rank + 1) // world
+    bits = 3 * (D - dc)
+    start, end = c0 << bits, c1 << bits
+    sh = 3 * (dc - k)
+    shJ = 6 * (J + 1)
+    WJ = (1 << (3 * D - shJ)) if 3 * D >= shJ else 1
+    return ShardPlan(world, rank, D, k, dc, J, (c0, c1), (start, end), (c0 >> sh, (c1 - 1) >> sh), WJ,
+                     (start >> shJ, max(end >> shJ, (start >> shJ) + 1)))
+
+
+def merge_tables(tables: list[np.ndarray]) -> np.ndarray:
+    """What the all-reduce computes: the entries of different ranks are disjoint, so sum == union."""
+    out = np.zeros_like(tables[0])
+    for t in tables:
+        assert not ((out != 0) & (t != 0)).any(), "two ranks wrote the same table entry"
+        out += t
+    return out
+
+
+@dataclass
+class ShardResult:
+    rank: int
+    n_voxels: int
+    n_nodes: int
+    n_data: int
+    node_range: tuple
+    data_range: tuple
+    nodes: np.ndarray      # uint8, this rank's node records
+    data: np.ndarray       # uint8, this rank's data records
+    stats: dict
+
+
+def assemble(results: list[ShardResult], gridsize: int):
+    """Concatenate the per-rank ranges into the complete file images (host side, tests / rank-0 writer)."""
+    rs = sorted(results, key=lambda r: r.rank)
+    nn, nd = rs[0].n_nodes, rs[0].n_data
+    pos = 0
+    for r in rs:
+        assert r.node_range[0] == pos or r.node_range[0] == r.node_range[1], (r.rank, r.node_range, pos)
+        pos = max(pos, r.node_range[1])
+    assert pos == nn, (pos, nn)
+    nodes = np.zeros(nn * NODE_BYTES, dtype=np.uint8)
+    data = np.zeros(nd * DATA_BYTES, dtype=np.uint8)
+    for r in rs:
+        nodes[r.node_range[0] * NODE_BYTES: r.node_range[1] * NODE_BYTES] = r.nodes
+        data[r.data_range[0] * DATA_BYTES: r.data_range[1] * DATA_BYTES] = r.data
+    return header_bytes(gridsize, nn, nd), nodes, data
+
+
+def run_single_process(tris, length: float, gridsize: int, world: int, memory_limit_mb: int = 2048,
+                       color: str = "model", device: int = 0, fetch: bool = True) -> list[ShardResult]:
+    """All `world` ranks as contexts of ONE process (sharing a GPU is fine): the table exchange is a
+    host-side sum. Used by the single-GPU parity tests of the sharded path and by the CLI."""
+    import torch
+    payload = tris.shape[1] == 21
+    ctxs = [SvoBuilder(device) for _ in range(world)]
+    try:
+        prm = SvoBuilder.make_params(length, gridsize, payload, memory_limit_mb, False, color)
+        tables = []
+        for r, sb in enumerate(ctxs):
+            sb.shard_configure(r, world)
+            sb.set_triangles(tris)
+            sb.partition(prm)
+            sb.voxelize()
+            t = torch.zeros(sb.shard_table_size(), dtype=torch.int64, device="cuda:%d" % device)
+            sb.shard_count(t.data_ptr())
+            sb.synchronize()
+            tables.append(t)
+        merged = torch.stack(tables).sum(dim=0)
+        # disjointness is part of the contract
+        assert int((torch.stack([(t != 0).to(torch.int64) for t in tables]).sum(dim=0) > 1).sum()) == 0
+        out = []
+        for r, sb in enumerate(ctxs):
+            nv, nn, nd = sb.shard_emit(merged.data_ptr())
+            nlo, nhi, dlo, dhi = sb.shard_ranges()
+            nodes = sb.fetch_nodes(nlo, nhi - nlo) if fetch else np.empty(0, np.uint8)
+            data = sb.fetch_data(dlo, dhi - dlo) if fetch else np.empty(0, np.uint8)
+            out.append(ShardResult(r, nv, nn, nd, (nlo, nhi), (dlo, dhi), nodes, data, sb.stats()))
+        return out
+    finally:
+        for sb in ctxs:
+            sb.close()
+
+
+class DistributedBuilder:
+    """One rank of a torch.distributed job (backend nccl, one process per GPU)."""
+
+    def __init__(self, dist, device: int):
+        import torch
+        self.dist = dist
+        self.torch = torch
+        self.rank = dist.get_rank()
+        self.world = dist.get_world_size()
+        self.sb = SvoBuilder(device)
+        self.sb.shard_configure(self.rank, self.world)
+        self.device = device
+        self.table = None
+
+    def set_stream(self, stream):
+        self.sb.set_stream(stream.cuda_stream)
+
+    def set_triangles(self, tris):
+        self.sb.set_triangles(tris)
+
+    def step(self, prm):
+        """partition -> voxelize -> local build -> NCCL all-reduce of the table -> merged emit."""
+        sb = self.sb
+        sb.partition(prm)
+        sb.voxelize()
+        n = sb.shard_table_size()
+        if self.table is None or self.table.numel() != n:
+            self.table = self.torch.zeros(n, dtype=self.torch.int64, device="cuda:%d" % self.device)
+        sb.shard_count(self.table.data_ptr())
+        self.dist.all_reduce(self.table)              # sum over ranks == union of disjoint entries (NCCL over NVLink)
+        return sb.shard_emit(self.table.data_ptr())
+
+    def close(self):
+        self.sb.close()
+
+
+# ----------------------------------------------------------------------------
+# numpy closed form of the file layout: used by the CPU tests of the
+# exchange protocol and as an independent check of the node ordering.
+# ----------------------------------------------------------------------------
+
+def subtree_table_from_codes(codes: np.ndarray, gridsize: int, p: ShardPlan) -> np.ndarray:
+    """Table entries {mask, S, leaves, 0} of the level-J subtrees inside p.morton_range, from sorted Morton codes."""
+    D, J = p.depth, p.top_local_level
+    shJ = 6 * (J + 1)
+    t = np.zeros(p.table_entries * 4, dtype=np.int64)
+    own = codes[(codes >= p.morton_range[0]) & (codes < p.morton_range[1])]
+    if own.size == 0:
+        return t
+    root_depth = D - 2 * (J + 1)
+    keys = own >> np.uint64(shJ)
+    for key in np.unique(keys):
+        sub = own[keys == key]
+        S = 0
+        for d in range(max(root_depth, 0) + 1, D + 1):
+            S += np.unique(sub >> np.uint64(3 * (D - d))).size
+        if root_depth < 0:       # virtual top word: depth -1 -> depth 0 (the root) is a child of the word
+            S += 0
+        bits = np.unique((sub >> np.uint64(shJ - 6)) & np.uint64(63))
+        mask = 0
+        for b in bits:
+            mask |= 1 << int(b)
+        e = int(key) * 4
+        t[e] = np.array(mask, dtype=np.uint64).astype(np.int64)
+        t[e + 1] = S
+        t[e + 2] = sub.size
+    return t
+
+
+def node_count_from_codes(codes: np.ndarray, gridsize: int) -> int:
+    """n_nodes of the reference's tree: distinct Morton prefixes over all depths (root included)."""
+    D = int(math.log2(gridsize))
+    if codes.size == 0:
+        return 1
+    return 1 + sum(np.unique(codes >> np.uint64(3 * (D - d))).size for d in range(1, D + 1))
+
+
+# ----------------------------------------------------------------------------
+# bench.py --gpus N (N > 1): weak scaling of the sharded path
+# ----------------------------------------------------------------------------
+
+def bench(args, rank, world, local, dist, peak, peak_src, ClockSampler):
+    import json
+    import torch
+    from . import meshgen
+    from bench import METRIC, UNIT, SPHERE_N
+
+    G = 2048                                  # 8 logical partitions of 1024^3 (default -l 2048)
+    octants = {2: [0, 4], 4: [0, 2, 4, 6], 8: list(range(8))}[world]
+    base = meshgen.displaced_sphere(SPHERE_N, SPHERE_N, seed=1, length=1.0)       # one sphere per populated octant
+    parts = []
+    for o in octants:
+        off = np.array([(o & 1), (o >> 1) & 1, (o >> 2) & 1], dtype=np.float32)
+        t = base.tris.reshape(-1, 3, 3) + off
+        parts.append(t.reshape(-1, 9))
+    tris = np.ascontiguousarray(np.concatenate(parts), dtype=np.float32)
+    T = tris.shape[0]
+    db = DistributedBuilder(dist, local)
+    stream = torch.cuda.Stream()
+    db.set_stream(stream)
+    prm = SvoBuilder.make_params(2.0, G, False)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    with torch.cuda.stream(stream):
+        d_tris = torch.from_numpy(tris).cuda()
+        torch.cuda.synchronize()
+        db.set_triangles(d_tris)
+        for _ in range(max(args.warmup, 3)):
+            flush.zero_()
+            nv, nn, nd = db.step(prm)
+        torch.cuda.synchronize()
+        dist.barrier()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+            time.sleep(0.3)
+        t0 = time.time()
+        evs = []
+        for _ in range(args.steps):
+            flush.zero_()
+            dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            nv, nn, nd = db.step(prm)
+            e1.record(stream)
+            evs.append((e0, e1))
+        torch.cuda.synchronize()
+        dist.barrier()
+        t1 = time.time()
+        ms = torch.tensor([a.elapsed_time(b) for a, b in evs], dtype=torch.float64, device="cuda")
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)                     # per step: the slowest rank
+    ms_per_step = float(ms.mean())
+    st = db.sb.stats()
+    launches = torch.tensor([st["kernel_launches"]], dtype=torch.int64, device="cuda")
+    dist.all_reduce(launches)
+    leaf_ms = torch.tensor([st["ms_emit_leaf"], st["ms_vox_small"]], dtype=torch.float64, device="cuda")
+    dist.all_reduce(leaf_ms, op=dist.ReduceOp.MAX)
+
+    # e2e: host triangles in, this rank's node / data range out to pinned host memory
+    nlo, nhi, dlo, dhi = db.sb.shard_ranges()
+    from .api import PinnedBuffer
+    h_tris = PinnedBuffer(tris.nbytes); h_tris.array[:] = tris.view(np.uint8).reshape(-1)
+    h_nodes = PinnedBuffer(max(nhi - nlo, 1) * 24 + 24 * 4096); h_data = PinnedBuffer(64)
+    tv = h_tris.array.view(np.float32).reshape(T, 9)
+    e2e = []
+    for i in range(3 + args.steps):
+        dist.barrier()
+        t = time.perf_counter()
+        db.set_triangles(tv)
+        db.step(prm)
+        a, b, c_, d = db.sb.shard_ranges()
+        db.sb.fetch_nodes(a, b - a, h_nodes.array[: (b - a) * 24])
+        if d > c_:
+            db.sb.fetch_data(c_, d - c_, h_data.array[: (d - c_) * 32])
+        dt = torch.tensor([time.perf_counter() - t], dtype=torch.float64, device="cuda")
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        if i >= 3:
+            e2e.append(float(dt))
+    e2e_s = sum(e2e) / len(e2e)
+    if rank == 0:
+        clocks = sampler.stop(t0, t1)
+        value = T / (ms_per_step * 1e-3)
+        alg = 8 * nv + 24 * nn
+        lm = float(leaf_ms[0])
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "voxels_per_s": nv / (ms_per_step * 1e-3),
+            "config": {"workload": "svo_builder_binary -s 2048 (8 logical partitions of 1024^3), one 2M-triangle displaced sphere in each of "
+                                   "%d octants, partitions sharded over %d B200, NCCL all-reduce of the subtree table" % (world, world),
+                       "gridsize": G, "n_triangles": T, "n_voxels": nv, "n_nodes": nn, "partitions": 8,
+                       "l2": "flushed between timed iterations (256 MB write)", "parallelism": "partition-sharded x%d" % world},
+            "roofline": {"bound": "hbm", "kernel": "k_emit_leaf (per rank)", "achieved": (alg / world) / max(lm, 1e-9) / 1e6, "peak": peak, "unit": "GB/s",
+                         "frac": (alg / world) / max(lm, 1e-9) / 1e6 / peak, "traffic": None, "peak_source": peak_src,
+                         "note": "octree build 8*N + 24*N_nodes bytes per rank / slowest rank's k_emit_leaf time"},
+            "e2e": {"value": T / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(tris.nbytes) * world,
+                    "d2h_bytes_per_step": int(nn * 24 + nd * 32), "ms_per_step": e2e_s * 1e3,
+                    "api": "svo_set_triangles + sharded step + svo_fetch_* per rank (pinned host buffers, wall clock, max over ranks)"},
+            "gpu_launches": int(launches) * args.steps, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    db.close()
+    dist.barrier()
+    dist.destroy_process_group()

@@ -1,0 +1,98 @@
+"""CPU tests of the multi-GPU host logic: the shard plan, and the table exchange run for real over
+torch.distributed (gloo, world_size 2) with per-rank tables derived from the oracle's voxels."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from ooc_svo_builder_b200 import meshgen as mg
+from ooc_svo_builder_b200 import sharded
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("g,P,world", [(2048, 8, 2), (2048, 8, 4), (2048, 8, 8), (4096, 64, 8), (8192, 512, 8), (1024, 1, 8), (256, 8, 2), (64, 1, 2)])
+def test_plan_tiles_the_grid(g, P, world):
+    plans = [sharded.plan(g, P, world, r) for r in range(world)]
+    assert plans[0].morton_range[0] == 0 and plans[-1].morton_range[1] == g ** 3
+    for a, b in zip(plans, plans[1:]):
+        assert a.morton_range[1] == b.morton_range[0]                 # contiguous Morton ranges
+        assert a.own_entries[1] <= b.own_entries[0] or a.own_entries == b.own_entries
+    p = plans[0]
+    assert p.dc >= p.k                                                # chunks never straddle a logical partition
+    assert 64 ** (p.top_local_level + 1) <= 8 ** (p.depth - p.dc)    # a top-local word stays inside one chunk
+    if P >= world:                                                    # whole partitions per rank
+        owned = [set(range(q.partition_range[0], q.partition_range[1] + 1)) for q in plans]
+        assert sum(len(o) for o in owned) == P and set().union(*owned) == set(range(P))
+
+
+def test_plan_rejects_tiny_grids():
+    with pytest.raises(ValueError):
+        sharded.plan(4, 1, 8, 0)
+
+
+def test_merge_tables_requires_disjoint_entries():
+    a = np.zeros(16, dtype=np.int64); b = np.zeros(16, dtype=np.int64)
+    a[0:4] = [5, 9, 3, 0]; b[8:12] = [1, 2, 1, 0]
+    m = sharded.merge_tables([a, b])
+    assert m[1] == 9 and m[9] == 2
+    with pytest.raises(AssertionError):
+        sharded.merge_tables([a, a])
+
+
+WORKER = r"""
+import os, sys, json
+import numpy as np
+import torch, torch.distributed as dist
+sys.path.insert(0, {root!r})
+from ooc_svo_builder_b200 import meshgen as mg, sharded
+from oracle import oracle as O
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+g = 64
+mesh = mg.icosphere(3)
+codes = O.voxelize(mesh.tris, mesh.length, g)            # P == 1: one partition, all triangles
+p = sharded.plan(g, 1, world, rank)
+mine = sharded.subtree_table_from_codes(codes, g, p)
+t = torch.from_numpy(mine.copy())
+dist.all_reduce(t)                                       # the one exchange of the sharded build
+merged = t.numpy()
+# every rank must now be able to derive the global counts
+D, J = p.depth, p.top_local_level
+dr = D - 2 * (J + 1)
+keys = np.flatnonzero(merged[0::4])
+n_nodes = int(merged[1::4].sum())
+for d in range(0, dr + 1):
+    n_nodes += np.unique(keys >> (3 * (dr - d))).size
+want = O.build(mesh.tris, mesh.length, g)
+ok = (n_nodes == want.n_nodes) and (int(merged[2::4].sum()) == want.n_voxels)
+own = (np.flatnonzero(mine[0::4]) >= p.own_entries[0]).all() and (np.flatnonzero(mine[0::4]) < p.own_entries[1]).all()
+gathered = [None] * world
+dist.all_gather_object(gathered, mine)
+if rank == 0:
+    ref = sharded.merge_tables(gathered)
+    print(json.dumps({{"ok": bool(ok and own and (ref == merged).all()), "n_nodes": n_nodes, "want": want.n_nodes}}))
+dist.destroy_process_group()
+"""
+
+
+def test_table_exchange_gloo_world2(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER.format(root=ROOT))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29611", str(script)], capture_output=True, text=True, timeout=300, env=env, cwd=ROOT)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    line = [l for l in p.stdout.splitlines() if l.startswith("{")][-1]
+    import json
+    r = json.loads(line)
+    assert r["ok"], r
+
+
+def test_node_count_closed_form(oracle):
+    # n_nodes = 1 + number of distinct Morton prefixes over all depths
+    m = mg.random_soup(400, seed=8)
+    codes = oracle.voxelize(m.tris, m.length, 128)
+    assert sharded.node_count_from_codes(codes, 128) == oracle.build(m.tris, m.length, 128).n_nodes
