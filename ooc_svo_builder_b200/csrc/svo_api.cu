@@ -229,8 +229,11 @@ VoxJob make_voxjob(svo_ctx* c) {
     J.queue[0] = c->queue[0].as<ull>();
     J.queue[1] = c->queue[1].as<ull>();
     J.qcount = c->qcount.as<ull>();
-    J.small_max = 128;
+    J.small_max = 256;
     J.medium_max = 32768;
+    J.small_windows = 4;
+    if (const char* e = getenv("SVO_SMALL_WINDOWS")) J.small_windows = (unsigned)strtoul(e, nullptr, 10);
+    J.tilemask = c->lv[0].mask.as<ull>();
     if (const char* e = getenv("SVO_SMALL_MAX")) J.small_max = strtoull(e, nullptr, 10);
     if (const char* e = getenv("SVO_MEDIUM_MAX")) J.medium_max = strtoull(e, nullptr, 10);
     J.tileidx = c->tileidx.p ? c->tileidx.as<uint32_t>() - c->bias[0] : nullptr;
@@ -643,7 +646,7 @@ static int build_phase_a(svo_ctx* c, ull* table) {
     // ---- top-down: compact tile lists ----
     if (c->lv[J].n) {
         k_compact_top<<<1, 1024, 0, c->stream>>>(c->dense[J].as<ull>(), c->nwords[J], c->bias[J], c->lv[J].key.as<ull>(), c->lv[J].mask.as<ull>(),
-                                                (payload && J == 0) ? c->tileidx.as<uint32_t>() : nullptr); LAUNCHED();
+                                                (payload && J == 0) ? c->tileidx.as<uint32_t>() : nullptr, J == 0 ? 1 : 0); LAUNCHED();
     }
     for (int j = J; j >= 0; j--) {
         PopcOp op{ c->lv[j].mask.as<ull>() };
@@ -652,7 +655,7 @@ static int build_phase_a(svo_ctx* c, ull* table) {
         if (j > 0 && c->lv[j].n) {
             k_expand<<<blocks_for(c->lv[j].n, WARPS_PER_BLOCK), WARPS_PER_BLOCK * 32, 0, c->stream>>>(
                 c->lv[j].view(), c->lv[j - 1].view(), c->dense[j - 1].as<ull>() - c->bias[j - 1],
-                (payload && j == 1) ? c->tileidx.as<uint32_t>() - c->bias[0] : nullptr); LAUNCHED();
+                (payload && j == 1) ? c->tileidx.as<uint32_t>() - c->bias[0] : nullptr, j == 1 ? 1 : 0); LAUNCHED();
         }
     }
     // ---- bottom-up: subtree sizes (+ leaf / internal counts) ----
@@ -724,14 +727,14 @@ static int build_phase_b(svo_ctx* c, const ull* table) {
         if (rc) return rc;
         // ---- upper compact lists (tiny), ending in the GLOBAL level-J list ----
         for (int j = top; j > J; j--) {
-            if (c->lv[j].n) { k_compact_top<<<1, 1024, 0, c->stream>>>(c->dense[j].as<ull>(), c->nwords[j], 0, c->lv[j].key.as<ull>(), c->lv[j].mask.as<ull>(), nullptr); LAUNCHED(); }
+            if (c->lv[j].n) { k_compact_top<<<1, 1024, 0, c->stream>>>(c->dense[j].as<ull>(), c->nwords[j], 0, c->lv[j].key.as<ull>(), c->lv[j].mask.as<ull>(), nullptr, 0); LAUNCHED(); }
         }
         for (int j = top; j > J; j--) {
             PopcOp op{ c->lv[j].mask.as<ull>() };
             if ((rc = exscan(c, op, c->lv[j].n, c->lv[j].fc.as<ull>()))) return rc;
         }
         // global level-J list: keys and masks from the dense mask column, in key order
-        if (c->glv.n) { k_compact_top<<<1, 1024, 0, c->stream>>>(c->dcol[0].as<ull>(), c->WJ, 0, c->glv.key.as<ull>(), c->glv.mask.as<ull>(), nullptr); LAUNCHED(); }
+        if (c->glv.n) { k_compact_top<<<1, 1024, 0, c->stream>>>(c->dcol[0].as<ull>(), c->WJ, 0, c->glv.key.as<ull>(), c->glv.mask.as<ull>(), nullptr, 0); LAUNCHED(); }
         {
             DenseColOp sop{ c->dcol[1].as<ull>(), c->glv.key.as<ull>() };
             if ((rc = exscan(c, sop, c->glv.n, c->glv.ps.as<ull>()))) return rc;

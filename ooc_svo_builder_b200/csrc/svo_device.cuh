@@ -200,6 +200,116 @@ __device__ __forceinline__ bool box_may_pass(const TriSetup& s, float u,
     return true;
 }
 
+// During voxelization a brick word uses the LINEAR in-brick layout (bit = z*16 + y*4 + x): box-aligned
+// windows can then be split into bricks with plain shifts. The octree wants the Morton layout (a byte =
+// one 2x2x2 child); the permutation is applied once per occupied brick when the tile lists are built.
+__host__ __device__ __forceinline__ uint64_t linear_to_morton64(uint64_t w) {
+    uint64_t t;
+    t = ((w >> 2) ^ w) & 0x0C0C0C0C0C0C0C0CULL;  w ^= t ^ (t << 2);     // swap index bits 1,2
+    t = ((w >> 12) ^ w) & 0x0000F0F00000F0F0ULL; w ^= t ^ (t << 12);    // swap index bits 2,4
+    t = ((w >> 8) ^ w) & 0x0000FF000000FF00ULL;  w ^= t ^ (t << 8);     // swap index bits 3,4
+    return w;
+}
+__host__ __device__ __forceinline__ int linear_to_morton_bit(int i) { return brick_bit(i & 3, (i >> 2) & 3, i >> 4); }
+
+// Conservative test of a whole 4x4x4 window of voxels anchored at (wx, wy, wz), branch free.
+// Returns the hit mask in the linear layout (bit = lz*16 + ly*4 + lx), restricted to the extents
+// (ea, eb, ec) <= 4 of the box inside the window. The nine edge functions only depend on two
+// coordinates each, so they are evaluated on three 4x4 projections (products hoisted per axis) and
+// expanded with multiplies; every rounded operation is the one the per-voxel test performs.
+__device__ __forceinline__ uint64_t eval_window(const TriSetup& s, float u, int wx, int wy, int wz, int ea, int eb, int ec) {
+    float px[4], py[4], pz[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        px[i] = fmul((float)(wx + i), u);
+        py[i] = fmul((float)(wy + i), u);
+        pz[i] = fmul((float)(wz + i), u);
+    }
+    uint32_t mxy = 0, myz = 0, mzx = 0;
+    {   // XY: edges 0..2, a = x, b = y; bit ly*4 + lx
+        float A[3][4], B[3][4];
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+#pragma unroll
+            for (int i = 0; i < 4; i++) { A[j][i] = fmul(s.ea[j], px[i]); B[j][i] = fmul(s.eb[j], py[i]); }
+#pragma unroll
+        for (int ly = 0; ly < 4; ly++)
+#pragma unroll
+            for (int lx = 0; lx < 4; lx++) {
+                const bool p = !(fadd(fadd(A[0][lx], B[0][ly]), s.ed[0]) < 0.0f) & !(fadd(fadd(A[1][lx], B[1][ly]), s.ed[1]) < 0.0f) &
+                               !(fadd(fadd(A[2][lx], B[2][ly]), s.ed[2]) < 0.0f);
+                mxy |= (uint32_t)p << (ly * 4 + lx);
+            }
+    }
+    {   // YZ: edges 3..5, a = y, b = z; bit lz*4 + ly
+        float A[3][4], B[3][4];
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+#pragma unroll
+            for (int i = 0; i < 4; i++) { A[j][i] = fmul(s.ea[3 + j], py[i]); B[j][i] = fmul(s.eb[3 + j], pz[i]); }
+#pragma unroll
+        for (int lz = 0; lz < 4; lz++)
+#pragma unroll
+            for (int ly = 0; ly < 4; ly++) {
+                const bool p = !(fadd(fadd(A[0][ly], B[0][lz]), s.ed[3]) < 0.0f) & !(fadd(fadd(A[1][ly], B[1][lz]), s.ed[4]) < 0.0f) &
+                               !(fadd(fadd(A[2][ly], B[2][lz]), s.ed[5]) < 0.0f);
+                myz |= (uint32_t)p << (lz * 4 + ly);
+            }
+    }
+    {   // ZX: edges 6..8, a = z, b = x; bit lz*4 + lx
+        float A[3][4], B[3][4];
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+#pragma unroll
+            for (int i = 0; i < 4; i++) { A[j][i] = fmul(s.ea[6 + j], pz[i]); B[j][i] = fmul(s.eb[6 + j], px[i]); }
+#pragma unroll
+        for (int lz = 0; lz < 4; lz++)
+#pragma unroll
+            for (int lx = 0; lx < 4; lx++) {
+                const bool p = !(fadd(fadd(A[0][lz], B[0][lx]), s.ed[6]) < 0.0f) & !(fadd(fadd(A[1][lz], B[1][lx]), s.ed[7]) < 0.0f) &
+                               !(fadd(fadd(A[2][lz], B[2][lx]), s.ed[8]) < 0.0f);
+                mzx |= (uint32_t)p << (lz * 4 + lx);
+            }
+    }
+    // expand the projections to the 64 voxels and restrict to the box
+    uint64_t cand = (uint64_t)mxy * 0x0001000100010001ULL;
+    {
+        uint64_t x = myz;                                   // bit k -> nibble k
+        x = (x | x << 24) & 0x000000FF000000FFULL;
+        x = (x | x << 12) & 0x000F000F000F000FULL;
+        x = (x | x << 6) & 0x0303030303030303ULL;
+        x = (x | x << 3) & 0x1111111111111111ULL;
+        cand &= x * 0xFULL;
+        uint64_t y = mzx;                                   // nibble lz -> 16-bit slice lz, repeated over ly
+        y = (y | y << 24) & 0x000000FF000000FFULL;
+        y = (y | y << 12) & 0x000F000F000F000FULL;
+        cand &= y * 0x1111ULL;
+    }
+    cand &= (uint64_t)((1u << ea) - 1u) * 0x1111111111111111ULL;
+    cand &= (uint64_t)((1u << (4 * eb)) - 1u) * 0x0001000100010001ULL;
+    cand &= lowmask(16 * ec);
+    if (cand == 0ULL) return 0ULL;
+    // plane test (voxelizer.cpp:266-268): n.p summed x, then y, then z, exactly like dot3
+    float nxp[4], nyp[4], nzp[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) { nxp[i] = fmul(s.nx, px[i]); nyp[i] = fmul(s.ny, py[i]); nzp[i] = fmul(s.nz, pz[i]); }
+    uint32_t plo = 0, phi = 0;
+#pragma unroll
+    for (int ly = 0; ly < 4; ly++)
+#pragma unroll
+        for (int lx = 0; lx < 4; lx++) {
+            const float sxy = fadd(nxp[lx], nyp[ly]);
+#pragma unroll
+            for (int lz = 0; lz < 4; lz++) {
+                const float nd = fadd(sxy, nzp[lz]);
+                const bool p = !(fmul(fadd(nd, s.d1), fadd(nd, s.d2)) > 0.0f);
+                const int bit = lz * 16 + ly * 4 + lx;
+                if (bit < 32) plo |= (uint32_t)p << bit; else phi |= (uint32_t)p << (bit - 32);
+            }
+        }
+    return cand & (((uint64_t)phi << 32) | plo);
+}
+
 struct GridBox { int x0, x1, y0, y1, z0, z1; };
 
 // Triangle bbox in grid coordinates, clamped INTO the partition box

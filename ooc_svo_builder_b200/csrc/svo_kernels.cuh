@@ -35,11 +35,13 @@ struct VoxJob {
     unsigned long long* queue[2];     // medium / large work queues: (part << 32 | tri)
     unsigned long long* qcount;       // [0] medium, [1] large, [2] small (statistics)
     unsigned long long small_max, medium_max;
+    unsigned small_windows;           // a small pair spans at most this many 4x4x4 windows
     // sharding: level-0 word range owned by this context and the voxel bounding box of its slab.
     // lvl[] / tileidx are biased so that they are indexed with GLOBAL word indices.
     unsigned long long w_lo, w_hi;
     int sb_lo[3], sb_hi[3];
     // payload owner pass
+    const unsigned long long* tilemask;   // compact level-0 masks (Morton layout)
     const uint32_t* tileidx;          // dense: level-0 word -> compact tile index
     const unsigned long long* leafprefix;  // exclusive popcount prefix over level-0 tiles
     uint32_t* owner;                  // per leaf: min triangle index that covers it
@@ -62,10 +64,11 @@ __device__ __forceinline__ void sink_fill(const VoxJob& J, uint64_t w, uint64_t 
 }
 // Payload owner pass: the reference's first-triangle-wins rule (voxelizer.cpp:263)
 // made order independent: owner = min triangle index over all triangles passing.
+// `bit` is the LINEAR in-brick index; leaf ranks follow the Morton order of the compact tile mask.
 __device__ __forceinline__ void sink_owner_bit(const VoxJob& J, uint64_t w, int bit, uint32_t tri) {
     if (w < J.w_lo || w >= J.w_hi) return;
-    const unsigned long long W = J.lvl[0][w];
-    const unsigned long long r = J.leafprefix[J.tileidx[w]] + __popcll(W & lowmask(bit));
+    const uint32_t t = J.tileidx[w];
+    const unsigned long long r = J.leafprefix[t] + __popcll(J.tilemask[t] & lowmask(linear_to_morton_bit(bit)));
     atomicMin(&J.owner[r], tri);
 }
 
@@ -110,6 +113,42 @@ __device__ __forceinline__ void warp_push(unsigned long long* counter, unsigned 
     if (lane == leader) base = atomicAdd(counter, (unsigned long long)__popc(m));
     base = __shfl_sync(0xffffffffu, base, leader);
     if (pred) q[base + __popc(m & ((1u << lane) - 1u))] = val;
+}
+
+// Split the hit mask of a box-aligned 4x4x4 window (linear layout) into the up to 8 bricks it straddles:
+// per axis the low part moves up by the window's offset inside the brick, the high part moves down into
+// the next brick; in the linear layout these are plain shifts once the part is masked out.
+template <bool OWNER>
+__device__ __forceinline__ void emit_window(const VoxJob& J, int wx, int wy, int wz, unsigned long long hits, uint32_t tri) {
+    const int ox = wx & 3, oy = wy & 3, oz = wz & 3;
+    const unsigned long long xlo = (unsigned long long)((1u << (4 - ox)) - 1u) * 0x1111111111111111ULL;
+    const unsigned long long ylo = (unsigned long long)((1u << (4 * (4 - oy))) - 1u) * 0x0001000100010001ULL;
+    const unsigned long long zlo = lowmask(16 * (4 - oz));
+    const uint32_t bx = (uint32_t)(wx >> 2), by = (uint32_t)(wy >> 2), bz = (uint32_t)(wz >> 2);
+    unsigned long long sx[2], sy[2], sz[2];
+    sx[0] = spread3(bx); sy[0] = spread3(by) << 1; sz[0] = spread3(bz) << 2;
+    sx[1] = ox ? spread3(bx + 1) : 0ULL; sy[1] = oy ? (spread3(by + 1) << 1) : 0ULL; sz[1] = oz ? (spread3(bz + 1) << 2) : 0ULL;
+#pragma unroll
+    for (int dz = 0; dz < 2; dz++)
+#pragma unroll
+        for (int dy = 0; dy < 2; dy++)
+#pragma unroll
+            for (int dx = 0; dx < 2; dx++) {
+                unsigned long long sub = hits & (dx ? ~xlo : xlo) & (dy ? ~ylo : ylo) & (dz ? ~zlo : zlo);
+                if (!sub) continue;
+                const int sh = (dx ? ox - 4 : ox) + 4 * (dy ? oy - 4 : oy) + 16 * (dz ? oz - 4 : oz);
+                sub = sh >= 0 ? (sub << sh) : (sub >> (-sh));
+                const uint64_t w = sx[dx] | sy[dy] | sz[dz];
+                if (!OWNER) {
+                    sink_fill(J, w, sub);
+                } else {
+                    while (sub) {
+                        const int bit = __ffsll((long long)sub) - 1;
+                        sub &= sub - 1;
+                        sink_owner_bit(J, w, bit, tri);
+                    }
+                }
+            }
 }
 
 // ---------------------------------------------------------------------------
@@ -157,7 +196,9 @@ __global__ void __launch_bounds__(VOX_BLOCK) k_vox_small(VoxJob J) {
         if (restrict_to_slab(J, b)) {
             const unsigned long long vol = (unsigned long long)(b.x1 - b.x0 + 1) * (unsigned long long)(b.y1 - b.y0 + 1) *
                                            (unsigned long long)(b.z1 - b.z0 + 1);
-            cls = vol <= J.small_max ? 0 : (vol <= J.medium_max ? 1 : 2);
+                // small = at most SMALL_WINDOWS 4x4x4 windows anchored at the box corner
+            const unsigned nw = (unsigned)((b.x1 - b.x0 + 4) >> 2) * (unsigned)((b.y1 - b.y0 + 4) >> 2) * (unsigned)((b.z1 - b.z0 + 4) >> 2);
+            cls = (vol <= J.small_max && nw <= J.small_windows) ? 0 : (vol <= J.medium_max ? 1 : 2);
         }
     }
     if (!OWNER) {
@@ -169,45 +210,12 @@ __global__ void __launch_bounds__(VOX_BLOCK) k_vox_small(VoxJob J) {
 
     TriSetup s;
     tri_setup(v, J.u, s);
-    const float u = J.u;
-    // brick-major traversal: one atomic per touched brick
-    for (int bz = b.z0 >> 2; bz <= (b.z1 >> 2); bz++) {
-        const int za = max(b.z0, bz << 2), zb = min(b.z1, (bz << 2) + 3);
-        for (int by = b.y0 >> 2; by <= (b.y1 >> 2); by++) {
-            const int ya = max(b.y0, by << 2), yb = min(b.y1, (by << 2) + 3);
-            for (int bx = b.x0 >> 2; bx <= (b.x1 >> 2); bx++) {
-                const int xa = max(b.x0, bx << 2), xb = min(b.x1, (bx << 2) + 3);
-                unsigned long long mask = 0;
-                for (int x = xa; x <= xb; x++) {
-                    const float px = fmul((float)x, u);
-                    for (int y = ya; y <= yb; y++) {
-                        const float py = fmul((float)y, u);
-                        // the XY edge functions do not depend on z: test once per column
-                        if (!edge_pass(s, 0, px, py) || !edge_pass(s, 1, px, py) || !edge_pass(s, 2, px, py)) continue;
-                        for (int z = za; z <= zb; z++) {
-                            const float pz = fmul((float)z, u);
-                            if (!plane_pass(s, px, py, pz)) continue;
-                            if (!edge_pass(s, 3, py, pz) || !edge_pass(s, 4, py, pz) || !edge_pass(s, 5, py, pz)) continue;
-                            if (!edge_pass(s, 6, pz, px) || !edge_pass(s, 7, pz, px) || !edge_pass(s, 8, pz, px)) continue;
-                            mask |= 1ULL << brick_bit(x, y, z);
-                        }
-                    }
-                }
-                if (mask) {
-                    const uint64_t w = morton3((uint32_t)bx, (uint32_t)by, (uint32_t)bz);
-                    if (!OWNER) {
-                        sink_fill(J, w, mask);
-                    } else {
-                        while (mask) {
-                            const int bit = __ffsll((long long)mask) - 1;
-                            mask &= mask - 1;
-                            sink_owner_bit(J, w, bit, tri);
-                        }
-                    }
-                }
+    for (int wz = b.z0; wz <= b.z1; wz += 4)
+        for (int wy = b.y0; wy <= b.y1; wy += 4)
+            for (int wx = b.x0; wx <= b.x1; wx += 4) {
+                const unsigned long long hits = eval_window(s, J.u, wx, wy, wz, min(4, b.x1 - wx + 1), min(4, b.y1 - wy + 1), min(4, b.z1 - wz + 1));
+                if (hits) emit_window<OWNER>(J, wx, wy, wz, hits, tri);
             }
-        }
-    }
 }
 
 // ---------------------------------------------------------------------------
@@ -225,9 +233,9 @@ __device__ __forceinline__ void warp_voxelize_box(const VoxJob& J, const TriSetu
     const unsigned long long nby = (unsigned long long)((b.y1 >> 2) - by0 + 1);
     const unsigned long long nbz = (unsigned long long)((b.z1 >> 2) - bz0 + 1);
     const unsigned long long nb = nbx * nby * nbz;
-    const int dx = (lane & 1) | ((lane >> 2) & 2);          // lane = bit index of the voxel (z bit 1 clear)
-    const int dy = ((lane >> 1) & 1) | ((lane >> 3) & 2);
-    const int dz = (lane >> 2) & 1;
+    const int dx = lane & 3;                                  // lane = LINEAR in-brick bit index z*16 + y*4 + x (lower half: z = 0, 1)
+    const int dy = (lane >> 2) & 3;
+    const int dz = lane >> 4;
     const float u = J.u;
     for (unsigned long long c = chunk0; c * 32ULL < nb; c += chunk_stride) {
         const unsigned long long bi = c * 32ULL + lane;
@@ -513,7 +521,7 @@ __global__ void __launch_bounds__(256) k_level_counts(unsigned long long* const*
 
 // Top local level: compact the non-zero words of the (small) dense level J into (key, mask). One block.
 __global__ void __launch_bounds__(1024) k_compact_top(const unsigned long long* dense, unsigned long long n, unsigned long long key_bias,
-                                                      unsigned long long* key, unsigned long long* mask, uint32_t* tileidx) {
+                                                      unsigned long long* key, unsigned long long* mask, uint32_t* tileidx, int is_level0) {
     unsigned long long carry = 0;
     for (unsigned long long b = 0; b < n; b += blockDim.x) {
         const unsigned long long idx = b + threadIdx.x;
@@ -521,7 +529,7 @@ __global__ void __launch_bounds__(1024) k_compact_top(const unsigned long long* 
         unsigned long long total;
         const unsigned long long ex = block_excl_scan(w != 0ULL ? 1ULL : 0ULL, total);
         if (w != 0ULL) {
-            key[carry + ex] = key_bias + idx; mask[carry + ex] = w;
+            key[carry + ex] = key_bias + idx; mask[carry + ex] = is_level0 ? linear_to_morton64(w) : w;
             if (tileidx) tileidx[idx] = (uint32_t)(carry + ex);     // level 0 only (payload owner pass)
         }
         carry += total;
@@ -610,7 +618,7 @@ struct InternalOp {
 // Top-down expansion: one warp per parent tile writes its children's keys and
 // gathers their words from the dense level below.
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_expand(Level parent, Level child, const unsigned long long* dense_child,
-                                                                uint32_t* tileidx) {
+                                                                uint32_t* tileidx, int child_is_level0) {
     const unsigned long long i = (unsigned long long)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
     if (i >= parent.n) return;
     const int lane = threadIdx.x & 31;
@@ -622,7 +630,8 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_expand(Level parent, L
             const unsigned long long c = fc + __popcll(W & lowmask(bit));
             const unsigned long long ck = (key << 6) | (unsigned long long)bit;
             child.key[c] = ck;
-            child.mask[c] = dense_child[ck];
+            const unsigned long long cw = dense_child[ck];
+            child.mask[c] = child_is_level0 ? linear_to_morton64(cw) : cw;     // bricks are voxelized in the linear layout
             if (tileidx) tileidx[ck] = (uint32_t)c;
         }
     }
