@@ -300,6 +300,7 @@ def ours(args):
         "config": {"workload": WORKLOAD, "gridsize": GRID, "n_triangles": T, "n_voxels": nv, "n_nodes": nn, "partitions": st["n_partitions"],
                    "l2": "flushed between timed iterations (256 MB write)", "parallelism": "1 GPU"},
         "stage_ms": {k: avg(k) for k in ("ms_partition", "ms_voxelize", "ms_vox_small", "ms_compact", "ms_build", "ms_emit", "ms_emit_leaf", "ms_clear")},
+        "pairs": {k: st[k] for k in ("n_pairs", "n_small", "n_medium", "n_large")},
         "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
         "gpu_launches": int(launches) * args.steps, "gpu_launches_per_step": int(launches),
         "clocks": clocks,

@@ -158,6 +158,10 @@ int exscan(svo_ctx* c, F f, ull n, ull* out) {
         CK(cudaMemsetAsync(out, 0, sizeof(ull), c->stream));
         return SVO_OK;
     }
+    if (n <= SCAN_SMALL_MAX) {
+        k_scan_small<<<1, 1024, 0, c->stream>>>(f, n, out); LAUNCHED();
+        return SVO_OK;
+    }
     const ull nt = (n + SCAN_TILE - 1) / SCAN_TILE;
     CK(c->scan_tmp.ensure((nt + 1) * sizeof(ull)));
     ull* tmp = c->scan_tmp.as<ull>();
@@ -229,9 +233,9 @@ VoxJob make_voxjob(svo_ctx* c) {
     J.queue[0] = c->queue[0].as<ull>();
     J.queue[1] = c->queue[1].as<ull>();
     J.qcount = c->qcount.as<ull>();
-    J.small_max = 256;
+    J.small_max = 512;
     J.medium_max = 32768;
-    J.small_windows = 4;
+    J.small_windows = 8;
     if (const char* e = getenv("SVO_SMALL_WINDOWS")) J.small_windows = (unsigned)strtoul(e, nullptr, 10);
     J.tilemask = c->lv[0].mask.as<ull>();
     if (const char* e = getenv("SVO_SMALL_MAX")) J.small_max = strtoull(e, nullptr, 10);
@@ -251,8 +255,7 @@ int launch_voxelizer(svo_ctx* c) {
     k_vox_small<OWNER><<<blocks_for(c->q_end - c->q_begin, VOX_BLOCK), VOX_BLOCK, smem, c->stream>>>(J); LAUNCHED();
     if (!OWNER) mark(c, EV_VS1);
     const unsigned grid = (unsigned)c->sm_count * 4;
-    k_vox_medium<OWNER><<<grid, WARPS_PER_BLOCK * 32, 0, c->stream>>>(J); LAUNCHED();
-    k_vox_large<OWNER><<<grid, WARPS_PER_BLOCK * 32, 0, c->stream>>>(J); LAUNCHED();
+    k_vox_queued<OWNER><<<grid, WARPS_PER_BLOCK * 32, 0, c->stream>>>(J); LAUNCHED();
     return SVO_OK;
 }
 

@@ -217,7 +217,11 @@ __host__ __device__ __forceinline__ int linear_to_morton_bit(int i) { return bri
 // (ea, eb, ec) <= 4 of the box inside the window. The nine edge functions only depend on two
 // coordinates each, so they are evaluated on three 4x4 projections (products hoisted per axis) and
 // expanded with multiplies; every rounded operation is the one the per-voxel test performs.
-__device__ __forceinline__ uint64_t eval_window(const TriSetup& s, float u, int wx, int wy, int wz, int ea, int eb, int ec) {
+// (ua, ub, uc) are WARP-UNIFORM upper bounds of (ea, eb, ec): rows / slices at or beyond them lie outside
+// every box of the warp and are skipped with uniform branches (their mask bits are don't-care: the box
+// mask clears them).
+__device__ __forceinline__ uint64_t eval_window(const TriSetup& s, float u, int wx, int wy, int wz, int ea, int eb, int ec,
+                                                int ua, int ub, int uc) {
     float px[4], py[4], pz[4];
 #pragma unroll
     for (int i = 0; i < 4; i++) {
@@ -225,7 +229,11 @@ __device__ __forceinline__ uint64_t eval_window(const TriSetup& s, float u, int 
         py[i] = fmul((float)(wy + i), u);
         pz[i] = fmul((float)(wz + i), u);
     }
-    uint32_t mxy = 0, myz = 0, mzx = 0;
+    // Mask assembly from sign bits: an edge value e = fadd(., ed) fails iff it is negative. ed is never -0
+    // (its last addend is std::max(0.0f, .) >= +0), so e is never -0, and a NaN result of a CUDA add is the
+    // canonical 0x7FFFFFFF (sign clear, like the reference's "not < 0"). So fail = sign(e0)|sign(e1)|sign(e2),
+    // pushed into the mask with one funnel shift per cell (cells visited from the highest bit down).
+    uint32_t fxy = 0, fyz = 0, fzx = 0;     // FAIL masks
     {   // XY: edges 0..2, a = x, b = y; bit ly*4 + lx
         float A[3][4], B[3][4];
 #pragma unroll
@@ -233,13 +241,15 @@ __device__ __forceinline__ uint64_t eval_window(const TriSetup& s, float u, int 
 #pragma unroll
             for (int i = 0; i < 4; i++) { A[j][i] = fmul(s.ea[j], px[i]); B[j][i] = fmul(s.eb[j], py[i]); }
 #pragma unroll
-        for (int ly = 0; ly < 4; ly++)
+        for (int ly = 3; ly >= 0; ly--) {
+            if (ly >= ub) { fxy <<= 4; continue; }
 #pragma unroll
-            for (int lx = 0; lx < 4; lx++) {
-                const bool p = !(fadd(fadd(A[0][lx], B[0][ly]), s.ed[0]) < 0.0f) & !(fadd(fadd(A[1][lx], B[1][ly]), s.ed[1]) < 0.0f) &
-                               !(fadd(fadd(A[2][lx], B[2][ly]), s.ed[2]) < 0.0f);
-                mxy |= (uint32_t)p << (ly * 4 + lx);
+            for (int lx = 3; lx >= 0; lx--) {
+                const uint32_t f = __float_as_uint(fadd(fadd(A[0][lx], B[0][ly]), s.ed[0])) | __float_as_uint(fadd(fadd(A[1][lx], B[1][ly]), s.ed[1])) |
+                                   __float_as_uint(fadd(fadd(A[2][lx], B[2][ly]), s.ed[2]));
+                fxy = __funnelshift_l(f, fxy, 1);
             }
+        }
     }
     {   // YZ: edges 3..5, a = y, b = z; bit lz*4 + ly
         float A[3][4], B[3][4];
@@ -248,13 +258,15 @@ __device__ __forceinline__ uint64_t eval_window(const TriSetup& s, float u, int 
 #pragma unroll
             for (int i = 0; i < 4; i++) { A[j][i] = fmul(s.ea[3 + j], py[i]); B[j][i] = fmul(s.eb[3 + j], pz[i]); }
 #pragma unroll
-        for (int lz = 0; lz < 4; lz++)
+        for (int lz = 3; lz >= 0; lz--) {
+            if (lz >= uc) { fyz <<= 4; continue; }
 #pragma unroll
-            for (int ly = 0; ly < 4; ly++) {
-                const bool p = !(fadd(fadd(A[0][ly], B[0][lz]), s.ed[3]) < 0.0f) & !(fadd(fadd(A[1][ly], B[1][lz]), s.ed[4]) < 0.0f) &
-                               !(fadd(fadd(A[2][ly], B[2][lz]), s.ed[5]) < 0.0f);
-                myz |= (uint32_t)p << (lz * 4 + ly);
+            for (int ly = 3; ly >= 0; ly--) {
+                const uint32_t f = __float_as_uint(fadd(fadd(A[0][ly], B[0][lz]), s.ed[3])) | __float_as_uint(fadd(fadd(A[1][ly], B[1][lz]), s.ed[4])) |
+                                   __float_as_uint(fadd(fadd(A[2][ly], B[2][lz]), s.ed[5]));
+                fyz = __funnelshift_l(f, fyz, 1);
             }
+        }
     }
     {   // ZX: edges 6..8, a = z, b = x; bit lz*4 + lx
         float A[3][4], B[3][4];
@@ -263,14 +275,17 @@ __device__ __forceinline__ uint64_t eval_window(const TriSetup& s, float u, int 
 #pragma unroll
             for (int i = 0; i < 4; i++) { A[j][i] = fmul(s.ea[6 + j], pz[i]); B[j][i] = fmul(s.eb[6 + j], px[i]); }
 #pragma unroll
-        for (int lz = 0; lz < 4; lz++)
+        for (int lz = 3; lz >= 0; lz--) {
+            if (lz >= uc) { fzx <<= 4; continue; }
 #pragma unroll
-            for (int lx = 0; lx < 4; lx++) {
-                const bool p = !(fadd(fadd(A[0][lz], B[0][lx]), s.ed[6]) < 0.0f) & !(fadd(fadd(A[1][lz], B[1][lx]), s.ed[7]) < 0.0f) &
-                               !(fadd(fadd(A[2][lz], B[2][lx]), s.ed[8]) < 0.0f);
-                mzx |= (uint32_t)p << (lz * 4 + lx);
+            for (int lx = 3; lx >= 0; lx--) {
+                const uint32_t f = __float_as_uint(fadd(fadd(A[0][lz], B[0][lx]), s.ed[6])) | __float_as_uint(fadd(fadd(A[1][lz], B[1][lx]), s.ed[7])) |
+                                   __float_as_uint(fadd(fadd(A[2][lz], B[2][lx]), s.ed[8]));
+                fzx = __funnelshift_l(f, fzx, 1);
             }
+        }
     }
+    const uint32_t mxy = ~fxy & 0xffffu, myz = ~fyz & 0xffffu, mzx = ~fzx & 0xffffu;
     // expand the projections to the 64 voxels and restrict to the box
     uint64_t cand = (uint64_t)mxy * 0x0001000100010001ULL;
     {
@@ -293,20 +308,28 @@ __device__ __forceinline__ uint64_t eval_window(const TriSetup& s, float u, int 
     float nxp[4], nyp[4], nzp[4];
 #pragma unroll
     for (int i = 0; i < 4; i++) { nxp[i] = fmul(s.nx, px[i]); nyp[i] = fmul(s.ny, py[i]); nzp[i] = fmul(s.nz, pz[i]); }
-    uint32_t plo = 0, phi = 0;
+    // reject iff fmul(a, b) > 0  <=>  sign(0 - fmul(a, b)) set (+-0 and NaN give a clear sign)
+    uint32_t rlo = 0, rhi = 0;              // REJECT masks, bit = lz*16 + ly*4 + lx
+    float sxy[4][4];
 #pragma unroll
     for (int ly = 0; ly < 4; ly++)
 #pragma unroll
-        for (int lx = 0; lx < 4; lx++) {
-            const float sxy = fadd(nxp[lx], nyp[ly]);
+        for (int lx = 0; lx < 4; lx++) sxy[ly][lx] = fadd(nxp[lx], nyp[ly]);
 #pragma unroll
-            for (int lz = 0; lz < 4; lz++) {
-                const float nd = fadd(sxy, nzp[lz]);
-                const bool p = !(fmul(fadd(nd, s.d1), fadd(nd, s.d2)) > 0.0f);
-                const int bit = lz * 16 + ly * 4 + lx;
-                if (bit < 32) plo |= (uint32_t)p << bit; else phi |= (uint32_t)p << (bit - 32);
+    for (int lz = 3; lz >= 0; lz--) {
+        if (lz >= uc) continue;                 // (a skipped slice is the top of its half: no shift needed, the bits stay clear)
+#pragma unroll
+        for (int ly = 3; ly >= 0; ly--) {
+            if (ly >= ub) { if (lz >= 2) rhi <<= 4; else rlo <<= 4; continue; }
+#pragma unroll
+            for (int lx = 3; lx >= 0; lx--) {
+                const float nd = fadd(sxy[ly][lx], nzp[lz]);
+                const uint32_t r = __float_as_uint(fsub(0.0f, fmul(fadd(nd, s.d1), fadd(nd, s.d2))));
+                if (lz >= 2) rhi = __funnelshift_l(r, rhi, 1); else rlo = __funnelshift_l(r, rlo, 1);
             }
         }
+    }
+    const uint32_t plo = ~rlo, phi = ~rhi;
     return cand & (((uint64_t)phi << 32) | plo);
 }
 

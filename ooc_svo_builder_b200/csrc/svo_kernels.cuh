@@ -17,7 +17,13 @@
 namespace svo {
 
 constexpr int MAX_LEVELS = 12;        // ceil(D/2), D <= 21 (libmorton's 21 bits per axis)
-constexpr int VOX_BLOCK = 128;        // threads per block of the small-bbox voxelizer
+#ifndef SVO_VOX_BLOCK
+#define SVO_VOX_BLOCK 128
+#endif
+#ifndef SVO_VOX_MINBLOCKS
+#define SVO_VOX_MINBLOCKS 4
+#endif
+constexpr int VOX_BLOCK = SVO_VOX_BLOCK;   // threads per block of the small-bbox voxelizer
 constexpr int WARPS_PER_BLOCK = 8;
 
 struct VoxJob {
@@ -128,27 +134,47 @@ __device__ __forceinline__ void emit_window(const VoxJob& J, int wx, int wy, int
     unsigned long long sx[2], sy[2], sz[2];
     sx[0] = spread3(bx); sy[0] = spread3(by) << 1; sz[0] = spread3(bz) << 2;
     sx[1] = ox ? spread3(bx + 1) : 0ULL; sy[1] = oy ? (spread3(by + 1) << 1) : 0ULL; sz[1] = oz ? (spread3(bz + 1) << 2) : 0ULL;
+    // phase 1: all (up to 8) brick atomics back to back, so that their round trips overlap
+    unsigned long long old[8];
+    uint64_t wi[8];
 #pragma unroll
-    for (int dz = 0; dz < 2; dz++)
-#pragma unroll
-        for (int dy = 0; dy < 2; dy++)
-#pragma unroll
-            for (int dx = 0; dx < 2; dx++) {
-                unsigned long long sub = hits & (dx ? ~xlo : xlo) & (dy ? ~ylo : ylo) & (dz ? ~zlo : zlo);
-                if (!sub) continue;
-                const int sh = (dx ? ox - 4 : ox) + 4 * (dy ? oy - 4 : oy) + 16 * (dz ? oz - 4 : oz);
-                sub = sh >= 0 ? (sub << sh) : (sub >> (-sh));
-                const uint64_t w = sx[dx] | sy[dy] | sz[dz];
-                if (!OWNER) {
-                    sink_fill(J, w, sub);
-                } else {
-                    while (sub) {
-                        const int bit = __ffsll((long long)sub) - 1;
-                        sub &= sub - 1;
-                        sink_owner_bit(J, w, bit, tri);
-                    }
+    for (int q = 0; q < 8; q++) {
+        const int dx = q & 1, dy = (q >> 1) & 1, dz = q >> 2;
+        unsigned long long sub = hits & (dx ? ~xlo : xlo) & (dy ? ~ylo : ylo) & (dz ? ~zlo : zlo);
+        old[q] = ~0ULL;
+        wi[q] = sx[dx] | sy[dy] | sz[dz];
+        if (sub) {
+            const int sh = (dx ? ox - 4 : ox) + 4 * (dy ? oy - 4 : oy) + 16 * (dz ? oz - 4 : oz);
+            sub = sh >= 0 ? (sub << sh) : (sub >> (-sh));
+            if (!OWNER) {
+                if (wi[q] >= J.w_lo && wi[q] < J.w_hi) old[q] = atomicOr(&J.lvl[0][wi[q]], sub);
+            } else {
+                while (sub) {
+                    const int bit = __ffsll((long long)sub) - 1;
+                    sub &= sub - 1;
+                    sink_owner_bit(J, wi[q], bit, tri);
                 }
             }
+        }
+    }
+    // phase 2: the thread that turned a word from zero to non-zero propagates one bit upwards (rare).
+    // The comparand is an opaque zero defined AFTER the last atomic was issued: otherwise the compiler tests
+    // each result right behind its atomic and the eight round trips serialize.
+    if (!OWNER) {
+        unsigned long long zero;
+        asm volatile("mov.u64 %0, 0;" : "=l"(zero));
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            if (old[q] == zero) {
+                uint64_t w = wi[q];
+                for (int j = 1; j < J.nl; j++) {
+                    const unsigned long long bit = 1ULL << (w & 63);
+                    w >>= 6;
+                    if (atomicOr(&J.lvl[j][w], bit) != 0ULL) break;
+                }
+            }
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -159,7 +185,7 @@ __device__ __forceinline__ void emit_window(const VoxJob& J, int wx, int wy, int
 // memory with float4 loads; gathered lists read the vertices directly.
 // ---------------------------------------------------------------------------
 template <bool OWNER>
-__global__ void __launch_bounds__(VOX_BLOCK) k_vox_small(VoxJob J) {
+__global__ void __launch_bounds__(VOX_BLOCK, SVO_VOX_MINBLOCKS) k_vox_small(VoxJob J) {
     extern __shared__ float4 s_stage4[];
     float* s_stage = reinterpret_cast<float*>(s_stage4);
     const uint64_t q0 = J.q_begin + (uint64_t)blockIdx.x * VOX_BLOCK;
@@ -206,6 +232,10 @@ __global__ void __launch_bounds__(VOX_BLOCK) k_vox_small(VoxJob J) {
         warp_push(&J.qcount[0], J.queue[0], cls == 1, e);
         warp_push(&J.qcount[1], J.queue[1], cls == 2, e);
     }
+    // warp-uniform upper bounds of the window extents (convergent point: every lane is still here)
+    const int ua = min(4, __reduce_max_sync(0xffffffffu, cls == 0 ? b.x1 - b.x0 + 1 : 0));
+    const int ub = min(4, __reduce_max_sync(0xffffffffu, cls == 0 ? b.y1 - b.y0 + 1 : 0));
+    const int uc = min(4, __reduce_max_sync(0xffffffffu, cls == 0 ? b.z1 - b.z0 + 1 : 0));
     if (cls != 0) return;
 
     TriSetup s;
@@ -213,7 +243,8 @@ __global__ void __launch_bounds__(VOX_BLOCK) k_vox_small(VoxJob J) {
     for (int wz = b.z0; wz <= b.z1; wz += 4)
         for (int wy = b.y0; wy <= b.y1; wy += 4)
             for (int wx = b.x0; wx <= b.x1; wx += 4) {
-                const unsigned long long hits = eval_window(s, J.u, wx, wy, wz, min(4, b.x1 - wx + 1), min(4, b.y1 - wy + 1), min(4, b.z1 - wz + 1));
+                const unsigned long long hits = eval_window(s, J.u, wx, wy, wz, min(4, b.x1 - wx + 1), min(4, b.y1 - wy + 1), min(4, b.z1 - wz + 1),
+                                                            ua, ub, uc);
                 if (hits) emit_window<OWNER>(J, wx, wy, wz, hits, tri);
             }
 }
@@ -303,7 +334,7 @@ __device__ __forceinline__ void queued_pair_setup(const VoxJob& J, unsigned long
 }
 
 template <bool OWNER>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_vox_medium(VoxJob J) {
+__device__ __forceinline__ void vox_medium_body(const VoxJob& J) {
     const unsigned long long n = J.qcount[0];
     const unsigned long long nwarps = (unsigned long long)gridDim.x * WARPS_PER_BLOCK;
     for (unsigned long long e = (unsigned long long)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5); e < n; e += nwarps) {
@@ -314,7 +345,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_vox_medium(VoxJob J) {
 }
 
 template <bool OWNER>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_vox_large(VoxJob J) {
+__device__ __forceinline__ void vox_large_body(const VoxJob& J) {
     const unsigned long long n = J.qcount[1];
     const unsigned long long nwarps = (unsigned long long)gridDim.x * WARPS_PER_BLOCK;
     const unsigned long long gw = (unsigned long long)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
@@ -323,6 +354,13 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_vox_large(VoxJob J) {
         queued_pair_setup(J, J.queue[1][e], tri, s, b);
         warp_voxelize_box<OWNER>(J, s, b, tri, gw, nwarps);
     }
+}
+
+// one launch for both queues (they are usually short or empty)
+template <bool OWNER>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_vox_queued(VoxJob J) {
+    vox_medium_body<OWNER>(J);
+    vox_large_body<OWNER>(J);
 }
 
 // ---------------------------------------------------------------------------
@@ -482,6 +520,22 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_final(F f, unsigned long 
         run += v[i];
     }
     if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) out[n] = tile_sums[gridDim.x];
+}
+
+// Small inputs (the upper pyramid levels): the whole exclusive scan in ONE block / one launch.
+constexpr unsigned long long SCAN_SMALL_MAX = 16384;
+template <class F>
+__global__ void __launch_bounds__(1024) k_scan_small(F f, unsigned long long n, unsigned long long* out) {
+    unsigned long long carry = 0;
+    for (unsigned long long b = 0; b < n; b += blockDim.x) {
+        const unsigned long long idx = b + threadIdx.x;
+        const unsigned long long v = idx < n ? f(idx) : 0ULL;
+        unsigned long long total;
+        const unsigned long long ex = block_excl_scan(v, total);
+        if (idx < n) out[idx] = carry + ex;
+        carry += total;
+    }
+    if (threadIdx.x == 0) out[n] = carry;
 }
 
 // ---------------------------------------------------------------------------
