@@ -215,7 +215,7 @@ def ours(args):
         sb.set_triangles(d_tris)
 
         def step():
-            sb.partition(prm)
+            sb.partition(prm, want_counts=False)
             sb.voxelize()
             return sb.build()
 

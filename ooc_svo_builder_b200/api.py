@@ -221,12 +221,16 @@ class SvoBuilder:
             self._keep = tris
             self._ck(self._lib.svo_set_triangles_device(self._h, tris.data_ptr(), tris.shape[0], tris.shape[1]))
 
-    def partition(self, params: Params) -> np.ndarray:
-        """partitioner.cpp:101-149 → per-partition triangle counts."""
+    def partition(self, params: Params, want_counts: bool = True) -> np.ndarray | None:
+        """partitioner.cpp:101-149 → per-partition triangle counts (the .trip header values).
+        want_counts=False skips the counting pass: the voxelizer enumerates partitions inline."""
         self.params = params
         P = estimate_partitions(params.gridsize, params.memory_limit_mb)
-        counts = np.zeros(P, dtype=np.uint64)
         n = C.c_uint64()
+        if not want_counts:
+            self._ck(self._lib.svo_partition(self._h, C.byref(params), C.byref(n), None, 0))
+            return None
+        counts = np.zeros(P, dtype=np.uint64)
         self._ck(self._lib.svo_partition(self._h, C.byref(params), C.byref(n), counts.ctypes.data, P))
         assert n.value == P
         return counts
@@ -301,7 +305,7 @@ class SvoBuilder:
         payload = tris.shape[1] == 21
         prm = self.make_params(length, gridsize, payload, memory_limit_mb, levels, color)
         self.set_triangles(tris)
-        self.partition(prm)
+        self.partition(prm, want_counts=False)
         self.voxelize()
         nv, nn, nd = self.build()
         if fetch:

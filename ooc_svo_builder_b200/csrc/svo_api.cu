@@ -104,8 +104,11 @@ struct svo_ctx {
     ull c0 = 0, c1 = 1, slab_start = 0, slab_end = 0, WJ = 1;
     ull bias[MAX_LEVELS];
     int sb_lo[3], sb_hi[3];
-    ull q_begin = 0, q_end = 0;
+    ull q_begin = 0, q_end = 0, qcap = 1;
     bool want_pl = false, phase_a_done = false;
+    bool use_lists = false;            // SVO_PARTITION_LISTS=1: build per-partition index lists (count / scan / fill)
+    float slab_min[32], slab_max[32];  // world slabs of the partition grid (partitioner.cpp:54-59)
+    ull p_first = 0, p_last = 0;
     DevBuf table_own, dcol[4];
     LevelBufs glv;                     // global level-J tile list (sharded / odd depth)
     std::vector<ull> h_table;
@@ -217,8 +220,12 @@ VoxJob make_voxjob(svo_ctx* c) {
     J.fpt = (uint32_t)c->fpt;
     J.q_begin = c->q_begin;
     J.q_end = c->q_end;
-    J.pair_tri = c->P == 1 ? nullptr : c->pair_tri.as<uint32_t>();
-    J.part_off = c->P == 1 ? nullptr : c->part_off.as<uint64_t>();
+    const bool lists = c->P > 1 && c->use_lists;
+    J.pair_tri = lists ? c->pair_tri.as<uint32_t>() : nullptr;
+    J.part_off = lists ? c->part_off.as<uint64_t>() : nullptr;
+    for (int i = 0; i < 32; i++) { J.bmin[i] = c->slab_min[i]; J.bmax[i] = c->slab_max[i]; }
+    J.p_first = (uint32_t)c->p_first; J.p_last = (uint32_t)c->p_last;
+    J.qcap = c->qcap;
     J.P = (uint32_t)c->P;
     J.k = (uint32_t)c->k;
     J.side = c->side;
@@ -252,7 +259,8 @@ int launch_voxelizer(svo_ctx* c) {
     VoxJob J = make_voxjob(c);
     const size_t smem = J.pair_tri ? 0 : (size_t)VOX_BLOCK * c->fpt * sizeof(float);
     if (!OWNER) mark(c, EV_VS0);
-    k_vox_small<OWNER><<<blocks_for(c->q_end - c->q_begin, VOX_BLOCK), VOX_BLOCK, smem, c->stream>>>(J); LAUNCHED();
+    if (J.pair_tri == nullptr && J.P > 1) { k_vox_small<OWNER, true><<<blocks_for(c->q_end - c->q_begin, VOX_BLOCK), VOX_BLOCK, smem, c->stream>>>(J); LAUNCHED(); }
+    else { k_vox_small<OWNER, false><<<blocks_for(c->q_end - c->q_begin, VOX_BLOCK), VOX_BLOCK, smem, c->stream>>>(J); LAUNCHED(); }
     if (!OWNER) mark(c, EV_VS1);
     const unsigned grid = (unsigned)c->sm_count * 4;
     k_vox_queued<OWNER><<<grid, WARPS_PER_BLOCK * 32, 0, c->stream>>>(J); LAUNCHED();
@@ -457,30 +465,39 @@ int svo_partition(svo_ctx* c, const svo_params* params, uint64_t* n_partitions, 
         B.tris = c->d_tris; B.fpt = (uint32_t)c->fpt; B.n_tris = c->n_tris; B.k = (uint32_t)c->k; B.P = (uint32_t)c->P;
         const float unit_part = (params->bbox_max0 - params->bbox_min0) / (float)g;   // partitioner.cpp:45
         for (uint32_t i = 0; i < (1u << c->k); i++) {
-            B.bmin[i] = (float)(uint32_t)(i * c->side) * unit_part;                    // :54-56
-            B.bmax[i] = (float)(uint32_t)((i + 1) * c->side - 1 + 1u) * unit_part;     // :57-59
+            c->slab_min[i] = B.bmin[i] = (float)(uint32_t)(i * c->side) * unit_part;                    // :54-56
+            c->slab_max[i] = B.bmax[i] = (float)(uint32_t)((i + 1) * c->side - 1 + 1u) * unit_part;     // :57-59
         }
-        CK(c->part_counts.ensure(c->P * sizeof(ull)));
-        CK(c->part_cursor.ensure(c->P * sizeof(ull)));
-        CK(c->part_off.ensure((c->P + 1) * sizeof(ull)));
-        CK(cudaMemsetAsync(c->part_counts.p, 0, c->P * sizeof(ull), c->stream));
-        CK(cudaMemsetAsync(c->part_cursor.p, 0, c->P * sizeof(ull), c->stream));
-        B.counts = c->part_counts.as<ull>(); B.cursor = c->part_cursor.as<ull>(); B.off = c->part_off.as<ull>();
-        if (c->n_tris) {
-            const size_t smem = c->P <= 4096 ? c->P * sizeof(unsigned) : 0;
-            k_bin<false><<<blocks_for(c->n_tris, 256), 256, smem, c->stream>>>(B); LAUNCHED();
+        const char* lists_env = getenv("SVO_PARTITION_LISTS");
+        c->use_lists = lists_env && lists_env[0] == '1';
+        c->n_pairs = 0;
+        // Default: the voxelizer enumerates each triangle's partitions inline (no lists, no read-back). The
+        // per-partition counts (what the reference writes to the .trip header) are computed only on request.
+        if (c->use_lists || part_tricounts) {
+            CK(c->part_counts.ensure(c->P * sizeof(ull)));
+            CK(c->part_cursor.ensure(c->P * sizeof(ull)));
+            CK(c->part_off.ensure((c->P + 1) * sizeof(ull)));
+            CK(cudaMemsetAsync(c->part_counts.p, 0, c->P * sizeof(ull), c->stream));
+            CK(cudaMemsetAsync(c->part_cursor.p, 0, c->P * sizeof(ull), c->stream));
+            B.counts = c->part_counts.as<ull>(); B.cursor = c->part_cursor.as<ull>(); B.off = c->part_off.as<ull>();
+            if (c->n_tris) {
+                const size_t smem = c->P <= 4096 ? c->P * sizeof(unsigned) : 0;
+                k_bin<false><<<blocks_for(c->n_tris, 256), 256, smem, c->stream>>>(B); LAUNCHED();
+            }
+            CountOp op{ c->part_counts.as<ull>() };
+            rc = exscan(c, op, c->P, c->part_off.as<ull>());
+            if (rc) return rc;
+            std::vector<ull> off(c->P + 1);
+            CK(cudaMemcpyAsync(off.data(), c->part_off.p, (c->P + 1) * sizeof(ull), cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+            for (uint64_t i = 0; i < c->P; i++) c->h_part_counts[i] = off[i + 1] - off[i];
+            c->n_pairs = off[c->P];
+            if (c->use_lists) {
+                CK(c->pair_tri.ensure((c->n_pairs ? c->n_pairs : 1) * sizeof(uint32_t)));
+                B.pair_tri = c->pair_tri.as<uint32_t>();
+                if (c->n_tris) { k_bin<true><<<blocks_for(c->n_tris, 256), 256, 0, c->stream>>>(B); LAUNCHED(); }
+            }
         }
-        CountOp op{ c->part_counts.as<ull>() };
-        rc = exscan(c, op, c->P, c->part_off.as<ull>());
-        if (rc) return rc;
-        std::vector<ull> off(c->P + 1);
-        CK(cudaMemcpyAsync(off.data(), c->part_off.p, (c->P + 1) * sizeof(ull), cudaMemcpyDeviceToHost, c->stream));
-        CK(cudaStreamSynchronize(c->stream));
-        for (uint64_t i = 0; i < c->P; i++) c->h_part_counts[i] = off[i + 1] - off[i];
-        c->n_pairs = off[c->P];
-        CK(c->pair_tri.ensure((c->n_pairs ? c->n_pairs : 1) * sizeof(uint32_t)));
-        B.pair_tri = c->pair_tri.as<uint32_t>();
-        if (c->n_tris) { k_bin<true><<<blocks_for(c->n_tris, 256), 256, 0, c->stream>>>(B); LAUNCHED(); }
     }
     mark(c, EV_PART1);
     rc = setup_geometry(c);
@@ -554,17 +571,21 @@ static int setup_geometry(svo_ctx* c) {
             }
         }
     }
-    // pairs of the partitions that intersect the slab
-    if (c->P == 1 || c->world == 1) { c->q_begin = 0; c->q_end = c->n_pairs; }
-    else {
+    // logical partitions that intersect the slab, and the work items this context walks
+    c->p_first = 0; c->p_last = c->P - 1;
+    if (c->world > 1 && c->P > 1) {
         const int sh = 3 * (dc - c->k);
-        const ull p_first = c->c0 >> sh, p_last = (c->c1 - 1) >> sh;
+        c->p_first = c->c0 >> sh; c->p_last = (c->c1 - 1) >> sh;
+    }
+    const bool lists = c->P > 1 && c->use_lists;
+    if (!lists) { c->q_begin = 0; c->q_end = c->n_tris; }        // one thread per triangle, partitions enumerated inline
+    else {
         ull acc = 0;
         c->q_begin = c->q_end = 0;
         for (ull p = 0; p < c->P; p++) {
-            if (p == p_first) c->q_begin = acc;
+            if (p == c->p_first) c->q_begin = acc;
             acc += c->h_part_counts[p];
-            if (p == p_last) c->q_end = acc;
+            if (p == c->p_last) c->q_end = acc;
         }
     }
     return SVO_OK;
@@ -578,8 +599,11 @@ int svo_voxelize(svo_ctx* c) {
     if (rc) return rc;
     CK(c->qcount.ensure(4 * sizeof(ull)));
     CK(cudaMemsetAsync(c->qcount.p, 0, 4 * sizeof(ull), c->stream));
+    // queue capacity: exact with lists; with inline enumeration a triangle may appear once per partition it
+    // touches, so leave headroom and detect overflow (qcount[3]) instead of trusting a bound
     const ull npairs = c->q_end - c->q_begin;
-    const size_t qbytes = (npairs ? npairs : 1) * sizeof(ull);
+    c->qcap = (c->P > 1 && !c->use_lists) ? npairs + npairs / 2 + (1u << 20) : (npairs ? npairs : 1);
+    const size_t qbytes = (size_t)c->qcap * sizeof(ull);
     CK(c->queue[0].ensure(qbytes));
     CK(c->queue[1].ensure(qbytes));
     mark(c, EV_VOX0);
@@ -636,7 +660,7 @@ static int build_phase_a(svo_ctx* c, ull* table) {
     // ---- sync #1: how many non-zero words does every local level hold? ----
     CK(cudaMemsetAsync(c->d_counts.p, 0, MAX_LEVELS * sizeof(ull), c->stream));
     {
-        dim3 grid(64, (unsigned)(J + 1));
+        dim3 grid((unsigned)c->sm_count * 4, (unsigned)(J + 1));
         k_level_counts<<<grid, 256, 0, c->stream>>>((ull* const*)c->d_lvlptrs.p, c->d_nwords.as<ull>(), J, c->d_counts.as<ull>()); LAUNCHED();
     }
     CK(cudaMemcpyAsync(c->h_pinned, c->d_counts.p, MAX_LEVELS * sizeof(ull), cudaMemcpyDeviceToHost, c->stream));
@@ -893,11 +917,17 @@ static int build_phase_b(svo_ctx* c, const ull* table) {
     c->dense_clean = true;
     mark(c, EV_CLR1);
     // queue statistics
-    CK(cudaMemcpyAsync(c->h_pinned + 40, c->qcount.p, 2 * sizeof(ull), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(c->h_pinned + 40, c->qcount.p, 4 * sizeof(ull), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
-    c->built = true;
     c->phase_a_done = false;
-    c->stats.n_partitions = c->P; c->stats.n_pairs = c->q_end - c->q_begin;
+    if (c->h_pinned[43]) {
+        c->dense_clean = false;
+        return fail(c, SVO_E_NOMEM, "work queue overflow: too many medium/large triangle-partition pairs for inline enumeration; "
+                                    "set SVO_PARTITION_LISTS=1 to build exact per-partition lists");
+    }
+    c->built = true;
+    c->stats.n_partitions = c->P;
+    c->stats.n_pairs = (c->P > 1 && !c->use_lists) ? c->h_pinned[42] : c->q_end - c->q_begin;
     c->stats.n_voxels = c->n_voxels; c->stats.n_nodes = c->n_nodes; c->stats.n_data = c->n_data;
     c->stats.n_medium = c->h_pinned[40]; c->stats.n_large = c->h_pinned[41];
     c->stats.n_small = c->stats.n_pairs - c->stats.n_medium - c->stats.n_large;

@@ -39,9 +39,14 @@ struct VoxJob {
     int nl;                           // pyramid levels
     unsigned long long* lvl[MAX_LEVELS];
     unsigned long long* queue[2];     // medium / large work queues: (part << 32 | tri)
-    unsigned long long* qcount;       // [0] medium, [1] large, [2] small (statistics)
+    unsigned long long* qcount;       // [0] medium, [1] large, [2] pairs seen (inline mode), [3] queue overflow flag
     unsigned long long small_max, medium_max;
     unsigned small_windows;           // a small pair spans at most this many 4x4x4 windows
+    unsigned long long qcap;          // capacity of each work queue (entries); overflow sets qcount[3]
+    // inline partition enumeration (pair_tri == NULL, P > 1): world slabs of the partition grid and the
+    // Morton range of partitions this context owns
+    float bmin[32], bmax[32];
+    uint32_t p_first, p_last;
     // sharding: level-0 word range owned by this context and the voxel bounding box of its slab.
     // lvl[] / tileidx are biased so that they are indexed with GLOBAL word indices.
     unsigned long long w_lo, w_hi;
@@ -109,8 +114,18 @@ __device__ __forceinline__ bool restrict_to_slab(const VoxJob& J, GridBox& b) {
     return b.x0 <= b.x1 && b.y0 <= b.y1 && b.z0 <= b.z1;
 }
 
+// Partition slabs touched by the interval [mn, mx]: slab i is kept unless (mx < bmin[i]) or (mn > bmax[i])
+// (intersectBoxBox, intersection.h:50-53, per axis). The kept slabs form a contiguous range [lo, hi].
+__device__ __forceinline__ void slab_range(const float* bmin, const float* bmax, int n, float mn, float mx, int& lo, int& hi) {
+    lo = n; hi = -1;
+    for (int i = 0; i < n; i++) {
+        if (!(mx < bmin[i]) && !(mn > bmax[i])) { if (i < lo) lo = i; hi = i; }
+    }
+}
+
 // Warp-aggregated queue push; must be called by all 32 lanes.
-__device__ __forceinline__ void warp_push(unsigned long long* counter, unsigned long long* q, bool pred, unsigned long long val) {
+__device__ __forceinline__ void warp_push(unsigned long long* counter, unsigned long long* q, unsigned long long cap,
+                                          unsigned long long* overflow, bool pred, unsigned long long val) {
     const unsigned m = __ballot_sync(0xffffffffu, pred);
     if (m == 0) return;
     const int lane = threadIdx.x & 31;
@@ -118,7 +133,10 @@ __device__ __forceinline__ void warp_push(unsigned long long* counter, unsigned 
     unsigned long long base = 0;
     if (lane == leader) base = atomicAdd(counter, (unsigned long long)__popc(m));
     base = __shfl_sync(0xffffffffu, base, leader);
-    if (pred) q[base + __popc(m & ((1u << lane) - 1u))] = val;
+    if (pred) {
+        const unsigned long long at = base + __popc(m & ((1u << lane) - 1u));
+        if (at < cap) q[at] = val; else *overflow = 1ULL;
+    }
 }
 
 // Split the hit mask of a box-aligned 4x4x4 window (linear layout) into the up to 8 bricks it straddles:
@@ -184,7 +202,7 @@ __device__ __forceinline__ void emit_window(const VoxJob& J, int wx, int wy, int
 // Identity lists (P == 1) stage the block's triangle records through shared
 // memory with float4 loads; gathered lists read the vertices directly.
 // ---------------------------------------------------------------------------
-template <bool OWNER>
+template <bool OWNER, bool ENUM>
 __global__ void __launch_bounds__(VOX_BLOCK, SVO_VOX_MINBLOCKS) k_vox_small(VoxJob J) {
     extern __shared__ float4 s_stage4[];
     float* s_stage = reinterpret_cast<float*>(s_stage4);
@@ -213,40 +231,70 @@ __global__ void __launch_bounds__(VOX_BLOCK, SVO_VOX_MINBLOCKS) k_vox_small(VoxJ
         part = pair_partition(J, q);
         load_vertices(J, tri, v);
     }
-    int cls = -1;
-    GridBox b = { 0, -1, 0, -1, 0, -1 };
+    // ---- the partitions of this triangle -------------------------------------------------------------
+    // list mode: one (the pair's). inline mode: every logical partition whose world box the triangle's
+    // bbox touches (inclusive float test, partitioner.cpp:117-126; the boxes are a product of per-axis
+    // slabs, so the test separates per axis) -- for P == 1 the reference does not test at all (:80-98).
+    int lx = 0, ly = 0, lz = 0, nx = 1, ny = 1, count = 0;
+    constexpr bool enumerate = ENUM;                              // (J.pair_tri == nullptr) && J.P > 1
     if (active) {
-        int px, py, pz;
-        partition_origin(J, part, px, py, pz);
-        b = clamped_box(v, J.unit_div, px, py, pz, (int)J.side);
-        if (restrict_to_slab(J, b)) {
-            const unsigned long long vol = (unsigned long long)(b.x1 - b.x0 + 1) * (unsigned long long)(b.y1 - b.y0 + 1) *
-                                           (unsigned long long)(b.z1 - b.z0 + 1);
-                // small = at most SMALL_WINDOWS 4x4x4 windows anchored at the box corner
-            const unsigned nw = (unsigned)((b.x1 - b.x0 + 4) >> 2) * (unsigned)((b.y1 - b.y0 + 4) >> 2) * (unsigned)((b.z1 - b.z0 + 4) >> 2);
-            cls = (vol <= J.small_max && nw <= J.small_windows) ? 0 : (vol <= J.medium_max ? 1 : 2);
+        count = 1;
+        if (enumerate) {
+            int hx, hy, hz;
+            slab_range(J.bmin, J.bmax, 1 << J.k, stdmin(v[0], stdmin(v[3], v[6])), stdmax(v[0], stdmax(v[3], v[6])), lx, hx);
+            slab_range(J.bmin, J.bmax, 1 << J.k, stdmin(v[1], stdmin(v[4], v[7])), stdmax(v[1], stdmax(v[4], v[7])), ly, hy);
+            slab_range(J.bmin, J.bmax, 1 << J.k, stdmin(v[2], stdmin(v[5], v[8])), stdmax(v[2], stdmax(v[5], v[8])), lz, hz);
+            nx = max(hx - lx + 1, 0); ny = max(hy - ly + 1, 0);
+            count = nx * ny * max(hz - lz + 1, 0);
         }
     }
-    if (!OWNER) {
-        const unsigned long long e = ((unsigned long long)part << 32) | tri;
-        warp_push(&J.qcount[0], J.queue[0], cls == 1, e);
-        warp_push(&J.qcount[1], J.queue[1], cls == 2, e);
-    }
-    // warp-uniform upper bounds of the window extents (convergent point: every lane is still here)
-    const int ua = min(4, __reduce_max_sync(0xffffffffu, cls == 0 ? b.x1 - b.x0 + 1 : 0));
-    const int ub = min(4, __reduce_max_sync(0xffffffffu, cls == 0 ? b.y1 - b.y0 + 1 : 0));
-    const int uc = min(4, __reduce_max_sync(0xffffffffu, cls == 0 ? b.z1 - b.z0 + 1 : 0));
-    if (cls != 0) return;
-
+    const int most = ENUM ? __reduce_max_sync(0xffffffffu, count) : 1;   // warp-uniform trip count (1 almost always)
     TriSetup s;
-    tri_setup(v, J.u, s);
-    for (int wz = b.z0; wz <= b.z1; wz += 4)
-        for (int wy = b.y0; wy <= b.y1; wy += 4)
-            for (int wx = b.x0; wx <= b.x1; wx += 4) {
-                const unsigned long long hits = eval_window(s, J.u, wx, wy, wz, min(4, b.x1 - wx + 1), min(4, b.y1 - wy + 1), min(4, b.z1 - wz + 1),
-                                                            ua, ub, uc);
-                if (hits) emit_window<OWNER>(J, wx, wy, wz, hits, tri);
+    bool have_setup = false;
+    for (int it = 0; it < most; it++) {
+        bool valid = it < count;
+        if (valid && enumerate) {
+            part = (uint32_t)morton3((uint32_t)(lx + it % nx), (uint32_t)(ly + (it / nx) % ny), (uint32_t)(lz + it / (nx * ny)));
+            valid = part >= J.p_first && part <= J.p_last;         // partitions of other ranks
+        }
+        int cls = -1;
+        GridBox b = { 0, -1, 0, -1, 0, -1 };
+        if (valid) {
+            int px, py, pz;
+            partition_origin(J, part, px, py, pz);
+            b = clamped_box(v, J.unit_div, px, py, pz, (int)J.side);
+            if (restrict_to_slab(J, b)) {
+                const unsigned long long vol = (unsigned long long)(b.x1 - b.x0 + 1) * (unsigned long long)(b.y1 - b.y0 + 1) *
+                                               (unsigned long long)(b.z1 - b.z0 + 1);
+                // small = a few 4x4x4 windows anchored at the box corner
+                const unsigned nw = (unsigned)((b.x1 - b.x0 + 4) >> 2) * (unsigned)((b.y1 - b.y0 + 4) >> 2) * (unsigned)((b.z1 - b.z0 + 4) >> 2);
+                cls = (vol <= J.small_max && nw <= J.small_windows) ? 0 : (vol <= J.medium_max ? 1 : 2);
             }
+        }
+        if (!OWNER) {
+            const unsigned long long e = ((unsigned long long)part << 32) | tri;
+            warp_push(&J.qcount[0], J.queue[0], J.qcap, &J.qcount[3], cls == 1, e);
+            warp_push(&J.qcount[1], J.queue[1], J.qcap, &J.qcount[3], cls == 2, e);
+            if (enumerate) {                                      // statistics: pairs seen by this context
+                const unsigned m = __ballot_sync(0xffffffffu, valid);
+                if ((threadIdx.x & 31) == 0 && m) atomicAdd(&J.qcount[2], (unsigned long long)__popc(m));
+            }
+        }
+        // warp-uniform upper bounds of the window extents (convergent point: every lane is here)
+        const int ua = min(4, __reduce_max_sync(0xffffffffu, cls == 0 ? b.x1 - b.x0 + 1 : 0));
+        const int ub = min(4, __reduce_max_sync(0xffffffffu, cls == 0 ? b.y1 - b.y0 + 1 : 0));
+        const int uc = min(4, __reduce_max_sync(0xffffffffu, cls == 0 ? b.z1 - b.z0 + 1 : 0));
+        if (cls == 0) {
+            if (!have_setup) { tri_setup(v, J.u, s); have_setup = true; }
+            for (int wz = b.z0; wz <= b.z1; wz += 4)
+                for (int wy = b.y0; wy <= b.y1; wy += 4)
+                    for (int wx = b.x0; wx <= b.x1; wx += 4) {
+                        const unsigned long long hits = eval_window(s, J.u, wx, wy, wz, min(4, b.x1 - wx + 1), min(4, b.y1 - wy + 1),
+                                                                    min(4, b.z1 - wz + 1), ua, ub, uc);
+                        if (hits) emit_window<OWNER>(J, wx, wy, wz, hits, tri);
+                    }
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -335,7 +383,7 @@ __device__ __forceinline__ void queued_pair_setup(const VoxJob& J, unsigned long
 
 template <bool OWNER>
 __device__ __forceinline__ void vox_medium_body(const VoxJob& J) {
-    const unsigned long long n = J.qcount[0];
+    const unsigned long long n = min(J.qcount[0], J.qcap);
     const unsigned long long nwarps = (unsigned long long)gridDim.x * WARPS_PER_BLOCK;
     for (unsigned long long e = (unsigned long long)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5); e < n; e += nwarps) {
         uint32_t tri; TriSetup s; GridBox b;
@@ -346,7 +394,7 @@ __device__ __forceinline__ void vox_medium_body(const VoxJob& J) {
 
 template <bool OWNER>
 __device__ __forceinline__ void vox_large_body(const VoxJob& J) {
-    const unsigned long long n = J.qcount[1];
+    const unsigned long long n = min(J.qcount[1], J.qcap);
     const unsigned long long nwarps = (unsigned long long)gridDim.x * WARPS_PER_BLOCK;
     const unsigned long long gw = (unsigned long long)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
     for (unsigned long long e = 0; e < n; e++) {
@@ -382,12 +430,7 @@ struct BinJob {
 };
 
 __device__ __forceinline__ void slab_range(const BinJob& B, float mn, float mx, int& lo, int& hi) {
-    // partition slab i is kept unless (mx < bmin[i]) or (mn > bmax[i])
-    const int n = 1 << B.k;
-    lo = n; hi = -1;
-    for (int i = 0; i < n; i++) {
-        if (!(mx < B.bmin[i]) && !(mn > B.bmax[i])) { if (i < lo) lo = i; hi = i; }
-    }
+    slab_range(B.bmin, B.bmax, 1 << B.k, mn, mx, lo, hi);
 }
 
 template <bool FILL>

@@ -157,7 +157,7 @@ class DistributedBuilder:
     def step(self, prm):
         """partition -> voxelize -> local build -> NCCL all-reduce of the table -> merged emit."""
         sb = self.sb
-        sb.partition(prm)
+        sb.partition(prm, want_counts=False)
         sb.voxelize()
         n = sb.shard_table_size()
         if self.table is None or self.table.numel() != n:
