@@ -106,6 +106,7 @@ struct svo_ctx {
     int sb_lo[3], sb_hi[3];
     ull q_begin = 0, q_end = 0, qcap = 1;
     bool want_pl = false, phase_a_done = false;
+    int jf = 0;                        // fused single-block kernels handle local levels jf..J (0 = not fused)
     bool use_lists = false;            // SVO_PARTITION_LISTS=1: build per-partition index lists (count / scan / fill)
     float slab_min[32], slab_max[32];  // world slabs of the partition grid (partitioner.cpp:54-59)
     ull p_first = 0, p_last = 0;
@@ -654,7 +655,7 @@ static int size_scans(svo_ctx* c, LevelBufs& L, const LevelBufs* child, bool pl,
 static int build_phase_a(svo_ctx* c, ull* table) {
     const int J = c->J;
     const bool payload = c->prm.payload != 0, levels = c->prm.generate_levels != 0;
-    const bool want_pl = payload || levels || c->world > 1;
+    const bool want_pl = levels || c->world > 1;       // leaf-count prefixes: only -levels data indices and the shard table need them
     c->want_pl = want_pl;
     mark(c, EV_BUILD0);
     // ---- sync #1: how many non-zero words does every local level hold? ----
@@ -670,16 +671,36 @@ static int build_phase_a(svo_ctx* c, ull* table) {
         if (rc) return rc;
     }
     if (payload) CK(c->tileidx.ensure((size_t)c->nwords[0] * sizeof(uint32_t)));
+    // levels jf..J with few tiles are walked by single-block fused kernels (one launch instead of ~9 per level)
+    c->jf = 0;
+    if (!levels && J >= 1) {
+        int jf = J + 1;
+        while (jf > 1 && c->lv[jf - 1].n <= 4096) jf--;
+        if (jf <= J) c->jf = jf;
+    }
+    const int jf = c->jf;
+    FusedJob F;
+    if (jf) {
+        memset(&F, 0, sizeof F);
+        for (int j = 0; j <= J; j++) { F.lv[j] = c->lv[j].view(); F.dense[j] = c->dense[j].as<ull>() - c->bias[j]; }
+        F.dense_top = c->dense[J].as<ull>(); F.top_words = c->nwords[J]; F.top_bias = c->bias[J];
+        F.J = J; F.jf = jf;
+    }
     // ---- top-down: compact tile lists ----
-    if (c->lv[J].n) {
+    if (jf) {
+        if (c->lv[J].n) { k_fused_down<<<1, 1024, 0, c->stream>>>(F); LAUNCHED(); }
+        else for (int j = jf; j <= J; j++) CK(cudaMemsetAsync(c->lv[j].fc.p, 0, sizeof(ull), c->stream));
+    } else if (c->lv[J].n) {
         k_compact_top<<<1, 1024, 0, c->stream>>>(c->dense[J].as<ull>(), c->nwords[J], c->bias[J], c->lv[J].key.as<ull>(), c->lv[J].mask.as<ull>(),
                                                 (payload && J == 0) ? c->tileidx.as<uint32_t>() : nullptr, J == 0 ? 1 : 0); LAUNCHED();
     }
     for (int j = J; j >= 0; j--) {
-        PopcOp op{ c->lv[j].mask.as<ull>() };
-        int rc = exscan(c, op, c->lv[j].n, c->lv[j].fc.as<ull>());
-        if (rc) return rc;
-        if (j > 0 && c->lv[j].n) {
+        if (!jf || j < jf) {
+            PopcOp op{ c->lv[j].mask.as<ull>() };
+            int rc = exscan(c, op, c->lv[j].n, c->lv[j].fc.as<ull>());
+            if (rc) return rc;
+        }
+        if (j > 0 && c->lv[j].n && (!jf || j <= jf)) {
             k_expand<<<blocks_for(c->lv[j].n, WARPS_PER_BLOCK), WARPS_PER_BLOCK * 32, 0, c->stream>>>(
                 c->lv[j].view(), c->lv[j - 1].view(), c->dense[j - 1].as<ull>() - c->bias[j - 1],
                 (payload && j == 1) ? c->tileidx.as<uint32_t>() - c->bias[0] : nullptr, j == 1 ? 1 : 0); LAUNCHED();
@@ -687,8 +708,13 @@ static int build_phase_a(svo_ctx* c, ull* table) {
     }
     // ---- bottom-up: subtree sizes (+ leaf / internal counts) ----
     for (int j = 0; j <= J; j++) {
+        if (jf && j >= jf) break;
         int rc = size_scans(c, c->lv[j], j ? &c->lv[j - 1] : nullptr, want_pl, levels);
         if (rc) return rc;
+    }
+    if (jf) {
+        if (c->lv[J].n) { k_fused_up<<<1, 1024, 0, c->stream>>>(F); LAUNCHED(); }
+        else for (int j = jf; j <= J; j++) CK(cudaMemsetAsync(c->lv[j].ps.p, 0, sizeof(ull), c->stream));
     }
     // ---- this rank's table entries ----
     if (table) {
@@ -847,7 +873,18 @@ static int build_phase_b(svo_ctx* c, const ull* table) {
     } else {
         int rc = emit_upper_levels();
         if (rc) return rc;
-        for (int j = J; j >= 1; j--) {
+        int j_start = J;
+        if (c->jf && c->jf < J) {
+            // fused single-block emission of the small local levels J .. jf+1
+            FusedJob F;
+            memset(&F, 0, sizeof F);
+            for (int j = 0; j <= J; j++) F.lv[j] = (j == J) ? LJ : c->lv[j].view();
+            F.J = J; F.jf = c->jf;
+            F.E = E; F.E.is_top = (J == top); F.E.root_here = (J == top) && d_even;
+            k_fused_emit<<<1, 1024, 0, c->stream>>>(F); LAUNCHED();
+            j_start = c->jf;
+        }
+        for (int j = j_start; j >= 1; j--) {
             if (!c->lv[j].n) continue;
             E.is_top = (j == top);
             E.root_here = (j == top) && d_even;
@@ -911,8 +948,12 @@ static int build_phase_b(svo_ctx* c, const ull* table) {
     mark(c, EV_BUILD1);
     // ---- leave a clean pyramid behind: zero exactly the words that were set ----
     mark(c, EV_CLR0);
-    for (int j = 0; j <= J; j++) {
-        if (c->lv[j].n) { k_sparse_clear<<<blocks_for(c->lv[j].n, 256), 256, 0, c->stream>>>(c->lv[j].key.as<ull>(), c->lv[j].n, c->dense[j].as<ull>() - c->bias[j]); LAUNCHED(); }
+    if (c->lv[0].n) {
+        ClearJob Cj;
+        memset(&Cj, 0, sizeof Cj);
+        for (int j = 0; j <= J; j++) { Cj.key[j] = c->lv[j].key.as<ull>(); Cj.dense[j] = c->dense[j].as<ull>() - c->bias[j]; Cj.n[j] = c->lv[j].n; }
+        dim3 grid((unsigned)std::min<ull>(blocks_for(c->lv[0].n, 256), (ull)c->sm_count * 16), (unsigned)(J + 1));
+        k_sparse_clear_all<<<grid, 256, 0, c->stream>>>(Cj); LAUNCHED();
     }
     c->dense_clean = true;
     mark(c, EV_CLR1);

@@ -566,7 +566,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_final(F f, unsigned long 
 }
 
 // Small inputs (the upper pyramid levels): the whole exclusive scan in ONE block / one launch.
-constexpr unsigned long long SCAN_SMALL_MAX = 16384;
+constexpr unsigned long long SCAN_SMALL_MAX = 32768;
 template <class F>
 __global__ void __launch_bounds__(1024) k_scan_small(F f, unsigned long long n, unsigned long long* out) {
     unsigned long long carry = 0;
@@ -971,6 +971,154 @@ __global__ void __launch_bounds__(128) k_levels_data(Level L, Level C, int level
 #pragma unroll
     for (int q = 0; q < 6; q++) L.cache[i * 6 + q] = wc[q];
     if (real_node) write_data_record(data, internal_data_index(E, L.pl[i + 1], ib + (L.pi[i + 1] - L.pi[i]) - 1ULL), wc);
+}
+
+// ---------------------------------------------------------------------------
+// Fused single-block kernels for the SMALL upper levels (a few thousand tiles in total): one launch walks
+// all of them instead of ~9 launches per level. Levels jf..J (jf >= 1) qualify when their tile counts are
+// small; the big levels below keep the multi-block kernels.
+// ---------------------------------------------------------------------------
+struct FusedJob {
+    Level lv[MAX_LEVELS];
+    const unsigned long long* dense[MAX_LEVELS];   // biased dense levels (indexed by global word index)
+    const unsigned long long* dense_top;           // unbiased dense level J
+    unsigned long long top_words, top_bias;
+    int J, jf;
+    EmitJob E;
+};
+
+__device__ __forceinline__ void block_scan_array(const unsigned long long* mask, unsigned long long n, unsigned long long* out) {
+    unsigned long long carry = 0;
+    for (unsigned long long b = 0; b < n; b += blockDim.x) {
+        const unsigned long long idx = b + threadIdx.x;
+        const unsigned long long v = idx < n ? (unsigned long long)__popcll(mask[idx]) : 0ULL;
+        unsigned long long total;
+        const unsigned long long ex = block_excl_scan(v, total);
+        if (idx < n) out[idx] = carry + ex;
+        carry += total;
+    }
+    if (threadIdx.x == 0) out[n] = carry;
+    __syncthreads();
+}
+
+// top-down: compact the top level, then (child prefix, expand) for levels J..jf; leaves fc[jf] ready so
+// that the regular k_expand can produce level jf-1.
+__global__ void __launch_bounds__(1024) k_fused_down(FusedJob F) {
+    {   // compact dense level J
+        unsigned long long carry = 0;
+        for (unsigned long long b = 0; b < F.top_words; b += blockDim.x) {
+            const unsigned long long idx = b + threadIdx.x;
+            const unsigned long long w = idx < F.top_words ? F.dense_top[idx] : 0ULL;
+            unsigned long long total;
+            const unsigned long long ex = block_excl_scan(w != 0ULL ? 1ULL : 0ULL, total);
+            if (w != 0ULL) { F.lv[F.J].key[carry + ex] = F.top_bias + idx; F.lv[F.J].mask[carry + ex] = w; }
+            carry += total;
+        }
+        __syncthreads();
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int j = F.J; j >= F.jf; j--) {
+        const Level P = F.lv[j];
+        block_scan_array(P.mask, P.n, P.fc);
+        if (j > F.jf) {
+            const Level C = F.lv[j - 1];
+            for (unsigned long long i = wid; i < P.n; i += nw) {
+                const unsigned long long W = P.mask[i], key = P.key[i], fc = P.fc[i];
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int bit = lane + 32 * h;
+                    if ((W >> bit) & 1ULL) {
+                        const unsigned long long c = fc + __popcll(W & lowmask(bit));
+                        const unsigned long long ck = (key << 6) | (unsigned long long)bit;
+                        C.key[c] = ck;
+                        C.mask[c] = F.dense[j - 1][ck];
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// bottom-up: subtree-size prefixes of levels jf..J (ps of level jf-1 must be complete)
+__global__ void __launch_bounds__(1024) k_fused_up(FusedJob F) {
+    for (int j = F.jf; j <= F.J; j++) {
+        const Level L = F.lv[j];
+        const unsigned long long* cps = F.lv[j - 1].ps;
+        unsigned long long carry = 0;
+        for (unsigned long long b = 0; b < L.n; b += blockDim.x) {
+            const unsigned long long idx = b + threadIdx.x;
+            unsigned long long v = 0;
+            if (idx < L.n) {
+                const unsigned long long w = L.mask[idx];
+                v = (unsigned long long)(__popcll(w) + __popc(nonzero_bytes(w))) + cps[L.fc[idx + 1]] - cps[L.fc[idx]];
+            }
+            unsigned long long total;
+            const unsigned long long ex = block_excl_scan(v, total);
+            if (idx < L.n) L.ps[idx] = carry + ex;
+            carry += total;
+        }
+        if (threadIdx.x == 0) L.ps[L.n] = carry;
+        __syncthreads();
+    }
+}
+
+// one tile of an upper level: records of its grandchildren + children, bases of the grandchild subtrees
+__device__ __forceinline__ void emit_upper_tile(const Level& L, const Level& C, const EmitJob& E, unsigned long long i, int lane) {
+    const unsigned long long W = L.mask[i], fc = L.fc[i], base = L.base[i];
+    const unsigned long long S = L.ps[i + 1] - L.ps[i];
+    const uint32_t nzb = nonzero_bytes(W);
+    const unsigned long long ps0 = C.ps[fc];
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const int bit = lane + 32 * h;
+        if ((W >> bit) & 1ULL) {
+            const int k = bit >> 3;
+            const unsigned long long c = fc + __popcll(W & lowmask(bit));
+            const unsigned long long gbase = base + (C.ps[c] - ps0) + __popcll(W & lowmask(8 * k));
+            C.base[c] = gbase;
+            const unsigned long long blk = base + (C.ps[fc + __popcll(W & lowmask(8 * (k + 1)))] - ps0) + __popcll(W & lowmask(8 * k));
+            const unsigned long long pos = blk + __popcll(W & lowmask(bit) & ~lowmask(8 * k));
+            const uint32_t gnz = nonzero_bytes(C.mask[c]);
+            unsigned long long* o = E.nodes + pos * 3;
+            o[0] = 0ULL;
+            o[1] = gbase + (C.ps[c + 1] - C.ps[c]) - __popc(gnz);
+            o[2] = child_offsets(gnz);
+        }
+    }
+    if (lane < 8 && ((nzb >> lane) & 1u)) {
+        const int k = lane;
+        const unsigned long long blk = base + (C.ps[fc + __popcll(W & lowmask(8 * (k + 1)))] - ps0) + __popcll(W & lowmask(8 * k));
+        unsigned long long* o = E.nodes + (base + S - __popc(nzb) + __popc(nzb & ((1u << k) - 1u))) * 3;
+        o[0] = 0ULL;
+        o[1] = blk;
+        o[2] = child_offsets((uint32_t)((W >> (8 * k)) & 0xffULL));
+    }
+}
+// top-down emission of levels J..jf+1 (each level writes the bases of the next); level jf itself is emitted
+// by the regular multi-block kernel afterwards. No -levels, no sharding on this path.
+__global__ void __launch_bounds__(1024) k_fused_emit(FusedJob F) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int j = F.J; j > F.jf; j--) {
+        const Level L = F.lv[j], C = F.lv[j - 1];
+        for (unsigned long long i = wid; i < L.n; i += nw) emit_upper_tile(L, C, F.E, i, lane);
+        if (j == F.J && F.E.root_here && threadIdx.x == 0 && L.n) {
+            const unsigned long long W = L.mask[0], S = L.ps[1] - L.ps[0];
+            const uint32_t nzb = nonzero_bytes(W);
+            unsigned long long* o = F.E.nodes + S * 3;
+            o[0] = 0ULL; o[1] = L.base[0] + S - __popc(nzb); o[2] = child_offsets(nzb);
+        }
+        __syncthreads();
+    }
+}
+
+// sparse clear of all levels in one launch (blockIdx.y = level)
+struct ClearJob { const unsigned long long* key[MAX_LEVELS]; unsigned long long* dense[MAX_LEVELS]; unsigned long long n[MAX_LEVELS]; };
+__global__ void __launch_bounds__(256) k_sparse_clear_all(ClearJob Cj) {
+    const int j = blockIdx.y;
+    const unsigned long long n = Cj.n[j];
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x)
+        Cj.dense[j][Cj.key[j][i]] = 0ULL;
 }
 
 // ascending Morton codes of the filled voxels
