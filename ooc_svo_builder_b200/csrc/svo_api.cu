@@ -88,7 +88,8 @@ struct svo_ctx {
     std::vector<uint64_t> h_part_counts;
 
     // work queues
-    DevBuf queue[2], qcount;
+    DevBuf queue[2], qcount, subset;
+    bool use_subset = false;
 
     // compact levels
     LevelBufs lv[MAX_LEVELS];
@@ -112,7 +113,9 @@ struct svo_ctx {
     ull p_first = 0, p_last = 0;
     DevBuf table_own, dcol[4];
     LevelBufs glv;                     // global level-J tile list (sharded / odd depth)
-    std::vector<ull> h_table;
+    std::vector<ull> h_table, h_rpos, h_rrec, h_ownbase;
+    DevBuf d_rpos, d_rrec;
+    ull n_upper_records = 0;
     ull leaf_offset = 0, n_voxels_local = 0;
     ull node_lo = 0, node_hi = 0, data_lo = 0, data_hi = 0;
 
@@ -260,8 +263,29 @@ int launch_voxelizer(svo_ctx* c) {
     VoxJob J = make_voxjob(c);
     const size_t smem = J.pair_tri ? 0 : (size_t)VOX_BLOCK * c->fpt * sizeof(float);
     if (!OWNER) mark(c, EV_VS0);
-    if (J.pair_tri == nullptr && J.P > 1) { k_vox_small<OWNER, true><<<blocks_for(c->q_end - c->q_begin, VOX_BLOCK), VOX_BLOCK, smem, c->stream>>>(J); LAUNCHED(); }
-    else { k_vox_small<OWNER, false><<<blocks_for(c->q_end - c->q_begin, VOX_BLOCK), VOX_BLOCK, smem, c->stream>>>(J); LAUNCHED(); }
+    if (c->use_subset) {
+        // sharded: compact the triangles that touch this rank's slab once (the owner pass reuses the list)
+        if (!OWNER) {
+            FilterJob Fj;
+            memset(&Fj, 0, sizeof Fj);
+            Fj.tris = c->d_tris; Fj.fpt = (uint32_t)c->fpt; Fj.n_tris = c->n_tris;
+            Fj.use_partitions = c->P > 1 ? 1 : 0; Fj.k = c->k;
+            for (int i = 0; i < 32; i++) { Fj.bmin[i] = c->slab_min[i]; Fj.bmax[i] = c->slab_max[i]; }
+            for (int a = 0; a < 3; a++) {
+                Fj.lo[a] = c->P > 1 ? c->sb_lo[a] / (int)c->side : c->sb_lo[a];
+                Fj.hi[a] = c->P > 1 ? c->sb_hi[a] / (int)c->side : c->sb_hi[a];
+            }
+            Fj.unit_div = c->unit_div; Fj.gmax = (int)c->prm.gridsize - 1;
+            Fj.out = c->subset.as<uint32_t>(); Fj.count = c->qcount.as<ull>() + 4;
+            k_owner_filter<<<blocks_for(c->n_tris, VOX_BLOCK), VOX_BLOCK, 0, c->stream>>>(Fj); LAUNCHED();
+        }
+        J.subset = c->subset.as<uint32_t>(); J.subset_count = c->qcount.as<ull>() + 4;
+        const unsigned g2 = (unsigned)c->sm_count * SVO_VOX_MINBLOCKS;
+        const size_t smem2 = (size_t)VOX_BLOCK * c->fpt * sizeof(float);
+        if (J.P > 1) { k_vox_small<OWNER, true, true><<<g2, VOX_BLOCK, smem2, c->stream>>>(J); LAUNCHED(); }
+        else { k_vox_small<OWNER, false, true><<<g2, VOX_BLOCK, smem2, c->stream>>>(J); LAUNCHED(); }
+    } else if (J.pair_tri == nullptr && J.P > 1) { k_vox_small<OWNER, true, false><<<blocks_for(c->q_end - c->q_begin, VOX_BLOCK), VOX_BLOCK, smem, c->stream>>>(J); LAUNCHED(); }
+    else { k_vox_small<OWNER, false, false><<<blocks_for(c->q_end - c->q_begin, VOX_BLOCK), VOX_BLOCK, smem, c->stream>>>(J); LAUNCHED(); }
     if (!OWNER) mark(c, EV_VS1);
     const unsigned grid = (unsigned)c->sm_count * 4;
     k_vox_queued<OWNER><<<grid, WARPS_PER_BLOCK * 32, 0, c->stream>>>(J); LAUNCHED();
@@ -345,7 +369,7 @@ void svo_ctx_destroy(svo_ctx* c) {
     for (int q = 0; q < 4; q++) c->dcol[q].release();
     c->d_lvlptrs.release(); c->d_nwords.release(); c->d_counts.release();
     c->part_counts.release(); c->part_cursor.release(); c->part_off.release(); c->pair_tri.release();
-    c->queue[0].release(); c->queue[1].release(); c->qcount.release();
+    c->queue[0].release(); c->queue[1].release(); c->qcount.release(); c->subset.release();
     c->scan_tmp.release(); c->nodes.release(); c->data.release(); c->owner.release(); c->tileidx.release(); c->codes.release();
     for (int i = 0; i < EV_COUNT; i++) cudaEventDestroy(c->ev[i]);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
@@ -598,8 +622,10 @@ int svo_voxelize(svo_ctx* c) {
     CK(cudaSetDevice(c->device));
     int rc = ensure_pyramid(c);
     if (rc) return rc;
-    CK(c->qcount.ensure(4 * sizeof(ull)));
-    CK(cudaMemsetAsync(c->qcount.p, 0, 4 * sizeof(ull), c->stream));
+    CK(c->qcount.ensure(8 * sizeof(ull)));
+    CK(cudaMemsetAsync(c->qcount.p, 0, 8 * sizeof(ull), c->stream));
+    c->use_subset = c->world > 1 && !(c->P > 1 && c->use_lists);
+    if (c->use_subset) CK(c->subset.ensure((size_t)(c->n_tris / VOX_BLOCK + 2) * sizeof(uint32_t)));
     // queue capacity: exact with lists; with inline enumeration a triangle may appear once per partition it
     // touches, so leave headroom and detect overflow (qcount[3]) instead of trusting a bound
     const ull npairs = c->q_end - c->q_begin;
@@ -682,7 +708,10 @@ static int build_phase_a(svo_ctx* c, ull* table) {
     FusedJob F;
     if (jf) {
         memset(&F, 0, sizeof F);
-        for (int j = 0; j <= J; j++) { F.lv[j] = c->lv[j].view(); F.dense[j] = c->dense[j].as<ull>() - c->bias[j]; }
+        for (int j = 0; j <= J; j++) {
+            F.lv[j] = c->lv[j].view(); F.dense[j] = c->dense[j].as<ull>() - c->bias[j];
+            if (!want_pl) F.lv[j].pl = nullptr;
+        }
         F.dense_top = c->dense[J].as<ull>(); F.top_words = c->nwords[J]; F.top_bias = c->bias[J];
         F.J = J; F.jf = jf;
     }
@@ -714,7 +743,10 @@ static int build_phase_a(svo_ctx* c, ull* table) {
     }
     if (jf) {
         if (c->lv[J].n) { k_fused_up<<<1, 1024, 0, c->stream>>>(F); LAUNCHED(); }
-        else for (int j = jf; j <= J; j++) CK(cudaMemsetAsync(c->lv[j].ps.p, 0, sizeof(ull), c->stream));
+        else for (int j = jf; j <= J; j++) {
+            CK(cudaMemsetAsync(c->lv[j].ps.p, 0, sizeof(ull), c->stream));
+            if (want_pl) CK(cudaMemsetAsync(c->lv[j].pl.p, 0, sizeof(ull), c->stream));
+        }
     }
     // ---- this rank's table entries ----
     if (table) {
@@ -731,16 +763,118 @@ static int build_phase_a(svo_ctx* c, ull* table) {
 }
 
 // ---------------------------------------------------------------------------
+// Sharded merge of the shared upper levels, on the host: the summed table holds {mask, S, leaves} of every
+// top-of-shard subtree (<= a few thousand entries). From it every rank derives, identically, the upper
+// 64-tree levels, the global record counts, the file base of each subtree, its own file range and the
+// (few) upper-level records that fall into that range. Same formulas as k_emit_upper.
+// ---------------------------------------------------------------------------
+static inline ull h_lowmask(int n) { return n >= 64 ? ~0ULL : ((1ULL << n) - 1ULL); }
+static int shard_host_merge(svo_ctx* c, const ull* table) {
+    const int J = c->J, top = c->nl - 1;
+    const ull WJ = c->WJ;
+    const bool d_even = (c->D % 2) == 0;
+    c->h_table.resize((size_t)WJ * 4);
+    CK(cudaMemcpyAsync(c->h_table.data(), table, (size_t)WJ * 4 * sizeof(ull), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    const ull* T = c->h_table.data();
+    std::vector<std::vector<ull>> M(top + 1), S(top + 1), B(top + 1);
+    M[J].resize(WJ); S[J].resize(WJ); B[J].assign(WJ, 0);
+    ull leaves_total = 0;
+    for (ull e = 0; e < WJ; e++) { M[J][e] = T[4 * e]; S[J][e] = T[4 * e + 1]; leaves_total += T[4 * e + 2]; }
+    for (int j = J + 1; j <= top; j++) {
+        const size_t n = (size_t)c->nwords[j];
+        M[j].assign(n, 0); S[j].assign(n, 0); B[j].assign(n, 0);
+        for (size_t ch = 0; ch < M[j - 1].size(); ch++) if (M[j - 1][ch]) M[j][ch >> 6] |= 1ULL << (ch & 63);
+        for (size_t w = 0; w < n; w++) {
+            const ull W = M[j][w];
+            if (!W) continue;
+            ull sz = (ull)__builtin_popcountll(W) + (ull)__builtin_popcount(nonzero_bytes(W));
+            for (int b = 0; b < 64; b++) if ((W >> b) & 1ULL) sz += S[j - 1][w * 64 + b];
+            S[j][w] = sz;
+        }
+    }
+    c->n_voxels = leaves_total;
+    c->n_nodes = leaves_total == 0 ? 1 : S[top][0] + (d_even ? 1 : 0);
+    // top-down: bases + upper records
+    std::vector<ull> rpos, rrec;
+    auto push = [&](ull pos, ull d0, ull d1, ull d2) { rpos.push_back(pos); rrec.push_back(d0); rrec.push_back(d1); rrec.push_back(d2); };
+    for (int j = top; j > J; j--) {
+        for (size_t w = 0; w < M[j].size(); w++) {
+            const ull W = M[j][w];
+            if (!W) continue;
+            const ull base = B[j][w], sz = S[j][w];
+            const uint32_t nzb = nonzero_bytes(W);
+            ull acc = 0;
+            for (int k = 0; k < 8; k++) {
+                const uint32_t byte = (uint32_t)((W >> (8 * k)) & 0xffULL);
+                if (!byte) continue;
+                const ull before = (ull)__builtin_popcountll(W & h_lowmask(8 * k));
+                for (int b = 0; b < 8; b++) if ((byte >> b) & 1u) {
+                    const size_t ch = w * 64 + 8 * k + b;
+                    B[j - 1][ch] = base + acc + before;
+                    acc += S[j - 1][ch];
+                }
+                const ull blk = base + acc + before;
+                ull r = 0;
+                for (int b = 0; b < 8; b++) if ((byte >> b) & 1u) {
+                    const size_t ch = w * 64 + 8 * k + b;
+                    const uint32_t gnz = nonzero_bytes(M[j - 1][ch]);
+                    push(blk + r++, 0ULL, B[j - 1][ch] + S[j - 1][ch] - (ull)__builtin_popcount(gnz), child_offsets(gnz));
+                }
+                push(base + sz - (ull)__builtin_popcount(nzb) + (ull)__builtin_popcount(nzb & ((1u << k) - 1u)), 0ULL, blk, child_offsets(byte));
+            }
+            if (j == top && d_even) push(sz, 0ULL, base + sz - (ull)__builtin_popcount(nzb), child_offsets(nzb));
+        }
+    }
+    // this rank's tiles, offsets and file range
+    const ull wj0 = c->bias[J], wj1 = c->bias[J] + c->nwords[J];
+    c->leaf_offset = 0; c->n_voxels_local = 0;
+    c->h_ownbase.clear();
+    for (ull e = 0; e < WJ; e++) {
+        if (!M[J][e]) continue;
+        if (e < wj0) c->leaf_offset += T[4 * e + 2];
+        else if (e < wj1) { c->h_ownbase.push_back(B[J][e]); c->n_voxels_local += T[4 * e + 2]; }
+    }
+    if (c->h_ownbase.size() != c->lv[J].n) return fail(c, SVO_E_INVALID, "sharded merge: table does not match this rank's tiles (was the table summed over all ranks?)");
+    auto first_base_from = [&](ull e0) -> ull { for (ull e = e0; e < WJ; e++) if (M[J][e]) return B[J][e]; return c->n_nodes; };
+    c->node_lo = c->rank == 0 ? 0 : first_base_from(wj0);
+    c->node_hi = c->rank == c->world - 1 ? c->n_nodes : first_base_from(wj1);
+    if (leaves_total == 0) { c->node_lo = c->rank == 0 ? 0 : 1; c->node_hi = 1; }
+    c->h_rpos.clear(); c->h_rrec.clear();
+    for (size_t i = 0; i < rpos.size(); i++) {
+        if (rpos[i] >= c->node_lo && rpos[i] < c->node_hi) {
+            c->h_rpos.push_back(rpos[i]);
+            c->h_rrec.push_back(rrec[3 * i]); c->h_rrec.push_back(rrec[3 * i + 1]); c->h_rrec.push_back(rrec[3 * i + 2]);
+        }
+    }
+    c->n_upper_records = c->h_rpos.size();
+    if (!c->h_ownbase.empty())
+        CK(cudaMemcpyAsync(c->lv[J].base.p, c->h_ownbase.data(), c->h_ownbase.size() * sizeof(ull), cudaMemcpyHostToDevice, c->stream));
+    if (c->n_upper_records) {
+        CK(c->d_rpos.ensure(c->n_upper_records * sizeof(ull)));
+        CK(c->d_rrec.ensure(c->n_upper_records * 3 * sizeof(ull)));
+        CK(cudaMemcpyAsync(c->d_rpos.p, c->h_rpos.data(), c->n_upper_records * sizeof(ull), cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(c->d_rrec.p, c->h_rrec.data(), c->n_upper_records * 3 * sizeof(ull), cudaMemcpyHostToDevice, c->stream));
+    }
+    return SVO_OK;
+}
+
+// ---------------------------------------------------------------------------
 // Build, phase B: replicated upper levels from the (summed) table, file bases top-down, emission.
 // ---------------------------------------------------------------------------
 static int build_phase_b(svo_ctx* c, const ull* table) {
     const int J = c->J, nl = c->nl, top = nl - 1;
     const bool payload = c->prm.payload != 0, levels = c->prm.generate_levels != 0;
     const bool want_pl = c->want_pl;
-    const bool upper = J < top;
+    const bool host_merge = c->world > 1;                 // sharded: upper levels merged on the host from the table
+    const bool upper = J < top && !host_merge;
     const bool d_even = (c->D % 2) == 0;
     ull goff = 0, n_gJ = c->lv[J].n;
     c->leaf_offset = 0;
+    if (host_merge) {
+        int rc = shard_host_merge(c, table);
+        if (rc) return rc;
+    }
     if (upper) {
         // ---- dense columns of the global level-J words + replicated upper pyramid ----
         for (int q = 0; q < 4; q++) CK(c->dcol[q].ensure((size_t)c->WJ * sizeof(ull)));
@@ -800,15 +934,17 @@ static int build_phase_b(svo_ctx* c, const ull* table) {
     }
     // ---- sync #2: record counts ----
     LevelBufs& topL = c->lv[top];
+    if (!host_merge) {
     CK(cudaMemcpyAsync(c->h_pinned + 32, c->lv[0].fc.as<ull>() + c->lv[0].n, sizeof(ull), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaMemcpyAsync(c->h_pinned + 33, topL.ps.as<ull>() + topL.n, sizeof(ull), cudaMemcpyDeviceToHost, c->stream));
     if (levels) CK(cudaMemcpyAsync(c->h_pinned + 34, topL.pi.as<ull>() + topL.n, sizeof(ull), cudaMemcpyDeviceToHost, c->stream));
     if (want_pl) CK(cudaMemcpyAsync(c->h_pinned + 35, topL.pl.as<ull>() + topL.n, sizeof(ull), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     c->n_voxels_local = c->h_pinned[32];
-    c->n_voxels = (c->world > 1) ? c->h_pinned[35] : c->n_voxels_local;
+    c->n_voxels = c->n_voxels_local;
     const ull s_top = c->h_pinned[33];
     c->n_nodes = c->n_voxels == 0 ? 1 : s_top + (d_even ? 1 : 0);
+    }
     c->n_data = payload ? 1 + c->n_voxels : 2;          // OctreeBuilder.cpp:25-29
     if (levels && c->n_voxels) c->n_data += c->h_pinned[34] - (d_even ? 0 : 1);   // one record per internal node (the virtual top word is no node)
 
@@ -831,12 +967,21 @@ static int build_phase_b(svo_ctx* c, const ull* table) {
     E.leaf_offset = c->leaf_offset;
     E.pos_lo = 0; E.pos_hi = ~0ULL;
     E.write_records = 1;
-    c->node_lo = 0; c->node_hi = c->n_nodes;
-    if (c->n_voxels) {
-        CK(cudaMemsetAsync(topL.base.p, 0, sizeof(ull), c->stream));
-        if (levels) CK(cudaMemsetAsync(topL.ibase.p, 0, sizeof(ull), c->stream));
+    if (!host_merge) {
+        c->node_lo = 0; c->node_hi = c->n_nodes;
+        if (c->n_voxels) {
+            CK(cudaMemsetAsync(topL.base.p, 0, sizeof(ull), c->stream));
+            if (levels) CK(cudaMemsetAsync(topL.ibase.p, 0, sizeof(ull), c->stream));
+        }
     }
     auto emit_upper_levels = [&](void) -> int {
+        if (host_merge) {
+            // the shared upper levels were merged on the host: scatter the records that fall into this rank's range
+            if (c->n_upper_records) {
+                k_scatter_records<<<blocks_for(c->n_upper_records, 256), 256, 0, c->stream>>>(c->d_rpos.as<ull>(), c->d_rrec.as<ull>(), c->n_upper_records, E.nodes); LAUNCHED();
+            }
+            return SVO_OK;
+        }
         for (int j = top; j > J; j--) {
             if (!c->lv[j].n) continue;
             E.is_top = (j == top);
@@ -845,23 +990,6 @@ static int build_phase_b(svo_ctx* c, const ull* table) {
         }
         return SVO_OK;
     };
-    if (c->world > 1 && c->n_voxels) {
-        // first pass over the replicated upper levels only propagates bases; then this rank's file range is known
-        E.write_records = 0;
-        int rc = emit_upper_levels();
-        if (rc) return rc;
-        E.write_records = 1;
-        const ull n_own = c->lv[J].n;
-        if (c->rank > 0 && goff < n_gJ) CK(cudaMemcpyAsync(c->h_pinned + 44, c->glv.base.as<ull>() + goff, sizeof(ull), cudaMemcpyDeviceToHost, c->stream));
-        if (goff + n_own < n_gJ) CK(cudaMemcpyAsync(c->h_pinned + 45, c->glv.base.as<ull>() + goff + n_own, sizeof(ull), cudaMemcpyDeviceToHost, c->stream));
-        CK(cudaStreamSynchronize(c->stream));
-        c->node_lo = c->rank == 0 ? 0 : (goff < n_gJ ? c->h_pinned[44] : c->n_nodes);
-        c->node_hi = (goff + n_own < n_gJ && c->rank != c->world - 1) ? c->h_pinned[45] : c->n_nodes;
-        if (c->rank == c->world - 1) c->node_hi = c->n_nodes;
-    } else if (c->world > 1) {
-        c->node_lo = c->rank == 0 ? 0 : 1; c->node_hi = 1;      // empty grid: rank 0 writes the null root
-        if (c->rank != 0) c->node_lo = c->node_hi = 1;
-    }
     const ull n_local_nodes = c->node_hi - c->node_lo;
     CK(c->nodes.ensure((size_t)(n_local_nodes ? n_local_nodes : 1) * SVO_NODE_BYTES));
     E.nodes = c->nodes.as<ull>() - c->node_lo * 3;

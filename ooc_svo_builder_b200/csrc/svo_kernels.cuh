@@ -47,6 +47,8 @@ struct VoxJob {
     // Morton range of partitions this context owns
     float bmin[32], bmax[32];
     uint32_t p_first, p_last;
+    const uint32_t* subset;               // sharded: triangles that touch this rank's slab (NULL = all triangles)
+    const unsigned long long* subset_count;
     // sharding: level-0 word range owned by this context and the voxel bounding box of its slab.
     // lvl[] / tileidx are biased so that they are indexed with GLOBAL word indices.
     unsigned long long w_lo, w_hi;
@@ -202,35 +204,10 @@ __device__ __forceinline__ void emit_window(const VoxJob& J, int wx, int wy, int
 // Identity lists (P == 1) stage the block's triangle records through shared
 // memory with float4 loads; gathered lists read the vertices directly.
 // ---------------------------------------------------------------------------
+// Everything after the vertices are in registers: enumerate the triangle's partitions, classify the clamped
+// boxes, route big ones to the queues, voxelize small ones. Must be called by whole warps.
 template <bool OWNER, bool ENUM>
-__global__ void __launch_bounds__(VOX_BLOCK, SVO_VOX_MINBLOCKS) k_vox_small(VoxJob J) {
-    extern __shared__ float4 s_stage4[];
-    float* s_stage = reinterpret_cast<float*>(s_stage4);
-    const uint64_t q0 = J.q_begin + (uint64_t)blockIdx.x * VOX_BLOCK;
-    const uint64_t q = q0 + threadIdx.x;
-    const bool active = q < J.q_end;
-    float v[9];
-    uint32_t tri = 0, part = 0;
-    if (J.pair_tri == nullptr) {
-        // block-contiguous records [q0, q0 + VOX_BLOCK): VOX_BLOCK * fpt floats, 16-byte aligned
-        const uint64_t nrec = (J.q_end - q0 < VOX_BLOCK) ? (J.q_end - q0) : VOX_BLOCK;
-        const uint64_t nfl = nrec * J.fpt;
-        const float* src = J.tris + q0 * J.fpt;
-        const uint64_t n4 = nfl >> 2;
-        const float4* src4 = reinterpret_cast<const float4*>(src);
-        for (uint64_t i = threadIdx.x; i < n4; i += VOX_BLOCK) s_stage4[i] = __ldg(src4 + i);
-        for (uint64_t i = (n4 << 2) + threadIdx.x; i < nfl; i += VOX_BLOCK) s_stage[i] = __ldg(src + i);
-        __syncthreads();
-        tri = (uint32_t)q;
-        if (active) {
-#pragma unroll
-            for (int i = 0; i < 9; i++) v[i] = s_stage[threadIdx.x * J.fpt + i];
-        }
-    } else if (active) {
-        tri = J.pair_tri[q];
-        part = pair_partition(J, q);
-        load_vertices(J, tri, v);
-    }
+__device__ __forceinline__ void vox_small_body(const VoxJob& J, bool active, uint32_t tri, uint32_t part, const float* v) {
     // ---- the partitions of this triangle -------------------------------------------------------------
     // list mode: one (the pair's). inline mode: every logical partition whose world box the triangle's
     // bbox touches (inclusive float test, partitioner.cpp:117-126; the boxes are a product of per-axis
@@ -295,6 +272,59 @@ __global__ void __launch_bounds__(VOX_BLOCK, SVO_VOX_MINBLOCKS) k_vox_small(VoxJ
                     }
         }
     }
+}
+
+// Stage VOX_BLOCK consecutive triangle records starting at q0 through shared memory (float4 loads).
+__device__ __forceinline__ void stage_block(const VoxJob& J, uint64_t q0, uint64_t q_end, float4* s_stage4, float* s_stage) {
+    const uint64_t nrec = (q_end - q0 < VOX_BLOCK) ? (q_end - q0) : VOX_BLOCK;
+    const uint64_t nfl = nrec * J.fpt;
+    const float* src = J.tris + q0 * J.fpt;                    // q0 is a multiple of VOX_BLOCK: 16-byte aligned
+    const uint64_t n4 = nfl >> 2;
+    const float4* src4 = reinterpret_cast<const float4*>(src);
+    for (uint64_t i = threadIdx.x; i < n4; i += VOX_BLOCK) s_stage4[i] = __ldg(src4 + i);
+    for (uint64_t i = (n4 << 2) + threadIdx.x; i < nfl; i += VOX_BLOCK) s_stage[i] = __ldg(src + i);
+    __syncthreads();
+}
+
+template <bool OWNER, bool ENUM, bool SUBSET>
+__global__ void __launch_bounds__(VOX_BLOCK, SVO_VOX_MINBLOCKS) k_vox_small(VoxJob J) {
+    extern __shared__ float4 s_stage4[];
+    float* s_stage = reinterpret_cast<float*>(s_stage4);
+    float v[9];
+    if (SUBSET) {
+        // sharded: persistent blocks walk the list of staging blocks that touch this rank's slab (k_owner_filter)
+        const unsigned long long count = *J.subset_count;
+        for (unsigned long long li = blockIdx.x; li < count; li += gridDim.x) {
+            const uint64_t q0 = (uint64_t)J.subset[li] * VOX_BLOCK;
+            const uint64_t q = q0 + threadIdx.x;
+            const bool active = q < J.q_end;
+            stage_block(J, q0, J.q_end, s_stage4, s_stage);
+            if (active) {
+#pragma unroll
+                for (int i = 0; i < 9; i++) v[i] = s_stage[threadIdx.x * J.fpt + i];
+            }
+            __syncthreads();                                   // the next iteration overwrites the staging buffer
+            vox_small_body<OWNER, ENUM>(J, active, (uint32_t)q, 0u, v);
+        }
+        return;
+    }
+    const uint64_t q0 = J.q_begin + (uint64_t)blockIdx.x * VOX_BLOCK;
+    const uint64_t q = q0 + threadIdx.x;
+    const bool active = q < J.q_end;
+    uint32_t tri = 0, part = 0;
+    if (J.pair_tri == nullptr) {
+        stage_block(J, q0, J.q_end, s_stage4, s_stage);
+        tri = (uint32_t)q;
+        if (active) {
+#pragma unroll
+            for (int i = 0; i < 9; i++) v[i] = s_stage[threadIdx.x * J.fpt + i];
+        }
+    } else if (active) {
+        tri = J.pair_tri[q];
+        part = pair_partition(J, q);
+        load_vertices(J, tri, v);
+    }
+    vox_small_body<OWNER, ENUM>(J, active, tri, part, v);
 }
 
 // ---------------------------------------------------------------------------
@@ -480,6 +510,42 @@ __global__ void __launch_bounds__(256) k_bin(BinJob B) {
             if (valid) B.pair_tri[B.off[part] + base + __popc(peers & ((1u << lane) - 1u))] = (uint32_t)t;
         }
     }
+}
+
+// Sharded runs: every rank holds all triangles but only voxelizes the ones that touch its slab. This light
+// pass (36 B read per triangle) lists the staging blocks (VOX_BLOCK consecutive triangles) that contain at
+// least one such triangle -- meshes are spatially coherent, so most blocks are all-or-nothing; the test is a
+// superset test on bounding boxes (the voxelizer still checks every partition / word exactly). partition mode: per-axis slab ranges against the
+// bounding box of the owned partitions; P == 1: clamped grid bbox against the slab's voxel box.
+struct FilterJob {
+    const float* tris; uint32_t fpt; unsigned long long n_tris;
+    int use_partitions, k;
+    float bmin[32], bmax[32];
+    int lo[3], hi[3];                 // owned box: partition coordinates (use_partitions) or voxels
+    float unit_div; int gmax;
+    uint32_t* out; unsigned long long* count;
+};
+__global__ void __launch_bounds__(VOX_BLOCK) k_owner_filter(FilterJob Fj) {
+    // one thread block = one staging block of VOX_BLOCK consecutive triangles of the voxelizer
+    const unsigned long long t = (unsigned long long)blockIdx.x * VOX_BLOCK + threadIdx.x;
+    bool keep = false;
+    if (t < Fj.n_tris) {
+        const float* v = Fj.tris + t * Fj.fpt;
+        float c[9];
+#pragma unroll
+        for (int i = 0; i < 9; i++) c[i] = __ldg(v + i);
+        keep = true;
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            const float mn = stdmin(c[a], stdmin(c[3 + a], c[6 + a])), mx = stdmax(c[a], stdmax(c[3 + a], c[6 + a]));
+            int l, h;
+            if (Fj.use_partitions) slab_range(Fj.bmin, Fj.bmax, 1 << Fj.k, mn, mx, l, h);
+            else { l = clampi(f2i(fmul(mn, Fj.unit_div)), 0, Fj.gmax); h = clampi(f2i(fmul(mx, Fj.unit_div)), 0, Fj.gmax); }
+            keep = keep && !(h < Fj.lo[a] || l > Fj.hi[a]);
+        }
+    }
+    const int any = __syncthreads_or(keep ? 1 : 0);
+    if (any && threadIdx.x == 0) Fj.out[atomicAdd(Fj.count, 1ULL)] = blockIdx.x;
 }
 
 // ---------------------------------------------------------------------------
@@ -1059,6 +1125,19 @@ __global__ void __launch_bounds__(1024) k_fused_up(FusedJob F) {
             carry += total;
         }
         if (threadIdx.x == 0) L.ps[L.n] = carry;
+        if (L.pl) {                                   // leaf-count prefix (sharded table / global leaf ranks)
+            const unsigned long long* cpl = F.lv[j - 1].pl;
+            unsigned long long lc = 0;
+            for (unsigned long long b = 0; b < L.n; b += blockDim.x) {
+                const unsigned long long idx = b + threadIdx.x;
+                const unsigned long long v = idx < L.n ? cpl[L.fc[idx + 1]] - cpl[L.fc[idx]] : 0ULL;
+                unsigned long long total;
+                const unsigned long long ex = block_excl_scan(v, total);
+                if (idx < L.n) L.pl[idx] = lc + ex;
+                lc += total;
+            }
+            if (threadIdx.x == 0) L.pl[L.n] = lc;
+        }
         __syncthreads();
     }
 }
@@ -1110,6 +1189,16 @@ __global__ void __launch_bounds__(1024) k_fused_emit(FusedJob F) {
         }
         __syncthreads();
     }
+}
+
+// sharded: the records of the shared upper levels are computed on the host from the exchanged table
+// (a few thousand at most) and scattered into this rank's part of the node array
+__global__ void __launch_bounds__(256) k_scatter_records(const unsigned long long* pos, const unsigned long long* rec, unsigned long long n,
+                                                         unsigned long long* nodes /* biased by -node_lo */) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned long long* o = nodes + pos[i] * 3;
+    o[0] = rec[3 * i]; o[1] = rec[3 * i + 1]; o[2] = rec[3 * i + 2];
 }
 
 // sparse clear of all levels in one launch (blockIdx.y = level)

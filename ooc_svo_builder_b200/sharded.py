@@ -147,8 +147,11 @@ class DistributedBuilder:
         self.sb.shard_configure(self.rank, self.world)
         self.device = device
         self.table = None
+        self.stream = None
 
     def set_stream(self, stream):
+        """Run the library's kernels AND the table all-reduce on this torch stream (one queue, no race)."""
+        self.stream = stream
         self.sb.set_stream(stream.cuda_stream)
 
     def set_triangles(self, tris):
@@ -163,8 +166,14 @@ class DistributedBuilder:
         if self.table is None or self.table.numel() != n:
             self.table = self.torch.zeros(n, dtype=self.torch.int64, device="cuda:%d" % self.device)
         sb.shard_count(self.table.data_ptr())
-        self.dist.all_reduce(self.table)              # sum over ranks == union of disjoint entries (NCCL over NVLink)
-        return sb.shard_emit(self.table.data_ptr())
+        if self.stream is not None:
+            with self.torch.cuda.stream(self.stream):   # same queue as the kernels that filled / will read the table
+                self.dist.all_reduce(self.table)
+        else:
+            sb.synchronize()                            # the library runs on its own stream: order it against torch's
+            self.dist.all_reduce(self.table)
+            self.torch.cuda.current_stream().synchronize()
+        return sb.shard_emit(self.table.data_ptr())      # sum over ranks == union of disjoint entries (NCCL over NVLink)
 
     def close(self):
         self.sb.close()
@@ -312,6 +321,8 @@ def bench(args, rank, world, local, dist, peak, peak_src, ClockSampler):
                     "d2h_bytes_per_step": int(nn * 24 + nd * 32), "ms_per_step": e2e_s * 1e3,
                     "api": "svo_set_triangles + sharded step + svo_fetch_* per rank (pinned host buffers, wall clock, max over ranks)"},
             "gpu_launches": int(launches) * args.steps, "clocks": clocks,
+            "stage_ms_rank0": {k: st[k] for k in ("ms_partition", "ms_voxelize", "ms_vox_small", "ms_compact", "ms_build", "ms_emit", "ms_emit_leaf", "ms_clear")},
+            "pairs_rank0": {k: st[k] for k in ("n_pairs", "n_small", "n_medium", "n_large")},
         }
         print(json.dumps(line), flush=True)
     db.close()
