@@ -681,7 +681,7 @@ static int size_scans(svo_ctx* c, LevelBufs& L, const LevelBufs* child, bool pl,
 static int build_phase_a(svo_ctx* c, ull* table) {
     const int J = c->J;
     const bool payload = c->prm.payload != 0, levels = c->prm.generate_levels != 0;
-    const bool want_pl = levels || c->world > 1;       // leaf-count prefixes: only -levels data indices and the shard table need them
+    const bool want_pl = levels;                        // leaf-count prefixes: only the -levels data indices need them
     c->want_pl = want_pl;
     mark(c, EV_BUILD0);
     // ---- sync #1: how many non-zero words does every local level hold? ----
@@ -752,9 +752,13 @@ static int build_phase_a(svo_ctx* c, ull* table) {
     if (table) {
         CK(cudaMemsetAsync(table, 0, (size_t)c->WJ * 4 * sizeof(ull), c->stream));
         if (c->lv[J].n) {
-            k_table_fill<<<blocks_for(c->lv[J].n, 256), 256, 0, c->stream>>>(c->lv[J].key.as<ull>(), c->lv[J].mask.as<ull>(), c->lv[J].ps.as<ull>(),
-                                                                               want_pl ? c->lv[J].pl.as<ull>() : nullptr,
-                                                                               levels ? c->lv[J].pi.as<ull>() : nullptr, c->lv[J].n, table); LAUNCHED();
+            TableFillJob Tf;
+            memset(&Tf, 0, sizeof Tf);
+            Tf.key = c->lv[J].key.as<ull>(); Tf.mask = c->lv[J].mask.as<ull>(); Tf.ps = c->lv[J].ps.as<ull>();
+            Tf.pi = levels ? c->lv[J].pi.as<ull>() : nullptr;
+            for (int j = 0; j <= J; j++) Tf.fc[j] = c->lv[j].fc.as<ull>();
+            Tf.n = c->lv[J].n; Tf.J = J; Tf.table = table;
+            k_table_fill<<<blocks_for(c->lv[J].n, 256), 256, 0, c->stream>>>(Tf); LAUNCHED();
         }
     }
     mark(c, EV_CMP1);
@@ -1096,7 +1100,8 @@ static int build_phase_b(svo_ctx* c, const ull* table) {
     }
     c->built = true;
     c->stats.n_partitions = c->P;
-    c->stats.n_pairs = (c->P > 1 && !c->use_lists) ? c->h_pinned[42] : c->q_end - c->q_begin;
+    // inline enumeration does not count pairs on the device; the sum of the per-partition counts is known when they were requested
+    c->stats.n_pairs = (c->P > 1 && !c->use_lists) ? c->n_pairs : c->q_end - c->q_begin;
     c->stats.n_voxels = c->n_voxels; c->stats.n_nodes = c->n_nodes; c->stats.n_data = c->n_data;
     c->stats.n_medium = c->h_pinned[40]; c->stats.n_large = c->h_pinned[41];
     c->stats.n_small = c->stats.n_pairs - c->stats.n_medium - c->stats.n_large;

@@ -212,77 +212,88 @@ __host__ __device__ __forceinline__ uint64_t linear_to_morton64(uint64_t w) {
 }
 __host__ __device__ __forceinline__ int linear_to_morton_bit(int i) { return brick_bit(i & 3, (i >> 2) & 3, i >> 4); }
 
-// Conservative test of a whole 4x4x4 window of voxels anchored at (wx, wy, wz), branch free.
+// Conservative test of a whole 4x4x4 window of voxels anchored at (wx, wy, wz).
 // Returns the hit mask in the linear layout (bit = lz*16 + ly*4 + lx), restricted to the extents
 // (ea, eb, ec) <= 4 of the box inside the window. The nine edge functions only depend on two
 // coordinates each, so they are evaluated on three 4x4 projections (products hoisted per axis) and
 // expanded with multiplies; every rounded operation is the one the per-voxel test performs.
-// (ua, ub, uc) are WARP-UNIFORM upper bounds of (ea, eb, ec): rows / slices at or beyond them lie outside
-// every box of the warp and are skipped with uniform branches (their mask bits are don't-care: the box
-// mask clears them).
+//
+// (ub, uc) are WARP-UNIFORM upper bounds of (eb, ec): the row (y) and slice (z) loops run to them, so there is
+// no divergence; rows / slices beyond them lie outside every box of the warp. The loops are deliberately NOT
+// unrolled (only the 4 cells of a row are): fully unrolled, the kernel exceeded the instruction cache and
+// stalled on instruction fetch (ncu: no_instruction was the top stall reason).
+//
+// Mask assembly from sign bits: an edge value e = fadd(., ed) fails iff it is negative. ed is never -0 (its last
+// addend is std::max(0.0f, .) >= +0), so e is never -0, and a NaN result of a CUDA add is the canonical
+// 0x7FFFFFFF (sign clear, like the reference's "not < 0"). So fail = sign(e0)|sign(e1)|sign(e2), pushed into
+// the mask with one funnel shift per cell (cells visited from the highest bit down). The plane test rejects
+// iff fmul(a, b) > 0  <=>  sign(0 - fmul(a, b)) set (+-0 and NaN give a clear sign).
 __device__ __forceinline__ uint64_t eval_window(const TriSetup& s, float u, int wx, int wy, int wz, int ea, int eb, int ec,
-                                                int ua, int ub, int uc) {
-    float px[4], py[4], pz[4];
+                                                int ub, int uc) {
+    float px[4], py[4];
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-        px[i] = fmul((float)(wx + i), u);
-        py[i] = fmul((float)(wy + i), u);
-        pz[i] = fmul((float)(wz + i), u);
-    }
-    // Mask assembly from sign bits: an edge value e = fadd(., ed) fails iff it is negative. ed is never -0
-    // (its last addend is std::max(0.0f, .) >= +0), so e is never -0, and a NaN result of a CUDA add is the
-    // canonical 0x7FFFFFFF (sign clear, like the reference's "not < 0"). So fail = sign(e0)|sign(e1)|sign(e2),
-    // pushed into the mask with one funnel shift per cell (cells visited from the highest bit down).
-    uint32_t fxy = 0, fyz = 0, fzx = 0;     // FAIL masks
-    {   // XY: edges 0..2, a = x, b = y; bit ly*4 + lx
-        float A[3][4], B[3][4];
+    for (int i = 0; i < 4; i++) { px[i] = fmul((float)(wx + i), u); py[i] = fmul((float)(wy + i), u); }
+    // ---- XY: edges 0..2, a = x, b = y; bit ly*4 + lx; rows = ly ----
+    uint32_t fxy = 0;
+    {
+        float A[3][4];
 #pragma unroll
         for (int j = 0; j < 3; j++)
 #pragma unroll
-            for (int i = 0; i < 4; i++) { A[j][i] = fmul(s.ea[j], px[i]); B[j][i] = fmul(s.eb[j], py[i]); }
-#pragma unroll
-        for (int ly = 3; ly >= 0; ly--) {
-            if (ly >= ub) { fxy <<= 4; continue; }
+            for (int i = 0; i < 4; i++) A[j][i] = fmul(s.ea[j], px[i]);
+#pragma unroll 1
+        for (int ly = ub - 1; ly >= 0; ly--) {
+            const float pyr = fmul((float)(wy + ly), u);
+            const float b0 = fmul(s.eb[0], pyr), b1 = fmul(s.eb[1], pyr), b2 = fmul(s.eb[2], pyr);
 #pragma unroll
             for (int lx = 3; lx >= 0; lx--) {
-                const uint32_t f = __float_as_uint(fadd(fadd(A[0][lx], B[0][ly]), s.ed[0])) | __float_as_uint(fadd(fadd(A[1][lx], B[1][ly]), s.ed[1])) |
-                                   __float_as_uint(fadd(fadd(A[2][lx], B[2][ly]), s.ed[2]));
+                const uint32_t f = __float_as_uint(fadd(fadd(A[0][lx], b0), s.ed[0])) | __float_as_uint(fadd(fadd(A[1][lx], b1), s.ed[1])) |
+                                   __float_as_uint(fadd(fadd(A[2][lx], b2), s.ed[2]));
                 fxy = __funnelshift_l(f, fxy, 1);
             }
         }
     }
-    {   // YZ: edges 3..5, a = y, b = z; bit lz*4 + ly
-        float A[3][4], B[3][4];
+    // ---- YZ (edges 3..5, a = y, b = z, bit lz*4 + ly), ZX (edges 6..8, a = z, b = x, bit lz*4 + lx) and the
+    //      plane test (voxelizer.cpp:266-268; n.p summed x, then y, then z like dot3): rows = lz ----
+    uint32_t fyz = 0, fzx = 0;
+    uint64_t reject = 0;
+    {
+        float Ayz[3][4], Bzx[3][4], nxp[4];
 #pragma unroll
         for (int j = 0; j < 3; j++)
 #pragma unroll
-            for (int i = 0; i < 4; i++) { A[j][i] = fmul(s.ea[3 + j], py[i]); B[j][i] = fmul(s.eb[3 + j], pz[i]); }
+            for (int i = 0; i < 4; i++) { Ayz[j][i] = fmul(s.ea[3 + j], py[i]); Bzx[j][i] = fmul(s.eb[6 + j], px[i]); }
 #pragma unroll
-        for (int lz = 3; lz >= 0; lz--) {
-            if (lz >= uc) { fyz <<= 4; continue; }
+        for (int i = 0; i < 4; i++) nxp[i] = fmul(s.nx, px[i]);
+#pragma unroll 1
+        for (int lz = uc - 1; lz >= 0; lz--) {
+            const float pzr = fmul((float)(wz + lz), u);
+            const float by0 = fmul(s.eb[3], pzr), by1 = fmul(s.eb[4], pzr), by2 = fmul(s.eb[5], pzr);
+            const float az0 = fmul(s.ea[6], pzr), az1 = fmul(s.ea[7], pzr), az2 = fmul(s.ea[8], pzr);
+            const float nzp = fmul(s.nz, pzr);
 #pragma unroll
             for (int ly = 3; ly >= 0; ly--) {
-                const uint32_t f = __float_as_uint(fadd(fadd(A[0][ly], B[0][lz]), s.ed[3])) | __float_as_uint(fadd(fadd(A[1][ly], B[1][lz]), s.ed[4])) |
-                                   __float_as_uint(fadd(fadd(A[2][ly], B[2][lz]), s.ed[5]));
+                const uint32_t f = __float_as_uint(fadd(fadd(Ayz[0][ly], by0), s.ed[3])) | __float_as_uint(fadd(fadd(Ayz[1][ly], by1), s.ed[4])) |
+                                   __float_as_uint(fadd(fadd(Ayz[2][ly], by2), s.ed[5]));
                 fyz = __funnelshift_l(f, fyz, 1);
             }
-        }
-    }
-    {   // ZX: edges 6..8, a = z, b = x; bit lz*4 + lx
-        float A[3][4], B[3][4];
-#pragma unroll
-        for (int j = 0; j < 3; j++)
-#pragma unroll
-            for (int i = 0; i < 4; i++) { A[j][i] = fmul(s.ea[6 + j], pz[i]); B[j][i] = fmul(s.eb[6 + j], px[i]); }
-#pragma unroll
-        for (int lz = 3; lz >= 0; lz--) {
-            if (lz >= uc) { fzx <<= 4; continue; }
 #pragma unroll
             for (int lx = 3; lx >= 0; lx--) {
-                const uint32_t f = __float_as_uint(fadd(fadd(A[0][lz], B[0][lx]), s.ed[6])) | __float_as_uint(fadd(fadd(A[1][lz], B[1][lx]), s.ed[7])) |
-                                   __float_as_uint(fadd(fadd(A[2][lz], B[2][lx]), s.ed[8]));
+                const uint32_t f = __float_as_uint(fadd(fadd(az0, Bzx[0][lx]), s.ed[6])) | __float_as_uint(fadd(fadd(az1, Bzx[1][lx]), s.ed[7])) |
+                                   __float_as_uint(fadd(fadd(az2, Bzx[2][lx]), s.ed[8]));
                 fzx = __funnelshift_l(f, fzx, 1);
             }
+            uint32_t rs = 0;
+#pragma unroll 1
+            for (int ly = ub - 1; ly >= 0; ly--) {
+                const float nyp = fmul(s.ny, fmul((float)(wy + ly), u));
+#pragma unroll
+                for (int lx = 3; lx >= 0; lx--) {
+                    const float nd = fadd(fadd(nxp[lx], nyp), nzp);
+                    rs = __funnelshift_l(__float_as_uint(fsub(0.0f, fmul(fadd(nd, s.d1), fadd(nd, s.d2)))), rs, 1);
+                }
+            }
+            reject |= (uint64_t)(rs & 0xffffu) << (16 * lz);
         }
     }
     const uint32_t mxy = ~fxy & 0xffffu, myz = ~fyz & 0xffffu, mzx = ~fzx & 0xffffu;
@@ -303,34 +314,7 @@ __device__ __forceinline__ uint64_t eval_window(const TriSetup& s, float u, int 
     cand &= (uint64_t)((1u << ea) - 1u) * 0x1111111111111111ULL;
     cand &= (uint64_t)((1u << (4 * eb)) - 1u) * 0x0001000100010001ULL;
     cand &= lowmask(16 * ec);
-    if (cand == 0ULL) return 0ULL;
-    // plane test (voxelizer.cpp:266-268): n.p summed x, then y, then z, exactly like dot3
-    float nxp[4], nyp[4], nzp[4];
-#pragma unroll
-    for (int i = 0; i < 4; i++) { nxp[i] = fmul(s.nx, px[i]); nyp[i] = fmul(s.ny, py[i]); nzp[i] = fmul(s.nz, pz[i]); }
-    // reject iff fmul(a, b) > 0  <=>  sign(0 - fmul(a, b)) set (+-0 and NaN give a clear sign)
-    uint32_t rlo = 0, rhi = 0;              // REJECT masks, bit = lz*16 + ly*4 + lx
-    float sxy[4][4];
-#pragma unroll
-    for (int ly = 0; ly < 4; ly++)
-#pragma unroll
-        for (int lx = 0; lx < 4; lx++) sxy[ly][lx] = fadd(nxp[lx], nyp[ly]);
-#pragma unroll
-    for (int lz = 3; lz >= 0; lz--) {
-        if (lz >= uc) continue;                 // (a skipped slice is the top of its half: no shift needed, the bits stay clear)
-#pragma unroll
-        for (int ly = 3; ly >= 0; ly--) {
-            if (ly >= ub) { if (lz >= 2) rhi <<= 4; else rlo <<= 4; continue; }
-#pragma unroll
-            for (int lx = 3; lx >= 0; lx--) {
-                const float nd = fadd(sxy[ly][lx], nzp[lz]);
-                const uint32_t r = __float_as_uint(fsub(0.0f, fmul(fadd(nd, s.d1), fadd(nd, s.d2))));
-                if (lz >= 2) rhi = __funnelshift_l(r, rhi, 1); else rlo = __funnelshift_l(r, rlo, 1);
-            }
-        }
-    }
-    const uint32_t plo = ~rlo, phi = ~rhi;
-    return cand & (((uint64_t)phi << 32) | plo);
+    return cand & ~reject;
 }
 
 struct GridBox { int x0, x1, y0, y1, z0, z1; };

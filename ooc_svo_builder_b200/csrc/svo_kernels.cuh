@@ -227,12 +227,15 @@ __device__ __forceinline__ void vox_small_body(const VoxJob& J, bool active, uin
     }
     const int most = ENUM ? __reduce_max_sync(0xffffffffu, count) : 1;   // warp-uniform trip count (1 almost always)
     TriSetup s;
-    bool have_setup = false;
+    if (count > 0) tri_setup(v, J.u, s);
+    const uint32_t part0 = enumerate ? (uint32_t)morton3((uint32_t)lx, (uint32_t)ly, (uint32_t)lz) : part;
     for (int it = 0; it < most; it++) {
         bool valid = it < count;
-        if (valid && enumerate) {
-            part = (uint32_t)morton3((uint32_t)(lx + it % nx), (uint32_t)(ly + (it / nx) % ny), (uint32_t)(lz + it / (nx * ny)));
-            valid = part >= J.p_first && part <= J.p_last;         // partitions of other ranks
+        if (enumerate) {
+            part = part0;
+            if (it > 0 && valid)     // rare: a triangle that straddles a partition boundary
+                part = (uint32_t)morton3((uint32_t)(lx + it % nx), (uint32_t)(ly + (it / nx) % ny), (uint32_t)(lz + it / (nx * ny)));
+            valid = valid && part >= J.p_first && part <= J.p_last;         // partitions of other ranks
         }
         int cls = -1;
         GridBox b = { 0, -1, 0, -1, 0, -1 };
@@ -252,22 +255,16 @@ __device__ __forceinline__ void vox_small_body(const VoxJob& J, bool active, uin
             const unsigned long long e = ((unsigned long long)part << 32) | tri;
             warp_push(&J.qcount[0], J.queue[0], J.qcap, &J.qcount[3], cls == 1, e);
             warp_push(&J.qcount[1], J.queue[1], J.qcap, &J.qcount[3], cls == 2, e);
-            if (enumerate) {                                      // statistics: pairs seen by this context
-                const unsigned m = __ballot_sync(0xffffffffu, valid);
-                if ((threadIdx.x & 31) == 0 && m) atomicAdd(&J.qcount[2], (unsigned long long)__popc(m));
-            }
         }
         // warp-uniform upper bounds of the window extents (convergent point: every lane is here)
-        const int ua = min(4, __reduce_max_sync(0xffffffffu, cls == 0 ? b.x1 - b.x0 + 1 : 0));
         const int ub = min(4, __reduce_max_sync(0xffffffffu, cls == 0 ? b.y1 - b.y0 + 1 : 0));
         const int uc = min(4, __reduce_max_sync(0xffffffffu, cls == 0 ? b.z1 - b.z0 + 1 : 0));
         if (cls == 0) {
-            if (!have_setup) { tri_setup(v, J.u, s); have_setup = true; }
             for (int wz = b.z0; wz <= b.z1; wz += 4)
                 for (int wy = b.y0; wy <= b.y1; wy += 4)
                     for (int wx = b.x0; wx <= b.x1; wx += 4) {
                         const unsigned long long hits = eval_window(s, J.u, wx, wy, wz, min(4, b.x1 - wx + 1), min(4, b.y1 - wy + 1),
-                                                                    min(4, b.z1 - wz + 1), ua, ub, uc);
+                                                                    min(4, b.z1 - wz + 1), ub, uc);
                         if (hits) emit_window<OWNER>(J, wx, wy, wz, hits, tri);
                     }
         }
@@ -702,16 +699,26 @@ __global__ void __launch_bounds__(1024) k_compact_top(const unsigned long long* 
 // The exchange table: one entry of 4 u64 per GLOBAL level-J word: {mask, subtree size S, leaves, internal nodes}.
 // Every rank writes the entries of its own words (all others stay zero), the caller sums the tables of
 // all ranks (NCCL all-reduce; the entries are disjoint, so the sum is the union).
-__global__ void __launch_bounds__(256) k_table_fill(const unsigned long long* key, const unsigned long long* mask, const unsigned long long* ps,
-                                                    const unsigned long long* pl, const unsigned long long* pi, unsigned long long n,
-                                                    unsigned long long* table) {
+struct TableFillJob {
+    const unsigned long long* key; const unsigned long long* mask; const unsigned long long* ps;
+    const unsigned long long* pi;                  // -levels only
+    const unsigned long long* fc[MAX_LEVELS];      // child-prefix arrays of levels 0..J: chasing them gives leaf ranks
+    unsigned long long n; int J;
+    unsigned long long* table;
+};
+// first leaf rank below tile i of level J: follow the first-child links down to level 0
+__device__ __forceinline__ unsigned long long first_leaf_below(const TableFillJob& T, unsigned long long i) {
+    for (int j = T.J; j >= 0; j--) i = T.fc[j][i];
+    return i;
+}
+__global__ void __launch_bounds__(256) k_table_fill(TableFillJob T) {
     const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    unsigned long long* e = table + key[i] * 4ULL;
-    e[0] = mask[i];
-    e[1] = ps[i + 1] - ps[i];
-    e[2] = pl ? pl[i + 1] - pl[i] : 0ULL;
-    e[3] = pi ? pi[i + 1] - pi[i] : 0ULL;
+    if (i >= T.n) return;
+    unsigned long long* e = T.table + T.key[i] * 4ULL;
+    e[0] = T.mask[i];
+    e[1] = T.ps[i + 1] - T.ps[i];
+    e[2] = first_leaf_below(T, i + 1) - first_leaf_below(T, i);     // fc[j][n_j] = n_{j-1}: the chain is valid for i = n too
+    e[3] = T.pi ? T.pi[i + 1] - T.pi[i] : 0ULL;
 }
 // Unpack the summed table into dense columns and rebuild the (tiny, replicated) upper dense levels.
 __global__ void __launch_bounds__(256) k_table_unpack(const unsigned long long* table, unsigned long long n, unsigned long long* dmask,
