@@ -178,6 +178,23 @@ int exscan(svo_ctx* c, F f, ull n, ull* out) {
     return SVO_OK;
 }
 
+// child prefix (fc) and subtree-size prefix (ps) of the brick level in one reduce / scan / rescan
+int exscan_level0(svo_ctx* c, const ull* mask, ull n, ull* fc, ull* ps) {
+    if (n == 0) {
+        CK(cudaMemsetAsync(fc, 0, sizeof(ull), c->stream));
+        CK(cudaMemsetAsync(ps, 0, sizeof(ull), c->stream));
+        return SVO_OK;
+    }
+    const ull nt = (n + SCAN_TILE - 1) / SCAN_TILE;
+    CK(c->scan_tmp.ensure(2 * (nt + 1) * sizeof(ull)));
+    ull* ta = c->scan_tmp.as<ull>();
+    ull* tb = ta + (nt + 1);
+    k_scan2_reduce<<<(unsigned)nt, SCAN_THREADS, 0, c->stream>>>(mask, n, ta, tb); LAUNCHED();
+    k_scan2_tiles<<<1, 1024, 0, c->stream>>>(ta, tb, nt); LAUNCHED();
+    k_scan2_final<<<(unsigned)nt, SCAN_THREADS, 0, c->stream>>>(mask, n, ta, tb, fc, ps); LAUNCHED();
+    return SVO_OK;
+}
+
 int ilog2u(uint64_t v) { int r = -1; while (v) { v >>= 1; r++; } return r; }
 
 // Allocates (and zeroes) the dense pyramid for the current geometry (gridsize, shard).
@@ -724,7 +741,10 @@ static int build_phase_a(svo_ctx* c, ull* table) {
                                                 (payload && J == 0) ? c->tileidx.as<uint32_t>() : nullptr, J == 0 ? 1 : 0); LAUNCHED();
     }
     for (int j = J; j >= 0; j--) {
-        if (!jf || j < jf) {
+        if (j == 0 && !levels && (!jf || jf > 0)) {
+            int rc = exscan_level0(c, c->lv[0].mask.as<ull>(), c->lv[0].n, c->lv[0].fc.as<ull>(), c->lv[0].ps.as<ull>());
+            if (rc) return rc;
+        } else if (!jf || j < jf) {
             PopcOp op{ c->lv[j].mask.as<ull>() };
             int rc = exscan(c, op, c->lv[j].n, c->lv[j].fc.as<ull>());
             if (rc) return rc;
@@ -738,6 +758,7 @@ static int build_phase_a(svo_ctx* c, ull* table) {
     // ---- bottom-up: subtree sizes (+ leaf / internal counts) ----
     for (int j = 0; j <= J; j++) {
         if (jf && j >= jf) break;
+        if (j == 0 && !levels) continue;                 // done together with fc by exscan_level0
         int rc = size_scans(c, c->lv[j], j ? &c->lv[j - 1] : nullptr, want_pl, levels);
         if (rc) return rc;
     }
