@@ -59,7 +59,7 @@ def build_cli(force: bool = False) -> list[str]:
             continue
         _run(["g++", "-std=c++17", "-O2", "-Wall", *defs, "-I" + os.path.join(ROOT, "include"),
               os.path.join(HOST, "svo_builder_main.cpp"), "-o", out,
-              "-L" + os.path.dirname(LIB), "-lsvo_b200", "-Wl,-rpath,$ORIGIN/../lib"])
+              "-L" + os.path.dirname(LIB), "-lsvo_b200", "-lpthread", "-Wl,-rpath,$ORIGIN/../lib"])
     return outs
 
 

@@ -16,7 +16,7 @@ typedef unsigned long long ull;
 
 namespace {
 
-thread_local std::string g_create_error;
+std::string g_create_error;          // svo_ctx_create failures (process-wide: the CLI creates the context on a helper thread)
 
 struct DevBuf {
     void* p = nullptr;

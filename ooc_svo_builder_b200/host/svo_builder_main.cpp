@@ -20,6 +20,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <future>
 #include <iostream>
 #include <sstream>
 #include <string>
@@ -223,13 +224,20 @@ int main(int argc, char** argv) {
         return 0;
     }
 
+    // CUDA start-up (driver + context, ~1 s) runs in the background while the triangle file is read. Only the
+    // chosen GPU is made visible to this process: initialising all eight devices of a box costs far more.
+    if (!std::getenv("CUDA_VISIBLE_DEVICES")) {
+        const std::string dev = std::to_string(opt.device);
+        setenv("CUDA_VISIBLE_DEVICES", dev.c_str(), 1);
+    }
+    const int device_index = std::getenv("SVO_KEEP_DEVICE_INDEX") ? opt.device : 0;
     svo_ctx* ctx = nullptr;
-    if (svo_ctx_create(opt.device, &ctx) != SVO_OK) die(nullptr, "svo_ctx_create");
+    std::future<int> ctx_ready = std::async(std::launch::async, [&ctx, device_index]() { return svo_ctx_create(device_index, &ctx); });
 
-    // triangle records straight into pinned memory, one large sequential read (replaces TriReader's 8192-triangle loop)
+    // triangle records with one large sequential read (replaces TriReader's 8192-triangle fread loop)
     const size_t tri_bytes = (size_t)hdr.n_triangles * kFloatsPerTri * sizeof(float);
-    float* tris = static_cast<float*>(svo_host_alloc(tri_bytes));
-    if (!tris) { std::cout << "Error: cannot allocate " << tri_bytes << " bytes of pinned host memory" << std::endl; return 0; }
+    float* tris = static_cast<float*>(std::malloc(tri_bytes ? tri_bytes : 1));
+    if (!tris) { std::cout << "Error: cannot allocate " << tri_bytes << " bytes of host memory" << std::endl; return 0; }
     {
         FILE* f = std::fopen(tridata.c_str(), "rb");
         size_t got = 0;
@@ -241,6 +249,7 @@ int main(int argc, char** argv) {
         std::fclose(f);
         if (got != tri_bytes) { std::cout << "Error: " << tridata << " holds " << got << " bytes, header promises " << tri_bytes << std::endl; return 0; }
     }
+    if (ctx_ready.get() != SVO_OK) die(nullptr, "svo_ctx_create");
     const double ms_in = t_in.ms();
 
     // ---- partitioning ----------------------------------------------------
@@ -293,18 +302,25 @@ int main(int argc, char** argv) {
     name << hdr.base << opt.gridsize << "_" << P;              // partitioner.cpp:90/141
     const std::string out_base = name.str();
     const size_t budget = std::max<size_t>((size_t)opt.memory_limit << 20, 1u << 20);
-    const size_t chunk_bytes = std::min<size_t>(budget, 256u << 20);
-    void* chunk = svo_host_alloc(chunk_bytes);
-    if (!chunk) { std::cout << "Error: cannot allocate pinned output buffer" << std::endl; return 0; }
+    const size_t chunk_bytes = std::min<size_t>(budget / 2, 128u << 20);          // two chunks in flight stay inside the -l budget
+    void* chunk[2] = { svo_host_alloc(chunk_bytes), svo_host_alloc(chunk_bytes) };
+    if (!chunk[0] || !chunk[1]) { std::cout << "Error: cannot allocate pinned output buffers" << std::endl; return 0; }
+    // device -> pinned chunk (svo_fetch_*) overlaps with fwrite of the previous chunk
     auto stream_out = [&](const std::string& path, uint64_t count, uint64_t rec, int (*fetch)(svo_ctx*, uint64_t, uint64_t, void*)) {
         FILE* f = std::fopen(path.c_str(), "wb");
         if (!f) { std::cout << "Error: cannot open " << path << " for writing" << std::endl; std::exit(0); }
         const uint64_t per = chunk_bytes / rec;
-        for (uint64_t first = 0; first < count; first += per) {
+        std::future<void> writing[2];
+        int slot = 0;
+        for (uint64_t first = 0; first < count; first += per, slot ^= 1) {
             const uint64_t n = std::min<uint64_t>(per, count - first);
-            if (fetch(ctx, first, n, chunk) != SVO_OK) die(ctx, "svo_fetch");
-            std::fwrite(chunk, rec, n, f);
+            if (writing[slot].valid()) writing[slot].get();
+            if (fetch(ctx, first, n, chunk[slot]) != SVO_OK) die(ctx, "svo_fetch");
+            void* src = chunk[slot];
+            writing[slot] = std::async(std::launch::async, [f, src, rec, n]() { std::fwrite(src, rec, n, f); });
+            if (writing[slot ^ 1].valid()) writing[slot ^ 1].get();          // keep the file writes in order
         }
+        for (auto& w : writing) if (w.valid()) w.get();
         std::fclose(f);
     };
     stream_out(out_base + ".octreenodes", n_nodes, SVO_NODE_BYTES, svo_fetch_nodes);
@@ -330,8 +346,9 @@ int main(int argc, char** argv) {
         std::cout << "  pairs: " << st.n_pairs << " (small " << st.n_small << ", medium " << st.n_medium << ", large " << st.n_large << ")\n"
                   << "  nodes: " << st.n_nodes << "  data: " << st.n_data << "  kernel launches: " << st.kernel_launches << std::endl;
     }
-    svo_host_free(chunk);
-    svo_host_free(tris);
+    svo_host_free(chunk[0]);
+    svo_host_free(chunk[1]);
+    std::free(tris);
     svo_ctx_destroy(ctx);
     return 0;
 }
