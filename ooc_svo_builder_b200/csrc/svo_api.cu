@@ -109,6 +109,7 @@ struct svo_ctx {
     bool want_pl = false, phase_a_done = false;
     int jf = 0;                        // fused single-block kernels handle local levels jf..J (0 = not fused)
     bool use_lists = false;            // SVO_PARTITION_LISTS=1: build per-partition index lists (count / scan / fill)
+    float inv_slab = 0.f;
     float slab_min[32], slab_max[32];  // world slabs of the partition grid (partitioner.cpp:54-59)
     ull p_first = 0, p_last = 0;
     DevBuf table_own, dcol[4];
@@ -246,6 +247,7 @@ VoxJob make_voxjob(svo_ctx* c) {
     J.part_off = lists ? c->part_off.as<uint64_t>() : nullptr;
     for (int i = 0; i < 32; i++) { J.bmin[i] = c->slab_min[i]; J.bmax[i] = c->slab_max[i]; }
     J.p_first = (uint32_t)c->p_first; J.p_last = (uint32_t)c->p_last;
+    J.inv_slab = c->inv_slab;
     J.qcap = c->qcap;
     J.P = (uint32_t)c->P;
     J.k = (uint32_t)c->k;
@@ -506,6 +508,7 @@ int svo_partition(svo_ctx* c, const svo_params* params, uint64_t* n_partitions, 
         memset(&B, 0, sizeof B);
         B.tris = c->d_tris; B.fpt = (uint32_t)c->fpt; B.n_tris = c->n_tris; B.k = (uint32_t)c->k; B.P = (uint32_t)c->P;
         const float unit_part = (params->bbox_max0 - params->bbox_min0) / (float)g;   // partitioner.cpp:45
+        c->inv_slab = B.inv_slab = 1.0f / ((float)c->side * unit_part);
         for (uint32_t i = 0; i < (1u << c->k); i++) {
             c->slab_min[i] = B.bmin[i] = (float)(uint32_t)(i * c->side) * unit_part;                    // :54-56
             c->slab_max[i] = B.bmax[i] = (float)(uint32_t)((i + 1) * c->side - 1 + 1u) * unit_part;     // :57-59
@@ -1125,7 +1128,8 @@ static int build_phase_b(svo_ctx* c, const ull* table) {
     c->stats.n_pairs = (c->P > 1 && !c->use_lists) ? c->n_pairs : c->q_end - c->q_begin;
     c->stats.n_voxels = c->n_voxels; c->stats.n_nodes = c->n_nodes; c->stats.n_data = c->n_data;
     c->stats.n_medium = c->h_pinned[40]; c->stats.n_large = c->h_pinned[41];
-    c->stats.n_small = c->stats.n_pairs - c->stats.n_medium - c->stats.n_large;
+    const ull queued = c->stats.n_medium + c->stats.n_large;
+    c->stats.n_small = c->stats.n_pairs >= queued ? c->stats.n_pairs - queued : 0;   // n_pairs is 0 when the pairs were not counted
     c->stats.ms_upload = span(c, EV_UP0, EV_UP1);
     c->stats.ms_partition = span(c, EV_PART0, EV_PART1);
     c->stats.ms_voxelize = span(c, EV_VOX0, EV_VOX1);

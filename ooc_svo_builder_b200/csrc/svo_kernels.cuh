@@ -46,6 +46,7 @@ struct VoxJob {
     // inline partition enumeration (pair_tri == NULL, P > 1): world slabs of the partition grid and the
     // Morton range of partitions this context owns
     float bmin[32], bmax[32];
+    float inv_slab;                   // ~ 1 / world width of a partition slab (estimate only)
     uint32_t p_first, p_last;
     const uint32_t* subset;               // sharded: triangles that touch this rank's slab (NULL = all triangles)
     const unsigned long long* subset_count;
@@ -117,12 +118,19 @@ __device__ __forceinline__ bool restrict_to_slab(const VoxJob& J, GridBox& b) {
 }
 
 // Partition slabs touched by the interval [mn, mx]: slab i is kept unless (mx < bmin[i]) or (mn > bmax[i])
-// (intersectBoxBox, intersection.h:50-53, per axis). The kept slabs form a contiguous range [lo, hi].
-__device__ __forceinline__ void slab_range(const float* bmin, const float* bmax, int n, float mn, float mx, int& lo, int& hi) {
-    lo = n; hi = -1;
-    for (int i = 0; i < n; i++) {
-        if (!(mx < bmin[i]) && !(mn > bmax[i])) { if (i < lo) lo = i; hi = i; }
-    }
+// (intersectBoxBox, intersection.h:50-53, per axis). bmin / bmax increase with i, so the kept slabs are the
+// range [lo, hi] with lo = first i with !(mn > bmax[i]) and hi = last i with !(mx < bmin[i]) (empty if lo > hi).
+// Both ends are found from an estimated slab (inv_w ~ 1 / slab width, a hint only) and fixed up with the
+// exact comparisons, so the result is the one a scan over all slabs gives (NaN compares false, as there).
+__device__ __forceinline__ void slab_range(const float* bmin, const float* bmax, int n, float inv_w, float mn, float mx, int& lo, int& hi) {
+    int i = clampi(__float2int_rz(fmul(mn, inv_w)), 0, n - 1);
+    while (i > 0 && !(mn > bmax[i - 1])) i--;
+    while (i < n && (mn > bmax[i])) i++;
+    lo = i;
+    int j = clampi(__float2int_rz(fmul(mx, inv_w)), 0, n - 1);
+    while (j < n - 1 && !(mx < bmin[j + 1])) j++;
+    while (j >= 0 && (mx < bmin[j])) j--;
+    hi = j;
 }
 
 // Warp-aggregated queue push; must be called by all 32 lanes.
@@ -218,9 +226,9 @@ __device__ __forceinline__ void vox_small_body(const VoxJob& J, bool active, uin
         count = 1;
         if (enumerate) {
             int hx, hy, hz;
-            slab_range(J.bmin, J.bmax, 1 << J.k, stdmin(v[0], stdmin(v[3], v[6])), stdmax(v[0], stdmax(v[3], v[6])), lx, hx);
-            slab_range(J.bmin, J.bmax, 1 << J.k, stdmin(v[1], stdmin(v[4], v[7])), stdmax(v[1], stdmax(v[4], v[7])), ly, hy);
-            slab_range(J.bmin, J.bmax, 1 << J.k, stdmin(v[2], stdmin(v[5], v[8])), stdmax(v[2], stdmax(v[5], v[8])), lz, hz);
+            slab_range(J.bmin, J.bmax, 1 << J.k, J.inv_slab, stdmin(v[0], stdmin(v[3], v[6])), stdmax(v[0], stdmax(v[3], v[6])), lx, hx);
+            slab_range(J.bmin, J.bmax, 1 << J.k, J.inv_slab, stdmin(v[1], stdmin(v[4], v[7])), stdmax(v[1], stdmax(v[4], v[7])), ly, hy);
+            slab_range(J.bmin, J.bmax, 1 << J.k, J.inv_slab, stdmin(v[2], stdmin(v[5], v[8])), stdmax(v[2], stdmax(v[5], v[8])), lz, hz);
             nx = max(hx - lx + 1, 0); ny = max(hy - ly + 1, 0);
             count = nx * ny * max(hz - lz + 1, 0);
         }
@@ -450,6 +458,7 @@ struct BinJob {
     uint64_t n_tris;
     uint32_t k, P;
     float bmin[32], bmax[32];         // world slab [bmin[i], bmax[i]] of slab i (same on every axis)
+    float inv_slab;
     unsigned long long* counts;       // P
     unsigned long long* cursor;       // P (fill pass)
     const unsigned long long* off;    // P+1 (fill pass)
@@ -457,7 +466,7 @@ struct BinJob {
 };
 
 __device__ __forceinline__ void slab_range(const BinJob& B, float mn, float mx, int& lo, int& hi) {
-    slab_range(B.bmin, B.bmax, 1 << B.k, mn, mx, lo, hi);
+    slab_range(B.bmin, B.bmax, 1 << B.k, B.inv_slab, mn, mx, lo, hi);
 }
 
 template <bool FILL>
@@ -535,10 +544,14 @@ __global__ void __launch_bounds__(VOX_BLOCK) k_owner_filter(FilterJob Fj) {
 #pragma unroll
         for (int a = 0; a < 3; a++) {
             const float mn = stdmin(c[a], stdmin(c[3 + a], c[6 + a])), mx = stdmax(c[a], stdmax(c[3 + a], c[6 + a]));
-            int l, h;
-            if (Fj.use_partitions) slab_range(Fj.bmin, Fj.bmax, 1 << Fj.k, mn, mx, l, h);
-            else { l = clampi(f2i(fmul(mn, Fj.unit_div)), 0, Fj.gmax); h = clampi(f2i(fmul(mx, Fj.unit_div)), 0, Fj.gmax); }
-            keep = keep && !(h < Fj.lo[a] || l > Fj.hi[a]);
+            if (Fj.use_partitions) {
+                // the kept slab range [L, H] meets the owned slabs [lo, hi] iff H >= lo and L <= hi; by monotonicity of
+                // the slab tables that is (mx >= bmin[lo]) and (mn <= bmax[hi]) -- two compares instead of a slab search
+                keep = keep && !(mx < Fj.bmin[Fj.lo[a]]) && !(mn > Fj.bmax[Fj.hi[a]]);
+            } else {
+                const int l = clampi(f2i(fmul(mn, Fj.unit_div)), 0, Fj.gmax), h = clampi(f2i(fmul(mx, Fj.unit_div)), 0, Fj.gmax);
+                keep = keep && !(h < Fj.lo[a] || l > Fj.hi[a]);
+            }
         }
     }
     const int any = __syncthreads_or(keep ? 1 : 0);
