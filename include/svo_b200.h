@@ -73,6 +73,7 @@ typedef struct svo_stats {
     float ms_vox_small;         /* k_vox_small alone (subset of ms_voxelize)                   */
     float ms_emit_leaf;         /* k_emit_leaf alone (subset of ms_emit)                       */
     float ms_compact;           /* level counts + top-down tile-list expansion + subtree sizes */
+    float ms_dispatch;          /* multi-GPU triangle dispatch over peer memory (count + send + wait) */
     uint32_t kernel_launches;   /* kernels launched by the last run                            */
 } svo_stats;
 
@@ -163,7 +164,8 @@ int svo_fetch_voxel_codes(svo_ctx* ctx, uint64_t* dst, uint64_t capacity, uint64
  * upper levels itself and emits its own contiguous range of the output files.
  *
  *   svo_shard_configure(rank, world)  before svo_partition
- *   svo_partition, svo_voxelize       as on one GPU (every rank sees all triangles)
+ *   svo_partition, svo_voxelize       as on one GPU (every rank sees all triangles, or the ones the
+ *                                     triangle dispatch below routed to it)
  *   svo_shard_table_size              u64 count of the table
  *   svo_shard_count(dev_table)        local build phase; zeroes the table, writes own entries
  *   <all-reduce(sum) dev_table>       the caller's collective
@@ -177,6 +179,41 @@ int svo_shard_table_size(svo_ctx* ctx, uint64_t* n_u64);
 int svo_shard_count(svo_ctx* ctx, uint64_t* dev_table);
 int svo_shard_emit(svo_ctx* ctx, const uint64_t* dev_table, uint64_t* n_voxels, uint64_t* n_nodes, uint64_t* n_data);
 int svo_shard_ranges(svo_ctx* ctx, uint64_t* node_lo, uint64_t* node_hi, uint64_t* data_lo, uint64_t* data_hi);
+
+/* ---- multi-GPU: triangle dispatch over NVLink peer memory -------------------
+ *
+ * Replaces, for the sharded build, the reference's partition files as the way
+ * triangles reach the worker that voxelizes them (partitioner.cpp:101-149 writes
+ * every triangle into the .tripdata file of each partition it touches; here it
+ * is written into the HBM of each RANK whose slab it touches). Every rank starts
+ * with a contiguous slice of the .tridata file in its own HBM (rank r holds the
+ * r-th slice, in file order); one kernel pass counts, a second writes the
+ * records straight into the peers' inboxes with NVLink stores -- no host
+ * staging, no NCCL on the data path. The inbox ends up ordered by (source rank,
+ * position in the slice) = file order, so the payload rule "first triangle in
+ * file order wins" (voxelizer.cpp:263) is kept. After svo_shard_dispatch_finish
+ * the inbox IS the context's triangle set (as after svo_set_triangles_device):
+ * continue with svo_partition / svo_voxelize / svo_shard_count / ... as usual.
+ *
+ *   svo_shard_dispatch_create(capacity, fpt, &inbox, &ctrl)   once; capacity = total triangle count of the
+ *                                                             mesh is always enough; same value on every rank
+ *   <share the two device pointers with the peers>            svo_ipc_export / svo_ipc_open across processes,
+ *                                                             the raw pointers inside one process
+ *   svo_shard_dispatch_attach(inbox_ptrs, ctrl_ptrs)          `world` entries each, entry [rank] = own buffers
+ *   per job:  svo_shard_dispatch_count -> svo_shard_dispatch_send -> svo_shard_dispatch_finish
+ *             (three calls so that one host thread can drive several ranks: issue each phase for all
+ *              ranks before the next; the cross-rank waits happen on the device, in stream order)
+ * Errors: SVO_E_RANGE if an inbox is too small (reported by every rank), SVO_E_CUDA if a peer never
+ * arrives (device-side wait gives up after a few seconds). At most 16 ranks. */
+int svo_shard_dispatch_create(svo_ctx* ctx, uint64_t capacity_tris, int floats_per_tri, void** dev_inbox, void** dev_ctrl);
+int svo_shard_dispatch_attach(svo_ctx* ctx, void* const* inbox_ptrs, void* const* ctrl_ptrs);
+int svo_shard_dispatch_count(svo_ctx* ctx, const svo_params* params, const float* dev_local_tris, uint64_t n_local, int floats_per_tri);
+int svo_shard_dispatch_send(svo_ctx* ctx);
+int svo_shard_dispatch_finish(svo_ctx* ctx, uint64_t* n_received);
+/* cudaIpcGetMemHandle / cudaIpcOpenMemHandle / cudaIpcCloseMemHandle as plain bytes (64-byte handle). */
+int svo_ipc_export(const void* dev_ptr, void* handle64);
+int svo_ipc_open(const void* handle64, void** dev_ptr);
+int svo_ipc_close(void* dev_ptr);
 
 /* ---- whole path ---------------------------------------------------------- */
 

@@ -29,6 +29,8 @@ ABI_SYMBOLS = [
     "svo_set_triangles", "svo_set_triangles_device", "svo_partition", "svo_voxelize", "svo_build",
     "svo_fetch_nodes", "svo_fetch_data", "svo_device_nodes", "svo_device_data", "svo_fetch_voxel_codes",
     "svo_shard_configure", "svo_shard_table_size", "svo_shard_count", "svo_shard_emit", "svo_shard_ranges",
+    "svo_shard_dispatch_create", "svo_shard_dispatch_attach", "svo_shard_dispatch_count", "svo_shard_dispatch_send",
+    "svo_shard_dispatch_finish", "svo_ipc_export", "svo_ipc_open", "svo_ipc_close",
     "svo_run", "svo_get_stats", "svo_synchronize", "svo_host_alloc", "svo_host_free",
 ]
 
@@ -53,6 +55,7 @@ class Stats(C.Structure):
                 ("ms_upload", C.c_float), ("ms_partition", C.c_float), ("ms_voxelize", C.c_float),
                 ("ms_build", C.c_float), ("ms_emit", C.c_float), ("ms_clear", C.c_float), ("ms_download", C.c_float),
                 ("ms_vox_small", C.c_float), ("ms_emit_leaf", C.c_float), ("ms_compact", C.c_float),
+                ("ms_dispatch", C.c_float),
                 ("kernel_launches", C.c_uint32)]
 
     def as_dict(self) -> dict:
@@ -95,6 +98,14 @@ def load_library(path: str | None = None):
     L.svo_shard_count.restype = i32; L.svo_shard_count.argtypes = [vp, vp]
     L.svo_shard_emit.restype = i32; L.svo_shard_emit.argtypes = [vp, vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
     L.svo_shard_ranges.restype = i32; L.svo_shard_ranges.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
+    L.svo_shard_dispatch_create.restype = i32; L.svo_shard_dispatch_create.argtypes = [vp, u64, i32, C.POINTER(vp), C.POINTER(vp)]
+    L.svo_shard_dispatch_attach.restype = i32; L.svo_shard_dispatch_attach.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
+    L.svo_shard_dispatch_count.restype = i32; L.svo_shard_dispatch_count.argtypes = [vp, C.POINTER(Params), vp, u64, i32]
+    L.svo_shard_dispatch_send.restype = i32; L.svo_shard_dispatch_send.argtypes = [vp]
+    L.svo_shard_dispatch_finish.restype = i32; L.svo_shard_dispatch_finish.argtypes = [vp, C.POINTER(u64)]
+    L.svo_ipc_export.restype = i32; L.svo_ipc_export.argtypes = [vp, vp]
+    L.svo_ipc_open.restype = i32; L.svo_ipc_open.argtypes = [vp, C.POINTER(vp)]
+    L.svo_ipc_close.restype = i32; L.svo_ipc_close.argtypes = [vp]
     L.svo_run.restype = i32; L.svo_run.argtypes = [vp, C.POINTER(Params), vp, u64, vp, u64, vp, u64, C.POINTER(Stats)]
     L.svo_get_stats.restype = i32; L.svo_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.svo_synchronize.restype = i32; L.svo_synchronize.argtypes = [vp]
@@ -102,6 +113,28 @@ def load_library(path: str | None = None):
     L.svo_host_free.restype = None; L.svo_host_free.argtypes = [vp]
     _lib = L
     return L
+
+
+def ipc_export(dev_ptr: int) -> bytes:
+    """cudaIpcGetMemHandle of a cudaMalloc'd pointer, as 64 bytes."""
+    buf = C.create_string_buffer(64)
+    rc = load_library().svo_ipc_export(dev_ptr, buf)
+    if rc != 0:
+        raise SvoError(rc, "cudaIpcGetMemHandle failed")
+    return buf.raw
+
+
+def ipc_open(handle: bytes) -> int:
+    """Maps a peer process's allocation into this process (cudaIpcOpenMemHandle, enables peer access)."""
+    p = C.c_void_p()
+    rc = load_library().svo_ipc_open(C.create_string_buffer(handle, 64), C.byref(p))
+    if rc != 0 or not p.value:
+        raise SvoError(rc, "cudaIpcOpenMemHandle failed")
+    return p.value
+
+
+def ipc_close(dev_ptr: int) -> None:
+    load_library().svo_ipc_close(dev_ptr)
 
 
 def estimate_partitions(gridsize: int, memory_limit_mb: int) -> int:
@@ -264,6 +297,34 @@ class SvoBuilder:
         a, b, c_, d = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint64()
         self._ck(self._lib.svo_shard_ranges(self._h, C.byref(a), C.byref(b), C.byref(c_), C.byref(d)))
         return a.value, b.value, c_.value, d.value
+
+    # -- triangle dispatch over peer memory (multi-GPU) -------------------------
+    def dispatch_create(self, capacity_tris: int, fpt: int) -> tuple[int, int]:
+        """Allocates this rank's inbox + control block; returns their device pointers (to share with the peers)."""
+        a, b = C.c_void_p(), C.c_void_p()
+        self._ck(self._lib.svo_shard_dispatch_create(self._h, capacity_tris, fpt, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def dispatch_attach(self, inbox_ptrs: list[int], ctrl_ptrs: list[int]) -> None:
+        n = len(inbox_ptrs)
+        A = (C.c_void_p * n)(*inbox_ptrs)
+        B = (C.c_void_p * n)(*ctrl_ptrs)
+        self._ck(self._lib.svo_shard_dispatch_attach(self._h, A, B))
+
+    def dispatch_count(self, params: Params, local_tris) -> None:
+        """local_tris: torch CUDA tensor (n_local, 9|21) float32 -- this rank's slice of the file, in file order."""
+        assert local_tris.is_cuda and local_tris.is_contiguous() and local_tris.element_size() == 4
+        self._keep_local = local_tris
+        self.params = params
+        self._ck(self._lib.svo_shard_dispatch_count(self._h, C.byref(params), local_tris.data_ptr(), local_tris.shape[0], local_tris.shape[1]))
+
+    def dispatch_send(self) -> None:
+        self._ck(self._lib.svo_shard_dispatch_send(self._h))
+
+    def dispatch_finish(self) -> int:
+        n = C.c_uint64()
+        self._ck(self._lib.svo_shard_dispatch_finish(self._h, C.byref(n)))
+        return n.value
 
     def fetch_nodes(self, first: int, count: int, out: np.ndarray | None = None) -> np.ndarray:
         if out is None:

@@ -3,6 +3,7 @@
 // point needs a compute-capability 10.x device.
 #include "../../include/svo_b200.h"
 #include "svo_kernels.cuh"
+#include "svo_dispatch.cuh"
 
 #include <cmath>
 #include <cstdio>
@@ -46,7 +47,7 @@ struct LevelBufs {
     }
 };
 
-enum { EV_UP0, EV_UP1, EV_PART0, EV_PART1, EV_VOX0, EV_VOX1, EV_BUILD0, EV_EMIT0, EV_EMIT1, EV_BUILD1, EV_VS0, EV_VS1, EV_EL0, EV_EL1, EV_CMP1, EV_CLR0, EV_CLR1, EV_DN0, EV_DN1, EV_COUNT };
+enum { EV_UP0, EV_UP1, EV_PART0, EV_PART1, EV_VOX0, EV_VOX1, EV_BUILD0, EV_EMIT0, EV_EMIT1, EV_BUILD1, EV_VS0, EV_VS1, EV_EL0, EV_EL1, EV_CMP1, EV_CLR0, EV_CLR1, EV_DN0, EV_DN1, EV_DSP0, EV_DSP1, EV_COUNT };
 
 }  // namespace
 
@@ -119,6 +120,19 @@ struct svo_ctx {
     ull n_upper_records = 0;
     ull leaf_offset = 0, n_voxels_local = 0;
     ull node_lo = 0, node_hi = 0, data_lo = 0, data_hi = 0;
+
+    // triangle dispatch over peer memory (svo_dispatch.cuh)
+    DevBuf inbox, ctrl_buf, blockcnt, blockoff;
+    uint64_t inbox_cap = 0;
+    int inbox_fpt = 0;
+    float* peer_inbox[MAX_WORLD];
+    DispatchCtrl* peer_ctrl[MAX_WORLD];
+    DispatchCtrl* h_ctrl = nullptr;   // pinned read-back copy
+    bool attached = false, dispatched = false;
+    int dispatch_phase = 0;           // 0 idle, 1 counted, 2 sent
+    ull dispatch_epoch = 0;
+    uint32_t dispatch_launches = 0;
+    DispatchJob dj;
 
     svo_stats stats;
     uint32_t launches = 0;
@@ -345,7 +359,7 @@ int svo_ctx_create(int device, svo_ctx** out) {
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10) {
-        char m[160];
+        char m[512];
         snprintf(m, sizeof m, "device %d (%s) is sm_%d%d; this library is built for sm_100a only", device, prop.name, prop.major, prop.minor);
         return fail(c, SVO_E_CUDA, m);
     }
@@ -389,6 +403,8 @@ void svo_ctx_destroy(svo_ctx* c) {
     c->d_lvlptrs.release(); c->d_nwords.release(); c->d_counts.release();
     c->part_counts.release(); c->part_cursor.release(); c->part_off.release(); c->pair_tri.release();
     c->queue[0].release(); c->queue[1].release(); c->qcount.release(); c->subset.release();
+    c->inbox.release(); c->ctrl_buf.release(); c->blockcnt.release(); c->blockoff.release();
+    if (c->h_ctrl) cudaFreeHost(c->h_ctrl);
     c->scan_tmp.release(); c->nodes.release(); c->data.release(); c->owner.release(); c->tileidx.release(); c->codes.release();
     for (int i = 0; i < EV_COUNT; i++) cudaEventDestroy(c->ev[i]);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
@@ -442,6 +458,7 @@ static int set_tris_common(svo_ctx* c, uint64_t n_tris, int fpt) {
     c->n_tris = n_tris;
     c->fpt = fpt;
     c->have_tris = true;
+    c->dispatched = false;
     c->partitioned = c->voxelized = c->built = false;
     return SVO_OK;
 }
@@ -476,16 +493,9 @@ int svo_set_triangles_device(svo_ctx* c, const float* tris, uint64_t n_tris, int
 
 static int setup_geometry(svo_ctx* c);
 
-int svo_partition(svo_ctx* c, const svo_params* params, uint64_t* n_partitions, uint64_t* part_tricounts, uint64_t cap) {
-    if (!c) return SVO_E_INVALID;
-    int rc = validate_params(c, params);
-    if (rc) return rc;
-    if (!c->have_tris) return fail(c, SVO_E_INVALID, "svo_partition before svo_set_triangles");
-    if ((params->payload ? 21 : 9) != c->fpt) return fail(c, SVO_E_INVALID, "params.payload does not match floats_per_tri");
-    CK(cudaSetDevice(c->device));
+// Grid constants of a job (host arithmetic only): depth, logical partitions, unit lengths, partition slabs.
+static int derive_grid(svo_ctx* c, const svo_params* params) {
     c->prm = *params;
-    c->voxelized = c->built = false;
-    c->launches = 0;
     const uint64_t g = params->gridsize;
     c->D = ilog2u(g);
     c->nl = (c->D + 1) / 2;
@@ -497,6 +507,28 @@ int svo_partition(svo_ctx* c, const svo_params* params, uint64_t* n_partitions, 
     const float rmin = svo_text_roundtrip_float(params->bbox_min0), rmax = svo_text_roundtrip_float(params->bbox_max0);
     c->unit_vox = (rmax - rmin) / (float)g;
     c->unit_div = 1.0f / c->unit_vox;                                          // voxelizer.cpp:164
+    if (c->P > 1) {
+        const float unit_part = (params->bbox_max0 - params->bbox_min0) / (float)g;   // partitioner.cpp:45
+        c->inv_slab = 1.0f / ((float)c->side * unit_part);
+        for (uint32_t i = 0; i < (1u << c->k); i++) {
+            c->slab_min[i] = (float)(uint32_t)(i * c->side) * unit_part;                    // :54-56
+            c->slab_max[i] = (float)(uint32_t)((i + 1) * c->side - 1 + 1u) * unit_part;     // :57-59
+        }
+    }
+    return SVO_OK;
+}
+
+int svo_partition(svo_ctx* c, const svo_params* params, uint64_t* n_partitions, uint64_t* part_tricounts, uint64_t cap) {
+    if (!c) return SVO_E_INVALID;
+    int rc = validate_params(c, params);
+    if (rc) return rc;
+    if (!c->have_tris) return fail(c, SVO_E_INVALID, "svo_partition before svo_set_triangles");
+    if ((params->payload ? 21 : 9) != c->fpt) return fail(c, SVO_E_INVALID, "params.payload does not match floats_per_tri");
+    CK(cudaSetDevice(c->device));
+    c->voxelized = c->built = false;
+    c->launches = 0;
+    rc = derive_grid(c, params);
+    if (rc) return rc;
     c->h_part_counts.assign(c->P, 0);
     mark(c, EV_PART0);
     if (c->P == 1) {
@@ -507,12 +539,8 @@ int svo_partition(svo_ctx* c, const svo_params* params, uint64_t* n_partitions, 
         BinJob B;
         memset(&B, 0, sizeof B);
         B.tris = c->d_tris; B.fpt = (uint32_t)c->fpt; B.n_tris = c->n_tris; B.k = (uint32_t)c->k; B.P = (uint32_t)c->P;
-        const float unit_part = (params->bbox_max0 - params->bbox_min0) / (float)g;   // partitioner.cpp:45
-        c->inv_slab = B.inv_slab = 1.0f / ((float)c->side * unit_part);
-        for (uint32_t i = 0; i < (1u << c->k); i++) {
-            c->slab_min[i] = B.bmin[i] = (float)(uint32_t)(i * c->side) * unit_part;                    // :54-56
-            c->slab_max[i] = B.bmax[i] = (float)(uint32_t)((i + 1) * c->side - 1 + 1u) * unit_part;     // :57-59
-        }
+        B.inv_slab = c->inv_slab;
+        for (uint32_t i = 0; i < (1u << c->k); i++) { B.bmin[i] = c->slab_min[i]; B.bmax[i] = c->slab_max[i]; }
         const char* lists_env = getenv("SVO_PARTITION_LISTS");
         c->use_lists = lists_env && lists_env[0] == '1';
         c->n_pairs = 0;
@@ -569,13 +597,35 @@ int svo_shard_configure(svo_ctx* c, int rank, int world) {
 // Shard geometry: the grid is cut into 8^dc chunks (subtrees at depth dc >= k), rank r owns a contiguous
 // Morton range of them. Pyramid levels 0..J live inside a chunk (local, dense per slab); levels above J are
 // tiny and replicated on every rank.
+static int shard_chunk_depth(const svo_ctx* c) {
+    if (c->world <= 1) return 0;
+    int need = 0;
+    while ((1 << (3 * need)) < c->world) need++;
+    return c->k > need ? c->k : need;
+}
+// voxel bounding box of the slab of `rank` (exact when the slab is a box, a superset otherwise)
+static void shard_box(const svo_ctx* c, int rank, int dc, int lo[3], int hi[3]) {
+    if (c->world == 1) {
+        for (int a = 0; a < 3; a++) { lo[a] = 0; hi[a] = (int)c->prm.gridsize - 1; }
+        return;
+    }
+    const ull nchunks = 1ULL << (3 * dc);
+    const ull c0 = nchunks * (ull)rank / (ull)c->world, c1 = nchunks * (ull)(rank + 1) / (ull)c->world;
+    const uint32_t cs = (uint32_t)(c->prm.gridsize >> dc);
+    for (int a = 0; a < 3; a++) { lo[a] = 0x7fffffff; hi[a] = -1; }
+    for (ull ch = c0; ch < c1; ch++) {
+        const uint32_t cc[3] = { compact3(ch), compact3(ch >> 1), compact3(ch >> 2) };
+        for (int a = 0; a < 3; a++) {
+            lo[a] = std::min(lo[a], (int)(cc[a] * cs));
+            hi[a] = std::max(hi[a], (int)(cc[a] * cs + cs - 1));
+        }
+    }
+}
+
 static int setup_geometry(svo_ctx* c) {
     const int D = c->D;
-    int dc = 0;
+    const int dc = shard_chunk_depth(c);
     if (c->world > 1) {
-        int need = 0;
-        while ((1 << (3 * need)) < c->world) need++;
-        dc = c->k > need ? c->k : need;
         if (D - dc < 2) return fail(c, SVO_E_INVALID, "gridsize too small for this many shards");
         if (c->prm.generate_levels) return fail(c, SVO_E_INVALID, "-levels is not supported on the sharded (multi-GPU) path yet");
     }
@@ -603,19 +653,7 @@ static int setup_geometry(svo_ctx* c) {
     const int shJ = 6 * (c->J + 1);
     c->WJ = 3 * D >= shJ ? (1ULL << (3 * D - shJ)) : 1ULL;
     // voxel bounding box of the slab (exact when the slab is a box, a superset otherwise; the sinks filter by word range)
-    if (c->world == 1) {
-        for (int a = 0; a < 3; a++) { c->sb_lo[a] = 0; c->sb_hi[a] = (int)c->prm.gridsize - 1; }
-    } else {
-        const uint32_t cs = (uint32_t)(c->prm.gridsize >> dc);
-        for (int a = 0; a < 3; a++) { c->sb_lo[a] = 0x7fffffff; c->sb_hi[a] = -1; }
-        for (ull ch = c->c0; ch < c->c1; ch++) {
-            const uint32_t cc[3] = { compact3(ch), compact3(ch >> 1), compact3(ch >> 2) };
-            for (int a = 0; a < 3; a++) {
-                c->sb_lo[a] = std::min(c->sb_lo[a], (int)(cc[a] * cs));
-                c->sb_hi[a] = std::max(c->sb_hi[a], (int)(cc[a] * cs + cs - 1));
-            }
-        }
-    }
+    shard_box(c, c->rank, dc, c->sb_lo, c->sb_hi);
     // logical partitions that intersect the slab, and the work items this context walks
     c->p_first = 0; c->p_last = c->P - 1;
     if (c->world > 1 && c->P > 1) {
@@ -644,7 +682,7 @@ int svo_voxelize(svo_ctx* c) {
     if (rc) return rc;
     CK(c->qcount.ensure(8 * sizeof(ull)));
     CK(cudaMemsetAsync(c->qcount.p, 0, 8 * sizeof(ull), c->stream));
-    c->use_subset = c->world > 1 && !(c->P > 1 && c->use_lists);
+    c->use_subset = c->world > 1 && !c->dispatched && !(c->P > 1 && c->use_lists);
     if (c->use_subset) CK(c->subset.ensure((size_t)(c->n_tris / VOX_BLOCK + 2) * sizeof(uint32_t)));
     // queue capacity: exact with lists; with inline enumeration a triangle may appear once per partition it
     // touches, so leave headroom and detect overflow (qcount[3]) instead of trusting a bound
@@ -1140,7 +1178,8 @@ static int build_phase_b(svo_ctx* c, const ull* table) {
     c->stats.ms_vox_small = span(c, EV_VS0, EV_VS1);
     c->stats.ms_emit_leaf = c->lv[0].n ? span(c, EV_EL0, EV_EL1) : 0.f;
     c->stats.ms_compact = span(c, EV_BUILD0, EV_CMP1);
-    c->stats.kernel_launches = c->launches;
+    c->stats.ms_dispatch = c->dispatched ? span(c, EV_DSP0, EV_DSP1) : 0.f;
+    c->stats.kernel_launches = c->launches + (c->dispatched ? c->dispatch_launches : 0);
     return SVO_OK;
 }
 
@@ -1196,6 +1235,176 @@ int svo_shard_ranges(svo_ctx* c, uint64_t* node_lo, uint64_t* node_hi, uint64_t*
     if (node_hi) *node_hi = c->node_hi;
     if (data_lo) *data_lo = c->data_lo;
     if (data_hi) *data_hi = c->data_hi;
+    return SVO_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Triangle dispatch over peer memory (svo_dispatch.cuh)
+// ---------------------------------------------------------------------------
+int svo_ipc_export(const void* dev_ptr, void* handle64) {
+    if (!dev_ptr || !handle64) return SVO_E_INVALID;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    if (cudaIpcGetMemHandle(&h, const_cast<void*>(dev_ptr)) != cudaSuccess) { (void)cudaGetLastError(); return SVO_E_CUDA; }
+    memcpy(handle64, &h, 64);
+    return SVO_OK;
+}
+int svo_ipc_open(const void* handle64, void** dev_ptr) {
+    if (!handle64 || !dev_ptr) return SVO_E_INVALID;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    if (cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { (void)cudaGetLastError(); *dev_ptr = nullptr; return SVO_E_CUDA; }
+    return SVO_OK;
+}
+int svo_ipc_close(void* dev_ptr) {
+    if (!dev_ptr) return SVO_OK;
+    if (cudaIpcCloseMemHandle(dev_ptr) != cudaSuccess) { (void)cudaGetLastError(); return SVO_E_CUDA; }
+    return SVO_OK;
+}
+
+int svo_shard_dispatch_create(svo_ctx* c, uint64_t capacity_tris, int fpt, void** dev_inbox, void** dev_ctrl) {
+    if (!c) return SVO_E_INVALID;
+    if (fpt != 9 && fpt != 21) return fail(c, SVO_E_INVALID, "floats_per_tri must be 9 (binary) or 21 (payload)");
+    if (capacity_tris > 0xffffffffULL) return fail(c, SVO_E_INVALID, "more than 2^32-1 triangles");
+    if (c->world > MAX_WORLD) return fail(c, SVO_E_INVALID, "triangle dispatch supports at most 16 ranks");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    c->attached = false; c->dispatched = false; c->dispatch_phase = 0;
+    // exact-size cudaMalloc allocations of their own: these are the buffers peers map
+    c->inbox.release(); c->ctrl_buf.release();
+    CK(cudaMalloc(&c->inbox.p, (size_t)(capacity_tris ? capacity_tris : 1) * fpt * sizeof(float) + 256));
+    c->inbox.cap = (size_t)(capacity_tris ? capacity_tris : 1) * fpt * sizeof(float) + 256;
+    CK(cudaMalloc(&c->ctrl_buf.p, sizeof(DispatchCtrl)));
+    c->ctrl_buf.cap = sizeof(DispatchCtrl);
+    CK(cudaMemset(c->ctrl_buf.p, 0, sizeof(DispatchCtrl)));
+    if (!c->h_ctrl) CK(cudaHostAlloc((void**)&c->h_ctrl, sizeof(DispatchCtrl), cudaHostAllocDefault));
+    c->inbox_cap = capacity_tris;
+    c->inbox_fpt = fpt;
+    c->dispatch_epoch = 0;
+    if (dev_inbox) *dev_inbox = c->inbox.p;
+    if (dev_ctrl) *dev_ctrl = c->ctrl_buf.p;
+    return SVO_OK;
+}
+
+int svo_shard_dispatch_attach(svo_ctx* c, void* const* inbox_ptrs, void* const* ctrl_ptrs) {
+    if (!c) return SVO_E_INVALID;
+    if (!c->inbox.p) return fail(c, SVO_E_INVALID, "svo_shard_dispatch_attach before svo_shard_dispatch_create");
+    if (!inbox_ptrs || !ctrl_ptrs) return fail(c, SVO_E_INVALID, "peer pointer arrays are NULL");
+    for (int r = 0; r < c->world; r++) {
+        if (!inbox_ptrs[r] || !ctrl_ptrs[r]) return fail(c, SVO_E_INVALID, "a peer pointer is NULL");
+        c->peer_inbox[r] = (float*)inbox_ptrs[r];
+        c->peer_ctrl[r] = (DispatchCtrl*)ctrl_ptrs[r];
+    }
+    if (c->peer_inbox[c->rank] != c->inbox.p || (void*)c->peer_ctrl[c->rank] != c->ctrl_buf.p)
+        return fail(c, SVO_E_INVALID, "entry [rank] of the peer arrays must be this context's own buffers");
+    c->attached = true;
+    return SVO_OK;
+}
+
+int svo_shard_dispatch_count(svo_ctx* c, const svo_params* params, const float* dev_local_tris, uint64_t n_local, int fpt) {
+    if (!c) return SVO_E_INVALID;
+    if (!c->attached) return fail(c, SVO_E_INVALID, "svo_shard_dispatch_count before svo_shard_dispatch_attach");
+    int rc = validate_params(c, params);
+    if (rc) return rc;
+    if (fpt != c->inbox_fpt || (params->payload ? 21 : 9) != fpt) return fail(c, SVO_E_INVALID, "floats_per_tri does not match the inbox / params.payload");
+    if (n_local && !dev_local_tris) return fail(c, SVO_E_INVALID, "dev_local_tris is NULL");
+    if (((uintptr_t)dev_local_tris & 15) != 0) return fail(c, SVO_E_INVALID, "device triangle pointer must be 16-byte aligned");
+    if (n_local > c->inbox_cap) return fail(c, SVO_E_RANGE, "local slice is larger than the inbox capacity");
+    CK(cudaSetDevice(c->device));
+    rc = derive_grid(c, params);
+    if (rc) return rc;
+    const int dc = shard_chunk_depth(c);
+    if (c->D - dc < 2) return fail(c, SVO_E_INVALID, "gridsize too small for this many shards");
+    c->partitioned = c->voxelized = c->built = false;
+    c->have_tris = false; c->dispatched = false;
+    for (int i = 0; i < EV_COUNT; i++) c->ev_set[i] = false;
+    c->dispatch_launches = 0;
+    const uint32_t launches_before = c->launches;
+    mark(c, EV_DSP0);
+    DispatchJob& D = c->dj;
+    memset(&D, 0, sizeof D);
+    D.tris = dev_local_tris; D.fpt = (uint32_t)fpt; D.n_local = n_local;
+    D.world = c->world; D.me = c->rank;
+    D.use_partitions = c->P > 1 ? 1 : 0; D.k = c->k;
+    for (int i = 0; i < 32; i++) { D.bmin[i] = c->slab_min[i]; D.bmax[i] = c->slab_max[i]; }
+    for (int r = 0; r < c->world; r++) {
+        int lo[3], hi[3];
+        shard_box(c, r, dc, lo, hi);
+        for (int a = 0; a < 3; a++) {
+            D.lo[r][a] = c->P > 1 ? lo[a] / (int)c->side : lo[a];
+            D.hi[r][a] = c->P > 1 ? hi[a] / (int)c->side : hi[a];
+        }
+        D.inbox[r] = c->peer_inbox[r];
+        D.ctrl[r] = c->peer_ctrl[r];
+    }
+    D.unit_div = c->unit_div; D.gmax = (int)c->prm.gridsize - 1;
+    D.nb = (n_local + VOX_BLOCK - 1) / VOX_BLOCK;
+    D.epoch = ++c->dispatch_epoch;
+    const ull ncnt = (ull)c->world * D.nb;
+    CK(c->blockcnt.ensure((size_t)(ncnt + 1) * sizeof(unsigned)));
+    CK(c->blockoff.ensure((size_t)(ncnt + 2) * sizeof(ull)));
+    D.blockcnt = c->blockcnt.as<unsigned>();
+    D.blockoff = c->blockoff.as<ull>();
+    if (D.nb) {
+        k_dispatch_count<<<(unsigned)D.nb, VOX_BLOCK, 0, c->stream>>>(D); LAUNCHED();
+        U32Op op{ D.blockcnt };
+        rc = exscan(c, op, ncnt, c->blockoff.as<ull>());
+        if (rc) return rc;
+    }
+    k_dispatch_post<<<1, MAX_WORLD, 0, c->stream>>>(D, 0); LAUNCHED();
+    c->dispatch_launches += c->launches - launches_before;
+    c->dispatch_phase = 1;
+    return SVO_OK;
+}
+
+int svo_shard_dispatch_send(svo_ctx* c) {
+    if (!c) return SVO_E_INVALID;
+    if (c->dispatch_phase != 1) return fail(c, SVO_E_INVALID, "svo_shard_dispatch_send before svo_shard_dispatch_count");
+    CK(cudaSetDevice(c->device));
+    const uint32_t launches_before = c->launches;
+    DispatchJob& D = c->dj;
+    k_dispatch_wait<<<1, MAX_WORLD, 0, c->stream>>>((DispatchCtrl*)c->ctrl_buf.p, c->world, 0, D.epoch); LAUNCHED();
+    if (D.nb) {
+        const size_t smem = 2 * (size_t)VOX_BLOCK * D.fpt * sizeof(float);
+        k_dispatch_write<<<(unsigned)D.nb, VOX_BLOCK, smem, c->stream>>>(D, c->inbox_cap); LAUNCHED();
+    }
+    k_dispatch_post<<<1, MAX_WORLD, 0, c->stream>>>(D, 1); LAUNCHED();
+    c->dispatch_launches += c->launches - launches_before;
+    c->dispatch_phase = 2;
+    return SVO_OK;
+}
+
+int svo_shard_dispatch_finish(svo_ctx* c, uint64_t* n_received) {
+    if (!c) return SVO_E_INVALID;
+    if (c->dispatch_phase != 2) return fail(c, SVO_E_INVALID, "svo_shard_dispatch_finish before svo_shard_dispatch_send");
+    CK(cudaSetDevice(c->device));
+    const uint32_t launches_before = c->launches;
+    k_dispatch_wait<<<1, MAX_WORLD, 0, c->stream>>>((DispatchCtrl*)c->ctrl_buf.p, c->world, 1, c->dj.epoch); LAUNCHED();
+    c->dispatch_launches += c->launches - launches_before;
+    mark(c, EV_DSP1);
+    CK(cudaMemcpyAsync(c->h_ctrl, c->ctrl_buf.p, sizeof(DispatchCtrl), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->dispatch_phase = 0;
+    if (c->h_ctrl->error) {
+        const ull e = c->h_ctrl->error;
+        CK(cudaMemsetAsync(&((DispatchCtrl*)c->ctrl_buf.p)->error, 0, sizeof(ull), c->stream));
+        return fail(c, e == 3 ? SVO_E_RANGE : SVO_E_CUDA,
+                    e == 3 ? "triangle dispatch: a peer inbox is too small for the triangles routed to it"
+                           : "triangle dispatch: timed out waiting for a peer rank");
+    }
+    // every rank holds the whole count matrix, so all of them see an overflowing column and fail together
+    ull n_in = 0;
+    for (int d = 0; d < c->world; d++) {
+        ull col = 0;
+        for (int s = 0; s < c->world; s++) col += c->h_ctrl->matrix[s][d];
+        if (col > c->inbox_cap) return fail(c, SVO_E_RANGE, "triangle dispatch: a peer inbox is too small for the triangles routed to it");
+        if (d == c->rank) n_in = col;
+    }
+    int rc = set_tris_common(c, n_in, c->inbox_fpt);
+    if (rc) return rc;
+    c->d_tris = c->inbox.as<float>();
+    c->dispatched = true;
+    if (n_received) *n_received = n_in;
     return SVO_OK;
 }
 

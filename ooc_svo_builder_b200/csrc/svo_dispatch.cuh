@@ -1,0 +1,174 @@
+// svo_dispatch.cuh -- triangle dispatch of the sharded (multi-GPU) build: an all-to-all of triangle
+// records written straight into the peers' HBM over NVLink / NVSwitch (peer stores), no host staging.
+//
+// Every rank starts with a contiguous 1/N slice of the .tridata file (TriReader reads the file front to
+// back, src/libs/libtri/include/TriReader.h:41-79; rank r's slice is what it would read r-th). A triangle
+// is needed by every rank whose slab its bounding box touches -- the partitioner's inclusive box test
+// (partitioner.cpp:117-126, intersection.h:50-53) lifted from logical partitions to rank slabs; the test
+// here is a superset test, the voxelizer on the receiving rank still applies the exact per-partition rule.
+//
+//   pass 1  k_dispatch_count   per staging block (128 consecutive local triangles) and destination: count
+//           exscan             block offsets per destination (hand-written scan, svo_kernels.cuh)
+//           k_dispatch_post    row of the count matrix M[src][dst] -> every peer's control block, flag A
+//   pass 2  k_dispatch_wait    until all rows arrived (flag A of every peer)
+//           k_dispatch_write   records -> peer inbox at  sum_{s < me} M[s][dst] + block offset  (stable:
+//                              the inbox is ordered by (source rank, local index) = file order, so the
+//                              payload rule "first triangle in file order wins" (voxelizer.cpp:263) holds
+//                              on inbox positions)
+//           k_dispatch_post    flag B
+//   finish  k_dispatch_wait    until every peer's records landed (flag B), then the voxelizer runs on the inbox
+//
+// Flags are epochs (monotonic), written with a system-scope fence behind the data they publish.
+#pragma once
+#include "svo_kernels.cuh"
+
+namespace svo {
+
+constexpr int MAX_WORLD = 16;
+
+// One per context, in cudaMalloc'd memory that peers map (IPC or same-process pointers).
+struct DispatchCtrl {
+    unsigned long long flag[2][MAX_WORLD];             // [phase][source rank] = last epoch that source finished
+    unsigned long long matrix[MAX_WORLD][MAX_WORLD];   // M[src][dst] triangle counts of the current epoch
+    unsigned long long error;                          // set by a wait that timed out
+};
+
+struct DispatchJob {
+    const float* tris; uint32_t fpt; unsigned long long n_local;
+    int world, me;
+    int use_partitions, k;
+    float bmin[32], bmax[32];
+    int lo[MAX_WORLD][3], hi[MAX_WORLD][3];     // destination boxes: partition coordinates (use_partitions) or voxels
+    float unit_div; int gmax;
+    unsigned int* blockcnt;                     // [world][nb]
+    const unsigned long long* blockoff;         // exclusive scan of blockcnt, [world * nb + 1]
+    unsigned long long nb;
+    float* inbox[MAX_WORLD];                    // peer inboxes
+    DispatchCtrl* ctrl[MAX_WORLD];              // peer control blocks (ctrl[me] = own)
+    unsigned long long epoch;
+};
+
+// Destination ranks of one triangle as a bit mask (superset test on bounding boxes, as k_owner_filter).
+__device__ __forceinline__ unsigned dispatch_mask(const DispatchJob& D, const float* c) {
+    unsigned m = (1u << D.world) - 1u;
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        const float mn = stdmin(c[a], stdmin(c[3 + a], c[6 + a])), mx = stdmax(c[a], stdmax(c[3 + a], c[6 + a]));
+        if (D.use_partitions) {
+            for (int d = 0; d < D.world; d++)
+                if ((mx < D.bmin[D.lo[d][a]]) || (mn > D.bmax[D.hi[d][a]])) m &= ~(1u << d);
+        } else {
+            const int l = clampi(f2i(fmul(mn, D.unit_div)), 0, D.gmax), h = clampi(f2i(fmul(mx, D.unit_div)), 0, D.gmax);
+            for (int d = 0; d < D.world; d++)
+                if (h < D.lo[d][a] || l > D.hi[d][a]) m &= ~(1u << d);
+        }
+    }
+    return m;
+}
+
+__global__ void __launch_bounds__(VOX_BLOCK) k_dispatch_count(DispatchJob D) {
+    const unsigned long long t = (unsigned long long)blockIdx.x * VOX_BLOCK + threadIdx.x;
+    unsigned m = 0;
+    if (t < D.n_local) {
+        const float* v = D.tris + t * D.fpt;
+        float c[9];
+#pragma unroll
+        for (int i = 0; i < 9; i++) c[i] = __ldg(v + i);
+        m = dispatch_mask(D, c);
+    }
+    for (int d = 0; d < D.world; d++) {
+        const int n = __syncthreads_count((m >> d) & 1u);
+        if (threadIdx.x == 0) D.blockcnt[(unsigned long long)d * D.nb + blockIdx.x] = (unsigned)n;
+    }
+}
+
+// One block, one thread per peer: publish (phase 0) this rank's row of the count matrix, then raise the flag.
+__global__ void __launch_bounds__(MAX_WORLD) k_dispatch_post(DispatchJob D, int phase) {
+    const int p = threadIdx.x;
+    if (p >= D.world) return;
+    if (phase == 0) {
+        for (int d = 0; d < D.world; d++) {
+            const unsigned long long n = D.nb ? D.blockoff[(unsigned long long)(d + 1) * D.nb] - D.blockoff[(unsigned long long)d * D.nb] : 0ULL;
+            *(volatile unsigned long long*)&D.ctrl[p]->matrix[D.me][d] = n;
+        }
+    }
+    __threadfence_system();
+    *(volatile unsigned long long*)&D.ctrl[p]->flag[phase][D.me] = D.epoch;
+}
+
+// One block, one thread per peer: spin until that peer's flag reaches the epoch. Gives up after ~4 s of GPU clock
+// (a peer that never arrives must not hang the device) and records the failure in ctrl->error.
+__global__ void __launch_bounds__(MAX_WORLD) k_dispatch_wait(DispatchCtrl* own, int world, int phase, unsigned long long epoch) {
+    const int p = threadIdx.x;
+    if (p >= world) return;
+    const volatile unsigned long long* f = &own->flag[phase][p];
+    const long long t0 = clock64();
+    while (*f < epoch) {
+        if (clock64() - t0 > 8000000000LL) { own->error = 1ULL + (unsigned long long)phase; break; }
+        __nanosleep(200);
+    }
+    __threadfence_system();
+}
+
+// Pass 2: staging block -> per destination, the selected records compacted in shared memory (stable) and
+// streamed to the peer inbox as one contiguous run of floats (coalesced NVLink stores).
+__global__ void __launch_bounds__(VOX_BLOCK) k_dispatch_write(DispatchJob D, unsigned long long inbox_cap) {
+    extern __shared__ float4 s_dyn4[];
+    float* s_in = reinterpret_cast<float*>(s_dyn4);
+    float* s_out = s_in + (size_t)VOX_BLOCK * D.fpt;
+    __shared__ unsigned s_warp[VOX_BLOCK / 32];
+    const unsigned long long q0 = (unsigned long long)blockIdx.x * VOX_BLOCK;
+    const unsigned long long nrec = D.n_local - q0 < VOX_BLOCK ? D.n_local - q0 : VOX_BLOCK;
+    const unsigned long long nfl = nrec * D.fpt;
+    {   // stage the block's records (q0 * fpt * 4 bytes is a multiple of 16)
+        const float* src = D.tris + q0 * D.fpt;
+        const unsigned long long n4 = nfl >> 2;
+        const float4* src4 = reinterpret_cast<const float4*>(src);
+        for (unsigned long long i = threadIdx.x; i < n4; i += VOX_BLOCK) s_dyn4[i] = __ldg(src4 + i);
+        for (unsigned long long i = (n4 << 2) + threadIdx.x; i < nfl; i += VOX_BLOCK) s_in[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    unsigned m = 0;
+    if (threadIdx.x < nrec) m = dispatch_mask(D, s_in + (size_t)threadIdx.x * D.fpt);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const DispatchCtrl* own = D.ctrl[D.me];
+    for (int d = 0; d < D.world; d++) {
+        const unsigned cnt = D.blockcnt[(unsigned long long)d * D.nb + blockIdx.x];
+        if (cnt == 0) continue;                                  // block-uniform
+        unsigned long long at = D.blockoff[(unsigned long long)d * D.nb + blockIdx.x] - D.blockoff[(unsigned long long)d * D.nb];
+        for (int s = 0; s < D.me; s++) at += own->matrix[s][d];
+        if (at + cnt > inbox_cap) {                              // block-uniform: never write past a peer's inbox
+            if (threadIdx.x == 0) *(volatile unsigned long long*)&D.ctrl[D.me]->error = 3ULL;
+            continue;
+        }
+        float* dst = D.inbox[d] + at * D.fpt;
+        const float* from = s_in;
+        if (cnt != nrec) {
+            // stable compaction of the selected records
+            const bool sel = (m >> d) & 1u;
+            const unsigned b = __ballot_sync(0xffffffffu, sel);
+            if (lane == 0) s_warp[wid] = __popc(b);
+            __syncthreads();
+            unsigned pos = __popc(b & ((1u << lane) - 1u));
+            for (int w = 0; w < wid; w++) pos += s_warp[w];
+            if (sel) {
+                const float* r = s_in + (size_t)threadIdx.x * D.fpt;
+                float* o = s_out + (size_t)pos * D.fpt;
+                for (uint32_t i = 0; i < D.fpt; i++) o[i] = r[i];
+            }
+            __syncthreads();
+            from = s_out;
+        }
+        const unsigned total = cnt * D.fpt;
+        for (unsigned i = threadIdx.x; i < total; i += VOX_BLOCK) dst[i] = from[i];
+        __syncthreads();                                         // s_out / s_warp are reused by the next destination
+    }
+    __threadfence_system();
+}
+
+struct U32Op {
+    const unsigned int* v;
+    __device__ unsigned long long operator()(unsigned long long i) const { return (unsigned long long)v[i]; }
+};
+
+}  // namespace svo

@@ -99,20 +99,46 @@ def assemble(results: list[ShardResult], gridsize: int):
     return header_bytes(gridsize, nn, nd), nodes, data
 
 
+def slice_bounds(n_tris: int, world: int, rank: int) -> tuple[int, int]:
+    """Rank `rank`'s contiguous slice [lo, hi) of the triangle file (file order, equal sizes up to rounding)."""
+    per = (n_tris + world - 1) // world
+    return min(rank * per, n_tris), min((rank + 1) * per, n_tris)
+
+
 def run_single_process(tris, length: float, gridsize: int, world: int, memory_limit_mb: int = 2048,
-                       color: str = "model", device: int = 0, fetch: bool = True) -> list[ShardResult]:
+                       color: str = "model", device: int = 0, fetch: bool = True, dispatch: bool = False,
+                       slices: list | None = None) -> list[ShardResult]:
     """All `world` ranks as contexts of ONE process (sharing a GPU is fine): the table exchange is a
-    host-side sum. Used by the single-GPU parity tests of the sharded path and by the CLI."""
+    host-side sum. Used by the single-GPU parity tests of the sharded path and by the CLI.
+    dispatch=True: every rank starts with only its slice of the file and the triangle dispatch
+    (svo_shard_dispatch_*) routes the records through the peers' inboxes -- same kernels as across GPUs,
+    the peer pointers just happen to be on one device. `slices` overrides the equal split ([(lo, hi)] per rank)."""
     import torch
     payload = tris.shape[1] == 21
     ctxs = [SvoBuilder(device) for _ in range(world)]
     try:
         prm = SvoBuilder.make_params(length, gridsize, payload, memory_limit_mb, False, color)
         tables = []
+        if dispatch:
+            T = tris.shape[0]
+            for r, sb in enumerate(ctxs):
+                sb.shard_configure(r, world)
+            ptrs = [sb.dispatch_create(T, tris.shape[1]) for sb in ctxs]
+            for sb in ctxs:
+                sb.dispatch_attach([p[0] for p in ptrs], [p[1] for p in ptrs])
+            bounds = slices or [slice_bounds(T, world, r) for r in range(world)]
+            local = [torch.from_numpy(np.ascontiguousarray(tris[lo:hi])).to("cuda:%d" % device) for lo, hi in bounds]
+            for sb, l in zip(ctxs, local):          # each phase for all ranks before the next (one host thread)
+                sb.dispatch_count(prm, l)
+            for sb in ctxs:
+                sb.dispatch_send()
+            for sb in ctxs:
+                sb.dispatch_finish()
         for r, sb in enumerate(ctxs):
-            sb.shard_configure(r, world)
-            sb.set_triangles(tris)
-            sb.partition(prm)
+            if not dispatch:
+                sb.shard_configure(r, world)
+                sb.set_triangles(tris)
+            sb.partition(prm, want_counts=not dispatch)
             sb.voxelize()
             t = torch.zeros(sb.shard_table_size(), dtype=torch.int64, device="cuda:%d" % device)
             sb.shard_count(t.data_ptr())
@@ -156,10 +182,39 @@ class DistributedBuilder:
 
     def set_triangles(self, tris):
         self.sb.set_triangles(tris)
+        self.local = None
+
+    def enable_dispatch(self, capacity_tris: int, fpt: int):
+        """Allocates the inbox, exchanges CUDA IPC handles with the peers (once) and maps their inboxes:
+        afterwards triangle records travel GPU -> GPU as NVLink stores issued by our own kernel."""
+        from .api import ipc_export, ipc_open
+        inbox, ctrl = self.sb.dispatch_create(capacity_tris, fpt)
+        mine = (ipc_export(inbox), ipc_export(ctrl))
+        handles = [None] * self.world
+        self.dist.all_gather_object(handles, mine)
+        ib, cb = [], []
+        self._opened = []
+        for r, (hi, hc) in enumerate(handles):
+            if r == self.rank:
+                ib.append(inbox); cb.append(ctrl)
+            else:
+                a, b = ipc_open(hi), ipc_open(hc)
+                self._opened += [a, b]
+                ib.append(a); cb.append(b)
+        self.sb.dispatch_attach(ib, cb)
+        self.dist.barrier()
+
+    def set_local_triangles(self, local):
+        """This rank's slice of the triangle file (torch CUDA tensor, file order across ranks)."""
+        self.local = local
 
     def step(self, prm):
-        """partition -> voxelize -> local build -> NCCL all-reduce of the table -> merged emit."""
+        """[dispatch ->] partition -> voxelize -> local build -> NCCL all-reduce of the table -> merged emit."""
         sb = self.sb
+        if getattr(self, "local", None) is not None:
+            sb.dispatch_count(prm, self.local)
+            sb.dispatch_send()
+            sb.dispatch_finish()
         sb.partition(prm, want_counts=False)
         sb.voxelize()
         n = sb.shard_table_size()
@@ -176,6 +231,13 @@ class DistributedBuilder:
         return sb.shard_emit(self.table.data_ptr())      # sum over ranks == union of disjoint entries (NCCL over NVLink)
 
     def close(self):
+        self.sb.synchronize()
+        if getattr(self, "_opened", None):
+            from .api import ipc_close
+            self.dist.barrier()                      # nobody unmaps while a peer may still be writing
+            for p in self._opened:
+                ipc_close(p)
+            self._opened = []
         self.sb.close()
 
 
@@ -233,22 +295,44 @@ def bench(args, rank, world, local, dist, peak, peak_src, ClockSampler):
     G = 2048                                  # 8 logical partitions of 1024^3 (default -l 2048)
     octants = {2: [0, 4], 4: [0, 2, 4, 6], 8: list(range(8))}[world]
     base = meshgen.displaced_sphere(SPHERE_N, SPHERE_N, seed=1, length=1.0)       # one sphere per populated octant
+    # File order: the i-th sphere of the file lies in the octant that rank i+1 owns, so with every rank holding the
+    # i-th slice of the file ALL triangle records cross NVLink in the dispatch (nothing is local by construction).
     parts = []
-    for o in octants:
+    for i in range(world):
+        o = octants[(i + 1) % world]
         off = np.array([(o & 1), (o >> 1) & 1, (o >> 2) & 1], dtype=np.float32)
         t = base.tris.reshape(-1, 3, 3) + off
         parts.append(t.reshape(-1, 9))
     tris = np.ascontiguousarray(np.concatenate(parts), dtype=np.float32)
     T = tris.shape[0]
+    lo_t, hi_t = slice_bounds(T, world, rank)
     db = DistributedBuilder(dist, local)
     stream = torch.cuda.Stream()
     db.set_stream(stream)
     prm = SvoBuilder.make_params(2.0, G, False)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    # triangle dispatch over NVLink peer memory (CUDA IPC); if the box cannot map peer memory, fall back to
+    # every rank holding the whole mesh (decided collectively, reported in config)
+    ok = torch.ones(1, dtype=torch.int32, device="cuda")
+    if os.environ.get("SVO_BENCH_DISPATCH", "1") != "1":
+        ok.zero_()
+    else:
+        try:
+            db.enable_dispatch(T, 9)
+        except Exception as e:      # noqa: BLE001
+            print("rank %d: triangle dispatch unavailable (%s)" % (rank, e), flush=True)
+            ok.zero_()
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    use_dispatch = bool(int(ok))
     with torch.cuda.stream(stream):
-        d_tris = torch.from_numpy(tris).cuda()
-        torch.cuda.synchronize()
-        db.set_triangles(d_tris)
+        if use_dispatch:
+            d_local = torch.from_numpy(tris[lo_t:hi_t]).cuda()
+            torch.cuda.synchronize()
+            db.set_local_triangles(d_local)
+        else:
+            d_tris = torch.from_numpy(tris).cuda()
+            torch.cuda.synchronize()
+            db.set_triangles(d_tris)
         for _ in range(max(args.warmup, 3)):
             flush.zero_()
             nv, nn, nd = db.step(prm)
@@ -281,16 +365,15 @@ def bench(args, rank, world, local, dist, peak, peak_src, ClockSampler):
     dist.all_reduce(leaf_ms, op=dist.ReduceOp.MAX)
 
     # e2e: HOST triangles in, this rank's node / data range out to pinned host memory. Every rank uploads only its
-    # 1/N slice of the triangle file over PCIe; the slices are all-gathered over NVLink (NCCL) so that each GPU
-    # holds the whole mesh (the binning needs every triangle), then the sharded step runs and each rank fetches
-    # its own range of the output files.
+    # 1/N slice of the triangle file over PCIe; the records then reach the ranks that voxelize them over NVLink
+    # (triangle dispatch; fallback: NCCL all-gather so that each GPU holds the whole mesh), the sharded step runs and
+    # each rank fetches its own range of the output files.
     nlo, nhi, dlo, dhi = db.sb.shard_ranges()
     from .api import PinnedBuffer
     per = (T + world - 1) // world
-    lo_t, hi_t = min(rank * per, T), min((rank + 1) * per, T)
     h_slice = torch.empty((per, 9), dtype=torch.float32).pin_memory()
     h_slice[: hi_t - lo_t].copy_(torch.from_numpy(tris[lo_t:hi_t]))
-    d_all = torch.empty((world * per, 9), dtype=torch.float32, device="cuda")
+    d_all = torch.empty((per if use_dispatch else world * per, 9), dtype=torch.float32, device="cuda")
     h_nodes = PinnedBuffer(max(nhi - nlo, 1) * 24 + 24 * 4096); h_data = PinnedBuffer(64)
     e2e = []
     with torch.cuda.stream(stream):
@@ -298,9 +381,13 @@ def bench(args, rank, world, local, dist, peak, peak_src, ClockSampler):
             torch.cuda.synchronize()
             dist.barrier()
             t = time.perf_counter()
-            d_all[rank * per:(rank + 1) * per].copy_(h_slice, non_blocking=True)                 # PCIe: 1/N of the mesh
-            dist.all_gather_into_tensor(d_all, d_all[rank * per:(rank + 1) * per])                 # NVLink: the rest
-            db.set_triangles(d_all[:T])
+            if use_dispatch:
+                d_all.copy_(h_slice, non_blocking=True)                                                # PCIe: 1/N of the mesh
+                db.set_local_triangles(d_all[: hi_t - lo_t])                                           # NVLink: inside step()
+            else:
+                d_all[rank * per:(rank + 1) * per].copy_(h_slice, non_blocking=True)                 # PCIe: 1/N of the mesh
+                dist.all_gather_into_tensor(d_all, d_all[rank * per:(rank + 1) * per])                 # NVLink: the rest
+                db.set_triangles(d_all[:T])
             db.step(prm)
             a, b, c_, d = db.sb.shard_ranges()
             db.sb.fetch_nodes(a, b - a, h_nodes.array[: (b - a) * 24])
@@ -321,7 +408,12 @@ def bench(args, rank, world, local, dist, peak, peak_src, ClockSampler):
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "voxels_per_s": nv / (ms_per_step * 1e-3),
             "config": {"workload": "svo_builder_binary -s 2048 (8 logical partitions of 1024^3), one 2M-triangle displaced sphere in each of "
-                                   "%d octants, partitions sharded over %d B200, NCCL all-reduce of the subtree table" % (world, world),
+                                   "%d octants, partitions sharded over %d B200; each rank starts with 1/%d of the triangle file in HBM; %s; "
+                                   "NCCL all-reduce of the subtree table" % (
+                                       world, world, world,
+                                       "triangle dispatch = our own all-to-all kernel storing records into peer HBM over NVLink, file ordered so that "
+                                       "every record crosses NVLink" if use_dispatch else "every rank holds the whole mesh (peer memory unavailable)"),
+                       "triangle_dispatch": "nvlink-peer-stores" if use_dispatch else "replicated",
                        "gridsize": G, "n_triangles": T, "n_voxels": nv, "n_nodes": nn, "partitions": 8,
                        "l2": "flushed between timed iterations (256 MB write)", "parallelism": "partition-sharded x%d" % world},
             "roofline": {"bound": "hbm", "kernel": "k_emit_leaf (per rank)", "achieved": (alg / world) / max(lm, 1e-9) / 1e6, "peak": peak, "unit": "GB/s",
@@ -329,10 +421,11 @@ def bench(args, rank, world, local, dist, peak, peak_src, ClockSampler):
                          "note": "octree build 8*N + 24*N_nodes bytes per rank / slowest rank's k_emit_leaf time"},
             "e2e": {"value": T / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(tris.nbytes),
                     "d2h_bytes_per_step": int(nn * 24 + nd * 32), "ms_per_step": e2e_s * 1e3,
-                    "api": "per rank: pinned H2D of 1/N of the .tridata + NCCL all-gather over NVLink + sharded step + svo_fetch_* of its "
-                           "file range to pinned host memory (wall clock, max over ranks)"},
+                    "api": "per rank: pinned H2D of 1/N of the .tridata + %s + sharded step + svo_fetch_* of its "
+                           "file range to pinned host memory (wall clock, max over ranks)" % (
+                               "triangle dispatch over NVLink" if use_dispatch else "NCCL all-gather over NVLink")},
             "gpu_launches": int(launches) * args.steps, "clocks": clocks,
-            "stage_ms_rank0": {k: st[k] for k in ("ms_partition", "ms_voxelize", "ms_vox_small", "ms_compact", "ms_build", "ms_emit", "ms_emit_leaf", "ms_clear")},
+            "stage_ms_rank0": {k: st[k] for k in ("ms_dispatch", "ms_partition", "ms_voxelize", "ms_vox_small", "ms_compact", "ms_build", "ms_emit", "ms_emit_leaf", "ms_clear")},
             "pairs_rank0": {k: st[k] for k in ("n_pairs", "n_small", "n_medium", "n_large")},
         }
         print(json.dumps(line), flush=True)

@@ -10,8 +10,8 @@ from ooc_svo_builder_b200 import sharded
 pytestmark = pytest.mark.gpu
 
 
-def _check(oracle, mesh, g, world, limit=2048, color="model"):
-    res = sharded.run_single_process(mesh.tris, mesh.length, g, world, memory_limit_mb=limit, color=color)
+def _check(oracle, mesh, g, world, limit=2048, color="model", **kw):
+    res = sharded.run_single_process(mesh.tris, mesh.length, g, world, memory_limit_mb=limit, color=color, **kw)
     hdr, nodes, data = sharded.assemble(res, g)
     want = oracle.build(mesh.tris, mesh.length, g, memory_limit_mb=limit, color=color)
     assert hdr == want.header
@@ -70,3 +70,109 @@ def test_sharded_levels_is_rejected():
             sb.partition(SvoBuilder.make_params(m.length, 64, False, levels=True))
     finally:
         sb.close()
+
+
+# ---- triangle dispatch over peer memory: every rank starts with a slice of the file only ----------------------
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_dispatch_single_partition_grid(oracle, world):
+    _check(oracle, mg.icosphere(5), 128, world, dispatch=True)
+    _check(oracle, mg.random_soup(1200, seed=3, large_frac=0.03), 256, world, dispatch=True)
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_dispatch_partitions(oracle, world):
+    _check(oracle, mg.icosphere(6), 256, world, limit=3, dispatch=True)
+    _check(oracle, mg.random_soup(1500, seed=5, large_frac=0.03), 256, world, limit=2, dispatch=True)
+    _check(oracle, mg.random_soup(1500, seed=11), 512, world, limit=2, dispatch=True)
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_dispatch_payload_keeps_file_order(oracle, world):
+    # first-triangle-wins (voxelizer.cpp:263) must survive the trip through the inboxes
+    m = mg.icosphere(5)
+    _check(oracle, mg.Mesh(mg.with_payload(m.tris), m.length), 256, world, limit=3, dispatch=True)
+    _check(oracle, mg.terrain(100, seed=2), 128, world, color="linear", dispatch=True)
+    _check(oracle, mg.random_soup(1500, seed=4, payload=True), 128, world, limit=2, dispatch=True)
+
+
+def test_dispatch_ragged_slices(oracle):
+    m = mg.random_soup(1000, seed=9, large_frac=0.02)
+    T = m.tris.shape[0]
+    _check(oracle, m, 256, 4, limit=3, dispatch=True, slices=[(0, T), (T, T), (T, T), (T, T)])          # all on rank 0
+    _check(oracle, m, 256, 4, limit=3, dispatch=True, slices=[(0, 0), (0, 1), (1, 130), (130, T)])      # empty / tiny slices
+    _check(oracle, mg.empty_mesh(), 256, 4, limit=3, dispatch=True)
+    _check(oracle, mg.single_triangle_on_partition_plane(), 256, 8, limit=3, dispatch=True)
+
+
+def test_dispatch_repeated_epochs(oracle):
+    # the same contexts run two jobs back to back: flags are epochs, the inbox is reused
+    import torch
+    from ooc_svo_builder_b200 import SvoBuilder
+    world = 4
+    ctxs = [SvoBuilder(0) for _ in range(world)]
+    try:
+        for r, sb in enumerate(ctxs):
+            sb.shard_configure(r, world)
+        ptrs = [sb.dispatch_create(4000, 9) for sb in ctxs]
+        for sb in ctxs:
+            sb.dispatch_attach([p[0] for p in ptrs], [p[1] for p in ptrs])
+        for seed, g in ((1, 128), (2, 256)):
+            m = mg.random_soup(3000, seed=seed)
+            prm = SvoBuilder.make_params(m.length, g, False, 2)
+            T = m.tris.shape[0]
+            local = [torch.from_numpy(m.tris[lo:hi].copy()).cuda() for lo, hi in (sharded.slice_bounds(T, world, r) for r in range(world))]
+            for sb, l in zip(ctxs, local):
+                sb.dispatch_count(prm, l)
+            for sb in ctxs:
+                sb.dispatch_send()
+            tables = []
+            for sb in ctxs:
+                sb.dispatch_finish()
+                sb.partition(prm, want_counts=False)
+                sb.voxelize()
+                t = torch.zeros(sb.shard_table_size(), dtype=torch.int64, device="cuda")
+                sb.shard_count(t.data_ptr())
+                sb.synchronize()
+                tables.append(t)
+            merged = torch.stack(tables).sum(dim=0)
+            res = []
+            for r, sb in enumerate(ctxs):
+                nv, nn, nd = sb.shard_emit(merged.data_ptr())
+                nlo, nhi, dlo, dhi = sb.shard_ranges()
+                res.append(sharded.ShardResult(r, nv, nn, nd, (nlo, nhi), (dlo, dhi), sb.fetch_nodes(nlo, nhi - nlo), sb.fetch_data(dlo, dhi - dlo), sb.stats()))
+            hdr, nodes, data = sharded.assemble(res, g)
+            want = oracle.build(m.tris, m.length, g, memory_limit_mb=2)
+            assert hdr == want.header and nodes.tobytes() == want.nodes and data.tobytes() == want.data
+    finally:
+        for sb in ctxs:
+            sb.close()
+
+
+def test_dispatch_inbox_overflow_is_reported_by_every_rank():
+    import torch
+    from ooc_svo_builder_b200 import SvoBuilder, SvoError
+    world = 2
+    ctxs = [SvoBuilder(0) for _ in range(world)]
+    try:
+        for r, sb in enumerate(ctxs):
+            sb.shard_configure(r, world)
+        m = mg.icosphere(4)                      # 5120 triangles, about half per rank
+        T = m.tris.shape[0]
+        ptrs = [sb.dispatch_create(T // 2, 9) for sb in ctxs]      # too small: boundary triangles go to both ranks
+        for sb in ctxs:
+            sb.dispatch_attach([p[0] for p in ptrs], [p[1] for p in ptrs])
+        prm = SvoBuilder.make_params(m.length, 128, False)
+        # file order of an icosphere is not spatial: each half routes ~half of its triangles to either rank
+        local = [torch.from_numpy(m.tris[lo:hi].copy()).cuda() for lo, hi in ((0, T // 2), (T // 2, T))]
+        for sb, l in zip(ctxs, local):
+            sb.dispatch_count(prm, l)
+        for sb in ctxs:
+            sb.dispatch_send()
+        for sb in ctxs:
+            with pytest.raises(SvoError) as e:
+                sb.dispatch_finish()
+            assert e.value.code == 4
+    finally:
+        for sb in ctxs:
+            sb.close()

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Strong scaling of a BASELINE.json config over the GPUs of one box (torchrun, one rank per GPU, NCCL):
-every rank holds the mesh, voxelizes + builds its partitions, the subtree table is all-reduced, every rank emits
+every rank holds 1/N of the triangle file (the others arrive by the NVLink triangle dispatch; SVO_BENCH_DISPATCH=0: every
+rank holds the whole mesh), voxelizes + builds its partitions, the subtree table is all-reduced, every rank emits
 its range of the node file. Prints the max-over-ranks step time and checks the global counts and that the
 per-rank ranges tile the file.
 
@@ -16,7 +17,7 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 from ooc_svo_builder_b200 import SvoBuilder, meshgen  # noqa: E402
-from ooc_svo_builder_b200.sharded import DistributedBuilder  # noqa: E402
+from ooc_svo_builder_b200.sharded import DistributedBuilder, slice_bounds  # noqa: E402
 
 CFG = {"c2": ("c2_displaced_sphere_1024", 1024), "c3": ("c3_terrain_2048_payload", 2048), "c4": ("c4_sphere_4096", 4096), "c5": ("c5_shell_8192", 8192)}
 
@@ -34,10 +35,18 @@ def main():
         stream = torch.cuda.Stream()
         db.set_stream(stream)
         prm = SvoBuilder.make_params(mesh.length, g, mesh.payload)
+        use_dispatch = os.environ.get("SVO_BENCH_DISPATCH", "1") == "1"
         with torch.cuda.stream(stream):
-            d = torch.from_numpy(mesh.tris).cuda()
-            torch.cuda.synchronize()
-            db.set_triangles(d)
+            if use_dispatch:
+                lo, hi = slice_bounds(mesh.n_triangles, world, rank)
+                d = torch.from_numpy(mesh.tris[lo:hi]).cuda()
+                torch.cuda.synchronize()
+                db.enable_dispatch(mesh.n_triangles, mesh.tris.shape[1])
+                db.set_local_triangles(d)
+            else:
+                d = torch.from_numpy(mesh.tris).cuda()
+                torch.cuda.synchronize()
+                db.set_triangles(d)
             ms = []
             for i in range(5):
                 dist.barrier()
@@ -52,7 +61,7 @@ def main():
         st = db.sb.stats()
         nlo, nhi, dlo, dhi = db.sb.shard_ranges()
         rng = [None] * world
-        dist.all_gather_object(rng, (nlo, nhi, st["ms_voxelize"], st["ms_build"], st["ms_emit_leaf"]))
+        dist.all_gather_object(rng, (nlo, nhi, st["ms_voxelize"], st["ms_build"], st["ms_emit_leaf"], st["ms_dispatch"]))
         if rank == 0:
             pos = 0
             for lo, hi, *_ in rng:
@@ -62,7 +71,8 @@ def main():
             step = float(t.mean())
             out[n] = {"world": world, "n_triangles": mesh.n_triangles, "gridsize": g, "n_voxels": nv, "n_nodes": nn, "ms_per_step_max_over_ranks": step,
                       "triangles_per_s": mesh.n_triangles / (step * 1e-3), "voxels_per_s": nv / (step * 1e-3),
-                      "per_rank": [{"node_range": [r[0], r[1]], "ms_voxelize": r[2], "ms_build": r[3], "ms_emit_leaf": r[4]} for r in rng]}
+                      "per_rank": [{"node_range": [r[0], r[1]], "ms_voxelize": r[2], "ms_build": r[3], "ms_emit_leaf": r[4], "ms_dispatch": r[5]} for r in rng],
+                      "triangle_dispatch": use_dispatch}
             print(n, json.dumps(out[n]), flush=True)
         db.close()
         del mesh, d
