@@ -73,7 +73,7 @@ typedef struct svo_stats {
     float ms_vox_small;         /* k_vox_small alone (subset of ms_voxelize)                   */
     float ms_emit_leaf;         /* k_emit_leaf alone (subset of ms_emit)                       */
     float ms_compact;           /* level counts + top-down tile-list expansion + subtree sizes */
-    float ms_dispatch;          /* multi-GPU triangle dispatch over peer memory (count + send + wait) */
+    float ms_dispatch;          /* multi-GPU: slice block-list pass (remote staging) or triangle dispatch */
     uint32_t kernel_launches;   /* kernels launched by the last run                            */
 } svo_stats;
 
@@ -180,9 +180,10 @@ int svo_shard_count(svo_ctx* ctx, uint64_t* dev_table);
 int svo_shard_emit(svo_ctx* ctx, const uint64_t* dev_table, uint64_t* n_voxels, uint64_t* n_nodes, uint64_t* n_data);
 int svo_shard_ranges(svo_ctx* ctx, uint64_t* node_lo, uint64_t* node_hi, uint64_t* data_lo, uint64_t* data_hi);
 
-/* ---- multi-GPU: triangle dispatch over NVLink peer memory -------------------
+/* ---- multi-GPU: triangle dispatch over NVLink peer memory (copying alternative) --
  *
- * Replaces, for the sharded build, the reference's partition files as the way
+ * For callers that want every rank to end up with a private, compact copy of
+ * its triangles (e.g. the slices cannot stay resident). Replaces, for the sharded build, the reference's partition files as the way
  * triangles reach the worker that voxelizes them (partitioner.cpp:101-149 writes
  * every triangle into the .tripdata file of each partition it touches; here it
  * is written into the HBM of each RANK whose slab it touches). Every rank starts
@@ -214,6 +215,39 @@ int svo_shard_dispatch_finish(svo_ctx* ctx, uint64_t* n_received);
 int svo_ipc_export(const void* dev_ptr, void* handle64);
 int svo_ipc_open(const void* handle64, void** dev_ptr);
 int svo_ipc_close(void* dev_ptr);
+
+/* ---- multi-GPU: remote staging of triangle slices (no copy at all) ----------
+ *
+ * The default multi-GPU input path. The triangle file stays where it was
+ * loaded: rank r keeps the r-th slice (file order) in a library-owned buffer in
+ * its own HBM, mapped by every peer. Per job each rank lists, for every
+ * destination rank, the 128-triangle staging blocks of ITS slice that touch the
+ * destination's slab (one light pass over the local slice; 4 bytes per block
+ * stored into the destination's list buffer over NVLink). The destination's
+ * voxelizer then stages exactly those blocks straight from the owner's HBM with
+ * NVLink loads, overlapped with the math of its other resident blocks -- the
+ * transfer is fused into the voxelizer kernel, triangle records are never
+ * copied, and per-rank work does not grow with the number of ranks. Global
+ * triangle index = file position, so the payload rule "first triangle in file
+ * order wins" (voxelizer.cpp:263) is kept.
+ *
+ *   svo_shard_slice_create(capacity, fpt, &slice, &list, &ctrl)  once; capacity = max triangles per slice,
+ *                                                                the SAME value on every rank
+ *   <share the three device pointers with the peers>             svo_ipc_export / svo_ipc_open, or raw pointers
+ *   svo_shard_slice_attach(slice_ptrs, list_ptrs, ctrl_ptrs)     `world` entries each, entry [rank] = own buffers
+ *   svo_shard_slice_upload(src, n_local)     host or device source -> this rank's slice buffer (stream ordered;
+ *                                            waits on the device until the peers have finished reading the old one)
+ *   per job: svo_shard_slice_publish(params, n_total)            n_total = triangles in all slices (sizes work queues)
+ *            svo_partition / svo_voxelize / svo_shard_count / <all-reduce> / svo_shard_emit   as usual
+ *   svo_shard_slice_fence                    stream-ordered wait until every peer has finished reading this rank's
+ *                                            slice for the last published job (call before writing into `slice`
+ *                                            yourself; upload and publish do it for you)
+ * Per-partition counts (svo_partition's part_tricounts) are not available in this mode. At most 16 ranks. */
+int svo_shard_slice_create(svo_ctx* ctx, uint64_t capacity_tris, int floats_per_tri, void** dev_slice, void** dev_list, void** dev_ctrl);
+int svo_shard_slice_attach(svo_ctx* ctx, void* const* slice_ptrs, void* const* list_ptrs, void* const* ctrl_ptrs);
+int svo_shard_slice_upload(svo_ctx* ctx, const float* src, uint64_t n_local);
+int svo_shard_slice_publish(svo_ctx* ctx, const svo_params* params, uint64_t n_total);
+int svo_shard_slice_fence(svo_ctx* ctx);
 
 /* ---- whole path ---------------------------------------------------------- */
 

@@ -31,6 +31,7 @@ ABI_SYMBOLS = [
     "svo_shard_configure", "svo_shard_table_size", "svo_shard_count", "svo_shard_emit", "svo_shard_ranges",
     "svo_shard_dispatch_create", "svo_shard_dispatch_attach", "svo_shard_dispatch_count", "svo_shard_dispatch_send",
     "svo_shard_dispatch_finish", "svo_ipc_export", "svo_ipc_open", "svo_ipc_close",
+    "svo_shard_slice_create", "svo_shard_slice_attach", "svo_shard_slice_upload", "svo_shard_slice_publish", "svo_shard_slice_fence",
     "svo_run", "svo_get_stats", "svo_synchronize", "svo_host_alloc", "svo_host_free",
 ]
 
@@ -103,6 +104,11 @@ def load_library(path: str | None = None):
     L.svo_shard_dispatch_count.restype = i32; L.svo_shard_dispatch_count.argtypes = [vp, C.POINTER(Params), vp, u64, i32]
     L.svo_shard_dispatch_send.restype = i32; L.svo_shard_dispatch_send.argtypes = [vp]
     L.svo_shard_dispatch_finish.restype = i32; L.svo_shard_dispatch_finish.argtypes = [vp, C.POINTER(u64)]
+    L.svo_shard_slice_create.restype = i32; L.svo_shard_slice_create.argtypes = [vp, u64, i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    L.svo_shard_slice_attach.restype = i32; L.svo_shard_slice_attach.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    L.svo_shard_slice_upload.restype = i32; L.svo_shard_slice_upload.argtypes = [vp, vp, u64]
+    L.svo_shard_slice_publish.restype = i32; L.svo_shard_slice_publish.argtypes = [vp, C.POINTER(Params), u64]
+    L.svo_shard_slice_fence.restype = i32; L.svo_shard_slice_fence.argtypes = [vp]
     L.svo_ipc_export.restype = i32; L.svo_ipc_export.argtypes = [vp, vp]
     L.svo_ipc_open.restype = i32; L.svo_ipc_open.argtypes = [vp, C.POINTER(vp)]
     L.svo_ipc_close.restype = i32; L.svo_ipc_close.argtypes = [vp]
@@ -297,6 +303,35 @@ class SvoBuilder:
         a, b, c_, d = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint64()
         self._ck(self._lib.svo_shard_ranges(self._h, C.byref(a), C.byref(b), C.byref(c_), C.byref(d)))
         return a.value, b.value, c_.value, d.value
+
+    # -- remote staging of triangle slices (multi-GPU, default input path) ------
+    def slice_create(self, capacity_tris: int, fpt: int) -> tuple[int, int, int]:
+        """Allocates this rank's slice / list / control buffers; returns their device pointers (to share with the peers)."""
+        a, b, c_ = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        self._ck(self._lib.svo_shard_slice_create(self._h, capacity_tris, fpt, C.byref(a), C.byref(b), C.byref(c_)))
+        return a.value, b.value, c_.value
+
+    def slice_attach(self, slice_ptrs: list[int], list_ptrs: list[int], ctrl_ptrs: list[int]) -> None:
+        n = len(slice_ptrs)
+        self._ck(self._lib.svo_shard_slice_attach(self._h, (C.c_void_p * n)(*slice_ptrs), (C.c_void_p * n)(*list_ptrs), (C.c_void_p * n)(*ctrl_ptrs)))
+
+    def slice_upload(self, tris) -> None:
+        """This rank's slice of the triangle file: numpy host array (pageable or pinned) or torch CUDA tensor, (n, 9|21) float32."""
+        if isinstance(tris, np.ndarray):
+            tris = np.ascontiguousarray(tris, dtype=np.float32)
+            ptr = tris.ctypes.data
+        else:
+            assert tris.is_contiguous() and tris.element_size() == 4
+            ptr = tris.data_ptr()
+        self._keep_local = tris
+        self._ck(self._lib.svo_shard_slice_upload(self._h, ptr, tris.shape[0]))
+
+    def slice_publish(self, params: Params, n_total: int) -> None:
+        self.params = params
+        self._ck(self._lib.svo_shard_slice_publish(self._h, C.byref(params), n_total))
+
+    def slice_fence(self) -> None:
+        self._ck(self._lib.svo_shard_slice_fence(self._h))
 
     # -- triangle dispatch over peer memory (multi-GPU) -------------------------
     def dispatch_create(self, capacity_tris: int, fpt: int) -> tuple[int, int]:

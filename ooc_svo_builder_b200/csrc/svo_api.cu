@@ -134,6 +134,17 @@ struct svo_ctx {
     uint32_t dispatch_launches = 0;
     DispatchJob dj;
 
+    // remote staging of triangle slices (svo_dispatch.cuh)
+    DevBuf slice, sl_list, sl_ctrl, sl_cursor;
+    uint64_t slice_cap = 0, sl_cap_blocks = 0, slice_n_local = 0;
+    int slice_fpt = 0;
+    float* peer_slice[MAX_WORLD];
+    uint32_t* peer_list[MAX_WORLD];
+    SliceCtrl* peer_slctrl[MAX_WORLD];
+    bool sl_attached = false, sliced = false;
+    ull sl_epoch = 0;
+    SliceJob sj;
+
     svo_stats stats;
     uint32_t launches = 0;
 };
@@ -287,6 +298,15 @@ VoxJob make_voxjob(svo_ctx* c) {
     J.tileidx = c->tileidx.p ? c->tileidx.as<uint32_t>() - c->bias[0] : nullptr;
     J.leafprefix = c->lv[0].fc.as<ull>();
     J.owner = c->owner.as<uint32_t>();
+    if (c->sliced) {
+        J.segs.n = c->world;
+        for (int r = 0; r < c->world; r++) J.segs.ptr[r] = c->peer_slice[r];
+        const SliceCtrl* own = (const SliceCtrl*)c->sl_ctrl.p;
+        J.segs.nslice = own->nslice;
+        J.subset = c->sl_list.as<uint32_t>();
+        J.pull_cap = c->sl_cap_blocks;
+        J.pull_counts = &own->count[0][c->rank];
+    }
     return J;
 }
 
@@ -296,7 +316,14 @@ int launch_voxelizer(svo_ctx* c) {
     VoxJob J = make_voxjob(c);
     const size_t smem = J.pair_tri ? 0 : (size_t)VOX_BLOCK * c->fpt * sizeof(float);
     if (!OWNER) mark(c, EV_VS0);
-    if (c->use_subset) {
+    if (c->sliced) {
+        // remote staging: wait (on the device) until every peer has published its block lists, then walk them
+        if (!OWNER) { k_slice_wait<<<1, MAX_WORLD, 0, c->stream>>>((SliceCtrl*)c->sl_ctrl.p, c->world, 0, c->sl_epoch); LAUNCHED(); }
+        const unsigned g2 = (unsigned)c->sm_count * SVO_VOX_MINBLOCKS;
+        const size_t smem2 = (size_t)VOX_BLOCK * c->fpt * sizeof(float);
+        if (J.P > 1) { k_vox_small<OWNER, true, true><<<g2, VOX_BLOCK, smem2, c->stream>>>(J); LAUNCHED(); }
+        else { k_vox_small<OWNER, false, true><<<g2, VOX_BLOCK, smem2, c->stream>>>(J); LAUNCHED(); }
+    } else if (c->use_subset) {
         // sharded: compact the triangles that touch this rank's slab once (the owner pass reuses the list)
         if (!OWNER) {
             FilterJob Fj;
@@ -403,6 +430,7 @@ void svo_ctx_destroy(svo_ctx* c) {
     c->d_lvlptrs.release(); c->d_nwords.release(); c->d_counts.release();
     c->part_counts.release(); c->part_cursor.release(); c->part_off.release(); c->pair_tri.release();
     c->queue[0].release(); c->queue[1].release(); c->qcount.release(); c->subset.release();
+    c->slice.release(); c->sl_list.release(); c->sl_ctrl.release(); c->sl_cursor.release();
     c->inbox.release(); c->ctrl_buf.release(); c->blockcnt.release(); c->blockoff.release();
     if (c->h_ctrl) cudaFreeHost(c->h_ctrl);
     c->scan_tmp.release(); c->nodes.release(); c->data.release(); c->owner.release(); c->tileidx.release(); c->codes.release();
@@ -459,6 +487,7 @@ static int set_tris_common(svo_ctx* c, uint64_t n_tris, int fpt) {
     c->fpt = fpt;
     c->have_tris = true;
     c->dispatched = false;
+    c->sliced = false;
     c->partitioned = c->voxelized = c->built = false;
     return SVO_OK;
 }
@@ -546,6 +575,8 @@ int svo_partition(svo_ctx* c, const svo_params* params, uint64_t* n_partitions, 
         c->n_pairs = 0;
         // Default: the voxelizer enumerates each triangle's partitions inline (no lists, no read-back). The
         // per-partition counts (what the reference writes to the .trip header) are computed only on request.
+        if (c->sliced && (c->use_lists || part_tricounts))
+            return fail(c, SVO_E_INVALID, "per-partition lists / counts are not available with remote triangle slices");
         if (c->use_lists || part_tricounts) {
             CK(c->part_counts.ensure(c->P * sizeof(ull)));
             CK(c->part_cursor.ensure(c->P * sizeof(ull)));
@@ -682,7 +713,7 @@ int svo_voxelize(svo_ctx* c) {
     if (rc) return rc;
     CK(c->qcount.ensure(8 * sizeof(ull)));
     CK(cudaMemsetAsync(c->qcount.p, 0, 8 * sizeof(ull), c->stream));
-    c->use_subset = c->world > 1 && !c->dispatched && !(c->P > 1 && c->use_lists);
+    c->use_subset = c->world > 1 && !c->dispatched && !c->sliced && !(c->P > 1 && c->use_lists);
     if (c->use_subset) CK(c->subset.ensure((size_t)(c->n_tris / VOX_BLOCK + 2) * sizeof(uint32_t)));
     // queue capacity: exact with lists; with inline enumeration a triangle may appear once per partition it
     // touches, so leave headroom and detect overflow (qcount[3]) instead of trusting a bound
@@ -1120,6 +1151,11 @@ static int build_phase_b(svo_ctx* c, const ull* table) {
             PayloadJob Pj;
             memset(&Pj, 0, sizeof Pj);
             Pj.tris = c->d_tris; Pj.owner = c->owner.as<uint32_t>();
+            if (c->sliced) {
+                Pj.segs.n = c->world;
+                for (int r = 0; r < c->world; r++) Pj.segs.ptr[r] = c->peer_slice[r];
+                Pj.segs.nslice = ((const SliceCtrl*)c->sl_ctrl.p)->nslice;
+            }
             Pj.data = c->data.as<float>() - c->data_lo * 8;
             Pj.unit_div = c->unit_div; Pj.gridsize_f = (float)c->prm.gridsize; Pj.color_mode = c->prm.color_mode;
             Pj.levels = levels ? 1 : 0;
@@ -1151,10 +1187,21 @@ static int build_phase_b(svo_ctx* c, const ull* table) {
     }
     c->dense_clean = true;
     mark(c, EV_CLR1);
+    c->h_pinned[48] = 0;
+    if (c->sliced) {
+        // this rank has finished reading its peers' slices and lists: they may be rewritten for the next job
+        k_slice_post<<<1, MAX_WORLD, 0, c->stream>>>(c->sj, 1); LAUNCHED();
+        CK(cudaMemcpyAsync(c->h_pinned + 48, &((SliceCtrl*)c->sl_ctrl.p)->error, sizeof(ull), cudaMemcpyDeviceToHost, c->stream));
+    }
     // queue statistics
     CK(cudaMemcpyAsync(c->h_pinned + 40, c->qcount.p, 4 * sizeof(ull), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     c->phase_a_done = false;
+    if (c->h_pinned[48]) {
+        CK(cudaMemsetAsync(&((SliceCtrl*)c->sl_ctrl.p)->error, 0, sizeof(ull), c->stream));
+        c->dense_clean = false;
+        return fail(c, SVO_E_CUDA, "remote triangle slices: timed out waiting for a peer rank");
+    }
     if (c->h_pinned[43]) {
         c->dense_clean = false;
         return fail(c, SVO_E_NOMEM, "work queue overflow: too many medium/large triangle-partition pairs for inline enumeration; "
@@ -1178,8 +1225,8 @@ static int build_phase_b(svo_ctx* c, const ull* table) {
     c->stats.ms_vox_small = span(c, EV_VS0, EV_VS1);
     c->stats.ms_emit_leaf = c->lv[0].n ? span(c, EV_EL0, EV_EL1) : 0.f;
     c->stats.ms_compact = span(c, EV_BUILD0, EV_CMP1);
-    c->stats.ms_dispatch = c->dispatched ? span(c, EV_DSP0, EV_DSP1) : 0.f;
-    c->stats.kernel_launches = c->launches + (c->dispatched ? c->dispatch_launches : 0);
+    c->stats.ms_dispatch = (c->dispatched || c->sliced) ? span(c, EV_DSP0, EV_DSP1) : 0.f;
+    c->stats.kernel_launches = c->launches + ((c->dispatched || c->sliced) ? c->dispatch_launches : 0);
     return SVO_OK;
 }
 
@@ -1405,6 +1452,131 @@ int svo_shard_dispatch_finish(svo_ctx* c, uint64_t* n_received) {
     c->d_tris = c->inbox.as<float>();
     c->dispatched = true;
     if (n_received) *n_received = n_in;
+    return SVO_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Remote staging of triangle slices (svo_dispatch.cuh)
+// ---------------------------------------------------------------------------
+int svo_shard_slice_create(svo_ctx* c, uint64_t capacity_tris, int fpt, void** dev_slice, void** dev_list, void** dev_ctrl) {
+    if (!c) return SVO_E_INVALID;
+    if (fpt != 9 && fpt != 21) return fail(c, SVO_E_INVALID, "floats_per_tri must be 9 (binary) or 21 (payload)");
+    if (c->world > MAX_WORLD) return fail(c, SVO_E_INVALID, "remote triangle slices support at most 16 ranks");
+    if (capacity_tris * (uint64_t)c->world > 0xffffffffULL) return fail(c, SVO_E_INVALID, "more than 2^32-1 triangles");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    c->sl_attached = false; c->sliced = false;
+    c->slice.release(); c->sl_list.release(); c->sl_ctrl.release();
+    const uint64_t cap = capacity_tris ? capacity_tris : 1;
+    c->sl_cap_blocks = (cap + VOX_BLOCK - 1) / VOX_BLOCK;
+    // exact cudaMalloc allocations of their own: these are the buffers peers map
+    const size_t slice_bytes = (size_t)c->sl_cap_blocks * VOX_BLOCK * fpt * sizeof(float);
+    const size_t list_bytes = (size_t)c->world * c->sl_cap_blocks * sizeof(uint32_t);
+    CK(cudaMalloc(&c->slice.p, slice_bytes)); c->slice.cap = slice_bytes;
+    CK(cudaMalloc(&c->sl_list.p, list_bytes)); c->sl_list.cap = list_bytes;
+    CK(cudaMalloc(&c->sl_ctrl.p, sizeof(SliceCtrl))); c->sl_ctrl.cap = sizeof(SliceCtrl);
+    CK(cudaMemset(c->sl_ctrl.p, 0, sizeof(SliceCtrl)));
+    CK(c->sl_cursor.ensure(MAX_WORLD * sizeof(ull)));
+    CK(cudaMemset(c->sl_cursor.p, 0, MAX_WORLD * sizeof(ull)));
+    c->slice_cap = capacity_tris;
+    c->slice_fpt = fpt;
+    c->slice_n_local = 0;
+    c->sl_epoch = 0;
+    if (dev_slice) *dev_slice = c->slice.p;
+    if (dev_list) *dev_list = c->sl_list.p;
+    if (dev_ctrl) *dev_ctrl = c->sl_ctrl.p;
+    return SVO_OK;
+}
+
+int svo_shard_slice_attach(svo_ctx* c, void* const* slice_ptrs, void* const* list_ptrs, void* const* ctrl_ptrs) {
+    if (!c) return SVO_E_INVALID;
+    if (!c->slice.p) return fail(c, SVO_E_INVALID, "svo_shard_slice_attach before svo_shard_slice_create");
+    if (!slice_ptrs || !list_ptrs || !ctrl_ptrs) return fail(c, SVO_E_INVALID, "peer pointer arrays are NULL");
+    for (int r = 0; r < c->world; r++) {
+        if (!slice_ptrs[r] || !list_ptrs[r] || !ctrl_ptrs[r]) return fail(c, SVO_E_INVALID, "a peer pointer is NULL");
+        c->peer_slice[r] = (float*)slice_ptrs[r];
+        c->peer_list[r] = (uint32_t*)list_ptrs[r];
+        c->peer_slctrl[r] = (SliceCtrl*)ctrl_ptrs[r];
+    }
+    if (c->peer_slice[c->rank] != c->slice.p || (void*)c->peer_list[c->rank] != c->sl_list.p || (void*)c->peer_slctrl[c->rank] != c->sl_ctrl.p)
+        return fail(c, SVO_E_INVALID, "entry [rank] of the peer arrays must be this context's own buffers");
+    c->sl_attached = true;
+    return SVO_OK;
+}
+
+int svo_shard_slice_fence(svo_ctx* c) {
+    if (!c) return SVO_E_INVALID;
+    if (!c->sl_attached) return fail(c, SVO_E_INVALID, "svo_shard_slice_fence before svo_shard_slice_attach");
+    CK(cudaSetDevice(c->device));
+    if (c->sl_epoch) { k_slice_wait<<<1, MAX_WORLD, 0, c->stream>>>((SliceCtrl*)c->sl_ctrl.p, c->world, 1, c->sl_epoch); LAUNCHED(); }
+    return SVO_OK;
+}
+
+int svo_shard_slice_upload(svo_ctx* c, const float* src, uint64_t n_local) {
+    if (!c) return SVO_E_INVALID;
+    if (!c->sl_attached) return fail(c, SVO_E_INVALID, "svo_shard_slice_upload before svo_shard_slice_attach");
+    if (n_local > c->slice_cap) return fail(c, SVO_E_RANGE, "slice is larger than the capacity given to svo_shard_slice_create");
+    if (n_local && !src) return fail(c, SVO_E_INVALID, "src is NULL");
+    int rc = svo_shard_slice_fence(c);                      // peers may still be reading the previous contents
+    if (rc) return rc;
+    for (int i = 0; i < EV_COUNT; i++) c->ev_set[i] = false;
+    mark(c, EV_UP0);
+    if (n_local) CK(cudaMemcpyAsync(c->slice.p, src, (size_t)n_local * c->slice_fpt * sizeof(float), cudaMemcpyDefault, c->stream));
+    mark(c, EV_UP1);
+    c->slice_n_local = n_local;
+    return SVO_OK;
+}
+
+int svo_shard_slice_publish(svo_ctx* c, const svo_params* params, uint64_t n_total) {
+    if (!c) return SVO_E_INVALID;
+    if (!c->sl_attached) return fail(c, SVO_E_INVALID, "svo_shard_slice_publish before svo_shard_slice_attach");
+    int rc = validate_params(c, params);
+    if (rc) return rc;
+    if ((params->payload ? 21 : 9) != c->slice_fpt) return fail(c, SVO_E_INVALID, "params.payload does not match the slices' floats_per_tri");
+    if (n_total > 0xffffffffULL) return fail(c, SVO_E_INVALID, "more than 2^32-1 triangles");
+    CK(cudaSetDevice(c->device));
+    rc = derive_grid(c, params);
+    if (rc) return rc;
+    const int dc = shard_chunk_depth(c);
+    if (c->D - dc < 2) return fail(c, SVO_E_INVALID, "gridsize too small for this many shards");
+    rc = svo_shard_slice_fence(c);                          // the peers' list buffers are about to be rewritten
+    if (rc) return rc;
+    const uint32_t launches_before = c->launches;
+    mark(c, EV_DSP0);
+    SliceJob& S = c->sj;
+    memset(&S, 0, sizeof S);
+    DispatchJob& D = S.D;
+    D.tris = c->slice.as<float>(); D.fpt = (uint32_t)c->slice_fpt; D.n_local = c->slice_n_local;
+    D.world = c->world; D.me = c->rank;
+    D.use_partitions = c->P > 1 ? 1 : 0; D.k = c->k;
+    for (int i = 0; i < 32; i++) { D.bmin[i] = c->slab_min[i]; D.bmax[i] = c->slab_max[i]; }
+    for (int r = 0; r < c->world; r++) {
+        int lo[3], hi[3];
+        shard_box(c, r, dc, lo, hi);
+        for (int a = 0; a < 3; a++) {
+            D.lo[r][a] = c->P > 1 ? lo[a] / (int)c->side : lo[a];
+            D.hi[r][a] = c->P > 1 ? hi[a] / (int)c->side : hi[a];
+        }
+        S.list[r] = c->peer_list[r];
+        S.ctrl[r] = c->peer_slctrl[r];
+    }
+    D.unit_div = c->unit_div; D.gmax = (int)c->prm.gridsize - 1;
+    D.nb = (D.n_local + VOX_BLOCK - 1) / VOX_BLOCK;
+    D.epoch = ++c->sl_epoch;
+    S.cap = c->sl_cap_blocks;
+    S.cursor = c->sl_cursor.as<ull>();
+    if (D.nb) { k_slice_filter<<<(unsigned)D.nb, VOX_BLOCK, 0, c->stream>>>(S); LAUNCHED(); }
+    k_slice_post<<<1, MAX_WORLD, 0, c->stream>>>(S, 0); LAUNCHED();
+    mark(c, EV_DSP1);
+    c->dispatch_launches = c->launches - launches_before;
+    // the triangle set of this context is now the union of all slices, addressed by file position
+    c->n_tris = n_total;
+    c->fpt = c->slice_fpt;
+    c->d_tris = c->slice.as<float>();
+    c->have_tris = true;
+    c->dispatched = false;
+    c->sliced = true;
+    c->partitioned = c->voxelized = c->built = false;
     return SVO_OK;
 }
 

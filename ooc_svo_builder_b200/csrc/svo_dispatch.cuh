@@ -24,8 +24,6 @@
 
 namespace svo {
 
-constexpr int MAX_WORLD = 16;
-
 // One per context, in cudaMalloc'd memory that peers map (IPC or same-process pointers).
 struct DispatchCtrl {
     unsigned long long flag[2][MAX_WORLD];             // [phase][source rank] = last epoch that source finished
@@ -162,6 +160,77 @@ __global__ void __launch_bounds__(VOX_BLOCK) k_dispatch_write(DispatchJob D, uns
         const unsigned total = cnt * D.fpt;
         for (unsigned i = threadIdx.x; i < total; i += VOX_BLOCK) dst[i] = from[i];
         __syncthreads();                                         // s_out / s_warp are reused by the next destination
+    }
+    __threadfence_system();
+}
+
+// ---------------------------------------------------------------------------
+// Remote staging ("slices"): nothing is copied. Rank s lists, for every destination rank, the staging blocks of
+// ITS slice that touch the destination's slab and stores the list into the destination's list buffer (4 bytes per
+// block over NVLink); the destination's voxelizer then stages exactly those blocks from rank s's HBM with NVLink
+// loads, overlapped with the math of its other resident blocks (k_vox_small, SUBSET + segs).
+//   flag[0][s] = epoch : rank s's lists and slice size for this job are published
+//   flag[1][s] = epoch : rank s has finished reading its peers' slices and lists (they may be rewritten)
+// ---------------------------------------------------------------------------
+struct SliceCtrl {
+    unsigned long long flag[2][MAX_WORLD];
+    unsigned long long count[MAX_WORLD][MAX_WORLD];    // count[src][dst]: blocks of slice src listed for dst (row dst's own column is what it reads)
+    unsigned long long nslice[MAX_WORLD];              // triangles in slice s
+    unsigned long long error;
+};
+
+struct SliceJob {
+    DispatchJob D;                              // geometry + local slice (tris, fpt, n_local, nb); inbox / blockcnt unused
+    uint32_t* list[MAX_WORLD];                  // peer list buffers: region [src * cap, (src + 1) * cap) belongs to source src
+    SliceCtrl* ctrl[MAX_WORLD];
+    unsigned long long cap;                     // blocks per region
+    unsigned long long* cursor;                 // local, MAX_WORLD counters (zeroed by k_slice_post)
+};
+
+__global__ void __launch_bounds__(VOX_BLOCK) k_slice_filter(SliceJob S) {
+    __shared__ unsigned s_any;
+    if (threadIdx.x == 0) s_any = 0;
+    __syncthreads();
+    const unsigned long long t = (unsigned long long)blockIdx.x * VOX_BLOCK + threadIdx.x;
+    unsigned m = 0;
+    if (t < S.D.n_local) {
+        const float* v = S.D.tris + t * S.D.fpt;
+        float c[9];
+#pragma unroll
+        for (int i = 0; i < 9; i++) c[i] = __ldg(v + i);
+        m = dispatch_mask(S.D, c);
+    }
+    m = __reduce_or_sync(0xffffffffu, m);
+    if ((threadIdx.x & 31) == 0 && m) atomicOr(&s_any, m);
+    __syncthreads();
+    const int d = threadIdx.x;
+    if (d < S.D.world && ((s_any >> d) & 1u)) {
+        const unsigned long long pos = atomicAdd(&S.cursor[d], 1ULL);
+        S.list[d][(unsigned long long)S.D.me * S.cap + pos] = blockIdx.x;      // pos < nb <= cap
+    }
+}
+
+// phase 0: publish counts + slice size, raise flag 0, reset the cursors. phase 1: raise flag 1 (done reading).
+__global__ void __launch_bounds__(MAX_WORLD) k_slice_post(SliceJob S, int phase) {
+    const int p = threadIdx.x;
+    if (p >= S.D.world) return;
+    if (phase == 0) {
+        *(volatile unsigned long long*)&S.ctrl[p]->count[S.D.me][p] = S.cursor[p];
+        *(volatile unsigned long long*)&S.ctrl[p]->nslice[S.D.me] = S.D.n_local;
+        S.cursor[p] = 0ULL;
+    }
+    __threadfence_system();
+    *(volatile unsigned long long*)&S.ctrl[p]->flag[phase][S.D.me] = S.D.epoch;
+}
+
+__global__ void __launch_bounds__(MAX_WORLD) k_slice_wait(SliceCtrl* own, int world, int phase, unsigned long long epoch) {
+    const int p = threadIdx.x;
+    if (p >= world) return;
+    const volatile unsigned long long* f = &own->flag[phase][p];
+    const long long t0 = clock64();
+    while (*f < epoch) {
+        if (clock64() - t0 > 8000000000LL) { own->error = 1ULL + (unsigned long long)phase; break; }
+        __nanosleep(200);
     }
     __threadfence_system();
 }

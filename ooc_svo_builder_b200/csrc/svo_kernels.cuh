@@ -26,6 +26,31 @@ constexpr int MAX_LEVELS = 12;        // ceil(D/2), D <= 21 (libmorton's 21 bits
 constexpr int VOX_BLOCK = SVO_VOX_BLOCK;   // threads per block of the small-bbox voxelizer
 constexpr int WARPS_PER_BLOCK = 8;
 
+constexpr int MAX_WORLD = 16;         // ranks of a sharded build that exchange through peer memory
+
+// Sharded builds with remote staging: the triangle file stays where it was loaded -- slice s in the HBM of rank s --
+// and kernels read the records they need straight from the owner's memory (NVLink loads through peer pointers).
+// Global triangle index = file position = (sum of the slice sizes before s) + position in slice s.
+struct TriSegs {
+    const float* ptr[MAX_WORLD];              // slice s (local or peer pointer)
+    const unsigned long long* nslice;         // device: triangles in every slice (published by the peers)
+    int n;                                    // 0 = one local array (VoxJob::tris)
+};
+// smem table of segment starts: base[s] = global index of the first triangle of slice s, base[n] = total
+__device__ __forceinline__ void segs_bases(const TriSegs& S, unsigned long long* s_base) {
+    if (threadIdx.x == 0) {
+        unsigned long long acc = 0;
+        for (int s = 0; s < S.n; s++) { s_base[s] = acc; acc += S.nslice[s]; }
+        s_base[S.n] = acc;
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ const float* segs_record(const TriSegs& S, const unsigned long long* s_base, uint32_t tri, uint32_t fpt) {
+    int s = 0;
+    while (s + 1 < S.n && (unsigned long long)tri >= s_base[s + 1]) s++;
+    return S.ptr[s] + ((unsigned long long)tri - s_base[s]) * fpt;
+}
+
 struct VoxJob {
     const float* tris;                // .tridata image
     uint32_t fpt;                     // floats per triangle: 9 or 21
@@ -50,6 +75,11 @@ struct VoxJob {
     uint32_t p_first, p_last;
     const uint32_t* subset;               // sharded: triangles that touch this rank's slab (NULL = all triangles)
     const unsigned long long* subset_count;
+    // sharded with remote staging: per source rank s, subset[s * pull_cap + i] lists the staging blocks of slice s
+    // that touch this rank's slab (written by rank s), pull_counts[s * MAX_WORLD] how many
+    TriSegs segs;
+    unsigned long long pull_cap;
+    const unsigned long long* pull_counts;
     // sharding: level-0 word range owned by this context and the voxel bounding box of its slab.
     // lvl[] / tileidx are biased so that they are indexed with GLOBAL word indices.
     unsigned long long w_lo, w_hi;
@@ -103,8 +133,8 @@ __device__ __forceinline__ void partition_origin(const VoxJob& J, uint32_t part,
     py = (int)(compact3(part >> 1) * J.side);
     pz = (int)(compact3(part >> 2) * J.side);
 }
-__device__ __forceinline__ void load_vertices(const VoxJob& J, uint32_t tri, float* v) {
-    const float* t = J.tris + (size_t)tri * J.fpt;
+__device__ __forceinline__ void load_vertices(const VoxJob& J, const unsigned long long* s_base, uint32_t tri, float* v) {
+    const float* t = J.segs.n ? segs_record(J.segs, s_base, tri, J.fpt) : J.tris + (size_t)tri * J.fpt;
 #pragma unroll
     for (int i = 0; i < 9; i++) v[i] = __ldg(t + i);
 }
@@ -279,11 +309,11 @@ __device__ __forceinline__ void vox_small_body(const VoxJob& J, bool active, uin
     }
 }
 
-// Stage VOX_BLOCK consecutive triangle records starting at q0 through shared memory (float4 loads).
-__device__ __forceinline__ void stage_block(const VoxJob& J, uint64_t q0, uint64_t q_end, float4* s_stage4, float* s_stage) {
+// Stage VOX_BLOCK consecutive triangle records starting at q0 of `tris` through shared memory (float4 loads).
+__device__ __forceinline__ void stage_block(const float* tris, uint32_t fpt, uint64_t q0, uint64_t q_end, float4* s_stage4, float* s_stage) {
     const uint64_t nrec = (q_end - q0 < VOX_BLOCK) ? (q_end - q0) : VOX_BLOCK;
-    const uint64_t nfl = nrec * J.fpt;
-    const float* src = J.tris + q0 * J.fpt;                    // q0 is a multiple of VOX_BLOCK: 16-byte aligned
+    const uint64_t nfl = nrec * fpt;
+    const float* src = tris + q0 * fpt;                        // q0 is a multiple of VOX_BLOCK: 16-byte aligned
     const uint64_t n4 = nfl >> 2;
     const float4* src4 = reinterpret_cast<const float4*>(src);
     for (uint64_t i = threadIdx.x; i < n4; i += VOX_BLOCK) s_stage4[i] = __ldg(src4 + i);
@@ -296,6 +326,34 @@ __global__ void __launch_bounds__(VOX_BLOCK, SVO_VOX_MINBLOCKS) k_vox_small(VoxJ
     extern __shared__ float4 s_stage4[];
     float* s_stage = reinterpret_cast<float*>(s_stage4);
     float v[9];
+    if (SUBSET && J.segs.n) {
+        // sharded, remote staging: persistent blocks walk the block lists the source ranks published for this rank and
+        // stage each block from its owner's HBM (NVLink loads); the loads of one block overlap the math of the others
+        __shared__ unsigned long long s_base[MAX_WORLD + 1], s_pref[MAX_WORLD + 1];
+        segs_bases(J.segs, s_base);
+        if (threadIdx.x == 0) {
+            unsigned long long acc = 0;
+            for (int s = 0; s < J.segs.n; s++) { s_pref[s] = acc; acc += J.pull_counts[(size_t)s * MAX_WORLD]; }
+            s_pref[J.segs.n] = acc;
+        }
+        __syncthreads();
+        const unsigned long long count = s_pref[J.segs.n];
+        int src = 0;
+        for (unsigned long long li = blockIdx.x; li < count; li += gridDim.x) {
+            while (li >= s_pref[src + 1]) src++;
+            const uint64_t q0 = (uint64_t)J.subset[(size_t)src * J.pull_cap + (li - s_pref[src])] * VOX_BLOCK;
+            const uint64_t nseg = s_base[src + 1] - s_base[src];
+            const bool active = q0 + threadIdx.x < nseg;
+            stage_block(J.segs.ptr[src], J.fpt, q0, nseg, s_stage4, s_stage);
+            if (active) {
+#pragma unroll
+                for (int i = 0; i < 9; i++) v[i] = s_stage[threadIdx.x * J.fpt + i];
+            }
+            __syncthreads();
+            vox_small_body<OWNER, ENUM>(J, active, (uint32_t)(s_base[src] + q0 + threadIdx.x), 0u, v);
+        }
+        return;
+    }
     if (SUBSET) {
         // sharded: persistent blocks walk the list of staging blocks that touch this rank's slab (k_owner_filter)
         const unsigned long long count = *J.subset_count;
@@ -303,7 +361,7 @@ __global__ void __launch_bounds__(VOX_BLOCK, SVO_VOX_MINBLOCKS) k_vox_small(VoxJ
             const uint64_t q0 = (uint64_t)J.subset[li] * VOX_BLOCK;
             const uint64_t q = q0 + threadIdx.x;
             const bool active = q < J.q_end;
-            stage_block(J, q0, J.q_end, s_stage4, s_stage);
+            stage_block(J.tris, J.fpt, q0, J.q_end, s_stage4, s_stage);
             if (active) {
 #pragma unroll
                 for (int i = 0; i < 9; i++) v[i] = s_stage[threadIdx.x * J.fpt + i];
@@ -318,7 +376,7 @@ __global__ void __launch_bounds__(VOX_BLOCK, SVO_VOX_MINBLOCKS) k_vox_small(VoxJ
     const bool active = q < J.q_end;
     uint32_t tri = 0, part = 0;
     if (J.pair_tri == nullptr) {
-        stage_block(J, q0, J.q_end, s_stage4, s_stage);
+        stage_block(J.tris, J.fpt, q0, J.q_end, s_stage4, s_stage);
         tri = (uint32_t)q;
         if (active) {
 #pragma unroll
@@ -327,7 +385,7 @@ __global__ void __launch_bounds__(VOX_BLOCK, SVO_VOX_MINBLOCKS) k_vox_small(VoxJ
     } else if (active) {
         tri = J.pair_tri[q];
         part = pair_partition(J, q);
-        load_vertices(J, tri, v);
+        load_vertices(J, nullptr, tri, v);
     }
     vox_small_body<OWNER, ENUM>(J, active, tri, part, v);
 }
@@ -404,11 +462,11 @@ __device__ __forceinline__ void warp_voxelize_box(const VoxJob& J, const TriSetu
     }
 }
 
-__device__ __forceinline__ void queued_pair_setup(const VoxJob& J, unsigned long long e, uint32_t& tri, TriSetup& s, GridBox& b) {
+__device__ __forceinline__ void queued_pair_setup(const VoxJob& J, const unsigned long long* s_base, unsigned long long e, uint32_t& tri, TriSetup& s, GridBox& b) {
     tri = (uint32_t)(e & 0xffffffffULL);
     const uint32_t part = (uint32_t)(e >> 32);
     float v[9];
-    load_vertices(J, tri, v);
+    load_vertices(J, s_base, tri, v);
     int px, py, pz;
     partition_origin(J, part, px, py, pz);
     b = clamped_box(v, J.unit_div, px, py, pz, (int)J.side);
@@ -417,24 +475,24 @@ __device__ __forceinline__ void queued_pair_setup(const VoxJob& J, unsigned long
 }
 
 template <bool OWNER>
-__device__ __forceinline__ void vox_medium_body(const VoxJob& J) {
+__device__ __forceinline__ void vox_medium_body(const VoxJob& J, const unsigned long long* s_base) {
     const unsigned long long n = min(J.qcount[0], J.qcap);
     const unsigned long long nwarps = (unsigned long long)gridDim.x * WARPS_PER_BLOCK;
     for (unsigned long long e = (unsigned long long)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5); e < n; e += nwarps) {
         uint32_t tri; TriSetup s; GridBox b;
-        queued_pair_setup(J, J.queue[0][e], tri, s, b);
+        queued_pair_setup(J, s_base, J.queue[0][e], tri, s, b);
         warp_voxelize_box<OWNER>(J, s, b, tri, 0ULL, 1ULL);
     }
 }
 
 template <bool OWNER>
-__device__ __forceinline__ void vox_large_body(const VoxJob& J) {
+__device__ __forceinline__ void vox_large_body(const VoxJob& J, const unsigned long long* s_base) {
     const unsigned long long n = min(J.qcount[1], J.qcap);
     const unsigned long long nwarps = (unsigned long long)gridDim.x * WARPS_PER_BLOCK;
     const unsigned long long gw = (unsigned long long)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
     for (unsigned long long e = 0; e < n; e++) {
         uint32_t tri; TriSetup s; GridBox b;
-        queued_pair_setup(J, J.queue[1][e], tri, s, b);
+        queued_pair_setup(J, s_base, J.queue[1][e], tri, s, b);
         warp_voxelize_box<OWNER>(J, s, b, tri, gw, nwarps);
     }
 }
@@ -442,8 +500,10 @@ __device__ __forceinline__ void vox_large_body(const VoxJob& J) {
 // one launch for both queues (they are usually short or empty)
 template <bool OWNER>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_vox_queued(VoxJob J) {
-    vox_medium_body<OWNER>(J);
-    vox_large_body<OWNER>(J);
+    __shared__ unsigned long long s_base[MAX_WORLD + 1];
+    if (J.segs.n) segs_bases(J.segs, s_base);
+    vox_medium_body<OWNER>(J, s_base);
+    vox_large_body<OWNER>(J, s_base);
 }
 
 // ---------------------------------------------------------------------------
@@ -1322,6 +1382,7 @@ __global__ void __launch_bounds__(256) k_sparse_clear(const unsigned long long* 
 // ---------------------------------------------------------------------------
 struct PayloadJob {
     const float* tris;        // 21-float records
+    TriSegs segs;             // remote staging: the owner's record is read from the slice that holds it
     const uint32_t* owner;    // per leaf
     float* data;              // n_data * 8 floats (32-byte records)
     float unit_div;
@@ -1332,6 +1393,8 @@ struct PayloadJob {
 };
 
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_payload(Level L, PayloadJob Pj) {
+    __shared__ unsigned long long s_base[MAX_WORLD + 1];
+    if (Pj.segs.n) segs_bases(Pj.segs, s_base);
     const unsigned long long i = (unsigned long long)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
     if (i >= L.n) return;
     const int lane = threadIdx.x & 31;
@@ -1343,7 +1406,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_payload(Level L, Paylo
         const unsigned long long r = fc + __popcll(W & lowmask(bit));
         const unsigned long long m = (key << 6) | (unsigned long long)bit;
         const uint32_t cx = compact3(m), cy = compact3(m >> 1), cz = compact3(m >> 2);
-        const float* t = Pj.tris + (size_t)Pj.owner[r] * 21;
+        const float* t = Pj.segs.n ? segs_record(Pj.segs, s_base, Pj.owner[r], 21) : Pj.tris + (size_t)Pj.owner[r] * 21;
         float v[21];
 #pragma unroll
         for (int q = 0; q < 21; q++) v[q] = __ldg(t + q);

@@ -107,12 +107,14 @@ def slice_bounds(n_tris: int, world: int, rank: int) -> tuple[int, int]:
 
 def run_single_process(tris, length: float, gridsize: int, world: int, memory_limit_mb: int = 2048,
                        color: str = "model", device: int = 0, fetch: bool = True, dispatch: bool = False,
-                       slices: list | None = None) -> list[ShardResult]:
+                       slices: list | None = None, remote: bool = False) -> list[ShardResult]:
     """All `world` ranks as contexts of ONE process (sharing a GPU is fine): the table exchange is a
     host-side sum. Used by the single-GPU parity tests of the sharded path and by the CLI.
     dispatch=True: every rank starts with only its slice of the file and the triangle dispatch
     (svo_shard_dispatch_*) routes the records through the peers' inboxes -- same kernels as across GPUs,
-    the peer pointers just happen to be on one device. `slices` overrides the equal split ([(lo, hi)] per rank)."""
+    the peer pointers just happen to be on one device. `slices` overrides the equal split ([(lo, hi)] per rank).
+    remote=True: remote staging (svo_shard_slice_*): every rank keeps only its slice, the voxelizers read the blocks
+    they need from the owners' buffers."""
     import torch
     payload = tris.shape[1] == 21
     ctxs = [SvoBuilder(device) for _ in range(world)]
@@ -134,11 +136,24 @@ def run_single_process(tris, length: float, gridsize: int, world: int, memory_li
                 sb.dispatch_send()
             for sb in ctxs:
                 sb.dispatch_finish()
+        if remote:
+            T = tris.shape[0]
+            bounds = slices or [slice_bounds(T, world, r) for r in range(world)]
+            cap = max(max(hi - lo for lo, hi in bounds), 1)
+            for r, sb in enumerate(ctxs):
+                sb.shard_configure(r, world)
+            ptrs = [sb.slice_create(cap, tris.shape[1]) for sb in ctxs]
+            for sb in ctxs:
+                sb.slice_attach([p[0] for p in ptrs], [p[1] for p in ptrs], [p[2] for p in ptrs])
+            for sb, (lo, hi) in zip(ctxs, bounds):
+                sb.slice_upload(tris[lo:hi])
+            for sb in ctxs:                         # each phase for all ranks before the next (one host thread)
+                sb.slice_publish(prm, T)
         for r, sb in enumerate(ctxs):
-            if not dispatch:
+            if not dispatch and not remote:
                 sb.shard_configure(r, world)
                 sb.set_triangles(tris)
-            sb.partition(prm, want_counts=not dispatch)
+            sb.partition(prm, want_counts=not (dispatch or remote))
             sb.voxelize()
             t = torch.zeros(sb.shard_table_size(), dtype=torch.int64, device="cuda:%d" % device)
             sb.shard_count(t.data_ptr())
@@ -183,6 +198,7 @@ class DistributedBuilder:
     def set_triangles(self, tris):
         self.sb.set_triangles(tris)
         self.local = None
+        self.sliced = False
 
     def enable_dispatch(self, capacity_tris: int, fpt: int):
         """Allocates the inbox, exchanges CUDA IPC handles with the peers (once) and maps their inboxes:
@@ -204,6 +220,32 @@ class DistributedBuilder:
         self.sb.dispatch_attach(ib, cb)
         self.dist.barrier()
 
+    def enable_slices(self, capacity_tris: int, fpt: int, n_total: int):
+        """Remote staging: allocates the slice / list / control buffers, exchanges CUDA IPC handles with the peers
+        (once) and maps theirs. Afterwards the voxelizer stages triangle blocks straight from the owners' HBM."""
+        from .api import ipc_export, ipc_open
+        mine_ptrs = self.sb.slice_create(capacity_tris, fpt)
+        handles = [None] * self.world
+        self.dist.all_gather_object(handles, tuple(ipc_export(p) for p in mine_ptrs))
+        cols = ([], [], [])
+        self._opened = getattr(self, "_opened", [])
+        for r, hs in enumerate(handles):
+            for q in range(3):
+                if r == self.rank:
+                    cols[q].append(mine_ptrs[q])
+                else:
+                    p = ipc_open(hs[q])
+                    self._opened.append(p)
+                    cols[q].append(p)
+        self.sb.slice_attach(*cols)
+        self.n_total = n_total
+        self.sliced = True
+        self.dist.barrier()
+
+    def upload_slice(self, tris):
+        """This rank's slice (numpy host array or torch CUDA tensor) -> the mapped slice buffer, stream ordered."""
+        self.sb.slice_upload(tris)
+
     def set_local_triangles(self, local):
         """This rank's slice of the triangle file (torch CUDA tensor, file order across ranks)."""
         self.local = local
@@ -211,7 +253,9 @@ class DistributedBuilder:
     def step(self, prm):
         """[dispatch ->] partition -> voxelize -> local build -> NCCL all-reduce of the table -> merged emit."""
         sb = self.sb
-        if getattr(self, "local", None) is not None:
+        if getattr(self, "sliced", False):
+            sb.slice_publish(prm, self.n_total)
+        elif getattr(self, "local", None) is not None:
             sb.dispatch_count(prm, self.local)
             sb.dispatch_send()
             sb.dispatch_finish()
@@ -296,7 +340,7 @@ def bench(args, rank, world, local, dist, peak, peak_src, ClockSampler):
     octants = {2: [0, 4], 4: [0, 2, 4, 6], 8: list(range(8))}[world]
     base = meshgen.displaced_sphere(SPHERE_N, SPHERE_N, seed=1, length=1.0)       # one sphere per populated octant
     # File order: the i-th sphere of the file lies in the octant that rank i+1 owns, so with every rank holding the
-    # i-th slice of the file ALL triangle records cross NVLink in the dispatch (nothing is local by construction).
+    # i-th slice of the file ALL triangle records cross NVLink (nothing is local by construction).
     parts = []
     for i in range(world):
         o = octants[(i + 1) % world]
@@ -311,21 +355,32 @@ def bench(args, rank, world, local, dist, peak, peak_src, ClockSampler):
     db.set_stream(stream)
     prm = SvoBuilder.make_params(2.0, G, False)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    # triangle dispatch over NVLink peer memory (CUDA IPC); if the box cannot map peer memory, fall back to
-    # every rank holding the whole mesh (decided collectively, reported in config)
+    # Input path (SVO_BENCH_INPUT): "remote" (default) = remote staging of triangle slices over NVLink peer memory;
+    # "dispatch" = copying all-to-all of triangle records into peer inboxes; "replicated" = every rank holds the whole
+    # mesh. Both peer-memory modes need CUDA IPC; if the box cannot map peer memory, fall back to "replicated"
+    # (decided collectively, reported in config).
+    mode = os.environ.get("SVO_BENCH_INPUT", "remote")
+    per = (T + world - 1) // world
     ok = torch.ones(1, dtype=torch.int32, device="cuda")
-    if os.environ.get("SVO_BENCH_DISPATCH", "1") != "1":
-        ok.zero_()
-    else:
+    if mode != "replicated":
         try:
-            db.enable_dispatch(T, 9)
+            if mode == "remote":
+                db.enable_slices(per, 9, T)
+            else:
+                db.enable_dispatch(T, 9)
         except Exception as e:      # noqa: BLE001
-            print("rank %d: triangle dispatch unavailable (%s)" % (rank, e), flush=True)
+            print("rank %d: peer memory unavailable (%s)" % (rank, e), flush=True)
             ok.zero_()
     dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-    use_dispatch = bool(int(ok))
+    if not bool(int(ok)):
+        mode = "replicated"
+        db.sliced = False
+    use_dispatch = mode != "replicated"
     with torch.cuda.stream(stream):
-        if use_dispatch:
+        if mode == "remote":
+            db.upload_slice(torch.from_numpy(tris[lo_t:hi_t]).cuda())
+            torch.cuda.synchronize()
+        elif mode == "dispatch":
             d_local = torch.from_numpy(tris[lo_t:hi_t]).cuda()
             torch.cuda.synchronize()
             db.set_local_triangles(d_local)
@@ -370,7 +425,6 @@ def bench(args, rank, world, local, dist, peak, peak_src, ClockSampler):
     # each rank fetches its own range of the output files.
     nlo, nhi, dlo, dhi = db.sb.shard_ranges()
     from .api import PinnedBuffer
-    per = (T + world - 1) // world
     h_slice = torch.empty((per, 9), dtype=torch.float32).pin_memory()
     h_slice[: hi_t - lo_t].copy_(torch.from_numpy(tris[lo_t:hi_t]))
     d_all = torch.empty((per if use_dispatch else world * per, 9), dtype=torch.float32, device="cuda")
@@ -381,7 +435,9 @@ def bench(args, rank, world, local, dist, peak, peak_src, ClockSampler):
             torch.cuda.synchronize()
             dist.barrier()
             t = time.perf_counter()
-            if use_dispatch:
+            if mode == "remote":
+                db.upload_slice(h_slice.numpy()[: hi_t - lo_t])                                       # PCIe: 1/N of the mesh, NVLink: inside step()
+            elif mode == "dispatch":
                 d_all.copy_(h_slice, non_blocking=True)                                                # PCIe: 1/N of the mesh
                 db.set_local_triangles(d_all[: hi_t - lo_t])                                           # NVLink: inside step()
             else:
@@ -411,9 +467,12 @@ def bench(args, rank, world, local, dist, peak, peak_src, ClockSampler):
                                    "%d octants, partitions sharded over %d B200; each rank starts with 1/%d of the triangle file in HBM; %s; "
                                    "NCCL all-reduce of the subtree table" % (
                                        world, world, world,
-                                       "triangle dispatch = our own all-to-all kernel storing records into peer HBM over NVLink, file ordered so that "
-                                       "every record crosses NVLink" if use_dispatch else "every rank holds the whole mesh (peer memory unavailable)"),
-                       "triangle_dispatch": "nvlink-peer-stores" if use_dispatch else "replicated",
+                                       {"remote": "remote staging: the voxelizer kernel reads the triangle blocks it needs straight from the owner's HBM "
+                                                  "with NVLink loads (no copy), file ordered so that every record crosses NVLink",
+                                        "dispatch": "triangle dispatch = our own all-to-all kernel storing records into peer HBM over NVLink, file ordered "
+                                                    "so that every record crosses NVLink",
+                                        "replicated": "every rank holds the whole mesh"}[mode]),
+                       "triangle_input": mode,
                        "gridsize": G, "n_triangles": T, "n_voxels": nv, "n_nodes": nn, "partitions": 8,
                        "l2": "flushed between timed iterations (256 MB write)", "parallelism": "partition-sharded x%d" % world},
             "roofline": {"bound": "hbm", "kernel": "k_emit_leaf (per rank)", "achieved": (alg / world) / max(lm, 1e-9) / 1e6, "peak": peak, "unit": "GB/s",
@@ -423,7 +482,8 @@ def bench(args, rank, world, local, dist, peak, peak_src, ClockSampler):
                     "d2h_bytes_per_step": int(nn * 24 + nd * 32), "ms_per_step": e2e_s * 1e3,
                     "api": "per rank: pinned H2D of 1/N of the .tridata + %s + sharded step + svo_fetch_* of its "
                            "file range to pinned host memory (wall clock, max over ranks)" % (
-                               "triangle dispatch over NVLink" if use_dispatch else "NCCL all-gather over NVLink")},
+                               {"remote": "remote staging over NVLink inside the voxelizer", "dispatch": "triangle dispatch over NVLink",
+                                "replicated": "NCCL all-gather over NVLink"}[mode])},
             "gpu_launches": int(launches) * args.steps, "clocks": clocks,
             "stage_ms_rank0": {k: st[k] for k in ("ms_dispatch", "ms_partition", "ms_voxelize", "ms_vox_small", "ms_compact", "ms_build", "ms_emit", "ms_emit_leaf", "ms_clear")},
             "pairs_rank0": {k: st[k] for k in ("n_pairs", "n_small", "n_medium", "n_large")},

@@ -176,3 +176,78 @@ def test_dispatch_inbox_overflow_is_reported_by_every_rank():
     finally:
         for sb in ctxs:
             sb.close()
+
+
+# ---- remote staging: every rank keeps its slice, voxelizers read blocks from the owners' buffers ------------------
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_remote_slices_single_partition_grid(oracle, world):
+    _check(oracle, mg.icosphere(5), 128, world, remote=True)
+    _check(oracle, mg.random_soup(1200, seed=3, large_frac=0.03), 256, world, remote=True)
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_remote_slices_partitions(oracle, world):
+    _check(oracle, mg.icosphere(6), 256, world, limit=3, remote=True)
+    _check(oracle, mg.random_soup(1500, seed=5, large_frac=0.03), 256, world, limit=2, remote=True)
+    _check(oracle, mg.random_soup(1500, seed=11), 512, world, limit=2, remote=True)
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_remote_slices_payload(oracle, world):
+    m = mg.icosphere(5)
+    _check(oracle, mg.Mesh(mg.with_payload(m.tris), m.length), 256, world, limit=3, remote=True)
+    _check(oracle, mg.terrain(100, seed=2), 128, world, color="linear", remote=True)
+    _check(oracle, mg.random_soup(1500, seed=4, payload=True, large_frac=0.03), 128, world, limit=2, remote=True)
+
+
+def test_remote_slices_ragged(oracle):
+    m = mg.random_soup(1000, seed=9, large_frac=0.02)
+    T = m.tris.shape[0]
+    _check(oracle, m, 256, 4, limit=3, remote=True, slices=[(0, T), (T, T), (T, T), (T, T)])
+    _check(oracle, m, 256, 4, limit=3, remote=True, slices=[(0, 0), (0, 1), (1, 130), (130, T)])
+    _check(oracle, mg.empty_mesh(), 256, 4, limit=3, remote=True)
+    _check(oracle, mg.single_triangle_on_partition_plane(), 256, 8, limit=3, remote=True)
+
+
+def test_remote_slices_repeated_jobs(oracle):
+    # same contexts, three jobs back to back with new slice contents: the fences order reuse of the buffers
+    import torch
+    from ooc_svo_builder_b200 import SvoBuilder
+    world = 4
+    ctxs = [SvoBuilder(0) for _ in range(world)]
+    try:
+        for r, sb in enumerate(ctxs):
+            sb.shard_configure(r, world)
+        ptrs = [sb.slice_create(1000, 9) for sb in ctxs]
+        for sb in ctxs:
+            sb.slice_attach([p[0] for p in ptrs], [p[1] for p in ptrs], [p[2] for p in ptrs])
+        for seed, g in ((1, 128), (2, 256), (3, 64)):
+            m = mg.random_soup(3000 + 100 * seed, seed=seed)
+            prm = SvoBuilder.make_params(m.length, g, False, 2)
+            T = m.tris.shape[0]
+            for r, sb in enumerate(ctxs):
+                lo, hi = sharded.slice_bounds(T, world, r)
+                sb.slice_upload(m.tris[lo:hi])
+            for sb in ctxs:
+                sb.slice_publish(prm, T)
+            tables = []
+            for sb in ctxs:
+                sb.partition(prm, want_counts=False)
+                sb.voxelize()
+                t = torch.zeros(sb.shard_table_size(), dtype=torch.int64, device="cuda")
+                sb.shard_count(t.data_ptr())
+                sb.synchronize()
+                tables.append(t)
+            merged = torch.stack(tables).sum(dim=0)
+            res = []
+            for r, sb in enumerate(ctxs):
+                nv, nn, nd = sb.shard_emit(merged.data_ptr())
+                nlo, nhi, dlo, dhi = sb.shard_ranges()
+                res.append(sharded.ShardResult(r, nv, nn, nd, (nlo, nhi), (dlo, dhi), sb.fetch_nodes(nlo, nhi - nlo), sb.fetch_data(dlo, dhi - dlo), sb.stats()))
+            hdr, nodes, data = sharded.assemble(res, g)
+            want = oracle.build(m.tris, m.length, g, memory_limit_mb=2)
+            assert hdr == want.header and nodes.tobytes() == want.nodes and data.tobytes() == want.data
+    finally:
+        for sb in ctxs:
+            sb.close()

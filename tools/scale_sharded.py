@@ -1,7 +1,6 @@
 #!/usr/bin/env python
 """Strong scaling of a BASELINE.json config over the GPUs of one box (torchrun, one rank per GPU, NCCL):
-every rank holds 1/N of the triangle file (the others arrive by the NVLink triangle dispatch; SVO_BENCH_DISPATCH=0: every
-rank holds the whole mesh), voxelizes + builds its partitions, the subtree table is all-reduced, every rank emits
+every rank holds 1/N of the triangle file (the others arrive by the NVLink triangle dispatch; SVO_BENCH_INPUT=remote|dispatch|replicated), voxelizes + builds its partitions, the subtree table is all-reduced, every rank emits
 its range of the node file. Prints the max-over-ranks step time and checks the global counts and that the
 per-rank ranges tile the file.
 
@@ -35,10 +34,16 @@ def main():
         stream = torch.cuda.Stream()
         db.set_stream(stream)
         prm = SvoBuilder.make_params(mesh.length, g, mesh.payload)
-        use_dispatch = os.environ.get("SVO_BENCH_DISPATCH", "1") == "1"
+        mode = os.environ.get("SVO_BENCH_INPUT", "remote")
+        use_dispatch = mode
         with torch.cuda.stream(stream):
-            if use_dispatch:
-                lo, hi = slice_bounds(mesh.n_triangles, world, rank)
+            lo, hi = slice_bounds(mesh.n_triangles, world, rank)
+            if mode == "remote":
+                db.enable_slices((mesh.n_triangles + world - 1) // world, mesh.tris.shape[1], mesh.n_triangles)
+                db.upload_slice(mesh.tris[lo:hi])
+                torch.cuda.synchronize()
+                d = None
+            elif mode == "dispatch":
                 d = torch.from_numpy(mesh.tris[lo:hi]).cuda()
                 torch.cuda.synchronize()
                 db.enable_dispatch(mesh.n_triangles, mesh.tris.shape[1])
