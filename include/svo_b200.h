@@ -231,20 +231,25 @@ int svo_ipc_close(void* dev_ptr);
  * triangle index = file position, so the payload rule "first triangle in file
  * order wins" (voxelizer.cpp:263) is kept.
  *
- *   svo_shard_slice_create(capacity, fpt, &slice, &list, &ctrl)  once; capacity = max triangles per slice,
- *                                                                the SAME value on every rank
- *   <share the three device pointers with the peers>             svo_ipc_export / svo_ipc_open, or raw pointers
- *   svo_shard_slice_attach(slice_ptrs, list_ptrs, ctrl_ptrs)     `world` entries each, entry [rank] = own buffers
+ *   svo_shard_slice_create(capacity, fpt, &window)   once; capacity = max triangles per slice, the SAME value on
+ *                                                    every rank. The window is ONE device allocation holding the
+ *                                                    control block, exchange table, block lists and the slice.
+ *   <share the window pointer with the peers>        svo_ipc_export / svo_ipc_open across processes, the raw
+ *                                                    pointer inside one process
+ *   svo_shard_slice_attach(windows)                  `world` entries, entry [rank] = own window
  *   svo_shard_slice_upload(src, n_local)     host or device source -> this rank's slice buffer (stream ordered;
  *                                            waits on the device until the peers have finished reading the old one)
  *   per job: svo_shard_slice_publish(params, n_total)            n_total = triangles in all slices (sizes work queues)
- *            svo_partition / svo_voxelize / svo_shard_count / <all-reduce> / svo_shard_emit   as usual
+ *            svo_partition / svo_voxelize / svo_shard_count / svo_shard_exchange / svo_shard_emit
+ *            (svo_shard_exchange replaces the caller's all-reduce of the table: every rank stores its own, disjoint
+ *             entries into the peers' windows with NVLink stores; no library collective on the path)
  *   svo_shard_slice_fence                    stream-ordered wait until every peer has finished reading this rank's
  *                                            slice for the last published job (call before writing into `slice`
  *                                            yourself; upload and publish do it for you)
  * Per-partition counts (svo_partition's part_tricounts) are not available in this mode. At most 16 ranks. */
-int svo_shard_slice_create(svo_ctx* ctx, uint64_t capacity_tris, int floats_per_tri, void** dev_slice, void** dev_list, void** dev_ctrl);
-int svo_shard_slice_attach(svo_ctx* ctx, void* const* slice_ptrs, void* const* list_ptrs, void* const* ctrl_ptrs);
+int svo_shard_slice_create(svo_ctx* ctx, uint64_t capacity_tris, int floats_per_tri, void** dev_window);
+int svo_shard_slice_attach(svo_ctx* ctx, void* const* windows);
+int svo_shard_exchange(svo_ctx* ctx, uint64_t* dev_table);
 int svo_shard_slice_upload(svo_ctx* ctx, const float* src, uint64_t n_local);
 int svo_shard_slice_publish(svo_ctx* ctx, const svo_params* params, uint64_t n_total);
 int svo_shard_slice_fence(svo_ctx* ctx);

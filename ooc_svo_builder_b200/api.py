@@ -32,6 +32,7 @@ ABI_SYMBOLS = [
     "svo_shard_dispatch_create", "svo_shard_dispatch_attach", "svo_shard_dispatch_count", "svo_shard_dispatch_send",
     "svo_shard_dispatch_finish", "svo_ipc_export", "svo_ipc_open", "svo_ipc_close",
     "svo_shard_slice_create", "svo_shard_slice_attach", "svo_shard_slice_upload", "svo_shard_slice_publish", "svo_shard_slice_fence",
+    "svo_shard_exchange",
     "svo_run", "svo_get_stats", "svo_synchronize", "svo_host_alloc", "svo_host_free",
 ]
 
@@ -104,8 +105,9 @@ def load_library(path: str | None = None):
     L.svo_shard_dispatch_count.restype = i32; L.svo_shard_dispatch_count.argtypes = [vp, C.POINTER(Params), vp, u64, i32]
     L.svo_shard_dispatch_send.restype = i32; L.svo_shard_dispatch_send.argtypes = [vp]
     L.svo_shard_dispatch_finish.restype = i32; L.svo_shard_dispatch_finish.argtypes = [vp, C.POINTER(u64)]
-    L.svo_shard_slice_create.restype = i32; L.svo_shard_slice_create.argtypes = [vp, u64, i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
-    L.svo_shard_slice_attach.restype = i32; L.svo_shard_slice_attach.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    L.svo_shard_slice_create.restype = i32; L.svo_shard_slice_create.argtypes = [vp, u64, i32, C.POINTER(vp)]
+    L.svo_shard_slice_attach.restype = i32; L.svo_shard_slice_attach.argtypes = [vp, C.POINTER(vp)]
+    L.svo_shard_exchange.restype = i32; L.svo_shard_exchange.argtypes = [vp, vp]
     L.svo_shard_slice_upload.restype = i32; L.svo_shard_slice_upload.argtypes = [vp, vp, u64]
     L.svo_shard_slice_publish.restype = i32; L.svo_shard_slice_publish.argtypes = [vp, C.POINTER(Params), u64]
     L.svo_shard_slice_fence.restype = i32; L.svo_shard_slice_fence.argtypes = [vp]
@@ -305,15 +307,20 @@ class SvoBuilder:
         return a.value, b.value, c_.value, d.value
 
     # -- remote staging of triangle slices (multi-GPU, default input path) ------
-    def slice_create(self, capacity_tris: int, fpt: int) -> tuple[int, int, int]:
-        """Allocates this rank's slice / list / control buffers; returns their device pointers (to share with the peers)."""
-        a, b, c_ = C.c_void_p(), C.c_void_p(), C.c_void_p()
-        self._ck(self._lib.svo_shard_slice_create(self._h, capacity_tris, fpt, C.byref(a), C.byref(b), C.byref(c_)))
-        return a.value, b.value, c_.value
+    def slice_create(self, capacity_tris: int, fpt: int) -> int:
+        """Allocates this rank's window (control block, exchange table, block lists, slice); returns its device
+        pointer (to share with the peers)."""
+        a = C.c_void_p()
+        self._ck(self._lib.svo_shard_slice_create(self._h, capacity_tris, fpt, C.byref(a)))
+        return a.value
 
-    def slice_attach(self, slice_ptrs: list[int], list_ptrs: list[int], ctrl_ptrs: list[int]) -> None:
-        n = len(slice_ptrs)
-        self._ck(self._lib.svo_shard_slice_attach(self._h, (C.c_void_p * n)(*slice_ptrs), (C.c_void_p * n)(*list_ptrs), (C.c_void_p * n)(*ctrl_ptrs)))
+    def slice_attach(self, windows: list[int]) -> None:
+        n = len(windows)
+        self._ck(self._lib.svo_shard_slice_attach(self._h, (C.c_void_p * n)(*windows)))
+
+    def shard_exchange(self, dev_table_ptr: int) -> None:
+        """The table exchange over peer memory (instead of the caller's all-reduce); needs the slice windows."""
+        self._ck(self._lib.svo_shard_exchange(self._h, dev_table_ptr))
 
     def slice_upload(self, tris) -> None:
         """This rank's slice of the triangle file: numpy host array (pageable or pinned) or torch CUDA tensor, (n, 9|21) float32."""

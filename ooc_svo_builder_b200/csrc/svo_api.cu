@@ -47,6 +47,8 @@ struct LevelBufs {
     }
 };
 
+constexpr size_t XTABLE_BYTES = 1u << 20;   // exchange table inside the slice window: up to 32768 top-of-shard entries
+
 enum { EV_UP0, EV_UP1, EV_PART0, EV_PART1, EV_VOX0, EV_VOX1, EV_BUILD0, EV_EMIT0, EV_EMIT1, EV_BUILD1, EV_VS0, EV_VS1, EV_EL0, EV_EL1, EV_CMP1, EV_CLR0, EV_CLR1, EV_DN0, EV_DN1, EV_DSP0, EV_DSP1, EV_COUNT };
 
 }  // namespace
@@ -135,7 +137,9 @@ struct svo_ctx {
     DispatchJob dj;
 
     // remote staging of triangle slices (svo_dispatch.cuh)
-    DevBuf slice, sl_list, sl_ctrl, sl_cursor;
+    DevBuf window, sl_cursor;          // window = [SliceCtrl | exchange table | block lists | slice], one allocation peers map
+    struct View { void* p = nullptr; template <class T> T* as() const { return static_cast<T*>(p); } } slice, sl_list, sl_ctrl, sl_xtable;
+    ull* peer_xtable[MAX_WORLD];
     uint64_t slice_cap = 0, sl_cap_blocks = 0, slice_n_local = 0;
     int slice_fpt = 0;
     float* peer_slice[MAX_WORLD];
@@ -320,9 +324,9 @@ int launch_voxelizer(svo_ctx* c) {
         // remote staging: wait (on the device) until every peer has published its block lists, then walk them
         if (!OWNER) { k_slice_wait<<<1, MAX_WORLD, 0, c->stream>>>((SliceCtrl*)c->sl_ctrl.p, c->world, 0, c->sl_epoch); LAUNCHED(); }
         const unsigned g2 = (unsigned)c->sm_count * SVO_VOX_MINBLOCKS;
-        const size_t smem2 = (size_t)VOX_BLOCK * c->fpt * sizeof(float);
-        if (J.P > 1) { k_vox_small<OWNER, true, true><<<g2, VOX_BLOCK, smem2, c->stream>>>(J); LAUNCHED(); }
-        else { k_vox_small<OWNER, false, true><<<g2, VOX_BLOCK, smem2, c->stream>>>(J); LAUNCHED(); }
+        const size_t smem2 = 2 * (size_t)VOX_BLOCK * c->fpt * sizeof(float);      // double-buffered staging
+        if (J.P > 1) { k_vox_small<OWNER, true, 2><<<g2, VOX_BLOCK, smem2, c->stream>>>(J); LAUNCHED(); }
+        else { k_vox_small<OWNER, false, 2><<<g2, VOX_BLOCK, smem2, c->stream>>>(J); LAUNCHED(); }
     } else if (c->use_subset) {
         // sharded: compact the triangles that touch this rank's slab once (the owner pass reuses the list)
         if (!OWNER) {
@@ -342,10 +346,10 @@ int launch_voxelizer(svo_ctx* c) {
         J.subset = c->subset.as<uint32_t>(); J.subset_count = c->qcount.as<ull>() + 4;
         const unsigned g2 = (unsigned)c->sm_count * SVO_VOX_MINBLOCKS;
         const size_t smem2 = (size_t)VOX_BLOCK * c->fpt * sizeof(float);
-        if (J.P > 1) { k_vox_small<OWNER, true, true><<<g2, VOX_BLOCK, smem2, c->stream>>>(J); LAUNCHED(); }
-        else { k_vox_small<OWNER, false, true><<<g2, VOX_BLOCK, smem2, c->stream>>>(J); LAUNCHED(); }
-    } else if (J.pair_tri == nullptr && J.P > 1) { k_vox_small<OWNER, true, false><<<blocks_for(c->q_end - c->q_begin, VOX_BLOCK), VOX_BLOCK, smem, c->stream>>>(J); LAUNCHED(); }
-    else { k_vox_small<OWNER, false, false><<<blocks_for(c->q_end - c->q_begin, VOX_BLOCK), VOX_BLOCK, smem, c->stream>>>(J); LAUNCHED(); }
+        if (J.P > 1) { k_vox_small<OWNER, true, 1><<<g2, VOX_BLOCK, smem2, c->stream>>>(J); LAUNCHED(); }
+        else { k_vox_small<OWNER, false, 1><<<g2, VOX_BLOCK, smem2, c->stream>>>(J); LAUNCHED(); }
+    } else if (J.pair_tri == nullptr && J.P > 1) { k_vox_small<OWNER, true, 0><<<blocks_for(c->q_end - c->q_begin, VOX_BLOCK), VOX_BLOCK, smem, c->stream>>>(J); LAUNCHED(); }
+    else { k_vox_small<OWNER, false, 0><<<blocks_for(c->q_end - c->q_begin, VOX_BLOCK), VOX_BLOCK, smem, c->stream>>>(J); LAUNCHED(); }
     if (!OWNER) mark(c, EV_VS1);
     const unsigned grid = (unsigned)c->sm_count * 4;
     k_vox_queued<OWNER><<<grid, WARPS_PER_BLOCK * 32, 0, c->stream>>>(J); LAUNCHED();
@@ -430,7 +434,7 @@ void svo_ctx_destroy(svo_ctx* c) {
     c->d_lvlptrs.release(); c->d_nwords.release(); c->d_counts.release();
     c->part_counts.release(); c->part_cursor.release(); c->part_off.release(); c->pair_tri.release();
     c->queue[0].release(); c->queue[1].release(); c->qcount.release(); c->subset.release();
-    c->slice.release(); c->sl_list.release(); c->sl_ctrl.release(); c->sl_cursor.release();
+    c->window.release(); c->sl_cursor.release();
     c->inbox.release(); c->ctrl_buf.release(); c->blockcnt.release(); c->blockoff.release();
     if (c->h_ctrl) cudaFreeHost(c->h_ctrl);
     c->scan_tmp.release(); c->nodes.release(); c->data.release(); c->owner.release(); c->tileidx.release(); c->codes.release();
@@ -1262,6 +1266,27 @@ int svo_shard_count(svo_ctx* c, uint64_t* dev_table) {
     return build_phase_a(c, (ull*)dev_table);
 }
 
+int svo_shard_exchange(svo_ctx* c, uint64_t* dev_table) {
+    if (!c) return SVO_E_INVALID;
+    if (!c->phase_a_done) return fail(c, SVO_E_INVALID, "svo_shard_exchange before svo_shard_count");
+    if (!c->sliced) return fail(c, SVO_E_INVALID, "svo_shard_exchange needs the peer windows of svo_shard_slice_*; otherwise sum the table with your own collective");
+    if (!dev_table) return fail(c, SVO_E_INVALID, "dev_table is NULL");
+    const size_t bytes = (size_t)c->WJ * 4 * sizeof(ull);
+    if (bytes > XTABLE_BYTES) return fail(c, SVO_E_RANGE, "subtree table is larger than the exchange window; sum it with your own collective");
+    CK(cudaSetDevice(c->device));
+    // own entries = the level-J words of this rank's slab: a contiguous range of the table; the ranges of all ranks tile it
+    XchgJob X;
+    memset(&X, 0, sizeof X);
+    X.src = (const ull*)dev_table;
+    X.lo = c->bias[c->J] * 4ULL; X.n = c->nwords[c->J] * 4ULL;
+    X.world = c->world; X.me = c->rank; X.epoch = c->sl_epoch;
+    for (int r = 0; r < c->world; r++) { X.xtable[r] = c->peer_xtable[r]; X.ctrl[r] = c->peer_slctrl[r]; }
+    k_xchg_push<<<c->world, 256, 0, c->stream>>>(X); LAUNCHED();
+    k_slice_wait<<<1, MAX_WORLD, 0, c->stream>>>((SliceCtrl*)c->sl_ctrl.p, c->world, 2, c->sl_epoch); LAUNCHED();
+    CK(cudaMemcpyAsync(dev_table, c->sl_xtable.p, bytes, cudaMemcpyDeviceToDevice, c->stream));
+    return SVO_OK;
+}
+
 int svo_shard_emit(svo_ctx* c, const uint64_t* dev_table, uint64_t* n_voxels, uint64_t* n_nodes, uint64_t* n_data) {
     if (!c) return SVO_E_INVALID;
     if (!c->phase_a_done) return fail(c, SVO_E_INVALID, "svo_shard_emit before svo_shard_count");
@@ -1458,7 +1483,20 @@ int svo_shard_dispatch_finish(svo_ctx* c, uint64_t* n_received) {
 // ---------------------------------------------------------------------------
 // Remote staging of triangle slices (svo_dispatch.cuh)
 // ---------------------------------------------------------------------------
-int svo_shard_slice_create(svo_ctx* c, uint64_t capacity_tris, int fpt, void** dev_slice, void** dev_list, void** dev_ctrl) {
+// Layout of the window every rank allocates (identical offsets on all ranks: same capacity, fpt, world)
+struct WindowLayout { size_t ctrl, xtable, list, slice, total; };
+static WindowLayout window_layout(uint64_t cap_blocks, int fpt, int world) {
+    WindowLayout L;
+    auto up = [](size_t v) { return (v + 4095) & ~(size_t)4095; };
+    L.ctrl = 0;
+    L.xtable = up(sizeof(SliceCtrl));
+    L.list = L.xtable + XTABLE_BYTES;
+    L.slice = L.list + up((size_t)world * cap_blocks * sizeof(uint32_t));
+    L.total = L.slice + up((size_t)cap_blocks * VOX_BLOCK * fpt * sizeof(float));
+    return L;
+}
+
+int svo_shard_slice_create(svo_ctx* c, uint64_t capacity_tris, int fpt, void** dev_window) {
     if (!c) return SVO_E_INVALID;
     if (fpt != 9 && fpt != 21) return fail(c, SVO_E_INVALID, "floats_per_tri must be 9 (binary) or 21 (payload)");
     if (c->world > MAX_WORLD) return fail(c, SVO_E_INVALID, "remote triangle slices support at most 16 ranks");
@@ -1466,15 +1504,14 @@ int svo_shard_slice_create(svo_ctx* c, uint64_t capacity_tris, int fpt, void** d
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->stream));
     c->sl_attached = false; c->sliced = false;
-    c->slice.release(); c->sl_list.release(); c->sl_ctrl.release();
+    c->window.release();
     const uint64_t cap = capacity_tris ? capacity_tris : 1;
     c->sl_cap_blocks = (cap + VOX_BLOCK - 1) / VOX_BLOCK;
-    // exact cudaMalloc allocations of their own: these are the buffers peers map
-    const size_t slice_bytes = (size_t)c->sl_cap_blocks * VOX_BLOCK * fpt * sizeof(float);
-    const size_t list_bytes = (size_t)c->world * c->sl_cap_blocks * sizeof(uint32_t);
-    CK(cudaMalloc(&c->slice.p, slice_bytes)); c->slice.cap = slice_bytes;
-    CK(cudaMalloc(&c->sl_list.p, list_bytes)); c->sl_list.cap = list_bytes;
-    CK(cudaMalloc(&c->sl_ctrl.p, sizeof(SliceCtrl))); c->sl_ctrl.cap = sizeof(SliceCtrl);
+    const WindowLayout L = window_layout(c->sl_cap_blocks, fpt, c->world);
+    // an exact cudaMalloc allocation of its own: this is the buffer peers map
+    CK(cudaMalloc(&c->window.p, L.total)); c->window.cap = L.total;
+    char* w = (char*)c->window.p;
+    c->sl_ctrl.p = w + L.ctrl; c->sl_xtable.p = w + L.xtable; c->sl_list.p = w + L.list; c->slice.p = w + L.slice;
     CK(cudaMemset(c->sl_ctrl.p, 0, sizeof(SliceCtrl)));
     CK(c->sl_cursor.ensure(MAX_WORLD * sizeof(ull)));
     CK(cudaMemset(c->sl_cursor.p, 0, MAX_WORLD * sizeof(ull)));
@@ -1482,24 +1519,24 @@ int svo_shard_slice_create(svo_ctx* c, uint64_t capacity_tris, int fpt, void** d
     c->slice_fpt = fpt;
     c->slice_n_local = 0;
     c->sl_epoch = 0;
-    if (dev_slice) *dev_slice = c->slice.p;
-    if (dev_list) *dev_list = c->sl_list.p;
-    if (dev_ctrl) *dev_ctrl = c->sl_ctrl.p;
+    if (dev_window) *dev_window = c->window.p;
     return SVO_OK;
 }
 
-int svo_shard_slice_attach(svo_ctx* c, void* const* slice_ptrs, void* const* list_ptrs, void* const* ctrl_ptrs) {
+int svo_shard_slice_attach(svo_ctx* c, void* const* windows) {
     if (!c) return SVO_E_INVALID;
-    if (!c->slice.p) return fail(c, SVO_E_INVALID, "svo_shard_slice_attach before svo_shard_slice_create");
-    if (!slice_ptrs || !list_ptrs || !ctrl_ptrs) return fail(c, SVO_E_INVALID, "peer pointer arrays are NULL");
+    if (!c->window.p) return fail(c, SVO_E_INVALID, "svo_shard_slice_attach before svo_shard_slice_create");
+    if (!windows) return fail(c, SVO_E_INVALID, "peer window array is NULL");
+    const WindowLayout L = window_layout(c->sl_cap_blocks, c->slice_fpt, c->world);
     for (int r = 0; r < c->world; r++) {
-        if (!slice_ptrs[r] || !list_ptrs[r] || !ctrl_ptrs[r]) return fail(c, SVO_E_INVALID, "a peer pointer is NULL");
-        c->peer_slice[r] = (float*)slice_ptrs[r];
-        c->peer_list[r] = (uint32_t*)list_ptrs[r];
-        c->peer_slctrl[r] = (SliceCtrl*)ctrl_ptrs[r];
+        if (!windows[r]) return fail(c, SVO_E_INVALID, "a peer window pointer is NULL");
+        char* w = (char*)windows[r];
+        c->peer_slctrl[r] = (SliceCtrl*)(w + L.ctrl);
+        c->peer_xtable[r] = (ull*)(w + L.xtable);
+        c->peer_list[r] = (uint32_t*)(w + L.list);
+        c->peer_slice[r] = (float*)(w + L.slice);
     }
-    if (c->peer_slice[c->rank] != c->slice.p || (void*)c->peer_list[c->rank] != c->sl_list.p || (void*)c->peer_slctrl[c->rank] != c->sl_ctrl.p)
-        return fail(c, SVO_E_INVALID, "entry [rank] of the peer arrays must be this context's own buffers");
+    if (windows[c->rank] != c->window.p) return fail(c, SVO_E_INVALID, "entry [rank] of the window array must be this context's own window");
     c->sl_attached = true;
     return SVO_OK;
 }

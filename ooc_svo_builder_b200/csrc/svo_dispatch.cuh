@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(VOX_BLOCK) k_dispatch_write(DispatchJob D, uns
 //   flag[1][s] = epoch : rank s has finished reading its peers' slices and lists (they may be rewritten)
 // ---------------------------------------------------------------------------
 struct SliceCtrl {
-    unsigned long long flag[2][MAX_WORLD];
+    unsigned long long flag[3][MAX_WORLD];             // [0] lists published, [1] done reading, [2] table entries pushed
     unsigned long long count[MAX_WORLD][MAX_WORLD];    // count[src][dst]: blocks of slice src listed for dst (row dst's own column is what it reads)
     unsigned long long nslice[MAX_WORLD];              // triangles in slice s
     unsigned long long error;
@@ -233,6 +233,29 @@ __global__ void __launch_bounds__(MAX_WORLD) k_slice_wait(SliceCtrl* own, int wo
         __nanosleep(200);
     }
     __threadfence_system();
+}
+
+// The one exchange of the sharded build -- the table of top-of-shard subtree records -- without a library collective:
+// the entries of different ranks are disjoint contiguous ranges, so every rank stores its own range into every peer's
+// exchange table (NVLink stores) and raises flag 2; after k_slice_wait(phase 2) each rank holds the complete table.
+struct XchgJob {
+    const unsigned long long* src;              // local table (only [lo, lo + n) is read)
+    unsigned long long lo, n;                   // own range, in u64
+    unsigned long long* xtable[MAX_WORLD];
+    SliceCtrl* ctrl[MAX_WORLD];
+    int world, me;
+    unsigned long long epoch;
+};
+__global__ void __launch_bounds__(256) k_xchg_push(XchgJob X) {
+    const int p = blockIdx.x;                   // one block per destination
+    unsigned long long* dst = X.xtable[p];
+    for (unsigned long long i = threadIdx.x; i < X.n; i += blockDim.x) dst[X.lo + i] = X.src[X.lo + i];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        *(volatile unsigned long long*)&X.ctrl[p]->flag[2][X.me] = X.epoch;
+    }
 }
 
 struct U32Op {

@@ -128,11 +128,7 @@ __device__ __forceinline__ uint32_t pair_partition(const VoxJob& J, uint64_t q) 
     }
     return lo;
 }
-__device__ __forceinline__ void partition_origin(const VoxJob& J, uint32_t part, int& px, int& py, int& pz) {
-    px = (int)(compact3(part) * J.side);          // voxelizer.cpp:149: decode(morton_start) -> (x, y, z)
-    py = (int)(compact3(part >> 1) * J.side);
-    pz = (int)(compact3(part >> 2) * J.side);
-}
+__device__ __forceinline__ uint32_t pack_slab(int ix, int iy, int iz) { return (uint32_t)ix | ((uint32_t)iy << 8) | ((uint32_t)iz << 16); }
 __device__ __forceinline__ void load_vertices(const VoxJob& J, const unsigned long long* s_base, uint32_t tri, float* v) {
     const float* t = J.segs.n ? segs_record(J.segs, s_base, tri, J.fpt) : J.tris + (size_t)tri * J.fpt;
 #pragma unroll
@@ -261,26 +257,26 @@ __device__ __forceinline__ void vox_small_body(const VoxJob& J, bool active, uin
             slab_range(J.bmin, J.bmax, 1 << J.k, J.inv_slab, stdmin(v[2], stdmin(v[5], v[8])), stdmax(v[2], stdmax(v[5], v[8])), lz, hz);
             nx = max(hx - lx + 1, 0); ny = max(hy - ly + 1, 0);
             count = nx * ny * max(hz - lz + 1, 0);
+        } else {
+            lx = (int)compact3(part); ly = (int)compact3(part >> 1); lz = (int)compact3(part >> 2);   // folds to 0 for P == 1
         }
     }
     const int most = ENUM ? __reduce_max_sync(0xffffffffu, count) : 1;   // warp-uniform trip count (1 almost always)
     TriSetup s;
     if (count > 0) tri_setup(v, J.u, s);
-    const uint32_t part0 = enumerate ? (uint32_t)morton3((uint32_t)lx, (uint32_t)ly, (uint32_t)lz) : part;
     for (int it = 0; it < most; it++) {
-        bool valid = it < count;
-        if (enumerate) {
-            part = part0;
-            if (it > 0 && valid)     // rare: a triangle that straddles a partition boundary
-                part = (uint32_t)morton3((uint32_t)(lx + it % nx), (uint32_t)(ly + (it / nx) % ny), (uint32_t)(lz + it / (nx * ny)));
-            valid = valid && part >= J.p_first && part <= J.p_last;         // partitions of other ranks
+        const bool valid = it < count;
+        // partition = slab coordinates (ix, iy, iz); no Morton round trip. Partitions of other ranks need no test of
+        // their own: a rank's slab is a box (an aligned power-of-two Morton range of chunks), so restrict_to_slab
+        // leaves nothing of a partition that lies outside it.
+        int ix = lx, iy = ly, iz = lz;
+        if (enumerate && it > 0 && valid) {     // rare: a triangle that straddles a partition boundary
+            ix = lx + it % nx; iy = ly + (it / nx) % ny; iz = lz + it / (nx * ny);
         }
         int cls = -1;
         GridBox b = { 0, -1, 0, -1, 0, -1 };
         if (valid) {
-            int px, py, pz;
-            partition_origin(J, part, px, py, pz);
-            b = clamped_box(v, J.unit_div, px, py, pz, (int)J.side);
+            b = clamped_box(v, J.unit_div, ix * (int)J.side, iy * (int)J.side, iz * (int)J.side, (int)J.side);   // voxelizer.cpp:149: partition origin
             if (restrict_to_slab(J, b)) {
                 const unsigned long long vol = (unsigned long long)(b.x1 - b.x0 + 1) * (unsigned long long)(b.y1 - b.y0 + 1) *
                                                (unsigned long long)(b.z1 - b.z0 + 1);
@@ -290,7 +286,7 @@ __device__ __forceinline__ void vox_small_body(const VoxJob& J, bool active, uin
             }
         }
         if (!OWNER) {
-            const unsigned long long e = ((unsigned long long)part << 32) | tri;
+            const unsigned long long e = ((unsigned long long)pack_slab(ix, iy, iz) << 32) | tri;     // queue entry: partition as slab coordinates
             warp_push(&J.qcount[0], J.queue[0], J.qcap, &J.qcount[3], cls == 1, e);
             warp_push(&J.qcount[1], J.queue[1], J.qcap, &J.qcount[3], cls == 2, e);
         }
@@ -321,12 +317,30 @@ __device__ __forceinline__ void stage_block(const float* tris, uint32_t fpt, uin
     __syncthreads();
 }
 
-template <bool OWNER, bool ENUM, bool SUBSET>
+// Same staging with cp.async (LDGSTS): the copy runs in the background while the block voxelizes the previous
+// staging block -- used by the persistent kernels, where the source may be a peer's HBM (NVLink latency).
+__device__ __forceinline__ void stage_block_async(const float* tris, uint32_t fpt, uint64_t q0, uint64_t q_end, float* s_stage) {
+    const uint64_t nrec = (q_end - q0 < VOX_BLOCK) ? (q_end - q0) : VOX_BLOCK;
+    const uint64_t nfl = nrec * fpt;
+    const float* src = tris + q0 * fpt;                        // 16-byte aligned (q0 is a multiple of VOX_BLOCK)
+    const uint64_t n4 = nfl >> 2;
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(s_stage);
+    for (uint64_t i = threadIdx.x; i < n4; i += VOX_BLOCK)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(sbase + (uint32_t)i * 16u), "l"(src + i * 4) : "memory");
+    for (uint64_t i = (n4 << 2) + threadIdx.x; i < nfl; i += VOX_BLOCK)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(sbase + (uint32_t)i * 4u), "l"(src + i) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
+// SUBSET: 0 = every triangle of [q_begin, q_end), 1 = the staging blocks listed by k_owner_filter (sharded, replicated
+// mesh), 2 = the staging blocks the source ranks listed for this rank, staged from their HBM (sharded, remote staging)
+template <bool OWNER, bool ENUM, int SUBSET>
 __global__ void __launch_bounds__(VOX_BLOCK, SVO_VOX_MINBLOCKS) k_vox_small(VoxJob J) {
     extern __shared__ float4 s_stage4[];
     float* s_stage = reinterpret_cast<float*>(s_stage4);
     float v[9];
-    if (SUBSET && J.segs.n) {
+    if (SUBSET == 2) {
         // sharded, remote staging: persistent blocks walk the block lists the source ranks published for this rank and
         // stage each block from its owner's HBM (NVLink loads); the loads of one block overlap the math of the others
         __shared__ unsigned long long s_base[MAX_WORLD + 1], s_pref[MAX_WORLD + 1];
@@ -338,23 +352,38 @@ __global__ void __launch_bounds__(VOX_BLOCK, SVO_VOX_MINBLOCKS) k_vox_small(VoxJ
         }
         __syncthreads();
         const unsigned long long count = s_pref[J.segs.n];
+        // double-buffered: while block `li` is voxelized, block `li + gridDim.x` streams into the other buffer
+        const uint32_t buf_floats = VOX_BLOCK * J.fpt;
         int src = 0;
-        for (unsigned long long li = blockIdx.x; li < count; li += gridDim.x) {
+        uint64_t q0 = 0, nseg = 0;
+        auto locate = [&](unsigned long long li) {
             while (li >= s_pref[src + 1]) src++;
-            const uint64_t q0 = (uint64_t)J.subset[(size_t)src * J.pull_cap + (li - s_pref[src])] * VOX_BLOCK;
-            const uint64_t nseg = s_base[src + 1] - s_base[src];
-            const bool active = q0 + threadIdx.x < nseg;
-            stage_block(J.segs.ptr[src], J.fpt, q0, nseg, s_stage4, s_stage);
+            q0 = (uint64_t)J.subset[(size_t)src * J.pull_cap + (li - s_pref[src])] * VOX_BLOCK;
+            nseg = s_base[src + 1] - s_base[src];
+        };
+        unsigned long long li = blockIdx.x;
+        if (li < count) { locate(li); stage_block_async(J.segs.ptr[src], J.fpt, q0, nseg, s_stage); }
+        cp_async_commit();
+        for (int it = 0; li < count; li += gridDim.x, it++) {
+            const float* cur = s_stage + (it & 1) * buf_floats;
+            const uint64_t my_q0 = q0, my_nseg = nseg;
+            const uint32_t tri = (uint32_t)(s_base[src] + q0 + threadIdx.x);
+            if (li + gridDim.x < count) { locate(li + gridDim.x); stage_block_async(J.segs.ptr[src], J.fpt, q0, nseg, s_stage + ((it + 1) & 1) * buf_floats); }
+            cp_async_commit();
+            cp_async_wait<1>();                                // everything but the newest group (the prefetch) has landed
+            __syncthreads();
+            const bool active = my_q0 + threadIdx.x < my_nseg;
             if (active) {
 #pragma unroll
-                for (int i = 0; i < 9; i++) v[i] = s_stage[threadIdx.x * J.fpt + i];
+                for (int i = 0; i < 9; i++) v[i] = cur[threadIdx.x * J.fpt + i];
             }
-            __syncthreads();
-            vox_small_body<OWNER, ENUM>(J, active, (uint32_t)(s_base[src] + q0 + threadIdx.x), 0u, v);
+            __syncthreads();                                   // the next iteration's prefetch overwrites `cur`
+            vox_small_body<OWNER, ENUM>(J, active, tri, 0u, v);
         }
+        cp_async_wait<0>();
         return;
     }
-    if (SUBSET) {
+    if (SUBSET == 1) {
         // sharded: persistent blocks walk the list of staging blocks that touch this rank's slab (k_owner_filter)
         const unsigned long long count = *J.subset_count;
         for (unsigned long long li = blockIdx.x; li < count; li += gridDim.x) {
@@ -464,11 +493,10 @@ __device__ __forceinline__ void warp_voxelize_box(const VoxJob& J, const TriSetu
 
 __device__ __forceinline__ void queued_pair_setup(const VoxJob& J, const unsigned long long* s_base, unsigned long long e, uint32_t& tri, TriSetup& s, GridBox& b) {
     tri = (uint32_t)(e & 0xffffffffULL);
-    const uint32_t part = (uint32_t)(e >> 32);
+    const uint32_t slab = (uint32_t)(e >> 32);                  // pack_slab(ix, iy, iz)
     float v[9];
     load_vertices(J, s_base, tri, v);
-    int px, py, pz;
-    partition_origin(J, part, px, py, pz);
+    const int px = (int)((slab & 0xffu) * J.side), py = (int)(((slab >> 8) & 0xffu) * J.side), pz = (int)(((slab >> 16) & 0xffu) * J.side);
     b = clamped_box(v, J.unit_div, px, py, pz, (int)J.side);
     restrict_to_slab(J, b);     // queued pairs are non-empty by construction
     tri_setup(v, J.u, s);

@@ -142,9 +142,9 @@ def run_single_process(tris, length: float, gridsize: int, world: int, memory_li
             cap = max(max(hi - lo for lo, hi in bounds), 1)
             for r, sb in enumerate(ctxs):
                 sb.shard_configure(r, world)
-            ptrs = [sb.slice_create(cap, tris.shape[1]) for sb in ctxs]
+            wins = [sb.slice_create(cap, tris.shape[1]) for sb in ctxs]
             for sb in ctxs:
-                sb.slice_attach([p[0] for p in ptrs], [p[1] for p in ptrs], [p[2] for p in ptrs])
+                sb.slice_attach(wins)
             for sb, (lo, hi) in zip(ctxs, bounds):
                 sb.slice_upload(tris[lo:hi])
             for sb in ctxs:                         # each phase for all ranks before the next (one host thread)
@@ -159,12 +159,21 @@ def run_single_process(tris, length: float, gridsize: int, world: int, memory_li
             sb.shard_count(t.data_ptr())
             sb.synchronize()
             tables.append(t)
-        merged = torch.stack(tables).sum(dim=0)
-        # disjointness is part of the contract
-        assert int((torch.stack([(t != 0).to(torch.int64) for t in tables]).sum(dim=0) > 1).sum()) == 0
+        if remote:
+            # one host thread drives all ranks: issue every rank's exchange before waiting on any of them (the
+            # device-side waits resolve once all ranks have pushed; nothing in between may synchronize the device)
+            for sb, t in zip(ctxs, tables):
+                sb.shard_exchange(t.data_ptr())
+            for sb in ctxs:
+                sb.synchronize()
+            assert all(bool((t == tables[0]).all()) for t in tables), "the peer-memory exchange left different tables on the ranks"
+        else:
+            merged = torch.stack(tables).sum(dim=0)
+            # disjointness is part of the contract
+            assert int((torch.stack([(t != 0).to(torch.int64) for t in tables]).sum(dim=0) > 1).sum()) == 0
         out = []
         for r, sb in enumerate(ctxs):
-            nv, nn, nd = sb.shard_emit(merged.data_ptr())
+            nv, nn, nd = sb.shard_emit(tables[r].data_ptr() if remote else merged.data_ptr())
             nlo, nhi, dlo, dhi = sb.shard_ranges()
             nodes = sb.fetch_nodes(nlo, nhi - nlo) if fetch else np.empty(0, np.uint8)
             data = sb.fetch_data(dlo, dhi - dlo) if fetch else np.empty(0, np.uint8)
@@ -224,20 +233,19 @@ class DistributedBuilder:
         """Remote staging: allocates the slice / list / control buffers, exchanges CUDA IPC handles with the peers
         (once) and maps theirs. Afterwards the voxelizer stages triangle blocks straight from the owners' HBM."""
         from .api import ipc_export, ipc_open
-        mine_ptrs = self.sb.slice_create(capacity_tris, fpt)
+        mine = self.sb.slice_create(capacity_tris, fpt)
         handles = [None] * self.world
-        self.dist.all_gather_object(handles, tuple(ipc_export(p) for p in mine_ptrs))
-        cols = ([], [], [])
+        self.dist.all_gather_object(handles, ipc_export(mine))
+        wins = []
         self._opened = getattr(self, "_opened", [])
-        for r, hs in enumerate(handles):
-            for q in range(3):
-                if r == self.rank:
-                    cols[q].append(mine_ptrs[q])
-                else:
-                    p = ipc_open(hs[q])
-                    self._opened.append(p)
-                    cols[q].append(p)
-        self.sb.slice_attach(*cols)
+        for r, h in enumerate(handles):
+            if r == self.rank:
+                wins.append(mine)
+            else:
+                p = ipc_open(h)
+                self._opened.append(p)
+                wins.append(p)
+        self.sb.slice_attach(wins)
         self.n_total = n_total
         self.sliced = True
         self.dist.barrier()
@@ -265,7 +273,9 @@ class DistributedBuilder:
         if self.table is None or self.table.numel() != n:
             self.table = self.torch.zeros(n, dtype=self.torch.int64, device="cuda:%d" % self.device)
         sb.shard_count(self.table.data_ptr())
-        if self.stream is not None:
+        if getattr(self, "sliced", False) and os.environ.get("SVO_TABLE_EXCHANGE", "peer") == "peer":
+            sb.shard_exchange(self.table.data_ptr())     # our own exchange over the peer windows (no NCCL on the path)
+        elif self.stream is not None:
             with self.torch.cuda.stream(self.stream):   # same queue as the kernels that filled / will read the table
                 self.dist.all_reduce(self.table)
         else:

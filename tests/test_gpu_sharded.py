@@ -219,9 +219,9 @@ def test_remote_slices_repeated_jobs(oracle):
     try:
         for r, sb in enumerate(ctxs):
             sb.shard_configure(r, world)
-        ptrs = [sb.slice_create(1000, 9) for sb in ctxs]
+        wins = [sb.slice_create(1000, 9) for sb in ctxs]
         for sb in ctxs:
-            sb.slice_attach([p[0] for p in ptrs], [p[1] for p in ptrs], [p[2] for p in ptrs])
+            sb.slice_attach(wins)
         for seed, g in ((1, 128), (2, 256), (3, 64)):
             m = mg.random_soup(3000 + 100 * seed, seed=seed)
             prm = SvoBuilder.make_params(m.length, g, False, 2)
