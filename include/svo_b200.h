@@ -74,6 +74,7 @@ typedef struct svo_stats {
     float ms_emit_leaf;         /* k_emit_leaf alone (subset of ms_emit)                       */
     float ms_compact;           /* level counts + top-down tile-list expansion + subtree sizes */
     float ms_dispatch;          /* multi-GPU: slice block-list pass (remote staging) or triangle dispatch */
+    float ms_peer_wait;         /* multi-GPU, remote staging: device-side wait for the peers' block lists  */
     uint32_t kernel_launches;   /* kernels launched by the last run                            */
 } svo_stats;
 

@@ -57,7 +57,7 @@ class Stats(C.Structure):
                 ("ms_upload", C.c_float), ("ms_partition", C.c_float), ("ms_voxelize", C.c_float),
                 ("ms_build", C.c_float), ("ms_emit", C.c_float), ("ms_clear", C.c_float), ("ms_download", C.c_float),
                 ("ms_vox_small", C.c_float), ("ms_emit_leaf", C.c_float), ("ms_compact", C.c_float),
-                ("ms_dispatch", C.c_float),
+                ("ms_dispatch", C.c_float), ("ms_peer_wait", C.c_float),
                 ("kernel_launches", C.c_uint32)]
 
     def as_dict(self) -> dict:

@@ -49,7 +49,7 @@ struct LevelBufs {
 
 constexpr size_t XTABLE_BYTES = 1u << 20;   // exchange table inside the slice window: up to 32768 top-of-shard entries
 
-enum { EV_UP0, EV_UP1, EV_PART0, EV_PART1, EV_VOX0, EV_VOX1, EV_BUILD0, EV_EMIT0, EV_EMIT1, EV_BUILD1, EV_VS0, EV_VS1, EV_EL0, EV_EL1, EV_CMP1, EV_CLR0, EV_CLR1, EV_DN0, EV_DN1, EV_DSP0, EV_DSP1, EV_COUNT };
+enum { EV_UP0, EV_UP1, EV_PART0, EV_PART1, EV_VOX0, EV_VOX1, EV_BUILD0, EV_EMIT0, EV_EMIT1, EV_BUILD1, EV_VS0, EV_VS1, EV_EL0, EV_EL1, EV_CMP1, EV_CLR0, EV_CLR1, EV_DN0, EV_DN1, EV_DSP0, EV_DSP1, EV_PW0, EV_PW1, EV_COUNT };
 
 }  // namespace
 
@@ -322,7 +322,12 @@ int launch_voxelizer(svo_ctx* c) {
     if (!OWNER) mark(c, EV_VS0);
     if (c->sliced) {
         // remote staging: wait (on the device) until every peer has published its block lists, then walk them
-        if (!OWNER) { k_slice_wait<<<1, MAX_WORLD, 0, c->stream>>>((SliceCtrl*)c->sl_ctrl.p, c->world, 0, c->sl_epoch); LAUNCHED(); }
+        if (!OWNER) {
+            mark(c, EV_PW0);
+            k_slice_wait<<<1, MAX_WORLD, 0, c->stream>>>((SliceCtrl*)c->sl_ctrl.p, c->world, 0, c->sl_epoch); LAUNCHED();
+            mark(c, EV_PW1);
+            mark(c, EV_VS0);                 // ms_vox_small excludes the wait for the peers' lists
+        }
         const unsigned g2 = (unsigned)c->sm_count * SVO_VOX_MINBLOCKS;
         const size_t smem2 = 2 * (size_t)VOX_BLOCK * c->fpt * sizeof(float);      // double-buffered staging
         if (J.P > 1) { k_vox_small<OWNER, true, 2><<<g2, VOX_BLOCK, smem2, c->stream>>>(J); LAUNCHED(); }
@@ -1229,6 +1234,7 @@ static int build_phase_b(svo_ctx* c, const ull* table) {
     c->stats.ms_vox_small = span(c, EV_VS0, EV_VS1);
     c->stats.ms_emit_leaf = c->lv[0].n ? span(c, EV_EL0, EV_EL1) : 0.f;
     c->stats.ms_compact = span(c, EV_BUILD0, EV_CMP1);
+    c->stats.ms_peer_wait = c->sliced ? span(c, EV_PW0, EV_PW1) : 0.f;
     c->stats.ms_dispatch = (c->dispatched || c->sliced) ? span(c, EV_DSP0, EV_DSP1) : 0.f;
     c->stats.kernel_launches = c->launches + ((c->dispatched || c->sliced) ? c->dispatch_launches : 0);
     return SVO_OK;

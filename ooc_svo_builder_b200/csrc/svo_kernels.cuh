@@ -317,21 +317,26 @@ __device__ __forceinline__ void stage_block(const float* tris, uint32_t fpt, uin
     __syncthreads();
 }
 
-// Same staging with cp.async (LDGSTS): the copy runs in the background while the block voxelizes the previous
-// staging block -- used by the persistent kernels, where the source may be a peer's HBM (NVLink latency).
-__device__ __forceinline__ void stage_block_async(const float* tris, uint32_t fpt, uint64_t q0, uint64_t q_end, float* s_stage) {
-    const uint64_t nrec = (q_end - q0 < VOX_BLOCK) ? (q_end - q0) : VOX_BLOCK;
-    const uint64_t nfl = nrec * fpt;
-    const float* src = tris + q0 * fpt;                        // 16-byte aligned (q0 is a multiple of VOX_BLOCK)
-    const uint64_t n4 = nfl >> 2;
-    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(s_stage);
-    for (uint64_t i = threadIdx.x; i < n4; i += VOX_BLOCK)
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(sbase + (uint32_t)i * 16u), "l"(src + i * 4) : "memory");
-    for (uint64_t i = (n4 << 2) + threadIdx.x; i < nfl; i += VOX_BLOCK)
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(sbase + (uint32_t)i * 4u), "l"(src + i) : "memory");
+// Bulk asynchronous staging (cp.async.bulk, the TMA engine) for the persistent remote-staging kernel: one thread
+// arms an mbarrier with the byte count and issues ONE copy of a whole staging block; the copy engine moves it into
+// shared memory while the block voxelizes the previous one. Measured on 2 x B200 (tools/native/p2p_probe.cu): LDGSTS
+// prefetch reaches the same NVLink bandwidth in isolation, but its long-lived remote requests sit in the SM's
+// load/store path and slow the voxelizer's own atomics down; the bulk engine does not go through it.
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count));
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void bulk_load(float* s_dst, const float* g_src, unsigned bytes, unsigned long long* bar) {
+    const uint32_t b = (uint32_t)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(b), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"((uint32_t)__cvta_generic_to_shared(s_dst)), "l"(g_src), "r"(bytes), "r"(b) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    const uint32_t b = (uint32_t)__cvta_generic_to_shared(bar);
+    asm volatile("{\n.reg .pred p;\nMBAR_WAIT: mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra MBAR_DONE;\nbra MBAR_WAIT;\nMBAR_DONE:\n}"
+                 :: "r"(b), "r"(parity) : "memory");
+}
 
 // SUBSET: 0 = every triangle of [q_begin, q_end), 1 = the staging blocks listed by k_owner_filter (sharded, replicated
 // mesh), 2 = the staging blocks the source ranks listed for this rank, staged from their HBM (sharded, remote staging)
@@ -352,8 +357,12 @@ __global__ void __launch_bounds__(VOX_BLOCK, SVO_VOX_MINBLOCKS) k_vox_small(VoxJ
         }
         __syncthreads();
         const unsigned long long count = s_pref[J.segs.n];
-        // double-buffered: while block `li` is voxelized, block `li + gridDim.x` streams into the other buffer
+        // double-buffered: while block `li` is voxelized, block `li + gridDim.x` streams into the other buffer.
+        // A whole staging block is copied every time (slices are padded to whole blocks), so the size is a multiple of 16.
+        __shared__ __align__(8) unsigned long long s_bar[2];
         const uint32_t buf_floats = VOX_BLOCK * J.fpt;
+        if (threadIdx.x == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); mbar_fence_init(); }
+        __syncthreads();
         int src = 0;
         uint64_t q0 = 0, nseg = 0;
         auto locate = [&](unsigned long long li) {
@@ -362,25 +371,28 @@ __global__ void __launch_bounds__(VOX_BLOCK, SVO_VOX_MINBLOCKS) k_vox_small(VoxJ
             nseg = s_base[src + 1] - s_base[src];
         };
         unsigned long long li = blockIdx.x;
-        if (li < count) { locate(li); stage_block_async(J.segs.ptr[src], J.fpt, q0, nseg, s_stage); }
-        cp_async_commit();
+        if (li < count) {
+            locate(li);
+            if (threadIdx.x == 0) bulk_load(s_stage, J.segs.ptr[src] + q0 * J.fpt, buf_floats * 4u, &s_bar[0]);
+        }
         for (int it = 0; li < count; li += gridDim.x, it++) {
             const float* cur = s_stage + (it & 1) * buf_floats;
             const uint64_t my_q0 = q0, my_nseg = nseg;
             const uint32_t tri = (uint32_t)(s_base[src] + q0 + threadIdx.x);
-            if (li + gridDim.x < count) { locate(li + gridDim.x); stage_block_async(J.segs.ptr[src], J.fpt, q0, nseg, s_stage + ((it + 1) & 1) * buf_floats); }
-            cp_async_commit();
-            cp_async_wait<1>();                                // everything but the newest group (the prefetch) has landed
-            __syncthreads();
+            if (li + gridDim.x < count) {
+                locate(li + gridDim.x);
+                // buffer (it + 1) & 1 was last read in iteration it - 1, before that iteration's __syncthreads
+                if (threadIdx.x == 0) bulk_load(s_stage + ((it + 1) & 1) * buf_floats, J.segs.ptr[src] + q0 * J.fpt, buf_floats * 4u, &s_bar[(it + 1) & 1]);
+            }
+            mbar_wait(&s_bar[it & 1], (unsigned)(it >> 1) & 1u);
             const bool active = my_q0 + threadIdx.x < my_nseg;
             if (active) {
 #pragma unroll
                 for (int i = 0; i < 9; i++) v[i] = cur[threadIdx.x * J.fpt + i];
             }
-            __syncthreads();                                   // the next iteration's prefetch overwrites `cur`
+            __syncthreads();                                   // everyone has its vertices: `cur` may be refilled
             vox_small_body<OWNER, ENUM>(J, active, tri, 0u, v);
         }
-        cp_async_wait<0>();
         return;
     }
     if (SUBSET == 1) {

@@ -495,7 +495,7 @@ def bench(args, rank, world, local, dist, peak, peak_src, ClockSampler):
                                {"remote": "remote staging over NVLink inside the voxelizer", "dispatch": "triangle dispatch over NVLink",
                                 "replicated": "NCCL all-gather over NVLink"}[mode])},
             "gpu_launches": int(launches) * args.steps, "clocks": clocks,
-            "stage_ms_rank0": {k: st[k] for k in ("ms_dispatch", "ms_partition", "ms_voxelize", "ms_vox_small", "ms_compact", "ms_build", "ms_emit", "ms_emit_leaf", "ms_clear")},
+            "stage_ms_rank0": {k: st[k] for k in ("ms_dispatch", "ms_peer_wait", "ms_partition", "ms_voxelize", "ms_vox_small", "ms_compact", "ms_build", "ms_emit", "ms_emit_leaf", "ms_clear")},
             "pairs_rank0": {k: st[k] for k in ("n_pairs", "n_small", "n_medium", "n_large")},
         }
         print(json.dumps(line), flush=True)
