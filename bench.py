@@ -252,7 +252,7 @@ def ours(args):
     # ---- roofline of the dominant kernel (CUDA events inside the library, on its launch stream) ----
     n_leafrec = None
     kern = {
-        "k_vox_small": {"ms": avg("ms_vox_small"), "bytes": T * 36 + 8 * 0},
+        "k_vox_warp": {"ms": avg("ms_vox_small"), "bytes": T * 36 + 8 * 0},
         "k_emit_leaf": {"ms": avg("ms_emit_leaf"), "bytes": 8 * nv + 24 * nn},
     }
     dom = max(kern, key=lambda k: kern[k]["ms"])
@@ -261,7 +261,7 @@ def ours(args):
         note = "octree build: 8*N voxels read + 24*N_nodes written (SURVEY.md §8d), divided by k_emit_leaf time"
     else:
         alg_bytes = T * 36 + (GRID ** 3) // 8 * 0 + 8 * nv
-        note = ("voxelizer: T*36 B triangle records read + 8 B per occupied voxel of bit-grid traffic, divided by k_vox_small time. "
+        note = ("voxelizer: T*36 B triangle records read + 8 B per occupied voxel of bit-grid traffic, divided by k_vox_warp time. "
                 "The kernel is instruction-bound, not HBM-bound (ncu: 120 M warp instructions, 29.9 of 32 threads active, 66 % issue "
                 "slots busy, DRAM 5 %): see profiles/README.md; the HBM-bound kernel of the path is k_emit_leaf (octree_build below)")
     achieved = alg_bytes / (kern[dom]["ms"] * 1e-3) / 1e9 if kern[dom]["ms"] > 0 else 0.0

@@ -93,6 +93,7 @@ struct svo_ctx {
     // work queues
     DevBuf queue[2], qcount, subset;
     bool use_subset = false;
+    bool warp_kernel = true;           // SVO_VOX_KERNEL=block selects the block-granular small-box voxelizer
 
     // compact levels
     LevelBufs lv[MAX_LEVELS];
@@ -145,7 +146,7 @@ struct svo_ctx {
     float* peer_slice[MAX_WORLD];
     uint32_t* peer_list[MAX_WORLD];
     SliceCtrl* peer_slctrl[MAX_WORLD];
-    bool sl_attached = false, sliced = false;
+    bool sl_attached = false, sliced = false, filter_attr_set = false;
     ull sl_epoch = 0;
     SliceJob sj;
 
@@ -308,7 +309,7 @@ VoxJob make_voxjob(svo_ctx* c) {
         const SliceCtrl* own = (const SliceCtrl*)c->sl_ctrl.p;
         J.segs.nslice = own->nslice;
         J.subset = c->sl_list.as<uint32_t>();
-        J.pull_cap = c->sl_cap_blocks;
+        J.pull_cap = c->sl_cap_blocks * 4;
         J.pull_counts = &own->count[0][c->rank];
     }
     return J;
@@ -329,9 +330,9 @@ int launch_voxelizer(svo_ctx* c) {
             mark(c, EV_VS0);                 // ms_vox_small excludes the wait for the peers' lists
         }
         const unsigned g2 = (unsigned)c->sm_count * SVO_VOX_MINBLOCKS;
-        const size_t smem2 = 2 * (size_t)VOX_BLOCK * c->fpt * sizeof(float);      // double-buffered staging
-        if (J.P > 1) { k_vox_small<OWNER, true, 2><<<g2, VOX_BLOCK, smem2, c->stream>>>(J); LAUNCHED(); }
-        else { k_vox_small<OWNER, false, 2><<<g2, VOX_BLOCK, smem2, c->stream>>>(J); LAUNCHED(); }
+        const size_t smem2 = 2 * (size_t)VOX_BLOCK * c->fpt * sizeof(float);      // per warp: two 32-triangle buffers
+        if (J.P > 1) { k_vox_warp<OWNER, true, 2><<<g2, VOX_BLOCK, smem2, c->stream>>>(J); LAUNCHED(); }
+        else { k_vox_warp<OWNER, false, 2><<<g2, VOX_BLOCK, smem2, c->stream>>>(J); LAUNCHED(); }
     } else if (c->use_subset) {
         // sharded: compact the triangles that touch this rank's slab once (the owner pass reuses the list)
         if (!OWNER) {
@@ -353,6 +354,13 @@ int launch_voxelizer(svo_ctx* c) {
         const size_t smem2 = (size_t)VOX_BLOCK * c->fpt * sizeof(float);
         if (J.P > 1) { k_vox_small<OWNER, true, 1><<<g2, VOX_BLOCK, smem2, c->stream>>>(J); LAUNCHED(); }
         else { k_vox_small<OWNER, false, 1><<<g2, VOX_BLOCK, smem2, c->stream>>>(J); LAUNCHED(); }
+    } else if (J.pair_tri == nullptr && c->warp_kernel) {
+        // one GPU (or a compact private copy): warp-persistent kernel over all 32-triangle units
+        const ull units = (c->q_end - c->q_begin + UNIT - 1) / UNIT;
+        const unsigned g2 = (unsigned)std::min<ull>((units + VOX_BLOCK / 32 - 1) / (VOX_BLOCK / 32), (ull)c->sm_count * SVO_VOX_MINBLOCKS);
+        const size_t smem2 = 2 * (size_t)VOX_BLOCK * c->fpt * sizeof(float);
+        if (J.P > 1) { k_vox_warp<OWNER, true, 0><<<g2, VOX_BLOCK, smem2, c->stream>>>(J); LAUNCHED(); }
+        else { k_vox_warp<OWNER, false, 0><<<g2, VOX_BLOCK, smem2, c->stream>>>(J); LAUNCHED(); }
     } else if (J.pair_tri == nullptr && J.P > 1) { k_vox_small<OWNER, true, 0><<<blocks_for(c->q_end - c->q_begin, VOX_BLOCK), VOX_BLOCK, smem, c->stream>>>(J); LAUNCHED(); }
     else { k_vox_small<OWNER, false, 0><<<blocks_for(c->q_end - c->q_begin, VOX_BLOCK), VOX_BLOCK, smem, c->stream>>>(J); LAUNCHED(); }
     if (!OWNER) mark(c, EV_VS1);
@@ -723,6 +731,7 @@ int svo_voxelize(svo_ctx* c) {
     CK(c->qcount.ensure(8 * sizeof(ull)));
     CK(cudaMemsetAsync(c->qcount.p, 0, 8 * sizeof(ull), c->stream));
     c->use_subset = c->world > 1 && !c->dispatched && !c->sliced && !(c->P > 1 && c->use_lists);
+    { const char* e = getenv("SVO_VOX_KERNEL"); c->warp_kernel = !(e && strcmp(e, "block") == 0); }
     if (c->use_subset) CK(c->subset.ensure((size_t)(c->n_tris / VOX_BLOCK + 2) * sizeof(uint32_t)));
     // queue capacity: exact with lists; with inline enumeration a triangle may appear once per partition it
     // touches, so leave headroom and detect overflow (qcount[3]) instead of trusting a bound
@@ -1411,6 +1420,7 @@ int svo_shard_dispatch_count(svo_ctx* c, const svo_params* params, const float* 
         for (int a = 0; a < 3; a++) {
             D.lo[r][a] = c->P > 1 ? lo[a] / (int)c->side : lo[a];
             D.hi[r][a] = c->P > 1 ? hi[a] / (int)c->side : hi[a];
+            if (c->P > 1) { D.lof[r][a] = c->slab_min[D.lo[r][a]]; D.hif[r][a] = c->slab_max[D.hi[r][a]]; }
         }
         D.inbox[r] = c->peer_inbox[r];
         D.ctrl[r] = c->peer_ctrl[r];
@@ -1497,7 +1507,7 @@ static WindowLayout window_layout(uint64_t cap_blocks, int fpt, int world) {
     L.ctrl = 0;
     L.xtable = up(sizeof(SliceCtrl));
     L.list = L.xtable + XTABLE_BYTES;
-    L.slice = L.list + up((size_t)world * cap_blocks * sizeof(uint32_t));
+    L.slice = L.list + up((size_t)world * cap_blocks * 4 * sizeof(uint32_t));      // one entry per 32-triangle unit
     L.total = L.slice + up((size_t)cap_blocks * VOX_BLOCK * fpt * sizeof(float));
     return L;
 }
@@ -1507,6 +1517,7 @@ int svo_shard_slice_create(svo_ctx* c, uint64_t capacity_tris, int fpt, void** d
     if (fpt != 9 && fpt != 21) return fail(c, SVO_E_INVALID, "floats_per_tri must be 9 (binary) or 21 (payload)");
     if (c->world > MAX_WORLD) return fail(c, SVO_E_INVALID, "remote triangle slices support at most 16 ranks");
     if (capacity_tris * (uint64_t)c->world > 0xffffffffULL) return fail(c, SVO_E_INVALID, "more than 2^32-1 triangles");
+    if (capacity_tris >= (1ULL << 28) * VOX_BLOCK) return fail(c, SVO_E_INVALID, "slice capacity above 2^35 triangles");
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->stream));
     c->sl_attached = false; c->sliced = false;
@@ -1599,6 +1610,7 @@ int svo_shard_slice_publish(svo_ctx* c, const svo_params* params, uint64_t n_tot
         for (int a = 0; a < 3; a++) {
             D.lo[r][a] = c->P > 1 ? lo[a] / (int)c->side : lo[a];
             D.hi[r][a] = c->P > 1 ? hi[a] / (int)c->side : hi[a];
+            if (c->P > 1) { D.lof[r][a] = c->slab_min[D.lo[r][a]]; D.hif[r][a] = c->slab_max[D.hi[r][a]]; }
         }
         S.list[r] = c->peer_list[r];
         S.ctrl[r] = c->peer_slctrl[r];
@@ -1606,9 +1618,14 @@ int svo_shard_slice_publish(svo_ctx* c, const svo_params* params, uint64_t n_tot
     D.unit_div = c->unit_div; D.gmax = (int)c->prm.gridsize - 1;
     D.nb = (D.n_local + VOX_BLOCK - 1) / VOX_BLOCK;
     D.epoch = ++c->sl_epoch;
-    S.cap = c->sl_cap_blocks;
+    S.cap = c->sl_cap_blocks * 4;
     S.cursor = c->sl_cursor.as<ull>();
-    if (D.nb) { k_slice_filter<<<(unsigned)D.nb, VOX_BLOCK, 0, c->stream>>>(S); LAUNCHED(); }
+    if (D.nb) {
+        const size_t smem = (size_t)FILTER_WARPS * VOX_BLOCK * c->slice_fpt * sizeof(float);      // 36 / 84 KB
+        if (!c->filter_attr_set) { CK(cudaFuncSetAttribute(k_slice_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, FILTER_WARPS * VOX_BLOCK * 21 * (int)sizeof(float))); c->filter_attr_set = true; }
+        const unsigned grid = (unsigned)std::min<ull>((D.nb + FILTER_WARPS - 1) / FILTER_WARPS, (ull)c->sm_count * 4);
+        k_slice_filter<<<grid, FILTER_WARPS * 32, smem, c->stream>>>(S); LAUNCHED();
+    }
     k_slice_post<<<1, MAX_WORLD, 0, c->stream>>>(S, 0); LAUNCHED();
     mark(c, EV_DSP1);
     c->dispatch_launches = c->launches - launches_before;

@@ -37,6 +37,7 @@ struct DispatchJob {
     int use_partitions, k;
     float bmin[32], bmax[32];
     int lo[MAX_WORLD][3], hi[MAX_WORLD][3];     // destination boxes: partition coordinates (use_partitions) or voxels
+    float lof[MAX_WORLD][3], hif[MAX_WORLD][3]; // use_partitions: bmin[lo], bmax[hi] -- the two world-space bounds the test needs
     float unit_div; int gmax;
     unsigned int* blockcnt;                     // [world][nb]
     const unsigned long long* blockoff;         // exclusive scan of blockcnt, [world * nb + 1]
@@ -53,8 +54,10 @@ __device__ __forceinline__ unsigned dispatch_mask(const DispatchJob& D, const fl
     for (int a = 0; a < 3; a++) {
         const float mn = stdmin(c[a], stdmin(c[3 + a], c[6 + a])), mx = stdmax(c[a], stdmax(c[3 + a], c[6 + a]));
         if (D.use_partitions) {
+            // the kept slab range [L, H] of the interval meets the destination's slabs [lo, hi] iff H >= lo and L <= hi; by
+            // monotonicity of the slab tables that is !(mx < bmin[lo]) and !(mn > bmax[hi]) (intersection.h:50-53 per axis)
             for (int d = 0; d < D.world; d++)
-                if ((mx < D.bmin[D.lo[d][a]]) || (mn > D.bmax[D.hi[d][a]])) m &= ~(1u << d);
+                if ((mx < D.lof[d][a]) || (mn > D.hif[d][a])) m &= ~(1u << d);
         } else {
             const int l = clampi(f2i(fmul(mn, D.unit_div)), 0, D.gmax), h = clampi(f2i(fmul(mx, D.unit_div)), 0, D.gmax);
             for (int d = 0; d < D.world; d++)
@@ -183,30 +186,54 @@ struct SliceJob {
     DispatchJob D;                              // geometry + local slice (tris, fpt, n_local, nb); inbox / blockcnt unused
     uint32_t* list[MAX_WORLD];                  // peer list buffers: region [src * cap, (src + 1) * cap) belongs to source src
     SliceCtrl* ctrl[MAX_WORLD];
-    unsigned long long cap;                     // blocks per region
+    unsigned long long cap;                     // list entries (32-triangle units) per region
     unsigned long long* cursor;                 // local, MAX_WORLD counters (zeroed by k_slice_post)
 };
 
-__global__ void __launch_bounds__(VOX_BLOCK) k_slice_filter(SliceJob S) {
-    __shared__ unsigned s_any;
-    if (threadIdx.x == 0) s_any = 0;
-    __syncthreads();
-    const unsigned long long t = (unsigned long long)blockIdx.x * VOX_BLOCK + threadIdx.x;
-    unsigned m = 0;
-    if (t < S.D.n_local) {
-        const float* v = S.D.tris + t * S.D.fpt;
-        float c[9];
+constexpr int FILTER_WARPS = 8;
+// One WARP per staging block (4 x 32 triangles): the block's 4608 / 10752 bytes are read with coalesced float4 loads
+// into the warp's shared-memory tile, each lane then tests 4 triangles. Every warp owns a contiguous run of staging
+// blocks and reserves list space once per 64 of them (lane d keeps the hit mask of destination d), so the list
+// cursors see ~1/20 of the atomics a per-block append would issue (those were the bottleneck: same-address atomics).
+__global__ void __launch_bounds__(FILTER_WARPS * 32) k_slice_filter(SliceJob S) {
+    extern __shared__ float4 s_f4[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t fpt = S.D.fpt;
+    float4* tile4 = s_f4 + (size_t)wid * (VOX_BLOCK * fpt / 4);
+    const float* tile = reinterpret_cast<const float*>(tile4);
+    const unsigned long long nwarps = (unsigned long long)gridDim.x * FILTER_WARPS;
+    const unsigned long long per = (S.D.nb + nwarps - 1) / nwarps;
+    const unsigned long long gw = (unsigned long long)blockIdx.x * FILTER_WARPS + wid;
+    const unsigned long long b1 = min(S.D.nb, (gw + 1) * per);
+    const unsigned n4 = VOX_BLOCK * fpt / 4;
+    static_assert(VOX_BLOCK == 128 && UNIT == 32, "a staging block is four 32-triangle units");
+    for (unsigned long long base = gw * per; base < b1; base += 16) {
+        unsigned long long hits = 0;                            // lane d: nibble j = warps of block base + j that touch destination d
+        const int nj = (int)min(16ULL, b1 - base);
+        for (int j = 0; j < nj; j++) {
+            const unsigned long long q0 = (base + j) * VOX_BLOCK;
+            const unsigned nrec = (unsigned)(S.D.n_local - q0 < VOX_BLOCK ? S.D.n_local - q0 : VOX_BLOCK);
+            const float4* src4 = reinterpret_cast<const float4*>(S.D.tris + q0 * fpt);   // the slice buffer is padded to whole blocks
+            for (unsigned i = lane; i < n4; i += 32) tile4[i] = __ldg(src4 + i);
+            __syncwarp();
 #pragma unroll
-        for (int i = 0; i < 9; i++) c[i] = __ldg(v + i);
-        m = dispatch_mask(S.D, c);
-    }
-    m = __reduce_or_sync(0xffffffffu, m);
-    if ((threadIdx.x & 31) == 0 && m) atomicOr(&s_any, m);
-    __syncthreads();
-    const int d = threadIdx.x;
-    if (d < S.D.world && ((s_any >> d) & 1u)) {
-        const unsigned long long pos = atomicAdd(&S.cursor[d], 1ULL);
-        S.list[d][(unsigned long long)S.D.me * S.cap + pos] = blockIdx.x;      // pos < nb <= cap
+            for (int k = 0; k < 4; k++) {                       // triangles 32k .. 32k + 31 are the voxelizer's warp k
+                const unsigned t = lane + 32u * k;
+                unsigned m = t < nrec ? dispatch_mask(S.D, tile + (size_t)t * fpt) : 0u;
+                m = __reduce_or_sync(0xffffffffu, m);
+                if ((m >> lane) & 1u) hits |= 1ULL << (4 * j + k);
+            }
+            __syncwarp();
+        }
+        if (lane < S.D.world && hits) {
+            unsigned long long pos = atomicAdd(&S.cursor[lane], (unsigned long long)__popcll(hits));
+            uint32_t* out = S.list[lane] + (unsigned long long)S.D.me * S.cap;
+            for (int j = 0; j < 16; j++) {
+                const uint32_t w = (uint32_t)((hits >> (4 * j)) & 15ULL);
+                for (uint32_t k = 0; k < 4; k++)
+                    if ((w >> k) & 1u) out[pos++] = (uint32_t)((base + j) * 4 + k);      // 32-triangle unit index; pos < 4 * nb <= cap
+            }
+        }
     }
 }
 

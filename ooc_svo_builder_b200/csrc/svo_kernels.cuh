@@ -338,63 +338,12 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
                  :: "r"(b), "r"(parity) : "memory");
 }
 
-// SUBSET: 0 = every triangle of [q_begin, q_end), 1 = the staging blocks listed by k_owner_filter (sharded, replicated
-// mesh), 2 = the staging blocks the source ranks listed for this rank, staged from their HBM (sharded, remote staging)
+// SUBSET: 0 = every triangle of [q_begin, q_end), 1 = the staging blocks listed by k_owner_filter (sharded, replicated mesh)
 template <bool OWNER, bool ENUM, int SUBSET>
 __global__ void __launch_bounds__(VOX_BLOCK, SVO_VOX_MINBLOCKS) k_vox_small(VoxJob J) {
     extern __shared__ float4 s_stage4[];
     float* s_stage = reinterpret_cast<float*>(s_stage4);
     float v[9];
-    if (SUBSET == 2) {
-        // sharded, remote staging: persistent blocks walk the block lists the source ranks published for this rank and
-        // stage each block from its owner's HBM (NVLink loads); the loads of one block overlap the math of the others
-        __shared__ unsigned long long s_base[MAX_WORLD + 1], s_pref[MAX_WORLD + 1];
-        segs_bases(J.segs, s_base);
-        if (threadIdx.x == 0) {
-            unsigned long long acc = 0;
-            for (int s = 0; s < J.segs.n; s++) { s_pref[s] = acc; acc += J.pull_counts[(size_t)s * MAX_WORLD]; }
-            s_pref[J.segs.n] = acc;
-        }
-        __syncthreads();
-        const unsigned long long count = s_pref[J.segs.n];
-        // double-buffered: while block `li` is voxelized, block `li + gridDim.x` streams into the other buffer.
-        // A whole staging block is copied every time (slices are padded to whole blocks), so the size is a multiple of 16.
-        __shared__ __align__(8) unsigned long long s_bar[2];
-        const uint32_t buf_floats = VOX_BLOCK * J.fpt;
-        if (threadIdx.x == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); mbar_fence_init(); }
-        __syncthreads();
-        int src = 0;
-        uint64_t q0 = 0, nseg = 0;
-        auto locate = [&](unsigned long long li) {
-            while (li >= s_pref[src + 1]) src++;
-            q0 = (uint64_t)J.subset[(size_t)src * J.pull_cap + (li - s_pref[src])] * VOX_BLOCK;
-            nseg = s_base[src + 1] - s_base[src];
-        };
-        unsigned long long li = blockIdx.x;
-        if (li < count) {
-            locate(li);
-            if (threadIdx.x == 0) bulk_load(s_stage, J.segs.ptr[src] + q0 * J.fpt, buf_floats * 4u, &s_bar[0]);
-        }
-        for (int it = 0; li < count; li += gridDim.x, it++) {
-            const float* cur = s_stage + (it & 1) * buf_floats;
-            const uint64_t my_q0 = q0, my_nseg = nseg;
-            const uint32_t tri = (uint32_t)(s_base[src] + q0 + threadIdx.x);
-            if (li + gridDim.x < count) {
-                locate(li + gridDim.x);
-                // buffer (it + 1) & 1 was last read in iteration it - 1, before that iteration's __syncthreads
-                if (threadIdx.x == 0) bulk_load(s_stage + ((it + 1) & 1) * buf_floats, J.segs.ptr[src] + q0 * J.fpt, buf_floats * 4u, &s_bar[(it + 1) & 1]);
-            }
-            mbar_wait(&s_bar[it & 1], (unsigned)(it >> 1) & 1u);
-            const bool active = my_q0 + threadIdx.x < my_nseg;
-            if (active) {
-#pragma unroll
-                for (int i = 0; i < 9; i++) v[i] = cur[threadIdx.x * J.fpt + i];
-            }
-            __syncthreads();                                   // everyone has its vertices: `cur` may be refilled
-            vox_small_body<OWNER, ENUM>(J, active, tri, 0u, v);
-        }
-        return;
-    }
     if (SUBSET == 1) {
         // sharded: persistent blocks walk the list of staging blocks that touch this rank's slab (k_owner_filter)
         const unsigned long long count = *J.subset_count;
@@ -429,6 +378,99 @@ __global__ void __launch_bounds__(VOX_BLOCK, SVO_VOX_MINBLOCKS) k_vox_small(VoxJ
         load_vertices(J, nullptr, tri, v);
     }
     vox_small_body<OWNER, ENUM>(J, active, tri, part, v);
+}
+
+// ---------------------------------------------------------------------------
+// Warp-persistent small-box voxelizer. The unit of work is 32 consecutive triangles (one per lane). Every WARP runs its
+// own loop: take a ticket (atomic counter, fetched two units ahead), bulk-copy the unit's records into its private
+// double buffer (cp.async.bulk + its own mbarrier), voxelize the previous unit meanwhile. No block-wide barrier in the
+// loop: a warp with expensive triangles does not hold up the other three (with block-granular staging every iteration
+// cost the maximum over the four warps), tickets balance the load across the whole grid, and units that lie in
+// another rank's slab are simply never listed.
+//   MODE 0: units are the consecutive 32-triangle runs of J.tris (one GPU, or a compact private copy)
+//   MODE 2: units listed by the source ranks for this rank (k_slice_filter), staged from the owner's HBM over NVLink
+// ---------------------------------------------------------------------------
+constexpr int UNIT = 32;
+template <bool OWNER, bool ENUM, int MODE>
+__global__ void __launch_bounds__(VOX_BLOCK, SVO_VOX_MINBLOCKS) k_vox_warp(VoxJob J) {
+    extern __shared__ float4 s_stage4[];
+    __shared__ __align__(8) unsigned long long s_bar[VOX_BLOCK / 32][2];
+    __shared__ unsigned long long s_base[MAX_WORLD + 1], s_pref[MAX_WORLD + 1];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t unit_floats = UNIT * J.fpt;
+    float* wbuf = reinterpret_cast<float*>(s_stage4) + (size_t)wid * 2 * unit_floats;
+    unsigned long long count;
+    if (MODE == 2) {
+        segs_bases(J.segs, s_base);
+        if (threadIdx.x == 0) {
+            unsigned long long acc = 0;
+            for (int s = 0; s < J.segs.n; s++) { s_pref[s] = acc; acc += J.pull_counts[(size_t)s * MAX_WORLD]; }
+            s_pref[J.segs.n] = acc;
+        }
+        __syncthreads();
+        count = s_pref[J.segs.n];
+    } else {
+        count = (J.q_end - J.q_begin + UNIT - 1) / UNIT;
+    }
+    if (lane == 0) { mbar_init(&s_bar[wid][0], 1); mbar_init(&s_bar[wid][1], 1); mbar_fence_init(); }
+    __syncwarp();
+    unsigned long long* ticket = J.qcount + (OWNER ? 6 : 5);
+    auto take = [&]() -> unsigned long long {               // lane 0 holds the value until it is broadcast
+        return lane == 0 ? atomicAdd(ticket, 1ULL) : 0ULL;
+    };
+    // state of the unit that was located last
+    int src = 0;
+    const float* uptr = nullptr;                            // first record of the unit
+    uint64_t ufirst = 0;                                    // global index of its first triangle
+    uint32_t uvalid = 0;                                    // triangles in it (<= 32)
+    auto locate = [&](unsigned long long u) {
+        if (MODE == 2) {
+            while (u >= s_pref[src + 1]) src++;             // a warp's tickets only grow: src moves forward
+            const uint64_t q0 = (uint64_t)J.subset[(size_t)src * J.pull_cap + (u - s_pref[src])] * UNIT;
+            const uint64_t nseg = s_base[src + 1] - s_base[src];
+            uptr = J.segs.ptr[src] + q0 * J.fpt;
+            ufirst = s_base[src] + q0;
+            uvalid = (uint32_t)(nseg - q0 < UNIT ? nseg - q0 : UNIT);
+        } else {
+            const uint64_t q0 = J.q_begin + u * UNIT;
+            uptr = J.tris + q0 * J.fpt;
+            ufirst = q0;
+            uvalid = (uint32_t)(J.q_end - q0 < UNIT ? J.q_end - q0 : UNIT);
+        }
+    };
+    // A full unit is staged by the bulk-copy engine; the (single) ragged last unit of an array is read directly, so that
+    // nothing is ever read past the end of a caller's buffer. Slices are padded, but the rule is the same for both modes.
+    auto stage = [&](int b) {
+        if (uvalid == UNIT && lane == 0) bulk_load(wbuf + (size_t)b * unit_floats, uptr, unit_floats * 4u, &s_bar[wid][b]);
+    };
+    unsigned long long cur = __shfl_sync(0xffffffffu, take(), 0);
+    unsigned long long next = __shfl_sync(0xffffffffu, take(), 0);
+    uint32_t phase = 0;
+    if (cur < count) { locate(cur); stage(0); }
+    float v[9];
+    for (int it = 0; cur < count; it++) {
+        const int b = it & 1;
+        const float* my_ptr = uptr;
+        const uint32_t my_valid = uvalid;
+        const uint32_t tri = (uint32_t)(ufirst + lane);
+        const unsigned long long ahead = take();            // ticket of iteration it + 2; consumed after the body
+        if (next < count) { locate(next); stage(b ^ 1); }   // buffer b^1 was last read in iteration it - 1 (before its __syncwarp)
+        const bool active = (uint32_t)lane < my_valid;
+        if (my_valid == UNIT) {
+            mbar_wait(&s_bar[wid][b], (phase >> b) & 1u);
+            phase ^= 1u << b;
+            const float* cbuf = wbuf + (size_t)b * unit_floats;
+#pragma unroll
+            for (int i = 0; i < 9; i++) v[i] = cbuf[lane * J.fpt + i];
+        } else if (active) {
+#pragma unroll
+            for (int i = 0; i < 9; i++) v[i] = __ldg(my_ptr + (size_t)lane * J.fpt + i);
+        }
+        __syncwarp();                                       // every lane has its vertices: the buffer may be refilled
+        vox_small_body<OWNER, ENUM>(J, active, tri, 0u, v);
+        cur = next;
+        next = __shfl_sync(0xffffffffu, ahead, 0);
+    }
 }
 
 // ---------------------------------------------------------------------------
