@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <string>
 #include <vector>
 
@@ -97,7 +98,8 @@ struct svo_ctx {
 
     // compact levels
     LevelBufs lv[MAX_LEVELS];
-    DevBuf scan_tmp;
+    DevBuf scan_tmp, lb_state, lb_ticket;
+    ull lb_epoch = 0, lb_tickets = 0;
 
     // outputs
     DevBuf nodes, data, owner, tileidx, codes;
@@ -177,6 +179,14 @@ int fail(svo_ctx* c, int code, const std::string& msg) {
         CK(cudaGetLastError());                                                                    \
     } while (0)
 
+// SVO_TIMELINE=1: host wall-clock stamps (us since the stamp named "partition") printed at the end of every build
+struct Timeline {
+    bool on = false; int n = 0; const char* name[32]; double t[32];
+    static double now() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3; }
+    void stamp(const char* w) { if (on && n < 32) { name[n] = w; t[n++] = now(); } }
+    void dump() { if (!on) return; for (int i = 0; i < n; i++) fprintf(stderr, "%s %.1f%s", name[i], t[i] - t[0], i + 1 < n ? " | " : "\n"); n = 0; }
+} g_tl;
+
 inline unsigned blocks_for(ull n, unsigned per) { return (unsigned)((n + per - 1) / per); }
 
 void mark(svo_ctx* c, int e) {
@@ -190,39 +200,60 @@ float span(svo_ctx* c, int a, int b) {
     return 0.f;
 }
 
+// state of the single-pass scans: persistent, epoch-tagged (no clearing between launches)
+int lookback_prepare(svo_ctx* c, ull nt, int nv) {
+    const size_t need = (size_t)(nt + 1) * nv * sizeof(ull);
+    if (need > c->lb_state.cap) {
+        CK(c->lb_state.ensure(need));
+        CK(cudaMemsetAsync(c->lb_state.p, 0, c->lb_state.cap, c->stream));
+        c->lb_epoch = 0;
+    }
+    if (!c->lb_ticket.p) {
+        CK(c->lb_ticket.ensure(sizeof(ull)));
+        CK(cudaMemsetAsync(c->lb_ticket.p, 0, sizeof(ull), c->stream));
+        c->lb_tickets = 0;
+    }
+    if (++c->lb_epoch >= 0xffff) {           // 16-bit epoch: start over with a clean state array
+        CK(cudaMemsetAsync(c->lb_state.p, 0, c->lb_state.cap, c->stream));
+        c->lb_epoch = 1;
+    }
+    return SVO_OK;
+}
+
+constexpr ull SCAN_ONE_BLOCK_MAX = 4096;     // up to here one block is faster than the look-back chain
+
 template <class F>
 int exscan(svo_ctx* c, F f, ull n, ull* out) {
     if (n == 0) {
         CK(cudaMemsetAsync(out, 0, sizeof(ull), c->stream));
         return SVO_OK;
     }
-    if (n <= SCAN_SMALL_MAX) {
+    if (n <= SCAN_ONE_BLOCK_MAX) {
         k_scan_small<<<1, 1024, 0, c->stream>>>(f, n, out); LAUNCHED();
         return SVO_OK;
     }
-    const ull nt = (n + SCAN_TILE - 1) / SCAN_TILE;
-    CK(c->scan_tmp.ensure((nt + 1) * sizeof(ull)));
-    ull* tmp = c->scan_tmp.as<ull>();
-    k_scan_reduce<<<(unsigned)nt, SCAN_THREADS, 0, c->stream>>>(f, n, tmp); LAUNCHED();
-    k_scan_tiles<<<1, 1024, 0, c->stream>>>(tmp, nt); LAUNCHED();
-    k_scan_final<<<(unsigned)nt, SCAN_THREADS, 0, c->stream>>>(f, n, tmp, out); LAUNCHED();
+    const ull nt = (n + LB_TILE - 1) / LB_TILE;
+    int rc = lookback_prepare(c, nt, 1);
+    if (rc) return rc;
+    OneValue<F> g{ f };
+    k_scan_lookback<1><<<(unsigned)nt, LB_THREADS, 0, c->stream>>>(g, n, out, (ull*)nullptr, c->lb_state.as<ull>(), c->lb_ticket.as<ull>(), c->lb_tickets, c->lb_epoch); LAUNCHED();
+    c->lb_tickets += nt;
     return SVO_OK;
 }
 
-// child prefix (fc) and subtree-size prefix (ps) of the brick level in one reduce / scan / rescan
+// child prefix (fc) and subtree-size prefix (ps) of the brick level in one single-pass scan
 int exscan_level0(svo_ctx* c, const ull* mask, ull n, ull* fc, ull* ps) {
     if (n == 0) {
         CK(cudaMemsetAsync(fc, 0, sizeof(ull), c->stream));
         CK(cudaMemsetAsync(ps, 0, sizeof(ull), c->stream));
         return SVO_OK;
     }
-    const ull nt = (n + SCAN_TILE - 1) / SCAN_TILE;
-    CK(c->scan_tmp.ensure(2 * (nt + 1) * sizeof(ull)));
-    ull* ta = c->scan_tmp.as<ull>();
-    ull* tb = ta + (nt + 1);
-    k_scan2_reduce<<<(unsigned)nt, SCAN_THREADS, 0, c->stream>>>(mask, n, ta, tb); LAUNCHED();
-    k_scan2_tiles<<<1, 1024, 0, c->stream>>>(ta, tb, nt); LAUNCHED();
-    k_scan2_final<<<(unsigned)nt, SCAN_THREADS, 0, c->stream>>>(mask, n, ta, tb, fc, ps); LAUNCHED();
+    const ull nt = (n + LB_TILE - 1) / LB_TILE;
+    int rc = lookback_prepare(c, nt, 2);
+    if (rc) return rc;
+    BrickPrefixes g{ mask };
+    k_scan_lookback<2><<<(unsigned)nt, LB_THREADS, 0, c->stream>>>(g, n, fc, ps, c->lb_state.as<ull>(), c->lb_ticket.as<ull>(), c->lb_tickets, c->lb_epoch); LAUNCHED();
+    c->lb_tickets += nt;
     return SVO_OK;
 }
 
@@ -450,6 +481,7 @@ void svo_ctx_destroy(svo_ctx* c) {
     c->window.release(); c->sl_cursor.release();
     c->inbox.release(); c->ctrl_buf.release(); c->blockcnt.release(); c->blockoff.release();
     if (c->h_ctrl) cudaFreeHost(c->h_ctrl);
+    c->lb_state.release(); c->lb_ticket.release();
     c->scan_tmp.release(); c->nodes.release(); c->data.release(); c->owner.release(); c->tileidx.release(); c->codes.release();
     for (int i = 0; i < EV_COUNT; i++) cudaEventDestroy(c->ev[i]);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
@@ -573,6 +605,7 @@ int svo_partition(svo_ctx* c, const svo_params* params, uint64_t* n_partitions, 
     CK(cudaSetDevice(c->device));
     c->voxelized = c->built = false;
     c->launches = 0;
+    g_tl.on = getenv("SVO_TIMELINE") != nullptr; g_tl.n = 0; g_tl.stamp("partition");
     rc = derive_grid(c, params);
     if (rc) return rc;
     c->h_part_counts.assign(c->P, 0);
@@ -742,9 +775,11 @@ int svo_voxelize(svo_ctx* c) {
     CK(c->queue[1].ensure(qbytes));
     mark(c, EV_VOX0);
     c->dense_clean = false;
+    g_tl.stamp("vox_launch");
     rc = launch_voxelizer<false>(c);
     if (rc) return rc;
     mark(c, EV_VOX1);
+    g_tl.stamp("vox_launched");
     c->voxelized = true;
     c->built = false;
     return SVO_OK;
@@ -798,7 +833,9 @@ static int build_phase_a(svo_ctx* c, ull* table) {
         k_level_counts<<<grid, 256, 0, c->stream>>>((ull* const*)c->d_lvlptrs.p, c->d_nwords.as<ull>(), J, c->d_counts.as<ull>()); LAUNCHED();
     }
     CK(cudaMemcpyAsync(c->h_pinned, c->d_counts.p, MAX_LEVELS * sizeof(ull), cudaMemcpyDeviceToHost, c->stream));
+    g_tl.stamp("sync1_wait");
     CK(cudaStreamSynchronize(c->stream));
+    g_tl.stamp("sync1_done");
     for (int j = 0; j <= J; j++) {
         int rc = alloc_level(c, c->lv[j], c->h_pinned[j], want_pl, levels);
         if (rc) return rc;
@@ -873,6 +910,7 @@ static int build_phase_a(svo_ctx* c, ull* table) {
         }
     }
     mark(c, EV_CMP1);
+    g_tl.stamp("phaseA_launched");
     c->phase_a_done = true;
     return SVO_OK;
 }
@@ -1054,7 +1092,9 @@ static int build_phase_b(svo_ctx* c, const ull* table) {
     CK(cudaMemcpyAsync(c->h_pinned + 33, topL.ps.as<ull>() + topL.n, sizeof(ull), cudaMemcpyDeviceToHost, c->stream));
     if (levels) CK(cudaMemcpyAsync(c->h_pinned + 34, topL.pi.as<ull>() + topL.n, sizeof(ull), cudaMemcpyDeviceToHost, c->stream));
     if (want_pl) CK(cudaMemcpyAsync(c->h_pinned + 35, topL.pl.as<ull>() + topL.n, sizeof(ull), cudaMemcpyDeviceToHost, c->stream));
+    g_tl.stamp("sync2_wait");
     CK(cudaStreamSynchronize(c->stream));
+    g_tl.stamp("sync2_done");
     c->n_voxels_local = c->h_pinned[32];
     c->n_voxels = c->n_voxels_local;
     const ull s_top = c->h_pinned[33];
@@ -1213,7 +1253,10 @@ static int build_phase_b(svo_ctx* c, const ull* table) {
     }
     // queue statistics
     CK(cudaMemcpyAsync(c->h_pinned + 40, c->qcount.p, 4 * sizeof(ull), cudaMemcpyDeviceToHost, c->stream));
+    g_tl.stamp("sync3_wait");
     CK(cudaStreamSynchronize(c->stream));
+    g_tl.stamp("sync3_done");
+    g_tl.dump();
     c->phase_a_done = false;
     if (c->h_pinned[48]) {
         CK(cudaMemsetAsync(&((SliceCtrl*)c->sl_ctrl.p)->error, 0, sizeof(ull), c->stream));

@@ -834,6 +834,102 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan2_final(const unsigned lon
     if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) { out_a[n] = sums_a[gridDim.x]; out_b[n] = sums_b[gridDim.x]; }
 }
 
+// ---------------------------------------------------------------------------
+// Single-pass exclusive scan (decoupled look-back), NV values per element in one pass: every element's functor is
+// evaluated once, one launch. Tiles are taken in ticket order (forward progress: every predecessor of a tile is
+// running or done); each tile publishes its aggregate, then its inclusive prefix, in a state word per value
+//   [epoch:16][status:2][value:46]     status 1 = aggregate, 2 = inclusive prefix
+// The epoch makes the persistent state array reusable without clearing it between launches.
+// ---------------------------------------------------------------------------
+constexpr int LB_THREADS = 256, LB_ITEMS = 8, LB_TILE = LB_THREADS * LB_ITEMS;
+__device__ __forceinline__ unsigned long long lb_pack(unsigned long long epoch, unsigned status, unsigned long long v) {
+    return (epoch << 48) | ((unsigned long long)status << 46) | (v & ((1ULL << 46) - 1ULL));
+}
+template <int NV, class F>
+__global__ void __launch_bounds__(LB_THREADS) k_scan_lookback(F f, unsigned long long n, unsigned long long* out0, unsigned long long* out1,
+                                                              unsigned long long* state, unsigned long long* ticket,
+                                                              unsigned long long ticket_base, unsigned long long epoch) {
+    __shared__ unsigned long long s_tile, s_prefix[NV];
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1ULL) - ticket_base;
+    __syncthreads();
+    const unsigned long long tile = s_tile;
+    const unsigned long long base = tile * LB_TILE + (unsigned long long)threadIdx.x * LB_ITEMS;
+    unsigned long long v[NV][LB_ITEMS], acc[NV], ex[NV], total[NV];
+#pragma unroll
+    for (int c = 0; c < NV; c++) acc[c] = 0;
+#pragma unroll
+    for (int i = 0; i < LB_ITEMS; i++) {
+        unsigned long long e[NV];
+#pragma unroll
+        for (int c = 0; c < NV; c++) e[c] = 0;
+        if (base + i < n) f(base + i, e);
+#pragma unroll
+        for (int c = 0; c < NV; c++) { v[c][i] = e[c]; acc[c] += e[c]; }
+    }
+#pragma unroll
+    for (int c = 0; c < NV; c++) ex[c] = block_excl_scan(acc[c], total[c]);
+    volatile unsigned long long* st = state;
+    if (threadIdx.x < 32) {
+        // Every value has its own chain of state words (a tile's words are written one at a time, so a reader must
+        // never combine the status of one value with the payload of another): one look-back per value.
+        const int lane = threadIdx.x;
+#pragma unroll
+        for (int c = 0; c < NV; c++) {
+            unsigned long long running = 0;
+            if (tile > 0) {
+                if (lane == 0) st[tile * NV + c] = lb_pack(epoch, 1u, total[c]);
+                long long idx = (long long)tile - 1;
+                while (true) {
+                    // lane l looks at tile idx - l; tiles before the first count as "inclusive prefix 0"
+                    const unsigned long long w = idx - lane >= 0 ? st[(idx - lane) * NV + c] : lb_pack(epoch, 2u, 0ULL);
+                    const unsigned status = (unsigned)(w >> 46) & 3u;
+                    const bool ok = (w >> 48) == epoch && status != 0u;
+                    const unsigned m_incl = __ballot_sync(0xffffffffu, ok && status == 2u);
+                    const unsigned m_bad = __ballot_sync(0xffffffffu, !ok);
+                    const int first = m_incl ? __ffs(m_incl) - 1 : 32;
+                    const unsigned need = first >= 31 ? 0xffffffffu : ((1u << (first + 1)) - 1u);
+                    if (m_bad & need) continue;                 // a predecessor has not published yet: look again
+                    unsigned long long x = lane <= first ? (w & ((1ULL << 46) - 1ULL)) : 0ULL;
+#pragma unroll
+                    for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d);
+                    running += x;
+                    if (first < 32) break;
+                    idx -= 32;
+                }
+            }
+            if (lane == 0) {
+                st[tile * NV + c] = lb_pack(epoch, 2u, running + total[c]);
+                s_prefix[c] = running;
+            }
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < NV; c++) {
+        unsigned long long* out = c == 0 ? out0 : out1;
+        unsigned long long run = s_prefix[c] + ex[c];
+#pragma unroll
+        for (int i = 0; i < LB_ITEMS; i++) {
+            if (base + i < n) out[base + i] = run;
+            run += v[c][i];
+        }
+        if (threadIdx.x == 0 && (tile + 1) * LB_TILE >= n) out[n] = s_prefix[c] + total[c];     // the last tile writes the total
+    }
+}
+template <class F>
+struct OneValue {        // adapts a functor `ull f(i)` to the NV = 1 interface
+    F f;
+    __device__ void operator()(unsigned long long i, unsigned long long (&e)[1]) const { e[0] = f(i); }
+};
+struct BrickPrefixes {   // level 0: leaf ranks (popcount) and subtree sizes popc(W) + popc8(W) of the same words
+    const unsigned long long* mask;
+    __device__ void operator()(unsigned long long i, unsigned long long (&e)[2]) const {
+        const unsigned long long w = mask[i];
+        const unsigned pc = __popcll(w);
+        e[0] = pc; e[1] = pc + __popc(nonzero_bytes(w));
+    }
+};
+
 // Small inputs (the upper pyramid levels): the whole exclusive scan in ONE block / one launch.
 constexpr unsigned long long SCAN_SMALL_MAX = 32768;
 template <class F>
