@@ -1086,19 +1086,30 @@ static int build_phase_b(svo_ctx* c, const ull* table) {
         }
     }
     // ---- sync #2: record counts ----
+    // Binary builds on one GPU that have a node buffer from an earlier build skip this sync: the records are emitted
+    // into the existing buffer (every write is guarded by its capacity), the counts are read back with the final sync,
+    // and only if the tree turned out larger than the buffer is the emission repeated into a bigger one.
     LevelBufs& topL = c->lv[top];
+    const ull spec_cap = c->nodes.cap / SVO_NODE_BYTES;
+    bool spec = !host_merge && !payload && !levels && c->lv[0].n > 0 && spec_cap > 0;
+    if (const char* e = getenv("SVO_SPECULATIVE_EMIT")) spec = spec && e[0] != '0';
     if (!host_merge) {
     CK(cudaMemcpyAsync(c->h_pinned + 32, c->lv[0].fc.as<ull>() + c->lv[0].n, sizeof(ull), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaMemcpyAsync(c->h_pinned + 33, topL.ps.as<ull>() + topL.n, sizeof(ull), cudaMemcpyDeviceToHost, c->stream));
     if (levels) CK(cudaMemcpyAsync(c->h_pinned + 34, topL.pi.as<ull>() + topL.n, sizeof(ull), cudaMemcpyDeviceToHost, c->stream));
     if (want_pl) CK(cudaMemcpyAsync(c->h_pinned + 35, topL.pl.as<ull>() + topL.n, sizeof(ull), cudaMemcpyDeviceToHost, c->stream));
-    g_tl.stamp("sync2_wait");
-    CK(cudaStreamSynchronize(c->stream));
-    g_tl.stamp("sync2_done");
-    c->n_voxels_local = c->h_pinned[32];
-    c->n_voxels = c->n_voxels_local;
-    const ull s_top = c->h_pinned[33];
-    c->n_nodes = c->n_voxels == 0 ? 1 : s_top + (d_even ? 1 : 0);
+    if (!spec) {
+        g_tl.stamp("sync2_wait");
+        CK(cudaStreamSynchronize(c->stream));
+        g_tl.stamp("sync2_done");
+        c->n_voxels_local = c->h_pinned[32];
+        c->n_voxels = c->n_voxels_local;
+        const ull s_top = c->h_pinned[33];
+        c->n_nodes = c->n_voxels == 0 ? 1 : s_top + (d_even ? 1 : 0);
+    } else {
+        c->n_voxels = c->n_voxels_local = 1;        // placeholders (non-zero: lv[0].n > 0); the real counts arrive with the final sync
+        c->n_nodes = spec_cap;
+    }
     }
     c->n_data = payload ? 1 + c->n_voxels : 2;          // OctreeBuilder.cpp:25-29
     if (levels && c->n_voxels) c->n_data += c->h_pinned[34] - (d_even ? 0 : 1);   // one record per internal node (the virtual top word is no node)
@@ -1149,6 +1160,7 @@ static int build_phase_b(svo_ctx* c, const ull* table) {
     CK(c->nodes.ensure((size_t)(n_local_nodes ? n_local_nodes : 1) * SVO_NODE_BYTES));
     E.nodes = c->nodes.as<ull>() - c->node_lo * 3;
     E.pos_lo = c->node_lo; E.pos_hi = c->node_hi;
+    auto emit_all = [&](void) -> int {
     if (c->n_voxels == 0) {
         // empty grid: finalizeTree pads everything and writes a null root (OctreeBuilder.cpp:36-42)
         static const ull null_root[3] = { 0ULL, 0ULL, ~0ULL };
@@ -1182,6 +1194,12 @@ static int build_phase_b(svo_ctx* c, const ull* table) {
             else { k_emit_leaf<<<blocks_for(L0.n, WARPS_PER_BLOCK * EMIT_TILES_PER_WARP), WARPS_PER_BLOCK * 32, 0, c->stream>>>(L0, E); LAUNCHED(); }
             mark(c, EV_EL1);
         }
+    }
+    return SVO_OK;
+    };
+    {
+        int rc = emit_all();
+        if (rc) return rc;
     }
     mark(c, EV_EMIT1);
     // ---- data records ----
@@ -1262,6 +1280,21 @@ static int build_phase_b(svo_ctx* c, const ull* table) {
         CK(cudaMemsetAsync(&((SliceCtrl*)c->sl_ctrl.p)->error, 0, sizeof(ull), c->stream));
         c->dense_clean = false;
         return fail(c, SVO_E_CUDA, "remote triangle slices: timed out waiting for a peer rank");
+    }
+    if (spec) {
+        // the counts the skipped sync would have delivered
+        c->n_voxels_local = c->n_voxels = c->h_pinned[32];
+        c->n_nodes = c->h_pinned[33] + (d_even ? 1 : 0);
+        c->node_lo = 0; c->node_hi = c->n_nodes;
+        if (c->n_nodes > spec_cap) {
+            // the tree outgrew the buffer of the earlier build: emit again into a big enough one (the tile lists are intact)
+            CK(c->nodes.ensure((size_t)c->n_nodes * SVO_NODE_BYTES));
+            E.nodes = c->nodes.as<ull>();
+            E.pos_lo = 0; E.pos_hi = c->n_nodes;
+            int rc = emit_all();
+            if (rc) return rc;
+            CK(cudaStreamSynchronize(c->stream));
+        }
     }
     if (c->h_pinned[43]) {
         c->dense_clean = false;

@@ -1234,6 +1234,8 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_emit_leaf(Level L, Emi
         const uint32_t info = __shfl_sync(0xffffffffu, myInfo, t);
         const uint32_t nzb = info & 0xffu;
         const int nleaf = (int)(info >> 8);
+        // capacity guard (speculative emission into an earlier build's buffer; a rank's own regions always pass)
+        if (base + (unsigned long long)(nleaf + __popc(nzb) + (E.root_here ? 1 : 0)) > E.pos_hi) continue;
         unsigned long long* out = E.nodes + base * 3;
         const int total = 3 * nleaf;
         if (!E.leaf_data_mode) {
@@ -1481,19 +1483,24 @@ __device__ __forceinline__ void emit_upper_tile(const Level& L, const Level& C, 
             const unsigned long long blk = base + (C.ps[fc + __popcll(W & lowmask(8 * (k + 1)))] - ps0) + __popcll(W & lowmask(8 * k));
             const unsigned long long pos = blk + __popcll(W & lowmask(bit) & ~lowmask(8 * k));
             const uint32_t gnz = nonzero_bytes(C.mask[c]);
-            unsigned long long* o = E.nodes + pos * 3;
-            o[0] = 0ULL;
-            o[1] = gbase + (C.ps[c + 1] - C.ps[c]) - __popc(gnz);
-            o[2] = child_offsets(gnz);
+            if (pos < E.pos_hi) {                               // capacity guard (speculative emission)
+                unsigned long long* o = E.nodes + pos * 3;
+                o[0] = 0ULL;
+                o[1] = gbase + (C.ps[c + 1] - C.ps[c]) - __popc(gnz);
+                o[2] = child_offsets(gnz);
+            }
         }
     }
     if (lane < 8 && ((nzb >> lane) & 1u)) {
         const int k = lane;
         const unsigned long long blk = base + (C.ps[fc + __popcll(W & lowmask(8 * (k + 1)))] - ps0) + __popcll(W & lowmask(8 * k));
-        unsigned long long* o = E.nodes + (base + S - __popc(nzb) + __popc(nzb & ((1u << k) - 1u))) * 3;
-        o[0] = 0ULL;
-        o[1] = blk;
-        o[2] = child_offsets((uint32_t)((W >> (8 * k)) & 0xffULL));
+        const unsigned long long pos = base + S - __popc(nzb) + __popc(nzb & ((1u << k) - 1u));
+        if (pos < E.pos_hi) {
+            unsigned long long* o = E.nodes + pos * 3;
+            o[0] = 0ULL;
+            o[1] = blk;
+            o[2] = child_offsets((uint32_t)((W >> (8 * k)) & 0xffULL));
+        }
     }
 }
 // top-down emission of levels J..jf+1 (each level writes the bases of the next); level jf itself is emitted
@@ -1506,8 +1513,10 @@ __global__ void __launch_bounds__(1024) k_fused_emit(FusedJob F) {
         if (j == F.J && F.E.root_here && threadIdx.x == 0 && L.n) {
             const unsigned long long W = L.mask[0], S = L.ps[1] - L.ps[0];
             const uint32_t nzb = nonzero_bytes(W);
-            unsigned long long* o = F.E.nodes + S * 3;
-            o[0] = 0ULL; o[1] = L.base[0] + S - __popc(nzb); o[2] = child_offsets(nzb);
+            if (S < F.E.pos_hi) {
+                unsigned long long* o = F.E.nodes + S * 3;
+                o[0] = 0ULL; o[1] = L.base[0] + S - __popc(nzb); o[2] = child_offsets(nzb);
+            }
         }
         __syncthreads();
     }

@@ -149,3 +149,18 @@ def test_svo_run_host_buffers(builder, oracle):
     data = np.zeros(want.n_data * 32, dtype=np.uint8)
     st = builder.run_host(prm, m.tris, nodes, data)
     assert st["n_nodes"] == want.n_nodes and nodes.tobytes() == want.nodes and data.tobytes() == want.data
+
+
+def test_speculative_emission_regrows_the_node_buffer(oracle):
+    # a context that built a SMALL tree first emits the next, larger tree speculatively into the old buffer (guarded),
+    # notices the overflow with the final sync and repeats the emission into a bigger buffer: files still byte-exact
+    from ooc_svo_builder_b200 import SvoBuilder
+    sb = SvoBuilder(0)
+    try:
+        for mesh, g in ((mg.icosphere(2), 32), (mg.icosphere(5), 256), (mg.icosphere(3), 64), (mg.random_soup(2000, seed=12), 256)):
+            got = sb.run(mesh.tris, mesh.length, g)
+            want = oracle.build(mesh.tris, mesh.length, g)
+            assert got.header == want.header
+            assert got.nodes.tobytes() == want.nodes and got.data.tobytes() == want.data
+    finally:
+        sb.close()
