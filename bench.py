@@ -262,12 +262,12 @@ def ours(args):
     else:
         alg_bytes = T * 36 + (GRID ** 3) // 8 * 0 + 8 * nv
         note = ("voxelizer: T*36 B triangle records read + 8 B per occupied voxel of bit-grid traffic, divided by k_vox_warp time. "
-                "The kernel is instruction-bound, not HBM-bound (ncu: 120 M warp instructions, 29.9 of 32 threads active, 66 % issue "
-                "slots busy, DRAM 5 %): see profiles/README.md; the HBM-bound kernel of the path is k_emit_leaf (octree_build below)")
+                "The kernel is instruction-bound, not HBM-bound (ncu: 125 M warp instructions, 29.3 of 32 threads active, 70 % issue "
+                "slots busy, DRAM 6 %): see profiles/README.md; the HBM-bound kernel of the path is k_emit_leaf (octree_build below)")
     achieved = alg_bytes / (kern[dom]["ms"] * 1e-3) / 1e9 if kern[dom]["ms"] > 0 else 0.0
     traffic = None
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic_c2.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r01g_traffic_c2.json")) as f:
             tj = json.load(f)
         traffic = tj[dom]["dram_bytes_read"] + tj[dom]["dram_bytes_write"]      # ncu --set full capture of the same workload
     except Exception:

@@ -112,6 +112,15 @@ float svo_text_roundtrip_float(float v);
 int svo_set_triangles(svo_ctx* ctx, const float* tris, uint64_t n_tris, int floats_per_tri);
 int svo_set_triangles_device(svo_ctx* ctx, const float* tris, uint64_t n_tris, int floats_per_tri);
 
+/* Streamed variant of svo_set_triangles for files larger than the host budget (-l): the caller reads the
+ * .tridata file in chunks (the role of TriReader's buffer, TriReader.h:9-40, with megabytes instead of 8192
+ * triangles) into TWO alternating pinned buffers (svo_host_alloc) and appends them; the copy of one chunk
+ * overlaps the fread of the next. When svo_triangles_append returns, every EARLIER chunk has reached the
+ * device (its buffer may be refilled); the chunk just passed is still in flight. The triangle set is complete
+ * when n_tris records have been appended. */
+int svo_triangles_begin(svo_ctx* ctx, uint64_t n_tris, int floats_per_tri);
+int svo_triangles_append(svo_ctx* ctx, const float* host_chunk, uint64_t n_chunk_tris);
+
 /* Replaces `TripInfo partition(tri_info, n_partitions, gridsize)`
  * (partitioner.cpp:101-149, BBoxBuffer.h:70-84, intersection.h:50-53): bins every
  * triangle into every logical partition whose world box its bbox touches

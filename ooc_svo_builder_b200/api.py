@@ -26,7 +26,7 @@ DATA_BYTES = 32
 ABI_SYMBOLS = [
     "svo_ctx_create", "svo_ctx_destroy", "svo_ctx_set_stream", "svo_last_error", "svo_version",
     "svo_estimate_partitions", "svo_text_roundtrip_float",
-    "svo_set_triangles", "svo_set_triangles_device", "svo_partition", "svo_voxelize", "svo_build",
+    "svo_set_triangles", "svo_set_triangles_device", "svo_triangles_begin", "svo_triangles_append", "svo_partition", "svo_voxelize", "svo_build",
     "svo_fetch_nodes", "svo_fetch_data", "svo_device_nodes", "svo_device_data", "svo_fetch_voxel_codes",
     "svo_shard_configure", "svo_shard_table_size", "svo_shard_count", "svo_shard_emit", "svo_shard_ranges",
     "svo_shard_dispatch_create", "svo_shard_dispatch_attach", "svo_shard_dispatch_count", "svo_shard_dispatch_send",
@@ -87,6 +87,8 @@ def load_library(path: str | None = None):
     L.svo_text_roundtrip_float.restype = C.c_float; L.svo_text_roundtrip_float.argtypes = [C.c_float]
     L.svo_set_triangles.restype = i32; L.svo_set_triangles.argtypes = [vp, vp, u64, i32]
     L.svo_set_triangles_device.restype = i32; L.svo_set_triangles_device.argtypes = [vp, vp, u64, i32]
+    L.svo_triangles_begin.restype = i32; L.svo_triangles_begin.argtypes = [vp, u64, i32]
+    L.svo_triangles_append.restype = i32; L.svo_triangles_append.argtypes = [vp, vp, u64]
     L.svo_partition.restype = i32; L.svo_partition.argtypes = [vp, C.POINTER(Params), C.POINTER(u64), vp, u64]
     L.svo_voxelize.restype = i32; L.svo_voxelize.argtypes = [vp]
     L.svo_build.restype = i32; L.svo_build.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
@@ -261,6 +263,22 @@ class SvoBuilder:
             assert tris.is_cuda and tris.is_contiguous() and tris.dtype.is_floating_point and tris.element_size() == 4
             self._keep = tris
             self._ck(self._lib.svo_set_triangles_device(self._h, tris.data_ptr(), tris.shape[0], tris.shape[1]))
+
+    def set_triangles_streamed(self, tris: np.ndarray, chunk_tris: int) -> None:
+        """svo_triangles_begin / _append with two alternating pinned chunks (what the CLI does while it reads the file)."""
+        tris = np.ascontiguousarray(tris, dtype=np.float32)
+        T, fpt = tris.shape
+        self._ck(self._lib.svo_triangles_begin(self._h, T, fpt))
+        bufs = [PinnedBuffer(max(chunk_tris, 1) * fpt * 4) for _ in range(2)]
+        flat = tris.reshape(-1).view(np.uint8)
+        for k, lo in enumerate(range(0, T, max(chunk_tris, 1))):
+            n = min(chunk_tris, T - lo)
+            b = bufs[k & 1]
+            b.array[: n * fpt * 4] = flat[lo * fpt * 4: (lo + n) * fpt * 4]
+            self._ck(self._lib.svo_triangles_append(self._h, b.ptr, n))
+        self.synchronize()
+        for b in bufs:
+            b.free()
 
     def partition(self, params: Params, want_counts: bool = True) -> np.ndarray | None:
         """partitioner.cpp:101-149 → per-partition triangle counts (the .trip header values).

@@ -70,6 +70,10 @@ struct svo_ctx {
     uint64_t n_tris = 0;
     int fpt = 0;
     bool have_tris = false;
+    uint64_t stream_fill = 0;          // svo_triangles_begin / _append: records copied so far
+    cudaEvent_t up_ev[2] = { nullptr, nullptr };
+    bool up_pending[2] = { false, false };
+    int up_slot = 0;
 
     // job
     svo_params prm;
@@ -484,6 +488,7 @@ void svo_ctx_destroy(svo_ctx* c) {
     c->lb_state.release(); c->lb_ticket.release();
     c->scan_tmp.release(); c->nodes.release(); c->data.release(); c->owner.release(); c->tileidx.release(); c->codes.release();
     for (int i = 0; i < EV_COUNT; i++) cudaEventDestroy(c->ev[i]);
+    for (int i = 0; i < 2; i++) if (c->up_ev[i]) cudaEventDestroy(c->up_ev[i]);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     cudaStreamDestroy(c->own_stream);
     delete c;
@@ -554,6 +559,44 @@ int svo_set_triangles(svo_ctx* c, const float* tris, uint64_t n_tris, int fpt) {
     if (bytes) CK(cudaMemcpyAsync(c->tri_own.p, tris, bytes, cudaMemcpyHostToDevice, c->stream));
     mark(c, EV_UP1);
     c->d_tris = c->tri_own.as<float>();
+    return SVO_OK;
+}
+
+int svo_triangles_begin(svo_ctx* c, uint64_t n_tris, int fpt) {
+    if (!c) return SVO_E_INVALID;
+    CK(cudaSetDevice(c->device));
+    int rc = set_tris_common(c, n_tris, fpt);
+    if (rc) return rc;
+    c->have_tris = false;                              // complete only after the last append
+    const size_t bytes = (size_t)n_tris * fpt * sizeof(float);
+    CK(c->tri_own.ensure(bytes ? bytes : 16));
+    c->d_tris = c->tri_own.as<float>();
+    c->stream_fill = 0;
+    for (int i = 0; i < EV_COUNT; i++) c->ev_set[i] = false;
+    mark(c, EV_UP0);
+    if (!c->up_ev[0]) { CK(cudaEventCreateWithFlags(&c->up_ev[0], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&c->up_ev[1], cudaEventDisableTiming)); }
+    c->up_slot = 0; c->up_pending[0] = c->up_pending[1] = false;
+    if (n_tris == 0) { c->have_tris = true; mark(c, EV_UP1); }
+    return SVO_OK;
+}
+
+int svo_triangles_append(svo_ctx* c, const float* host_chunk, uint64_t n) {
+    if (!c) return SVO_E_INVALID;
+    if (c->have_tris || !c->d_tris || c->d_tris != c->tri_own.as<float>()) return fail(c, SVO_E_INVALID, "svo_triangles_append without svo_triangles_begin");
+    if (c->stream_fill + n > c->n_tris) return fail(c, SVO_E_RANGE, "more triangles appended than announced");
+    if (n && !host_chunk) return fail(c, SVO_E_INVALID, "host_chunk is NULL");
+    CK(cudaSetDevice(c->device));
+    const size_t rec = (size_t)c->fpt * sizeof(float);
+    if (n) CK(cudaMemcpyAsync((char*)c->tri_own.p + c->stream_fill * rec, host_chunk, n * rec, cudaMemcpyHostToDevice, c->stream));
+    // double-buffer contract: when this call returns, every EARLIER chunk has been copied (its buffer may be refilled);
+    // the chunk just passed is still in flight
+    const int slot = c->up_slot;
+    CK(cudaEventRecord(c->up_ev[slot], c->stream));
+    c->up_pending[slot] = true;
+    if (c->up_pending[slot ^ 1]) { CK(cudaEventSynchronize(c->up_ev[slot ^ 1])); c->up_pending[slot ^ 1] = false; }
+    c->up_slot = slot ^ 1;
+    c->stream_fill += n;
+    if (c->stream_fill == c->n_tris) { c->have_tris = true; mark(c, EV_UP1); }
     return SVO_OK;
 }
 

@@ -234,22 +234,58 @@ int main(int argc, char** argv) {
     svo_ctx* ctx = nullptr;
     std::future<int> ctx_ready = std::async(std::launch::async, [&ctx, device_index]() { return svo_ctx_create(device_index, &ctx); });
 
-    // triangle records with one large sequential read (replaces TriReader's 8192-triangle fread loop)
-    const size_t tri_bytes = (size_t)hdr.n_triangles * kFloatsPerTri * sizeof(float);
-    float* tris = static_cast<float*>(std::malloc(tri_bytes ? tri_bytes : 1));
-    if (!tris) { std::cout << "Error: cannot allocate " << tri_bytes << " bytes of host memory" << std::endl; return 0; }
+    // Triangle records: the file is read in chunks into two alternating pinned buffers and streamed to the device, the
+    // copy of one chunk overlapping the fread of the next (replaces TriReader's 8192-triangle fread loop,
+    // TriReader.h:41-79). The two chunks stay inside the -l budget; the whole file is never resident on the host.
+    const size_t rec_bytes = (size_t)kFloatsPerTri * sizeof(float);
+    const size_t tri_bytes = (size_t)hdr.n_triangles * rec_bytes;
     {
+        const size_t in_budget = std::max<size_t>((size_t)opt.memory_limit << 20, 1u << 20);
+        const size_t chunk_tris = std::max<size_t>(std::min<size_t>(in_budget / 4, 64u << 20) / rec_bytes, 1);
         FILE* f = std::fopen(tridata.c_str(), "rb");
-        size_t got = 0;
-        while (got < tri_bytes) {
-            const size_t r = std::fread(reinterpret_cast<char*>(tris) + got, 1, std::min<size_t>(tri_bytes - got, 64u << 20), f);
-            if (r == 0) break;
-            got += r;
+        // while the CUDA context comes up (~1 s), read the head of the file into ordinary memory (within the budget)
+        const size_t head_cap = std::min<size_t>(tri_bytes, (in_budget / 2) / rec_bytes * rec_bytes);
+        char* head = static_cast<char*>(std::malloc(head_cap ? head_cap : 1));
+        size_t head_have = 0;
+        while (f && head && head_have < head_cap && ctx_ready.wait_for(std::chrono::seconds(0)) != std::future_status::ready) {
+            const size_t want = std::min<size_t>(head_cap - head_have, (8u << 20) / rec_bytes * rec_bytes + rec_bytes);
+            const size_t r = std::fread(head + head_have, 1, want, f);
+            if (r != want) { head_have += r; break; }
+            head_have += r;
         }
-        std::fclose(f);
-        if (got != tri_bytes) { std::cout << "Error: " << tridata << " holds " << got << " bytes, header promises " << tri_bytes << std::endl; return 0; }
+        head_have = head_have / rec_bytes * rec_bytes;
+        if (f) std::fseek(f, (long)head_have, SEEK_SET);
+        if (ctx_ready.get() != SVO_OK) die(nullptr, "svo_ctx_create");
+        void* in_chunk[2] = { svo_host_alloc(chunk_tris * rec_bytes), svo_host_alloc(chunk_tris * rec_bytes) };
+        if (!in_chunk[0] || !in_chunk[1]) { std::cout << "Error: cannot allocate pinned input buffers" << std::endl; return 0; }
+        if (svo_triangles_begin(ctx, hdr.n_triangles, kFloatsPerTri) != SVO_OK) die(ctx, "svo_triangles_begin");
+        size_t got = 0;
+        if (head_have) {
+            if (svo_triangles_append(ctx, reinterpret_cast<const float*>(head), head_have / rec_bytes) != SVO_OK) die(ctx, "svo_triangles_append");
+            if (svo_synchronize(ctx) != SVO_OK) die(ctx, "svo_synchronize");      // `head` is pageable and freed right away
+            got = head_have;
+        }
+        std::free(head);
+        int slot = 0;
+        while (f && got < tri_bytes) {
+            const size_t want = std::min<size_t>(tri_bytes - got, chunk_tris * rec_bytes);
+            size_t have = 0;
+            while (have < want) {
+                const size_t r = std::fread(static_cast<char*>(in_chunk[slot]) + have, 1, want - have, f);
+                if (r == 0) break;
+                have += r;
+            }
+            if (have != want) break;
+            if (svo_triangles_append(ctx, static_cast<const float*>(in_chunk[slot]), want / rec_bytes) != SVO_OK) die(ctx, "svo_triangles_append");
+            got += want;
+            slot ^= 1;
+        }
+        if (f) std::fclose(f);
+        if (got != tri_bytes) { std::cout << "Error: " << tridata << " holds fewer than the " << tri_bytes << " bytes the header promises" << std::endl; return 0; }
+        if (svo_synchronize(ctx) != SVO_OK) die(ctx, "svo_synchronize");
+        svo_host_free(in_chunk[0]);
+        svo_host_free(in_chunk[1]);
     }
-    if (ctx_ready.get() != SVO_OK) die(nullptr, "svo_ctx_create");
     const double ms_in = t_in.ms();
 
     // ---- partitioning ----------------------------------------------------
@@ -273,7 +309,6 @@ int main(int argc, char** argv) {
     prm.color_mode = opt.color;
     prm.sparseness_limit = opt.sparseness;
 
-    if (svo_set_triangles(ctx, tris, hdr.n_triangles, kFloatsPerTri) != SVO_OK) die(ctx, "svo_set_triangles");
     std::vector<uint64_t> tricounts(P, 0);
     uint64_t P_lib = 0;
     if (svo_partition(ctx, &prm, &P_lib, tricounts.data(), P) != SVO_OK) die(ctx, "svo_partition");
@@ -348,7 +383,6 @@ int main(int argc, char** argv) {
     }
     svo_host_free(chunk[0]);
     svo_host_free(chunk[1]);
-    std::free(tris);
     svo_ctx_destroy(ctx);
     return 0;
 }

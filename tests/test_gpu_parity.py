@@ -164,3 +164,16 @@ def test_speculative_emission_regrows_the_node_buffer(oracle):
             assert got.nodes.tobytes() == want.nodes and got.data.tobytes() == want.data
     finally:
         sb.close()
+
+
+@pytest.mark.parametrize("chunk", [1, 1000, 4096, 10 ** 6])
+def test_streamed_triangle_upload(oracle, builder, chunk):
+    # svo_triangles_begin / _append (what the CLI does while it reads the file) == svo_set_triangles
+    from ooc_svo_builder_b200 import SvoBuilder
+    m = mg.random_soup(5000, seed=21, large_frac=0.01) if chunk > 1 else mg.icosphere(1)
+    builder.set_triangles_streamed(m.tris, chunk)
+    prm = SvoBuilder.make_params(m.length, 128, False)
+    builder.partition(prm, want_counts=False); builder.voxelize()
+    nv, nn, nd = builder.build()
+    want = oracle.build(m.tris, m.length, 128)
+    assert builder.fetch_nodes(0, nn).tobytes() == want.nodes and nv == want.n_voxels

@@ -96,3 +96,13 @@ def test_node_count_closed_form(oracle):
     m = mg.random_soup(400, seed=8)
     codes = oracle.voxelize(m.tris, m.length, 128)
     assert sharded.node_count_from_codes(codes, 128) == oracle.build(m.tris, m.length, 128).n_nodes
+
+
+@pytest.mark.parametrize("T,world", [(0, 2), (1, 8), (127, 4), (128, 4), (1000, 8), (2 ** 20 + 3, 8)])
+def test_slices_tile_the_triangle_file(T, world):
+    # rank r holds the r-th slice in file order: contiguous, disjoint, complete, equal capacity
+    b = [sharded.slice_bounds(T, world, r) for r in range(world)]
+    assert b[0][0] == 0 and b[-1][1] == T
+    assert all(x[1] == y[0] for x, y in zip(b, b[1:]))
+    cap = (T + world - 1) // world
+    assert all(0 <= hi - lo <= cap for lo, hi in b)
