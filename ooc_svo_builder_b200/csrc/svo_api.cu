@@ -102,7 +102,7 @@ struct svo_ctx {
 
     // compact levels
     LevelBufs lv[MAX_LEVELS];
-    DevBuf scan_tmp, lb_state, lb_ticket;
+    DevBuf lb_state, lb_ticket;
     ull lb_epoch = 0, lb_tickets = 0;
 
     // outputs
@@ -486,7 +486,7 @@ void svo_ctx_destroy(svo_ctx* c) {
     c->inbox.release(); c->ctrl_buf.release(); c->blockcnt.release(); c->blockoff.release();
     if (c->h_ctrl) cudaFreeHost(c->h_ctrl);
     c->lb_state.release(); c->lb_ticket.release();
-    c->scan_tmp.release(); c->nodes.release(); c->data.release(); c->owner.release(); c->tileidx.release(); c->codes.release();
+    c->nodes.release(); c->data.release(); c->owner.release(); c->tileidx.release(); c->codes.release();
     for (int i = 0; i < EV_COUNT; i++) cudaEventDestroy(c->ev[i]);
     for (int i = 0; i < 2; i++) if (c->up_ev[i]) cudaEventDestroy(c->up_ev[i]);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
@@ -1741,9 +1741,14 @@ int svo_shard_slice_publish(svo_ctx* c, const svo_params* params, uint64_t n_tot
     S.cursor = c->sl_cursor.as<ull>();
     if (D.nb) {
         const size_t smem = (size_t)FILTER_WARPS * VOX_BLOCK * c->slice_fpt * sizeof(float);      // 36 / 84 KB
-        if (!c->filter_attr_set) { CK(cudaFuncSetAttribute(k_slice_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, FILTER_WARPS * VOX_BLOCK * 21 * (int)sizeof(float))); c->filter_attr_set = true; }
+        if (!c->filter_attr_set) {
+            CK(cudaFuncSetAttribute(k_slice_filter<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, FILTER_WARPS * VOX_BLOCK * 9 * (int)sizeof(float)));
+            CK(cudaFuncSetAttribute(k_slice_filter<21>, cudaFuncAttributeMaxDynamicSharedMemorySize, FILTER_WARPS * VOX_BLOCK * 21 * (int)sizeof(float)));
+            c->filter_attr_set = true;
+        }
         const unsigned grid = (unsigned)std::min<ull>((D.nb + FILTER_WARPS - 1) / FILTER_WARPS, (ull)c->sm_count * 4);
-        k_slice_filter<<<grid, FILTER_WARPS * 32, smem, c->stream>>>(S); LAUNCHED();
+        if (c->slice_fpt == 9) { k_slice_filter<9><<<grid, FILTER_WARPS * 32, smem, c->stream>>>(S); LAUNCHED(); }
+        else { k_slice_filter<21><<<grid, FILTER_WARPS * 32, smem, c->stream>>>(S); LAUNCHED(); }
     }
     k_slice_post<<<1, MAX_WORLD, 0, c->stream>>>(S, 0); LAUNCHED();
     mark(c, EV_DSP1);

@@ -191,22 +191,32 @@ struct SliceJob {
 };
 
 constexpr int FILTER_WARPS = 8;
+// order-preserving float <-> int maps (for the integer warp reductions): a < b  <=>  ord(a) < ord(b) for non-NaN floats
+__device__ __forceinline__ int float_to_ord(float f) { const int i = __float_as_int(f); return i ^ ((i >> 31) & 0x7fffffff); }
+__device__ __forceinline__ float ord_to_float(int i) { return __int_as_float(i ^ ((i >> 31) & 0x7fffffff)); }
 // One WARP per staging block (4 x 32 triangles): the block's 4608 / 10752 bytes are read with coalesced float4 loads
-// into the warp's shared-memory tile, each lane then tests 4 triangles. Every warp owns a contiguous run of staging
-// blocks and reserves list space once per 64 of them (lane d keeps the hit mask of destination d), so the list
-// cursors see ~1/20 of the atomics a per-block append would issue (those were the bottleneck: same-address atomics).
+// into the warp's shared-memory tile. Every warp owns a contiguous run of staging blocks and reserves list space once
+// per 16 of them (lane d keeps the hit mask of destination d), so the list cursors see a fraction of the atomics a
+// per-block append would issue (same-address atomics were the bottleneck of the first version).
+template <int FPT>
 __global__ void __launch_bounds__(FILTER_WARPS * 32) k_slice_filter(SliceJob S) {
     extern __shared__ float4 s_f4[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const uint32_t fpt = S.D.fpt;
+    constexpr uint32_t fpt = FPT;
     float4* tile4 = s_f4 + (size_t)wid * (VOX_BLOCK * fpt / 4);
     const float* tile = reinterpret_cast<const float*>(tile4);
     const unsigned long long nwarps = (unsigned long long)gridDim.x * FILTER_WARPS;
     const unsigned long long per = (S.D.nb + nwarps - 1) / nwarps;
     const unsigned long long gw = (unsigned long long)blockIdx.x * FILTER_WARPS + wid;
     const unsigned long long b1 = min(S.D.nb, (gw + 1) * per);
-    const unsigned n4 = VOX_BLOCK * fpt / 4;
+    constexpr int PER_LANE = VOX_BLOCK * FPT / 4 / 32;          // float4 loads per lane and staging block: 9 or 21
     static_assert(VOX_BLOCK == 128 && UNIT == 32, "a staging block is four 32-triangle units");
+    // lane d tests destination d: its box, once, in registers
+    const int dd = lane < S.D.world ? lane : 0;
+    float d_lof[3], d_hif[3];
+    int d_lo[3], d_hi[3];
+#pragma unroll
+    for (int a = 0; a < 3; a++) { d_lof[a] = S.D.lof[dd][a]; d_hif[a] = S.D.hif[dd][a]; d_lo[a] = S.D.lo[dd][a]; d_hi[a] = S.D.hi[dd][a]; }
     for (unsigned long long base = gw * per; base < b1; base += 16) {
         unsigned long long hits = 0;                            // lane d: nibble j = warps of block base + j that touch destination d
         const int nj = (int)min(16ULL, b1 - base);
@@ -214,14 +224,52 @@ __global__ void __launch_bounds__(FILTER_WARPS * 32) k_slice_filter(SliceJob S) 
             const unsigned long long q0 = (base + j) * VOX_BLOCK;
             const unsigned nrec = (unsigned)(S.D.n_local - q0 < VOX_BLOCK ? S.D.n_local - q0 : VOX_BLOCK);
             const float4* src4 = reinterpret_cast<const float4*>(S.D.tris + q0 * fpt);   // the slice buffer is padded to whole blocks
-            for (unsigned i = lane; i < n4; i += 32) tile4[i] = __ldg(src4 + i);
+            {   // all loads of the block in flight before the first store (a rolled loop would serialise nine DRAM latencies)
+                float4 r[PER_LANE];
+#pragma unroll
+                for (int i = 0; i < PER_LANE; i++) r[i] = __ldg(src4 + lane + 32 * i);
+#pragma unroll
+                for (int i = 0; i < PER_LANE; i++) tile4[lane + 32 * i] = r[i];
+            }
             __syncwarp();
 #pragma unroll
-            for (int k = 0; k < 4; k++) {                       // triangles 32k .. 32k + 31 are the voxelizer's warp k
+            for (int k = 0; k < 4; k++) {                       // triangles 32k .. 32k + 31 are unit k of the block
+                // One test per UNIT and destination instead of one per triangle: the unit's bounding box (six warp
+                // reductions) against the destination box, lane d testing destination d. A superset of the union of the
+                // per-triangle tests (per axis it is exactly their union), which is all the list needs: the voxelizer on
+                // the destination applies the exact per-partition rule to every triangle. Units with a NaN or an
+                // absurdly large coordinate (float -> int conversion no longer monotone) go to every destination.
                 const unsigned t = lane + 32u * k;
-                unsigned m = t < nrec ? dispatch_mask(S.D, tile + (size_t)t * fpt) : 0u;
-                m = __reduce_or_sync(0xffffffffu, m);
-                if ((m >> lane) & 1u) hits |= 1ULL << (4 * j + k);
+                float mn[3], mx[3];
+                bool odd = false;
+                if (t < nrec) {
+                    const float* c = tile + (size_t)t * fpt;
+#pragma unroll
+                    for (int a = 0; a < 3; a++) {
+                        mn[a] = stdmin(c[a], stdmin(c[3 + a], c[6 + a])); mx[a] = stdmax(c[a], stdmax(c[3 + a], c[6 + a]));
+                        odd = odd || !(fabsf(fmul(mn[a], S.D.unit_div)) < 1.0e9f) || !(fabsf(fmul(mx[a], S.D.unit_div)) < 1.0e9f);   // NaN compares false
+                    }
+                } else {
+#pragma unroll
+                    for (int a = 0; a < 3; a++) { mn[a] = __int_as_float(0x7f800000); mx[a] = __int_as_float(0xff800000); }
+                }
+                const bool any_odd = __any_sync(0xffffffffu, odd);
+                const bool any_tri = __any_sync(0xffffffffu, t < nrec);
+                bool touch = true;
+#pragma unroll
+                for (int a = 0; a < 3; a++) {
+                    const float umn = ord_to_float(__reduce_min_sync(0xffffffffu, float_to_ord(mn[a])));
+                    const float umx = ord_to_float(__reduce_max_sync(0xffffffffu, float_to_ord(mx[a])));
+                    if (lane < S.D.world) {
+                        if (S.D.use_partitions) {
+                            touch = touch && !(umx < d_lof[a]) && !(umn > d_hif[a]);
+                        } else {
+                            const int l = clampi(f2i(fmul(umn, S.D.unit_div)), 0, S.D.gmax), h = clampi(f2i(fmul(umx, S.D.unit_div)), 0, S.D.gmax);
+                            touch = touch && !(h < d_lo[a] || l > d_hi[a]);
+                        }
+                    }
+                }
+                if (lane < S.D.world && any_tri && (touch || any_odd)) hits |= 1ULL << (4 * j + k);
             }
             __syncwarp();
         }

@@ -701,12 +701,10 @@ __global__ void __launch_bounds__(VOX_BLOCK) k_owner_filter(FilterJob Fj) {
 }
 
 // ---------------------------------------------------------------------------
-// Hand-written exclusive scan (no CUB): reduce per tile -> scan tile sums in one
-// block -> rescan tiles with their offset. out has n + 1 entries (out[n] = total).
+// Hand-written exclusive scans (no CUB). out has n + 1 entries (out[n] = total). Small inputs: one block
+// (k_scan_small); everything else: one single-pass look-back launch (k_scan_lookback).
 // ---------------------------------------------------------------------------
-constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_ITEMS = 8;
-constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 
 __device__ __forceinline__ unsigned long long warp_incl_scan(unsigned long long v) {
     const int lane = threadIdx.x & 31;
@@ -733,105 +731,6 @@ __device__ __forceinline__ unsigned long long block_excl_scan(unsigned long long
     __syncthreads();
     total = s_w[nw - 1];
     return inc - v + (wid ? s_w[wid - 1] : 0ULL);
-}
-
-template <class F>
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_reduce(F f, unsigned long long n, unsigned long long* tile_sums) {
-    const unsigned long long base = (unsigned long long)blockIdx.x * SCAN_TILE;
-    unsigned long long acc = 0;
-#pragma unroll
-    for (int i = 0; i < SCAN_ITEMS; i++) {
-        const unsigned long long idx = base + (unsigned long long)i * SCAN_THREADS + threadIdx.x;
-        if (idx < n) acc += f(idx);
-    }
-    unsigned long long total;
-    block_excl_scan(acc, total);
-    if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
-}
-// single block: in-place exclusive scan of tile_sums[0..nt), total to tile_sums[nt]
-__global__ void __launch_bounds__(1024) k_scan_tiles(unsigned long long* tile_sums, unsigned long long nt) {
-    unsigned long long carry = 0;
-    for (unsigned long long b = 0; b < nt; b += blockDim.x) {
-        const unsigned long long idx = b + threadIdx.x;
-        const unsigned long long v = idx < nt ? tile_sums[idx] : 0ULL;
-        unsigned long long total;
-        const unsigned long long ex = block_excl_scan(v, total);
-        if (idx < nt) tile_sums[idx] = carry + ex;
-        carry += total;
-    }
-    if (threadIdx.x == 0) tile_sums[nt] = carry;
-}
-template <class F>
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_final(F f, unsigned long long n, const unsigned long long* tile_sums,
-                                                             unsigned long long* out) {
-    // blocked arrangement: thread t owns SCAN_ITEMS consecutive elements
-    const unsigned long long base = (unsigned long long)blockIdx.x * SCAN_TILE + (unsigned long long)threadIdx.x * SCAN_ITEMS;
-    unsigned long long v[SCAN_ITEMS];
-    unsigned long long acc = 0;
-#pragma unroll
-    for (int i = 0; i < SCAN_ITEMS; i++) {
-        v[i] = (base + i < n) ? f(base + i) : 0ULL;
-        acc += v[i];
-    }
-    unsigned long long total;
-    unsigned long long run = block_excl_scan(acc, total) + tile_sums[blockIdx.x];
-#pragma unroll
-    for (int i = 0; i < SCAN_ITEMS; i++) {
-        if (base + i < n) out[base + i] = run;
-        run += v[i];
-    }
-    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) out[n] = tile_sums[gridDim.x];
-}
-
-// Level 0 (bricks) needs two prefixes of the same words: popcount (leaf ranks / child index) and subtree size
-// popc(W) + popc8(W). Same reduce / scan / rescan scheme, both values per pass: 3 launches instead of 6.
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan2_reduce(const unsigned long long* mask, unsigned long long n,
-                                                               unsigned long long* sums_a, unsigned long long* sums_b) {
-    const unsigned long long base = (unsigned long long)blockIdx.x * SCAN_TILE;
-    unsigned long long a = 0, b = 0;
-#pragma unroll
-    for (int i = 0; i < SCAN_ITEMS; i++) {
-        const unsigned long long idx = base + (unsigned long long)i * SCAN_THREADS + threadIdx.x;
-        if (idx < n) { const unsigned long long w = mask[idx]; const unsigned pc = __popcll(w); a += pc; b += pc + __popc(nonzero_bytes(w)); }
-    }
-    unsigned long long ta, tb;
-    block_excl_scan(a, ta);
-    block_excl_scan(b, tb);
-    if (threadIdx.x == 0) { sums_a[blockIdx.x] = ta; sums_b[blockIdx.x] = tb; }
-}
-__global__ void __launch_bounds__(1024) k_scan2_tiles(unsigned long long* sums_a, unsigned long long* sums_b, unsigned long long nt) {
-    unsigned long long ca = 0, cb = 0;
-    for (unsigned long long b0 = 0; b0 < nt; b0 += blockDim.x) {
-        const unsigned long long idx = b0 + threadIdx.x;
-        const unsigned long long va = idx < nt ? sums_a[idx] : 0ULL, vb = idx < nt ? sums_b[idx] : 0ULL;
-        unsigned long long ta, tb;
-        const unsigned long long ea = block_excl_scan(va, ta);
-        const unsigned long long eb = block_excl_scan(vb, tb);
-        if (idx < nt) { sums_a[idx] = ca + ea; sums_b[idx] = cb + eb; }
-        ca += ta; cb += tb;
-    }
-    if (threadIdx.x == 0) { sums_a[nt] = ca; sums_b[nt] = cb; }
-}
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan2_final(const unsigned long long* mask, unsigned long long n, const unsigned long long* sums_a,
-                                                              const unsigned long long* sums_b, unsigned long long* out_a, unsigned long long* out_b) {
-    const unsigned long long base = (unsigned long long)blockIdx.x * SCAN_TILE + (unsigned long long)threadIdx.x * SCAN_ITEMS;
-    unsigned va[SCAN_ITEMS], vb[SCAN_ITEMS];
-    unsigned long long a = 0, b = 0;
-#pragma unroll
-    for (int i = 0; i < SCAN_ITEMS; i++) {
-        va[i] = 0; vb[i] = 0;
-        if (base + i < n) { const unsigned long long w = mask[base + i]; va[i] = __popcll(w); vb[i] = va[i] + __popc(nonzero_bytes(w)); }
-        a += va[i]; b += vb[i];
-    }
-    unsigned long long ta, tb;
-    unsigned long long ra = block_excl_scan(a, ta) + sums_a[blockIdx.x];
-    unsigned long long rb = block_excl_scan(b, tb) + sums_b[blockIdx.x];
-#pragma unroll
-    for (int i = 0; i < SCAN_ITEMS; i++) {
-        if (base + i < n) { out_a[base + i] = ra; out_b[base + i] = rb; }
-        ra += va[i]; rb += vb[i];
-    }
-    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) { out_a[n] = sums_a[gridDim.x]; out_b[n] = sums_b[gridDim.x]; }
 }
 
 // ---------------------------------------------------------------------------
@@ -931,7 +830,6 @@ struct BrickPrefixes {   // level 0: leaf ranks (popcount) and subtree sizes pop
 };
 
 // Small inputs (the upper pyramid levels): the whole exclusive scan in ONE block / one launch.
-constexpr unsigned long long SCAN_SMALL_MAX = 32768;
 template <class F>
 __global__ void __launch_bounds__(1024) k_scan_small(F f, unsigned long long n, unsigned long long* out) {
     // blocked arrangement: thread t owns SCAN_ITEMS consecutive elements of each 8192-element chunk

@@ -251,3 +251,11 @@ def test_remote_slices_repeated_jobs(oracle):
     finally:
         for sb in ctxs:
             sb.close()
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_remote_slices_degenerate_and_box(oracle, world):
+    # zero-area / axis-aligned triangles on partition planes: the unit-level routing test must stay a superset
+    _check(oracle, mg.degenerate_mix(), 256, world, limit=2, remote=True)
+    _check(oracle, mg.degenerate_mix(), 64, world, remote=True)
+    _check(oracle, mg.axis_aligned_box(), 256, world, limit=3, remote=True)
