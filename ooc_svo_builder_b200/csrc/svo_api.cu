@@ -346,6 +346,7 @@ VoxJob make_voxjob(svo_ctx* c) {
         J.subset = c->sl_list.as<uint32_t>();
         J.pull_cap = c->sl_cap_blocks * 4;
         J.pull_counts = &own->count[0][c->rank];
+        J.pull_first = c->rank;
     }
     return J;
 }

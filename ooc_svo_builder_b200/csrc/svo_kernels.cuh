@@ -80,6 +80,7 @@ struct VoxJob {
     TriSegs segs;
     unsigned long long pull_cap;
     const unsigned long long* pull_counts;
+    int pull_first;                       // this rank walks the sources in the order pull_first, pull_first + 1, ... (mod n)
     // sharding: level-0 word range owned by this context and the voxel bounding box of its slab.
     // lvl[] / tileidx are biased so that they are indexed with GLOBAL word indices.
     unsigned long long w_lo, w_hi;
@@ -401,10 +402,13 @@ __global__ void __launch_bounds__(VOX_BLOCK, SVO_VOX_MINBLOCKS) k_vox_warp(VoxJo
     float* wbuf = reinterpret_cast<float*>(s_stage4) + (size_t)wid * 2 * unit_floats;
     unsigned long long count;
     if (MODE == 2) {
+        // Sources are walked in rotated order, starting with this rank's own slice: if every rank began with source 0,
+        // all of them would pull from the same GPU at the same time (its NVLink egress, ~750 GB/s, shared by N readers)
+        // and then move on together; rotated, each source serves about one reader at a time.
         segs_bases(J.segs, s_base);
         if (threadIdx.x == 0) {
             unsigned long long acc = 0;
-            for (int s = 0; s < J.segs.n; s++) { s_pref[s] = acc; acc += J.pull_counts[(size_t)s * MAX_WORLD]; }
+            for (int i = 0; i < J.segs.n; i++) { s_pref[i] = acc; acc += J.pull_counts[(size_t)((J.pull_first + i) % J.segs.n) * MAX_WORLD]; }
             s_pref[J.segs.n] = acc;
         }
         __syncthreads();
@@ -425,11 +429,12 @@ __global__ void __launch_bounds__(VOX_BLOCK, SVO_VOX_MINBLOCKS) k_vox_warp(VoxJo
     uint32_t uvalid = 0;                                    // triangles in it (<= 32)
     auto locate = [&](unsigned long long u) {
         if (MODE == 2) {
-            while (u >= s_pref[src + 1]) src++;             // a warp's tickets only grow: src moves forward
-            const uint64_t q0 = (uint64_t)J.subset[(size_t)src * J.pull_cap + (u - s_pref[src])] * UNIT;
-            const uint64_t nseg = s_base[src + 1] - s_base[src];
-            uptr = J.segs.ptr[src] + q0 * J.fpt;
-            ufirst = s_base[src] + q0;
+            while (u >= s_pref[src + 1]) src++;             // a warp's tickets only grow: src (position in the rotated order) moves forward
+            const int r = (J.pull_first + src) % J.segs.n;  // the source rank
+            const uint64_t q0 = (uint64_t)J.subset[(size_t)r * J.pull_cap + (u - s_pref[src])] * UNIT;
+            const uint64_t nseg = s_base[r + 1] - s_base[r];
+            uptr = J.segs.ptr[r] + q0 * J.fpt;
+            ufirst = s_base[r] + q0;
             uvalid = (uint32_t)(nseg - q0 < UNIT ? nseg - q0 : UNIT);
         } else {
             const uint64_t q0 = J.q_begin + u * UNIT;
