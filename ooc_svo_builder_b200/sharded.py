@@ -211,41 +211,74 @@ class DistributedBuilder:
 
     def enable_dispatch(self, capacity_tris: int, fpt: int):
         """Allocates the inbox, exchanges CUDA IPC handles with the peers (once) and maps their inboxes:
-        afterwards triangle records travel GPU -> GPU as NVLink stores issued by our own kernel."""
+        afterwards triangle records travel GPU -> GPU as NVLink stores issued by our own kernel. Raises on every
+        rank if any rank fails."""
         from .api import ipc_export, ipc_open
-        inbox, ctrl = self.sb.dispatch_create(capacity_tris, fpt)
-        mine = (ipc_export(inbox), ipc_export(ctrl))
+        inbox = ctrl = mine = err = None
+        try:
+            inbox, ctrl = self.sb.dispatch_create(capacity_tris, fpt)
+            mine = (ipc_export(inbox), ipc_export(ctrl))
+        except Exception as e:      # noqa: BLE001
+            err = e
         handles = [None] * self.world
         self.dist.all_gather_object(handles, mine)
         ib, cb = [], []
-        self._opened = []
-        for r, (hi, hc) in enumerate(handles):
-            if r == self.rank:
-                ib.append(inbox); cb.append(ctrl)
-            else:
-                a, b = ipc_open(hi), ipc_open(hc)
-                self._opened += [a, b]
-                ib.append(a); cb.append(b)
-        self.sb.dispatch_attach(ib, cb)
+        self._opened = getattr(self, "_opened", [])
+        if err is None and all(h is not None for h in handles):
+            try:
+                for r, (hi, hc) in enumerate(handles):
+                    if r == self.rank:
+                        ib.append(inbox); cb.append(ctrl)
+                    else:
+                        a, b = ipc_open(hi), ipc_open(hc)
+                        self._opened += [a, b]
+                        ib.append(a); cb.append(b)
+                self.sb.dispatch_attach(ib, cb)
+            except Exception as e:      # noqa: BLE001
+                err = e
+        elif err is None:
+            err = RuntimeError("a peer rank could not create its inbox")
+        if not self._agree(err is None):
+            raise RuntimeError("triangle dispatch unavailable: %s" % (err if err is not None else "a peer rank failed"))
         self.dist.barrier()
 
+    def _agree(self, ok: bool) -> bool:
+        """True iff every rank reports ok (one tiny all-reduce; keeps the ranks in step when one of them fails)."""
+        t = self.torch.tensor([1 if ok else 0], dtype=self.torch.int32, device="cuda:%d" % self.device)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN)
+        return bool(int(t))
+
     def enable_slices(self, capacity_tris: int, fpt: int, n_total: int):
-        """Remote staging: allocates the slice / list / control buffers, exchanges CUDA IPC handles with the peers
-        (once) and maps theirs. Afterwards the voxelizer stages triangle blocks straight from the owners' HBM."""
+        """Remote staging: allocates this rank's window, exchanges CUDA IPC handles with the peers (once) and maps
+        theirs. Afterwards the voxelizer stages triangle blocks straight from the owners' HBM. Raises on EVERY rank if
+        any rank cannot allocate or map (so that the caller can fall back collectively)."""
         from .api import ipc_export, ipc_open
-        mine = self.sb.slice_create(capacity_tris, fpt)
+        mine, handle, err = None, None, None
+        try:
+            mine = self.sb.slice_create(capacity_tris, fpt)
+            handle = ipc_export(mine)
+        except Exception as e:      # noqa: BLE001
+            err = e
         handles = [None] * self.world
-        self.dist.all_gather_object(handles, ipc_export(mine))
+        self.dist.all_gather_object(handles, handle)
         wins = []
         self._opened = getattr(self, "_opened", [])
-        for r, h in enumerate(handles):
-            if r == self.rank:
-                wins.append(mine)
-            else:
-                p = ipc_open(h)
-                self._opened.append(p)
-                wins.append(p)
-        self.sb.slice_attach(wins)
+        if err is None and all(h is not None for h in handles):
+            try:
+                for r, h in enumerate(handles):
+                    if r == self.rank:
+                        wins.append(mine)
+                    else:
+                        p = ipc_open(h)
+                        self._opened.append(p)
+                        wins.append(p)
+                self.sb.slice_attach(wins)
+            except Exception as e:      # noqa: BLE001
+                err = e
+        elif err is None:
+            err = RuntimeError("a peer rank could not create its window")
+        if not self._agree(err is None):
+            raise RuntimeError("remote staging unavailable: %s" % (err if err is not None else "a peer rank failed"))
         self.n_total = n_total
         self.sliced = True
         self.dist.barrier()
