@@ -54,7 +54,18 @@ enum { EV_UP0, EV_UP1, EV_PART0, EV_PART1, EV_VOX0, EV_VOX1, EV_BUILD0, EV_EMIT0
 
 }  // namespace
 
+namespace {
+// SVO_TIMELINE=1: host wall-clock stamps (us since the stamp named "partition") printed at the end of every build
+struct Timeline {
+    bool on = false; int n = 0; const char* name[32]; double t[32];
+    static double now() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3; }
+    void stamp(const char* w) { if (on && n < 32) { name[n] = w; t[n++] = now(); } }
+    void dump() { if (!on) return; for (int i = 0; i < n; i++) fprintf(stderr, "%s %.1f%s", name[i], t[i] - t[0], i + 1 < n ? " | " : "\n"); n = 0; }
+};
+}  // namespace
+
 struct svo_ctx {
+    Timeline tl;
     int device = 0;
     int sm_count = 148;
     cudaStream_t stream = nullptr;
@@ -183,13 +194,7 @@ int fail(svo_ctx* c, int code, const std::string& msg) {
         CK(cudaGetLastError());                                                                    \
     } while (0)
 
-// SVO_TIMELINE=1: host wall-clock stamps (us since the stamp named "partition") printed at the end of every build
-struct Timeline {
-    bool on = false; int n = 0; const char* name[32]; double t[32];
-    static double now() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3; }
-    void stamp(const char* w) { if (on && n < 32) { name[n] = w; t[n++] = now(); } }
-    void dump() { if (!on) return; for (int i = 0; i < n; i++) fprintf(stderr, "%s %.1f%s", name[i], t[i] - t[0], i + 1 < n ? " | " : "\n"); n = 0; }
-} g_tl;
+
 
 inline unsigned blocks_for(ull n, unsigned per) { return (unsigned)((n + per - 1) / per); }
 
@@ -649,7 +654,7 @@ int svo_partition(svo_ctx* c, const svo_params* params, uint64_t* n_partitions, 
     CK(cudaSetDevice(c->device));
     c->voxelized = c->built = false;
     c->launches = 0;
-    g_tl.on = getenv("SVO_TIMELINE") != nullptr; g_tl.n = 0; g_tl.stamp("partition");
+    c->tl.on = getenv("SVO_TIMELINE") != nullptr; c->tl.n = 0; c->tl.stamp("partition");
     rc = derive_grid(c, params);
     if (rc) return rc;
     c->h_part_counts.assign(c->P, 0);
@@ -819,11 +824,11 @@ int svo_voxelize(svo_ctx* c) {
     CK(c->queue[1].ensure(qbytes));
     mark(c, EV_VOX0);
     c->dense_clean = false;
-    g_tl.stamp("vox_launch");
+    c->tl.stamp("vox_launch");
     rc = launch_voxelizer<false>(c);
     if (rc) return rc;
     mark(c, EV_VOX1);
-    g_tl.stamp("vox_launched");
+    c->tl.stamp("vox_launched");
     c->voxelized = true;
     c->built = false;
     return SVO_OK;
@@ -877,9 +882,9 @@ static int build_phase_a(svo_ctx* c, ull* table) {
         k_level_counts<<<grid, 256, 0, c->stream>>>((ull* const*)c->d_lvlptrs.p, c->d_nwords.as<ull>(), J, c->d_counts.as<ull>()); LAUNCHED();
     }
     CK(cudaMemcpyAsync(c->h_pinned, c->d_counts.p, MAX_LEVELS * sizeof(ull), cudaMemcpyDeviceToHost, c->stream));
-    g_tl.stamp("sync1_wait");
+    c->tl.stamp("sync1_wait");
     CK(cudaStreamSynchronize(c->stream));
-    g_tl.stamp("sync1_done");
+    c->tl.stamp("sync1_done");
     for (int j = 0; j <= J; j++) {
         int rc = alloc_level(c, c->lv[j], c->h_pinned[j], want_pl, levels);
         if (rc) return rc;
@@ -954,7 +959,7 @@ static int build_phase_a(svo_ctx* c, ull* table) {
         }
     }
     mark(c, EV_CMP1);
-    g_tl.stamp("phaseA_launched");
+    c->tl.stamp("phaseA_launched");
     c->phase_a_done = true;
     return SVO_OK;
 }
@@ -1143,9 +1148,9 @@ static int build_phase_b(svo_ctx* c, const ull* table) {
     if (levels) CK(cudaMemcpyAsync(c->h_pinned + 34, topL.pi.as<ull>() + topL.n, sizeof(ull), cudaMemcpyDeviceToHost, c->stream));
     if (want_pl) CK(cudaMemcpyAsync(c->h_pinned + 35, topL.pl.as<ull>() + topL.n, sizeof(ull), cudaMemcpyDeviceToHost, c->stream));
     if (!spec) {
-        g_tl.stamp("sync2_wait");
+        c->tl.stamp("sync2_wait");
         CK(cudaStreamSynchronize(c->stream));
-        g_tl.stamp("sync2_done");
+        c->tl.stamp("sync2_done");
         c->n_voxels_local = c->h_pinned[32];
         c->n_voxels = c->n_voxels_local;
         const ull s_top = c->h_pinned[33];
@@ -1315,10 +1320,10 @@ static int build_phase_b(svo_ctx* c, const ull* table) {
     }
     // queue statistics
     CK(cudaMemcpyAsync(c->h_pinned + 40, c->qcount.p, 4 * sizeof(ull), cudaMemcpyDeviceToHost, c->stream));
-    g_tl.stamp("sync3_wait");
+    c->tl.stamp("sync3_wait");
     CK(cudaStreamSynchronize(c->stream));
-    g_tl.stamp("sync3_done");
-    g_tl.dump();
+    c->tl.stamp("sync3_done");
+    c->tl.dump();
     c->phase_a_done = false;
     if (c->h_pinned[48]) {
         CK(cudaMemsetAsync(&((SliceCtrl*)c->sl_ctrl.p)->error, 0, sizeof(ull), c->stream));
