@@ -190,6 +190,21 @@ int svo_shard_count(svo_ctx* ctx, uint64_t* dev_table);
 int svo_shard_emit(svo_ctx* ctx, const uint64_t* dev_table, uint64_t* n_voxels, uint64_t* n_nodes, uint64_t* n_data);
 int svo_shard_ranges(svo_ctx* ctx, uint64_t* node_lo, uint64_t* node_hi, uint64_t* data_lo, uint64_t* data_hi);
 
+/* The host-side merge svo_shard_emit performs, as a pure function (no GPU, no context): from the summed table of a job
+ * it derives the global counts, rank `rank`'s range of the .octreenodes file and the records of the shared upper octree
+ * levels that fall into that range (rec_pos[i] = file position, rec_words[3i..3i+2] = the 24-byte record, octree_io.h:62-66).
+ * For callers that size or pre-allocate the output files before emission, and for CPU tests of the exchange protocol.
+ * rec_pos / rec_words may be NULL (counts only). Errors: svo_last_error(NULL). */
+typedef struct svo_shard_layout {
+    uint64_t n_voxels, n_nodes;          /* global: "Total amount of voxels", .octree n_nodes          */
+    uint64_t node_lo, node_hi;           /* this rank's records of .octreenodes                          */
+    uint64_t leaf_offset;                /* voxels in the slabs of lower ranks (payload: data index offset) */
+    uint64_t n_voxels_local;             /* voxels in this rank's slab                                    */
+    uint64_t n_upper_records;            /* shared-level records inside [node_lo, node_hi)               */
+} svo_shard_layout;
+int svo_shard_layout_from_table(const svo_params* params, int rank, int world, const uint64_t* host_table, uint64_t n_u64,
+                                svo_shard_layout* out, uint64_t* rec_pos, uint64_t* rec_words, uint64_t rec_capacity);
+
 /* ---- multi-GPU: triangle dispatch over NVLink peer memory (copying alternative) --
  *
  * For callers that want every rank to end up with a private, compact copy of

@@ -32,7 +32,7 @@ ABI_SYMBOLS = [
     "svo_shard_dispatch_create", "svo_shard_dispatch_attach", "svo_shard_dispatch_count", "svo_shard_dispatch_send",
     "svo_shard_dispatch_finish", "svo_ipc_export", "svo_ipc_open", "svo_ipc_close",
     "svo_shard_slice_create", "svo_shard_slice_attach", "svo_shard_slice_upload", "svo_shard_slice_publish", "svo_shard_slice_fence",
-    "svo_shard_exchange",
+    "svo_shard_exchange", "svo_shard_layout_from_table",
     "svo_run", "svo_get_stats", "svo_synchronize", "svo_host_alloc", "svo_host_free",
 ]
 
@@ -62,6 +62,11 @@ class Stats(C.Structure):
 
     def as_dict(self) -> dict:
         return {n: getattr(self, n) for n, _ in self._fields_ if n != "reserved"}
+
+
+class ShardLayout(C.Structure):
+    _fields_ = [("n_voxels", C.c_uint64), ("n_nodes", C.c_uint64), ("node_lo", C.c_uint64), ("node_hi", C.c_uint64),
+                ("leaf_offset", C.c_uint64), ("n_voxels_local", C.c_uint64), ("n_upper_records", C.c_uint64)]
 
 
 _lib = None
@@ -110,6 +115,8 @@ def load_library(path: str | None = None):
     L.svo_shard_slice_create.restype = i32; L.svo_shard_slice_create.argtypes = [vp, u64, i32, C.POINTER(vp)]
     L.svo_shard_slice_attach.restype = i32; L.svo_shard_slice_attach.argtypes = [vp, C.POINTER(vp)]
     L.svo_shard_exchange.restype = i32; L.svo_shard_exchange.argtypes = [vp, vp]
+    L.svo_shard_layout_from_table.restype = i32
+    L.svo_shard_layout_from_table.argtypes = [C.POINTER(Params), i32, i32, vp, u64, C.POINTER(ShardLayout), vp, vp, u64]
     L.svo_shard_slice_upload.restype = i32; L.svo_shard_slice_upload.argtypes = [vp, vp, u64]
     L.svo_shard_slice_publish.restype = i32; L.svo_shard_slice_publish.argtypes = [vp, C.POINTER(Params), u64]
     L.svo_shard_slice_fence.restype = i32; L.svo_shard_slice_fence.argtypes = [vp]
@@ -145,6 +152,24 @@ def ipc_open(handle: bytes) -> int:
 
 def ipc_close(dev_ptr: int) -> None:
     load_library().svo_ipc_close(dev_ptr)
+
+
+def shard_layout_from_table(params: Params, rank: int, world: int, table: np.ndarray):
+    """svo_shard_layout_from_table: the host-side merge of the sharded build as a pure function (no GPU).
+    Returns (layout dict, rec_pos uint64[n], rec_words uint64[n, 3])."""
+    L = load_library()
+    table = np.ascontiguousarray(table).view(np.uint64)
+    out = ShardLayout()
+    rc = L.svo_shard_layout_from_table(C.byref(params), rank, world, table.ctypes.data, table.size, C.byref(out), None, None, 0)
+    if rc != 0:
+        raise SvoError(rc, (L.svo_last_error(None) or b"").decode())
+    n = out.n_upper_records
+    pos = np.zeros(max(n, 1), dtype=np.uint64)
+    words = np.zeros((max(n, 1), 3), dtype=np.uint64)
+    rc = L.svo_shard_layout_from_table(C.byref(params), rank, world, table.ctypes.data, table.size, C.byref(out), pos.ctypes.data, words.ctypes.data, n)
+    if rc != 0:
+        raise SvoError(rc, (L.svo_last_error(None) or b"").decode())
+    return {k: getattr(out, k) for k, _ in ShardLayout._fields_}, pos[:n], words[:n]
 
 
 def estimate_partitions(gridsize: int, memory_limit_mb: int) -> int:

@@ -971,14 +971,13 @@ static int build_phase_a(svo_ctx* c, ull* table) {
 // (few) upper-level records that fall into that range. Same formulas as k_emit_upper.
 // ---------------------------------------------------------------------------
 static inline ull h_lowmask(int n) { return n >= 64 ? ~0ULL : ((1ULL << n) - 1ULL); }
-static int shard_host_merge(svo_ctx* c, const ull* table) {
+// Pure host arithmetic (no CUDA): T = the summed table, geometry from derive_grid / setup_geometry. Fills the global counts,
+// this rank's file range and leaf offsets, the bases of its own level-J tiles (h_ownbase) and the upper-level records that
+// fall into its range (h_rpos / h_rrec). Also behind svo_shard_layout_from_table, which the CPU tests check against the oracle.
+static void shard_merge_compute(svo_ctx* c, const ull* T) {
     const int J = c->J, top = c->nl - 1;
     const ull WJ = c->WJ;
     const bool d_even = (c->D % 2) == 0;
-    c->h_table.resize((size_t)WJ * 4);
-    CK(cudaMemcpyAsync(c->h_table.data(), table, (size_t)WJ * 4 * sizeof(ull), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    const ull* T = c->h_table.data();
     std::vector<std::vector<ull>> M(top + 1), S(top + 1), B(top + 1);
     M[J].resize(WJ); S[J].resize(WJ); B[J].assign(WJ, 0);
     ull leaves_total = 0;
@@ -1037,7 +1036,6 @@ static int shard_host_merge(svo_ctx* c, const ull* table) {
         if (e < wj0) c->leaf_offset += T[4 * e + 2];
         else if (e < wj1) { c->h_ownbase.push_back(B[J][e]); c->n_voxels_local += T[4 * e + 2]; }
     }
-    if (c->h_ownbase.size() != c->lv[J].n) return fail(c, SVO_E_INVALID, "sharded merge: table does not match this rank's tiles (was the table summed over all ranks?)");
     auto first_base_from = [&](ull e0) -> ull { for (ull e = e0; e < WJ; e++) if (M[J][e]) return B[J][e]; return c->n_nodes; };
     c->node_lo = c->rank == 0 ? 0 : first_base_from(wj0);
     c->node_hi = c->rank == c->world - 1 ? c->n_nodes : first_base_from(wj1);
@@ -1050,6 +1048,16 @@ static int shard_host_merge(svo_ctx* c, const ull* table) {
         }
     }
     c->n_upper_records = c->h_rpos.size();
+}
+
+static int shard_host_merge(svo_ctx* c, const ull* table) {
+    const int J = c->J;
+    const ull WJ = c->WJ;
+    c->h_table.resize((size_t)WJ * 4);
+    CK(cudaMemcpyAsync(c->h_table.data(), table, (size_t)WJ * 4 * sizeof(ull), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    shard_merge_compute(c, c->h_table.data());
+    if (c->h_ownbase.size() != c->lv[J].n) return fail(c, SVO_E_INVALID, "sharded merge: table does not match this rank's tiles (was the table summed over all ranks?)");
     if (!c->h_ownbase.empty())
         CK(cudaMemcpyAsync(c->lv[J].base.p, c->h_ownbase.data(), c->h_ownbase.size() * sizeof(ull), cudaMemcpyHostToDevice, c->stream));
     if (c->n_upper_records) {
@@ -1767,6 +1775,35 @@ int svo_shard_slice_publish(svo_ctx* c, const svo_params* params, uint64_t n_tot
     c->dispatched = false;
     c->sliced = true;
     c->partitioned = c->voxelized = c->built = false;
+    return SVO_OK;
+}
+
+int svo_shard_layout_from_table(const svo_params* params, int rank, int world, const uint64_t* host_table, uint64_t n_u64,
+                                svo_shard_layout* out, uint64_t* rec_pos, uint64_t* rec_words, uint64_t rec_capacity) {
+    if (!params || !host_table || !out) return fail(nullptr, SVO_E_INVALID, "svo_shard_layout_from_table: NULL argument");
+    if (world < 1 || rank < 0 || rank >= world || (world & (world - 1)) != 0)
+        return fail(nullptr, SVO_E_INVALID, "shard world size must be a power of two and 0 <= rank < world");
+    svo_ctx tmp;                                   // geometry only: no CUDA call is made on it
+    svo_ctx* c = &tmp;
+    memset(c->nwords, 0, sizeof c->nwords);
+    memset(c->bias, 0, sizeof c->bias);
+    int rc = validate_params(c, params);
+    if (rc == SVO_OK) { c->world = world; c->rank = rank; rc = derive_grid(c, params); }
+    if (rc == SVO_OK) rc = setup_geometry(c);
+    if (rc != SVO_OK) return fail(nullptr, rc, tmp.err);
+    if (n_u64 != c->WJ * 4) return fail(nullptr, SVO_E_RANGE, "table size does not match svo_shard_table_size for this geometry");
+    shard_merge_compute(c, (const ull*)host_table);
+    out->n_voxels = c->n_voxels; out->n_nodes = c->n_nodes;
+    out->node_lo = c->node_lo; out->node_hi = c->node_hi;
+    out->leaf_offset = c->leaf_offset; out->n_voxels_local = c->n_voxels_local;
+    out->n_upper_records = c->n_upper_records;
+    if (rec_pos && rec_words) {
+        if (rec_capacity < c->n_upper_records) return fail(nullptr, SVO_E_RANGE, "rec_capacity is smaller than n_upper_records");
+        for (ull i = 0; i < c->n_upper_records; i++) {
+            rec_pos[i] = c->h_rpos[i];
+            for (int q = 0; q < 3; q++) rec_words[3 * i + q] = c->h_rrec[3 * i + q];
+        }
+    }
     return SVO_OK;
 }
 

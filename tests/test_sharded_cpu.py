@@ -106,3 +106,58 @@ def test_slices_tile_the_triangle_file(T, world):
     assert all(x[1] == y[0] for x, y in zip(b, b[1:]))
     cap = (T + world - 1) // world
     assert all(0 <= hi - lo <= cap for lo, hi in b)
+
+
+def _codes_from_octree(nodes: bytes, gridsize: int) -> np.ndarray:
+    """Ascending Morton codes of the leaves of an .octreenodes image (root = last record, octree_io.h:62-66, Node.h:13-65)."""
+    rec = np.frombuffer(nodes, dtype=np.uint8).reshape(-1, 24)
+    base = rec[:, 8:16].copy().view(np.uint64).reshape(-1)
+    off = rec[:, 16:24].copy().view(np.int8)
+    D = int(np.log2(gridsize))
+    out = []
+    stack = [(len(rec) - 1, 0, 0)]
+    while stack:
+        i, depth, prefix = stack.pop()
+        if depth == D:
+            out.append(prefix)
+            continue
+        for ch in range(8):
+            if off[i, ch] >= 0:
+                stack.append((int(base[i]) + int(off[i, ch]), depth + 1, prefix * 8 + ch))
+    return np.array(sorted(out), dtype=np.uint64)
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+@pytest.mark.parametrize("case", ["ico_g64_p1", "soup_g128_p1", "soup_g256_p8", "ico_g32_odd"])
+def test_host_merge_against_the_oracle(oracle, world, case):
+    """The merge of the shared upper levels (svo_shard_emit's host part, exposed as svo_shard_layout_from_table) needs no
+    GPU: feed it the table built from the oracle's voxels and compare the counts, the per-rank file ranges and every
+    upper-level record it produces with the oracle's .octreenodes image, byte for byte."""
+    from ooc_svo_builder_b200 import SvoBuilder, estimate_partitions
+    from ooc_svo_builder_b200.api import shard_layout_from_table
+    mesh, g, limit = {"ico_g64_p1": (mg.icosphere(3), 64, 2048), "soup_g128_p1": (mg.random_soup(500, seed=2, large_frac=0.02), 128, 2048),
+                      "soup_g256_p8": (mg.random_soup(600, seed=5, large_frac=0.02), 256, 2), "ico_g32_odd": (mg.icosphere(2), 32, 2048)}[case]
+    P = estimate_partitions(g, limit)
+    want = oracle.build(mesh.tris, mesh.length, g, memory_limit_mb=limit)
+    codes = _codes_from_octree(want.nodes, g)          # the voxels of THIS build (with P > 1 they depend on the partitioning, SURVEY F5)
+    assert codes.size == want.n_voxels
+    if P == 1:
+        assert (codes == oracle.voxelize(mesh.tris, mesh.length, g)).all()
+    try:
+        plans = [sharded.plan(g, P, world, r) for r in range(world)]
+    except ValueError:
+        pytest.skip("grid too small for this many shards")
+    merged = sharded.merge_tables([sharded.subtree_table_from_codes(codes, g, p) for p in plans])
+    prm = SvoBuilder.make_params(mesh.length, g, False, limit)
+    want_nodes = np.frombuffer(want.nodes, dtype=np.uint64).reshape(-1, 3)
+    pos_end, seen = 0, 0
+    for r in range(world):
+        lay, rpos, rwords = shard_layout_from_table(prm, r, world, merged)
+        assert lay["n_voxels"] == want.n_voxels and lay["n_nodes"] == want.n_nodes
+        assert lay["node_lo"] == pos_end or lay["node_lo"] == lay["node_hi"]
+        pos_end = max(pos_end, lay["node_hi"])
+        assert ((rpos >= lay["node_lo"]) & (rpos < lay["node_hi"])).all()
+        assert (want_nodes[rpos.astype(np.int64)] == rwords).all(), "an upper-level record differs from the oracle's node file"
+        seen += len(rpos)
+    assert pos_end == want.n_nodes
+    assert seen > 0
