@@ -63,9 +63,21 @@ def build_cli(force: bool = False) -> list[str]:
     return outs
 
 
+def build_tools(force: bool = False) -> list[str]:
+    """Stand-alone CUDA tools (not part of the product): the NVLink staging microbenchmark."""
+    src = os.path.join(ROOT, "tools", "native", "p2p_probe.cu")
+    out = os.path.join(ROOT, "tools", "native", "p2p_probe")
+    if not os.path.exists(src):
+        return []
+    if force or not _newer(out, [src]):
+        _run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-o", out, src])
+    return [out]
+
+
 def build_all(force: bool = False) -> None:
     build_library(force)
     build_cli(force)
+    build_tools(force)
 
 
 if __name__ == "__main__":

@@ -71,9 +71,19 @@ ok = (n_nodes == want.n_nodes) and (int(merged[2::4].sum()) == want.n_voxels)
 own = (np.flatnonzero(mine[0::4]) >= p.own_entries[0]).all() and (np.flatnonzero(mine[0::4]) < p.own_entries[1]).all()
 gathered = [None] * world
 dist.all_gather_object(gathered, mine)
+# ... and its own range of the node file with the library's host-side merge (no GPU involved)
+from ooc_svo_builder_b200 import SvoBuilder
+from ooc_svo_builder_b200.api import shard_layout_from_table
+lay, rpos, rwords = shard_layout_from_table(SvoBuilder.make_params(mesh.length, g, False), rank, world, merged)
+want_nodes = np.frombuffer(want.nodes, dtype=np.uint64).reshape(-1, 3)
+rec_ok = bool((want_nodes[rpos.astype(np.int64)] == rwords).all())
+ranges = [None] * world
+dist.all_gather_object(ranges, (lay["node_lo"], lay["node_hi"], lay["n_nodes"], rec_ok))
 if rank == 0:
     ref = sharded.merge_tables(gathered)
-    print(json.dumps({{"ok": bool(ok and own and (ref == merged).all()), "n_nodes": n_nodes, "want": want.n_nodes}}))
+    tiled = ranges[0][0] == 0 and all(a[1] == b[0] for a, b in zip(ranges, ranges[1:])) and ranges[-1][1] == want.n_nodes
+    print(json.dumps({{"ok": bool(ok and own and (ref == merged).all() and tiled and all(r[3] and r[2] == want.n_nodes for r in ranges)),
+                      "n_nodes": n_nodes, "want": want.n_nodes, "ranges": ranges}}))
 dist.destroy_process_group()
 """
 
