@@ -11,6 +11,10 @@
 //   * compact tile lists per level (key, mask, child prefix, subtree-size prefix,
 //     file base), built top-down from the pyramid, so every pass after the
 //     voxelizer is O(occupied), never O(grid).
+// Kernels in this file: voxelizer (k_vox_warp, k_vox_small, k_vox_queued), partitioner (k_bin, k_owner_filter), scans
+// (k_scan_small, k_scan_lookback), pyramid compaction (k_level_counts, k_compact_top, k_expand, k_fused_down / _up),
+// emission (k_fused_emit, k_emit_upper, k_emit_leaf, k_emit_leaf_levels, k_levels_data, k_payload), clean-up
+// (k_sparse_clear_all). The multi-GPU exchange kernels are in svo_dispatch.cuh.
 #pragma once
 #include "svo_device.cuh"
 
@@ -233,11 +237,13 @@ __device__ __forceinline__ void emit_window(const VoxJob& J, int wx, int wy, int
 }
 
 // ---------------------------------------------------------------------------
-// Voxelizer, small bounding boxes: one thread per triangle/partition pair.
+// Voxelizer, small bounding boxes: one lane per triangle/partition pair.
 // OWNER = false: fill the bit-grid and route bigger pairs to the queues.
 // OWNER = true : payload owner pass over the same pairs (queues already built).
-// Identity lists (P == 1) stage the block's triangle records through shared
-// memory with float4 loads; gathered lists read the vertices directly.
+// vox_small_body is the per-warp work; two kernels drive it:
+//   k_vox_warp  (default) persistent warps, 32-triangle units, per-warp bulk-copy staging, ticket scheduling
+//   k_vox_small block-granular: a block stages 128 records through shared memory with float4 loads (identity
+//               lists), or reads the vertices of gathered per-partition lists directly
 // ---------------------------------------------------------------------------
 // Everything after the vertices are in registers: enumerate the triangle's partitions, classify the clamped
 // boxes, route big ones to the queues, voxelize small ones. Must be called by whole warps.
