@@ -171,3 +171,22 @@ def test_host_merge_against_the_oracle(oracle, world, case):
         seen += len(rpos)
     assert pos_end == want.n_nodes
     assert seen > 0
+
+
+def test_host_merge_rejects_bad_arguments():
+    from ooc_svo_builder_b200 import SvoBuilder, SvoError
+    from ooc_svo_builder_b200.api import shard_layout_from_table
+    prm = SvoBuilder.make_params(2.0, 64, False)
+    p = sharded.plan(64, 1, 2, 0)
+    good = np.zeros(p.table_entries * 4, dtype=np.int64)
+    lay, rpos, _ = shard_layout_from_table(prm, 0, 2, good)                   # empty grid: one null root, on rank 0
+    assert lay["n_voxels"] == 0 and lay["n_nodes"] == 1 and (lay["node_lo"], lay["node_hi"]) == (0, 1) and len(rpos) == 0
+    lay1, _, _ = shard_layout_from_table(prm, 1, 2, good)
+    assert (lay1["node_lo"], lay1["node_hi"]) == (1, 1)
+    for bad in (lambda: shard_layout_from_table(prm, 0, 3, good),             # world must be a power of two
+                lambda: shard_layout_from_table(prm, 2, 2, good),             # rank out of range
+                lambda: shard_layout_from_table(prm, 0, 2, good[:-4]),        # table of the wrong size
+                lambda: shard_layout_from_table(SvoBuilder.make_params(2.0, 4, False), 0, 8, good),          # grid too small for 8 shards
+                lambda: shard_layout_from_table(SvoBuilder.make_params(2.0, 64, False, levels=True), 0, 2, good)):   # -levels is not sharded
+        with pytest.raises(SvoError):
+            bad()
