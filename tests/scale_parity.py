@@ -3,7 +3,7 @@
 reference CLI (oracle/_ref, CPU, 1 thread) and our CLI (ooc_svo_builder_b200/bin, B200) on the same files and
 compares the three output files byte for byte. Prints wall-clock times of both processes (file IO included).
 
-    python tools/scale_parity.py c3 c4
+    python tests/scale_parity.py c3 c4
 """
 import hashlib
 import json

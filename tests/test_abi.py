@@ -53,10 +53,11 @@ def test_compute_fails_loudly_without_gpu():
 
 
 def test_product_never_imports_the_oracle():
-    # the oracle is test infrastructure: nothing under the package may reference it
-    pkg = os.path.join(ROOT, "ooc_svo_builder_b200")
-    for d, _, files in os.walk(pkg):
+    # the oracle is test infrastructure: nothing under the package, the tools or the public header may reference it
+    for top in ("ooc_svo_builder_b200", "tools", "include"):
+      for d, _, files in os.walk(os.path.join(ROOT, top)):
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 txt = open(os.path.join(d, f), errors="ignore").read()
-                assert "liboracle" not in txt and "svo_oracle" not in txt and "from oracle" not in txt and "import oracle" not in txt, os.path.join(d, f)
+                assert ("liboracle" not in txt and "svo_oracle" not in txt and "from oracle" not in txt and "import oracle" not in txt
+                        and '"oracle"' not in txt), os.path.join(d, f)
