@@ -8,14 +8,16 @@ sparse clear that re-arms the bit-grid) over the workload.  N = 1 runs
 BASELINE.json configs[1]: `svo_builder_binary -s 1024` on a synthetic 2 M-triangle
 displaced sphere.  N > 1 (torchrun, one rank per GPU) runs the sharded path: a
 (2*1024)^3 grid whose 8 logical partitions are 1024^3 each; N of the octants hold
-one displaced sphere each, rank r voxelizes and builds the partitions it owns,
-the subtree sizes are all-gathered over NCCL and the shared upper levels are
-merged (weak scaling: per-GPU work fixed).
+one displaced sphere each; every rank holds 1/N of the triangle file, voxelizes
+(staging the records it needs from the owning GPU's HBM over NVLink) and builds the
+partitions it owns, the subtree table is exchanged over peer memory and the shared
+upper levels are merged (weak scaling: per-GPU work fixed).
 
 `value` is triangles/s with inputs resident in HBM; `e2e` is the same metric
 through the C-ABI call svo_run() with HOST buffers (H2D + D2H inside the timed
 region).  The reference arm (--impl reference) times the unmodified reference
-CPU binary from oracle/_ref (1 thread: the reference is single threaded).
+CPU binary from oracle/_ref (1 thread: the reference is single threaded) on the
+same workload as our arm at the given N.
 """
 from __future__ import annotations
 
@@ -163,14 +165,22 @@ def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    mesh = make_mesh()
-    tps, vps, info = run_reference_cpu(mesh, GRID, max(1, args.steps), max(0, min(args.warmup, 1)))
+    workload, grid = WORKLOAD, GRID
+    if args.gpus > 1:
+        # the same workload our arm runs at N GPUs (weak scaling: N spheres in the octants of a 2048^3 grid, 8 partitions)
+        from ooc_svo_builder_b200 import meshgen, sharded
+        tris, grid, length = sharded.bench_mesh(args.gpus, SPHERE_N)
+        mesh = meshgen.Mesh(tris, length)
+        workload = sharded.bench_workload(args.gpus)
+    else:
+        mesh = make_mesh()
+    tps, vps, info = run_reference_cpu(mesh, grid, max(1, args.steps), max(0, min(args.warmup, 1)))
     line = {
         "impl": "reference", "metric": METRIC, "value": tps, "unit": UNIT, "n_gpus": args.gpus, "steps": info["runs"],
         "warmup": min(args.warmup, 1), "ms_per_step": info["mean_s"] * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "voxels_per_s": vps,
-        "config": {"workload": WORKLOAD, "gridsize": GRID, "n_triangles": mesh.n_triangles, "n_voxels": info["n_voxels"]},
+        "config": {"workload": workload, "gridsize": grid, "n_triangles": mesh.n_triangles, "n_voxels": info["n_voxels"]},
         "cpu_baseline": {"value": tps, "unit": UNIT, "cores": 1, "kind": info["kind"], "sample": info["sample"], "host_cores": info["host_cores"]},
         "e2e": {"value": tps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }

@@ -373,30 +373,44 @@ def node_count_from_codes(codes: np.ndarray, gridsize: int) -> int:
 # bench.py --gpus N (N > 1): weak scaling of the sharded path
 # ----------------------------------------------------------------------------
 
-def bench(args, rank, world, local, dist, peak, peak_src, ClockSampler):
-    import json
-    import torch
-    from . import meshgen
-    from bench import METRIC, UNIT, SPHERE_N
+BENCH_GRID = 2048                             # 8 logical partitions of 1024^3 (default -l 2048)
+BENCH_LENGTH = 2.0
 
-    G = 2048                                  # 8 logical partitions of 1024^3 (default -l 2048)
+
+def bench_mesh(world: int, sphere_n: int):
+    """The weak-scaling workload of `bench.py --gpus N` (both arms): one displaced sphere per populated octant of a
+    2048^3 grid. File order: the i-th sphere of the file lies in the octant that rank i+1 owns, so with every rank
+    holding the i-th slice of the file ALL triangle records cross NVLink (nothing is local by construction).
+    Returns (tris (T, 9) float32, gridsize, bbox length)."""
+    from . import meshgen
     octants = {2: [0, 4], 4: [0, 2, 4, 6], 8: list(range(8))}[world]
-    base = meshgen.displaced_sphere(SPHERE_N, SPHERE_N, seed=1, length=1.0)       # one sphere per populated octant
-    # File order: the i-th sphere of the file lies in the octant that rank i+1 owns, so with every rank holding the
-    # i-th slice of the file ALL triangle records cross NVLink (nothing is local by construction).
+    base = meshgen.displaced_sphere(sphere_n, sphere_n, seed=1, length=1.0)
     parts = []
     for i in range(world):
         o = octants[(i + 1) % world]
         off = np.array([(o & 1), (o >> 1) & 1, (o >> 2) & 1], dtype=np.float32)
         t = base.tris.reshape(-1, 3, 3) + off
         parts.append(t.reshape(-1, 9))
-    tris = np.ascontiguousarray(np.concatenate(parts), dtype=np.float32)
+    return np.ascontiguousarray(np.concatenate(parts), dtype=np.float32), BENCH_GRID, BENCH_LENGTH
+
+
+def bench_workload(world: int) -> str:
+    return ("svo_builder_binary -s 2048 (8 logical partitions of 1024^3), one 2M-triangle displaced sphere in each of %d octants" % world)
+
+
+def bench(args, rank, world, local, dist, peak, peak_src, ClockSampler):
+    import json
+    import torch
+    from . import meshgen
+    from bench import METRIC, UNIT, SPHERE_N
+
+    tris, G, length = bench_mesh(world, SPHERE_N)
     T = tris.shape[0]
     lo_t, hi_t = slice_bounds(T, world, rank)
     db = DistributedBuilder(dist, local)
     stream = torch.cuda.Stream()
     db.set_stream(stream)
-    prm = SvoBuilder.make_params(2.0, G, False)
+    prm = SvoBuilder.make_params(length, G, False)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     # Input path (SVO_BENCH_INPUT): "remote" (default) = remote staging of triangle slices over NVLink peer memory;
     # "dispatch" = copying all-to-all of triangle records into peer inboxes; "replicated" = every rank holds the whole
@@ -506,15 +520,16 @@ def bench(args, rank, world, local, dist, peak, peak_src, ClockSampler):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "voxels_per_s": nv / (ms_per_step * 1e-3),
-            "config": {"workload": "svo_builder_binary -s 2048 (8 logical partitions of 1024^3), one 2M-triangle displaced sphere in each of "
-                                   "%d octants, partitions sharded over %d B200; each rank starts with 1/%d of the triangle file in HBM; %s; "
-                                   "NCCL all-reduce of the subtree table" % (
-                                       world, world, world,
+            "config": {"workload": bench_workload(world) + ", partitions sharded over %d B200; each rank starts with 1/%d of the triangle file in "
+                                   "HBM; %s; subtree table exchanged %s" % (
+                                       world, world,
                                        {"remote": "remote staging: the voxelizer kernel reads the triangle blocks it needs straight from the owner's HBM "
                                                   "with NVLink loads (no copy), file ordered so that every record crosses NVLink",
                                         "dispatch": "triangle dispatch = our own all-to-all kernel storing records into peer HBM over NVLink, file ordered "
                                                     "so that every record crosses NVLink",
-                                        "replicated": "every rank holds the whole mesh"}[mode]),
+                                        "replicated": "every rank holds the whole mesh"}[mode],
+                                       "over NVLink peer memory (our own kernels)" if (mode == "remote" and os.environ.get("SVO_TABLE_EXCHANGE", "peer") == "peer")
+                                       else "with an NCCL all-reduce"),
                        "triangle_input": mode,
                        "gridsize": G, "n_triangles": T, "n_voxels": nv, "n_nodes": nn, "partitions": 8,
                        "l2": "flushed between timed iterations (256 MB write)", "parallelism": "partition-sharded x%d" % world},
