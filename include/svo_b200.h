@@ -28,6 +28,7 @@ extern "C" {
 #define SVO_E_CUDA        2   /* CUDA runtime error or no usable device            */
 #define SVO_E_NOMEM       3   /* device or host allocation failed                  */
 #define SVO_E_RANGE       4   /* destination buffer too small / range out of bounds*/
+#define SVO_E_RETRY       5   /* sharded build only: repeat svo_shard_count / _exchange / _emit (see svo_shard_emit)   */
 
 /* main.cpp:23 `enum ColorType`, selected by `-c` (main.cpp:152-178). */
 #define SVO_COLOR_MODEL   0
@@ -183,7 +184,17 @@ int svo_fetch_voxel_codes(svo_ctx* ctx, uint64_t* dst, uint64_t capacity, uint64
  *   svo_shard_ranges                  [node_lo, node_hi) / [data_lo, data_hi): the records this
  *                                     context holds; svo_fetch_* take global record positions
  *                                     inside these ranges. The ranges of all ranks tile the files.
- * -levels is not supported on the sharded path yet (SVO_E_INVALID). */
+ * -levels is not supported on the sharded path yet (SVO_E_INVALID).
+ *
+ * SVO_E_RETRY. From its second job on a context builds speculatively: tile lists and node buffer keep the
+ * capacities of the previous job and nothing waits for the host between svo_voxelize and the end of
+ * svo_shard_emit. When the table goes through svo_shard_exchange (peer memory) and some rank's tile lists
+ * turn out too small, that rank has no table entries to offer; it says so inside the exchange, and EVERY
+ * rank's svo_shard_emit returns SVO_E_RETRY in that step. All ranks then repeat svo_shard_count ->
+ * svo_shard_exchange -> svo_shard_emit (no new svo_voxelize: the voxelized grids are kept); the ranks that
+ * overflowed take a sized build. Local builds are speculative only on contexts whose previous job used
+ * svo_shard_exchange (such a context is expected to keep using it); with the caller's own collective builds
+ * are always sized and SVO_E_RETRY never occurs. */
 int svo_shard_configure(svo_ctx* ctx, int rank, int world);
 int svo_shard_table_size(svo_ctx* ctx, uint64_t* n_u64);
 int svo_shard_count(svo_ctx* ctx, uint64_t* dev_table);

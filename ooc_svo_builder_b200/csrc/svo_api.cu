@@ -3,6 +3,7 @@
 // point needs a compute-capability 10.x device.
 #include "../../include/svo_b200.h"
 #include "svo_kernels.cuh"
+#include "svo_build.cuh"
 #include "svo_dispatch.cuh"
 
 #include <cmath>
@@ -43,7 +44,7 @@ struct LevelBufs {
         Level L;
         L.key = key.as<ull>(); L.mask = mask.as<ull>(); L.fc = fc.as<ull>(); L.ps = ps.as<ull>(); L.base = base.as<ull>();
         L.pi = pi.as<ull>(); L.pl = pl.as<ull>(); L.ibase = ibase.as<ull>(); L.cache = cache.as<float>();
-        L.n = n;
+        L.n = n; L.np = nullptr; L.cap = n;
         return L;
     }
 };
@@ -116,6 +117,14 @@ struct svo_ctx {
     DevBuf lb_state, lb_ticket;
     ull lb_epoch = 0, lb_tickets = 0;
 
+    // device-driven build (svo_build.cuh): counts live in a device-resident BuildInfo; list capacities are remembered
+    // from the previous build so that a steady-state build needs no host read-back before the final one
+    DevBuf info_buf, merge_scratch, merge_rpos, merge_rrec;
+    BuildInfo* h_info = nullptr;       // pinned copy
+    bool fast = false, spec = false, fast_caps_ok = false;
+    int jB = 1;                        // levels 1..jB are scanned by k_dense_scan, jB+1..J by k_small_levels
+    ull fcap[MAX_LEVELS];              // entries the tile lists of each level hold
+
     // outputs
     DevBuf nodes, data, owner, tileidx, codes;
     uint64_t n_voxels = 0, n_nodes = 0, n_data = 0;
@@ -164,7 +173,9 @@ struct svo_ctx {
     uint32_t* peer_list[MAX_WORLD];
     SliceCtrl* peer_slctrl[MAX_WORLD];
     bool sl_attached = false, sliced = false, filter_attr_set = false;
-    ull sl_epoch = 0;
+    ull sl_epoch = 0, xchg_epoch = 0;
+    bool exchanged_by_peer_memory = false;   // the table of this job went through svo_shard_exchange (poison-aware)
+    bool uses_peer_exchange = false;         // ... and so did an earlier job of this context: local builds may be speculative
     SliceJob sj;
 
     svo_stats stats;
@@ -210,42 +221,39 @@ float span(svo_ctx* c, int a, int b) {
 }
 
 // state of the single-pass scans: persistent, epoch-tagged (no clearing between launches)
-int lookback_prepare(svo_ctx* c, ull nt, int nv) {
-    const size_t need = (size_t)(nt + 1) * nv * sizeof(ull);
+int lookback_prepare(svo_ctx* c, ull nt) {
+    const size_t need = (size_t)(nt + 1) * LB_STATE * sizeof(ull);
     if (need > c->lb_state.cap) {
         CK(c->lb_state.ensure(need));
         CK(cudaMemsetAsync(c->lb_state.p, 0, c->lb_state.cap, c->stream));
-        c->lb_epoch = 0;
     }
     if (!c->lb_ticket.p) {
         CK(c->lb_ticket.ensure(sizeof(ull)));
         CK(cudaMemsetAsync(c->lb_ticket.p, 0, sizeof(ull), c->stream));
         c->lb_tickets = 0;
     }
-    if (++c->lb_epoch >= 0xffff) {           // 16-bit epoch: start over with a clean state array
-        CK(cudaMemsetAsync(c->lb_state.p, 0, c->lb_state.cap, c->stream));
-        c->lb_epoch = 1;
-    }
+    ++c->lb_epoch;                           // 62 bits: never wraps
     return SVO_OK;
 }
 
 constexpr ull SCAN_ONE_BLOCK_MAX = 4096;     // up to here one block is faster than the look-back chain
 
+// Exclusive scan of f over [0, n) into out[0..n]. np != NULL: the count lives on the device (n is the capacity the grid is sized for).
 template <class F>
-int exscan(svo_ctx* c, F f, ull n, ull* out) {
+int exscan(svo_ctx* c, F f, ull n, ull* out, const ull* np = nullptr, BuildInfo* info = nullptr) {
     if (n == 0) {
         CK(cudaMemsetAsync(out, 0, sizeof(ull), c->stream));
         return SVO_OK;
     }
     if (n <= SCAN_ONE_BLOCK_MAX) {
-        k_scan_small<<<1, 1024, 0, c->stream>>>(f, n, out); LAUNCHED();
+        k_scan_small<<<1, 1024, 0, c->stream>>>(f, n, np, out, info); LAUNCHED();
         return SVO_OK;
     }
     const ull nt = (n + LB_TILE - 1) / LB_TILE;
-    int rc = lookback_prepare(c, nt, 1);
+    int rc = lookback_prepare(c, nt);
     if (rc) return rc;
     OneValue<F> g{ f };
-    k_scan_lookback<1><<<(unsigned)nt, LB_THREADS, 0, c->stream>>>(g, n, out, (ull*)nullptr, c->lb_state.as<ull>(), c->lb_ticket.as<ull>(), c->lb_tickets, c->lb_epoch); LAUNCHED();
+    k_scan_lookback<1><<<(unsigned)nt, LB_THREADS, 0, c->stream>>>(g, n, np, out, (ull*)nullptr, c->lb_state.as<ull>(), c->lb_ticket.as<ull>(), c->lb_tickets, c->lb_epoch, info); LAUNCHED();
     c->lb_tickets += nt;
     return SVO_OK;
 }
@@ -258,10 +266,10 @@ int exscan_level0(svo_ctx* c, const ull* mask, ull n, ull* fc, ull* ps) {
         return SVO_OK;
     }
     const ull nt = (n + LB_TILE - 1) / LB_TILE;
-    int rc = lookback_prepare(c, nt, 2);
+    int rc = lookback_prepare(c, nt);
     if (rc) return rc;
     BrickPrefixes g{ mask };
-    k_scan_lookback<2><<<(unsigned)nt, LB_THREADS, 0, c->stream>>>(g, n, fc, ps, c->lb_state.as<ull>(), c->lb_ticket.as<ull>(), c->lb_tickets, c->lb_epoch); LAUNCHED();
+    k_scan_lookback<2><<<(unsigned)nt, LB_THREADS, 0, c->stream>>>(g, n, (const ull*)nullptr, fc, ps, c->lb_state.as<ull>(), c->lb_ticket.as<ull>(), c->lb_tickets, c->lb_epoch, (BuildInfo*)nullptr); LAUNCHED();
     c->lb_tickets += nt;
     return SVO_OK;
 }
@@ -271,7 +279,9 @@ int ilog2u(uint64_t v) { int r = -1; while (v) { v >>= 1; r++; } return r; }
 // Allocates (and zeroes) the dense pyramid for the current geometry (gridsize, shard).
 int ensure_pyramid(svo_ctx* c) {
     const uint64_t g = c->prm.gridsize;
-    const uint64_t geom_key = (g << 16) | ((uint64_t)c->world << 8) | (uint64_t)c->rank;
+    // everything nwords[] depends on: gridsize, shard layout (world, rank) and the chunk depth / top local level (which
+    // change with -l on a sharded context)
+    const uint64_t geom_key = (g << 32) | ((uint64_t)c->dc << 24) | ((uint64_t)c->J << 16) | ((uint64_t)c->world << 8) | (uint64_t)c->rank;
     if (c->dense_grid != geom_key) {
         size_t total = 0;
         for (int j = 0; j < c->nl; j++) total += (size_t)c->nwords[j] * 8;
@@ -299,7 +309,7 @@ int ensure_pyramid(svo_ctx* c) {
         CK(cudaStreamSynchronize(c->stream));      // ptrs / nwords are stack / member memory
     }
     if (!c->dense_clean) {
-        for (int j = 0; j <= c->J; j++) CK(cudaMemsetAsync(c->dense[j].p, 0, (size_t)c->nwords[j] * 8, c->stream));
+        for (int j = 0; j < c->nl; j++) CK(cudaMemsetAsync(c->dense[j].p, 0, (size_t)c->nwords[j] * 8, c->stream));
         c->dense_clean = true;
     }
     return SVO_OK;
@@ -456,12 +466,14 @@ int svo_ctx_create(int device, svo_ctx** out) {
     memset(&n->prm, 0, sizeof n->prm);
     memset(n->nwords, 0, sizeof n->nwords);
     memset(n->bias, 0, sizeof n->bias);
+    memset(n->fcap, 0, sizeof n->fcap);
     for (int i = 0; i < EV_COUNT; i++) n->ev_set[i] = false;
     c = n;
     cudaError_t e2 = cudaStreamCreateWithFlags(&n->own_stream, cudaStreamNonBlocking);
     n->stream = n->own_stream;
     for (int i = 0; i < EV_COUNT && e2 == cudaSuccess; i++) e2 = cudaEventCreate(&n->ev[i]);
     if (e2 == cudaSuccess) e2 = cudaHostAlloc((void**)&n->h_pinned, 64 * sizeof(ull), cudaHostAllocDefault);
+    if (e2 == cudaSuccess) e2 = cudaHostAlloc((void**)&n->h_info, sizeof(BuildInfo), cudaHostAllocDefault);
     if (e2 != cudaSuccess) {
         std::string m = std::string("context setup: ") + cudaGetErrorString(e2);
         delete n;
@@ -496,6 +508,9 @@ void svo_ctx_destroy(svo_ctx* c) {
     for (int i = 0; i < EV_COUNT; i++) cudaEventDestroy(c->ev[i]);
     for (int i = 0; i < 2; i++) if (c->up_ev[i]) cudaEventDestroy(c->up_ev[i]);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
+    if (c->h_info) cudaFreeHost(c->h_info);
+    c->info_buf.release(); c->merge_scratch.release(); c->merge_rpos.release(); c->merge_rrec.release();
+    c->d_rpos.release(); c->d_rrec.release();
     cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -875,6 +890,10 @@ static int build_phase_a(svo_ctx* c, ull* table) {
     const bool want_pl = levels;                        // leaf-count prefixes: only the -levels data indices need them
     c->want_pl = want_pl;
     mark(c, EV_BUILD0);
+    // the voxelizer maintains dense levels 0 and 1 only: rebuild the levels above from level 1
+    for (int j = 1; j < J; j++) {
+        k_pyramid_up<<<blocks_for(c->nwords[j], 256), 256, 0, c->stream>>>(c->dense[j].as<ull>(), c->nwords[j], c->bias[j], c->dense[j + 1].as<ull>() - c->bias[j + 1]); LAUNCHED();
+    }
     // ---- sync #1: how many non-zero words does every local level hold? ----
     CK(cudaMemsetAsync(c->d_counts.p, 0, MAX_LEVELS * sizeof(ull), c->stream));
     {
@@ -954,7 +973,7 @@ static int build_phase_a(svo_ctx* c, ull* table) {
             Tf.key = c->lv[J].key.as<ull>(); Tf.mask = c->lv[J].mask.as<ull>(); Tf.ps = c->lv[J].ps.as<ull>();
             Tf.pi = levels ? c->lv[J].pi.as<ull>() : nullptr;
             for (int j = 0; j <= J; j++) Tf.fc[j] = c->lv[j].fc.as<ull>();
-            Tf.n = c->lv[J].n; Tf.J = J; Tf.table = table;
+            Tf.n = c->lv[J].n; Tf.J = J; Tf.table = table;      // np, info: NULL (memset)
             k_table_fill<<<blocks_for(c->lv[J].n, 256), 256, 0, c->stream>>>(Tf); LAUNCHED();
         }
     }
@@ -1069,6 +1088,60 @@ static int shard_host_merge(svo_ctx* c, const ull* table) {
     return SVO_OK;
 }
 
+// Tail of every build: tell the peers this rank is done reading, fetch the queue statistics, the one final
+// synchronisation, stage times. `post_done`: false when the caller may still have to repeat the build (the peers'
+// slices must stay readable).
+static int finish_build_sync(svo_ctx* c, bool post_done) {
+    c->h_pinned[48] = 0;
+    if (c->sliced && post_done) {
+        // this rank has finished reading its peers' slices and lists: they may be rewritten for the next job
+        k_slice_post<<<1, MAX_WORLD, 0, c->stream>>>(c->sj, 1); LAUNCHED();
+    }
+    if (c->sliced) CK(cudaMemcpyAsync(c->h_pinned + 48, &((SliceCtrl*)c->sl_ctrl.p)->error, sizeof(ull), cudaMemcpyDeviceToHost, c->stream));
+    // queue statistics
+    CK(cudaMemcpyAsync(c->h_pinned + 40, c->qcount.p, 4 * sizeof(ull), cudaMemcpyDeviceToHost, c->stream));
+    c->tl.stamp("sync3_wait");
+    CK(cudaStreamSynchronize(c->stream));
+    c->tl.stamp("sync3_done");
+    if (c->h_pinned[48]) {
+        CK(cudaMemsetAsync(&((SliceCtrl*)c->sl_ctrl.p)->error, 0, sizeof(ull), c->stream));
+        c->dense_clean = false;
+        return fail(c, SVO_E_CUDA, "remote triangle slices: timed out waiting for a peer rank");
+    }
+    if (c->h_pinned[43]) {
+        c->dense_clean = false;
+        return fail(c, SVO_E_NOMEM, "work queue overflow: too many medium/large triangle-partition pairs for inline enumeration; "
+                                    "set SVO_PARTITION_LISTS=1 to build exact per-partition lists");
+    }
+    return SVO_OK;
+}
+static void finish_build_stats(svo_ctx* c) {
+    c->tl.dump();
+    c->phase_a_done = false;
+    c->built = true;
+    c->voxelized = false;            // the pyramid has been consumed (and cleared): a new build needs a new svo_voxelize
+    c->stats.n_partitions = c->P;
+    // inline enumeration does not count pairs on the device; the sum of the per-partition counts is known when they were requested
+    c->stats.n_pairs = (c->P > 1 && !c->use_lists) ? c->n_pairs : c->q_end - c->q_begin;
+    c->stats.n_voxels = c->n_voxels; c->stats.n_nodes = c->n_nodes; c->stats.n_data = c->n_data;
+    c->stats.n_medium = c->h_pinned[40]; c->stats.n_large = c->h_pinned[41];
+    const ull queued = c->stats.n_medium + c->stats.n_large;
+    c->stats.n_small = c->stats.n_pairs >= queued ? c->stats.n_pairs - queued : 0;   // n_pairs is 0 when the pairs were not counted
+    c->stats.ms_upload = span(c, EV_UP0, EV_UP1);
+    c->stats.ms_partition = span(c, EV_PART0, EV_PART1);
+    c->stats.ms_voxelize = span(c, EV_VOX0, EV_VOX1);
+    c->stats.ms_build = span(c, EV_BUILD0, EV_BUILD1);
+    c->stats.ms_emit = span(c, EV_EMIT0, EV_EMIT1);
+    c->stats.ms_clear = span(c, EV_CLR0, EV_CLR1);
+    c->stats.ms_download = 0.f;
+    c->stats.ms_vox_small = span(c, EV_VS0, EV_VS1);
+    c->stats.ms_emit_leaf = c->lv[0].n ? span(c, EV_EL0, EV_EL1) : 0.f;
+    c->stats.ms_compact = span(c, EV_BUILD0, EV_CMP1);
+    c->stats.ms_peer_wait = c->sliced ? span(c, EV_PW0, EV_PW1) : 0.f;
+    c->stats.ms_dispatch = (c->dispatched || c->sliced) ? span(c, EV_DSP0, EV_DSP1) : 0.f;
+    c->stats.kernel_launches = c->launches + ((c->dispatched || c->sliced) ? c->dispatch_launches : 0);
+}
+
 // ---------------------------------------------------------------------------
 // Build, phase B: replicated upper levels from the (summed) table, file bases top-down, emission.
 // ---------------------------------------------------------------------------
@@ -1143,19 +1216,12 @@ static int build_phase_b(svo_ctx* c, const ull* table) {
         }
     }
     // ---- sync #2: record counts ----
-    // Binary builds on one GPU that have a node buffer from an earlier build skip this sync: the records are emitted
-    // into the existing buffer (every write is guarded by its capacity), the counts are read back with the final sync,
-    // and only if the tree turned out larger than the buffer is the emission repeated into a bigger one.
     LevelBufs& topL = c->lv[top];
-    const ull spec_cap = c->nodes.cap / SVO_NODE_BYTES;
-    bool spec = !host_merge && !payload && !levels && c->lv[0].n > 0 && spec_cap > 0;
-    if (const char* e = getenv("SVO_SPECULATIVE_EMIT")) spec = spec && e[0] != '0';
     if (!host_merge) {
-    CK(cudaMemcpyAsync(c->h_pinned + 32, c->lv[0].fc.as<ull>() + c->lv[0].n, sizeof(ull), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaMemcpyAsync(c->h_pinned + 33, topL.ps.as<ull>() + topL.n, sizeof(ull), cudaMemcpyDeviceToHost, c->stream));
-    if (levels) CK(cudaMemcpyAsync(c->h_pinned + 34, topL.pi.as<ull>() + topL.n, sizeof(ull), cudaMemcpyDeviceToHost, c->stream));
-    if (want_pl) CK(cudaMemcpyAsync(c->h_pinned + 35, topL.pl.as<ull>() + topL.n, sizeof(ull), cudaMemcpyDeviceToHost, c->stream));
-    if (!spec) {
+        CK(cudaMemcpyAsync(c->h_pinned + 32, c->lv[0].fc.as<ull>() + c->lv[0].n, sizeof(ull), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaMemcpyAsync(c->h_pinned + 33, topL.ps.as<ull>() + topL.n, sizeof(ull), cudaMemcpyDeviceToHost, c->stream));
+        if (levels) CK(cudaMemcpyAsync(c->h_pinned + 34, topL.pi.as<ull>() + topL.n, sizeof(ull), cudaMemcpyDeviceToHost, c->stream));
+        if (want_pl) CK(cudaMemcpyAsync(c->h_pinned + 35, topL.pl.as<ull>() + topL.n, sizeof(ull), cudaMemcpyDeviceToHost, c->stream));
         c->tl.stamp("sync2_wait");
         CK(cudaStreamSynchronize(c->stream));
         c->tl.stamp("sync2_done");
@@ -1163,10 +1229,6 @@ static int build_phase_b(svo_ctx* c, const ull* table) {
         c->n_voxels = c->n_voxels_local;
         const ull s_top = c->h_pinned[33];
         c->n_nodes = c->n_voxels == 0 ? 1 : s_top + (d_even ? 1 : 0);
-    } else {
-        c->n_voxels = c->n_voxels_local = 1;        // placeholders (non-zero: lv[0].n > 0); the real counts arrive with the final sync
-        c->n_nodes = spec_cap;
-    }
     }
     c->n_data = payload ? 1 + c->n_voxels : 2;          // OctreeBuilder.cpp:25-29
     if (levels && c->n_voxels) c->n_data += c->h_pinned[34] - (d_even ? 0 : 1);   // one record per internal node (the virtual top word is no node)
@@ -1188,7 +1250,7 @@ static int build_phase_b(svo_ctx* c, const ull* table) {
     E.levels = levels ? 1 : 0;
     E.virtual_top = d_even ? 0 : 1;
     E.leaf_offset = c->leaf_offset;
-    E.pos_lo = 0; E.pos_hi = ~0ULL;
+    E.pos_lo = 0; E.pos_hi = ~0ULL; E.cap = ~0ULL;
     E.write_records = 1;
     if (!host_merge) {
         c->node_lo = 0; c->node_hi = c->n_nodes;
@@ -1201,7 +1263,7 @@ static int build_phase_b(svo_ctx* c, const ull* table) {
         if (host_merge) {
             // the shared upper levels were merged on the host: scatter the records that fall into this rank's range
             if (c->n_upper_records) {
-                k_scatter_records<<<blocks_for(c->n_upper_records, 256), 256, 0, c->stream>>>(c->d_rpos.as<ull>(), c->d_rrec.as<ull>(), c->n_upper_records, E.nodes); LAUNCHED();
+                k_scatter_records<<<blocks_for(c->n_upper_records, 256), 256, 0, c->stream>>>(c->d_rpos.as<ull>(), c->d_rrec.as<ull>(), c->n_upper_records, (const ull*)nullptr, E); LAUNCHED();
             }
             return SVO_OK;
         }
@@ -1215,8 +1277,8 @@ static int build_phase_b(svo_ctx* c, const ull* table) {
     };
     const ull n_local_nodes = c->node_hi - c->node_lo;
     CK(c->nodes.ensure((size_t)(n_local_nodes ? n_local_nodes : 1) * SVO_NODE_BYTES));
-    E.nodes = c->nodes.as<ull>() - c->node_lo * 3;
-    E.pos_lo = c->node_lo; E.pos_hi = c->node_hi;
+    E.nodes = c->nodes.as<ull>();
+    E.pos_lo = c->node_lo; E.pos_hi = c->node_hi; E.cap = n_local_nodes;
     auto emit_all = [&](void) -> int {
     if (c->n_voxels == 0) {
         // empty grid: finalizeTree pads everything and writes a null root (OctreeBuilder.cpp:36-42)
@@ -1320,65 +1382,342 @@ static int build_phase_b(svo_ctx* c, const ull* table) {
     }
     c->dense_clean = true;
     mark(c, EV_CLR1);
-    c->h_pinned[48] = 0;
-    if (c->sliced) {
-        // this rank has finished reading its peers' slices and lists: they may be rewritten for the next job
-        k_slice_post<<<1, MAX_WORLD, 0, c->stream>>>(c->sj, 1); LAUNCHED();
-        CK(cudaMemcpyAsync(c->h_pinned + 48, &((SliceCtrl*)c->sl_ctrl.p)->error, sizeof(ull), cudaMemcpyDeviceToHost, c->stream));
+    {
+        int rc = finish_build_sync(c, true);
+        if (rc) return rc;
     }
-    // queue statistics
-    CK(cudaMemcpyAsync(c->h_pinned + 40, c->qcount.p, 4 * sizeof(ull), cudaMemcpyDeviceToHost, c->stream));
-    c->tl.stamp("sync3_wait");
+    finish_build_stats(c);
+    return SVO_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Device-driven build (svo_build.cuh). Phase A: tile lists of the local levels straight from the dense pyramid, subtree
+// sizes, this rank's table entries. Phase B: merged upper levels (k_shard_merge), emission, clear.
+// In steady state (list and node-buffer capacities known from the previous build, binary mode) nothing between the
+// voxelizer launch and the final synchronisation waits for the host. The first build of a context, payload builds
+// and builds that outgrow the capacities take the same kernels with two read-backs (counts, record range).
+// ---------------------------------------------------------------------------
+static bool fast_path_applies(const svo_ctx* c) {
+    if (c->prm.generate_levels || c->J < 1) return false;
+    const char* e = getenv("SVO_BUILD_PATH");
+    return !(e && strcmp(e, "classic") == 0);
+}
+static Level fast_view(svo_ctx* c, int j) {
+    Level L = c->lv[j].view();
+    L.np = &c->info_buf.as<BuildInfo>()->count[j];
+    L.cap = c->fcap[j];
+    L.n = c->fcap[j];
+    return L;
+}
+static int read_info(svo_ctx* c, const char* stamp) {
+    CK(cudaMemcpyAsync(c->h_info, c->info_buf.p, sizeof(BuildInfo), cudaMemcpyDeviceToHost, c->stream));
+    c->tl.stamp(stamp);
     CK(cudaStreamSynchronize(c->stream));
-    c->tl.stamp("sync3_done");
-    c->tl.dump();
-    c->phase_a_done = false;
-    if (c->h_pinned[48]) {
-        CK(cudaMemsetAsync(&((SliceCtrl*)c->sl_ctrl.p)->error, 0, sizeof(ull), c->stream));
-        c->dense_clean = false;
-        return fail(c, SVO_E_CUDA, "remote triangle slices: timed out waiting for a peer rank");
-    }
-    if (spec) {
-        // the counts the skipped sync would have delivered
-        c->n_voxels_local = c->n_voxels = c->h_pinned[32];
-        c->n_nodes = c->h_pinned[33] + (d_even ? 1 : 0);
-        c->node_lo = 0; c->node_hi = c->n_nodes;
-        if (c->n_nodes > spec_cap) {
-            // the tree outgrew the buffer of the earlier build: emit again into a big enough one (the tile lists are intact)
-            CK(c->nodes.ensure((size_t)c->n_nodes * SVO_NODE_BYTES));
-            E.nodes = c->nodes.as<ull>();
-            E.pos_lo = 0; E.pos_hi = c->n_nodes;
-            int rc = emit_all();
+    return SVO_OK;
+}
+static int fast_check_info(svo_ctx* c) {
+    const ull o = c->h_info->overflow;
+    if (o & (1ULL << 40)) { c->dense_clean = false; return fail(c, SVO_E_CUDA, "octree build: a look-back scan timed out"); }
+    if (o & (1ULL << 41)) { c->dense_clean = false; return fail(c, SVO_E_INVALID, "sharded merge: table does not match this rank's tiles (was the table exchanged / summed over all ranks?)"); }
+    if (o & (1ULL << 42)) { c->dense_clean = false; return fail(c, SVO_E_RANGE, "sharded merge: upper-level record buffer too small"); }
+    return SVO_OK;
+}
+
+static int fast_phase_a(svo_ctx* c, ull* table, bool fill_table, bool force_sync) {
+    const int J = c->J;
+    const bool payload = c->prm.payload != 0;
+    c->want_pl = false;
+    c->jf = 0;
+    int jB = 1;
+    for (int j = 2; j <= J; j++) if (c->nwords[j] > SMALL_LEVEL_WORDS) jB = j;
+    c->jB = jB;
+    CK(c->info_buf.ensure(sizeof(BuildInfo)));
+    BuildInfo* dinfo = c->info_buf.as<BuildInfo>();
+    // sharded: a speculative local build that aborts leaves this rank without table entries; only the peer-memory
+    // exchange can tell the peers (poisoned flag, svo_dispatch.cuh), so other exchanges get sized builds
+    // (a context whose previous job went through svo_shard_exchange is taken to keep doing so)
+    bool spec = c->fast_caps_ok && !payload && !force_sync && c->nodes.cap > 0 && (c->world == 1 || (c->sliced && c->uses_peer_exchange));
+    c->exchanged_by_peer_memory = false;
+    if (const char* e = getenv("SVO_SPECULATIVE_BUILD")) spec = spec && e[0] != '0';
+    c->spec = spec;
+    mark(c, EV_BUILD0);
+    CK(cudaMemsetAsync(dinfo, 0, sizeof(BuildInfo), c->stream));
+    auto dense_pass = [&](int count_only) -> int {
+        for (int j = 1; j <= jB; j++) {
+            const ull nt = (c->nwords[j] + DS_TILE - 1) / DS_TILE;
+            int rc = lookback_prepare(c, nt);
             if (rc) return rc;
-            CK(cudaStreamSynchronize(c->stream));
+            DenseScanJob Dj;
+            memset(&Dj, 0, sizeof Dj);
+            Dj.dense = c->dense[j].as<ull>(); Dj.n = c->nwords[j]; Dj.bias = c->bias[j];
+            Dj.next = j < J ? c->dense[j + 1].as<ull>() - c->bias[j + 1] : nullptr;
+            Dj.key = c->lv[j].key.as<ull>(); Dj.mask = c->lv[j].mask.as<ull>(); Dj.fc = c->lv[j].fc.as<ull>();
+            Dj.cap = c->fcap[j]; Dj.cap_child = c->fcap[j - 1];
+            Dj.j = j; Dj.count_only = count_only; Dj.info = dinfo;
+            Dj.state = c->lb_state.as<ull>(); Dj.ticket = c->lb_ticket.as<ull>(); Dj.ticket_base = c->lb_tickets; Dj.epoch = c->lb_epoch;
+            k_dense_scan<<<(unsigned)nt, DS_THREADS, 0, c->stream>>>(Dj); LAUNCHED();
+            c->lb_tickets += nt;
+        }
+        if (jB < J) {
+            SmallLevelsJob S;
+            memset(&S, 0, sizeof S);
+            S.j0 = jB + 1; S.J = J; S.count_only = count_only; S.info = dinfo;
+            for (int j = jB; j <= J; j++) {
+                S.dense[j] = c->dense[j].as<ull>(); S.nwords[j] = c->nwords[j]; S.bias[j] = c->bias[j];
+                S.key[j] = c->lv[j].key.as<ull>(); S.mask[j] = c->lv[j].mask.as<ull>(); S.fc[j] = c->lv[j].fc.as<ull>();
+                S.cap[j] = c->fcap[j];
+            }
+            k_small_levels<<<1, 1024, 0, c->stream>>>(S); LAUNCHED();
+        }
+        return SVO_OK;
+    };
+    if (!spec) {
+        // ---- counts first (read-back #1), then lists of exactly the right size (+ slack for the builds to come) ----
+        int rc = dense_pass(1);
+        if (rc) return rc;
+        if ((rc = read_info(c, "sync1_wait"))) return rc;
+        c->tl.stamp("sync1_done");
+        if ((rc = fast_check_info(c))) return rc;
+        for (int j = 0; j <= J; j++) {
+            const ull n = c->h_info->count[j];
+            const ull want = n + n / 8 + 64;
+            if (want > c->fcap[j]) c->fcap[j] = want;
+        }
+        CK(cudaMemsetAsync(dinfo, 0, sizeof(BuildInfo), c->stream));
+    }
+    for (int j = 0; j <= J; j++) {
+        int rc = alloc_level(c, c->lv[j], c->fcap[j], false, false);      // no-op once the lists are large enough
+        if (rc) return rc;
+        c->lv[j].n = 0;
+    }
+    if (payload) CK(c->tileidx.ensure((size_t)c->nwords[0] * sizeof(uint32_t)));
+    int rc = dense_pass(0);
+    if (rc) return rc;
+    {   // bricks: lists, leaf ranks, subtree sizes of levels 0 and 1
+        const ull n1 = spec ? c->fcap[1] : c->h_info->count[1];
+        const ull nt = std::max<ull>((n1 + BP_TILE - 1) / BP_TILE, 1);
+        if ((rc = lookback_prepare(c, nt))) return rc;
+        BrickJob B;
+        memset(&B, 0, sizeof B);
+        B.L1 = fast_view(c, 1); B.L0 = fast_view(c, 0);
+        B.dense0 = c->dense[0].as<ull>() - c->bias[0];
+        B.tileidx = payload ? c->tileidx.as<uint32_t>() - c->bias[0] : nullptr;
+        B.info = dinfo;
+        B.state = c->lb_state.as<ull>(); B.ticket = c->lb_ticket.as<ull>(); B.ticket_base = c->lb_tickets; B.epoch = c->lb_epoch;
+        k_brick_pass<<<(unsigned)nt, BP_WARPS * 32, 0, c->stream>>>(B); LAUNCHED();
+        c->lb_tickets += nt;
+    }
+    // subtree sizes of the levels above: look-back scans for the big ones, one block for the small ones
+    for (int j = 2; j <= jB; j++) {
+        SizeOp op{ c->lv[j].mask.as<ull>(), c->lv[j].fc.as<ull>(), c->lv[j - 1].ps.as<ull>() };
+        const ull n = spec ? c->fcap[j] : c->h_info->count[j];
+        if ((rc = exscan(c, op, n, c->lv[j].ps.as<ull>(), &dinfo->count[j], dinfo))) return rc;
+    }
+    if (jB < J) {
+        FusedJob F;
+        memset(&F, 0, sizeof F);
+        for (int j = jB; j <= J; j++) { F.lv[j] = fast_view(c, j); F.lv[j].pl = nullptr; }
+        F.J = J; F.jf = jB + 1; F.E.info = dinfo;
+        k_fused_up<<<1, 1024, 0, c->stream>>>(F); LAUNCHED();
+    }
+    // ---- this rank's table entries ----
+    if (fill_table) {
+        CK(cudaMemsetAsync(table, 0, (size_t)c->WJ * 4 * sizeof(ull), c->stream));
+        TableFillJob Tf;
+        memset(&Tf, 0, sizeof Tf);
+        Tf.key = c->lv[J].key.as<ull>(); Tf.mask = c->lv[J].mask.as<ull>(); Tf.ps = c->lv[J].ps.as<ull>();
+        for (int j = 0; j <= J; j++) Tf.fc[j] = c->lv[j].fc.as<ull>();
+        Tf.n = c->fcap[J]; Tf.np = &dinfo->count[J]; Tf.J = J; Tf.table = table; Tf.info = dinfo;
+        const ull nJ = spec ? std::min<ull>(c->fcap[J], c->nwords[J]) : c->h_info->count[J];
+        if (nJ) { k_table_fill<<<blocks_for(nJ, 256), 256, 0, c->stream>>>(Tf); LAUNCHED(); }
+    }
+    mark(c, EV_CMP1);
+    c->tl.stamp("phaseA_launched");
+    c->phase_a_done = true;
+    return SVO_OK;
+}
+
+static int fast_phase_b(svo_ctx* c, ull* table) {
+    const int J = c->J, nl = c->nl, top = nl - 1, jB = c->jB;
+    const bool payload = c->prm.payload != 0;
+    const bool d_even = (c->D % 2) == 0;
+    BuildInfo* dinfo = c->info_buf.as<BuildInfo>();
+    const bool spec = c->spec;
+    // ---- merged upper levels, file range of this rank, bases of its top tiles ----
+    ull n_scratch = 0, rcap = 2;
+    for (int j = J; j <= top; j++) n_scratch += (j == J ? c->WJ : c->nwords[j]);
+    for (int j = J + 1; j <= top; j++) rcap += c->nwords[j] * 73;
+    CK(c->merge_scratch.ensure((size_t)n_scratch * 3 * sizeof(ull)));
+    CK(c->merge_rpos.ensure((size_t)rcap * sizeof(ull)));
+    CK(c->merge_rrec.ensure((size_t)rcap * 3 * sizeof(ull)));
+    {
+        MergeJob Mj;
+        memset(&Mj, 0, sizeof Mj);
+        Mj.table = table; Mj.WJ = c->WJ;
+        Mj.J = J; Mj.top = top; Mj.d_even = d_even ? 1 : 0; Mj.rank = c->rank; Mj.world = c->world;
+        ull off = 0;
+        for (int j = J; j <= top; j++) {
+            Mj.nW[j] = j == J ? c->WJ : c->nwords[j];
+            Mj.M[j] = c->merge_scratch.as<ull>() + off; Mj.S[j] = Mj.M[j] + n_scratch; Mj.B[j] = Mj.S[j] + n_scratch;
+            off += Mj.nW[j];
+        }
+        Mj.wj0 = c->bias[J]; Mj.wj1 = c->bias[J] + c->nwords[J];
+        Mj.rpos = c->merge_rpos.as<ull>(); Mj.rrec = c->merge_rrec.as<ull>(); Mj.rcap = rcap;
+        Mj.keyJ = c->lv[J].key.as<ull>(); Mj.baseJ = c->lv[J].base.as<ull>(); Mj.capJ = c->fcap[J];
+        Mj.info = dinfo;
+        Mj.nodes_cap = spec ? c->nodes.cap / SVO_NODE_BYTES : ~0ULL;
+        k_shard_merge<<<1, 1024, 0, c->stream>>>(Mj); LAUNCHED();
+    }
+    if (!spec) {
+        // ---- read-back #2: record counts and this rank's range ----
+        int rc = read_info(c, "sync2_wait");
+        if (rc) return rc;
+        c->tl.stamp("sync2_done");
+        if ((rc = fast_check_info(c))) return rc;
+        if (c->h_info->overflow) { c->dense_clean = false; return fail(c, SVO_E_CUDA, "octree build: list capacity exceeded in a sized build (internal error)"); }
+        const ull n_local = c->h_info->node_hi - c->h_info->node_lo;
+        CK(c->nodes.ensure((size_t)(n_local ? n_local : 1) * SVO_NODE_BYTES));
+    }
+    EmitJob E;
+    memset(&E, 0, sizeof E);
+    E.nodes = c->nodes.as<ull>();
+    E.cap = c->nodes.cap / SVO_NODE_BYTES;
+    E.info = dinfo;
+    E.leaf_data_mode = payload ? 1 : 0;
+    E.virtual_top = d_even ? 0 : 1;
+    E.write_records = 1;
+    mark(c, EV_EMIT0);
+    k_scatter_records<<<(unsigned)std::min<ull>(blocks_for(rcap, 256), 64), 256, 0, c->stream>>>(c->merge_rpos.as<ull>(), c->merge_rrec.as<ull>(), rcap, &dinfo->n_upper, E); LAUNCHED();
+    auto launch_n = [&](int j) -> ull { return spec ? std::min<ull>(c->fcap[j], c->nwords[j]) : c->h_info->count[j]; };
+    const int root_level_here = (J == top) && d_even;
+    // the top levels with at most a few hundred tiles are emitted by ONE block (each level writes the bases of the
+    // next), everything below by one multi-block launch per level
+    int jE = jB;
+    for (int j = jB + 1; j <= J; j++) if (c->nwords[j] > 256) jE = j;
+    if (jE < J) {
+        FusedJob F;
+        memset(&F, 0, sizeof F);
+        for (int j = jE; j <= J; j++) F.lv[j] = fast_view(c, j);
+        F.J = J; F.jf = jE;
+        F.E = E; F.E.is_top = (J == top); F.E.root_here = root_level_here;
+        k_fused_emit<<<1, 1024, 0, c->stream>>>(F); LAUNCHED();
+    }
+    for (int j = jE; j >= 1; j--) {
+        const ull n = launch_n(j);
+        if (!n) continue;
+        E.is_top = (j == top);
+        E.root_here = (j == J) && root_level_here;
+        k_emit_upper<<<blocks_for(n, WARPS_PER_BLOCK), WARPS_PER_BLOCK * 32, 0, c->stream>>>(fast_view(c, j), fast_view(c, j - 1), E); LAUNCHED();
+    }
+    E.is_top = 0; E.root_here = 0;
+    mark(c, EV_EL0);
+    if (launch_n(0)) {
+        k_emit_leaf<<<blocks_for(launch_n(0), WARPS_PER_BLOCK * EMIT_TILES_PER_WARP), WARPS_PER_BLOCK * 32, 0, c->stream>>>(fast_view(c, 0), E); LAUNCHED();
+    }
+    mark(c, EV_EL1);
+    mark(c, EV_EMIT1);
+    // ---- data records ----
+    if (!payload) {
+        // 2 records, all on rank 0 (n_data is known without the counts)
+        CK(c->data.ensure(2 * SVO_DATA_BYTES));
+        static const uint32_t white[16] = { 0, 0, 0, 0, 0, 0, 0, 0,                         // record 0: NULL
+                                            0, 0, 0x3f800000u, 0x3f800000u, 0x3f800000u, 0, 0, 0 };  // record 1: white voxel
+        if (c->rank == 0) CK(cudaMemcpyAsync(c->data.p, white, sizeof white, cudaMemcpyHostToDevice, c->stream));
+    } else {
+        // payload builds are sized builds: the counts are on the host
+        c->leaf_offset = c->h_info->leaf_offset;
+        c->n_voxels_local = c->h_info->n_leaves_local;
+        c->n_voxels = c->h_info->n_voxels;
+        c->data_lo = c->rank == 0 ? 0 : 1 + c->leaf_offset;
+        c->data_hi = 1 + c->leaf_offset + c->n_voxels_local;
+        if (c->world == 1) { c->data_lo = 0; c->data_hi = 1 + c->n_voxels; }
+        const ull n_local_data = c->data_hi - c->data_lo;
+        CK(c->data.ensure((size_t)(n_local_data ? n_local_data : 1) * SVO_DATA_BYTES));
+        if (c->rank == 0) CK(cudaMemsetAsync(c->data.p, 0, SVO_DATA_BYTES, c->stream));
+        if (c->n_voxels_local) {
+            CK(c->owner.ensure((size_t)c->n_voxels_local * sizeof(uint32_t)));
+            CK(cudaMemsetAsync(c->owner.p, 0xff, (size_t)c->n_voxels_local * sizeof(uint32_t), c->stream));
+            c->lv[0].n = c->h_info->count[0];
+            int rc = launch_voxelizer<true>(c);
+            if (rc) return rc;
+            PayloadJob Pj;
+            memset(&Pj, 0, sizeof Pj);
+            Pj.tris = c->d_tris; Pj.owner = c->owner.as<uint32_t>();
+            if (c->sliced) {
+                Pj.segs.n = c->world;
+                for (int r = 0; r < c->world; r++) Pj.segs.ptr[r] = c->peer_slice[r];
+                Pj.segs.nslice = ((const SliceCtrl*)c->sl_ctrl.p)->nslice;
+            }
+            Pj.data = c->data.as<float>() - c->data_lo * 8;
+            Pj.unit_div = c->unit_div; Pj.gridsize_f = (float)c->prm.gridsize; Pj.color_mode = c->prm.color_mode;
+            Pj.levels = 0;
+            Pj.leaf_offset = c->leaf_offset;
+            k_payload<<<blocks_for(launch_n(0), WARPS_PER_BLOCK), WARPS_PER_BLOCK * 32, 0, c->stream>>>(fast_view(c, 0), Pj); LAUNCHED();
         }
     }
-    if (c->h_pinned[43]) {
-        c->dense_clean = false;
-        return fail(c, SVO_E_NOMEM, "work queue overflow: too many medium/large triangle-partition pairs for inline enumeration; "
-                                    "set SVO_PARTITION_LISTS=1 to build exact per-partition lists");
+    mark(c, EV_BUILD1);
+    // ---- leave a clean pyramid behind: zero exactly the words that were set (skipped by an aborted build) ----
+    mark(c, EV_CLR0);
+    {
+        ClearJob Cj;
+        memset(&Cj, 0, sizeof Cj);
+        for (int j = 0; j <= J; j++) { Cj.key[j] = c->lv[j].key.as<ull>(); Cj.dense[j] = c->dense[j].as<ull>() - c->bias[j]; Cj.n[j] = c->fcap[j]; }
+        Cj.info = dinfo;
+        const ull n0 = std::max<ull>(launch_n(0), 1);
+        dim3 grid((unsigned)std::min<ull>(blocks_for(n0, 256), (ull)c->sm_count * 16), (unsigned)(J + 1));
+        k_sparse_clear_all<<<grid, 256, 0, c->stream>>>(Cj); LAUNCHED();
     }
-    c->built = true;
-    c->stats.n_partitions = c->P;
-    // inline enumeration does not count pairs on the device; the sum of the per-partition counts is known when they were requested
-    c->stats.n_pairs = (c->P > 1 && !c->use_lists) ? c->n_pairs : c->q_end - c->q_begin;
-    c->stats.n_voxels = c->n_voxels; c->stats.n_nodes = c->n_nodes; c->stats.n_data = c->n_data;
-    c->stats.n_medium = c->h_pinned[40]; c->stats.n_large = c->h_pinned[41];
-    const ull queued = c->stats.n_medium + c->stats.n_large;
-    c->stats.n_small = c->stats.n_pairs >= queued ? c->stats.n_pairs - queued : 0;   // n_pairs is 0 when the pairs were not counted
-    c->stats.ms_upload = span(c, EV_UP0, EV_UP1);
-    c->stats.ms_partition = span(c, EV_PART0, EV_PART1);
-    c->stats.ms_voxelize = span(c, EV_VOX0, EV_VOX1);
-    c->stats.ms_build = span(c, EV_BUILD0, EV_BUILD1);
-    c->stats.ms_emit = span(c, EV_EMIT0, EV_EMIT1);
-    c->stats.ms_clear = span(c, EV_CLR0, EV_CLR1);
-    c->stats.ms_download = 0.f;
-    c->stats.ms_vox_small = span(c, EV_VS0, EV_VS1);
-    c->stats.ms_emit_leaf = c->lv[0].n ? span(c, EV_EL0, EV_EL1) : 0.f;
-    c->stats.ms_compact = span(c, EV_BUILD0, EV_CMP1);
-    c->stats.ms_peer_wait = c->sliced ? span(c, EV_PW0, EV_PW1) : 0.f;
-    c->stats.ms_dispatch = (c->dispatched || c->sliced) ? span(c, EV_DSP0, EV_DSP1) : 0.f;
-    c->stats.kernel_launches = c->launches + ((c->dispatched || c->sliced) ? c->dispatch_launches : 0);
+    mark(c, EV_CLR1);
+    CK(cudaMemcpyAsync(c->h_info, c->info_buf.p, sizeof(BuildInfo), cudaMemcpyDeviceToHost, c->stream));
+    return SVO_OK;
+}
+
+// One fast build, phases A (unless already done by svo_shard_count) and B, with the repeat of a speculative build that
+// outgrew its capacities. `table`: the subtree table (own entries on one GPU; complete after the exchange when sharded).
+static int fast_build(svo_ctx* c, ull* table, bool phase_a_needed) {
+    int rc;
+    if (phase_a_needed && (rc = fast_phase_a(c, table, true, false))) return rc;
+    if ((rc = fast_phase_b(c, table))) return rc;
+    // (a speculative build that has to be repeated only re-reads this rank's own pyramid and the complete table: the
+    // peers may be told right away that their slices are no longer needed)
+    if ((rc = finish_build_sync(c, true))) return rc;
+    if ((rc = fast_check_info(c))) return rc;
+    if (c->h_info->overflow && c->world > 1 && (c->h_info->overflow & ((1ULL << 43) | 0xffffffffULL))) {
+        // This rank's (bits 0..31) or a peer's (bit 43) speculative LOCAL build was aborted before the table exchange:
+        // the exchanged table is incomplete on every rank, and every rank knows (poisoned exchange flag). All of them
+        // return SVO_E_RETRY now; the pyramids are intact, the ranks that overflowed take a sized build next time.
+        if (!c->spec && !(c->h_info->overflow & (1ULL << 43))) { c->dense_clean = false; return fail(c, SVO_E_CUDA, "octree build: list capacity exceeded in a sized build (internal error)"); }
+        if (!c->exchanged_by_peer_memory) { c->dense_clean = false; return fail(c, SVO_E_CUDA, "octree build: speculative local build aborted without a poison-aware exchange (internal error)"); }
+        if (c->h_info->overflow & 0xffffffffULL) c->fast_caps_ok = false;
+        c->phase_a_done = false;
+        return fail(c, SVO_E_RETRY, "a rank's tile lists outgrew the capacities of the previous build: repeat svo_shard_count / svo_shard_exchange / svo_shard_emit (the voxelized grid is kept)");
+    }
+    if (c->h_info->overflow) {
+        if (!c->spec) { c->dense_clean = false; return fail(c, SVO_E_CUDA, "octree build: list capacity exceeded in a sized build (internal error)"); }
+        // the tree outgrew the lists / node buffer of the earlier builds: every kernel behind the detection returned at
+        // once, the pyramid is intact. Repeat with counts read back and exact sizes (the table is complete already).
+        c->fast_caps_ok = false;
+        if ((rc = fast_phase_a(c, table, c->world == 1, true))) return rc;
+        if ((rc = fast_phase_b(c, table))) return rc;
+        if ((rc = finish_build_sync(c, false))) return rc;
+        if ((rc = fast_check_info(c))) return rc;
+        if (c->h_info->overflow) { c->dense_clean = false; return fail(c, SVO_E_CUDA, "octree build: list capacity exceeded in a sized build (internal error)"); }
+    }
+    c->dense_clean = true;
+    c->fast_caps_ok = true;
+    const BuildInfo& I = *c->h_info;
+    for (int j = 0; j <= c->J; j++) c->lv[j].n = I.count[j];
+    c->n_voxels = I.n_voxels; c->n_nodes = I.n_nodes;
+    c->n_voxels_local = I.n_leaves_local; c->leaf_offset = I.leaf_offset;
+    c->node_lo = I.node_lo; c->node_hi = I.node_hi;
+    c->n_upper_records = I.n_upper;
+    const bool payload = c->prm.payload != 0;
+    c->n_data = payload ? 1 + c->n_voxels : 2;          // OctreeBuilder.cpp:25-29
+    if (!payload) {
+        c->data_lo = 0; c->data_hi = c->n_data;
+        if (c->rank != 0) c->data_lo = c->data_hi = c->n_data;
+    }
+    finish_build_stats(c);
     return SVO_OK;
 }
 
@@ -1387,12 +1726,20 @@ int svo_build(svo_ctx* c, uint64_t* n_voxels, uint64_t* n_nodes, uint64_t* n_dat
     if (!c->voxelized) return fail(c, SVO_E_INVALID, "svo_build before svo_voxelize");
     if (c->world != 1) return fail(c, SVO_E_INVALID, "sharded context: use svo_shard_count / svo_shard_emit");
     CK(cudaSetDevice(c->device));
-    const bool upper = c->J < c->nl - 1;
-    if (upper) CK(c->table_own.ensure((size_t)c->WJ * 4 * sizeof(ull)));
-    int rc = build_phase_a(c, upper ? c->table_own.as<ull>() : nullptr);
-    if (rc) return rc;
-    rc = build_phase_b(c, upper ? c->table_own.as<ull>() : nullptr);
-    if (rc) return rc;
+    c->fast = fast_path_applies(c);
+    int rc;
+    if (c->fast) {
+        CK(c->table_own.ensure((size_t)c->WJ * 4 * sizeof(ull)));
+        rc = fast_build(c, c->table_own.as<ull>(), true);
+        if (rc) return rc;
+    } else {
+        const bool upper = c->J < c->nl - 1;
+        if (upper) CK(c->table_own.ensure((size_t)c->WJ * 4 * sizeof(ull)));
+        rc = build_phase_a(c, upper ? c->table_own.as<ull>() : nullptr);
+        if (rc) return rc;
+        rc = build_phase_b(c, upper ? c->table_own.as<ull>() : nullptr);
+        if (rc) return rc;
+    }
     if (n_voxels) *n_voxels = c->n_voxels;
     if (n_nodes) *n_nodes = c->n_nodes;
     if (n_data) *n_data = c->n_data;
@@ -1411,6 +1758,8 @@ int svo_shard_count(svo_ctx* c, uint64_t* dev_table) {
     if (!c->voxelized) return fail(c, SVO_E_INVALID, "svo_shard_count before svo_voxelize");
     if (!dev_table) return fail(c, SVO_E_INVALID, "dev_table is NULL");
     CK(cudaSetDevice(c->device));
+    c->fast = fast_path_applies(c);
+    if (c->fast) return fast_phase_a(c, (ull*)dev_table, true, false);
     return build_phase_a(c, (ull*)dev_table);
 }
 
@@ -1427,10 +1776,13 @@ int svo_shard_exchange(svo_ctx* c, uint64_t* dev_table) {
     memset(&X, 0, sizeof X);
     X.src = (const ull*)dev_table;
     X.lo = c->bias[c->J] * 4ULL; X.n = c->nwords[c->J] * 4ULL;
-    X.world = c->world; X.me = c->rank; X.epoch = c->sl_epoch;
+    X.world = c->world; X.me = c->rank; X.epoch = ++c->xchg_epoch;      // every rank calls the exchange the same number of times
+    X.info = c->fast ? c->info_buf.as<BuildInfo>() : nullptr;
     for (int r = 0; r < c->world; r++) { X.xtable[r] = c->peer_xtable[r]; X.ctrl[r] = c->peer_slctrl[r]; }
     k_xchg_push<<<c->world, 256, 0, c->stream>>>(X); LAUNCHED();
-    k_slice_wait<<<1, MAX_WORLD, 0, c->stream>>>((SliceCtrl*)c->sl_ctrl.p, c->world, 2, c->sl_epoch); LAUNCHED();
+    k_xchg_wait<<<1, MAX_WORLD, 0, c->stream>>>((SliceCtrl*)c->sl_ctrl.p, c->world, c->xchg_epoch, c->fast ? c->info_buf.as<BuildInfo>() : nullptr); LAUNCHED();
+    c->exchanged_by_peer_memory = true;
+    c->uses_peer_exchange = true;
     CK(cudaMemcpyAsync(dev_table, c->sl_xtable.p, bytes, cudaMemcpyDeviceToDevice, c->stream));
     return SVO_OK;
 }
@@ -1440,7 +1792,7 @@ int svo_shard_emit(svo_ctx* c, const uint64_t* dev_table, uint64_t* n_voxels, ui
     if (!c->phase_a_done) return fail(c, SVO_E_INVALID, "svo_shard_emit before svo_shard_count");
     if (!dev_table) return fail(c, SVO_E_INVALID, "dev_table is NULL");
     CK(cudaSetDevice(c->device));
-    int rc = build_phase_b(c, (const ull*)dev_table);
+    int rc = c->fast ? fast_build(c, (ull*)dev_table, false) : build_phase_b(c, (const ull*)dev_table);
     if (rc) return rc;
     if (n_voxels) *n_voxels = c->n_voxels;
     if (n_nodes) *n_nodes = c->n_nodes;
@@ -1668,7 +2020,7 @@ int svo_shard_slice_create(svo_ctx* c, uint64_t capacity_tris, int fpt, void** d
     c->slice_cap = capacity_tris;
     c->slice_fpt = fpt;
     c->slice_n_local = 0;
-    c->sl_epoch = 0;
+    c->sl_epoch = 0; c->xchg_epoch = 0; c->uses_peer_exchange = false;
     if (dev_window) *dev_window = c->window.p;
     return SVO_OK;
 }

@@ -1,0 +1,390 @@
+// svo_build.cuh -- device-driven octree build ("fast path": no -levels, at least two pyramid levels per slab).
+//
+// Replaces OctreeBuilder::addVoxel x N + finalizeTree (src/svo_builder/OctreeBuilder.cpp:34-168) with passes that need
+// NO host read-back between them: every count lives in a device-resident BuildInfo, launch grids are sized from the
+// capacities of the previous build, and a build whose lists outgrow them aborts itself (pyramid intact) and is
+// repeated by the host with exact sizes.
+//
+//   k_dense_scan    one single-pass look-back scan over a DENSE pyramid level j >= 1 (the voxelizer maintains levels 0
+//                   and 1 with fire-and-forget reductions): compacts the non-zero words into the tile list
+//                   (key, mask, child prefix fc), sets the words' bits in dense level j+1, counts tiles and children
+//   k_small_levels  the same for all levels with <= 4096 dense words, in ONE block
+//   k_brick_pass    one warp per level-1 tile: gathers its <= 64 brick words from dense level 0, converts them to the
+//                   Morton layout, and scans (leaves, brick subtree sizes, level-1 subtree sizes) in one look-back
+//                   chain -> brick list (key, mask, leaf rank fc, size prefix ps) and the level-1 size prefix
+//   k_shard_merge   the shared upper levels from the exchanged subtree table, in one block: global counts, this
+//                   rank's file range, bases of its top tiles, the upper records inside its range
+//                   (same arithmetic as the host-side svo_shard_layout_from_table)
+#pragma once
+#include "svo_kernels.cuh"
+
+namespace svo {
+
+// Classic path (tiny grids, -levels): dense level j+1 from dense level j, one thread per word. dst is pre-biased
+// (indexed with global word indices) and clean.
+__global__ void __launch_bounds__(256) k_pyramid_up(const unsigned long long* src, unsigned long long n, unsigned long long bias, unsigned long long* dst) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (src[i] != 0ULL) {
+        const unsigned long long g = bias + i;
+        red_or(dst + (g >> 6), 1ULL << (g & 63));
+    }
+}
+
+// ---------------------------------------------------------------------------
+// k_dense_scan
+// ---------------------------------------------------------------------------
+constexpr int DS_THREADS = 256, DS_ITEMS = 8, DS_TILE = DS_THREADS * DS_ITEMS;
+constexpr unsigned long long SMALL_LEVEL_WORDS = 4096;     // dense levels up to this size are walked by k_small_levels
+
+struct DenseScanJob {
+    const unsigned long long* dense;      // the slab's dense words of level j
+    unsigned long long n, bias;           // word count; global word index = bias + i
+    unsigned long long* next;             // dense level j + 1, pre-biased (indexed with the global index >> 6); NULL at the top local level
+    unsigned long long* key; unsigned long long* mask; unsigned long long* fc;     // tile list of level j
+    unsigned long long cap, cap_child;    // capacities of the lists of level j and level j - 1
+    int j, count_only;                    // count_only: no list writes, no overflow flags (first build of a context)
+    BuildInfo* info;
+    unsigned long long* state; unsigned long long* ticket; unsigned long long ticket_base, epoch;
+};
+
+__global__ void __launch_bounds__(DS_THREADS) k_dense_scan(DenseScanJob Dj) {
+    __shared__ unsigned long long s_tile, s_prefix[2];
+    if (threadIdx.x == 0) s_tile = atomicAdd(Dj.ticket, 1ULL) - Dj.ticket_base;
+    __syncthreads();
+    const unsigned long long tile = s_tile;
+    if (tile * DS_TILE >= Dj.n || build_aborted(Dj.info)) return;
+    const unsigned long long base = tile * DS_TILE + (unsigned long long)threadIdx.x * DS_ITEMS;
+    unsigned long long w[DS_ITEMS];
+    if (base + DS_ITEMS <= Dj.n) {
+        const ulonglong2* p = reinterpret_cast<const ulonglong2*>(Dj.dense + base);      // base is a multiple of 8 words
+#pragma unroll
+        for (int i = 0; i < DS_ITEMS / 2; i++) { const ulonglong2 v = __ldcg(p + i); w[2 * i] = v.x; w[2 * i + 1] = v.y; }
+    } else {
+#pragma unroll
+        for (int i = 0; i < DS_ITEMS; i++) w[i] = base + i < Dj.n ? __ldcg(Dj.dense + base + i) : 0ULL;
+    }
+    unsigned nz = 0, pc = 0;
+#pragma unroll
+    for (int i = 0; i < DS_ITEMS; i++) { nz += w[i] != 0ULL ? 1u : 0u; pc += (unsigned)__popcll(w[i]); }
+    unsigned long long total;
+    const unsigned long long ex = block_excl_scan(((unsigned long long)pc << 16) | nz, total);    // nz <= 2048 per block
+    if (threadIdx.x < 32) {
+        const unsigned long long tot[2] = { total & 0xffffULL, total >> 16 };
+        unsigned long long pre[2];
+        lookback<2>(Dj.state, Dj.epoch, tile, tot, pre, &Dj.info->overflow);
+        if (threadIdx.x == 0) { s_prefix[0] = pre[0]; s_prefix[1] = pre[1]; }
+    }
+    __syncthreads();
+    unsigned long long at = s_prefix[0] + (ex & 0xffffULL), cp = s_prefix[1] + (ex >> 16);
+    unsigned long long up_word = ~0ULL, up_bits = 0ULL;
+#pragma unroll
+    for (int i = 0; i < DS_ITEMS; i++) {
+        if (w[i] == 0ULL) continue;
+        const unsigned long long g = Dj.bias + base + i;
+        if (!Dj.count_only && at < Dj.cap) { Dj.key[at] = g; Dj.mask[at] = w[i]; Dj.fc[at] = cp; }
+        at++;
+        cp += (unsigned)__popcll(w[i]);
+        if (Dj.next) {
+            if ((g >> 6) != up_word) { if (up_bits) red_or(Dj.next + up_word, up_bits); up_word = g >> 6; up_bits = 0ULL; }
+            up_bits |= 1ULL << (g & 63);
+        }
+    }
+    if (up_bits) red_or(Dj.next + up_word, up_bits);
+    if (threadIdx.x == 0 && (tile + 1) * DS_TILE >= Dj.n) {       // the last tile: totals
+        const unsigned long long n_tiles = s_prefix[0] + (total & 0xffffULL), n_children = s_prefix[1] + (total >> 16);
+        Dj.info->count[Dj.j] = n_tiles;
+        if (Dj.j == 1) Dj.info->count[0] = n_children;
+        if (!Dj.count_only) {
+            if (n_tiles <= Dj.cap) Dj.fc[n_tiles] = n_children;   // fc[n] = total: the lists have room for cap + 2 entries
+            if (n_tiles > Dj.cap) atomicOr(&Dj.info->overflow, 1ULL << Dj.j);
+            if (n_children > Dj.cap_child) atomicOr(&Dj.info->overflow, 1ULL << (Dj.j - 1));
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// k_small_levels: dense levels j0..J (each <= SMALL_LEVEL_WORDS words) in one block: tile list of every level and the
+// dense level above it. Dense level j0 is complete when the kernel starts (the last k_dense_scan set its bits).
+// ---------------------------------------------------------------------------
+struct SmallLevelsJob {
+    int j0, J, count_only;
+    unsigned long long* dense[MAX_LEVELS];        // local arrays (not biased)
+    unsigned long long nwords[MAX_LEVELS], bias[MAX_LEVELS];
+    unsigned long long* key[MAX_LEVELS]; unsigned long long* mask[MAX_LEVELS]; unsigned long long* fc[MAX_LEVELS];
+    unsigned long long cap[MAX_LEVELS];
+    BuildInfo* info;
+};
+__global__ void __launch_bounds__(1024) k_small_levels(SmallLevelsJob S) {
+    if (build_aborted(S.info)) return;
+    for (int j = S.j0; j <= S.J; j++) {
+        const unsigned long long n = S.nwords[j];
+        unsigned long long c_nz = 0, c_pc = 0;
+        for (unsigned long long b = 0; b < n; b += blockDim.x) {
+            const unsigned long long i = b + threadIdx.x;
+            const unsigned long long w = i < n ? __ldcg(S.dense[j] + i) : 0ULL;
+            unsigned long long total;
+            const unsigned long long ex = block_excl_scan(((unsigned long long)__popcll(w) << 32) | (w != 0ULL ? 1ULL : 0ULL), total);
+            if (w != 0ULL) {
+                const unsigned long long at = c_nz + (ex & 0xffffffffULL), g = S.bias[j] + i;
+                if (!S.count_only && at < S.cap[j]) { S.key[j][at] = g; S.mask[j][at] = w; S.fc[j][at] = c_pc + (ex >> 32); }
+                if (j < S.J) red_or(S.dense[j + 1] + ((g >> 6) - S.bias[j + 1]), 1ULL << (g & 63));
+            }
+            c_nz += total & 0xffffffffULL;
+            c_pc += total >> 32;
+        }
+        if (threadIdx.x == 0) {
+            S.info->count[j] = c_nz;
+            if (j == 1) S.info->count[0] = c_pc;
+            if (!S.count_only) {
+                if (c_nz <= S.cap[j]) S.fc[j][c_nz] = c_pc;
+                if (c_nz > S.cap[j]) atomicOr(&S.info->overflow, 1ULL << j);
+                if (c_pc > S.cap[j - 1]) atomicOr(&S.info->overflow, 1ULL << (j - 1));
+            }
+        }
+        __threadfence();
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------
+// k_brick_pass
+// ---------------------------------------------------------------------------
+constexpr int BP_WARPS = 8, BP_PER_WARP = 4, BP_TILE = BP_WARPS * BP_PER_WARP;     // level-1 tiles per block
+struct BrickJob {
+    Level L1;                             // key, mask, fc in; ps out (n + 1)
+    Level L0;                             // key, mask, fc, ps out
+    const unsigned long long* dense0;     // pre-biased: indexed with global level-0 word indices
+    uint32_t* tileidx;                    // pre-biased dense map word -> compact index (payload owner pass) or NULL
+    BuildInfo* info;
+    unsigned long long* state; unsigned long long* ticket; unsigned long long ticket_base, epoch;
+};
+__global__ void __launch_bounds__(BP_WARPS * 32) k_brick_pass(BrickJob B) {
+    __shared__ unsigned long long s_tile, s_prefix[3];
+    __shared__ unsigned s_tot[BP_TILE][3], s_ex[BP_TILE][3];
+    if (threadIdx.x == 0) s_tile = atomicAdd(B.ticket, 1ULL) - B.ticket_base;
+    __syncthreads();
+    if (build_aborted(B.info)) return;
+    const unsigned long long tile = s_tile;
+    const unsigned long long n1 = level_n(B.L1);
+    if (tile * BP_TILE >= n1) {
+        if (tile == 0 && threadIdx.x == 0) { B.L0.fc[0] = 0ULL; B.L0.ps[0] = 0ULL; B.L1.ps[0] = 0ULL; B.info->n_leaves_local = 0ULL; }
+        return;
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    unsigned long long m[BP_PER_WARP][2];         // this lane's two bricks of each tile, Morton layout
+    unsigned pre[BP_PER_WARP][2];                 // exclusive prefix inside the tile: leaves | sizes << 16
+    unsigned long long W1[BP_PER_WARP], K1[BP_PER_WARP], F1[BP_PER_WARP];
+#pragma unroll
+    for (int q = 0; q < BP_PER_WARP; q++) {
+        const unsigned long long t = tile * BP_TILE + (unsigned long long)wid * BP_PER_WARP + q;
+        W1[q] = 0ULL; K1[q] = 0ULL; F1[q] = 0ULL;
+        if (t < n1) { W1[q] = B.L1.mask[t]; K1[q] = B.L1.key[t]; F1[q] = B.L1.fc[t]; }
+        unsigned v[2];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int bit = lane + 32 * h;
+            m[q][h] = 0ULL;
+            if ((W1[q] >> bit) & 1ULL) m[q][h] = linear_to_morton64(__ldcg(B.dense0 + ((K1[q] << 6) | (unsigned long long)bit)));
+            const unsigned leaves = (unsigned)__popcll(m[q][h]);
+            v[h] = leaves | ((leaves + (unsigned)__popc(nonzero_bytes(m[q][h]))) << 16);
+        }
+        // exclusive prefix over the 64 children in bit order (bits 0..31 = half 0)
+        unsigned i0 = v[0], i1 = v[1];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned a = __shfl_up_sync(0xffffffffu, i0, d), b = __shfl_up_sync(0xffffffffu, i1, d);
+            if (lane >= d) { i0 += a; i1 += b; }
+        }
+        const unsigned t0 = __shfl_sync(0xffffffffu, i0, 31), t1 = __shfl_sync(0xffffffffu, i1, 31);
+        pre[q][0] = i0 - v[0];
+        pre[q][1] = t0 + i1 - v[1];
+        if (lane == 0) {
+            const unsigned tot = t0 + t1;              // leaves <= 4096, sizes <= 4608: no carry between the halves
+            const int s = wid * BP_PER_WARP + q;
+            s_tot[s][0] = tot & 0xffffu;
+            s_tot[s][1] = tot >> 16;
+            s_tot[s][2] = t < n1 ? (tot >> 16) + (unsigned)__popcll(W1[q]) + (unsigned)__popc(nonzero_bytes(W1[q])) : 0u;   // S of the level-1 tile
+        }
+    }
+    __syncthreads();
+    if (wid == 0) {
+        unsigned long long tot[3], prefix[3];
+        unsigned x[3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            x[c] = s_tot[lane][c];
+            unsigned inc = x[c];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const unsigned a = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += a; }
+            s_ex[lane][c] = inc - x[c];
+            tot[c] = __shfl_sync(0xffffffffu, inc, 31);
+        }
+        lookback<3>(B.state, B.epoch, tile, tot, prefix, &B.info->overflow);
+        if (lane == 0) {
+#pragma unroll
+            for (int c = 0; c < 3; c++) s_prefix[c] = prefix[c];
+            if ((tile + 1) * BP_TILE >= n1) {         // the last tile: totals behind the lists
+                const unsigned long long n0 = B.info->count[0];
+                if (n0 <= B.L0.cap) { B.L0.fc[n0] = prefix[0] + tot[0]; B.L0.ps[n0] = prefix[1] + tot[1]; }
+                B.L1.ps[n1] = prefix[2] + tot[2];
+                B.info->n_leaves_local = prefix[0] + tot[0];
+            }
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < BP_PER_WARP; q++) {
+        const unsigned long long t = tile * BP_TILE + (unsigned long long)wid * BP_PER_WARP + q;
+        if (t >= n1) continue;
+        const int s = wid * BP_PER_WARP + q;
+        const unsigned long long lp = s_prefix[0] + s_ex[s][0], sp = s_prefix[1] + s_ex[s][1];
+        if (lane == 0) B.L1.ps[t] = s_prefix[2] + s_ex[s][2];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int bit = lane + 32 * h;
+            if (!((W1[q] >> bit) & 1ULL)) continue;
+            const unsigned long long c = F1[q] + __popcll(W1[q] & lowmask(bit));
+            if (c >= B.L0.cap) continue;                   // (the overflow flag is already set by the level-1 scan)
+            const unsigned long long ck = (K1[q] << 6) | (unsigned long long)bit;
+            B.L0.key[c] = ck;
+            B.L0.mask[c] = m[q][h];
+            B.L0.fc[c] = lp + (pre[q][h] & 0xffffu);
+            B.L0.ps[c] = sp + (pre[q][h] >> 16);
+            if (B.tileidx) B.tileidx[ck] = (uint32_t)c;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// k_shard_merge: the shared upper levels (above the top local level J) from the complete subtree table
+// {mask, S, leaves, internals} per global level-J word. One block. The same arithmetic as shard_merge_compute()
+// in svo_api.cu (host, behind svo_shard_layout_from_table) and as k_emit_upper.
+// ---------------------------------------------------------------------------
+struct MergeJob {
+    const unsigned long long* table; unsigned long long WJ;
+    int J, top, d_even, rank, world;
+    unsigned long long nW[MAX_LEVELS];            // global word counts of levels J..top
+    unsigned long long wj0, wj1;                  // own entries [wj0, wj1)
+    unsigned long long* M[MAX_LEVELS]; unsigned long long* S[MAX_LEVELS]; unsigned long long* B[MAX_LEVELS];   // scratch, levels J..top
+    unsigned long long* rpos; unsigned long long* rrec; unsigned long long rcap;      // upper records inside this rank's range
+    const unsigned long long* keyJ; unsigned long long* baseJ; unsigned long long capJ; // own level-J tile list
+    BuildInfo* info;
+    unsigned long long nodes_cap;                 // capacity of the node buffer (speculative emission); ~0 when it is sized afterwards
+};
+__global__ void __launch_bounds__(1024) k_shard_merge(MergeJob Mj) {
+    __shared__ unsigned long long s_leaves, s_before, s_own, s_lo, s_hi, s_nrec, s_nodes;
+    if (build_aborted(Mj.info)) return;
+    const int J = Mj.J, top = Mj.top;
+    if (threadIdx.x == 0) { s_leaves = 0; s_before = 0; s_own = 0; s_lo = ~0ULL; s_hi = ~0ULL; s_nrec = 0; }
+    __syncthreads();
+    {   // level J: columns of the table, leaf totals
+        unsigned long long a = 0, b = 0, o = 0;
+        for (unsigned long long e = threadIdx.x; e < Mj.WJ; e += blockDim.x) {
+            const unsigned long long mk = Mj.table[4 * e], lv = Mj.table[4 * e + 2];
+            Mj.M[J][e] = mk; Mj.S[J][e] = Mj.table[4 * e + 1]; Mj.B[J][e] = 0ULL;
+            if (mk) { a += lv; if (e < Mj.wj0) b += lv; else if (e < Mj.wj1) o += lv; }
+        }
+        if (a) atomicAdd(&s_leaves, a);
+        if (b) atomicAdd(&s_before, b);
+        if (o) atomicAdd(&s_own, o);
+    }
+    __syncthreads();
+    // bottom-up: masks and subtree sizes of the upper levels
+    for (int j = J + 1; j <= top; j++) {
+        for (unsigned long long w = threadIdx.x; w < Mj.nW[j]; w += blockDim.x) {
+            unsigned long long W = 0, sz = 0;
+            for (int b = 0; b < 64; b++) {
+                const unsigned long long ch = w * 64 + b;
+                if (ch < Mj.nW[j - 1] && Mj.M[j - 1][ch]) { W |= 1ULL << b; sz += Mj.S[j - 1][ch]; }
+            }
+            if (W) sz += (unsigned long long)(__popcll(W) + __popc(nonzero_bytes(W)));
+            Mj.M[j][w] = W; Mj.S[j][w] = sz; Mj.B[j][w] = 0ULL;
+        }
+        __syncthreads();
+    }
+    const unsigned long long leaves_total = s_leaves;
+    const unsigned long long n_nodes = leaves_total == 0 ? 1ULL : Mj.S[top][0] + (Mj.d_even ? 1ULL : 0ULL);
+    // top-down: bases (pass 0), then the upper records that fall into this rank's range (pass 1)
+    for (int pass = 0; pass < 2; pass++) {
+        const unsigned long long lo = s_lo, hi = s_hi;
+        auto push = [&](unsigned long long pos, unsigned long long d1, unsigned long long d2) {
+            if (pass == 0 || pos < lo || pos >= hi) return;
+            const unsigned long long at = atomicAdd(&s_nrec, 1ULL);
+            if (at < Mj.rcap) { Mj.rpos[at] = pos; Mj.rrec[3 * at] = 0ULL; Mj.rrec[3 * at + 1] = d1; Mj.rrec[3 * at + 2] = d2; }
+        };
+        for (int j = top; j > J; j--) {
+            for (unsigned long long w = threadIdx.x; w < Mj.nW[j]; w += blockDim.x) {
+                const unsigned long long W = Mj.M[j][w];
+                if (!W) continue;
+                const unsigned long long base = Mj.B[j][w], sz = Mj.S[j][w];
+                const uint32_t nzb = nonzero_bytes(W);
+                unsigned long long acc = 0;
+                for (int k = 0; k < 8; k++) {
+                    const uint32_t byte = (uint32_t)((W >> (8 * k)) & 0xffULL);
+                    if (!byte) continue;
+                    const unsigned long long before = (unsigned long long)__popcll(W & lowmask(8 * k));
+                    for (int b = 0; b < 8; b++) if ((byte >> b) & 1u) {
+                        const unsigned long long ch = w * 64 + 8 * k + b;
+                        if (pass == 0) Mj.B[j - 1][ch] = base + acc + before;
+                        acc += Mj.S[j - 1][ch];
+                    }
+                    const unsigned long long blk = base + acc + before;
+                    unsigned long long r = 0;
+                    for (int b = 0; b < 8; b++) if ((byte >> b) & 1u) {
+                        const unsigned long long ch = w * 64 + 8 * k + b;
+                        const uint32_t gnz = nonzero_bytes(Mj.M[j - 1][ch]);
+                        push(blk + r++, Mj.B[j - 1][ch] + Mj.S[j - 1][ch] - (unsigned long long)__popc(gnz), child_offsets(gnz));
+                    }
+                    push(base + sz - (unsigned long long)__popc(nzb) + (unsigned long long)__popc(nzb & ((1u << k) - 1u)), blk, child_offsets(byte));
+                }
+                if (j == top && Mj.d_even) push(sz, base + sz - (unsigned long long)__popc(nzb), child_offsets(nzb));
+            }
+            __syncthreads();
+        }
+        if (pass == 0) {
+            // this rank's range: from the base of its first tile to the base of the first tile of the next rank
+            unsigned long long lo_c = ~0ULL, hi_c = ~0ULL;
+            for (unsigned long long e = threadIdx.x; e < Mj.WJ; e += blockDim.x) {
+                if (!Mj.M[J][e]) continue;
+                const unsigned long long bse = Mj.B[J][e];
+                if (e >= Mj.wj0 && bse < lo_c) lo_c = bse;
+                if (e >= Mj.wj1 && bse < hi_c) hi_c = bse;
+            }
+            if (lo_c != ~0ULL) atomicMin(&s_lo, lo_c);
+            if (hi_c != ~0ULL) atomicMin(&s_hi, hi_c);
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                unsigned long long nlo = Mj.rank == 0 ? 0ULL : (s_lo == ~0ULL ? n_nodes : s_lo);
+                unsigned long long nhi = Mj.rank == Mj.world - 1 ? n_nodes : (s_hi == ~0ULL ? n_nodes : s_hi);
+                if (leaves_total == 0) { nlo = Mj.rank == 0 ? 0ULL : 1ULL; nhi = 1ULL; }
+                s_lo = nlo; s_hi = nhi; s_nodes = n_nodes;
+            }
+            __syncthreads();
+        }
+    }
+    if (leaves_total == 0 && Mj.rank == 0 && threadIdx.x == 0) {
+        // empty grid: finalizeTree pads everything and writes a null root (OctreeBuilder.cpp:36-42)
+        const unsigned long long at = atomicAdd(&s_nrec, 1ULL);
+        if (at < Mj.rcap) { Mj.rpos[at] = 0ULL; Mj.rrec[3 * at] = 0ULL; Mj.rrec[3 * at + 1] = 0ULL; Mj.rrec[3 * at + 2] = ~0ULL; }
+    }
+    // bases of this rank's own level-J tiles
+    {
+        unsigned long long nJ = Mj.info->count[J];
+        if (nJ > Mj.capJ) nJ = Mj.capJ;
+        for (unsigned long long i = threadIdx.x; i < nJ; i += blockDim.x) Mj.baseJ[i] = Mj.B[J][Mj.keyJ[i]];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        BuildInfo* I = Mj.info;
+        I->n_voxels = leaves_total; I->n_nodes = s_nodes;
+        I->leaf_offset = s_before;
+        I->node_lo = s_lo; I->node_hi = s_hi;
+        I->n_upper = s_nrec < Mj.rcap ? s_nrec : Mj.rcap;
+        if (s_own != I->n_leaves_local) atomicOr(&I->overflow, 1ULL << 41);        // the table does not match this rank's tiles
+        if (s_hi - s_lo > Mj.nodes_cap) atomicOr(&I->overflow, 1ULL << 32);
+        if (s_nrec > Mj.rcap) atomicOr(&I->overflow, 1ULL << 42);
+    }
+}
+
+}  // namespace svo

@@ -312,7 +312,11 @@ __global__ void __launch_bounds__(MAX_WORLD) k_slice_wait(SliceCtrl* own, int wo
 
 // The one exchange of the sharded build -- the table of top-of-shard subtree records -- without a library collective:
 // the entries of different ranks are disjoint contiguous ranges, so every rank stores its own range into every peer's
-// exchange table (NVLink stores) and raises flag 2; after k_slice_wait(phase 2) each rank holds the complete table.
+// exchange table (NVLink stores) and raises flag 2; after k_xchg_wait each rank holds the complete table.
+// Flag value = 2 * exchange epoch + poison. A rank whose speculative local build was aborted (its lists outgrew the
+// capacities of the previous build, BuildInfo::overflow) has no valid entries to offer: it raises the flag with the
+// poison bit, every peer's wait marks its own build as "repeat" (overflow bit 43) and ALL ranks return SVO_E_RETRY
+// from svo_shard_emit in the same step -- no host read-back is needed to keep the ranks in agreement.
 struct XchgJob {
     const unsigned long long* src;              // local table (only [lo, lo + n) is read)
     unsigned long long lo, n;                   // own range, in u64
@@ -320,17 +324,32 @@ struct XchgJob {
     SliceCtrl* ctrl[MAX_WORLD];
     int world, me;
     unsigned long long epoch;
+    const BuildInfo* info;                      // NULL: the entries are always valid (sized builds)
 };
 __global__ void __launch_bounds__(256) k_xchg_push(XchgJob X) {
     const int p = blockIdx.x;                   // one block per destination
+    const bool poisoned = build_aborted(X.info);
     unsigned long long* dst = X.xtable[p];
-    for (unsigned long long i = threadIdx.x; i < X.n; i += blockDim.x) dst[X.lo + i] = X.src[X.lo + i];
+    if (!poisoned) for (unsigned long long i = threadIdx.x; i < X.n; i += blockDim.x) dst[X.lo + i] = X.src[X.lo + i];
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence_system();
-        *(volatile unsigned long long*)&X.ctrl[p]->flag[2][X.me] = X.epoch;
+        *(volatile unsigned long long*)&X.ctrl[p]->flag[2][X.me] = 2ULL * X.epoch + (poisoned ? 1ULL : 0ULL);
     }
+}
+__global__ void __launch_bounds__(MAX_WORLD) k_xchg_wait(SliceCtrl* own, int world, unsigned long long epoch, BuildInfo* info) {
+    const int p = threadIdx.x;
+    if (p >= world) return;
+    const volatile unsigned long long* f = &own->flag[2][p];
+    const long long t0 = clock64();
+    unsigned long long v;
+    while (((v = *f) >> 1) < epoch) {
+        if (clock64() - t0 > 8000000000LL) { own->error = 3ULL; break; }
+        __nanosleep(200);
+    }
+    if ((v >> 1) == epoch && (v & 1ULL) && info) atomicOr(&info->overflow, 1ULL << 43);
+    __threadfence_system();
 }
 
 struct U32Op {

@@ -99,17 +99,16 @@ struct VoxJob {
 // ---------------------------------------------------------------------------
 // hit sinks
 // ---------------------------------------------------------------------------
-// Binary pass: 64-bit atomicOr into the brick word; the thread that turns a word
-// from zero to non-zero propagates one bit to the level above, and so on.
+// Binary pass: fire-and-forget 64-bit OR reductions (RED, no return value, nothing to wait for): the brick word at
+// level 0 and, unconditionally, the brick's bit in the level-1 word above it. Levels >= 2 are rebuilt from the dense
+// level 1 after the voxelizer (k_dense_scan / k_small_levels in svo_build.cuh, k_pyramid_up for the classic path).
+__device__ __forceinline__ void red_or(unsigned long long* p, unsigned long long v) {
+    asm volatile("red.global.or.b64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
 __device__ __forceinline__ void sink_fill(const VoxJob& J, uint64_t w, uint64_t mask) {
     if (w < J.w_lo || w >= J.w_hi) return;          // another rank's slab
-    unsigned long long old = atomicOr(&J.lvl[0][w], (unsigned long long)mask);
-    int j = 0;
-    while (old == 0ULL && ++j < J.nl) {
-        const unsigned long long bit = 1ULL << (w & 63);
-        w >>= 6;
-        old = atomicOr(&J.lvl[j][w], bit);
-    }
+    red_or(&J.lvl[0][w], (unsigned long long)mask);
+    if (J.nl > 1) red_or(&J.lvl[1][w >> 6], 1ULL << (w & 63));
 }
 // Payload owner pass: the reference's first-triangle-wins rule (voxelizer.cpp:263)
 // made order independent: owner = min triangle index over all triangles passing.
@@ -180,9 +179,15 @@ __device__ __forceinline__ void warp_push(unsigned long long* counter, unsigned 
     }
 }
 
+// Morton code of the next brick along one axis: add one inside the axis' bit lane (the other lanes are filled with
+// ones so that the carry ripples through them)
+__device__ __forceinline__ unsigned long long morton_inc(unsigned long long m, unsigned long long lane_mask) {
+    return ((m | ~lane_mask) + 1ULL) & lane_mask;
+}
 // Split the hit mask of a box-aligned 4x4x4 window (linear layout) into the up to 8 bricks it straddles:
 // per axis the low part moves up by the window's offset inside the brick, the high part moves down into
 // the next brick; in the linear layout these are plain shifts once the part is masked out.
+// The window lies inside the clamped box of the pair, which lies inside this rank's slab (a box): no range test.
 template <bool OWNER>
 __device__ __forceinline__ void emit_window(const VoxJob& J, int wx, int wy, int wz, unsigned long long hits, uint32_t tri) {
     const int ox = wx & 3, oy = wy & 3, oz = wz & 3;
@@ -191,45 +196,32 @@ __device__ __forceinline__ void emit_window(const VoxJob& J, int wx, int wy, int
     const unsigned long long zlo = lowmask(16 * (4 - oz));
     const uint32_t bx = (uint32_t)(wx >> 2), by = (uint32_t)(wy >> 2), bz = (uint32_t)(wz >> 2);
     unsigned long long sx[2], sy[2], sz[2];
-    sx[0] = spread3(bx); sy[0] = spread3(by) << 1; sz[0] = spread3(bz) << 2;
-    sx[1] = ox ? spread3(bx + 1) : 0ULL; sy[1] = oy ? (spread3(by + 1) << 1) : 0ULL; sz[1] = oz ? (spread3(bz + 1) << 2) : 0ULL;
-    // phase 1: all (up to 8) brick atomics back to back, so that their round trips overlap
-    unsigned long long old[8];
-    uint64_t wi[8];
+    if (J.g <= 4096u) {                              // warp-uniform: bricks have <= 10 bits per axis, 32-bit interleave
+        sx[0] = spread3_10(bx); sy[0] = (unsigned long long)spread3_10(by) << 1; sz[0] = (unsigned long long)spread3_10(bz) << 2;
+    } else {
+        sx[0] = spread3(bx); sy[0] = spread3(by) << 1; sz[0] = spread3(bz) << 2;
+    }
+    sx[1] = morton_inc(sx[0], 0x1249249249249249ULL);
+    sy[1] = morton_inc(sy[0], 0x2492492492492492ULL);
+    sz[1] = morton_inc(sz[0], 0x4924924924924924ULL);
+    unsigned long long* const l0 = J.lvl[0];
+    unsigned long long* const l1 = J.nl > 1 ? J.lvl[1] : nullptr;
 #pragma unroll
     for (int q = 0; q < 8; q++) {
         const int dx = q & 1, dy = (q >> 1) & 1, dz = q >> 2;
         unsigned long long sub = hits & (dx ? ~xlo : xlo) & (dy ? ~ylo : ylo) & (dz ? ~zlo : zlo);
-        old[q] = ~0ULL;
-        wi[q] = sx[dx] | sy[dy] | sz[dz];
         if (sub) {
+            const uint64_t wi = sx[dx] | sy[dy] | sz[dz];
             const int sh = (dx ? ox - 4 : ox) + 4 * (dy ? oy - 4 : oy) + 16 * (dz ? oz - 4 : oz);
             sub = sh >= 0 ? (sub << sh) : (sub >> (-sh));
             if (!OWNER) {
-                if (wi[q] >= J.w_lo && wi[q] < J.w_hi) old[q] = atomicOr(&J.lvl[0][wi[q]], sub);
+                red_or(l0 + wi, sub);
+                if (l1) red_or(l1 + (wi >> 6), 1ULL << (wi & 63));
             } else {
                 while (sub) {
                     const int bit = __ffsll((long long)sub) - 1;
                     sub &= sub - 1;
-                    sink_owner_bit(J, wi[q], bit, tri);
-                }
-            }
-        }
-    }
-    // phase 2: the thread that turned a word from zero to non-zero propagates one bit upwards (rare).
-    // The comparand is an opaque zero defined AFTER the last atomic was issued: otherwise the compiler tests
-    // each result right behind its atomic and the eight round trips serialize.
-    if (!OWNER) {
-        unsigned long long zero;
-        asm volatile("mov.u64 %0, 0;" : "=l"(zero));
-#pragma unroll
-        for (int q = 0; q < 8; q++) {
-            if (old[q] == zero) {
-                uint64_t w = wi[q];
-                for (int j = 1; j < J.nl; j++) {
-                    const unsigned long long bit = 1ULL << (w & 63);
-                    w >>= 6;
-                    if (atomicOr(&J.lvl[j][w], bit) != 0ULL) break;
+                    sink_owner_bit(J, wi, bit, tri);
                 }
             }
         }
@@ -292,7 +284,7 @@ __device__ __forceinline__ void vox_small_body(const VoxJob& J, bool active, uin
                 cls = (vol <= J.small_max && nw <= J.small_windows) ? 0 : (vol <= J.medium_max ? 1 : 2);
             }
         }
-        if (!OWNER) {
+        if (!OWNER && __any_sync(0xffffffffu, cls > 0)) {       // rare: some lane holds a medium / large pair
             const unsigned long long e = ((unsigned long long)pack_slab(ix, iy, iz) << 32) | tri;     // queue entry: partition as slab coordinates
             warp_push(&J.qcount[0], J.queue[0], J.qcap, &J.qcount[3], cls == 1, e);
             warp_push(&J.qcount[1], J.queue[1], J.qcap, &J.qcount[3], cls == 2, e);
@@ -745,24 +737,108 @@ __device__ __forceinline__ unsigned long long block_excl_scan(unsigned long long
 }
 
 // ---------------------------------------------------------------------------
-// Single-pass exclusive scan (decoupled look-back), NV values per element in one pass: every element's functor is
-// evaluated once, one launch. Tiles are taken in ticket order (forward progress: every predecessor of a tile is
-// running or done); each tile publishes its aggregate, then its inclusive prefix, in a state word per value
-//   [epoch:16][status:2][value:46]     status 1 = aggregate, 2 = inclusive prefix
-// The epoch makes the persistent state array reusable without clearing it between launches.
+// Device-resident result block of a build: tile counts of the local levels, global counts, this rank's file range.
+// Filled by the build kernels, read back once with the final synchronisation; kernels launched with grids sized
+// from CAPACITIES (remembered from the previous build) read the real counts from here, so that a steady-state build
+// needs no host read-back in the middle (OctreeBuilder.cpp:34-55: the counts are only needed at finalizeTree).
+// ---------------------------------------------------------------------------
+struct BuildInfo {
+    unsigned long long count[MAX_LEVELS];     // tiles (non-zero words) of the local levels 0..J
+    unsigned long long n_leaves_local;        // voxels in this rank's slab
+    unsigned long long s_local;               // sum of the subtree sizes of this rank's level-J tiles
+    unsigned long long n_voxels, n_nodes;     // global
+    unsigned long long leaf_offset;           // voxels in the slabs of lower ranks
+    unsigned long long node_lo, node_hi;      // this rank's records of the node file
+    unsigned long long n_upper;               // shared upper-level records inside [node_lo, node_hi)
+    unsigned long long overflow;              // bit j: list of level j too small; bit 32: node buffer; bit 40: look-back timeout.
+                                              // Once set, every later kernel of the build returns at once (the pyramid stays intact).
+};
+__device__ __forceinline__ bool build_aborted(const BuildInfo* info) { return info && *(volatile const unsigned long long*)&info->overflow != 0ULL; }
+
+// ---------------------------------------------------------------------------
+// Single-pass exclusive scan (decoupled look-back) of NV values per element: every element's functor is evaluated
+// once, one launch. Tiles are taken in ticket order (forward progress: every predecessor of a tile is running or
+// done). A tile publishes its aggregate, later its inclusive prefix, in an 8-word state record
+//   [0] flag = epoch << 2 | status (1 = aggregate valid, 2 = inclusive prefix valid)   [1..NV] aggregate   [1+NV..2NV] inclusive
+// Values are written once per epoch and BEFORE the flag that announces them (fence in between), so ONE look-back
+// chain serves all NV values. The epoch makes the persistent state array reusable without clearing it.
 // ---------------------------------------------------------------------------
 constexpr int LB_THREADS = 256, LB_ITEMS = 8, LB_TILE = LB_THREADS * LB_ITEMS;
-__device__ __forceinline__ unsigned long long lb_pack(unsigned long long epoch, unsigned status, unsigned long long v) {
-    return (epoch << 48) | ((unsigned long long)status << 46) | (v & ((1ULL << 46) - 1ULL));
+constexpr int LB_STATE = 8;                   // u64 per tile
+constexpr int LB_MAXV = 3;
+// Called by all 32 lanes of ONE warp. total[] = this tile's aggregate; returns the exclusive prefix of the tile in
+// prefix[] (every lane) and publishes the inclusive prefix. A wait that never ends (cannot happen with ticket order;
+// a guard against hanging the device) sets *err.
+template <int NV>
+__device__ __forceinline__ void lookback(unsigned long long* state, unsigned long long epoch, unsigned long long tile,
+                                         const unsigned long long (&total)[NV], unsigned long long (&prefix)[NV], unsigned long long* err) {
+    static_assert(1 + 2 * NV <= LB_STATE, "state record too small");
+    volatile unsigned long long* st = state;
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int c = 0; c < NV; c++) prefix[c] = 0ULL;
+    if (tile > 0) {
+        if (lane == 0) {
+#pragma unroll
+            for (int c = 0; c < NV; c++) st[tile * LB_STATE + 1 + c] = total[c];
+            __threadfence();
+            st[tile * LB_STATE] = (epoch << 2) | 1ULL;
+        }
+        long long idx = (long long)tile - 1;
+        unsigned spins = 0;
+        while (true) {
+            // lane l looks at tile idx - l; tiles before the first count as "inclusive prefix 0"
+            const long long p = idx - lane;
+            const unsigned long long f = p >= 0 ? st[p * LB_STATE] : ((epoch << 2) | 2ULL);
+            const unsigned status = (unsigned)(f & 3ULL);
+            const bool ok = (f >> 2) == epoch && status != 0u;
+            const unsigned m_incl = __ballot_sync(0xffffffffu, ok && status == 2u);
+            const unsigned m_bad = __ballot_sync(0xffffffffu, !ok);
+            const int first = m_incl ? __ffs(m_incl) - 1 : 32;
+            const unsigned need = first >= 31 ? 0xffffffffu : ((1u << (first + 1)) - 1u);
+            if (m_bad & need) {                      // a predecessor has not published yet: look again
+                if (++spins > (1u << 22)) { if (lane == 0 && err) atomicOr(err, 1ULL << 40); break; }
+                __nanosleep(20);
+                continue;
+            }
+            __threadfence();                         // the values were written before the flag
+            const bool take = lane <= first && p >= 0;
+#pragma unroll
+            for (int c = 0; c < NV; c++) {
+                unsigned long long x = take ? st[p * LB_STATE + 1 + (status == 2u ? NV : 0) + c] : 0ULL;
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d);
+                prefix[c] += x;
+            }
+            if (first < 32) break;
+            idx -= 32;
+        }
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int c = 0; c < NV; c++) st[tile * LB_STATE + 1 + NV + c] = prefix[c] + total[c];
+        __threadfence();
+        st[tile * LB_STATE] = (epoch << 2) | 2ULL;
+    }
 }
+
+// Generic exclusive scan of f over [0, n): out has n + 1 entries (out[n] = total). n comes from the host (np == NULL)
+// or from device memory (np != NULL: the launch grid was sized for `n` = the capacity, the real count is min(*np, n)).
 template <int NV, class F>
-__global__ void __launch_bounds__(LB_THREADS) k_scan_lookback(F f, unsigned long long n, unsigned long long* out0, unsigned long long* out1,
+__global__ void __launch_bounds__(LB_THREADS) k_scan_lookback(F f, unsigned long long n, const unsigned long long* np,
+                                                              unsigned long long* out0, unsigned long long* out1,
                                                               unsigned long long* state, unsigned long long* ticket,
-                                                              unsigned long long ticket_base, unsigned long long epoch) {
+                                                              unsigned long long ticket_base, unsigned long long epoch, BuildInfo* info) {
     __shared__ unsigned long long s_tile, s_prefix[NV];
     if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1ULL) - ticket_base;
     __syncthreads();
+    if (build_aborted(info)) return;
+    if (np) { const unsigned long long v = *np; n = v < n ? v : n; }
     const unsigned long long tile = s_tile;
+    if (tile * LB_TILE >= n) {
+        if (tile == 0 && threadIdx.x == 0) { out0[0] = 0ULL; if (NV > 1) out1[0] = 0ULL; }      // empty input: out[n] = out[0] = 0
+        return;
+    }
     const unsigned long long base = tile * LB_TILE + (unsigned long long)threadIdx.x * LB_ITEMS;
     unsigned long long v[NV][LB_ITEMS], acc[NV], ex[NV], total[NV];
 #pragma unroll
@@ -778,39 +854,12 @@ __global__ void __launch_bounds__(LB_THREADS) k_scan_lookback(F f, unsigned long
     }
 #pragma unroll
     for (int c = 0; c < NV; c++) ex[c] = block_excl_scan(acc[c], total[c]);
-    volatile unsigned long long* st = state;
     if (threadIdx.x < 32) {
-        // Every value has its own chain of state words (a tile's words are written one at a time, so a reader must
-        // never combine the status of one value with the payload of another): one look-back per value.
-        const int lane = threadIdx.x;
+        unsigned long long pre[NV];
+        lookback<NV>(state, epoch, tile, total, pre, info ? &info->overflow : nullptr);
+        if (threadIdx.x == 0) {
 #pragma unroll
-        for (int c = 0; c < NV; c++) {
-            unsigned long long running = 0;
-            if (tile > 0) {
-                if (lane == 0) st[tile * NV + c] = lb_pack(epoch, 1u, total[c]);
-                long long idx = (long long)tile - 1;
-                while (true) {
-                    // lane l looks at tile idx - l; tiles before the first count as "inclusive prefix 0"
-                    const unsigned long long w = idx - lane >= 0 ? st[(idx - lane) * NV + c] : lb_pack(epoch, 2u, 0ULL);
-                    const unsigned status = (unsigned)(w >> 46) & 3u;
-                    const bool ok = (w >> 48) == epoch && status != 0u;
-                    const unsigned m_incl = __ballot_sync(0xffffffffu, ok && status == 2u);
-                    const unsigned m_bad = __ballot_sync(0xffffffffu, !ok);
-                    const int first = m_incl ? __ffs(m_incl) - 1 : 32;
-                    const unsigned need = first >= 31 ? 0xffffffffu : ((1u << (first + 1)) - 1u);
-                    if (m_bad & need) continue;                 // a predecessor has not published yet: look again
-                    unsigned long long x = lane <= first ? (w & ((1ULL << 46) - 1ULL)) : 0ULL;
-#pragma unroll
-                    for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d);
-                    running += x;
-                    if (first < 32) break;
-                    idx -= 32;
-                }
-            }
-            if (lane == 0) {
-                st[tile * NV + c] = lb_pack(epoch, 2u, running + total[c]);
-                s_prefix[c] = running;
-            }
+            for (int c = 0; c < NV; c++) s_prefix[c] = pre[c];
         }
     }
     __syncthreads();
@@ -842,7 +891,9 @@ struct BrickPrefixes {   // level 0: leaf ranks (popcount) and subtree sizes pop
 
 // Small inputs (the upper pyramid levels): the whole exclusive scan in ONE block / one launch.
 template <class F>
-__global__ void __launch_bounds__(1024) k_scan_small(F f, unsigned long long n, unsigned long long* out) {
+__global__ void __launch_bounds__(1024) k_scan_small(F f, unsigned long long n, const unsigned long long* np, unsigned long long* out, const BuildInfo* info) {
+    if (build_aborted(info)) return;
+    if (np) { const unsigned long long v = *np; n = v < n ? v : n; }
     // blocked arrangement: thread t owns SCAN_ITEMS consecutive elements of each 8192-element chunk
     unsigned long long carry = 0;
     for (unsigned long long b = 0; b < n; b += (unsigned long long)blockDim.x * SCAN_ITEMS) {
@@ -880,8 +931,15 @@ struct Level {
     unsigned long long* pl;       // n + 1  exclusive prefix of the leaf counts
     unsigned long long* ibase;    // n      internal nodes completed (post-order) before the tile's subtree begins
     float* cache;                 // n * 6  averaged colour + normal of the tile's node (Node::data_cache)
-    unsigned long long n;
+    unsigned long long n;         // tile count known on the host (np == NULL) ...
+    const unsigned long long* np; // ... or device-resident (BuildInfo::count[j]); then the lists hold `cap` entries
+    unsigned long long cap;
 };
+__device__ __forceinline__ unsigned long long level_n(const Level& L) {
+    if (!L.np) return L.n;
+    const unsigned long long v = *L.np;
+    return v < L.cap ? v : L.cap;
+}
 
 // counts[j] = number of non-zero words of local dense level j, j = 0..J: for j < J that is the number
 // of set bits of level j+1; for the top local level J the words are counted directly.
@@ -926,7 +984,9 @@ struct TableFillJob {
     const unsigned long long* pi;                  // -levels only
     const unsigned long long* fc[MAX_LEVELS];      // child-prefix arrays of levels 0..J: chasing them gives leaf ranks
     unsigned long long n; int J;
+    const unsigned long long* np;                  // device-resident count (fast path) or NULL
     unsigned long long* table;
+    BuildInfo* info;
 };
 // first leaf rank below tile i of level J: follow the first-child links down to level 0
 __device__ __forceinline__ unsigned long long first_leaf_below(const TableFillJob& T, unsigned long long i) {
@@ -934,8 +994,11 @@ __device__ __forceinline__ unsigned long long first_leaf_below(const TableFillJo
     return i;
 }
 __global__ void __launch_bounds__(256) k_table_fill(TableFillJob T) {
+    if (build_aborted(T.info)) return;
     const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= T.n) return;
+    unsigned long long n = T.n;
+    if (T.np) { const unsigned long long v = *T.np; n = v < n ? v : n; }
+    if (i >= n) return;
     unsigned long long* e = T.table + T.key[i] * 4ULL;
     e[0] = T.mask[i];
     e[1] = T.ps[i + 1] - T.ps[i];
@@ -1030,19 +1093,33 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_expand(Level parent, L
 }
 
 struct EmitJob {
-    unsigned long long* nodes;        // n_nodes * 3 u64
+    unsigned long long* nodes;        // this rank's node records: record `pos` of the file lives at nodes + (pos - node_lo) * 3
     int is_top;                       // this level holds the single top word
     int root_here;                    // D even: the top word IS the root -> write its record at S(top)
     int leaf_data_mode;               // level 0: 0 = binary (data = 1), 1 = payload (data = 1 + leaf rank)
     int levels;                       // -levels: internal nodes carry a data index too
     int virtual_top;                  // D odd: the top word is not a node (its byte 0 is the root)
-    // sharding: `nodes` is biased by -pos_lo records; replicated upper levels only write [pos_lo, pos_hi)
+    // this rank's range [pos_lo, pos_hi) of the file and the leaves in the slabs of lower ranks: by value (info == NULL)
+    // or device-resident (fast path: BuildInfo::node_lo / node_hi / leaf_offset)
     unsigned long long pos_lo, pos_hi;
-    unsigned long long leaf_offset;   // leaves in the slabs of lower ranks
-    int write_records;                // 0: only propagate the subtree bases (first pass of the replicated upper levels)
+    unsigned long long leaf_offset;
+    unsigned long long cap;           // records the node buffer holds (speculative emission into an earlier build's buffer)
+    const BuildInfo* info;
+    int write_records;                // 0: only propagate the subtree bases
 };
-__device__ __forceinline__ bool emit_here(const EmitJob& E, unsigned long long pos) {
-    return E.write_records && pos >= E.pos_lo && pos < E.pos_hi;
+struct NodeRange { unsigned long long lo, hi, leaf_offset; };
+__device__ __forceinline__ NodeRange node_range(const EmitJob& E) {
+    NodeRange r;
+    if (E.info) {
+        r.lo = E.info->node_lo; r.hi = E.info->node_hi; r.leaf_offset = E.info->leaf_offset;
+    } else { r.lo = E.pos_lo; r.hi = E.pos_hi; r.leaf_offset = E.leaf_offset; }
+    if (r.hi - r.lo > E.cap) r.hi = r.lo + E.cap;
+    return r;
+}
+// where record `pos` goes, or NULL when it belongs to another rank (or does not fit the buffer)
+__device__ __forceinline__ unsigned long long* node_slot(const EmitJob& E, const NodeRange& r, unsigned long long pos) {
+    if (!E.write_records || pos < r.lo || pos >= r.hi) return nullptr;
+    return E.nodes + (pos - r.lo) * 3ULL;
 }
 
 // -levels: data index of an internal node = records written before it. Payload mode interleaves the
@@ -1052,13 +1129,9 @@ __device__ __forceinline__ unsigned long long internal_data_index(const EmitJob&
     return (E.leaf_data_mode ? 1ULL + leaves_through : 2ULL) + rank;
 }
 
-// Upper levels (tile = node at depth d with two packed levels): writes the
-// records of its grandchildren (tiles of the level below) and children, and the
-// file base of every grandchild subtree.
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_emit_upper(Level L, Level C, EmitJob E) {
-    const unsigned long long i = (unsigned long long)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
-    if (i >= L.n) return;
-    const int lane = threadIdx.x & 31;
+// One tile of an upper level (tile = node at depth d with two packed levels): writes the records of its
+// grandchildren (tiles of the level below) and children, and the file base of every grandchild subtree.
+__device__ __forceinline__ void emit_upper_tile(const Level& L, const Level& C, const EmitJob& E, const NodeRange& R, unsigned long long i, int lane) {
     const unsigned long long W = L.mask[i], fc = L.fc[i], base = L.base[i];
     const unsigned long long S = L.ps[i + 1] - L.ps[i];
     const uint32_t nzb = nonzero_bytes(W);
@@ -1084,8 +1157,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_emit_upper(Level L, Le
                 C.ibase[c] = gib;
                 gdata = internal_data_index(E, C.pl[c + 1], gib + (C.pi[c + 1] - C.pi[c]) - 1ULL);
             }
-            if (emit_here(E, pos)) {
-                unsigned long long* o = E.nodes + pos * 3;
+            if (unsigned long long* o = node_slot(E, R, pos)) {
                 o[0] = gdata;
                 o[1] = gbase + gS - __popc(gnz);
                 o[2] = child_offsets(gnz);
@@ -1099,78 +1171,105 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_emit_upper(Level L, Le
         const unsigned long long pos = base + S - __popc(nzb) + __popc(nzb & ((1u << k) - 1u));
         unsigned long long cdata = 0ULL;
         if (E.levels) cdata = internal_data_index(E, C.pl[cend], L.ibase[i] + (C.pi[cend] - C.pi[fc]) + __popc(nzb & ((1u << k) - 1u)));
-        if (emit_here(E, pos)) {
-            unsigned long long* o = E.nodes + pos * 3;
+        if (unsigned long long* o = node_slot(E, R, pos)) {
             o[0] = cdata;
             o[1] = blk;
             o[2] = child_offsets((uint32_t)((W >> (8 * k)) & 0xffULL));
         }
     }
-    if (E.root_here && lane == 8 && emit_here(E, S)) {
-        unsigned long long* o = E.nodes + S * 3;
-        o[0] = E.levels ? internal_data_index(E, L.pl[i + 1], L.ibase[i] + (L.pi[i + 1] - L.pi[i]) - 1ULL) : 0ULL;
-        o[1] = base + S - __popc(nzb);
-        o[2] = child_offsets(nzb);
+    if (E.root_here && lane == 8) {
+        if (unsigned long long* o = node_slot(E, R, S)) {
+            o[0] = E.levels ? internal_data_index(E, L.pl[i + 1], L.ibase[i] + (L.pi[i + 1] - L.pi[i]) - 1ULL) : 0ULL;
+            o[1] = base + S - __popc(nzb);
+            o[2] = child_offsets(nzb);
+        }
     }
 }
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_emit_upper(Level L, Level C, EmitJob E) {
+    if (build_aborted(E.info)) return;
+    const unsigned long long i = (unsigned long long)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    if (i >= level_n(L)) return;
+    const NodeRange R = node_range(E);
+    emit_upper_tile(L, C, E, R, i, threadIdx.x & 31);
+}
 
-// Level 0 (bricks): the whole subtree region of a brick is contiguous in the file:
-// popc(W) leaf records followed by one record per non-zero byte. A warp takes 32
-// consecutive bricks (one coalesced load of their words and bases), then streams
-// each brick's region out as consecutive 8-byte words: the leaf part is a
-// period-3 pattern, so a store instruction covers 256 contiguous bytes; the
-// child records are written by lanes 0..7.
+// Level 0 (bricks): the whole subtree region of a brick is contiguous in the file: popc(W) leaf records followed by
+// one record per non-zero byte. A warp takes 32 consecutive bricks (one coalesced load of their words and bases).
+//   phase 1, cooperative: each brick's run of leaf records is streamed out as 16-BYTE stores (two 8-byte words of
+//     a 24-byte record stream; which field a word holds is its index mod 3, independent of the brick), one 8-byte
+//     store in front / behind where the run starts / ends on an odd word;
+//   phase 2, lane-serial: every lane writes the (<= 8) child records of its own brick, 16 + 8 bytes each.
+// Writes are guarded by this rank's range of the file and the capacity of the buffer (speculative emission).
 constexpr int EMIT_TILES_PER_WARP = 32;
+// 16-byte store to a 16-byte aligned address. Inline PTX on purpose: written as a C++ vector store, the two branches of
+// "aligned: 16 + 8, else 8 + 16" write the same bytes and the compiler folds them into ONE (then misaligned) form.
+__device__ __forceinline__ void st128(unsigned long long* p, unsigned long long a, unsigned long long b) {
+    asm volatile("st.global.v2.u64 [%0], {%1, %2};" :: "l"(p), "l"(a), "l"(b) : "memory");
+}
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_emit_leaf(Level L, EmitJob E) {
     __shared__ unsigned long long s_off[256];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) s_off[i] = child_offsets((uint32_t)i);
     __syncthreads();
+    if (build_aborted(E.info)) return;
     const int lane = threadIdx.x & 31;
+    const unsigned long long n = level_n(L);
     const unsigned long long t0 = ((unsigned long long)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5)) * EMIT_TILES_PER_WARP;
-    if (t0 >= L.n) return;
-    const int cnt = (int)min((unsigned long long)EMIT_TILES_PER_WARP, L.n - t0);
+    if (t0 >= n) return;
+    const int cnt = (int)min((unsigned long long)EMIT_TILES_PER_WARP, n - t0);
+    const NodeRange R = node_range(E);
     unsigned long long myW = 0, myBase = 0, myFc = 0;
     if (lane < cnt) {
         myW = L.mask[t0 + lane];
         myBase = L.base[t0 + lane];
         if (E.leaf_data_mode) myFc = L.fc[t0 + lane];
     }
-    const uint32_t myInfo = nonzero_bytes(myW) | ((uint32_t)__popcll(myW) << 8);    // each lane decodes its own brick once
-    const int f = lane % 3;                        // field of word q = lane + 32 * it: (lane + 2 * it) % 3
+    const uint32_t nzb = nonzero_bytes(myW);
+    const int myLeaf = __popcll(myW);
+    // a rank's own bricks always lie inside its range; the capacity guard drops whole bricks
+    const bool ok = lane < cnt && E.write_records && myBase >= R.lo &&
+                    myBase + (unsigned long long)(myLeaf + __popc(nzb) + (E.root_here ? 1 : 0)) <= R.hi;
+    const unsigned long long myRel = ok ? (myBase - R.lo) * 3ULL : 0ULL;          // first word of the region in the buffer
+    const int run = ok ? 3 * myLeaf : 0;                                          // words of the leaf run
+    const unsigned long long leaf1 = 1ULL + R.leaf_offset + myFc;                 // payload: data index of the brick's first leaf
+    const int l2 = (2 * lane) % 3;
+    // ---- phase 1 ----
     for (int t = 0; t < cnt; t++) {
-        const unsigned long long W = __shfl_sync(0xffffffffu, myW, t);
-        const unsigned long long base = __shfl_sync(0xffffffffu, myBase, t);
-        const uint32_t info = __shfl_sync(0xffffffffu, myInfo, t);
-        const uint32_t nzb = info & 0xffu;
-        const int nleaf = (int)(info >> 8);
-        // capacity guard (speculative emission into an earlier build's buffer; a rank's own regions always pass)
-        if (base + (unsigned long long)(nleaf + __popc(nzb) + (E.root_here ? 1 : 0)) > E.pos_hi) continue;
-        unsigned long long* out = E.nodes + base * 3;
-        const int total = 3 * nleaf;
-        if (!E.leaf_data_mode) {
-            int ff = f;
-            for (int q = lane; q < total; q += 32) {
-                out[q] = ff == 0 ? 1ULL : (ff == 1 ? 0ULL : ~0ULL);
-                ff += 2; if (ff >= 3) ff -= 3;       // (q + 32) % 3 == (q % 3 + 2) % 3
-            }
-        } else {
-            const unsigned long long leaf0 = 1ULL + E.leaf_offset + __shfl_sync(0xffffffffu, myFc, t);   // data index = 1 + leaf rank
-            int ff = f;
-            for (int q = lane; q < total; q += 32) {
-                out[q] = ff == 0 ? leaf0 + (unsigned)(q / 3) : (ff == 1 ? 0ULL : ~0ULL);
-                ff += 2; if (ff >= 3) ff -= 3;
-            }
+        const int words = __shfl_sync(0xffffffffu, run, t);
+        if (words == 0) continue;
+        const unsigned long long w0 = __shfl_sync(0xffffffffu, myRel, t);
+        const unsigned long long d0 = E.leaf_data_mode ? __shfl_sync(0xffffffffu, leaf1, t) : 1ULL;
+        unsigned long long* out = E.nodes + w0;
+        const int odd = (int)(w0 & 1ULL);
+        // relative words [odd, last) are written as aligned pairs, q = odd + 2 * (lane + 32 * i)
+        const int last = words - ((words - odd) & 1);
+        int f = odd + l2; if (f >= 3) f -= 3;               // field of word q: q % 3 (w0 = 3 * base: a multiple of three words)
+        for (int q = odd + 2 * lane; q < last; q += 64) {
+            unsigned long long a, b;                        // binary: (1, 0) (0, ~0) (~0, 1); payload: the data index of the record
+            if (f == 0) { a = E.leaf_data_mode ? d0 + (unsigned)(q / 3) : 1ULL; b = 0ULL; }
+            else if (f == 1) { a = 0ULL; b = ~0ULL; }
+            else { a = ~0ULL; b = E.leaf_data_mode ? d0 + (unsigned)((q + 1) / 3) : 1ULL; }
+            st128(out + q, a, b);
+            f = f == 2 ? 0 : f + 1;                         // 64 % 3 == 1
         }
-        if (lane < 8 && ((nzb >> lane) & 1u)) {
-            unsigned long long* o = out + 3 * (nleaf + __popc(nzb & ((1u << lane) - 1u)));
-            o[0] = 0ULL;
-            o[1] = base + __popcll(W & lowmask(8 * lane));
-            o[2] = s_off[(W >> (8 * lane)) & 0xffULL];
+        if (odd && lane == 31) out[0] = d0;                 // word 0: the data field of the first record
+        if (last < words && lane == 30) out[words - 1] = ~0ULL;          // the run's last word: an offsets field
+    }
+    // ---- phase 2 ----
+    if (ok) {
+        unsigned long long* o = E.nodes + myRel + 3 * myLeaf;
+        unsigned m = nzb;
+        while (m) {
+            const int k = __ffs(m) - 1;
+            m &= m - 1;
+            const unsigned long long cb = myBase + __popcll(myW & lowmask(8 * k));
+            const unsigned long long off = s_off[(myW >> (8 * k)) & 0xffULL];
+            if (((uintptr_t)o & 15) == 0) { st128(o, 0ULL, cb); o[2] = off; }
+            else { o[0] = 0ULL; st128(o + 1, cb, off); }
+            o += 3;
         }
-        if (E.root_here && lane == 8) {   // gridsize 4: the single brick is the root
-            unsigned long long* o = out + 3 * (nleaf + __popc(nzb));
+        if (E.root_here) {   // gridsize 4: the single brick is the root
             o[0] = 0ULL;
-            o[1] = base + nleaf;
+            o[1] = myBase + myLeaf;
             o[2] = child_offsets(nzb);
         }
     }
@@ -1181,6 +1280,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_emit_leaf(Level L, Emi
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_emit_leaf_levels(Level L, EmitJob E) {
     const unsigned long long i = (unsigned long long)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
     if (i >= L.n) return;
+    const NodeRange R = node_range(E);
     const int lane = threadIdx.x & 31;
     const unsigned long long W = L.mask[i], base = L.base[i], ib = L.ibase[i], lp = L.fc[i];
     const uint32_t nzb = nonzero_bytes(W);
@@ -1190,24 +1290,27 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_emit_leaf_levels(Level
         const int bit = lane + 32 * h;
         if ((W >> bit) & 1ULL) {
             const int r = __popcll(W & lowmask(bit));
-            unsigned long long* o = E.nodes + (base + r) * 3;
-            o[0] = E.leaf_data_mode ? 1ULL + lp + r + ib + __popc(nzb & ((1u << (bit >> 3)) - 1u)) : 1ULL;
-            o[1] = 0ULL;
-            o[2] = ~0ULL;
+            if (unsigned long long* o = node_slot(E, R, base + r)) {
+                o[0] = E.leaf_data_mode ? 1ULL + lp + r + ib + __popc(nzb & ((1u << (bit >> 3)) - 1u)) : 1ULL;
+                o[1] = 0ULL;
+                o[2] = ~0ULL;
+            }
         }
     }
     if (lane < 8 && ((nzb >> lane) & 1u)) {
         const int k = lane;
-        unsigned long long* o = E.nodes + (base + nleaf + __popc(nzb & ((1u << k) - 1u))) * 3;
-        o[0] = internal_data_index(E, lp + __popcll(W & lowmask(8 * (k + 1))), ib + __popc(nzb & ((1u << k) - 1u)));
-        o[1] = base + __popcll(W & lowmask(8 * k));
-        o[2] = child_offsets((uint32_t)((W >> (8 * k)) & 0xffULL));
+        if (unsigned long long* o = node_slot(E, R, base + nleaf + __popc(nzb & ((1u << k) - 1u)))) {
+            o[0] = internal_data_index(E, lp + __popcll(W & lowmask(8 * (k + 1))), ib + __popc(nzb & ((1u << k) - 1u)));
+            o[1] = base + __popcll(W & lowmask(8 * k));
+            o[2] = child_offsets((uint32_t)((W >> (8 * k)) & 0xffULL));
+        }
     }
     if (E.root_here && lane == 8) {   // gridsize 4
-        unsigned long long* o = E.nodes + (base + nleaf + __popc(nzb)) * 3;
-        o[0] = internal_data_index(E, lp + nleaf, ib + __popc(nzb));
-        o[1] = base + nleaf;
-        o[2] = child_offsets(nzb);
+        if (unsigned long long* o = node_slot(E, R, base + nleaf + __popc(nzb))) {
+            o[0] = internal_data_index(E, lp + nleaf, ib + __popc(nzb));
+            o[1] = base + nleaf;
+            o[2] = child_offsets(nzb);
+        }
     }
 }
 
@@ -1341,92 +1444,56 @@ __global__ void __launch_bounds__(1024) k_fused_down(FusedJob F) {
 
 // bottom-up: subtree-size prefixes of levels jf..J (ps of level jf-1 must be complete)
 __global__ void __launch_bounds__(1024) k_fused_up(FusedJob F) {
+    if (build_aborted(F.E.info)) return;
     for (int j = F.jf; j <= F.J; j++) {
         const Level L = F.lv[j];
+        const unsigned long long n = level_n(L);
         const unsigned long long* cps = F.lv[j - 1].ps;
         unsigned long long carry = 0;
-        for (unsigned long long b = 0; b < L.n; b += blockDim.x) {
+        for (unsigned long long b = 0; b < n; b += blockDim.x) {
             const unsigned long long idx = b + threadIdx.x;
             unsigned long long v = 0;
-            if (idx < L.n) {
+            if (idx < n) {
                 const unsigned long long w = L.mask[idx];
                 v = (unsigned long long)(__popcll(w) + __popc(nonzero_bytes(w))) + cps[L.fc[idx + 1]] - cps[L.fc[idx]];
             }
             unsigned long long total;
             const unsigned long long ex = block_excl_scan(v, total);
-            if (idx < L.n) L.ps[idx] = carry + ex;
+            if (idx < n) L.ps[idx] = carry + ex;
             carry += total;
         }
-        if (threadIdx.x == 0) L.ps[L.n] = carry;
+        if (threadIdx.x == 0) L.ps[n] = carry;
         if (L.pl) {                                   // leaf-count prefix (sharded table / global leaf ranks)
             const unsigned long long* cpl = F.lv[j - 1].pl;
             unsigned long long lc = 0;
-            for (unsigned long long b = 0; b < L.n; b += blockDim.x) {
+            for (unsigned long long b = 0; b < n; b += blockDim.x) {
                 const unsigned long long idx = b + threadIdx.x;
-                const unsigned long long v = idx < L.n ? cpl[L.fc[idx + 1]] - cpl[L.fc[idx]] : 0ULL;
+                const unsigned long long v = idx < n ? cpl[L.fc[idx + 1]] - cpl[L.fc[idx]] : 0ULL;
                 unsigned long long total;
                 const unsigned long long ex = block_excl_scan(v, total);
-                if (idx < L.n) L.pl[idx] = lc + ex;
+                if (idx < n) L.pl[idx] = lc + ex;
                 lc += total;
             }
-            if (threadIdx.x == 0) L.pl[L.n] = lc;
+            if (threadIdx.x == 0) L.pl[n] = lc;
         }
+        __threadfence();
         __syncthreads();
     }
 }
 
-// one tile of an upper level: records of its grandchildren + children, bases of the grandchild subtrees
-__device__ __forceinline__ void emit_upper_tile(const Level& L, const Level& C, const EmitJob& E, unsigned long long i, int lane) {
-    const unsigned long long W = L.mask[i], fc = L.fc[i], base = L.base[i];
-    const unsigned long long S = L.ps[i + 1] - L.ps[i];
-    const uint32_t nzb = nonzero_bytes(W);
-    const unsigned long long ps0 = C.ps[fc];
-#pragma unroll
-    for (int h = 0; h < 2; h++) {
-        const int bit = lane + 32 * h;
-        if ((W >> bit) & 1ULL) {
-            const int k = bit >> 3;
-            const unsigned long long c = fc + __popcll(W & lowmask(bit));
-            const unsigned long long gbase = base + (C.ps[c] - ps0) + __popcll(W & lowmask(8 * k));
-            C.base[c] = gbase;
-            const unsigned long long blk = base + (C.ps[fc + __popcll(W & lowmask(8 * (k + 1)))] - ps0) + __popcll(W & lowmask(8 * k));
-            const unsigned long long pos = blk + __popcll(W & lowmask(bit) & ~lowmask(8 * k));
-            const uint32_t gnz = nonzero_bytes(C.mask[c]);
-            if (pos < E.pos_hi) {                               // capacity guard (speculative emission)
-                unsigned long long* o = E.nodes + pos * 3;
-                o[0] = 0ULL;
-                o[1] = gbase + (C.ps[c + 1] - C.ps[c]) - __popc(gnz);
-                o[2] = child_offsets(gnz);
-            }
-        }
-    }
-    if (lane < 8 && ((nzb >> lane) & 1u)) {
-        const int k = lane;
-        const unsigned long long blk = base + (C.ps[fc + __popcll(W & lowmask(8 * (k + 1)))] - ps0) + __popcll(W & lowmask(8 * k));
-        const unsigned long long pos = base + S - __popc(nzb) + __popc(nzb & ((1u << k) - 1u));
-        if (pos < E.pos_hi) {
-            unsigned long long* o = E.nodes + pos * 3;
-            o[0] = 0ULL;
-            o[1] = blk;
-            o[2] = child_offsets((uint32_t)((W >> (8 * k)) & 0xffULL));
-        }
-    }
-}
 // top-down emission of levels J..jf+1 (each level writes the bases of the next); level jf itself is emitted
-// by the regular multi-block kernel afterwards. No -levels, no sharding on this path.
+// by the regular multi-block kernel afterwards. No -levels on this path.
 __global__ void __launch_bounds__(1024) k_fused_emit(FusedJob F) {
+    if (build_aborted(F.E.info)) return;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const NodeRange R = node_range(F.E);
     for (int j = F.J; j > F.jf; j--) {
         const Level L = F.lv[j], C = F.lv[j - 1];
-        for (unsigned long long i = wid; i < L.n; i += nw) emit_upper_tile(L, C, F.E, i, lane);
-        if (j == F.J && F.E.root_here && threadIdx.x == 0 && L.n) {
-            const unsigned long long W = L.mask[0], S = L.ps[1] - L.ps[0];
-            const uint32_t nzb = nonzero_bytes(W);
-            if (S < F.E.pos_hi) {
-                unsigned long long* o = F.E.nodes + S * 3;
-                o[0] = 0ULL; o[1] = L.base[0] + S - __popc(nzb); o[2] = child_offsets(nzb);
-            }
-        }
+        const unsigned long long n = level_n(L);
+        EmitJob E = F.E;
+        E.root_here = (j == F.J) ? F.E.root_here : 0;
+        for (unsigned long long i = wid; i < n; i += nw) emit_upper_tile(L, C, E, R, i, lane);
+        __threadfence();
         __syncthreads();
     }
 }
@@ -1434,18 +1501,25 @@ __global__ void __launch_bounds__(1024) k_fused_emit(FusedJob F) {
 // sharded: the records of the shared upper levels are computed on the host from the exchanged table
 // (a few thousand at most) and scattered into this rank's part of the node array
 __global__ void __launch_bounds__(256) k_scatter_records(const unsigned long long* pos, const unsigned long long* rec, unsigned long long n,
-                                                         unsigned long long* nodes /* biased by -node_lo */) {
-    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    unsigned long long* o = nodes + pos[i] * 3;
-    o[0] = rec[3 * i]; o[1] = rec[3 * i + 1]; o[2] = rec[3 * i + 2];
+                                                         const unsigned long long* np, EmitJob E) {
+    if (build_aborted(E.info)) return;
+    if (np) { const unsigned long long v = *np; n = v < n ? v : n; }
+    const NodeRange R = node_range(E);
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+        if (unsigned long long* o = node_slot(E, R, pos[i])) { o[0] = rec[3 * i]; o[1] = rec[3 * i + 1]; o[2] = rec[3 * i + 2]; }
+    }
 }
 
 // sparse clear of all levels in one launch (blockIdx.y = level)
-struct ClearJob { const unsigned long long* key[MAX_LEVELS]; unsigned long long* dense[MAX_LEVELS]; unsigned long long n[MAX_LEVELS]; };
+struct ClearJob {
+    const unsigned long long* key[MAX_LEVELS]; unsigned long long* dense[MAX_LEVELS]; unsigned long long n[MAX_LEVELS];
+    const BuildInfo* info;            // fast path: the counts live on the device (n[] = capacities); an aborted build keeps its pyramid
+};
 __global__ void __launch_bounds__(256) k_sparse_clear_all(ClearJob Cj) {
+    if (build_aborted(Cj.info)) return;
     const int j = blockIdx.y;
-    const unsigned long long n = Cj.n[j];
+    unsigned long long n = Cj.n[j];
+    if (Cj.info) { const unsigned long long v = Cj.info->count[j]; n = v < n ? v : n; }
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x)
         Cj.dense[j][Cj.key[j][i]] = 0ULL;
 }
@@ -1453,7 +1527,7 @@ __global__ void __launch_bounds__(256) k_sparse_clear_all(ClearJob Cj) {
 // ascending Morton codes of the filled voxels
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_voxel_codes(Level L, unsigned long long* codes, unsigned long long capacity) {
     const unsigned long long i = (unsigned long long)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
-    if (i >= L.n) return;
+    if (i >= level_n(L)) return;
     const int lane = threadIdx.x & 31;
     const unsigned long long W = L.mask[i], key = L.key[i], fc = L.fc[i];
 #pragma unroll
@@ -1492,7 +1566,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_payload(Level L, Paylo
     __shared__ unsigned long long s_base[MAX_WORLD + 1];
     if (Pj.segs.n) segs_bases(Pj.segs, s_base);
     const unsigned long long i = (unsigned long long)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
-    if (i >= L.n) return;
+    if (i >= level_n(L)) return;
     const int lane = threadIdx.x & 31;
     const unsigned long long W = L.mask[i], key = L.key[i], fc = L.fc[i];
 #pragma unroll

@@ -18,7 +18,7 @@ from dataclasses import dataclass
 
 import numpy as np
 
-from .api import SvoBuilder, header_bytes, estimate_partitions, NODE_BYTES, DATA_BYTES
+from .api import SvoBuilder, SvoError, header_bytes, estimate_partitions, NODE_BYTES, DATA_BYTES
 
 
 @dataclass
@@ -155,33 +155,51 @@ def run_single_process(tris, length: float, gridsize: int, world: int, memory_li
                 sb.set_triangles(tris)
             sb.partition(prm, want_counts=not (dispatch or remote))
             sb.voxelize()
-            t = torch.zeros(sb.shard_table_size(), dtype=torch.int64, device="cuda:%d" % device)
+            tables.append(torch.zeros(sb.shard_table_size(), dtype=torch.int64, device="cuda:%d" % device))
+        return shard_build_single_process(ctxs, tables, remote, fetch)
+    finally:
+        for sb in ctxs:
+            sb.close()
+
+
+def shard_build_single_process(ctxs, tables, remote: bool, fetch: bool = True) -> list[ShardResult]:
+    """svo_shard_count -> exchange -> svo_shard_emit for all ranks of one process (contexts already voxelized).
+    Repeats the three calls for ALL ranks when the library answers SVO_E_RETRY (include/svo_b200.h)."""
+    import torch
+    for attempt in range(4):
+        for sb, t in zip(ctxs, tables):
             sb.shard_count(t.data_ptr())
-            sb.synchronize()
-            tables.append(t)
+            if not remote:
+                sb.synchronize()
         if remote:
             # one host thread drives all ranks: issue every rank's exchange before waiting on any of them (the
             # device-side waits resolve once all ranks have pushed; nothing in between may synchronize the device)
             for sb, t in zip(ctxs, tables):
                 sb.shard_exchange(t.data_ptr())
-            for sb in ctxs:
-                sb.synchronize()
-            assert all(bool((t == tables[0]).all()) for t in tables), "the peer-memory exchange left different tables on the ranks"
         else:
             merged = torch.stack(tables).sum(dim=0)
             # disjointness is part of the contract
             assert int((torch.stack([(t != 0).to(torch.int64) for t in tables]).sum(dim=0) > 1).sum()) == 0
-        out = []
+        out, retry = [], 0
         for r, sb in enumerate(ctxs):
-            nv, nn, nd = sb.shard_emit(tables[r].data_ptr() if remote else merged.data_ptr())
+            try:
+                nv, nn, nd = sb.shard_emit(tables[r].data_ptr() if remote else merged.data_ptr())
+            except SvoError as e:
+                if e.code != 5:
+                    raise
+                retry += 1
+                continue
             nlo, nhi, dlo, dhi = sb.shard_ranges()
             nodes = sb.fetch_nodes(nlo, nhi - nlo) if fetch else np.empty(0, np.uint8)
             data = sb.fetch_data(dlo, dhi - dlo) if fetch else np.empty(0, np.uint8)
             out.append(ShardResult(r, nv, nn, nd, (nlo, nhi), (dlo, dhi), nodes, data, sb.stats()))
-        return out
-    finally:
-        for sb in ctxs:
-            sb.close()
+        if retry == 0:
+            if remote:
+                assert all(bool((t == tables[0]).all()) for t in tables), "the peer-memory exchange left different tables on the ranks"
+            return out
+        assert retry == len(ctxs), "SVO_E_RETRY must be answered by every rank in the same step (%d of %d)" % (retry, len(ctxs))
+    raise RuntimeError("sharded build did not settle after 4 attempts")
+
 
 
 class DistributedBuilder:
@@ -305,17 +323,25 @@ class DistributedBuilder:
         n = sb.shard_table_size()
         if self.table is None or self.table.numel() != n:
             self.table = self.torch.zeros(n, dtype=self.torch.int64, device="cuda:%d" % self.device)
-        sb.shard_count(self.table.data_ptr())
-        if getattr(self, "sliced", False) and os.environ.get("SVO_TABLE_EXCHANGE", "peer") == "peer":
-            sb.shard_exchange(self.table.data_ptr())     # our own exchange over the peer windows (no NCCL on the path)
-        elif self.stream is not None:
-            with self.torch.cuda.stream(self.stream):   # same queue as the kernels that filled / will read the table
+        self.retries = 0
+        while True:
+            sb.shard_count(self.table.data_ptr())
+            if getattr(self, "sliced", False) and os.environ.get("SVO_TABLE_EXCHANGE", "peer") == "peer":
+                sb.shard_exchange(self.table.data_ptr())     # our own exchange over the peer windows (no NCCL on the path)
+            elif self.stream is not None:
+                with self.torch.cuda.stream(self.stream):   # same queue as the kernels that filled / will read the table
+                    self.dist.all_reduce(self.table)
+            else:
+                sb.synchronize()                            # the library runs on its own stream: order it against torch's
                 self.dist.all_reduce(self.table)
-        else:
-            sb.synchronize()                            # the library runs on its own stream: order it against torch's
-            self.dist.all_reduce(self.table)
-            self.torch.cuda.current_stream().synchronize()
-        return sb.shard_emit(self.table.data_ptr())      # sum over ranks == union of disjoint entries (NCCL over NVLink)
+                self.torch.cuda.current_stream().synchronize()
+            try:
+                return sb.shard_emit(self.table.data_ptr())      # sum over ranks == union of disjoint entries (NCCL over NVLink)
+            except SvoError as e:
+                # SVO_E_RETRY: some rank's speculative local build outgrew its lists; every rank sees it in the same step
+                if e.code != 5 or self.retries >= 3:
+                    raise
+                self.retries += 1
 
     def close(self):
         self.sb.synchronize()

@@ -259,3 +259,41 @@ def test_remote_slices_degenerate_and_box(oracle, world):
     _check(oracle, mg.degenerate_mix(), 256, world, limit=2, remote=True)
     _check(oracle, mg.degenerate_mix(), 64, world, remote=True)
     _check(oracle, mg.axis_aligned_box(), 256, world, limit=3, remote=True)
+
+
+def test_remote_speculative_builds_and_collective_retry(oracle):
+    """The same sharded contexts run three jobs over the peer-memory exchange: the second repeats the first (speculative
+    builds, no host read-back), the third is larger: some rank's lists overflow, it poisons the exchange flag and ALL
+    ranks answer SVO_E_RETRY in the same step; the repeated build is sized and byte-exact."""
+    import torch
+    from ooc_svo_builder_b200 import SvoBuilder
+    world = 4
+    small, big = mg.icosphere(4), mg.random_soup(6000, seed=31, large_frac=0.02)
+    cap = 6000
+    ctxs = [SvoBuilder(0) for _ in range(world)]
+    try:
+        for r, sb in enumerate(ctxs):
+            sb.shard_configure(r, world)
+        wins = [sb.slice_create(cap, 9) for sb in ctxs]
+        for sb in ctxs:
+            sb.slice_attach(wins)
+        for mesh, g in ((small, 128), (small, 128), (big, 256), (big, 256), (small, 128)):
+            prm = SvoBuilder.make_params(mesh.length, g, False, 2)
+            T = mesh.tris.shape[0]
+            for r, sb in enumerate(ctxs):
+                lo, hi = sharded.slice_bounds(T, world, r)
+                sb.slice_upload(mesh.tris[lo:hi])
+            for sb in ctxs:
+                sb.slice_publish(prm, T)
+            tables = []
+            for sb in ctxs:
+                sb.partition(prm, want_counts=False)
+                sb.voxelize()
+                tables.append(torch.zeros(sb.shard_table_size(), dtype=torch.int64, device="cuda"))
+            res = sharded.shard_build_single_process(ctxs, tables, True)
+            hdr, nodes, data = sharded.assemble(res, g)
+            want = oracle.build(mesh.tris, mesh.length, g, memory_limit_mb=2)
+            assert hdr == want.header and nodes.tobytes() == want.nodes and data.tobytes() == want.data
+    finally:
+        for sb in ctxs:
+            sb.close()
