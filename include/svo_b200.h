@@ -77,6 +77,11 @@ typedef struct svo_stats {
     float ms_dispatch;          /* multi-GPU: slice block-list pass (remote staging) or triangle dispatch */
     float ms_peer_wait;         /* multi-GPU, remote staging: device-side wait for the peers' block lists  */
     uint32_t kernel_launches;   /* kernels launched by the last run                            */
+    uint32_t speculative;       /* 1: the build ran without a host read-back before the final one (capacities of the previous build) */
+    uint64_t n_bricks;          /* occupied 4x4x4 bricks (octree nodes at depth D-2) of this context's slab               */
+    uint64_t n_tiles1;          /* occupied 16^3 tiles (non-zero words of pyramid level 1) of this context's slab         */
+    uint64_t n_brick_records;   /* node records of this context's brick subtrees (leaves + depth D-1 nodes): what the
+                                   brick-level emitter writes; 0 on the host-driven (classic) build path                  */
 } svo_stats;
 
 /* ---- lifetime ------------------------------------------------------------ */
@@ -151,7 +156,7 @@ int svo_build(svo_ctx* ctx, uint64_t* n_voxels, uint64_t* n_nodes, uint64_t* n_d
  * [first, first+count) of the .octreenodes / .octreedata image into caller
  * memory (count * 24 resp. count * 32 bytes). Chunk the calls to stream the
  * result within a host memory budget (-l). */
-int svo_fetch_nodes(svo_ctx* ctx, uint64_t first, uint64_t count, void* dst);
+int svo_fetch_nodes(svo_ctx* ctx, uint64_t first, uint64_t count, void* dst);   /* dst: host memory, or device memory of ctx's device */
 int svo_fetch_data(svo_ctx* ctx, uint64_t first, uint64_t count, void* dst);
 
 /* Device-resident views of the same images (valid until the next svo_partition /

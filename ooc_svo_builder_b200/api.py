@@ -58,7 +58,8 @@ class Stats(C.Structure):
                 ("ms_build", C.c_float), ("ms_emit", C.c_float), ("ms_clear", C.c_float), ("ms_download", C.c_float),
                 ("ms_vox_small", C.c_float), ("ms_emit_leaf", C.c_float), ("ms_compact", C.c_float),
                 ("ms_dispatch", C.c_float), ("ms_peer_wait", C.c_float),
-                ("kernel_launches", C.c_uint32)]
+                ("kernel_launches", C.c_uint32), ("speculative", C.c_uint32),
+                ("n_bricks", C.c_uint64), ("n_tiles1", C.c_uint64), ("n_brick_records", C.c_uint64)]
 
     def as_dict(self) -> dict:
         return {n: getattr(self, n) for n, _ in self._fields_ if n != "reserved"}
@@ -411,10 +412,13 @@ class SvoBuilder:
         self._ck(self._lib.svo_shard_dispatch_finish(self._h, C.byref(n)))
         return n.value
 
-    def fetch_nodes(self, first: int, count: int, out: np.ndarray | None = None) -> np.ndarray:
+    def fetch_nodes(self, first: int, count: int, out=None):
+        """Records [first, first + count) of the node file into `out`: a numpy uint8 array (host) or a torch CUDA
+        uint8 tensor on this context's device (device-to-device copy)."""
         if out is None:
             out = np.empty(count * NODE_BYTES, dtype=np.uint8)
-        self._ck(self._lib.svo_fetch_nodes(self._h, first, count, out.ctypes.data))
+        ptr = out.ctypes.data if isinstance(out, np.ndarray) else out.data_ptr()
+        self._ck(self._lib.svo_fetch_nodes(self._h, first, count, ptr))
         return out
 
     def fetch_data(self, first: int, count: int, out: np.ndarray | None = None) -> np.ndarray:

@@ -1124,6 +1124,9 @@ static void finish_build_stats(svo_ctx* c) {
     // inline enumeration does not count pairs on the device; the sum of the per-partition counts is known when they were requested
     c->stats.n_pairs = (c->P > 1 && !c->use_lists) ? c->n_pairs : c->q_end - c->q_begin;
     c->stats.n_voxels = c->n_voxels; c->stats.n_nodes = c->n_nodes; c->stats.n_data = c->n_data;
+    c->stats.n_bricks = c->lv[0].n; c->stats.n_tiles1 = c->J >= 1 ? c->lv[1].n : 0;
+    c->stats.speculative = (c->fast && c->spec) ? 1u : 0u;
+    c->stats.n_brick_records = c->fast ? c->h_info->n_brick_records : 0;
     c->stats.n_medium = c->h_pinned[40]; c->stats.n_large = c->h_pinned[41];
     const ull queued = c->stats.n_medium + c->stats.n_large;
     c->stats.n_small = c->stats.n_pairs >= queued ? c->stats.n_pairs - queued : 0;   // n_pairs is 0 when the pairs were not counted
@@ -2166,7 +2169,7 @@ static int fetch_common(svo_ctx* c, const DevBuf& src, uint64_t lo, uint64_t hi,
     if (count && !dst) return fail(c, SVO_E_INVALID, "dst is NULL");
     CK(cudaSetDevice(c->device));
     mark(c, EV_DN0);
-    if (count) CK(cudaMemcpyAsync(dst, (const char*)src.p + first * rec, count * rec, cudaMemcpyDeviceToHost, c->stream));
+    if (count) CK(cudaMemcpyAsync(dst, (const char*)src.p + first * rec, count * rec, cudaMemcpyDefault, c->stream));    // dst: host, or device memory (UVA)
     mark(c, EV_DN1);
     CK(cudaStreamSynchronize(c->stream));
     c->stats.ms_download += span(c, EV_DN0, EV_DN1);

@@ -229,6 +229,7 @@ __global__ void __launch_bounds__(BP_WARPS * 32) k_brick_pass(BrickJob B) {
                 if (n0 <= B.L0.cap) { B.L0.fc[n0] = prefix[0] + tot[0]; B.L0.ps[n0] = prefix[1] + tot[1]; }
                 B.L1.ps[n1] = prefix[2] + tot[2];
                 B.info->n_leaves_local = prefix[0] + tot[0];
+                B.info->n_brick_records = prefix[1] + tot[1];
             }
         }
     }

@@ -745,7 +745,7 @@ __device__ __forceinline__ unsigned long long block_excl_scan(unsigned long long
 struct BuildInfo {
     unsigned long long count[MAX_LEVELS];     // tiles (non-zero words) of the local levels 0..J
     unsigned long long n_leaves_local;        // voxels in this rank's slab
-    unsigned long long s_local;               // sum of the subtree sizes of this rank's level-J tiles
+    unsigned long long n_brick_records;       // records of this rank's brick subtrees: leaves + depth D-1 nodes (what k_emit_leaf writes)
     unsigned long long n_voxels, n_nodes;     // global
     unsigned long long leaf_offset;           // voxels in the slabs of lower ranks
     unsigned long long node_lo, node_hi;      // this rank's records of the node file
@@ -1194,11 +1194,12 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_emit_upper(Level L, Le
 }
 
 // Level 0 (bricks): the whole subtree region of a brick is contiguous in the file: popc(W) leaf records followed by
-// one record per non-zero byte. A warp takes 32 consecutive bricks (one coalesced load of their words and bases).
-//   phase 1, cooperative: each brick's run of leaf records is streamed out as 16-BYTE stores (two 8-byte words of
-//     a 24-byte record stream; which field a word holds is its index mod 3, independent of the brick), one 8-byte
-//     store in front / behind where the run starts / ends on an odd word;
-//   phase 2, lane-serial: every lane writes the (<= 8) child records of its own brick, 16 + 8 bytes each.
+// one record per non-zero byte. A warp takes 32 consecutive bricks (one coalesced load of their words and bases) and
+// walks them FOUR at a time, eight lanes per brick:
+//   * the run of leaf records is streamed out as 16-BYTE stores, 128 contiguous bytes per brick and step (which field
+//     of the 24-byte record a word holds is its index mod 3, independent of the brick); one 8-byte store in front /
+//     behind where the run starts / ends on an odd word;
+//   * lane k of the group writes the child record of byte k (16 + 8 bytes).
 // Writes are guarded by this rank's range of the file and the capacity of the buffer (speculative emission).
 constexpr int EMIT_TILES_PER_WARP = 32;
 // 16-byte store to a 16-byte aligned address. Inline PTX on purpose: written as a C++ vector store, the two branches of
@@ -1223,53 +1224,53 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_emit_leaf(Level L, Emi
         myBase = L.base[t0 + lane];
         if (E.leaf_data_mode) myFc = L.fc[t0 + lane];
     }
-    const uint32_t nzb = nonzero_bytes(myW);
     const int myLeaf = __popcll(myW);
     // a rank's own bricks always lie inside its range; the capacity guard drops whole bricks
     const bool ok = lane < cnt && E.write_records && myBase >= R.lo &&
-                    myBase + (unsigned long long)(myLeaf + __popc(nzb) + (E.root_here ? 1 : 0)) <= R.hi;
+                    myBase + (unsigned long long)(myLeaf + __popc(nonzero_bytes(myW)) + (E.root_here ? 1 : 0)) <= R.hi;
+    if (!ok) myW = 0ULL;                                                          // nothing is written for this brick
     const unsigned long long myRel = ok ? (myBase - R.lo) * 3ULL : 0ULL;          // first word of the region in the buffer
-    const int run = ok ? 3 * myLeaf : 0;                                          // words of the leaf run
     const unsigned long long leaf1 = 1ULL + R.leaf_offset + myFc;                 // payload: data index of the brick's first leaf
-    const int l2 = (2 * lane) % 3;
-    // ---- phase 1 ----
-    for (int t = 0; t < cnt; t++) {
-        const int words = __shfl_sync(0xffffffffu, run, t);
-        if (words == 0) continue;
+    const int g = lane >> 3, s = lane & 7;                                        // group (brick of the round), lane in the group
+    const int s2 = (2 * s) % 3;
+    for (int r = 0; r < cnt; r += 4) {
+        const int t = r + g;                                                      // brick of this group (lanes beyond cnt hold W = 0)
+        const unsigned long long W = __shfl_sync(0xffffffffu, myW, t);
         const unsigned long long w0 = __shfl_sync(0xffffffffu, myRel, t);
-        const unsigned long long d0 = E.leaf_data_mode ? __shfl_sync(0xffffffffu, leaf1, t) : 1ULL;
+        const unsigned long long base = __shfl_sync(0xffffffffu, myBase, t);
+        unsigned long long d0 = 1ULL;
+        if (E.leaf_data_mode) d0 = __shfl_sync(0xffffffffu, leaf1, t);
+        if (W == 0ULL) continue;
+        const int nleaf = __popcll(W), words = 3 * nleaf;
         unsigned long long* out = E.nodes + w0;
         const int odd = (int)(w0 & 1ULL);
-        // relative words [odd, last) are written as aligned pairs, q = odd + 2 * (lane + 32 * i)
+        // relative words [odd, last) are written as aligned pairs, q = odd + 2 * (s + 8 * i)
         const int last = words - ((words - odd) & 1);
-        int f = odd + l2; if (f >= 3) f -= 3;               // field of word q: q % 3 (w0 = 3 * base: a multiple of three words)
-        for (int q = odd + 2 * lane; q < last; q += 64) {
+        int f = odd + s2; if (f >= 3) f -= 3;               // field of word q: q % 3 (w0 = 3 * base: a multiple of three words)
+        for (int q = odd + 2 * s; q < last; q += 16) {
             unsigned long long a, b;                        // binary: (1, 0) (0, ~0) (~0, 1); payload: the data index of the record
             if (f == 0) { a = E.leaf_data_mode ? d0 + (unsigned)(q / 3) : 1ULL; b = 0ULL; }
             else if (f == 1) { a = 0ULL; b = ~0ULL; }
             else { a = ~0ULL; b = E.leaf_data_mode ? d0 + (unsigned)((q + 1) / 3) : 1ULL; }
             st128(out + q, a, b);
-            f = f == 2 ? 0 : f + 1;                         // 64 % 3 == 1
+            f = f == 2 ? 0 : f + 1;                         // 16 % 3 == 1
         }
-        if (odd && lane == 31) out[0] = d0;                 // word 0: the data field of the first record
-        if (last < words && lane == 30) out[words - 1] = ~0ULL;          // the run's last word: an offsets field
-    }
-    // ---- phase 2 ----
-    if (ok) {
-        unsigned long long* o = E.nodes + myRel + 3 * myLeaf;
-        unsigned m = nzb;
-        while (m) {
-            const int k = __ffs(m) - 1;
-            m &= m - 1;
-            const unsigned long long cb = myBase + __popcll(myW & lowmask(8 * k));
-            const unsigned long long off = s_off[(myW >> (8 * k)) & 0xffULL];
+        if (odd && s == 7) out[0] = d0;                     // word 0: the data field of the first record
+        if (last < words && s == 6) out[words - 1] = ~0ULL; // the run's last word: an offsets field
+        // child record of byte s
+        const uint32_t byte = (uint32_t)((W >> (8 * s)) & 0xffULL);
+        const uint32_t nzb = nonzero_bytes(W);
+        if (byte) {
+            unsigned long long* o = out + words + 3 * __popc(nzb & ((1u << s) - 1u));
+            const unsigned long long cb = base + __popcll(W & lowmask(8 * s));
+            const unsigned long long off = s_off[byte];
             if (((uintptr_t)o & 15) == 0) { st128(o, 0ULL, cb); o[2] = off; }
             else { o[0] = 0ULL; st128(o + 1, cb, off); }
-            o += 3;
         }
-        if (E.root_here) {   // gridsize 4: the single brick is the root
+        if (E.root_here && s == 0) {   // gridsize 4: the single brick is the root
+            unsigned long long* o = out + words + 3 * __popc(nzb);
             o[0] = 0ULL;
-            o[1] = myBase + myLeaf;
+            o[1] = base + nleaf;
             o[2] = child_offsets(nzb);
         }
     }

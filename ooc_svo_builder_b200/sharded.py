@@ -393,186 +393,3 @@ def node_count_from_codes(codes: np.ndarray, gridsize: int) -> int:
     if codes.size == 0:
         return 1
     return 1 + sum(np.unique(codes >> np.uint64(3 * (D - d))).size for d in range(1, D + 1))
-
-
-# ----------------------------------------------------------------------------
-# bench.py --gpus N (N > 1): weak scaling of the sharded path
-# ----------------------------------------------------------------------------
-
-BENCH_GRID = 2048                             # 8 logical partitions of 1024^3 (default -l 2048)
-BENCH_LENGTH = 2.0
-
-
-def bench_mesh(world: int, sphere_n: int):
-    """The weak-scaling workload of `bench.py --gpus N` (both arms): one displaced sphere per populated octant of a
-    2048^3 grid. File order: the i-th sphere of the file lies in the octant that rank i+1 owns, so with every rank
-    holding the i-th slice of the file ALL triangle records cross NVLink (nothing is local by construction).
-    Returns (tris (T, 9) float32, gridsize, bbox length)."""
-    from . import meshgen
-    octants = {2: [0, 4], 4: [0, 2, 4, 6], 8: list(range(8))}[world]
-    base = meshgen.displaced_sphere(sphere_n, sphere_n, seed=1, length=1.0)
-    parts = []
-    for i in range(world):
-        o = octants[(i + 1) % world]
-        off = np.array([(o & 1), (o >> 1) & 1, (o >> 2) & 1], dtype=np.float32)
-        t = base.tris.reshape(-1, 3, 3) + off
-        parts.append(t.reshape(-1, 9))
-    return np.ascontiguousarray(np.concatenate(parts), dtype=np.float32), BENCH_GRID, BENCH_LENGTH
-
-
-def bench_workload(world: int) -> str:
-    return ("svo_builder_binary -s 2048 (8 logical partitions of 1024^3), one 2M-triangle displaced sphere in each of %d octants" % world)
-
-
-def bench(args, rank, world, local, dist, peak, peak_src, ClockSampler):
-    import json
-    import torch
-    from . import meshgen
-    from bench import METRIC, UNIT, SPHERE_N
-
-    tris, G, length = bench_mesh(world, SPHERE_N)
-    T = tris.shape[0]
-    lo_t, hi_t = slice_bounds(T, world, rank)
-    db = DistributedBuilder(dist, local)
-    stream = torch.cuda.Stream()
-    db.set_stream(stream)
-    prm = SvoBuilder.make_params(length, G, False)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    # Input path (SVO_BENCH_INPUT): "remote" (default) = remote staging of triangle slices over NVLink peer memory;
-    # "dispatch" = copying all-to-all of triangle records into peer inboxes; "replicated" = every rank holds the whole
-    # mesh. Both peer-memory modes need CUDA IPC; if the box cannot map peer memory, fall back to "replicated"
-    # (decided collectively, reported in config).
-    mode = os.environ.get("SVO_BENCH_INPUT", "remote")
-    per = (T + world - 1) // world
-    ok = torch.ones(1, dtype=torch.int32, device="cuda")
-    if mode != "replicated":
-        try:
-            if mode == "remote":
-                db.enable_slices(per, 9, T)
-            else:
-                db.enable_dispatch(T, 9)
-        except Exception as e:      # noqa: BLE001
-            print("rank %d: peer memory unavailable (%s)" % (rank, e), flush=True)
-            ok.zero_()
-    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-    if not bool(int(ok)):
-        mode = "replicated"
-        db.sliced = False
-    use_dispatch = mode != "replicated"
-    with torch.cuda.stream(stream):
-        if mode == "remote":
-            db.upload_slice(torch.from_numpy(tris[lo_t:hi_t]).cuda())
-            torch.cuda.synchronize()
-        elif mode == "dispatch":
-            d_local = torch.from_numpy(tris[lo_t:hi_t]).cuda()
-            torch.cuda.synchronize()
-            db.set_local_triangles(d_local)
-        else:
-            d_tris = torch.from_numpy(tris).cuda()
-            torch.cuda.synchronize()
-            db.set_triangles(d_tris)
-        for _ in range(max(args.warmup, 3)):
-            flush.zero_()
-            nv, nn, nd = db.step(prm)
-        torch.cuda.synchronize()
-        dist.barrier()
-        sampler = ClockSampler(local)
-        if rank == 0:
-            sampler.start()
-            time.sleep(0.3)
-        t0 = time.time()
-        evs = []
-        for _ in range(args.steps):
-            flush.zero_()
-            dist.barrier()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
-            nv, nn, nd = db.step(prm)
-            e1.record(stream)
-            evs.append((e0, e1))
-        torch.cuda.synchronize()
-        dist.barrier()
-        t1 = time.time()
-        ms = torch.tensor([a.elapsed_time(b) for a, b in evs], dtype=torch.float64, device="cuda")
-    dist.all_reduce(ms, op=dist.ReduceOp.MAX)                     # per step: the slowest rank
-    ms_per_step = float(ms.mean())
-    st = db.sb.stats()
-    launches = torch.tensor([st["kernel_launches"]], dtype=torch.int64, device="cuda")
-    dist.all_reduce(launches)
-    leaf_ms = torch.tensor([st["ms_emit_leaf"], st["ms_vox_small"]], dtype=torch.float64, device="cuda")
-    dist.all_reduce(leaf_ms, op=dist.ReduceOp.MAX)
-
-    # e2e: HOST triangles in, this rank's node / data range out to pinned host memory. Every rank uploads only its
-    # 1/N slice of the triangle file over PCIe; the records then reach the ranks that voxelize them over NVLink
-    # (triangle dispatch; fallback: NCCL all-gather so that each GPU holds the whole mesh), the sharded step runs and
-    # each rank fetches its own range of the output files.
-    nlo, nhi, dlo, dhi = db.sb.shard_ranges()
-    from .api import PinnedBuffer
-    h_slice = torch.empty((per, 9), dtype=torch.float32).pin_memory()
-    h_slice[: hi_t - lo_t].copy_(torch.from_numpy(tris[lo_t:hi_t]))
-    d_all = torch.empty((per if use_dispatch else world * per, 9), dtype=torch.float32, device="cuda")
-    h_nodes = PinnedBuffer(max(nhi - nlo, 1) * 24 + 24 * 4096); h_data = PinnedBuffer(64)
-    e2e = []
-    with torch.cuda.stream(stream):
-        for i in range(3 + args.steps):
-            torch.cuda.synchronize()
-            dist.barrier()
-            t = time.perf_counter()
-            if mode == "remote":
-                db.upload_slice(h_slice.numpy()[: hi_t - lo_t])                                       # PCIe: 1/N of the mesh, NVLink: inside step()
-            elif mode == "dispatch":
-                d_all.copy_(h_slice, non_blocking=True)                                                # PCIe: 1/N of the mesh
-                db.set_local_triangles(d_all[: hi_t - lo_t])                                           # NVLink: inside step()
-            else:
-                d_all[rank * per:(rank + 1) * per].copy_(h_slice, non_blocking=True)                 # PCIe: 1/N of the mesh
-                dist.all_gather_into_tensor(d_all, d_all[rank * per:(rank + 1) * per])                 # NVLink: the rest
-                db.set_triangles(d_all[:T])
-            db.step(prm)
-            a, b, c_, d = db.sb.shard_ranges()
-            db.sb.fetch_nodes(a, b - a, h_nodes.array[: (b - a) * 24])
-            if d > c_:
-                db.sb.fetch_data(c_, d - c_, h_data.array[: (d - c_) * 32])
-            dt = torch.tensor([time.perf_counter() - t], dtype=torch.float64, device="cuda")
-            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-            if i >= 3:
-                e2e.append(float(dt))
-    e2e_s = sum(e2e) / len(e2e)
-    if rank == 0:
-        clocks = sampler.stop(t0, t1)
-        value = T / (ms_per_step * 1e-3)
-        alg = 8 * nv + 24 * nn
-        lm = float(leaf_ms[0])
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "voxels_per_s": nv / (ms_per_step * 1e-3),
-            "config": {"workload": bench_workload(world) + ", partitions sharded over %d B200; each rank starts with 1/%d of the triangle file in "
-                                   "HBM; %s; subtree table exchanged %s" % (
-                                       world, world,
-                                       {"remote": "remote staging: the voxelizer kernel reads the triangle blocks it needs straight from the owner's HBM "
-                                                  "with NVLink loads (no copy), file ordered so that every record crosses NVLink",
-                                        "dispatch": "triangle dispatch = our own all-to-all kernel storing records into peer HBM over NVLink, file ordered "
-                                                    "so that every record crosses NVLink",
-                                        "replicated": "every rank holds the whole mesh"}[mode],
-                                       "over NVLink peer memory (our own kernels)" if (mode == "remote" and os.environ.get("SVO_TABLE_EXCHANGE", "peer") == "peer")
-                                       else "with an NCCL all-reduce"),
-                       "triangle_input": mode,
-                       "gridsize": G, "n_triangles": T, "n_voxels": nv, "n_nodes": nn, "partitions": 8,
-                       "l2": "flushed between timed iterations (256 MB write)", "parallelism": "partition-sharded x%d" % world},
-            "roofline": {"bound": "hbm", "kernel": "k_emit_leaf (per rank)", "achieved": (alg / world) / max(lm, 1e-9) / 1e6, "peak": peak, "unit": "GB/s",
-                         "frac": (alg / world) / max(lm, 1e-9) / 1e6 / peak, "traffic": None, "peak_source": peak_src,
-                         "note": "octree build 8*N + 24*N_nodes bytes per rank / slowest rank's k_emit_leaf time"},
-            "e2e": {"value": T / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(tris.nbytes),
-                    "d2h_bytes_per_step": int(nn * 24 + nd * 32), "ms_per_step": e2e_s * 1e3,
-                    "api": "per rank: pinned H2D of 1/N of the .tridata + %s + sharded step + svo_fetch_* of its "
-                           "file range to pinned host memory (wall clock, max over ranks)" % (
-                               {"remote": "remote staging over NVLink inside the voxelizer", "dispatch": "triangle dispatch over NVLink",
-                                "replicated": "NCCL all-gather over NVLink"}[mode])},
-            "gpu_launches": int(launches) * args.steps, "clocks": clocks,
-            "stage_ms_rank0": {k: st[k] for k in ("ms_dispatch", "ms_peer_wait", "ms_partition", "ms_voxelize", "ms_vox_small", "ms_compact", "ms_build", "ms_emit", "ms_emit_leaf", "ms_clear")},
-            "pairs_rank0": {k: st[k] for k in ("n_pairs", "n_small", "n_medium", "n_large")},
-        }
-        print(json.dumps(line), flush=True)
-    db.close()
-    dist.barrier()
-    dist.destroy_process_group()
