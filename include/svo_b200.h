@@ -200,6 +200,8 @@ int svo_fetch_voxel_codes(svo_ctx* ctx, uint64_t* dst, uint64_t capacity, uint64
  * overflowed take a sized build. Local builds are speculative only on contexts whose previous job used
  * svo_shard_exchange (such a context is expected to keep using it); with the caller's own collective builds
  * are always sized and SVO_E_RETRY never occurs. */
+/* dev_table may be NULL in svo_shard_count / svo_shard_exchange / svo_shard_emit: the library then uses a table of its
+ * own (callers without a device allocator, e.g. the CLI; only meaningful with svo_shard_exchange). */
 int svo_shard_configure(svo_ctx* ctx, int rank, int world);
 int svo_shard_table_size(svo_ctx* ctx, uint64_t* n_u64);
 int svo_shard_count(svo_ctx* ctx, uint64_t* dev_table);
@@ -276,7 +278,8 @@ int svo_ipc_close(void* dev_ptr);
  *                                                    every rank. The window is ONE device allocation holding the
  *                                                    control block, exchange table, block lists and the slice.
  *   <share the window pointer with the peers>        svo_ipc_export / svo_ipc_open across processes, the raw
- *                                                    pointer inside one process
+ *                                                    pointer inside one process (svo_shard_slice_attach enables peer
+ *                                                    access between the devices itself)
  *   svo_shard_slice_attach(windows)                  `world` entries, entry [rank] = own window
  *   svo_shard_slice_upload(src, n_local)     host or device source -> this rank's slice buffer (stream ordered;
  *                                            waits on the device until the peers have finished reading the old one)
@@ -292,6 +295,10 @@ int svo_shard_slice_create(svo_ctx* ctx, uint64_t capacity_tris, int floats_per_
 int svo_shard_slice_attach(svo_ctx* ctx, void* const* windows);
 int svo_shard_exchange(svo_ctx* ctx, uint64_t* dev_table);
 int svo_shard_slice_upload(svo_ctx* ctx, const float* src, uint64_t n_local);
+/* Streamed variant of svo_shard_slice_upload (what svo_triangles_begin / _append are to svo_set_triangles): announce
+ * the slice size, then append chunks from two alternating pinned buffers; same double-buffer contract. */
+int svo_shard_slice_begin(svo_ctx* ctx, uint64_t n_local);
+int svo_shard_slice_append(svo_ctx* ctx, const float* host_chunk, uint64_t n_chunk_tris);
 int svo_shard_slice_publish(svo_ctx* ctx, const svo_params* params, uint64_t n_total);
 int svo_shard_slice_fence(svo_ctx* ctx);
 
@@ -309,6 +316,10 @@ int svo_run(svo_ctx* ctx, const svo_params* params,
             svo_stats* stats);
 
 int svo_get_stats(svo_ctx* ctx, svo_stats* stats);
+
+/* Voxels found in every logical partition (the "found N new voxels" line of the reference's -v output, main.cpp:348;
+ * voxelizer.cpp:289 counts them in `nfilled`). After svo_build; one GPU (a sharded context reports its own slab). */
+int svo_partition_voxel_counts(svo_ctx* ctx, uint64_t* counts, uint64_t capacity);
 
 /* Blocks until all work queued on ctx's stream has finished. */
 int svo_synchronize(svo_ctx* ctx);

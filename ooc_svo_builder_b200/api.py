@@ -31,7 +31,8 @@ ABI_SYMBOLS = [
     "svo_shard_configure", "svo_shard_table_size", "svo_shard_count", "svo_shard_emit", "svo_shard_ranges",
     "svo_shard_dispatch_create", "svo_shard_dispatch_attach", "svo_shard_dispatch_count", "svo_shard_dispatch_send",
     "svo_shard_dispatch_finish", "svo_ipc_export", "svo_ipc_open", "svo_ipc_close",
-    "svo_shard_slice_create", "svo_shard_slice_attach", "svo_shard_slice_upload", "svo_shard_slice_publish", "svo_shard_slice_fence",
+    "svo_shard_slice_create", "svo_shard_slice_attach", "svo_shard_slice_upload", "svo_shard_slice_begin", "svo_shard_slice_append",
+    "svo_shard_slice_publish", "svo_shard_slice_fence", "svo_partition_voxel_counts",
     "svo_shard_exchange", "svo_shard_layout_from_table",
     "svo_run", "svo_get_stats", "svo_synchronize", "svo_host_alloc", "svo_host_free",
 ]
@@ -119,6 +120,9 @@ def load_library(path: str | None = None):
     L.svo_shard_layout_from_table.restype = i32
     L.svo_shard_layout_from_table.argtypes = [C.POINTER(Params), i32, i32, vp, u64, C.POINTER(ShardLayout), vp, vp, u64]
     L.svo_shard_slice_upload.restype = i32; L.svo_shard_slice_upload.argtypes = [vp, vp, u64]
+    L.svo_shard_slice_begin.restype = i32; L.svo_shard_slice_begin.argtypes = [vp, u64]
+    L.svo_shard_slice_append.restype = i32; L.svo_shard_slice_append.argtypes = [vp, vp, u64]
+    L.svo_partition_voxel_counts.restype = i32; L.svo_partition_voxel_counts.argtypes = [vp, vp, u64]
     L.svo_shard_slice_publish.restype = i32; L.svo_shard_slice_publish.argtypes = [vp, C.POINTER(Params), u64]
     L.svo_shard_slice_fence.restype = i32; L.svo_shard_slice_fence.argtypes = [vp]
     L.svo_ipc_export.restype = i32; L.svo_ipc_export.argtypes = [vp, vp]
@@ -434,6 +438,13 @@ class SvoBuilder:
         n = C.c_uint64()
         self._ck(self._lib.svo_fetch_voxel_codes(self._h, out.ctypes.data, out.size, C.byref(n)))
         return out[: n.value]
+
+    def partition_voxel_counts(self) -> np.ndarray:
+        """Voxels per logical partition (the reference's per-partition `found N new voxels`, main.cpp:348)."""
+        P = estimate_partitions(self.params.gridsize, self.params.memory_limit_mb)
+        out = np.zeros(P, dtype=np.uint64)
+        self._ck(self._lib.svo_partition_voxel_counts(self._h, out.ctypes.data, P))
+        return out
 
     def device_nodes(self) -> tuple[int, int]:
         p, n = C.c_void_p(), C.c_uint64()

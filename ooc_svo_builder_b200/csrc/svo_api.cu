@@ -123,6 +123,8 @@ struct svo_ctx {
     BuildInfo* h_info = nullptr;       // pinned copy
     bool fast = false, spec = false, fast_caps_ok = false;
     int jB = 1;                        // levels 1..jB are scanned by k_dense_scan, jB+1..J by k_small_levels
+    int jE = 1;                        // levels jE+1..J are emitted by the single-block top kernel
+    int top_pending = 0;               // k_top stages of phase A whose launch was deferred to phase B (one GPU)
     ull fcap[MAX_LEVELS];              // entries the tile lists of each level hold
 
     // outputs
@@ -174,6 +176,7 @@ struct svo_ctx {
     SliceCtrl* peer_slctrl[MAX_WORLD];
     bool sl_attached = false, sliced = false, filter_attr_set = false;
     ull sl_epoch = 0, xchg_epoch = 0;
+    int sl_world = 0;                        // world size the window was laid out for
     bool exchanged_by_peer_memory = false;   // the table of this job went through svo_shard_exchange (poison-aware)
     bool uses_peer_exchange = false;         // ... and so did an earlier job of this context: local builds may be speculative
     SliceJob sj;
@@ -382,8 +385,14 @@ int launch_voxelizer(svo_ctx* c) {
         }
         const unsigned g2 = (unsigned)c->sm_count * SVO_VOX_MINBLOCKS;
         const size_t smem2 = 2 * (size_t)VOX_BLOCK * c->fpt * sizeof(float);      // per warp: two 32-triangle buffers
-        if (J.P > 1) { k_vox_warp<OWNER, true, 2><<<g2, VOX_BLOCK, smem2, c->stream>>>(J); LAUNCHED(); }
-        else { k_vox_warp<OWNER, false, 2><<<g2, VOX_BLOCK, smem2, c->stream>>>(J); LAUNCHED(); }
+        const bool big = c->prm.gridsize > 4096;
+        if (J.P > 1) {
+            if (big) { k_vox_warp<OWNER, true, 2, true><<<g2, VOX_BLOCK, smem2, c->stream>>>(J); LAUNCHED(); }
+            else { k_vox_warp<OWNER, true, 2, false><<<g2, VOX_BLOCK, smem2, c->stream>>>(J); LAUNCHED(); }
+        } else {
+            if (big) { k_vox_warp<OWNER, false, 2, true><<<g2, VOX_BLOCK, smem2, c->stream>>>(J); LAUNCHED(); }
+            else { k_vox_warp<OWNER, false, 2, false><<<g2, VOX_BLOCK, smem2, c->stream>>>(J); LAUNCHED(); }
+        }
     } else if (c->use_subset) {
         // sharded: compact the triangles that touch this rank's slab once (the owner pass reuses the list)
         if (!OWNER) {
@@ -410,8 +419,14 @@ int launch_voxelizer(svo_ctx* c) {
         const ull units = (c->q_end - c->q_begin + UNIT - 1) / UNIT;
         const unsigned g2 = (unsigned)std::min<ull>((units + VOX_BLOCK / 32 - 1) / (VOX_BLOCK / 32), (ull)c->sm_count * SVO_VOX_MINBLOCKS);
         const size_t smem2 = 2 * (size_t)VOX_BLOCK * c->fpt * sizeof(float);
-        if (J.P > 1) { k_vox_warp<OWNER, true, 0><<<g2, VOX_BLOCK, smem2, c->stream>>>(J); LAUNCHED(); }
-        else { k_vox_warp<OWNER, false, 0><<<g2, VOX_BLOCK, smem2, c->stream>>>(J); LAUNCHED(); }
+        const bool big = c->prm.gridsize > 4096;
+        if (J.P > 1) {
+            if (big) { k_vox_warp<OWNER, true, 0, true><<<g2, VOX_BLOCK, smem2, c->stream>>>(J); LAUNCHED(); }
+            else { k_vox_warp<OWNER, true, 0, false><<<g2, VOX_BLOCK, smem2, c->stream>>>(J); LAUNCHED(); }
+        } else {
+            if (big) { k_vox_warp<OWNER, false, 0, true><<<g2, VOX_BLOCK, smem2, c->stream>>>(J); LAUNCHED(); }
+            else { k_vox_warp<OWNER, false, 0, false><<<g2, VOX_BLOCK, smem2, c->stream>>>(J); LAUNCHED(); }
+        }
     } else if (J.pair_tri == nullptr && J.P > 1) { k_vox_small<OWNER, true, 0><<<blocks_for(c->q_end - c->q_begin, VOX_BLOCK), VOX_BLOCK, smem, c->stream>>>(J); LAUNCHED(); }
     else { k_vox_small<OWNER, false, 0><<<blocks_for(c->q_end - c->q_begin, VOX_BLOCK), VOX_BLOCK, smem, c->stream>>>(J); LAUNCHED(); }
     if (!OWNER) mark(c, EV_VS1);
@@ -733,6 +748,7 @@ int svo_shard_configure(svo_ctx* c, int rank, int world) {
     if (!c) return SVO_E_INVALID;
     if (world < 1 || rank < 0 || rank >= world || (world & (world - 1)) != 0)
         return fail(c, SVO_E_INVALID, "shard world size must be a power of two and 0 <= rank < world");
+    if (world != c->world || rank != c->rank) { c->sl_attached = false; c->attached = false; c->sliced = false; c->dispatched = false; }
     c->world = world;
     c->rank = rank;
     c->partitioned = c->voxelized = c->built = false;
@@ -1313,7 +1329,8 @@ static int build_phase_b(svo_ctx* c, const ull* table) {
             const Level L0 = (J == 0) ? LJ : c->lv[0].view();
             mark(c, EV_EL0);
             if (levels) { k_emit_leaf_levels<<<blocks_for(L0.n, WARPS_PER_BLOCK), WARPS_PER_BLOCK * 32, 0, c->stream>>>(L0, E); LAUNCHED(); }
-            else { k_emit_leaf<<<blocks_for(L0.n, WARPS_PER_BLOCK * EMIT_TILES_PER_WARP), WARPS_PER_BLOCK * 32, 0, c->stream>>>(L0, E); LAUNCHED(); }
+            else if (payload) { k_emit_leaf<true><<<blocks_for(L0.n, WARPS_PER_BLOCK * EMIT_TILES_PER_WARP), WARPS_PER_BLOCK * 32, 0, c->stream>>>(L0, E); LAUNCHED(); }
+            else { k_emit_leaf<false><<<blocks_for(L0.n, WARPS_PER_BLOCK * EMIT_TILES_PER_WARP), WARPS_PER_BLOCK * 32, 0, c->stream>>>(L0, E); LAUNCHED(); }
             mark(c, EV_EL1);
         }
     }
@@ -1426,6 +1443,73 @@ static int fast_check_info(svo_ctx* c) {
     return SVO_OK;
 }
 
+// The single-block stages of a build (k_top, svo_build.cuh) for the current geometry and buffers.
+static int make_topjob(svo_ctx* c, ull* table, TopJob& P) {
+    const int J = c->J, nl = c->nl, top = nl - 1, jB = c->jB;
+    const bool d_even = (c->D % 2) == 0;
+    BuildInfo* dinfo = c->info_buf.as<BuildInfo>();
+    memset(&P, 0, sizeof P);
+    P.info = dinfo;
+    // small levels jB+1..J: lists
+    P.S.j0 = jB + 1; P.S.J = J; P.S.count_only = 0; P.S.info = dinfo;
+    for (int j = jB; j <= J; j++) {
+        P.S.dense[j] = c->dense[j].as<ull>(); P.S.nwords[j] = c->nwords[j]; P.S.bias[j] = c->bias[j];
+        P.S.key[j] = c->lv[j].key.as<ull>(); P.S.mask[j] = c->lv[j].mask.as<ull>(); P.S.fc[j] = c->lv[j].fc.as<ull>();
+        P.S.cap[j] = c->fcap[j];
+    }
+    // sizes of jB+1..J, emission of the levels with at most a few hundred tiles (jE+1..J); the rest is emitted by one
+    // multi-block launch per level
+    int jE = jB;
+    for (int j = jB + 1; j <= J; j++) if (c->nwords[j] > 256) jE = j;
+    c->jE = jE;
+    for (int j = jB; j <= J; j++) { P.F.lv[j] = fast_view(c, j); P.F.lv[j].pl = nullptr; }
+    P.F.J = J; P.F.jf = jE; P.F.jf_up = jB + 1;
+    EmitJob& E = P.F.E;
+    E.nodes = c->nodes.as<ull>();
+    E.cap = c->nodes.cap / SVO_NODE_BYTES;
+    E.info = dinfo;
+    E.leaf_data_mode = c->prm.payload ? 1 : 0;
+    E.virtual_top = d_even ? 0 : 1;
+    E.write_records = 1;
+    E.is_top = (J == top); E.root_here = ((J == top) && d_even) ? 1 : 0;
+    // table entries of this rank
+    P.T.key = c->lv[J].key.as<ull>(); P.T.mask = c->lv[J].mask.as<ull>(); P.T.ps = c->lv[J].ps.as<ull>();
+    for (int j = 0; j <= J; j++) P.T.fc[j] = c->lv[j].fc.as<ull>();
+    P.T.n = c->fcap[J]; P.T.np = &dinfo->count[J]; P.T.J = J; P.T.table = table; P.T.info = dinfo;
+    P.table_words = c->WJ * 4;
+    // merge of the shared upper levels
+    ull n_scratch = 0, rcap = 2;
+    for (int j = J; j <= top; j++) n_scratch += (j == J ? c->WJ : c->nwords[j]);
+    for (int j = J + 1; j <= top; j++) rcap += c->nwords[j] * 73;
+    CK(c->merge_scratch.ensure((size_t)n_scratch * 3 * sizeof(ull)));
+    CK(c->merge_rpos.ensure((size_t)rcap * sizeof(ull)));
+    CK(c->merge_rrec.ensure((size_t)rcap * 3 * sizeof(ull)));
+    MergeJob& Mj = P.M;
+    Mj.table = table; Mj.WJ = c->WJ;
+    Mj.J = J; Mj.top = top; Mj.d_even = d_even ? 1 : 0; Mj.rank = c->rank; Mj.world = c->world;
+    ull off = 0;
+    for (int j = J; j <= top; j++) {
+        Mj.nW[j] = j == J ? c->WJ : c->nwords[j];
+        Mj.M[j] = c->merge_scratch.as<ull>() + off; Mj.S[j] = Mj.M[j] + n_scratch; Mj.B[j] = Mj.S[j] + n_scratch;
+        off += Mj.nW[j];
+    }
+    Mj.wj0 = c->bias[J]; Mj.wj1 = c->bias[J] + c->nwords[J];
+    Mj.rpos = c->merge_rpos.as<ull>(); Mj.rrec = c->merge_rrec.as<ull>(); Mj.rcap = rcap;
+    Mj.keyJ = c->lv[J].key.as<ull>(); Mj.baseJ = c->lv[J].base.as<ull>(); Mj.capJ = c->fcap[J];
+    Mj.info = dinfo;
+    Mj.nodes_cap = c->spec ? c->nodes.cap / SVO_NODE_BYTES : ~0ULL;
+    return SVO_OK;
+}
+static int launch_top(svo_ctx* c, ull* table, int stages) {
+    if (!stages) return SVO_OK;
+    TopJob P;
+    int rc = make_topjob(c, table, P);
+    if (rc) return rc;
+    P.stages = stages;
+    k_top<<<1, 1024, 0, c->stream>>>(P); LAUNCHED();
+    return SVO_OK;
+}
+
 static int fast_phase_a(svo_ctx* c, ull* table, bool fill_table, bool force_sync) {
     const int J = c->J;
     const bool payload = c->prm.payload != 0;
@@ -1461,15 +1545,11 @@ static int fast_phase_a(svo_ctx* c, ull* table, bool fill_table, bool force_sync
             k_dense_scan<<<(unsigned)nt, DS_THREADS, 0, c->stream>>>(Dj); LAUNCHED();
             c->lb_tickets += nt;
         }
-        if (jB < J) {
+        if (count_only && jB < J) {
             SmallLevelsJob S;
             memset(&S, 0, sizeof S);
-            S.j0 = jB + 1; S.J = J; S.count_only = count_only; S.info = dinfo;
-            for (int j = jB; j <= J; j++) {
-                S.dense[j] = c->dense[j].as<ull>(); S.nwords[j] = c->nwords[j]; S.bias[j] = c->bias[j];
-                S.key[j] = c->lv[j].key.as<ull>(); S.mask[j] = c->lv[j].mask.as<ull>(); S.fc[j] = c->lv[j].fc.as<ull>();
-                S.cap[j] = c->fcap[j];
-            }
+            S.j0 = jB + 1; S.J = J; S.count_only = 1; S.info = dinfo;
+            for (int j = jB; j <= J; j++) { S.dense[j] = c->dense[j].as<ull>(); S.nwords[j] = c->nwords[j]; S.bias[j] = c->bias[j]; }
             k_small_levels<<<1, 1024, 0, c->stream>>>(S); LAUNCHED();
         }
         return SVO_OK;
@@ -1497,7 +1577,7 @@ static int fast_phase_a(svo_ctx* c, ull* table, bool fill_table, bool force_sync
     int rc = dense_pass(0);
     if (rc) return rc;
     {   // bricks: lists, leaf ranks, subtree sizes of levels 0 and 1
-        const ull n1 = spec ? c->fcap[1] : c->h_info->count[1];
+        const ull n1 = spec ? std::min<ull>(c->fcap[1], c->nwords[1]) : c->h_info->count[1];
         const ull nt = std::max<ull>((n1 + BP_TILE - 1) / BP_TILE, 1);
         if ((rc = lookback_prepare(c, nt))) return rc;
         BrickJob B;
@@ -1510,29 +1590,18 @@ static int fast_phase_a(svo_ctx* c, ull* table, bool fill_table, bool force_sync
         k_brick_pass<<<(unsigned)nt, BP_WARPS * 32, 0, c->stream>>>(B); LAUNCHED();
         c->lb_tickets += nt;
     }
-    // subtree sizes of the levels above: look-back scans for the big ones, one block for the small ones
+    // subtree sizes of the big levels above: look-back scans (the small levels follow in k_top)
     for (int j = 2; j <= jB; j++) {
         SizeOp op{ c->lv[j].mask.as<ull>(), c->lv[j].fc.as<ull>(), c->lv[j - 1].ps.as<ull>() };
-        const ull n = spec ? c->fcap[j] : c->h_info->count[j];
+        const ull n = spec ? std::min<ull>(c->fcap[j], c->nwords[j]) : c->h_info->count[j];
         if ((rc = exscan(c, op, n, c->lv[j].ps.as<ull>(), &dinfo->count[j], dinfo))) return rc;
     }
-    if (jB < J) {
-        FusedJob F;
-        memset(&F, 0, sizeof F);
-        for (int j = jB; j <= J; j++) { F.lv[j] = fast_view(c, j); F.lv[j].pl = nullptr; }
-        F.J = J; F.jf = jB + 1; F.E.info = dinfo;
-        k_fused_up<<<1, 1024, 0, c->stream>>>(F); LAUNCHED();
-    }
-    // ---- this rank's table entries ----
-    if (fill_table) {
-        CK(cudaMemsetAsync(table, 0, (size_t)c->WJ * 4 * sizeof(ull), c->stream));
-        TableFillJob Tf;
-        memset(&Tf, 0, sizeof Tf);
-        Tf.key = c->lv[J].key.as<ull>(); Tf.mask = c->lv[J].mask.as<ull>(); Tf.ps = c->lv[J].ps.as<ull>();
-        for (int j = 0; j <= J; j++) Tf.fc[j] = c->lv[j].fc.as<ull>();
-        Tf.n = c->fcap[J]; Tf.np = &dinfo->count[J]; Tf.J = J; Tf.table = table; Tf.info = dinfo;
-        const ull nJ = spec ? std::min<ull>(c->fcap[J], c->nwords[J]) : c->h_info->count[J];
-        if (nJ) { k_table_fill<<<blocks_for(nJ, 256), 256, 0, c->stream>>>(Tf); LAUNCHED(); }
+    // ---- everything one block does: small-level lists and sizes, this rank's table entries. On one GPU the launch is
+    // deferred to phase B, where the merge, the scattered upper records and the top-level emission join it ----
+    c->top_pending = TOP_LISTS | TOP_SIZES | (fill_table ? TOP_TABLE : 0);
+    if (c->world > 1) {
+        if ((rc = launch_top(c, table, c->top_pending))) return rc;
+        c->top_pending = 0;
     }
     mark(c, EV_CMP1);
     c->tl.stamp("phaseA_launched");
@@ -1541,71 +1610,41 @@ static int fast_phase_a(svo_ctx* c, ull* table, bool fill_table, bool force_sync
 }
 
 static int fast_phase_b(svo_ctx* c, ull* table) {
-    const int J = c->J, nl = c->nl, top = nl - 1, jB = c->jB;
+    const int J = c->J;
     const bool payload = c->prm.payload != 0;
-    const bool d_even = (c->D % 2) == 0;
     BuildInfo* dinfo = c->info_buf.as<BuildInfo>();
     const bool spec = c->spec;
-    // ---- merged upper levels, file range of this rank, bases of its top tiles ----
-    ull n_scratch = 0, rcap = 2;
-    for (int j = J; j <= top; j++) n_scratch += (j == J ? c->WJ : c->nwords[j]);
-    for (int j = J + 1; j <= top; j++) rcap += c->nwords[j] * 73;
-    CK(c->merge_scratch.ensure((size_t)n_scratch * 3 * sizeof(ull)));
-    CK(c->merge_rpos.ensure((size_t)rcap * sizeof(ull)));
-    CK(c->merge_rrec.ensure((size_t)rcap * 3 * sizeof(ull)));
-    {
-        MergeJob Mj;
-        memset(&Mj, 0, sizeof Mj);
-        Mj.table = table; Mj.WJ = c->WJ;
-        Mj.J = J; Mj.top = top; Mj.d_even = d_even ? 1 : 0; Mj.rank = c->rank; Mj.world = c->world;
-        ull off = 0;
-        for (int j = J; j <= top; j++) {
-            Mj.nW[j] = j == J ? c->WJ : c->nwords[j];
-            Mj.M[j] = c->merge_scratch.as<ull>() + off; Mj.S[j] = Mj.M[j] + n_scratch; Mj.B[j] = Mj.S[j] + n_scratch;
-            off += Mj.nW[j];
-        }
-        Mj.wj0 = c->bias[J]; Mj.wj1 = c->bias[J] + c->nwords[J];
-        Mj.rpos = c->merge_rpos.as<ull>(); Mj.rrec = c->merge_rrec.as<ull>(); Mj.rcap = rcap;
-        Mj.keyJ = c->lv[J].key.as<ull>(); Mj.baseJ = c->lv[J].base.as<ull>(); Mj.capJ = c->fcap[J];
-        Mj.info = dinfo;
-        Mj.nodes_cap = spec ? c->nodes.cap / SVO_NODE_BYTES : ~0ULL;
-        k_shard_merge<<<1, 1024, 0, c->stream>>>(Mj); LAUNCHED();
-    }
+    int rc;
     if (!spec) {
-        // ---- read-back #2: record counts and this rank's range ----
-        int rc = read_info(c, "sync2_wait");
-        if (rc) return rc;
+        // ---- merged upper levels; read-back #2: record counts and this rank's range ----
+        if ((rc = launch_top(c, table, c->top_pending | TOP_MERGE))) return rc;
+        c->top_pending = 0;
+        if (c->world == 1) mark(c, EV_CMP1);
+        if ((rc = read_info(c, "sync2_wait"))) return rc;
         c->tl.stamp("sync2_done");
         if ((rc = fast_check_info(c))) return rc;
         if (c->h_info->overflow) { c->dense_clean = false; return fail(c, SVO_E_CUDA, "octree build: list capacity exceeded in a sized build (internal error)"); }
         const ull n_local = c->h_info->node_hi - c->h_info->node_lo;
         CK(c->nodes.ensure((size_t)(n_local ? n_local : 1) * SVO_NODE_BYTES));
+        mark(c, EV_EMIT0);
+        if ((rc = launch_top(c, table, TOP_SCATTER | TOP_EMIT))) return rc;
+    } else {
+        // ---- one launch: [small-level lists and sizes, table,] merge, scattered upper records, top-level emission ----
+        mark(c, EV_EMIT0);
+        if ((rc = launch_top(c, table, c->top_pending | TOP_MERGE | TOP_SCATTER | TOP_EMIT))) return rc;
+        c->top_pending = 0;
     }
     EmitJob E;
-    memset(&E, 0, sizeof E);
-    E.nodes = c->nodes.as<ull>();
-    E.cap = c->nodes.cap / SVO_NODE_BYTES;
-    E.info = dinfo;
-    E.leaf_data_mode = payload ? 1 : 0;
-    E.virtual_top = d_even ? 0 : 1;
-    E.write_records = 1;
-    mark(c, EV_EMIT0);
-    k_scatter_records<<<(unsigned)std::min<ull>(blocks_for(rcap, 256), 64), 256, 0, c->stream>>>(c->merge_rpos.as<ull>(), c->merge_rrec.as<ull>(), rcap, &dinfo->n_upper, E); LAUNCHED();
+    {
+        TopJob P;
+        if ((rc = make_topjob(c, table, P))) return rc;
+        E = P.F.E;
+    }
+    const int top = c->nl - 1;
+    const bool d_even = (c->D % 2) == 0;
     auto launch_n = [&](int j) -> ull { return spec ? std::min<ull>(c->fcap[j], c->nwords[j]) : c->h_info->count[j]; };
     const int root_level_here = (J == top) && d_even;
-    // the top levels with at most a few hundred tiles are emitted by ONE block (each level writes the bases of the
-    // next), everything below by one multi-block launch per level
-    int jE = jB;
-    for (int j = jB + 1; j <= J; j++) if (c->nwords[j] > 256) jE = j;
-    if (jE < J) {
-        FusedJob F;
-        memset(&F, 0, sizeof F);
-        for (int j = jE; j <= J; j++) F.lv[j] = fast_view(c, j);
-        F.J = J; F.jf = jE;
-        F.E = E; F.E.is_top = (J == top); F.E.root_here = root_level_here;
-        k_fused_emit<<<1, 1024, 0, c->stream>>>(F); LAUNCHED();
-    }
-    for (int j = jE; j >= 1; j--) {
+    for (int j = c->jE; j >= 1; j--) {
         const ull n = launch_n(j);
         if (!n) continue;
         E.is_top = (j == top);
@@ -1615,7 +1654,9 @@ static int fast_phase_b(svo_ctx* c, ull* table) {
     E.is_top = 0; E.root_here = 0;
     mark(c, EV_EL0);
     if (launch_n(0)) {
-        k_emit_leaf<<<blocks_for(launch_n(0), WARPS_PER_BLOCK * EMIT_TILES_PER_WARP), WARPS_PER_BLOCK * 32, 0, c->stream>>>(fast_view(c, 0), E); LAUNCHED();
+        const unsigned grid = blocks_for(launch_n(0), WARPS_PER_BLOCK * EMIT_TILES_PER_WARP);
+        if (payload) { k_emit_leaf<true><<<grid, WARPS_PER_BLOCK * 32, 0, c->stream>>>(fast_view(c, 0), E); LAUNCHED(); }
+        else { k_emit_leaf<false><<<grid, WARPS_PER_BLOCK * 32, 0, c->stream>>>(fast_view(c, 0), E); LAUNCHED(); }
     }
     mark(c, EV_EL1);
     mark(c, EV_EMIT1);
@@ -1641,7 +1682,7 @@ static int fast_phase_b(svo_ctx* c, ull* table) {
             CK(c->owner.ensure((size_t)c->n_voxels_local * sizeof(uint32_t)));
             CK(cudaMemsetAsync(c->owner.p, 0xff, (size_t)c->n_voxels_local * sizeof(uint32_t), c->stream));
             c->lv[0].n = c->h_info->count[0];
-            int rc = launch_voxelizer<true>(c);
+            rc = launch_voxelizer<true>(c);
             if (rc) return rc;
             PayloadJob Pj;
             memset(&Pj, 0, sizeof Pj);
@@ -1759,8 +1800,8 @@ int svo_shard_table_size(svo_ctx* c, uint64_t* n_u64) {
 int svo_shard_count(svo_ctx* c, uint64_t* dev_table) {
     if (!c) return SVO_E_INVALID;
     if (!c->voxelized) return fail(c, SVO_E_INVALID, "svo_shard_count before svo_voxelize");
-    if (!dev_table) return fail(c, SVO_E_INVALID, "dev_table is NULL");
     CK(cudaSetDevice(c->device));
+    if (!dev_table) { CK(c->table_own.ensure((size_t)c->WJ * 4 * sizeof(ull))); dev_table = c->table_own.as<uint64_t>(); }      // library-owned table
     c->fast = fast_path_applies(c);
     if (c->fast) return fast_phase_a(c, (ull*)dev_table, true, false);
     return build_phase_a(c, (ull*)dev_table);
@@ -1770,6 +1811,7 @@ int svo_shard_exchange(svo_ctx* c, uint64_t* dev_table) {
     if (!c) return SVO_E_INVALID;
     if (!c->phase_a_done) return fail(c, SVO_E_INVALID, "svo_shard_exchange before svo_shard_count");
     if (!c->sliced) return fail(c, SVO_E_INVALID, "svo_shard_exchange needs the peer windows of svo_shard_slice_*; otherwise sum the table with your own collective");
+    if (!dev_table) dev_table = c->table_own.as<uint64_t>();
     if (!dev_table) return fail(c, SVO_E_INVALID, "dev_table is NULL");
     const size_t bytes = (size_t)c->WJ * 4 * sizeof(ull);
     if (bytes > XTABLE_BYTES) return fail(c, SVO_E_RANGE, "subtree table is larger than the exchange window; sum it with your own collective");
@@ -1793,6 +1835,7 @@ int svo_shard_exchange(svo_ctx* c, uint64_t* dev_table) {
 int svo_shard_emit(svo_ctx* c, const uint64_t* dev_table, uint64_t* n_voxels, uint64_t* n_nodes, uint64_t* n_data) {
     if (!c) return SVO_E_INVALID;
     if (!c->phase_a_done) return fail(c, SVO_E_INVALID, "svo_shard_emit before svo_shard_count");
+    if (!dev_table) dev_table = c->table_own.as<uint64_t>();
     if (!dev_table) return fail(c, SVO_E_INVALID, "dev_table is NULL");
     CK(cudaSetDevice(c->device));
     int rc = c->fast ? fast_build(c, (ull*)dev_table, false) : build_phase_b(c, (const ull*)dev_table);
@@ -2021,6 +2064,7 @@ int svo_shard_slice_create(svo_ctx* c, uint64_t capacity_tris, int fpt, void** d
     CK(c->sl_cursor.ensure(MAX_WORLD * sizeof(ull)));
     CK(cudaMemset(c->sl_cursor.p, 0, MAX_WORLD * sizeof(ull)));
     c->slice_cap = capacity_tris;
+    c->sl_world = c->world;
     c->slice_fpt = fpt;
     c->slice_n_local = 0;
     c->sl_epoch = 0; c->xchg_epoch = 0; c->uses_peer_exchange = false;
@@ -2032,9 +2076,19 @@ int svo_shard_slice_attach(svo_ctx* c, void* const* windows) {
     if (!c) return SVO_E_INVALID;
     if (!c->window.p) return fail(c, SVO_E_INVALID, "svo_shard_slice_attach before svo_shard_slice_create");
     if (!windows) return fail(c, SVO_E_INVALID, "peer window array is NULL");
+    if (c->world != c->sl_world) return fail(c, SVO_E_INVALID, "svo_shard_configure changed the world size after svo_shard_slice_create: create the window again");
+    CK(cudaSetDevice(c->device));
     const WindowLayout L = window_layout(c->sl_cap_blocks, c->slice_fpt, c->world);
     for (int r = 0; r < c->world; r++) {
         if (!windows[r]) return fail(c, SVO_E_INVALID, "a peer window pointer is NULL");
+        // a raw pointer of another device of THIS process (several contexts in one process): map it. Pointers that came
+        // through svo_ipc_open are mapped already.
+        cudaPointerAttributes pa;
+        if (cudaPointerGetAttributes(&pa, windows[r]) == cudaSuccess && pa.type == cudaMemoryTypeDevice && pa.device != c->device) {
+            const cudaError_t pe = cudaDeviceEnablePeerAccess(pa.device, 0);
+            if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) { (void)cudaGetLastError(); return fail(c, SVO_E_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(pe)); }
+        }
+        (void)cudaGetLastError();
         char* w = (char*)windows[r];
         c->peer_slctrl[r] = (SliceCtrl*)(w + L.ctrl);
         c->peer_xtable[r] = (ull*)(w + L.xtable);
@@ -2069,9 +2123,45 @@ int svo_shard_slice_upload(svo_ctx* c, const float* src, uint64_t n_local) {
     return SVO_OK;
 }
 
+int svo_shard_slice_begin(svo_ctx* c, uint64_t n_local) {
+    if (!c) return SVO_E_INVALID;
+    if (!c->sl_attached) return fail(c, SVO_E_INVALID, "svo_shard_slice_begin before svo_shard_slice_attach");
+    if (n_local > c->slice_cap) return fail(c, SVO_E_RANGE, "slice is larger than the capacity given to svo_shard_slice_create");
+    int rc = svo_shard_slice_fence(c);                      // peers may still be reading the previous contents
+    if (rc) return rc;
+    for (int i = 0; i < EV_COUNT; i++) c->ev_set[i] = false;
+    mark(c, EV_UP0);
+    if (!c->up_ev[0]) { CK(cudaEventCreateWithFlags(&c->up_ev[0], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&c->up_ev[1], cudaEventDisableTiming)); }
+    c->up_slot = 0; c->up_pending[0] = c->up_pending[1] = false;
+    c->slice_n_local = n_local;
+    c->stream_fill = 0;
+    if (n_local == 0) mark(c, EV_UP1);
+    return SVO_OK;
+}
+
+int svo_shard_slice_append(svo_ctx* c, const float* host_chunk, uint64_t n) {
+    if (!c) return SVO_E_INVALID;
+    if (!c->sl_attached) return fail(c, SVO_E_INVALID, "svo_shard_slice_append before svo_shard_slice_attach");
+    if (c->stream_fill + n > c->slice_n_local) return fail(c, SVO_E_RANGE, "more triangles appended than announced");
+    if (n && !host_chunk) return fail(c, SVO_E_INVALID, "host_chunk is NULL");
+    CK(cudaSetDevice(c->device));
+    const size_t rec = (size_t)c->slice_fpt * sizeof(float);
+    if (n) CK(cudaMemcpyAsync((char*)c->slice.p + c->stream_fill * rec, host_chunk, n * rec, cudaMemcpyHostToDevice, c->stream));
+    // same double-buffer contract as svo_triangles_append: on return every EARLIER chunk has been copied
+    const int slot = c->up_slot;
+    CK(cudaEventRecord(c->up_ev[slot], c->stream));
+    c->up_pending[slot] = true;
+    if (c->up_pending[slot ^ 1]) { CK(cudaEventSynchronize(c->up_ev[slot ^ 1])); c->up_pending[slot ^ 1] = false; }
+    c->up_slot = slot ^ 1;
+    c->stream_fill += n;
+    if (c->stream_fill == c->slice_n_local) mark(c, EV_UP1);
+    return SVO_OK;
+}
+
 int svo_shard_slice_publish(svo_ctx* c, const svo_params* params, uint64_t n_total) {
     if (!c) return SVO_E_INVALID;
     if (!c->sl_attached) return fail(c, SVO_E_INVALID, "svo_shard_slice_publish before svo_shard_slice_attach");
+    if (c->world != c->sl_world) return fail(c, SVO_E_INVALID, "svo_shard_configure changed the world size after svo_shard_slice_create: create the window again");
     int rc = validate_params(c, params);
     if (rc) return rc;
     if ((params->payload ? 21 : 9) != c->slice_fpt) return fail(c, SVO_E_INVALID, "params.payload does not match the slices' floats_per_tri");
@@ -2212,6 +2302,23 @@ int svo_fetch_voxel_codes(svo_ctx* c, uint64_t* dst, uint64_t capacity, uint64_t
     CK(c->codes.ensure((size_t)n * sizeof(ull)));
     k_voxel_codes<<<blocks_for(c->lv[0].n, WARPS_PER_BLOCK), WARPS_PER_BLOCK * 32, 0, c->stream>>>(c->lv[0].view(), c->codes.as<ull>(), n); LAUNCHED();
     CK(cudaMemcpyAsync(dst, c->codes.p, (size_t)n * sizeof(ull), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return SVO_OK;
+}
+
+int svo_partition_voxel_counts(svo_ctx* c, uint64_t* counts, uint64_t capacity) {
+    if (!c) return SVO_E_INVALID;
+    if (!c->built) return fail(c, SVO_E_INVALID, "svo_partition_voxel_counts before svo_build");
+    if (!counts || capacity < c->P) return fail(c, SVO_E_RANGE, "counts capacity is smaller than the partition count");
+    CK(cudaSetDevice(c->device));
+    CK(c->part_counts.ensure(c->P * sizeof(ull)));
+    CK(cudaMemsetAsync(c->part_counts.p, 0, c->P * sizeof(ull), c->stream));
+    if (c->lv[0].n) {
+        // a level-0 word covers 6 Morton bits, a partition 3 * (D - k): partition of a brick = key >> (3 (D - k) - 6)
+        const int sh = 3 * (c->D - c->k) - 6;
+        k_partition_voxels<<<blocks_for(c->lv[0].n, 256), 256, 0, c->stream>>>(c->lv[0].key.as<ull>(), c->lv[0].mask.as<ull>(), c->lv[0].n, sh, c->part_counts.as<ull>()); LAUNCHED();
+    }
+    CK(cudaMemcpyAsync(counts, c->part_counts.p, c->P * sizeof(ull), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     return SVO_OK;
 }

@@ -115,8 +115,7 @@ struct SmallLevelsJob {
     unsigned long long cap[MAX_LEVELS];
     BuildInfo* info;
 };
-__global__ void __launch_bounds__(1024) k_small_levels(SmallLevelsJob S) {
-    if (build_aborted(S.info)) return;
+__device__ __forceinline__ void small_levels_body(const SmallLevelsJob& S) {
     for (int j = S.j0; j <= S.J; j++) {
         const unsigned long long n = S.nwords[j];
         unsigned long long c_nz = 0, c_pc = 0;
@@ -146,11 +145,15 @@ __global__ void __launch_bounds__(1024) k_small_levels(SmallLevelsJob S) {
         __syncthreads();
     }
 }
+__global__ void __launch_bounds__(1024) k_small_levels(SmallLevelsJob S) {
+    if (build_aborted(S.info)) return;
+    small_levels_body(S);
+}
 
 // ---------------------------------------------------------------------------
 // k_brick_pass
 // ---------------------------------------------------------------------------
-constexpr int BP_WARPS = 8, BP_PER_WARP = 4, BP_TILE = BP_WARPS * BP_PER_WARP;     // level-1 tiles per block
+constexpr int BP_WARPS = 8, BP_PER_WARP = 8, BP_TILE = BP_WARPS * BP_PER_WARP;     // level-1 tiles per block
 struct BrickJob {
     Level L1;                             // key, mask, fc in; ps out (n + 1)
     Level L0;                             // key, mask, fc, ps out
@@ -159,6 +162,21 @@ struct BrickJob {
     BuildInfo* info;
     unsigned long long* state; unsigned long long* ticket; unsigned long long ticket_base, epoch;
 };
+// this lane's two bricks (bits lane, lane + 32) of level-1 tile (W1, K1): Morton-layout words and leaves | sizes << 16
+__device__ __forceinline__ void brick_pair(const unsigned long long* dense0, unsigned long long W1, unsigned long long K1, int lane,
+                                           unsigned long long (&m)[2], unsigned (&v)[2]) {
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const int bit = lane + 32 * h;
+        m[h] = 0ULL;
+        if ((W1 >> bit) & 1ULL) m[h] = linear_to_morton64(__ldcg(dense0 + ((K1 << 6) | (unsigned long long)bit)));
+        const unsigned leaves = (unsigned)__popcll(m[h]);
+        v[h] = leaves | ((leaves + (unsigned)__popc(nonzero_bytes(m[h]))) << 16);
+    }
+}
+// Two sweeps over the block's tiles: totals first (nothing is kept in registers, so that several blocks fit an SM and
+// the whole look-back chain runs in one wave), then -- with the block's prefix known -- the bricks are gathered again
+// (L1 / L2 hits) and written.
 __global__ void __launch_bounds__(BP_WARPS * 32) k_brick_pass(BrickJob B) {
     __shared__ unsigned long long s_tile, s_prefix[3];
     __shared__ unsigned s_tot[BP_TILE][3], s_ex[BP_TILE][3];
@@ -168,56 +186,42 @@ __global__ void __launch_bounds__(BP_WARPS * 32) k_brick_pass(BrickJob B) {
     const unsigned long long tile = s_tile;
     const unsigned long long n1 = level_n(B.L1);
     if (tile * BP_TILE >= n1) {
-        if (tile == 0 && threadIdx.x == 0) { B.L0.fc[0] = 0ULL; B.L0.ps[0] = 0ULL; B.L1.ps[0] = 0ULL; B.info->n_leaves_local = 0ULL; }
+        if (tile == 0 && threadIdx.x == 0) { B.L0.fc[0] = 0ULL; B.L0.ps[0] = 0ULL; B.L1.ps[0] = 0ULL; B.info->n_leaves_local = 0ULL; B.info->n_brick_records = 0ULL; }
         return;
     }
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    unsigned long long m[BP_PER_WARP][2];         // this lane's two bricks of each tile, Morton layout
-    unsigned pre[BP_PER_WARP][2];                 // exclusive prefix inside the tile: leaves | sizes << 16
-    unsigned long long W1[BP_PER_WARP], K1[BP_PER_WARP], F1[BP_PER_WARP];
-#pragma unroll
+    const unsigned long long tw0 = tile * BP_TILE + (unsigned long long)wid * BP_PER_WARP;
+    // lane q of the warp holds the descriptor of the warp's q-th tile
+    unsigned long long myW1 = 0ULL, myK1 = 0ULL, myF1 = 0ULL;
+    if (lane < BP_PER_WARP && tw0 + lane < n1) { myW1 = B.L1.mask[tw0 + lane]; myK1 = B.L1.key[tw0 + lane]; myF1 = B.L1.fc[tw0 + lane]; }
+    // ---- sweep 1: totals of every tile ----
+#pragma unroll 2
     for (int q = 0; q < BP_PER_WARP; q++) {
-        const unsigned long long t = tile * BP_TILE + (unsigned long long)wid * BP_PER_WARP + q;
-        W1[q] = 0ULL; K1[q] = 0ULL; F1[q] = 0ULL;
-        if (t < n1) { W1[q] = B.L1.mask[t]; K1[q] = B.L1.key[t]; F1[q] = B.L1.fc[t]; }
-        unsigned v[2];
+        const unsigned long long W1 = __shfl_sync(0xffffffffu, myW1, q), K1 = __shfl_sync(0xffffffffu, myK1, q);
+        unsigned long long m[2]; unsigned v[2];
+        brick_pair(B.dense0, W1, K1, lane, m, v);
+        unsigned tot = v[0] + v[1];                    // leaves <= 4096, sizes <= 4608 per tile: no carry between the halves
 #pragma unroll
-        for (int h = 0; h < 2; h++) {
-            const int bit = lane + 32 * h;
-            m[q][h] = 0ULL;
-            if ((W1[q] >> bit) & 1ULL) m[q][h] = linear_to_morton64(__ldcg(B.dense0 + ((K1[q] << 6) | (unsigned long long)bit)));
-            const unsigned leaves = (unsigned)__popcll(m[q][h]);
-            v[h] = leaves | ((leaves + (unsigned)__popc(nonzero_bytes(m[q][h]))) << 16);
-        }
-        // exclusive prefix over the 64 children in bit order (bits 0..31 = half 0)
-        unsigned i0 = v[0], i1 = v[1];
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const unsigned a = __shfl_up_sync(0xffffffffu, i0, d), b = __shfl_up_sync(0xffffffffu, i1, d);
-            if (lane >= d) { i0 += a; i1 += b; }
-        }
-        const unsigned t0 = __shfl_sync(0xffffffffu, i0, 31), t1 = __shfl_sync(0xffffffffu, i1, 31);
-        pre[q][0] = i0 - v[0];
-        pre[q][1] = t0 + i1 - v[1];
+        for (int d = 16; d > 0; d >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, d);
         if (lane == 0) {
-            const unsigned tot = t0 + t1;              // leaves <= 4096, sizes <= 4608: no carry between the halves
             const int s = wid * BP_PER_WARP + q;
             s_tot[s][0] = tot & 0xffffu;
             s_tot[s][1] = tot >> 16;
-            s_tot[s][2] = t < n1 ? (tot >> 16) + (unsigned)__popcll(W1[q]) + (unsigned)__popc(nonzero_bytes(W1[q])) : 0u;   // S of the level-1 tile
+            s_tot[s][2] = W1 ? (tot >> 16) + (unsigned)__popcll(W1) + (unsigned)__popc(nonzero_bytes(W1)) : 0u;   // S of the level-1 tile
         }
     }
     __syncthreads();
     if (wid == 0) {
+        // exclusive scan over the block's BP_TILE = 64 tiles (two per lane) and the look-back
         unsigned long long tot[3], prefix[3];
-        unsigned x[3];
 #pragma unroll
         for (int c = 0; c < 3; c++) {
-            x[c] = s_tot[lane][c];
-            unsigned inc = x[c];
+            const unsigned x0 = s_tot[2 * lane][c], x1 = s_tot[2 * lane + 1][c];
+            unsigned inc = x0 + x1;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) { const unsigned a = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += a; }
-            s_ex[lane][c] = inc - x[c];
+            s_ex[2 * lane][c] = inc - x0 - x1;
+            s_ex[2 * lane + 1][c] = inc - x1;
             tot[c] = __shfl_sync(0xffffffffu, inc, 31);
         }
         lookback<3>(B.state, B.epoch, tile, tot, prefix, &B.info->overflow);
@@ -234,24 +238,35 @@ __global__ void __launch_bounds__(BP_WARPS * 32) k_brick_pass(BrickJob B) {
         }
     }
     __syncthreads();
-#pragma unroll
+    // ---- sweep 2: the bricks ----
+#pragma unroll 2
     for (int q = 0; q < BP_PER_WARP; q++) {
-        const unsigned long long t = tile * BP_TILE + (unsigned long long)wid * BP_PER_WARP + q;
-        if (t >= n1) continue;
+        const unsigned long long W1 = __shfl_sync(0xffffffffu, myW1, q), K1 = __shfl_sync(0xffffffffu, myK1, q), F1 = __shfl_sync(0xffffffffu, myF1, q);
+        if (W1 == 0ULL) continue;                          // (warp-uniform) beyond the list
+        unsigned long long m[2]; unsigned v[2];
+        brick_pair(B.dense0, W1, K1, lane, m, v);
+        unsigned i0 = v[0], i1 = v[1];                     // exclusive prefix over the 64 children in bit order (bits 0..31 = half 0)
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned a = __shfl_up_sync(0xffffffffu, i0, d), b = __shfl_up_sync(0xffffffffu, i1, d);
+            if (lane >= d) { i0 += a; i1 += b; }
+        }
+        const unsigned t0 = __shfl_sync(0xffffffffu, i0, 31);
+        const unsigned pre[2] = { i0 - v[0], t0 + i1 - v[1] };
         const int s = wid * BP_PER_WARP + q;
         const unsigned long long lp = s_prefix[0] + s_ex[s][0], sp = s_prefix[1] + s_ex[s][1];
-        if (lane == 0) B.L1.ps[t] = s_prefix[2] + s_ex[s][2];
+        if (lane == 0) B.L1.ps[tw0 + q] = s_prefix[2] + s_ex[s][2];
 #pragma unroll
         for (int h = 0; h < 2; h++) {
             const int bit = lane + 32 * h;
-            if (!((W1[q] >> bit) & 1ULL)) continue;
-            const unsigned long long c = F1[q] + __popcll(W1[q] & lowmask(bit));
+            if (!((W1 >> bit) & 1ULL)) continue;
+            const unsigned long long c = F1 + __popcll(W1 & lowmask(bit));
             if (c >= B.L0.cap) continue;                   // (the overflow flag is already set by the level-1 scan)
-            const unsigned long long ck = (K1[q] << 6) | (unsigned long long)bit;
+            const unsigned long long ck = (K1 << 6) | (unsigned long long)bit;
             B.L0.key[c] = ck;
-            B.L0.mask[c] = m[q][h];
-            B.L0.fc[c] = lp + (pre[q][h] & 0xffffu);
-            B.L0.ps[c] = sp + (pre[q][h] >> 16);
+            B.L0.mask[c] = m[h];
+            B.L0.fc[c] = lp + (pre[h] & 0xffffu);
+            B.L0.ps[c] = sp + (pre[h] >> 16);
             if (B.tileidx) B.tileidx[ck] = (uint32_t)c;
         }
     }
@@ -273,9 +288,8 @@ struct MergeJob {
     BuildInfo* info;
     unsigned long long nodes_cap;                 // capacity of the node buffer (speculative emission); ~0 when it is sized afterwards
 };
-__global__ void __launch_bounds__(1024) k_shard_merge(MergeJob Mj) {
+__device__ __forceinline__ void shard_merge_body(const MergeJob& Mj) {
     __shared__ unsigned long long s_leaves, s_before, s_own, s_lo, s_hi, s_nrec, s_nodes;
-    if (build_aborted(Mj.info)) return;
     const int J = Mj.J, top = Mj.top;
     if (threadIdx.x == 0) { s_leaves = 0; s_before = 0; s_own = 0; s_lo = ~0ULL; s_hi = ~0ULL; s_nrec = 0; }
     __syncthreads();
@@ -386,6 +400,41 @@ __global__ void __launch_bounds__(1024) k_shard_merge(MergeJob Mj) {
         if (s_hi - s_lo > Mj.nodes_cap) atomicOr(&I->overflow, 1ULL << 32);
         if (s_nrec > Mj.rcap) atomicOr(&I->overflow, 1ULL << 42);
     }
+    __threadfence();
+    __syncthreads();
+}
+__global__ void __launch_bounds__(1024) k_shard_merge(MergeJob Mj) {
+    if (build_aborted(Mj.info)) return;
+    shard_merge_body(Mj);
+}
+
+// ---------------------------------------------------------------------------
+// k_top: everything of a build that ONE block does -- the small upper levels (lists, subtree sizes), this rank's table
+// entries, the merge of the shared levels, the scattered upper records and the emission of the top levels -- as stages
+// of a single launch, so that a build pays one launch latency for them instead of six. The host picks the stages:
+// all of them on one GPU; [lists, sizes, table] | exchange | [merge, scatter, emit] when sharded; the merge alone
+// when the node buffer still has to be sized on the host.
+// ---------------------------------------------------------------------------
+enum { TOP_LISTS = 1, TOP_SIZES = 2, TOP_TABLE = 4, TOP_MERGE = 8, TOP_SCATTER = 16, TOP_EMIT = 32 };
+struct TopJob {
+    int stages;
+    SmallLevelsJob S;
+    FusedJob F;                       // lv[jB..J] views; jf_up = first level of the size pass, jf = last level NOT emitted here
+    TableFillJob T; unsigned long long table_words;
+    MergeJob M;
+    BuildInfo* info;
+};
+__global__ void __launch_bounds__(1024) k_top(TopJob P) {
+    if ((P.stages & TOP_LISTS) && !build_aborted(P.info)) small_levels_body(P.S);
+    if ((P.stages & TOP_SIZES) && !build_aborted(P.info)) fused_up_body(P.F, P.F.jf_up);
+    if ((P.stages & TOP_TABLE) && !build_aborted(P.info)) table_fill_body(P.T, P.table_words);
+    if ((P.stages & TOP_MERGE) && !build_aborted(P.info)) shard_merge_body(P.M);
+    if ((P.stages & TOP_SCATTER) && !build_aborted(P.info)) {
+        scatter_records_body(P.M.rpos, P.M.rrec, P.M.rcap, &P.info->n_upper, P.F.E, threadIdx.x, blockDim.x);
+        __threadfence();
+        __syncthreads();
+    }
+    if ((P.stages & TOP_EMIT) && !build_aborted(P.info)) fused_emit_body(P.F);
 }
 
 }  // namespace svo

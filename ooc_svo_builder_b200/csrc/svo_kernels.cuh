@@ -16,6 +16,7 @@
 // emission (k_fused_emit, k_emit_upper, k_emit_leaf, k_emit_leaf_levels, k_levels_data, k_payload), clean-up
 // (k_sparse_clear_all). The multi-GPU exchange kernels are in svo_dispatch.cuh.
 #pragma once
+#include <type_traits>
 #include "svo_device.cuh"
 
 namespace svo {
@@ -181,29 +182,27 @@ __device__ __forceinline__ void warp_push(unsigned long long* counter, unsigned 
 
 // Morton code of the next brick along one axis: add one inside the axis' bit lane (the other lanes are filled with
 // ones so that the carry ripples through them)
-__device__ __forceinline__ unsigned long long morton_inc(unsigned long long m, unsigned long long lane_mask) {
-    return ((m | ~lane_mask) + 1ULL) & lane_mask;
-}
+template <class U>
+__device__ __forceinline__ U morton_inc(U m, U lane_mask) { return ((m | ~lane_mask) + (U)1) & lane_mask; }
 // Split the hit mask of a box-aligned 4x4x4 window (linear layout) into the up to 8 bricks it straddles:
 // per axis the low part moves up by the window's offset inside the brick, the high part moves down into
 // the next brick; in the linear layout these are plain shifts once the part is masked out.
 // The window lies inside the clamped box of the pair, which lies inside this rank's slab (a box): no range test.
-template <bool OWNER>
+// BIG = false: grids up to 4096^3 -- bricks have at most 10 bits per axis, word indices fit 32 bits.
+template <bool OWNER, bool BIG>
 __device__ __forceinline__ void emit_window(const VoxJob& J, int wx, int wy, int wz, unsigned long long hits, uint32_t tri) {
+    typedef typename std::conditional<BIG, unsigned long long, uint32_t>::type idx_t;
     const int ox = wx & 3, oy = wy & 3, oz = wz & 3;
     const unsigned long long xlo = (unsigned long long)((1u << (4 - ox)) - 1u) * 0x1111111111111111ULL;
     const unsigned long long ylo = (unsigned long long)((1u << (4 * (4 - oy))) - 1u) * 0x0001000100010001ULL;
     const unsigned long long zlo = lowmask(16 * (4 - oz));
     const uint32_t bx = (uint32_t)(wx >> 2), by = (uint32_t)(wy >> 2), bz = (uint32_t)(wz >> 2);
-    unsigned long long sx[2], sy[2], sz[2];
-    if (J.g <= 4096u) {                              // warp-uniform: bricks have <= 10 bits per axis, 32-bit interleave
-        sx[0] = spread3_10(bx); sy[0] = (unsigned long long)spread3_10(by) << 1; sz[0] = (unsigned long long)spread3_10(bz) << 2;
-    } else {
-        sx[0] = spread3(bx); sy[0] = spread3(by) << 1; sz[0] = spread3(bz) << 2;
-    }
-    sx[1] = morton_inc(sx[0], 0x1249249249249249ULL);
-    sy[1] = morton_inc(sy[0], 0x2492492492492492ULL);
-    sz[1] = morton_inc(sz[0], 0x4924924924924924ULL);
+    idx_t sx[2], sy[2], sz[2];
+    if (BIG) { sx[0] = (idx_t)spread3(bx); sy[0] = (idx_t)(spread3(by) << 1); sz[0] = (idx_t)(spread3(bz) << 2); }
+    else { sx[0] = (idx_t)spread3_10(bx); sy[0] = (idx_t)(spread3_10(by) << 1); sz[0] = (idx_t)(spread3_10(bz) << 2); }
+    sx[1] = morton_inc<idx_t>(sx[0], (idx_t)0x1249249249249249ULL);
+    sy[1] = morton_inc<idx_t>(sy[0], (idx_t)0x2492492492492492ULL);
+    sz[1] = morton_inc<idx_t>(sz[0], (idx_t)0x4924924924924924ULL);
     unsigned long long* const l0 = J.lvl[0];
     unsigned long long* const l1 = J.nl > 1 ? J.lvl[1] : nullptr;
 #pragma unroll
@@ -211,17 +210,17 @@ __device__ __forceinline__ void emit_window(const VoxJob& J, int wx, int wy, int
         const int dx = q & 1, dy = (q >> 1) & 1, dz = q >> 2;
         unsigned long long sub = hits & (dx ? ~xlo : xlo) & (dy ? ~ylo : ylo) & (dz ? ~zlo : zlo);
         if (sub) {
-            const uint64_t wi = sx[dx] | sy[dy] | sz[dz];
+            const idx_t wi = sx[dx] | sy[dy] | sz[dz];
             const int sh = (dx ? ox - 4 : ox) + 4 * (dy ? oy - 4 : oy) + 16 * (dz ? oz - 4 : oz);
             sub = sh >= 0 ? (sub << sh) : (sub >> (-sh));
             if (!OWNER) {
                 red_or(l0 + wi, sub);
-                if (l1) red_or(l1 + (wi >> 6), 1ULL << (wi & 63));
+                if (l1) red_or(l1 + (wi >> 6), 1ULL << ((unsigned)wi & 63u));
             } else {
                 while (sub) {
                     const int bit = __ffsll((long long)sub) - 1;
                     sub &= sub - 1;
-                    sink_owner_bit(J, wi, bit, tri);
+                    sink_owner_bit(J, (uint64_t)wi, bit, tri);
                 }
             }
         }
@@ -239,7 +238,7 @@ __device__ __forceinline__ void emit_window(const VoxJob& J, int wx, int wy, int
 // ---------------------------------------------------------------------------
 // Everything after the vertices are in registers: enumerate the triangle's partitions, classify the clamped
 // boxes, route big ones to the queues, voxelize small ones. Must be called by whole warps.
-template <bool OWNER, bool ENUM>
+template <bool OWNER, bool ENUM, bool BIG>
 __device__ __forceinline__ void vox_small_body(const VoxJob& J, bool active, uint32_t tri, uint32_t part, const float* v) {
     // ---- the partitions of this triangle -------------------------------------------------------------
     // list mode: one (the pair's). inline mode: every logical partition whose world box the triangle's
@@ -292,14 +291,19 @@ __device__ __forceinline__ void vox_small_body(const VoxJob& J, bool active, uin
         // warp-uniform upper bounds of the window extents (convergent point: every lane is here)
         const int ub = min(4, __reduce_max_sync(0xffffffffu, cls == 0 ? b.y1 - b.y0 + 1 : 0));
         const int uc = min(4, __reduce_max_sync(0xffffffffu, cls == 0 ? b.z1 - b.z0 + 1 : 0));
-        if (cls == 0) {
-            for (int wz = b.z0; wz <= b.z1; wz += 4)
-                for (int wy = b.y0; wy <= b.y1; wy += 4)
-                    for (int wx = b.x0; wx <= b.x1; wx += 4) {
-                        const unsigned long long hits = eval_window(s, J.u, wx, wy, wz, min(4, b.x1 - wx + 1), min(4, b.y1 - wy + 1),
-                                                                    min(4, b.z1 - wz + 1), ub, uc);
-                        if (hits) emit_window<OWNER>(J, wx, wy, wz, hits, tri);
-                    }
+        // the (usually one) 4x4x4 windows of the box, anchored at its corner: ONE flat loop with a warp-uniform trip count
+        const int nwx = cls == 0 ? (b.x1 - b.x0 + 4) >> 2 : 0, nwy = (b.y1 - b.y0 + 4) >> 2;
+        const int mine = cls == 0 ? nwx * nwy * ((b.z1 - b.z0 + 4) >> 2) : 0;
+        const int trips = __reduce_max_sync(0xffffffffu, mine);
+        int cx = 0, cy = 0, cz = 0;
+        for (int w = 0; w < trips; w++) {
+            if (w < mine) {
+                const int wx = b.x0 + 4 * cx, wy = b.y0 + 4 * cy, wz = b.z0 + 4 * cz;
+                const unsigned long long hits = eval_window(s, J.u, wx, wy, wz, min(4, b.x1 - wx + 1), min(4, b.y1 - wy + 1),
+                                                            min(4, b.z1 - wz + 1), ub, uc);
+                if (hits) emit_window<OWNER, BIG>(J, wx, wy, wz, hits, tri);
+                if (++cx == nwx) { cx = 0; if (++cy == nwy) { cy = 0; cz++; } }
+            }
         }
     }
 }
@@ -356,7 +360,7 @@ __global__ void __launch_bounds__(VOX_BLOCK, SVO_VOX_MINBLOCKS) k_vox_small(VoxJ
                 for (int i = 0; i < 9; i++) v[i] = s_stage[threadIdx.x * J.fpt + i];
             }
             __syncthreads();                                   // the next iteration overwrites the staging buffer
-            vox_small_body<OWNER, ENUM>(J, active, (uint32_t)q, 0u, v);
+            vox_small_body<OWNER, ENUM, true>(J, active, (uint32_t)q, 0u, v);
         }
         return;
     }
@@ -376,7 +380,7 @@ __global__ void __launch_bounds__(VOX_BLOCK, SVO_VOX_MINBLOCKS) k_vox_small(VoxJ
         part = pair_partition(J, q);
         load_vertices(J, nullptr, tri, v);
     }
-    vox_small_body<OWNER, ENUM>(J, active, tri, part, v);
+    vox_small_body<OWNER, ENUM, true>(J, active, tri, part, v);
 }
 
 // ---------------------------------------------------------------------------
@@ -390,7 +394,7 @@ __global__ void __launch_bounds__(VOX_BLOCK, SVO_VOX_MINBLOCKS) k_vox_small(VoxJ
 //   MODE 2: units listed by the source ranks for this rank (k_slice_filter), staged from the owner's HBM over NVLink
 // ---------------------------------------------------------------------------
 constexpr int UNIT = 32;
-template <bool OWNER, bool ENUM, int MODE>
+template <bool OWNER, bool ENUM, int MODE, bool BIG>
 __global__ void __launch_bounds__(VOX_BLOCK, SVO_VOX_MINBLOCKS) k_vox_warp(VoxJob J) {
     extern __shared__ float4 s_stage4[];
     __shared__ __align__(8) unsigned long long s_bar[VOX_BLOCK / 32][2];
@@ -470,7 +474,7 @@ __global__ void __launch_bounds__(VOX_BLOCK, SVO_VOX_MINBLOCKS) k_vox_warp(VoxJo
             for (int i = 0; i < 9; i++) v[i] = __ldg(my_ptr + (size_t)lane * J.fpt + i);
         }
         __syncwarp();                                       // every lane has its vertices: the buffer may be refilled
-        vox_small_body<OWNER, ENUM>(J, active, tri, 0u, v);
+        vox_small_body<OWNER, ENUM, BIG>(J, active, tri, 0u, v);
         cur = next;
         next = __shfl_sync(0xffffffffu, ahead, 0);
     }
@@ -993,17 +997,30 @@ __device__ __forceinline__ unsigned long long first_leaf_below(const TableFillJo
     for (int j = T.J; j >= 0; j--) i = T.fc[j][i];
     return i;
 }
+__device__ __forceinline__ void table_fill_entry(const TableFillJob& T, unsigned long long i) {
+    unsigned long long* e = T.table + T.key[i] * 4ULL;
+    e[0] = T.mask[i];
+    e[1] = T.ps[i + 1] - T.ps[i];
+    e[2] = first_leaf_below(T, i + 1) - first_leaf_below(T, i);     // fc[j][n_j] = n_{j-1}: the chain is valid for i = n too
+    e[3] = T.pi ? T.pi[i + 1] - T.pi[i] : 0ULL;
+}
 __global__ void __launch_bounds__(256) k_table_fill(TableFillJob T) {
     if (build_aborted(T.info)) return;
     const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long n = T.n;
     if (T.np) { const unsigned long long v = *T.np; n = v < n ? v : n; }
     if (i >= n) return;
-    unsigned long long* e = T.table + T.key[i] * 4ULL;
-    e[0] = T.mask[i];
-    e[1] = T.ps[i + 1] - T.ps[i];
-    e[2] = first_leaf_below(T, i + 1) - first_leaf_below(T, i);     // fc[j][n_j] = n_{j-1}: the chain is valid for i = n too
-    e[3] = T.pi ? T.pi[i + 1] - T.pi[i] : 0ULL;
+    table_fill_entry(T, i);
+}
+// the same by ONE block (fused top kernel): zeroes the table first; `zero_words` u64
+__device__ __forceinline__ void table_fill_body(const TableFillJob& T, unsigned long long zero_words) {
+    for (unsigned long long i = threadIdx.x; i < zero_words; i += blockDim.x) T.table[i] = 0ULL;
+    __syncthreads();
+    unsigned long long n = T.n;
+    if (T.np) { const unsigned long long v = *T.np; n = v < n ? v : n; }
+    for (unsigned long long i = threadIdx.x; i < n; i += blockDim.x) table_fill_entry(T, i);
+    __threadfence();
+    __syncthreads();
 }
 // Unpack the summed table into dense columns and rebuild the (tiny, replicated) upper dense levels.
 __global__ void __launch_bounds__(256) k_table_unpack(const unsigned long long* table, unsigned long long n, unsigned long long* dmask,
@@ -1207,6 +1224,7 @@ constexpr int EMIT_TILES_PER_WARP = 32;
 __device__ __forceinline__ void st128(unsigned long long* p, unsigned long long a, unsigned long long b) {
     asm volatile("st.global.v2.u64 [%0], {%1, %2};" :: "l"(p), "l"(a), "l"(b) : "memory");
 }
+template <bool PAYLOAD>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_emit_leaf(Level L, EmitJob E) {
     __shared__ unsigned long long s_off[256];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) s_off[i] = child_offsets((uint32_t)i);
@@ -1222,12 +1240,11 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_emit_leaf(Level L, Emi
     if (lane < cnt) {
         myW = L.mask[t0 + lane];
         myBase = L.base[t0 + lane];
-        if (E.leaf_data_mode) myFc = L.fc[t0 + lane];
+        if (PAYLOAD) myFc = L.fc[t0 + lane];
     }
-    const int myLeaf = __popcll(myW);
     // a rank's own bricks always lie inside its range; the capacity guard drops whole bricks
     const bool ok = lane < cnt && E.write_records && myBase >= R.lo &&
-                    myBase + (unsigned long long)(myLeaf + __popc(nonzero_bytes(myW)) + (E.root_here ? 1 : 0)) <= R.hi;
+                    myBase + (unsigned long long)(__popcll(myW) + __popc(nonzero_bytes(myW)) + (E.root_here ? 1 : 0)) <= R.hi;
     if (!ok) myW = 0ULL;                                                          // nothing is written for this brick
     const unsigned long long myRel = ok ? (myBase - R.lo) * 3ULL : 0ULL;          // first word of the region in the buffer
     const unsigned long long leaf1 = 1ULL + R.leaf_offset + myFc;                 // payload: data index of the brick's first leaf
@@ -1239,7 +1256,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_emit_leaf(Level L, Emi
         const unsigned long long w0 = __shfl_sync(0xffffffffu, myRel, t);
         const unsigned long long base = __shfl_sync(0xffffffffu, myBase, t);
         unsigned long long d0 = 1ULL;
-        if (E.leaf_data_mode) d0 = __shfl_sync(0xffffffffu, leaf1, t);
+        if (PAYLOAD) d0 = __shfl_sync(0xffffffffu, leaf1, t);
         if (W == 0ULL) continue;
         const int nleaf = __popcll(W), words = 3 * nleaf;
         unsigned long long* out = E.nodes + w0;
@@ -1247,13 +1264,30 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_emit_leaf(Level L, Emi
         // relative words [odd, last) are written as aligned pairs, q = odd + 2 * (s + 8 * i)
         const int last = words - ((words - odd) & 1);
         int f = odd + s2; if (f >= 3) f -= 3;               // field of word q: q % 3 (w0 = 3 * base: a multiple of three words)
-        for (int q = odd + 2 * s; q < last; q += 16) {
-            unsigned long long a, b;                        // binary: (1, 0) (0, ~0) (~0, 1); payload: the data index of the record
-            if (f == 0) { a = E.leaf_data_mode ? d0 + (unsigned)(q / 3) : 1ULL; b = 0ULL; }
-            else if (f == 1) { a = 0ULL; b = ~0ULL; }
-            else { a = ~0ULL; b = E.leaf_data_mode ? d0 + (unsigned)((q + 1) / 3) : 1ULL; }
-            st128(out + q, a, b);
-            f = f == 2 ? 0 : f + 1;                         // 16 % 3 == 1
+        if (!PAYLOAD) {
+            // the three pair patterns (1, 0) (0, ~0) (~0, 1) in the order this lane meets them: the field advances by
+            // 16 % 3 == 1 per step, so three steps are one period
+            const unsigned long long a0 = f == 0 ? 1ULL : (f == 1 ? 0ULL : ~0ULL), b0 = f == 0 ? 0ULL : (f == 1 ? ~0ULL : 1ULL);
+            const unsigned long long a1 = b0 == 0ULL ? 0ULL : (b0 == 1ULL ? 1ULL : ~0ULL);      // pattern of field f + 1
+            const unsigned long long b1 = a1 == 1ULL ? 0ULL : (a1 == 0ULL ? ~0ULL : 1ULL);
+            const unsigned long long a2 = b1 == 0ULL ? 0ULL : (b1 == 1ULL ? 1ULL : ~0ULL);
+            const unsigned long long b2 = a2 == 1ULL ? 0ULL : (a2 == 0ULL ? ~0ULL : 1ULL);
+            unsigned long long* p = out + odd + 2 * s;
+            unsigned long long* const end = out + last;
+            for (; p < end; p += 48) {
+                st128(p, a0, b0);
+                if (p + 16 < end) st128(p + 16, a1, b1);
+                if (p + 32 < end) st128(p + 32, a2, b2);
+            }
+        } else {
+            for (int q = odd + 2 * s; q < last; q += 16) {
+                unsigned long long a, b;                    // the data index of the record in the data field
+                if (f == 0) { a = d0 + (unsigned)(q / 3); b = 0ULL; }
+                else if (f == 1) { a = 0ULL; b = ~0ULL; }
+                else { a = ~0ULL; b = d0 + (unsigned)((q + 1) / 3); }
+                st128(out + q, a, b);
+                f = f == 2 ? 0 : f + 1;
+            }
         }
         if (odd && s == 7) out[0] = d0;                     // word 0: the data field of the first record
         if (last < words && s == 6) out[words - 1] = ~0ULL; // the run's last word: an offsets field
@@ -1386,7 +1420,8 @@ struct FusedJob {
     const unsigned long long* dense[MAX_LEVELS];   // biased dense levels (indexed by global word index)
     const unsigned long long* dense_top;           // unbiased dense level J
     unsigned long long top_words, top_bias;
-    int J, jf;
+    int J, jf;                                     // k_fused_emit / k_fused_down: levels above jf
+    int jf_up;                                     // fused top kernel: subtree sizes of levels jf_up..J
     EmitJob E;
 };
 
@@ -1444,9 +1479,8 @@ __global__ void __launch_bounds__(1024) k_fused_down(FusedJob F) {
 }
 
 // bottom-up: subtree-size prefixes of levels jf..J (ps of level jf-1 must be complete)
-__global__ void __launch_bounds__(1024) k_fused_up(FusedJob F) {
-    if (build_aborted(F.E.info)) return;
-    for (int j = F.jf; j <= F.J; j++) {
+__device__ __forceinline__ void fused_up_body(const FusedJob& F, int jf) {
+    for (int j = jf; j <= F.J; j++) {
         const Level L = F.lv[j];
         const unsigned long long n = level_n(L);
         const unsigned long long* cps = F.lv[j - 1].ps;
@@ -1481,11 +1515,14 @@ __global__ void __launch_bounds__(1024) k_fused_up(FusedJob F) {
         __syncthreads();
     }
 }
+__global__ void __launch_bounds__(1024) k_fused_up(FusedJob F) {
+    if (build_aborted(F.E.info)) return;
+    fused_up_body(F, F.jf);
+}
 
 // top-down emission of levels J..jf+1 (each level writes the bases of the next); level jf itself is emitted
 // by the regular multi-block kernel afterwards. No -levels on this path.
-__global__ void __launch_bounds__(1024) k_fused_emit(FusedJob F) {
-    if (build_aborted(F.E.info)) return;
+__device__ __forceinline__ void fused_emit_body(const FusedJob& F) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const NodeRange R = node_range(F.E);
     for (int j = F.J; j > F.jf; j--) {
@@ -1498,17 +1535,25 @@ __global__ void __launch_bounds__(1024) k_fused_emit(FusedJob F) {
         __syncthreads();
     }
 }
+__global__ void __launch_bounds__(1024) k_fused_emit(FusedJob F) {
+    if (build_aborted(F.E.info)) return;
+    fused_emit_body(F);
+}
 
 // sharded: the records of the shared upper levels are computed on the host from the exchanged table
 // (a few thousand at most) and scattered into this rank's part of the node array
+__device__ __forceinline__ void scatter_records_body(const unsigned long long* pos, const unsigned long long* rec, unsigned long long n,
+                                                     const unsigned long long* np, const EmitJob& E, unsigned long long first, unsigned long long stride) {
+    if (np) { const unsigned long long v = *np; n = v < n ? v : n; }
+    const NodeRange R = node_range(E);
+    for (unsigned long long i = first; i < n; i += stride) {
+        if (unsigned long long* o = node_slot(E, R, pos[i])) { o[0] = rec[3 * i]; o[1] = rec[3 * i + 1]; o[2] = rec[3 * i + 2]; }
+    }
+}
 __global__ void __launch_bounds__(256) k_scatter_records(const unsigned long long* pos, const unsigned long long* rec, unsigned long long n,
                                                          const unsigned long long* np, EmitJob E) {
     if (build_aborted(E.info)) return;
-    if (np) { const unsigned long long v = *np; n = v < n ? v : n; }
-    const NodeRange R = node_range(E);
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
-        if (unsigned long long* o = node_slot(E, R, pos[i])) { o[0] = rec[3 * i]; o[1] = rec[3 * i + 1]; o[2] = rec[3 * i + 2]; }
-    }
+    scatter_records_body(pos, rec, n, np, E, (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x, (unsigned long long)gridDim.x * blockDim.x);
 }
 
 // sparse clear of all levels in one launch (blockIdx.y = level)
@@ -1539,6 +1584,16 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_voxel_codes(Level L, u
             if (r < capacity) codes[r] = (key << 6) | (unsigned long long)bit;
         }
     }
+}
+
+// voxels per logical partition (what the reference prints per partition with -v, main.cpp:348): leaves of the bricks
+// whose Morton prefix is the partition index. sh < 0: a partition is smaller than a brick (not reachable: P <= 8^5, g >= 4 side).
+__global__ void __launch_bounds__(256) k_partition_voxels(const unsigned long long* key, const unsigned long long* mask, unsigned long long n, int sh,
+                                                         unsigned long long* counts) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long p = sh >= 0 ? key[i] >> sh : 0ULL;
+    atomicAdd(&counts[p], (unsigned long long)__popcll(mask[i]));
 }
 
 // zero exactly the words that were set, so the next run starts from a clean pyramid

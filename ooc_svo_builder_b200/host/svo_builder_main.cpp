@@ -14,8 +14,16 @@
 // Like the reference, every user error prints a message and exits with status 0.
 #include "svo_b200.h"
 
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include <algorithm>
+#include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -48,6 +56,7 @@ struct Options {
     bool levels = false;
     bool verbose = false;
     int device = 0;
+    int gpus = 1;                    // -gpus N: shard the partitions over N devices (one context per device, in-process)
 };
 
 struct TriHeader {
@@ -80,6 +89,7 @@ void usage() {
                  "-c <option>           Coloring of voxels (Options: model (default), fixed, linear, normal)\n"
                  "-d <percentage>       Percentage of memory limit to be used additionaly for sparseness optimization\n"
                  "-g <device>           CUDA device index (default 0)\n"
+                 "-gpus <n>             Shard the build over the first n visible CUDA devices (power of two, default 1)\n"
                  "-v                    Be very verbose.\n"
                  "-h                    Print help and exit." << std::endl;
 }
@@ -124,6 +134,9 @@ Options parse(int argc, char** argv) {
             o.levels = true;
         } else if (a == "-g") {
             o.device = std::atoi(value().c_str());
+        } else if (a == "-gpus") {
+            o.gpus = std::atoi(value().c_str());
+            if (o.gpus < 1 || (o.gpus & (o.gpus - 1)) != 0 || o.gpus > 16) bad_arguments("Requested GPU count must be a power of 2 (1..16)");
         } else if (a == "-c") {
             const std::string c = value();
             if (kBinary) {
@@ -191,6 +204,140 @@ bool read_tri_header(const std::string& path, TriHeader& h) {
     std::exit(0);
 }
 
+// ---------------------------------------------------------------------------
+// File IO at memory speed: positional reads / writes from several threads through rings of pinned chunks.
+// ---------------------------------------------------------------------------
+bool pread_all(int fd, char* dst, size_t n, off_t off) {
+    while (n) {
+        const ssize_t r = ::pread(fd, dst, n, off);
+        if (r <= 0) return false;
+        dst += r; n -= (size_t)r; off += r;
+    }
+    return true;
+}
+bool pwrite_all(int fd, const char* src, size_t n, off_t off) {
+    while (n) {
+        const ssize_t r = ::pwrite(fd, src, n, off);
+        if (r <= 0) return false;
+        src += r; n -= (size_t)r; off += r;
+    }
+    return true;
+}
+
+// Reads bytes [first, first + total) of `fd` in chunks of `chunk` bytes with `n_threads` readers into a ring of
+// pinned buffers and hands the chunks IN ORDER to `consume(ptr, bytes)`. consume's contract is the library's
+// double-buffer rule (svo_triangles_append): when it returns, every EARLIER chunk has been copied to the device, so a
+// slot is reusable once the chunk after it has been consumed (replaces TriReader's fread loop, TriReader.h:41-79).
+template <class Consume>
+bool stream_in(int fd, off_t first, size_t total, size_t chunk, int n_threads, Consume consume) {
+    if (total == 0) return true;
+    const size_t n_chunks = (total + chunk - 1) / chunk;
+    const int R = (int)std::min<size_t>(n_chunks, (size_t)n_threads + 2);
+    std::vector<void*> slot(R, nullptr);
+    for (auto& p : slot) { p = svo_host_alloc(chunk); if (!p) return false; }
+    std::mutex mu;
+    std::condition_variable cv;
+    std::vector<char> ready(n_chunks, 0);
+    size_t released = 0;                      // chunks [0, released) no longer occupy their slot
+    std::atomic<size_t> next{ 0 };
+    std::atomic<bool> failed{ false };
+    auto reader = [&]() {
+        for (;;) {
+            const size_t i = next.fetch_add(1);
+            if (i >= n_chunks || failed) return;
+            {   // slot i % R is free once chunk i - R has been released
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return failed || i < released + (size_t)R; });
+            }
+            const size_t off = i * chunk, len = std::min(chunk, total - off);
+            if (!pread_all(fd, static_cast<char*>(slot[i % R]), len, first + (off_t)off)) failed = true;
+            { std::lock_guard<std::mutex> lk(mu); ready[i] = 1; }
+            cv.notify_all();
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 0; t < std::min<int>(n_threads, (int)n_chunks); t++) th.emplace_back(reader);
+    bool ok = true;
+    for (size_t i = 0; i < n_chunks && ok; i++) {
+        {
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&] { return failed || ready[i]; });
+        }
+        if (failed) { ok = false; break; }
+        const size_t off = i * chunk, len = std::min(chunk, total - off);
+        if (!consume(slot[i % R], len)) { ok = false; failed = true; }
+        { std::lock_guard<std::mutex> lk(mu); released = i; }       // chunk i - 1 has reached the device
+        cv.notify_all();
+    }
+    failed = failed || !ok;
+    { std::lock_guard<std::mutex> lk(mu); released = n_chunks; }
+    cv.notify_all();
+    for (auto& t : th) t.join();
+    for (auto p : slot) svo_host_free(p);
+    return ok && !failed;
+}
+
+// Streams records [first, first + count) of a context's output (fetch = svo_fetch_nodes / svo_fetch_data) to `fd` at
+// byte offset first * rec: device -> pinned chunk (the fetch is synchronous) -> pwrite by a pool of writer threads.
+// Positional writes: the order in which chunks reach the file does not matter (replaces writeNode / writeVoxelData,
+// octree_io.h:49-66). Chunks stay inside `budget` bytes in total.
+bool stream_out(svo_ctx* ctx, int fd, uint64_t first, uint64_t count, uint64_t rec, int (*fetch)(svo_ctx*, uint64_t, uint64_t, void*),
+                size_t budget, int n_threads, std::string& err) {
+    if (count == 0) return true;
+    const int R = n_threads + 1;
+    const size_t chunk_bytes = std::max<size_t>(std::min<size_t>(budget / (size_t)R, 64u << 20) / rec * rec, rec);
+    const uint64_t per = chunk_bytes / rec;
+    const uint64_t n_chunks = (count + per - 1) / per;
+    std::vector<void*> slot(R, nullptr);
+    for (auto& p : slot) { p = svo_host_alloc(chunk_bytes); if (!p) { err = "cannot allocate pinned output buffers"; return false; } }
+    std::mutex mu;
+    std::condition_variable cv;
+    std::vector<int> state(R, 0);             // 0 free, 1 filled (waiting for a writer), 2 being written
+    std::vector<uint64_t> slot_first(R, 0), slot_n(R, 0);
+    bool done = false, failed = false;
+    auto writer = [&]() {
+        for (;;) {
+            int k = -1;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { for (int i = 0; i < R; i++) if (state[i] == 1) return true; return done || failed; });
+                for (int i = 0; i < R; i++) if (state[i] == 1) { k = i; break; }
+                if (k < 0) return;
+                state[k] = 2;
+            }
+            const bool ok = pwrite_all(fd, static_cast<const char*>(slot[k]), (size_t)(slot_n[k] * rec), (off_t)(slot_first[k] * rec));
+            { std::lock_guard<std::mutex> lk(mu); state[k] = 0; if (!ok) failed = true; }
+            cv.notify_all();
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 0; t < n_threads; t++) th.emplace_back(writer);
+    for (uint64_t i = 0; i < n_chunks; i++) {
+        int k = -1;
+        {
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&] { for (int j = 0; j < R; j++) if (state[j] == 0) return true; return failed; });
+            if (failed) break;
+            for (int j = 0; j < R; j++) if (state[j] == 0) { k = j; break; }
+        }
+        const uint64_t f0 = first + i * per, n = std::min<uint64_t>(per, first + count - f0);
+        if (fetch(ctx, f0, n, slot[k]) != SVO_OK) { std::lock_guard<std::mutex> lk(mu); failed = true; err = std::string("svo_fetch: ") + svo_last_error(ctx); break; }
+        { std::lock_guard<std::mutex> lk(mu); slot_first[k] = f0; slot_n[k] = n; state[k] = 1; }
+        cv.notify_all();
+    }
+    { std::lock_guard<std::mutex> lk(mu); done = true; }
+    cv.notify_all();
+    for (auto& t : th) t.join();
+    for (auto p : slot) svo_host_free(p);
+    if (failed && err.empty()) err = "write error (disk full?)";
+    return !failed;
+}
+
+int io_threads() {
+    if (const char* e = std::getenv("SVO_IO_THREADS")) return std::max(1, std::atoi(e));
+    return (int)std::min<unsigned>(std::max(2u, std::thread::hardware_concurrency() / 2), 8u);
+}
+
 }  // namespace
 
 int main(int argc, char** argv) {
@@ -224,79 +371,22 @@ int main(int argc, char** argv) {
         return 0;
     }
 
-    // CUDA start-up (driver + context, ~1 s) runs in the background while the triangle file is read. Only the
-    // chosen GPU is made visible to this process: initialising all eight devices of a box costs far more.
-    if (!std::getenv("CUDA_VISIBLE_DEVICES")) {
+    // Devices. One GPU: only the chosen device is made visible to this process when the user did not restrict the set
+    // (initialising all eight devices of a box costs far more than one); with CUDA_VISIBLE_DEVICES given by the user,
+    // -g indexes into that set. -gpus N: the first N visible devices.
+    const int world = opt.gpus;
+    const bool user_set = std::getenv("CUDA_VISIBLE_DEVICES") != nullptr;
+    if (!user_set && world == 1) {
         const std::string dev = std::to_string(opt.device);
         setenv("CUDA_VISIBLE_DEVICES", dev.c_str(), 1);
     }
-    const int device_index = std::getenv("SVO_KEEP_DEVICE_INDEX") ? opt.device : 0;
-    svo_ctx* ctx = nullptr;
-    std::future<int> ctx_ready = std::async(std::launch::async, [&ctx, device_index]() { return svo_ctx_create(device_index, &ctx); });
+    const int first_device = (world == 1) ? (user_set ? opt.device : 0) : 0;
 
-    // Triangle records: the file is read in chunks into two alternating pinned buffers and streamed to the device, the
-    // copy of one chunk overlapping the fread of the next (replaces TriReader's 8192-triangle fread loop,
-    // TriReader.h:41-79). The two chunks stay inside the -l budget; the whole file is never resident on the host.
-    const size_t rec_bytes = (size_t)kFloatsPerTri * sizeof(float);
-    const size_t tri_bytes = (size_t)hdr.n_triangles * rec_bytes;
-    {
-        const size_t in_budget = std::max<size_t>((size_t)opt.memory_limit << 20, 1u << 20);
-        const size_t chunk_tris = std::max<size_t>(std::min<size_t>(in_budget / 4, 64u << 20) / rec_bytes, 1);
-        FILE* f = std::fopen(tridata.c_str(), "rb");
-        // while the CUDA context comes up (~1 s), read the head of the file into ordinary memory (within the budget)
-        const size_t head_cap = std::min<size_t>(tri_bytes, (in_budget / 2) / rec_bytes * rec_bytes);
-        char* head = static_cast<char*>(std::malloc(head_cap ? head_cap : 1));
-        size_t head_have = 0;
-        while (f && head && head_have < head_cap && ctx_ready.wait_for(std::chrono::seconds(0)) != std::future_status::ready) {
-            const size_t want = std::min<size_t>(head_cap - head_have, (8u << 20) / rec_bytes * rec_bytes + rec_bytes);
-            const size_t r = std::fread(head + head_have, 1, want, f);
-            if (r != want) { head_have += r; break; }
-            head_have += r;
-        }
-        head_have = head_have / rec_bytes * rec_bytes;
-        if (f) std::fseek(f, (long)head_have, SEEK_SET);
-        if (ctx_ready.get() != SVO_OK) die(nullptr, "svo_ctx_create");
-        void* in_chunk[2] = { svo_host_alloc(chunk_tris * rec_bytes), svo_host_alloc(chunk_tris * rec_bytes) };
-        if (!in_chunk[0] || !in_chunk[1]) { std::cout << "Error: cannot allocate pinned input buffers" << std::endl; return 0; }
-        if (svo_triangles_begin(ctx, hdr.n_triangles, kFloatsPerTri) != SVO_OK) die(ctx, "svo_triangles_begin");
-        size_t got = 0;
-        if (head_have) {
-            if (svo_triangles_append(ctx, reinterpret_cast<const float*>(head), head_have / rec_bytes) != SVO_OK) die(ctx, "svo_triangles_append");
-            if (svo_synchronize(ctx) != SVO_OK) die(ctx, "svo_synchronize");      // `head` is pageable and freed right away
-            got = head_have;
-        }
-        std::free(head);
-        int slot = 0;
-        while (f && got < tri_bytes) {
-            const size_t want = std::min<size_t>(tri_bytes - got, chunk_tris * rec_bytes);
-            size_t have = 0;
-            while (have < want) {
-                const size_t r = std::fread(static_cast<char*>(in_chunk[slot]) + have, 1, want - have, f);
-                if (r == 0) break;
-                have += r;
-            }
-            if (have != want) break;
-            if (svo_triangles_append(ctx, static_cast<const float*>(in_chunk[slot]), want / rec_bytes) != SVO_OK) die(ctx, "svo_triangles_append");
-            got += want;
-            slot ^= 1;
-        }
-        if (f) std::fclose(f);
-        if (got != tri_bytes) { std::cout << "Error: " << tridata << " holds fewer than the " << tri_bytes << " bytes the header promises" << std::endl; return 0; }
-        if (svo_synchronize(ctx) != SVO_OK) die(ctx, "svo_synchronize");
-        svo_host_free(in_chunk[0]);
-        svo_host_free(in_chunk[1]);
-    }
-    const double ms_in = t_in.ms();
-
-    // ---- partitioning ----------------------------------------------------
-    WallTimer t_part;
-    std::cout << "Estimating best partition count ..." << std::endl;
-    const uint64_t required = (opt.gridsize * opt.gridsize * opt.gridsize) / 1024 / 1024;
-    std::cout << "  to do this in-core I would need " << required << " Mb of system memory" << std::endl;
-    const uint64_t P = svo_estimate_partitions(opt.gridsize, opt.memory_limit);
-    if (P == 1) std::cout << "  memory limit of " << opt.memory_limit << " Mb allows that" << std::endl;
-    else std::cout << "  going to do it in " << P << " partitions of " << required / P << " Mb each." << std::endl;
-    std::cout << "Partitioning data into " << P << " partitions ... " << std::flush;
+    // CUDA start-up (driver + one context per device, ~1 s) runs in the background while the file is opened
+    std::vector<svo_ctx*> ctx(world, nullptr);
+    std::vector<std::future<int>> ctx_ready;
+    for (int r = 0; r < world; r++)
+        ctx_ready.push_back(std::async(std::launch::async, [&ctx, r, first_device]() { return svo_ctx_create(first_device + r, &ctx[r]); }));
 
     svo_params prm;
     std::memset(&prm, 0, sizeof prm);
@@ -309,26 +399,121 @@ int main(int argc, char** argv) {
     prm.color_mode = opt.color;
     prm.sparseness_limit = opt.sparseness;
 
+    const size_t rec_bytes = (size_t)kFloatsPerTri * sizeof(float);
+    const size_t tri_bytes = (size_t)hdr.n_triangles * rec_bytes;
+    const size_t budget = std::max<size_t>((size_t)opt.memory_limit << 20, 1u << 20);
+    const int n_io = io_threads();
+    const int in_fd = ::open(tridata.c_str(), O_RDONLY);
+    struct stat sb;
+    if (in_fd < 0 || ::fstat(in_fd, &sb) != 0 || (size_t)sb.st_size < tri_bytes) {
+        std::cout << "Error: " << tridata << " holds fewer than the " << tri_bytes << " bytes the header promises" << std::endl;
+        return 0;
+    }
+    for (int r = 0; r < world; r++) if (ctx_ready[r].get() != SVO_OK) die(nullptr, "svo_ctx_create");
+
+    // Triangle records: the file is read by several threads (pread) into a ring of pinned chunks inside the -l budget
+    // and streamed to the device(s) in file order; the whole file is never resident on the host.
+    const size_t chunk_in = std::max<size_t>(std::min<size_t>(budget / (size_t)(n_io + 2) / (size_t)world, 32u << 20) / rec_bytes, 1) * rec_bytes;
+    const uint64_t per_rank = (hdr.n_triangles + (uint64_t)world - 1) / (uint64_t)world;       // rank r holds slice r of the file
+    std::vector<void*> windows(world, nullptr);
+    if (world == 1) {
+        if (svo_triangles_begin(ctx[0], hdr.n_triangles, kFloatsPerTri) != SVO_OK) die(ctx[0], "svo_triangles_begin");
+        const bool ok = stream_in(in_fd, 0, tri_bytes, chunk_in, n_io, [&](void* p, size_t len) {
+            return svo_triangles_append(ctx[0], static_cast<const float*>(p), len / rec_bytes) == SVO_OK;
+        });
+        if (!ok) { std::cout << "Error reading " << tridata << ": " << svo_last_error(ctx[0]) << std::endl; return 0; }
+        if (svo_synchronize(ctx[0]) != SVO_OK) die(ctx[0], "svo_synchronize");
+    } else {
+        if (opt.levels) { std::cout << "Error: -levels is not available with -gpus > 1" << std::endl; return 0; }
+        for (int r = 0; r < world; r++) {
+            if (svo_shard_configure(ctx[r], r, world) != SVO_OK) die(ctx[r], "svo_shard_configure");
+            if (svo_shard_slice_create(ctx[r], per_rank, kFloatsPerTri, &windows[r]) != SVO_OK) die(ctx[r], "svo_shard_slice_create");
+        }
+        for (int r = 0; r < world; r++)
+            if (svo_shard_slice_attach(ctx[r], windows.data()) != SVO_OK) die(ctx[r], "svo_shard_slice_attach");
+        std::vector<std::future<bool>> up;
+        for (int r = 0; r < world; r++) {
+            up.push_back(std::async(std::launch::async, [&, r]() {
+                const uint64_t lo = std::min<uint64_t>((uint64_t)r * per_rank, hdr.n_triangles), hi = std::min<uint64_t>(lo + per_rank, hdr.n_triangles);
+                if (svo_shard_slice_begin(ctx[r], hi - lo) != SVO_OK) return false;
+                const bool ok = stream_in(in_fd, (off_t)(lo * rec_bytes), (size_t)(hi - lo) * rec_bytes, chunk_in, std::max(1, n_io / world), [&](void* p, size_t len) {
+                    return svo_shard_slice_append(ctx[r], static_cast<const float*>(p), len / rec_bytes) == SVO_OK;
+                });
+                return ok && svo_synchronize(ctx[r]) == SVO_OK;
+            }));
+        }
+        for (int r = 0; r < world; r++) if (!up[r].get()) { std::cout << "Error reading " << tridata << ": " << svo_last_error(ctx[r]) << std::endl; return 0; }
+    }
+    ::close(in_fd);
+    const double ms_in = t_in.ms();
+
+    // ---- partitioning ----------------------------------------------------
+    WallTimer t_part;
+    std::cout << "Estimating best partition count ..." << std::endl;
+    const uint64_t required = (opt.gridsize * opt.gridsize * opt.gridsize) / 1024 / 1024;
+    std::cout << "  to do this in-core I would need " << required << " Mb of system memory" << std::endl;
+    const uint64_t P = svo_estimate_partitions(opt.gridsize, opt.memory_limit);
+    if (P == 1) std::cout << "  memory limit of " << opt.memory_limit << " Mb allows that" << std::endl;
+    else std::cout << "  going to do it in " << P << " partitions of " << required / P << " Mb each." << std::endl;
+    std::cout << "Partitioning data into " << P << " partitions ... " << std::flush;
+
     std::vector<uint64_t> tricounts(P, 0);
-    uint64_t P_lib = 0;
-    if (svo_partition(ctx, &prm, &P_lib, tricounts.data(), P) != SVO_OK) die(ctx, "svo_partition");
+    bool have_tricounts = false;
+    if (world == 1) {
+        uint64_t P_lib = 0;
+        if (svo_partition(ctx[0], &prm, &P_lib, tricounts.data(), P) != SVO_OK) die(ctx[0], "svo_partition");
+        have_tricounts = true;
+    }
     std::cout << "done." << std::endl;
-    if (opt.verbose) {
+    if (opt.verbose && have_tricounts) {
         for (uint64_t i = 0; i < P; i++) std::cout << "  partition " << i << " - tri_count: " << tricounts[i] << std::endl;
     }
     const double ms_part = t_part.ms();
 
     // ---- voxelize + build -------------------------------------------------
+    // All partitions are voxelized and built in ONE pass on the device(s); the reference's per-partition progress lines
+    // (main.cpp:334-352) are printed afterwards, when the per-partition voxel counts exist.
     WallTimer t_vox;
+    uint64_t n_voxels = 0, n_nodes = 0, n_data = 0;
+    std::vector<uint64_t> voxcounts(P, 0);
+    if (world == 1) {
+        if (svo_voxelize(ctx[0]) != SVO_OK) die(ctx[0], "svo_voxelize");
+        if (svo_build(ctx[0], &n_voxels, &n_nodes, &n_data) != SVO_OK) die(ctx[0], "svo_build");
+        if (svo_partition_voxel_counts(ctx[0], voxcounts.data(), P) != SVO_OK) die(ctx[0], "svo_partition_voxel_counts");
+    } else {
+        // one host thread per device: publish the slice lists, voxelize (staging triangles from the peers' HBM over
+        // NVLink), local build, table exchange over peer memory, merged emission. SVO_E_RETRY is answered by every rank
+        // in the same step (include/svo_b200.h): all of them repeat the last three calls.
+        std::vector<uint64_t> nv(world), nn(world), nd(world);
+        std::vector<std::vector<uint64_t>> vc(world, std::vector<uint64_t>(P, 0));
+        std::vector<std::future<int>> job;
+        for (int r = 0; r < world; r++) {
+            job.push_back(std::async(std::launch::async, [&, r]() -> int {
+                svo_ctx* c = ctx[r];
+                if (svo_shard_slice_publish(c, &prm, hdr.n_triangles) != SVO_OK) return 1;
+                if (svo_partition(c, &prm, nullptr, nullptr, 0) != SVO_OK) return 1;
+                if (svo_voxelize(c) != SVO_OK) return 1;
+                int rc = SVO_E_RETRY;
+                for (int attempt = 0; attempt < 4 && rc == SVO_E_RETRY; attempt++) {      // NULL: the library's own table
+                    if (svo_shard_count(c, nullptr) != SVO_OK) { rc = 1; break; }
+                    if (svo_shard_exchange(c, nullptr) != SVO_OK) { rc = 1; break; }
+                    rc = svo_shard_emit(c, nullptr, &nv[r], &nn[r], &nd[r]);
+                }
+                if (rc == SVO_OK && svo_partition_voxel_counts(c, vc[r].data(), P) != SVO_OK) rc = 1;
+                return rc;
+            }));
+        }
+        for (int r = 0; r < world; r++) if (job[r].get() != SVO_OK) die(ctx[r], "the sharded build");
+        n_voxels = nv[0]; n_nodes = nn[0]; n_data = nd[0];
+        for (int r = 0; r < world; r++) for (uint64_t i = 0; i < P; i++) voxcounts[i] += vc[r][i];
+    }
     for (uint64_t i = 0; i < P; i++) {
-        if (tricounts[i] == 0) continue;                       // main.cpp:330
+        if (have_tricounts ? tricounts[i] == 0 : voxcounts[i] == 0) continue;      // main.cpp:330 (without per-partition lists: empty partitions)
         std::cout << "Voxelizing partition " << i << " ..." << std::endl;
-        if (opt.verbose) std::cout << "  reading " << tricounts[i] << " triangles from device list " << i << std::endl;
+        if (opt.verbose && have_tricounts) std::cout << "  reading " << tricounts[i] << " triangles from device list " << i << std::endl;
+        if (opt.verbose) std::cout << "  found " << voxcounts[i] << " new voxels." << std::endl;
         std::cout << "Building SVO for partition " << i << " ..." << std::endl;
     }
-    if (svo_voxelize(ctx) != SVO_OK) die(ctx, "svo_voxelize");
-    uint64_t n_voxels = 0, n_nodes = 0, n_data = 0;
-    if (svo_build(ctx, &n_voxels, &n_nodes, &n_data) != SVO_OK) die(ctx, "svo_build");
     const double ms_vox = t_vox.ms();
 
     // ---- stream the result to disk within the -l budget ---------------------
@@ -336,41 +521,43 @@ int main(int argc, char** argv) {
     std::ostringstream name;
     name << hdr.base << opt.gridsize << "_" << P;              // partitioner.cpp:90/141
     const std::string out_base = name.str();
-    const size_t budget = std::max<size_t>((size_t)opt.memory_limit << 20, 1u << 20);
-    const size_t chunk_bytes = std::min<size_t>(budget / 2, 128u << 20);          // two chunks in flight stay inside the -l budget
-    void* chunk[2] = { svo_host_alloc(chunk_bytes), svo_host_alloc(chunk_bytes) };
-    if (!chunk[0] || !chunk[1]) { std::cout << "Error: cannot allocate pinned output buffers" << std::endl; return 0; }
-    // device -> pinned chunk (svo_fetch_*) overlaps with fwrite of the previous chunk
-    auto stream_out = [&](const std::string& path, uint64_t count, uint64_t rec, int (*fetch)(svo_ctx*, uint64_t, uint64_t, void*)) {
-        FILE* f = std::fopen(path.c_str(), "wb");
-        if (!f) { std::cout << "Error: cannot open " << path << " for writing" << std::endl; std::exit(0); }
-        const uint64_t per = chunk_bytes / rec;
-        std::future<void> writing[2];
-        int slot = 0;
-        for (uint64_t first = 0; first < count; first += per, slot ^= 1) {
-            const uint64_t n = std::min<uint64_t>(per, count - first);
-            if (writing[slot].valid()) writing[slot].get();
-            if (fetch(ctx, first, n, chunk[slot]) != SVO_OK) die(ctx, "svo_fetch");
-            void* src = chunk[slot];
-            writing[slot] = std::async(std::launch::async, [f, src, rec, n]() { std::fwrite(src, rec, n, f); });
-            if (writing[slot ^ 1].valid()) writing[slot ^ 1].get();          // keep the file writes in order
+    auto write_file = [&](const std::string& path, uint64_t total, uint64_t rec, bool nodes) {
+        const int fd = ::open(path.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+        if (fd < 0) { std::cout << "Error: cannot open " << path << " for writing" << std::endl; std::exit(0); }
+        if (::ftruncate(fd, (off_t)(total * rec)) != 0) { std::cout << "Error: cannot size " << path << std::endl; std::exit(0); }
+        std::vector<std::future<std::string>> w;
+        for (int r = 0; r < world; r++) {
+            w.push_back(std::async(std::launch::async, [&, r]() -> std::string {
+                uint64_t lo = 0, hi = total;
+                if (world > 1) {
+                    uint64_t nlo, nhi, dlo, dhi;
+                    if (svo_shard_ranges(ctx[r], &nlo, &nhi, &dlo, &dhi) != SVO_OK) return svo_last_error(ctx[r]);
+                    lo = nodes ? nlo : dlo; hi = nodes ? nhi : dhi;
+                }
+                std::string err;
+                stream_out(ctx[r], fd, lo, hi - lo, rec, nodes ? svo_fetch_nodes : svo_fetch_data, budget / (size_t)world, std::max(1, n_io / world / 2 + 1), err);
+                return err;
+            }));
         }
-        for (auto& w : writing) if (w.valid()) w.get();
-        std::fclose(f);
+        for (int r = 0; r < world; r++) { const std::string e = w[r].get(); if (!e.empty()) { std::cout << "Error writing " << path << ": " << e << std::endl; std::exit(0); } }
+        if (::close(fd) != 0) { std::cout << "Error closing " << path << std::endl; std::exit(0); }
     };
-    stream_out(out_base + ".octreenodes", n_nodes, SVO_NODE_BYTES, svo_fetch_nodes);
-    stream_out(out_base + ".octreedata", n_data, SVO_DATA_BYTES, svo_fetch_data);
+    write_file(out_base + ".octreenodes", n_nodes, SVO_NODE_BYTES, true);
+    write_file(out_base + ".octreedata", n_data, SVO_DATA_BYTES, false);
     {
         std::ofstream h((out_base + ".octree").c_str());        // octree_io.h:74-83
         h << "#octreeheader 1\n" << "gridlength " << opt.gridsize << "\n" << "n_nodes " << n_nodes << "\n" << "n_data " << n_data << "\nEND\n";
+        h.flush();
+        if (!h) { std::cout << "Error writing " << out_base << ".octree" << std::endl; return 0; }
     }
     const double ms_out = t_out.ms();
     std::cout << "done" << std::endl;
     std::cout << "Total amount of voxels: " << n_voxels << std::endl;
 
     svo_stats st;
-    svo_get_stats(ctx, &st);
+    svo_get_stats(ctx[0], &st);
     // same sections as the reference's printTimerInfo (main.cpp:219-241); algorithm times are CUDA-event device times
+    // (rank 0's with -gpus > 1)
     std::cout << "Total MAIN time      : " << t_main.ms() << " ms." << std::endl;
     std::cout << "PARTITIONING\n  Total time\t\t: " << ms_part + ms_in << " ms.\n  IO IN time\t\t: " << ms_in
               << " ms.\n  algorithm time\t: " << st.ms_partition << " ms. (device)\n  upload time\t\t: " << st.ms_upload << " ms. (device)" << std::endl;
@@ -379,10 +566,9 @@ int main(int argc, char** argv) {
     std::cout << "SVO BUILDING\n  algorithm time\t: " << st.ms_build << " ms. (device)\n  IO OUT time\t\t: " << ms_out << " ms." << std::endl;
     if (opt.verbose) {
         std::cout << "  pairs: " << st.n_pairs << " (small " << st.n_small << ", medium " << st.n_medium << ", large " << st.n_large << ")\n"
-                  << "  nodes: " << st.n_nodes << "  data: " << st.n_data << "  kernel launches: " << st.kernel_launches << std::endl;
+                  << "  nodes: " << st.n_nodes << "  data: " << st.n_data << "  kernel launches: " << st.kernel_launches
+                  << "  devices: " << world << "  io threads: " << n_io << std::endl;
     }
-    svo_host_free(chunk[0]);
-    svo_host_free(chunk[1]);
-    svo_ctx_destroy(ctx);
+    for (int r = 0; r < world; r++) svo_ctx_destroy(ctx[r]);
     return 0;
 }
