@@ -54,6 +54,12 @@ typedef struct svo_params {
     float    sparseness_limit;  /* -d as a fraction; accepted for CLI compatibility. It only
                                    switches the reference between two routes that produce the
                                    same files (voxelizer.cpp:176-186, main.cpp:355-368).       */
+    int32_t  separability;      /* 0 or 26: the reference's conservative (26-separating) Schwarz-Seidel test
+                                   (voxelizer.cpp:138-307). 6: OPT-IN 6-separating ("thin") variant of the same
+                                   paper -- plane test against the voxel's centre segment along the dominant normal
+                                   axis + the one projection orthogonal to it at the voxel centre. The reference has
+                                   no such mode (its only test is the conservative one); the definition is restated in
+                                   the C file of the test oracle (oracle/), which is what this mode is tested against. */
 } svo_params;
 
 /* Counters and device-side stage timings (CUDA events) of the last run. */

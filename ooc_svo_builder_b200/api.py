@@ -48,7 +48,7 @@ class Params(C.Structure):
     _fields_ = [("gridsize", C.c_uint64), ("memory_limit_mb", C.c_uint64),
                 ("bbox_min0", C.c_float), ("bbox_max0", C.c_float),
                 ("payload", C.c_int32), ("generate_levels", C.c_int32), ("color_mode", C.c_int32),
-                ("sparseness_limit", C.c_float)]
+                ("sparseness_limit", C.c_float), ("separability", C.c_int32)]
 
 
 class Stats(C.Structure):
@@ -278,9 +278,9 @@ class SvoBuilder:
 
     @staticmethod
     def make_params(length: float, gridsize: int, payload: bool, memory_limit_mb: int = 2048,
-                    levels: bool = False, color: str = "model", bbox_min0: float = 0.0) -> Params:
+                    levels: bool = False, color: str = "model", bbox_min0: float = 0.0, separability: int = 26) -> Params:
         return Params(gridsize, memory_limit_mb, np.float32(bbox_min0), np.float32(bbox_min0) + np.float32(length),
-                      int(payload), int(levels), COLOR_MODES[color], 0.10)
+                      int(payload), int(levels), COLOR_MODES[color], 0.10, int(separability))
 
     # -- stages -----------------------------------------------------------
     def set_triangles(self, tris) -> None:
@@ -461,10 +461,10 @@ class SvoBuilder:
 
     # -- whole path -------------------------------------------------------
     def run(self, tris, length: float, gridsize: int, memory_limit_mb: int = 2048,
-            levels: bool = False, color: str = "model", fetch: bool = True) -> Octree:
+            levels: bool = False, color: str = "model", fetch: bool = True, separability: int = 26) -> Octree:
         """main.cpp:298-389: partition → voxelize → build (→ fetch)."""
         payload = tris.shape[1] == 21
-        prm = self.make_params(length, gridsize, payload, memory_limit_mb, levels, color)
+        prm = self.make_params(length, gridsize, payload, memory_limit_mb, levels, color, separability=separability)
         self.set_triangles(tris)
         self.partition(prm, want_counts=False)
         self.voxelize()

@@ -338,6 +338,7 @@ VoxJob make_voxjob(svo_ctx* c) {
     J.g = (uint32_t)c->prm.gridsize;
     J.u = c->unit_vox;
     J.unit_div = c->unit_div;
+    J.six = c->prm.separability == 6 ? 1 : 0;
     J.nl = c->J + 1;                                             // the cascade stops at the top local level
     for (int j = 0; j <= c->J; j++) J.lvl[j] = c->dense[j].as<ull>() - c->bias[j];   // indexed with global word indices
     J.w_lo = c->bias[0];
@@ -443,6 +444,7 @@ int validate_params(svo_ctx* c, const svo_params* p) {
     if (p->memory_limit_mb < 1) return fail(c, SVO_E_INVALID, "memory_limit_mb must be >= 1");
     if (!(p->bbox_max0 > p->bbox_min0)) return fail(c, SVO_E_INVALID, "bbox_max0 must exceed bbox_min0");
     if (p->color_mode < 0 || p->color_mode > 3) return fail(c, SVO_E_INVALID, "unknown color_mode");
+    if (p->separability != 0 && p->separability != 6 && p->separability != 26) return fail(c, SVO_E_INVALID, "separability must be 0 / 26 (conservative, the reference's test) or 6 (thin)");
     return SVO_OK;
 }
 

@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(1024) k_small_levels(SmallLevelsJob S) {
 // ---------------------------------------------------------------------------
 // k_brick_pass
 // ---------------------------------------------------------------------------
-constexpr int BP_WARPS = 8, BP_PER_WARP = 8, BP_TILE = BP_WARPS * BP_PER_WARP;     // level-1 tiles per block
+constexpr int BP_WARPS = 8, BP_PER_WARP = 4, BP_TILE = BP_WARPS * BP_PER_WARP;     // level-1 tiles per block
 struct BrickJob {
     Level L1;                             // key, mask, fc in; ps out (n + 1)
     Level L0;                             // key, mask, fc, ps out
@@ -194,8 +194,8 @@ __global__ void __launch_bounds__(BP_WARPS * 32) k_brick_pass(BrickJob B) {
     // lane q of the warp holds the descriptor of the warp's q-th tile
     unsigned long long myW1 = 0ULL, myK1 = 0ULL, myF1 = 0ULL;
     if (lane < BP_PER_WARP && tw0 + lane < n1) { myW1 = B.L1.mask[tw0 + lane]; myK1 = B.L1.key[tw0 + lane]; myF1 = B.L1.fc[tw0 + lane]; }
-    // ---- sweep 1: totals of every tile ----
-#pragma unroll 2
+    // ---- sweep 1: totals of every tile (fully unrolled: the gathers of all the warp's tiles are in flight together) ----
+#pragma unroll
     for (int q = 0; q < BP_PER_WARP; q++) {
         const unsigned long long W1 = __shfl_sync(0xffffffffu, myW1, q), K1 = __shfl_sync(0xffffffffu, myK1, q);
         unsigned long long m[2]; unsigned v[2];
@@ -212,16 +212,16 @@ __global__ void __launch_bounds__(BP_WARPS * 32) k_brick_pass(BrickJob B) {
     }
     __syncthreads();
     if (wid == 0) {
-        // exclusive scan over the block's BP_TILE = 64 tiles (two per lane) and the look-back
+        // exclusive scan over the block's BP_TILE = 32 tiles (one per lane) and the look-back
+        static_assert(BP_TILE == 32, "one tile per lane of warp 0");
         unsigned long long tot[3], prefix[3];
 #pragma unroll
         for (int c = 0; c < 3; c++) {
-            const unsigned x0 = s_tot[2 * lane][c], x1 = s_tot[2 * lane + 1][c];
-            unsigned inc = x0 + x1;
+            const unsigned x = s_tot[lane][c];
+            unsigned inc = x;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) { const unsigned a = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += a; }
-            s_ex[2 * lane][c] = inc - x0 - x1;
-            s_ex[2 * lane + 1][c] = inc - x1;
+            s_ex[lane][c] = inc - x;
             tot[c] = __shfl_sync(0xffffffffu, inc, 31);
         }
         lookback<3>(B.state, B.epoch, tile, tot, prefix, &B.info->overflow);
@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(BP_WARPS * 32) k_brick_pass(BrickJob B) {
     }
     __syncthreads();
     // ---- sweep 2: the bricks ----
-#pragma unroll 2
+#pragma unroll
     for (int q = 0; q < BP_PER_WARP; q++) {
         const unsigned long long W1 = __shfl_sync(0xffffffffu, myW1, q), K1 = __shfl_sync(0xffffffffu, myK1, q), F1 = __shfl_sync(0xffffffffu, myF1, q);
         if (W1 == 0ULL) continue;                          // (warp-uniform) beyond the list

@@ -113,8 +113,12 @@ struct TriSetup {
     float ea[9], eb[9], ed[9];
 };
 
-// v = v0 v1 v2 (9 floats); u = unitlength
-__device__ __forceinline__ void tri_setup(const float* v, float u, TriSetup& s) {
+// v = v0 v1 v2 (9 floats); u = unitlength. six: the opt-in 6-separating variant (not in the reference; definition and
+// float op order restated in the C file of the test oracle under oracle/): the plane test runs against the voxel's centre segment along the
+// dominant normal axis, only the projection orthogonal to that axis is tested, at the projected voxel centre. It is
+// expressed through the SAME setup record -- other d1 / d2, the two unused projections get (0, 0, +0) edge functions
+// that always pass -- so that every kernel behind the setup (window evaluation, exact box pruning) serves both variants.
+__device__ __forceinline__ void tri_setup(const float* v, float u, TriSetup& s, bool six = false) {
     float e0x = fsub(v[3], v[0]), e0y = fsub(v[4], v[1]), e0z = fsub(v[5], v[2]);   // :207
     float e1x = fsub(v[6], v[3]), e1y = fsub(v[7], v[4]), e1z = fsub(v[8], v[5]);   // :208
     float e2x = fsub(v[0], v[6]), e2y = fsub(v[1], v[7]), e2z = fsub(v[2], v[8]);   // :209
@@ -149,6 +153,27 @@ __device__ __forceinline__ void tri_setup(const float* v, float u, TriSetup& s) 
         if (s.ny < 0.0f) { a = fmul(-1.0f, a); b = fmul(-1.0f, b); }
         s.ea[6 + j] = a; s.eb[6 + j] = b;
         s.ed[6 + j] = fadd(fadd(fmul(-1.0f, dot2(a, b, vz, vx)), stdmax(0.0f, fmul(u, a))), stdmax(0.0f, fmul(u, b)));
+    }
+    if (six) {
+        const float ax = fabsf(s.nx), ay = fabsf(s.ny), az = fabsf(s.nz);
+        const int k = (ax >= ay && ax >= az) ? 0 : (ay >= az ? 1 : 2);            // dominant axis
+        const float h = fmul(u, 0.5f);
+        const float c1x = k == 0 ? 0.0f : h, c1y = k == 1 ? 0.0f : h, c1z = k == 2 ? 0.0f : h;
+        const float c2x = k == 0 ? u : h, c2y = k == 1 ? u : h, c2z = k == 2 ? u : h;
+        s.d1 = dot3(s.nx, s.ny, s.nz, fsub(c1x, v[0]), fsub(c1y, v[1]), fsub(c1z, v[2]));
+        s.d2 = dot3(s.nx, s.ny, s.nz, fsub(c2x, v[0]), fsub(c2y, v[1]), fsub(c2z, v[2]));
+        // plane p (0 = XY, 1 = YZ, 2 = ZX) is orthogonal to axis (p + 2) % 3; its first / second coordinate are axis p, (p + 1) % 3
+#pragma unroll
+        for (int p = 0; p < 3; p++) {
+            const bool keep = ((p + 2) % 3) == k;
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                const int i = 3 * p + j;
+                if (!keep) { s.ea[i] = 0.0f; s.eb[i] = 0.0f; s.ed[i] = 0.0f; continue; }
+                const float va = v[3 * j + p], vb = v[3 * j + (p + 1) % 3];
+                s.ed[i] = fadd(fadd(fmul(-1.0f, dot2(s.ea[i], s.eb[i], va, vb)), fmul(h, s.ea[i])), fmul(h, s.eb[i]));
+            }
+        }
     }
 }
 

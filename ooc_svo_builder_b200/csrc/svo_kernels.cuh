@@ -66,6 +66,7 @@ struct VoxJob {
     uint32_t side;                    // partition side in voxels = g >> k
     uint32_t g;
     float u, unit_div;                // unit length, 1/u (voxelizer.cpp:164)
+    int six;                          // opt-in 6-separating variant (svo_params::separability == 6)
     int nl;                           // pyramid levels
     unsigned long long* lvl[MAX_LEVELS];
     unsigned long long* queue[2];     // medium / large work queues: (part << 32 | tri)
@@ -261,7 +262,7 @@ __device__ __forceinline__ void vox_small_body(const VoxJob& J, bool active, uin
     }
     const int most = ENUM ? __reduce_max_sync(0xffffffffu, count) : 1;   // warp-uniform trip count (1 almost always)
     TriSetup s;
-    if (count > 0) tri_setup(v, J.u, s);
+    if (count > 0) tri_setup(v, J.u, s, J.six != 0);
     for (int it = 0; it < most; it++) {
         const bool valid = it < count;
         // partition = slab coordinates (ix, iy, iz); no Morton round trip. Partitions of other ranks need no test of
@@ -560,7 +561,7 @@ __device__ __forceinline__ void queued_pair_setup(const VoxJob& J, const unsigne
     const int px = (int)((slab & 0xffu) * J.side), py = (int)(((slab >> 8) & 0xffu) * J.side), pz = (int)(((slab >> 16) & 0xffu) * J.side);
     b = clamped_box(v, J.unit_div, px, py, pz, (int)J.side);
     restrict_to_slab(J, b);     // queued pairs are non-empty by construction
-    tri_setup(v, J.u, s);
+    tri_setup(v, J.u, s, J.six != 0);
 }
 
 template <bool OWNER>
@@ -1218,7 +1219,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_emit_upper(Level L, Le
 //     behind where the run starts / ends on an odd word;
 //   * lane k of the group writes the child record of byte k (16 + 8 bytes).
 // Writes are guarded by this rank's range of the file and the capacity of the buffer (speculative emission).
-constexpr int EMIT_TILES_PER_WARP = 32;
+constexpr int EMIT_TILES_PER_WARP = 64;         // two batches of 32 bricks per warp: both batches' descriptors are loaded up front
 // 16-byte store to a 16-byte aligned address. Inline PTX on purpose: written as a C++ vector store, the two branches of
 // "aligned: 16 + 8, else 8 + 16" write the same bytes and the compiler folds them into ONE (then misaligned) form.
 __device__ __forceinline__ void st128(unsigned long long* p, unsigned long long a, unsigned long long b) {
@@ -1234,78 +1235,89 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_emit_leaf(Level L, Emi
     const unsigned long long n = level_n(L);
     const unsigned long long t0 = ((unsigned long long)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5)) * EMIT_TILES_PER_WARP;
     if (t0 >= n) return;
-    const int cnt = (int)min((unsigned long long)EMIT_TILES_PER_WARP, n - t0);
     const NodeRange R = node_range(E);
-    unsigned long long myW = 0, myBase = 0, myFc = 0;
-    if (lane < cnt) {
-        myW = L.mask[t0 + lane];
-        myBase = L.base[t0 + lane];
-        if (PAYLOAD) myFc = L.fc[t0 + lane];
+    unsigned long long bW[2], bBase[2], bFc[2];
+#pragma unroll
+    for (int h = 0; h < 2; h++) {                        // all loads of the warp's 64 bricks in flight together
+        const unsigned long long t = t0 + 32 * h + lane;
+        bW[h] = 0ULL; bBase[h] = 0ULL; bFc[h] = 0ULL;
+        if (t < n) {
+            bW[h] = L.mask[t];
+            bBase[h] = L.base[t];
+            if (PAYLOAD) bFc[h] = L.fc[t];
+        }
     }
-    // a rank's own bricks always lie inside its range; the capacity guard drops whole bricks
-    const bool ok = lane < cnt && E.write_records && myBase >= R.lo &&
-                    myBase + (unsigned long long)(__popcll(myW) + __popc(nonzero_bytes(myW)) + (E.root_here ? 1 : 0)) <= R.hi;
-    if (!ok) myW = 0ULL;                                                          // nothing is written for this brick
-    const unsigned long long myRel = ok ? (myBase - R.lo) * 3ULL : 0ULL;          // first word of the region in the buffer
-    const unsigned long long leaf1 = 1ULL + R.leaf_offset + myFc;                 // payload: data index of the brick's first leaf
     const int g = lane >> 3, s = lane & 7;                                        // group (brick of the round), lane in the group
     const int s2 = (2 * s) % 3;
-    for (int r = 0; r < cnt; r += 4) {
-        const int t = r + g;                                                      // brick of this group (lanes beyond cnt hold W = 0)
-        const unsigned long long W = __shfl_sync(0xffffffffu, myW, t);
-        const unsigned long long w0 = __shfl_sync(0xffffffffu, myRel, t);
-        const unsigned long long base = __shfl_sync(0xffffffffu, myBase, t);
-        unsigned long long d0 = 1ULL;
-        if (PAYLOAD) d0 = __shfl_sync(0xffffffffu, leaf1, t);
-        if (W == 0ULL) continue;
-        const int nleaf = __popcll(W), words = 3 * nleaf;
-        unsigned long long* out = E.nodes + w0;
-        const int odd = (int)(w0 & 1ULL);
-        // relative words [odd, last) are written as aligned pairs, q = odd + 2 * (s + 8 * i)
-        const int last = words - ((words - odd) & 1);
-        int f = odd + s2; if (f >= 3) f -= 3;               // field of word q: q % 3 (w0 = 3 * base: a multiple of three words)
-        if (!PAYLOAD) {
-            // the three pair patterns (1, 0) (0, ~0) (~0, 1) in the order this lane meets them: the field advances by
-            // 16 % 3 == 1 per step, so three steps are one period
-            const unsigned long long a0 = f == 0 ? 1ULL : (f == 1 ? 0ULL : ~0ULL), b0 = f == 0 ? 0ULL : (f == 1 ? ~0ULL : 1ULL);
-            const unsigned long long a1 = b0 == 0ULL ? 0ULL : (b0 == 1ULL ? 1ULL : ~0ULL);      // pattern of field f + 1
-            const unsigned long long b1 = a1 == 1ULL ? 0ULL : (a1 == 0ULL ? ~0ULL : 1ULL);
-            const unsigned long long a2 = b1 == 0ULL ? 0ULL : (b1 == 1ULL ? 1ULL : ~0ULL);
-            const unsigned long long b2 = a2 == 1ULL ? 0ULL : (a2 == 0ULL ? ~0ULL : 1ULL);
-            unsigned long long* p = out + odd + 2 * s;
-            unsigned long long* const end = out + last;
-            for (; p < end; p += 48) {
-                st128(p, a0, b0);
-                if (p + 16 < end) st128(p + 16, a1, b1);
-                if (p + 32 < end) st128(p + 32, a2, b2);
+#pragma unroll 1
+    for (int h = 0; h < 2; h++) {
+        if (t0 + 32 * h >= n) break;
+        const int cnt = (int)min(32ULL, n - (t0 + 32 * h));
+        unsigned long long myW = h ? bW[1] : bW[0];
+        const unsigned long long myBase = h ? bBase[1] : bBase[0], myFc = h ? bFc[1] : bFc[0];
+        // a rank's own bricks always lie inside its range; the capacity guard drops whole bricks
+        const bool ok = lane < cnt && E.write_records && myBase >= R.lo &&
+                        myBase + (unsigned long long)(__popcll(myW) + __popc(nonzero_bytes(myW)) + (E.root_here ? 1 : 0)) <= R.hi;
+        if (!ok) myW = 0ULL;                                                          // nothing is written for this brick
+        const unsigned long long myRel = ok ? (myBase - R.lo) * 3ULL : 0ULL;          // first word of the region in the buffer
+        const unsigned long long leaf1 = 1ULL + R.leaf_offset + myFc;                 // payload: data index of the brick's first leaf
+        for (int r = 0; r < cnt; r += 4) {
+            const int t = r + g;                                                      // brick of this group (lanes beyond cnt hold W = 0)
+            const unsigned long long W = __shfl_sync(0xffffffffu, myW, t);
+            const unsigned long long w0 = __shfl_sync(0xffffffffu, myRel, t);
+            const unsigned long long base = __shfl_sync(0xffffffffu, myBase, t);
+            unsigned long long d0 = 1ULL;
+            if (PAYLOAD) d0 = __shfl_sync(0xffffffffu, leaf1, t);
+            if (W == 0ULL) continue;
+            const int nleaf = __popcll(W), words = 3 * nleaf;
+            unsigned long long* out = E.nodes + w0;
+            const int odd = (int)(w0 & 1ULL);
+            // relative words [odd, last) are written as aligned pairs, q = odd + 2 * (s + 8 * i)
+            const int last = words - ((words - odd) & 1);
+            int f = odd + s2; if (f >= 3) f -= 3;               // field of word q: q % 3 (w0 = 3 * base: a multiple of three words)
+            if (!PAYLOAD) {
+                // the three pair patterns (1, 0) (0, ~0) (~0, 1) in the order this lane meets them: the field advances by
+                // 16 % 3 == 1 per step, so three steps are one period
+                const unsigned long long a0 = f == 0 ? 1ULL : (f == 1 ? 0ULL : ~0ULL), b0 = f == 0 ? 0ULL : (f == 1 ? ~0ULL : 1ULL);
+                const unsigned long long a1 = b0;                                                   // the pair one word further on
+                const unsigned long long b1 = a1 == 1ULL ? 0ULL : (a1 == 0ULL ? ~0ULL : 1ULL);
+                const unsigned long long a2 = b1;
+                const unsigned long long b2 = a2 == 1ULL ? 0ULL : (a2 == 0ULL ? ~0ULL : 1ULL);
+                unsigned long long* p = out + odd + 2 * s;
+                unsigned long long* const end = out + last;
+                for (; p < end; p += 48) {
+                    st128(p, a0, b0);
+                    if (p + 16 < end) st128(p + 16, a1, b1);
+                    if (p + 32 < end) st128(p + 32, a2, b2);
+                }
+            } else {
+                for (int q = odd + 2 * s; q < last; q += 16) {
+                    unsigned long long a, b;                    // the data index of the record in the data field
+                    if (f == 0) { a = d0 + (unsigned)(q / 3); b = 0ULL; }
+                    else if (f == 1) { a = 0ULL; b = ~0ULL; }
+                    else { a = ~0ULL; b = d0 + (unsigned)((q + 1) / 3); }
+                    st128(out + q, a, b);
+                    f = f == 2 ? 0 : f + 1;
+                }
             }
-        } else {
-            for (int q = odd + 2 * s; q < last; q += 16) {
-                unsigned long long a, b;                    // the data index of the record in the data field
-                if (f == 0) { a = d0 + (unsigned)(q / 3); b = 0ULL; }
-                else if (f == 1) { a = 0ULL; b = ~0ULL; }
-                else { a = ~0ULL; b = d0 + (unsigned)((q + 1) / 3); }
-                st128(out + q, a, b);
-                f = f == 2 ? 0 : f + 1;
+            if (odd && s == 7) out[0] = d0;                     // word 0: the data field of the first record
+            if (last < words && s == 6) out[words - 1] = ~0ULL; // the run's last word: an offsets field
+            // child record of byte s
+            const uint32_t byte = (uint32_t)((W >> (8 * s)) & 0xffULL);
+            const uint32_t nzb = nonzero_bytes(W);
+            if (byte) {
+                unsigned long long* o = out + words + 3 * __popc(nzb & ((1u << s) - 1u));
+                const unsigned long long cb = base + __popcll(W & lowmask(8 * s));
+                const unsigned long long off = s_off[byte];
+                if (((uintptr_t)o & 15) == 0) { st128(o, 0ULL, cb); o[2] = off; }
+                else { o[0] = 0ULL; st128(o + 1, cb, off); }
             }
-        }
-        if (odd && s == 7) out[0] = d0;                     // word 0: the data field of the first record
-        if (last < words && s == 6) out[words - 1] = ~0ULL; // the run's last word: an offsets field
-        // child record of byte s
-        const uint32_t byte = (uint32_t)((W >> (8 * s)) & 0xffULL);
-        const uint32_t nzb = nonzero_bytes(W);
-        if (byte) {
-            unsigned long long* o = out + words + 3 * __popc(nzb & ((1u << s) - 1u));
-            const unsigned long long cb = base + __popcll(W & lowmask(8 * s));
-            const unsigned long long off = s_off[byte];
-            if (((uintptr_t)o & 15) == 0) { st128(o, 0ULL, cb); o[2] = off; }
-            else { o[0] = 0ULL; st128(o + 1, cb, off); }
-        }
-        if (E.root_here && s == 0) {   // gridsize 4: the single brick is the root
-            unsigned long long* o = out + words + 3 * __popc(nzb);
-            o[0] = 0ULL;
-            o[1] = base + nleaf;
-            o[2] = child_offsets(nzb);
+            if (E.root_here && s == 0) {   // gridsize 4: the single brick is the root
+                unsigned long long* o = out + words + 3 * __popc(nzb);
+                o[0] = 0ULL;
+                o[1] = base + nleaf;
+                o[2] = child_offsets(nzb);
+            }
         }
     }
 }

@@ -57,6 +57,7 @@ struct Options {
     bool verbose = false;
     int device = 0;
     int gpus = 1;                    // -gpus N: shard the partitions over N devices (one context per device, in-process)
+    int separability = 26;           // -sep 6: opt-in 6-separating variant (not in the reference)
 };
 
 struct TriHeader {
@@ -90,6 +91,7 @@ void usage() {
                  "-d <percentage>       Percentage of memory limit to be used additionaly for sparseness optimization\n"
                  "-g <device>           CUDA device index (default 0)\n"
                  "-gpus <n>             Shard the build over the first n visible CUDA devices (power of two, default 1)\n"
+                 "-sep <26|6>           Separability: 26 = conservative voxelization (default, the reference's), 6 = thin\n"
                  "-v                    Be very verbose.\n"
                  "-h                    Print help and exit." << std::endl;
 }
@@ -134,6 +136,9 @@ Options parse(int argc, char** argv) {
             o.levels = true;
         } else if (a == "-g") {
             o.device = std::atoi(value().c_str());
+        } else if (a == "-sep") {
+            o.separability = std::atoi(value().c_str());
+            if (o.separability != 6 && o.separability != 26) bad_arguments("Requested separability must be 26 (conservative, default) or 6 (thin)");
         } else if (a == "-gpus") {
             o.gpus = std::atoi(value().c_str());
             if (o.gpus < 1 || (o.gpus & (o.gpus - 1)) != 0 || o.gpus > 16) bad_arguments("Requested GPU count must be a power of 2 (1..16)");
@@ -398,6 +403,7 @@ int main(int argc, char** argv) {
     prm.generate_levels = opt.levels ? 1 : 0;
     prm.color_mode = opt.color;
     prm.sparseness_limit = opt.sparseness;
+    prm.separability = opt.separability;
 
     const size_t rec_bytes = (size_t)kFloatsPerTri * sizeof(float);
     const size_t tri_bytes = (size_t)hdr.n_triangles * rec_bytes;

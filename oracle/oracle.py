@@ -88,6 +88,7 @@ def lib():
         L.svo_oracle_build_from_codes.restype = C.c_int
         L.svo_oracle_build_from_codes.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.POINTER(_Result)]
         L.svo_oracle_free.argtypes = [C.POINTER(_Result)]
+        L.svo_oracle_set_separability.argtypes = [C.c_int]
         L.svo_oracle_morton_encode.restype = C.c_uint64
         L.svo_oracle_morton_encode.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32]
         _lib = L
@@ -108,12 +109,17 @@ def _take(res: _Result, gridsize: int) -> OctreeFiles:
 
 
 def build(tris: np.ndarray, length: float, gridsize: int, memory_limit_mb: int = 2048,
-          levels: bool = False, color: str = "model") -> OctreeFiles:
-    """The restatement's whole pipeline (main.cpp:281-399). bbox = 0..length."""
+          levels: bool = False, color: str = "model", separability: int = 26) -> OctreeFiles:
+    """The restatement's whole pipeline (main.cpp:281-399). bbox = 0..length.
+    separability=6: the 6-separating variant (not in the reference; see svo_oracle.c)."""
     tris = np.ascontiguousarray(tris, dtype=np.float32)
     res = _Result()
-    rc = lib().svo_oracle_build(tris.ctypes.data, tris.shape[0], tris.shape[1], 0.0, np.float32(length),
-                                gridsize, memory_limit_mb, int(levels), COLOR_MODES[color], C.byref(res))
+    lib().svo_oracle_set_separability(separability)
+    try:
+        rc = lib().svo_oracle_build(tris.ctypes.data, tris.shape[0], tris.shape[1], 0.0, np.float32(length),
+                                    gridsize, memory_limit_mb, int(levels), COLOR_MODES[color], C.byref(res))
+    finally:
+        lib().svo_oracle_set_separability(26)
     assert rc == 0
     return _take(res, gridsize)
 
@@ -135,7 +141,7 @@ def partition_counts(tris: np.ndarray, length: float, gridsize: int, n_partition
 
 
 def voxelize(tris: np.ndarray, length: float, gridsize: int,
-             morton_start: int = 0, morton_end: int | None = None) -> np.ndarray:
+             morton_start: int = 0, morton_end: int | None = None, separability: int = 26) -> np.ndarray:
     """voxelize_schwarz_method over all triangles for one Morton range;
     returns the ascending Morton codes of the filled voxels."""
     tris = np.ascontiguousarray(tris, dtype=np.float32)
@@ -144,8 +150,12 @@ def voxelize(tris: np.ndarray, length: float, gridsize: int,
     vox = np.zeros(morton_end - morton_start, dtype=np.uint8)
     rt = lib().svo_oracle_text_roundtrip
     unit = np.float32(np.float32(rt(np.float32(length))) - np.float32(rt(0.0))) / np.float32(gridsize)
-    lib().svo_oracle_voxelize(tris.ctypes.data, tris.shape[1], None, tris.shape[0], morton_start, morton_end,
-                              np.float32(unit), vox.ctypes.data, None)
+    lib().svo_oracle_set_separability(separability)
+    try:
+        lib().svo_oracle_voxelize(tris.ctypes.data, tris.shape[1], None, tris.shape[0], morton_start, morton_end,
+                                  np.float32(unit), vox.ctypes.data, None)
+    finally:
+        lib().svo_oracle_set_separability(26)
     return np.flatnonzero(vox).astype(np.uint64) + np.uint64(morton_start)
 
 

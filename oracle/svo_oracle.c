@@ -197,6 +197,21 @@ static void barycentric_colour(const float* t /*21 floats*/, const float* n, flo
     for (int r = 0; r < 3; r++) out[r] = b[0] * c0[r] + b[1] * c1[r] + b[2] * c2[r];
 }
 
+/* Separability of the voxelization. 26 = the reference's conservative test (voxelizer.cpp:138-307). 6 = the
+ * 6-separating ("thin") variant of the same paper (Schwarz & Seidel 2010, "Fast parallel surface and solid
+ * voxelization on GPUs", sec. 4.2). The reference does NOT implement it: there is nothing to pin this
+ * restatement to but the published definition, so parity for this variant is "CUDA path == this restatement", not
+ * "== reference". Definition used (same setup arithmetic as the conservative test, glm op order):
+ *   k      = dominant axis of the triangle normal n (|n_x| >= |n_y| and |n_x| >= |n_z| -> x; else |n_y| >= |n_z| -> y; else z)
+ *   target = the axis-parallel segment through the voxel centre along k (its two face centres)
+ *   plane  : d1 = n . (c1 - v0), d2 = n . (c2 - v0) with c1 = (h, h, h) but c1[k] = 0, c2 = (h, h, h) but c2[k] = u, h = u / 2;
+ *            reject iff (n . p + d1) (n . p + d2) > 0                    (the plane separates the segment's end points)
+ *   edges  : ONLY the projection orthogonal to k, evaluated at the projected voxel CENTRE:
+ *            d_e = -(n_e . v_i) + h n_e.x + h n_e.y ; reject iff n_e . p + d_e < 0
+ * The candidate box (clamped bounding box) is the conservative one. */
+static int g_separability = 26;
+void svo_oracle_set_separability(int s) { g_separability = (s == 6) ? 6 : 26; }
+
 /* Shared body. If `pay` != NULL payload records are appended (svo_builder);
  * otherwise this is the BINARY_VOXELIZATION build. */
 static uint64_t voxelize_partition(const float* tris, int fpt, const uint64_t* ids, uint64_t n_ids,
@@ -247,6 +262,24 @@ static uint64_t voxelize_partition(const float* tris, int fpt, const uint64_t* i
                 ne[p][j][0] = nx; ne[p][j][1] = ny;
                 de[p][j] = (-1.0f * dot2(nx, ny, V[j][A], V[j][B]))
                            + stdmaxf(0.0f, unitlength * nx) + stdmaxf(0.0f, unitlength * ny); /* :228-230 */
+            }
+        }
+        if (g_separability == 6) {
+            const float ax = fabsf(n[0]), ay = fabsf(n[1]), az = fabsf(n[2]);
+            const int k = (ax >= ay && ax >= az) ? 0 : (ay >= az ? 1 : 2);
+            const float h = unitlength * 0.5f;
+            float c1[3] = { h, h, h }, c2[3] = { h, h, h };
+            c1[k] = 0.0f; c2[k] = unitlength;
+            for (int q2 = 0; q2 < 3; q2++) { a1[q2] = c1[q2] - v0[q2]; a2[q2] = c2[q2] - v0[q2]; }
+            d1 = dot3(n, a1);
+            d2 = dot3(n, a2);
+            for (int p = 0; p < 3; p++) {
+                int A = PA[p], B = PB[p];
+                for (int j = 0; j < 3; j++) {
+                    if (PN[p] != k) { ne[p][j][0] = 0.0f; ne[p][j][1] = 0.0f; de[p][j] = 0.0f; continue; }
+                    const float nx = ne[p][j][0], ny = ne[p][j][1];
+                    de[p][j] = ((-1.0f * dot2(nx, ny, V[j][A], V[j][B])) + h * nx) + h * ny;
+                }
             }
         }
         for (int x = gmn[0]; x <= gmx[0]; x++) {                                   /* :257-259 */

@@ -70,6 +70,10 @@ int svo_oracle_build_from_codes(const uint64_t* codes, uint64_t n, uint64_t grid
 
 void svo_oracle_free(svo_oracle_result* r);
 
+/* 26 (default) = the reference's conservative test; 6 = the 6-separating variant (NOT in the reference: a restatement
+ * of the published definition, see svo_oracle.c). Process-wide switch of svo_oracle_voxelize / svo_oracle_build. */
+void svo_oracle_set_separability(int separability);
+
 /* libmorton morton3D_64_encode / decode (x -> bit 0, y -> bit 1, z -> bit 2). */
 uint64_t svo_oracle_morton_encode(uint32_t x, uint32_t y, uint32_t z);
 void svo_oracle_morton_decode(uint64_t m, uint32_t* x, uint32_t* y, uint32_t* z);

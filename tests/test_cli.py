@@ -72,3 +72,38 @@ def test_cli_output_files_match_oracle(tmp_path, oracle, payload, args):
         ref = oracle.ref_build(m, g, memory_limit_mb=lim if "-l" in args else None, levels="-levels" in args,
                                color=color if "-c" in args else None)
         assert (ref.header, ref.nodes, ref.data) == (got.header, got.nodes, got.data)
+
+
+@pytest.mark.gpu
+def test_cli_threaded_io_with_a_small_budget(tmp_path, oracle):
+    """-l 2: the input ring and the output chunks shrink to a few hundred KB, so the file is read by several pread
+    threads in many chunks and written by several pwrite threads: same bytes, and the -v lines of the reference."""
+    m = mg.displaced_sphere(120, 120, seed=8)
+    hdr = mg.write_tri(str(tmp_path / "mesh"), m)
+    rc, out = run("svo_builder_binary", "-f", hdr, "-s", "256", "-l", "2", "-v")
+    assert rc == 0, out
+    want = oracle.build(m.tris, m.length, 256, memory_limit_mb=2)
+    got = oracle.read_outputs(str(tmp_path / "mesh") + "256_%d" % want.n_partitions)
+    assert (got.header, got.nodes, got.data) == (want.header, want.nodes, want.data), out[-1500:]
+    found = [int(line.split()[1]) for line in out.splitlines() if line.strip().startswith("found ")]
+    assert found and sum(found) == want.n_voxels                      # main.cpp:348, per partition
+    assert "Total amount of voxels: %d" % want.n_voxels in out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("gpus", [2, 8])
+@pytest.mark.parametrize("payload", [False, True])
+def test_cli_multi_gpu_files_match_oracle(tmp_path, oracle, gpus, payload):
+    import torch
+    if torch.cuda.device_count() < gpus:
+        pytest.skip("needs %d GPUs, this box has %d" % (gpus, torch.cuda.device_count()))
+    m = mg.displaced_sphere(150, 150, seed=9)
+    if payload:
+        m = mg.Mesh(mg.with_payload(m.tris), m.length)
+    hdr = mg.write_tri(str(tmp_path / "mesh"), m)
+    exe = "svo_builder" if payload else "svo_builder_binary"
+    rc, out = run(exe, "-f", hdr, "-s", "512", "-l", "100", "-gpus", str(gpus), "-v")
+    assert rc == 0, out
+    want = oracle.build(m.tris, m.length, 512, memory_limit_mb=100)
+    got = oracle.read_outputs(str(tmp_path / "mesh") + "512_%d" % want.n_partitions)
+    assert (got.header, got.nodes, got.data) == (want.header, want.nodes, want.data), out[-1500:]
