@@ -553,41 +553,73 @@ def ours_sharded(args, rank, world, local, dist, peak, peak_src):
 
     # ---- e2e: HOST triangles in, this rank's node / data range out to pinned host memory. Every rank uploads only its
     # 1/N slice of the triangle file over PCIe; the records reach the ranks that voxelize them over NVLink, the sharded
-    # step runs and each rank fetches its own range of the output files. No per-step barrier: the ranks are coupled by
-    # the exchange inside the step only.
+    # step runs and each rank fetches its own range of the output files. Same method as N = 1: TWO steps in flight -- two
+    # independent sets of contexts / peer windows / streams per rank, each driven by its own host thread -- and no
+    # per-step barrier: the ranks are coupled by the exchange inside a step only. (Input modes other than "remote" use
+    # NCCL inside the step and keep one step in flight.)
     h_slice = torch.empty((per, 9), dtype=torch.float32).pin_memory()
     h_slice[: hi_t - lo_t].copy_(torch.from_numpy(tris[lo_t:hi_t]))
     use_dispatch = mode != "replicated"
+    n_lanes = 2 if mode == "remote" else 1
+    lanes = [(db, stream)]
+    if n_lanes == 2:
+        db2 = DistributedBuilder(dist, local)
+        stream2 = torch.cuda.Stream()
+        db2.set_stream(stream2)
+        db2.enable_slices(per, 9, T)
+        lanes.append((db2, stream2))
     d_in = torch.empty((per if use_dispatch else world * per, 9), dtype=torch.float32, device="cuda")
-    h_nodes = PinnedBuffer(max(nhi - nlo, 1) * 24 + 24 * 4096)
-    h_data = PinnedBuffer(64)
-    with torch.cuda.stream(stream):
-        def e2e_step():
-            if mode == "remote":
-                db.upload_slice(h_slice.numpy()[: hi_t - lo_t])                                       # PCIe: 1/N of the mesh, NVLink: inside step()
-            elif mode == "dispatch":
-                d_in.copy_(h_slice, non_blocking=True)
-                db.set_local_triangles(d_in[: hi_t - lo_t])
-            else:
-                d_in[rank * per:(rank + 1) * per].copy_(h_slice, non_blocking=True)
-                dist.all_gather_into_tensor(d_in, d_in[rank * per:(rank + 1) * per])
-                db.set_triangles(d_in[:T])
-            db.step(prm)
-            a, b, c_, d = db.sb.shard_ranges()
-            db.sb.fetch_nodes(a, b - a, h_nodes.array[: (b - a) * 24])
-            if d > c_:
-                db.sb.fetch_data(c_, d - c_, h_data.array[: (d - c_) * 32])
-        for _ in range(3):
-            e2e_step()
-        torch.cuda.synchronize()
-        dist.barrier()
-        t = time.perf_counter()
-        for _ in range(args.steps):
-            e2e_step()
-        torch.cuda.synchronize()
-        dt = torch.tensor([time.perf_counter() - t], dtype=torch.float64, device="cuda")
+    outs = [(PinnedBuffer(max(nhi - nlo, 1) * 24 + 24 * 4096), PinnedBuffer(64)) for _ in lanes]
+
+    def e2e_step(k):
+        dbk, _ = lanes[k]
+        h_nodes, h_data = outs[k]
+        if mode == "remote":
+            dbk.upload_slice(h_slice.numpy()[: hi_t - lo_t])                                       # PCIe: 1/N of the mesh, NVLink: inside step()
+        elif mode == "dispatch":
+            d_in.copy_(h_slice, non_blocking=True)
+            dbk.set_local_triangles(d_in[: hi_t - lo_t])
+        else:
+            d_in[rank * per:(rank + 1) * per].copy_(h_slice, non_blocking=True)
+            dist.all_gather_into_tensor(d_in, d_in[rank * per:(rank + 1) * per])
+            dbk.set_triangles(d_in[:T])
+        dbk.step(prm)
+        a, b, c_, d = dbk.sb.shard_ranges()
+        dbk.sb.fetch_nodes(a, b - a, h_nodes.array[: (b - a) * 24])
+        if d > c_:
+            dbk.sb.fetch_data(c_, d - c_, h_data.array[: (d - c_) * 32])
+
+    errors = []
+
+    def lane_worker(k, n):
+        try:
+            torch.cuda.set_device(local)
+            with torch.cuda.stream(lanes[k][1]):
+                for _ in range(n):
+                    e2e_step(k)
+        except Exception as e:      # noqa: BLE001
+            errors.append("%s: %s" % (type(e).__name__, e))
+
+    for k in range(n_lanes):                                  # warm every lane (first step of a context is a sized build)
+        lane_worker(k, 3)
+    torch.cuda.synchronize()
+    dist.barrier()
+    per_lane = (args.steps + n_lanes - 1) // n_lanes
+    ths = [threading.Thread(target=lane_worker, args=(k, per_lane)) for k in range(n_lanes)]
+    t = time.perf_counter()
+    for th in ths:
+        th.start()
+    for th in ths:
+        th.join()
+    torch.cuda.synchronize()
+    dt = torch.tensor([time.perf_counter() - t], dtype=torch.float64, device="cuda")
     dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-    e2e_s = float(dt) / args.steps
+    e2e_s = float(dt) / (per_lane * n_lanes)
+    if errors:
+        raise SystemExit("e2e lane failed on rank %d: %s" % (rank, errors[0]))
+    assert outs[0][0].array[: (nhi - nlo) * 24].tobytes() == outs[-1][0].array[: (nhi - nlo) * 24].tobytes()      # both lanes: the same file range
+    if n_lanes == 2:
+        lanes[1][0].close()
 
     strong = None
     if os.environ.get("SVO_BENCH_STRONG", "1") != "0":
@@ -627,10 +659,11 @@ def ours_sharded(args, rank, world, local, dist, peak, peak_src):
                          "octree_build_stage": frac_entry((8 * nv + 24 * nn) / world, stage_max["ms_build"], peak)},
             "e2e": {"value": T / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(tris.nbytes),
                     "d2h_bytes_per_step": int(nn * 24 + nd * 32), "ms_per_step": e2e_s * 1e3,
+                    "in_flight": n_lanes,
                     "api": "per rank: pinned H2D of 1/N of the .tridata + %s + sharded step + svo_fetch_* of its file range to pinned host memory; wall clock "
-                           "over %d back-to-back steps, max over ranks, no per-step barrier" % (
+                           "over %d steps, %d in flight (independent context sets on their own host threads), max over ranks, no per-step barrier" % (
                                {"remote": "remote staging over NVLink inside the voxelizer", "dispatch": "triangle dispatch over NVLink",
-                                "replicated": "NCCL all-gather over NVLink"}[mode], args.steps)},
+                                "replicated": "NCCL all-gather over NVLink"}[mode], per_lane * n_lanes, n_lanes)},
             "gpu_launches": int(launches) * args.steps, "clocks": clocks,
             "stage_ms_max_over_ranks": stage_max,
             "pairs_rank0": {k: st[k] for k in ("n_pairs", "n_small", "n_medium", "n_large")},

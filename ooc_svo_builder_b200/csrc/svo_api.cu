@@ -44,7 +44,7 @@ struct LevelBufs {
         Level L;
         L.key = key.as<ull>(); L.mask = mask.as<ull>(); L.fc = fc.as<ull>(); L.ps = ps.as<ull>(); L.base = base.as<ull>();
         L.pi = pi.as<ull>(); L.pl = pl.as<ull>(); L.ibase = ibase.as<ull>(); L.cache = cache.as<float>();
-        L.n = n; L.np = nullptr; L.cap = n;
+        L.n = n; L.np = nullptr; L.cap = n; L.clear = nullptr;
         return L;
     }
 };
@@ -1429,6 +1429,7 @@ static Level fast_view(svo_ctx* c, int j) {
     L.np = &c->info_buf.as<BuildInfo>()->count[j];
     L.cap = c->fcap[j];
     L.n = c->fcap[j];
+    L.clear = c->dense[j].as<ull>() - c->bias[j];      // the emitter of every level clears the words of its tiles
     return L;
 }
 static int read_info(svo_ctx* c, const char* stamp) {
@@ -1702,17 +1703,9 @@ static int fast_phase_b(svo_ctx* c, ull* table) {
         }
     }
     mark(c, EV_BUILD1);
-    // ---- leave a clean pyramid behind: zero exactly the words that were set (skipped by an aborted build) ----
+    // (the pyramid is clean again: every emitter zeroed the dense words of the tiles it handled; an aborted build
+    // launched no emitter and keeps its pyramid)
     mark(c, EV_CLR0);
-    {
-        ClearJob Cj;
-        memset(&Cj, 0, sizeof Cj);
-        for (int j = 0; j <= J; j++) { Cj.key[j] = c->lv[j].key.as<ull>(); Cj.dense[j] = c->dense[j].as<ull>() - c->bias[j]; Cj.n[j] = c->fcap[j]; }
-        Cj.info = dinfo;
-        const ull n0 = std::max<ull>(launch_n(0), 1);
-        dim3 grid((unsigned)std::min<ull>(blocks_for(n0, 256), (ull)c->sm_count * 16), (unsigned)(J + 1));
-        k_sparse_clear_all<<<grid, 256, 0, c->stream>>>(Cj); LAUNCHED();
-    }
     mark(c, EV_CLR1);
     CK(cudaMemcpyAsync(c->h_info, c->info_buf.p, sizeof(BuildInfo), cudaMemcpyDeviceToHost, c->stream));
     return SVO_OK;

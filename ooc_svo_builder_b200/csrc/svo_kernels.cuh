@@ -156,6 +156,9 @@ __device__ __forceinline__ bool restrict_to_slab(const VoxJob& J, GridBox& b) {
 // exact comparisons, so the result is the one a scan over all slabs gives (NaN compares false, as there).
 __device__ __forceinline__ void slab_range(const float* bmin, const float* bmax, int n, float inv_w, float mn, float mx, int& lo, int& hi) {
     int i = clampi(__float2int_rz(fmul(mn, inv_w)), 0, n - 1);
+    // fast path (almost every triangle lies in ONE slab): slab i is the whole kept range iff it is kept, its lower
+    // neighbour is dropped by mn and its upper neighbour by mx -- the same comparisons the loops below would make
+    if (!(mn > bmax[i]) && !(mx < bmin[i]) && (i == 0 || mn > bmax[i - 1]) && (i == n - 1 || mx < bmin[i + 1])) { lo = hi = i; return; }
     while (i > 0 && !(mn > bmax[i - 1])) i--;
     while (i < n && (mn > bmax[i])) i++;
     lo = i;
@@ -939,6 +942,8 @@ struct Level {
     unsigned long long n;         // tile count known on the host (np == NULL) ...
     const unsigned long long* np; // ... or device-resident (BuildInfo::count[j]); then the lists hold `cap` entries
     unsigned long long cap;
+    unsigned long long* clear;    // fast path: the level's dense words (pre-biased); the emitter of the level zeroes the word of
+                                  // every tile it handles, which leaves a clean pyramid without a separate clearing pass
 };
 __device__ __forceinline__ unsigned long long level_n(const Level& L) {
     if (!L.np) return L.n;
@@ -992,6 +997,8 @@ struct TableFillJob {
     const unsigned long long* np;                  // device-resident count (fast path) or NULL
     unsigned long long* table;
     BuildInfo* info;
+    int stride;                                    // u64 per entry: 4, or 8 with -levels (entry[4..6] = the tile's 6-float data cache)
+    const float* cache;                            // -levels: Node::data_cache of the level-J tiles (k_levels_data)
 };
 // first leaf rank below tile i of level J: follow the first-child links down to level 0
 __device__ __forceinline__ unsigned long long first_leaf_below(const TableFillJob& T, unsigned long long i) {
@@ -999,11 +1006,18 @@ __device__ __forceinline__ unsigned long long first_leaf_below(const TableFillJo
     return i;
 }
 __device__ __forceinline__ void table_fill_entry(const TableFillJob& T, unsigned long long i) {
-    unsigned long long* e = T.table + T.key[i] * 4ULL;
+    unsigned long long* e = T.table + T.key[i] * (unsigned long long)(T.stride ? T.stride : 4);
     e[0] = T.mask[i];
     e[1] = T.ps[i + 1] - T.ps[i];
     e[2] = first_leaf_below(T, i + 1) - first_leaf_below(T, i);     // fc[j][n_j] = n_{j-1}: the chain is valid for i = n too
     e[3] = T.pi ? T.pi[i + 1] - T.pi[i] : 0ULL;
+    if (T.stride == 8 && T.cache) {
+        const uint32_t* cb = reinterpret_cast<const uint32_t*>(T.cache + i * 6);
+        e[4] = (unsigned long long)cb[0] | ((unsigned long long)cb[1] << 32);
+        e[5] = (unsigned long long)cb[2] | ((unsigned long long)cb[3] << 32);
+        e[6] = (unsigned long long)cb[4] | ((unsigned long long)cb[5] << 32);
+        e[7] = 0ULL;
+    }
 }
 __global__ void __launch_bounds__(256) k_table_fill(TableFillJob T) {
     if (build_aborted(T.info)) return;
@@ -1143,8 +1157,10 @@ __device__ __forceinline__ unsigned long long* node_slot(const EmitJob& E, const
 // -levels: data index of an internal node = records written before it. Payload mode interleaves the
 // leaf records (written at addVoxel) with the internal ones (written in post-order by groupNodes):
 // 1 + leaves up to the end of its subtree + its post-order rank. Binary mode has no leaf records: 2 + rank.
+// Sharded: `leaves_through` counts this rank's leaves only, E.leaf_offset adds the slabs of lower ranks; `rank` is global
+// (the ibase values of a rank's top tiles come from the merge of the shared levels).
 __device__ __forceinline__ unsigned long long internal_data_index(const EmitJob& E, unsigned long long leaves_through, unsigned long long rank) {
-    return (E.leaf_data_mode ? 1ULL + leaves_through : 2ULL) + rank;
+    return (E.leaf_data_mode ? 1ULL + E.leaf_offset + leaves_through : 2ULL) + rank;
 }
 
 // One tile of an upper level (tile = node at depth d with two packed levels): writes the records of its
@@ -1154,6 +1170,7 @@ __device__ __forceinline__ void emit_upper_tile(const Level& L, const Level& C, 
     const unsigned long long S = L.ps[i + 1] - L.ps[i];
     const uint32_t nzb = nonzero_bytes(W);
     const unsigned long long ps0 = C.ps[fc];
+    if (L.clear && lane == 31) L.clear[L.key[i]] = 0ULL;
 #pragma unroll
     for (int h = 0; h < 2; h++) {
         const int bit = lane + 32 * h;
@@ -1245,6 +1262,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_emit_leaf(Level L, Emi
             bW[h] = L.mask[t];
             bBase[h] = L.base[t];
             if (PAYLOAD) bFc[h] = L.fc[t];
+            if (L.clear) L.clear[L.key[t]] = 0ULL;
         }
     }
     const int g = lane >> 3, s = lane & 7;                                        // group (brick of the round), lane in the group
@@ -1338,7 +1356,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_emit_leaf_levels(Level
         if ((W >> bit) & 1ULL) {
             const int r = __popcll(W & lowmask(bit));
             if (unsigned long long* o = node_slot(E, R, base + r)) {
-                o[0] = E.leaf_data_mode ? 1ULL + lp + r + ib + __popc(nzb & ((1u << (bit >> 3)) - 1u)) : 1ULL;
+                o[0] = E.leaf_data_mode ? 1ULL + E.leaf_offset + lp + r + ib + __popc(nzb & ((1u << (bit >> 3)) - 1u)) : 1ULL;
                 o[1] = 0ULL;
                 o[2] = ~0ULL;
             }
@@ -1376,10 +1394,13 @@ __device__ __forceinline__ void write_data_record(float* data, unsigned long lon
     o[0] = make_float4(0.0f, 0.0f, canon_nan(c[0]), canon_nan(c[1]));              // morton 0
     o[1] = make_float4(canon_nan(c[2]), canon_nan(c[3]), canon_nan(c[4]), canon_nan(c[5]));
 }
-__global__ void __launch_bounds__(128) k_levels_data(Level L, Level C, int level, EmitJob E, float* data, int real_node) {
+// `data` is this rank's part of the data file biased by -data_lo records (record index = global data index).
+// cache_only (sharded -levels, before the exchange): no record is written; the leaf records are read from a local
+// staging array in leaf-rank order (record 1 + leaf rank) -- only the tiles' data caches are wanted, for the table.
+__global__ void __launch_bounds__(128) k_levels_data(Level L, Level C, int level, EmitJob E, float* data, int real_node, int cache_only) {
     const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= L.n) return;
-    const unsigned long long W = L.mask[i], fc = L.fc[i], ib = L.ibase[i];
+    const unsigned long long W = L.mask[i], fc = L.fc[i], ib = cache_only ? 0ULL : L.ibase[i];
     const uint32_t nzb = nonzero_bytes(W);
     float wsum[6] = { 0.f, 0.f, 0.f, 0.f, 0.f, 0.f };
     float wn = 0.0f;
@@ -1396,7 +1417,7 @@ __global__ void __launch_bounds__(128) k_levels_data(Level L, Level C, int level
             cn = fadd(cn, 1.0f);
             if (level == 0) {
                 if (E.leaf_data_mode) {     // payload leaves cache their data record (OctreeBuilder.cpp:160)
-                    const float* rec = data + (1ULL + c + ib + krank) * 8ULL;
+                    const float* rec = data + (cache_only ? 1ULL + c : 1ULL + E.leaf_offset + c + ib + krank) * 8ULL;
 #pragma unroll
                     for (int q = 0; q < 6; q++) csum[q] = fadd(csum[q], rec[2 + q]);
                 }                           // binary leaves cache zeros (OctreeBuilder.cpp:137-141)
@@ -1410,7 +1431,7 @@ __global__ void __launch_bounds__(128) k_levels_data(Level L, Level C, int level
         const unsigned long long cend = fc + __popcll(W & lowmask(8 * (k + 1)));
         const unsigned long long leaves_through = level == 0 ? cend : C.pl[cend];
         const unsigned long long rank = ib + (level == 0 ? 0ULL : C.pi[cend] - C.pi[fc]) + krank;
-        write_data_record(data, internal_data_index(E, leaves_through, rank), cc);
+        if (!cache_only) write_data_record(data, internal_data_index(E, leaves_through, rank), cc);
         wn = fadd(wn, 1.0f);
 #pragma unroll
         for (int q = 0; q < 6; q++) wsum[q] = fadd(wsum[q], cc[q]);
@@ -1419,7 +1440,7 @@ __global__ void __launch_bounds__(128) k_levels_data(Level L, Level C, int level
     finish_average(wsum, wn, wc);
 #pragma unroll
     for (int q = 0; q < 6; q++) L.cache[i * 6 + q] = wc[q];
-    if (real_node) write_data_record(data, internal_data_index(E, L.pl[i + 1], ib + (L.pi[i + 1] - L.pi[i]) - 1ULL), wc);
+    if (real_node && !cache_only) write_data_record(data, internal_data_index(E, L.pl[i + 1], ib + (L.pi[i + 1] - L.pi[i]) - 1ULL), wc);
 }
 
 // ---------------------------------------------------------------------------
@@ -1566,6 +1587,14 @@ __global__ void __launch_bounds__(256) k_scatter_records(const unsigned long lon
                                                          const unsigned long long* np, EmitJob E) {
     if (build_aborted(E.info)) return;
     scatter_records_body(pos, rec, n, np, E, (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x, (unsigned long long)gridDim.x * blockDim.x);
+}
+
+// sharded -levels: the data records of the shared upper levels' internal nodes, computed by the host-side merge
+__global__ void __launch_bounds__(256) k_scatter_data_records(const unsigned long long* pos, const float* rec, unsigned long long n,
+                                                              float* data /* biased by -data_lo records */) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    write_data_record(data, pos[i], rec + 6 * i);
 }
 
 // sparse clear of all levels in one launch (blockIdx.y = level)
