@@ -195,7 +195,8 @@ int svo_fetch_voxel_codes(svo_ctx* ctx, uint64_t* dst, uint64_t capacity, uint64
  *   svo_shard_ranges                  [node_lo, node_hi) / [data_lo, data_hi): the records this
  *                                     context holds; svo_fetch_* take global record positions
  *                                     inside these ranges. The ranges of all ranks tile the files.
- * -levels is not supported on the sharded path yet (SVO_E_INVALID).
+ * -levels: the table entries grow to 8 x u64 (the tile's 6-float data cache rides along) and the shared upper levels
+ * are averaged by every rank on the host from the table (the reference's float op order); builds are sized.
  *
  * SVO_E_RETRY. From its second job on a context builds speculatively: tile lists and node buffer keep the
  * capacities of the previous job and nothing waits for the host between svo_voxelize and the end of

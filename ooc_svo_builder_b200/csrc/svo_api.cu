@@ -146,8 +146,11 @@ struct svo_ctx {
     ull p_first = 0, p_last = 0;
     DevBuf table_own, dcol[4];
     LevelBufs glv;                     // global level-J tile list (sharded / odd depth)
-    std::vector<ull> h_table, h_rpos, h_rrec, h_ownbase;
-    DevBuf d_rpos, d_rrec;
+    std::vector<ull> h_table, h_rpos, h_rrec, h_ownbase, h_ownibase, h_dpos;
+    std::vector<float> h_drec;
+    DevBuf d_rpos, d_rrec, d_dpos, d_drec, stage_data;
+    bool owner_ready = false;           // sharded -levels: the owner pass already ran before the exchange
+    int tstride = 4;                    // u64 per exchange-table entry: 4, or 8 with -levels (+ the tile's 6-float data cache)
     ull n_upper_records = 0;
     ull leaf_offset = 0, n_voxels_local = 0;
     ull node_lo = 0, node_hi = 0, data_lo = 0, data_hi = 0;
@@ -527,7 +530,7 @@ void svo_ctx_destroy(svo_ctx* c) {
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     if (c->h_info) cudaFreeHost(c->h_info);
     c->info_buf.release(); c->merge_scratch.release(); c->merge_rpos.release(); c->merge_rrec.release();
-    c->d_rpos.release(); c->d_rrec.release();
+    c->d_rpos.release(); c->d_rrec.release(); c->d_dpos.release(); c->d_drec.release(); c->stage_data.release();
     cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -790,8 +793,8 @@ static int setup_geometry(svo_ctx* c) {
     const int dc = shard_chunk_depth(c);
     if (c->world > 1) {
         if (D - dc < 2) return fail(c, SVO_E_INVALID, "gridsize too small for this many shards");
-        if (c->prm.generate_levels) return fail(c, SVO_E_INVALID, "-levels is not supported on the sharded (multi-GPU) path yet");
     }
+    c->tstride = (c->world > 1 && c->prm.generate_levels) ? 8 : 4;
     c->dc = dc;
     c->J = (D - dc) / 2 - 1;
     if (c->J < 0) c->J = 0;                                     // gridsize 2: the single level-0 word is the (virtual) top
@@ -982,9 +985,49 @@ static int build_phase_a(svo_ctx* c, ull* table) {
             if (want_pl) CK(cudaMemsetAsync(c->lv[j].pl.p, 0, sizeof(ull), c->stream));
         }
     }
+    // ---- sharded -levels: the data caches (averaged colour + normal, Node::data_cache) of this rank's top tiles go into the
+    // table, so that every rank can average the shared upper levels (OctreeBuilder.cpp:82-99). They only depend on leaf
+    // VALUES, not on data indices: payload leaves are computed into a staging array in leaf-rank order (the owner pass is
+    // kept for phase B), binary leaves cache zeros; k_levels_data then runs in cache-only mode.
+    c->owner_ready = false;
+    if (levels && c->world > 1) {
+        CK(cudaMemcpyAsync(c->h_pinned + 36, c->lv[0].fc.as<ull>() + c->lv[0].n, sizeof(ull), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        const ull nleaf = c->lv[0].n ? c->h_pinned[36] : 0;
+        EmitJob Ec;
+        memset(&Ec, 0, sizeof Ec);
+        Ec.leaf_data_mode = payload ? 1 : 0; Ec.levels = 1;
+        float* stage = nullptr;
+        if (payload && nleaf) {
+            CK(c->stage_data.ensure((size_t)(nleaf + 1) * SVO_DATA_BYTES));
+            CK(c->owner.ensure((size_t)nleaf * sizeof(uint32_t)));
+            CK(cudaMemsetAsync(c->owner.p, 0xff, (size_t)nleaf * sizeof(uint32_t), c->stream));
+            int rc = launch_voxelizer<true>(c);
+            if (rc) return rc;
+            PayloadJob Pj;
+            memset(&Pj, 0, sizeof Pj);
+            Pj.tris = c->d_tris; Pj.owner = c->owner.as<uint32_t>();
+            if (c->sliced) {
+                Pj.segs.n = c->world;
+                for (int r = 0; r < c->world; r++) Pj.segs.ptr[r] = c->peer_slice[r];
+                Pj.segs.nslice = ((const SliceCtrl*)c->sl_ctrl.p)->nslice;
+            }
+            Pj.data = c->stage_data.as<float>();
+            Pj.unit_div = c->unit_div; Pj.gridsize_f = (float)c->prm.gridsize; Pj.color_mode = c->prm.color_mode;
+            Pj.levels = 0; Pj.leaf_offset = 0;
+            k_payload<<<blocks_for(c->lv[0].n, WARPS_PER_BLOCK), WARPS_PER_BLOCK * 32, 0, c->stream>>>(c->lv[0].view(), Pj); LAUNCHED();
+            c->owner_ready = true;
+            stage = c->stage_data.as<float>();
+        }
+        for (int j = 0; j <= J; j++) {
+            if (!c->lv[j].n) continue;
+            const Level L = c->lv[j].view();
+            k_levels_data<<<blocks_for(L.n, 128), 128, 0, c->stream>>>(L, j ? c->lv[j - 1].view() : L, j, Ec, stage, 0, 1); LAUNCHED();
+        }
+    }
     // ---- this rank's table entries ----
     if (table) {
-        CK(cudaMemsetAsync(table, 0, (size_t)c->WJ * 4 * sizeof(ull), c->stream));
+        CK(cudaMemsetAsync(table, 0, (size_t)c->WJ * c->tstride * sizeof(ull), c->stream));
         if (c->lv[J].n) {
             TableFillJob Tf;
             memset(&Tf, 0, sizeof Tf);
@@ -992,6 +1035,7 @@ static int build_phase_a(svo_ctx* c, ull* table) {
             Tf.pi = levels ? c->lv[J].pi.as<ull>() : nullptr;
             for (int j = 0; j <= J; j++) Tf.fc[j] = c->lv[j].fc.as<ull>();
             Tf.n = c->lv[J].n; Tf.J = J; Tf.table = table;      // np, info: NULL (memset)
+            Tf.stride = c->tstride; Tf.cache = (c->tstride == 8) ? c->lv[J].cache.as<float>() : nullptr;
             k_table_fill<<<blocks_for(c->lv[J].n, 256), 256, 0, c->stream>>>(Tf); LAUNCHED();
         }
     }
@@ -1011,14 +1055,25 @@ static inline ull h_lowmask(int n) { return n >= 64 ? ~0ULL : ((1ULL << n) - 1UL
 // Pure host arithmetic (no CUDA): T = the summed table, geometry from derive_grid / setup_geometry. Fills the global counts,
 // this rank's file range and leaf offsets, the bases of its own level-J tiles (h_ownbase) and the upper-level records that
 // fall into its range (h_rpos / h_rrec). Also behind svo_shard_layout_from_table, which the CPU tests check against the oracle.
+// -levels on the host: Node::data_cache arithmetic of OctreeBuilder.cpp:82-99 in the reference's float op order (the same as
+// finish_average / k_levels_data on the device): colour = sum / n, normal = normalize(sum / n).
+static inline void h_finish_average(const float* sum, float notnull, float* out) {
+    out[0] = sum[0] / notnull; out[1] = sum[1] / notnull; out[2] = sum[2] / notnull;
+    const float tx = sum[3] / notnull, ty = sum[4] / notnull, tz = sum[5] / notnull;
+    const float d = (tx * tx + ty * ty) + tz * tz;
+    const float inv = 1.0f / sqrtf(d);
+    out[3] = tx * inv; out[4] = ty * inv; out[5] = tz * inv;
+}
 static void shard_merge_compute(svo_ctx* c, const ull* T) {
     const int J = c->J, top = c->nl - 1;
     const ull WJ = c->WJ;
     const bool d_even = (c->D % 2) == 0;
+    const bool levels = c->prm.generate_levels != 0, payload = c->prm.payload != 0;
+    const int ts = levels ? 8 : 4;                          // u64 per table entry
     std::vector<std::vector<ull>> M(top + 1), S(top + 1), B(top + 1);
     M[J].resize(WJ); S[J].resize(WJ); B[J].assign(WJ, 0);
     ull leaves_total = 0;
-    for (ull e = 0; e < WJ; e++) { M[J][e] = T[4 * e]; S[J][e] = T[4 * e + 1]; leaves_total += T[4 * e + 2]; }
+    for (ull e = 0; e < WJ; e++) { M[J][e] = T[ts * e]; S[J][e] = T[ts * e + 1]; leaves_total += T[ts * e + 2]; }
     for (int j = J + 1; j <= top; j++) {
         const size_t n = (size_t)c->nwords[j];
         M[j].assign(n, 0); S[j].assign(n, 0); B[j].assign(n, 0);
@@ -1033,45 +1088,116 @@ static void shard_merge_compute(svo_ctx* c, const ull* T) {
     }
     c->n_voxels = leaves_total;
     c->n_nodes = leaves_total == 0 ? 1 : S[top][0] + (d_even ? 1 : 0);
+    // ---- -levels: internal-node counts, leaves through every subtree, data caches bottom-up; ranks and data indices top-down ----
+    std::vector<std::vector<ull>> I(top + 1), LT(top + 1), IB(top + 1);      // internals in the subtree; leaves up to its END; post-order rank before it
+    std::vector<std::vector<float>> CA(top + 1), CC(top + 1);                // tile cache (6 floats), byte-children caches (8 x 6 floats)
+    if (levels) {
+        I[J].assign(WJ, 0); LT[J].assign(WJ, 0); IB[J].assign(WJ, 0); CA[J].assign(WJ * 6, 0.f);
+        ull run = 0;
+        for (ull e = 0; e < WJ; e++) {
+            run += T[ts * e + 2];
+            LT[J][e] = run;
+            I[J][e] = T[ts * e + 3];
+            uint32_t w[6] = { (uint32_t)T[ts * e + 4], (uint32_t)(T[ts * e + 4] >> 32), (uint32_t)T[ts * e + 5], (uint32_t)(T[ts * e + 5] >> 32),
+                              (uint32_t)T[ts * e + 6], (uint32_t)(T[ts * e + 6] >> 32) };
+            memcpy(&CA[J][e * 6], w, sizeof w);
+        }
+        for (int j = J + 1; j <= top; j++) {
+            const size_t n = M[j].size();
+            I[j].assign(n, 0); LT[j].assign(n, 0); IB[j].assign(n, 0); CA[j].assign(n * 6, 0.f); CC[j].assign(n * 48, 0.f);
+            for (size_t w = 0; w < n; w++) {
+                const ull W = M[j][w];
+                // leaves through the end of this word's range even when it is empty (prefix of the last child)
+                LT[j][w] = LT[j - 1][std::min(w * 64 + 63, LT[j - 1].size() - 1)];
+                if (!W) continue;
+                ull inter = 1ULL + (ull)__builtin_popcount(nonzero_bytes(W));
+                float wsum[6] = { 0.f, 0.f, 0.f, 0.f, 0.f, 0.f }, wn = 0.0f;
+                for (int k = 0; k < 8; k++) {
+                    const uint32_t byte = (uint32_t)((W >> (8 * k)) & 0xffULL);
+                    if (!byte) continue;
+                    float csum[6] = { 0.f, 0.f, 0.f, 0.f, 0.f, 0.f }, cn = 0.0f;
+                    for (int b = 0; b < 8; b++) if ((byte >> b) & 1u) {
+                        const size_t ch = w * 64 + 8 * k + b;
+                        inter += I[j - 1][ch];
+                        cn = cn + 1.0f;
+                        for (int q = 0; q < 6; q++) csum[q] = csum[q] + CA[j - 1][ch * 6 + q];
+                    }
+                    float* cc = &CC[j][(w * 8 + k) * 6];
+                    h_finish_average(csum, cn, cc);
+                    wn = wn + 1.0f;
+                    for (int q = 0; q < 6; q++) wsum[q] = wsum[q] + cc[q];
+                }
+                h_finish_average(wsum, wn, &CA[j][w * 6]);
+                I[j][w] = inter;
+            }
+        }
+    }
+    const ull n_internal = (levels && leaves_total) ? I[top][0] - (d_even ? 0ULL : 1ULL) : 0ULL;     // the virtual top word of an odd depth is no node
+    c->n_data = (payload ? 1 + leaves_total : 2) + n_internal;                                       // OctreeBuilder.cpp:25-29 (+ one record per internal node)
+    auto data_index = [&](ull leaves_through, ull rank) -> ull { return (payload ? 1ULL + leaves_through : 2ULL) + rank; };
     // top-down: bases + upper records
-    std::vector<ull> rpos, rrec;
+    std::vector<ull> rpos, rrec, dpos;
+    std::vector<float> drec;
     auto push = [&](ull pos, ull d0, ull d1, ull d2) { rpos.push_back(pos); rrec.push_back(d0); rrec.push_back(d1); rrec.push_back(d2); };
+    auto push_data = [&](ull idx, const float* six) { dpos.push_back(idx); for (int q = 0; q < 6; q++) drec.push_back(six[q]); };
     for (int j = top; j > J; j--) {
         for (size_t w = 0; w < M[j].size(); w++) {
             const ull W = M[j][w];
             if (!W) continue;
             const ull base = B[j][w], sz = S[j][w];
             const uint32_t nzb = nonzero_bytes(W);
-            ull acc = 0;
+            const ull ib = levels ? IB[j][w] : 0ULL;
+            ull acc = 0, iacc = 0;
             for (int k = 0; k < 8; k++) {
                 const uint32_t byte = (uint32_t)((W >> (8 * k)) & 0xffULL);
                 if (!byte) continue;
                 const ull before = (ull)__builtin_popcountll(W & h_lowmask(8 * k));
+                const ull krank = (ull)__builtin_popcount(nzb & ((1u << k) - 1u));
+                std::vector<ull> gdata(8, 0ULL);
+                size_t last_ch = 0;
                 for (int b = 0; b < 8; b++) if ((byte >> b) & 1u) {
                     const size_t ch = w * 64 + 8 * k + b;
                     B[j - 1][ch] = base + acc + before;
                     acc += S[j - 1][ch];
+                    if (levels) {
+                        const ull gib = ib + iacc + krank;                       // internals completed before this grandchild's subtree
+                        IB[j - 1][ch] = gib;
+                        gdata[b] = data_index(LT[j - 1][ch], gib + I[j - 1][ch] - 1ULL);
+                        iacc += I[j - 1][ch];
+                        last_ch = ch;
+                    }
                 }
                 const ull blk = base + acc + before;
                 ull r = 0;
                 for (int b = 0; b < 8; b++) if ((byte >> b) & 1u) {
                     const size_t ch = w * 64 + 8 * k + b;
                     const uint32_t gnz = nonzero_bytes(M[j - 1][ch]);
-                    push(blk + r++, 0ULL, B[j - 1][ch] + S[j - 1][ch] - (ull)__builtin_popcount(gnz), child_offsets(gnz));
+                    push(blk + r++, gdata[b], B[j - 1][ch] + S[j - 1][ch] - (ull)__builtin_popcount(gnz), child_offsets(gnz));
                 }
-                push(base + sz - (ull)__builtin_popcount(nzb) + (ull)__builtin_popcount(nzb & ((1u << k) - 1u)), 0ULL, blk, child_offsets(byte));
+                ull cdata = 0ULL;
+                if (levels) {
+                    cdata = data_index(LT[j - 1][last_ch], ib + iacc + krank);   // the byte's node completes right behind its last grandchild
+                    push_data(cdata, &CC[j][(w * 8 + k) * 6]);
+                }
+                push(base + sz - (ull)__builtin_popcount(nzb) + krank, cdata, blk, child_offsets(byte));
             }
-            if (j == top && d_even) push(sz, 0ULL, base + sz - (ull)__builtin_popcount(nzb), child_offsets(nzb));
+            const bool real_node = !(j == top && !d_even);
+            ull own = 0ULL;
+            if (levels && real_node) {
+                own = data_index(LT[j][w], ib + I[j][w] - 1ULL);
+                push_data(own, &CA[j][w * 6]);
+            }
+            if (j == top && d_even) push(sz, own, base + sz - (ull)__builtin_popcount(nzb), child_offsets(nzb));
         }
     }
     // this rank's tiles, offsets and file range
     const ull wj0 = c->bias[J], wj1 = c->bias[J] + c->nwords[J];
     c->leaf_offset = 0; c->n_voxels_local = 0;
-    c->h_ownbase.clear();
+    c->h_ownbase.clear(); c->h_ownibase.clear();
     for (ull e = 0; e < WJ; e++) {
         if (!M[J][e]) continue;
-        if (e < wj0) c->leaf_offset += T[4 * e + 2];
-        else if (e < wj1) { c->h_ownbase.push_back(B[J][e]); c->n_voxels_local += T[4 * e + 2]; }
+        if (e < wj0) c->leaf_offset += T[ts * e + 2];
+        else if (e < wj1) { c->h_ownbase.push_back(B[J][e]); if (levels) c->h_ownibase.push_back(IB[J][e]); c->n_voxels_local += T[ts * e + 2]; }
     }
     auto first_base_from = [&](ull e0) -> ull { for (ull e = e0; e < WJ; e++) if (M[J][e]) return B[J][e]; return c->n_nodes; };
     c->node_lo = c->rank == 0 ? 0 : first_base_from(wj0);
@@ -1085,18 +1211,45 @@ static void shard_merge_compute(svo_ctx* c, const ull* T) {
         }
     }
     c->n_upper_records = c->h_rpos.size();
+    // ---- data file range of this rank ----
+    c->h_dpos.clear(); c->h_drec.clear();
+    if (levels) {
+        // first data record of a top tile's subtree: its first leaf (payload) or its first internal node (binary), i.e. the
+        // record with `leaves before` leaves and IB internal nodes in front of it
+        auto first_data_from = [&](ull e0) -> ull {
+            for (ull e = e0; e < WJ; e++) if (M[J][e]) return data_index(LT[J][e] - T[ts * e + 2], IB[J][e]);
+            return c->n_data;
+        };
+        c->data_lo = c->rank == 0 ? 0 : first_data_from(wj0);
+        c->data_hi = c->rank == c->world - 1 ? c->n_data : first_data_from(wj1);
+        if (leaves_total == 0) { c->data_lo = c->rank == 0 ? 0 : c->n_data; c->data_hi = c->n_data; }
+        for (size_t i = 0; i < dpos.size(); i++) {
+            if (dpos[i] >= c->data_lo && dpos[i] < c->data_hi) {
+                c->h_dpos.push_back(dpos[i]);
+                for (int q = 0; q < 6; q++) c->h_drec.push_back(drec[6 * i + q]);
+            }
+        }
+    } else if (payload) {
+        c->data_lo = c->rank == 0 ? 0 : 1 + c->leaf_offset;
+        c->data_hi = 1 + c->leaf_offset + c->n_voxels_local;
+    } else {
+        c->data_lo = 0; c->data_hi = c->n_data;
+        if (c->rank != 0) c->data_lo = c->data_hi = c->n_data;
+    }
 }
 
 static int shard_host_merge(svo_ctx* c, const ull* table) {
     const int J = c->J;
     const ull WJ = c->WJ;
-    c->h_table.resize((size_t)WJ * 4);
-    CK(cudaMemcpyAsync(c->h_table.data(), table, (size_t)WJ * 4 * sizeof(ull), cudaMemcpyDeviceToHost, c->stream));
+    c->h_table.resize((size_t)WJ * c->tstride);
+    CK(cudaMemcpyAsync(c->h_table.data(), table, (size_t)WJ * c->tstride * sizeof(ull), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     shard_merge_compute(c, c->h_table.data());
     if (c->h_ownbase.size() != c->lv[J].n) return fail(c, SVO_E_INVALID, "sharded merge: table does not match this rank's tiles (was the table summed over all ranks?)");
     if (!c->h_ownbase.empty())
         CK(cudaMemcpyAsync(c->lv[J].base.p, c->h_ownbase.data(), c->h_ownbase.size() * sizeof(ull), cudaMemcpyHostToDevice, c->stream));
+    if (!c->h_ownibase.empty())
+        CK(cudaMemcpyAsync(c->lv[J].ibase.p, c->h_ownibase.data(), c->h_ownibase.size() * sizeof(ull), cudaMemcpyHostToDevice, c->stream));
     if (c->n_upper_records) {
         CK(c->d_rpos.ensure(c->n_upper_records * sizeof(ull)));
         CK(c->d_rrec.ensure(c->n_upper_records * 3 * sizeof(ull)));
@@ -1251,8 +1404,10 @@ static int build_phase_b(svo_ctx* c, const ull* table) {
         const ull s_top = c->h_pinned[33];
         c->n_nodes = c->n_voxels == 0 ? 1 : s_top + (d_even ? 1 : 0);
     }
-    c->n_data = payload ? 1 + c->n_voxels : 2;          // OctreeBuilder.cpp:25-29
-    if (levels && c->n_voxels) c->n_data += c->h_pinned[34] - (d_even ? 0 : 1);   // one record per internal node (the virtual top word is no node)
+    if (!host_merge) {
+        c->n_data = payload ? 1 + c->n_voxels : 2;          // OctreeBuilder.cpp:25-29
+        if (levels && c->n_voxels) c->n_data += c->h_pinned[34] - (d_even ? 0 : 1);   // one record per internal node (the virtual top word is no node)
+    }                                                       // (sharded: shard_merge_compute)
 
     // level-J view of this rank's tiles inside the global list
     Level LJ = c->lv[J].view();
@@ -1344,27 +1499,28 @@ static int build_phase_b(svo_ctx* c, const ull* table) {
     }
     mark(c, EV_EMIT1);
     // ---- data records ----
+    // This rank's range of the data file: everything on one GPU; sharded: shard_merge_compute set it (payload: the leaf
+    // records of its slab; -levels: leaves and internal records interleaved in post-order, the shared upper levels'
+    // records fall to the rank whose range holds their index).
+    if (!host_merge) {
+        c->data_lo = 0; c->data_hi = c->n_data;
+    }
+    const ull n_local_data = c->data_hi - c->data_lo;
+    CK(c->data.ensure((size_t)(n_local_data ? n_local_data : 1) * SVO_DATA_BYTES));
+    float* const data_biased = c->data.as<float>() - c->data_lo * 8;          // record index = global data index
     if (!payload) {
-        c->data_lo = 0; c->data_hi = c->n_data;                  // 2 records (+ internal records with -levels), all on rank 0
-        if (c->rank != 0) c->data_lo = c->data_hi = c->n_data;
-        CK(c->data.ensure((size_t)(c->n_data) * SVO_DATA_BYTES));
         static const uint32_t white[16] = { 0, 0, 0, 0, 0, 0, 0, 0,                         // record 0: NULL
                                             0, 0, 0x3f800000u, 0x3f800000u, 0x3f800000u, 0, 0, 0 };  // record 1: white voxel
         if (c->rank == 0) CK(cudaMemcpyAsync(c->data.p, white, sizeof white, cudaMemcpyHostToDevice, c->stream));
     } else {
-        if (c->world == 1) { c->data_lo = 0; c->data_hi = c->n_data; }
-        else {
-            c->data_lo = c->rank == 0 ? 0 : 1 + c->leaf_offset;
-            c->data_hi = 1 + c->leaf_offset + c->n_voxels_local;
-        }
-        const ull n_local_data = c->data_hi - c->data_lo;
-        CK(c->data.ensure((size_t)(n_local_data ? n_local_data : 1) * SVO_DATA_BYTES));
         if (c->rank == 0) CK(cudaMemsetAsync(c->data.p, 0, SVO_DATA_BYTES, c->stream));
         if (c->n_voxels_local) {
-            CK(c->owner.ensure((size_t)c->n_voxels_local * sizeof(uint32_t)));
-            CK(cudaMemsetAsync(c->owner.p, 0xff, (size_t)c->n_voxels_local * sizeof(uint32_t), c->stream));
-            int rc = launch_voxelizer<true>(c);
-            if (rc) return rc;
+            if (!c->owner_ready) {
+                CK(c->owner.ensure((size_t)c->n_voxels_local * sizeof(uint32_t)));
+                CK(cudaMemsetAsync(c->owner.p, 0xff, (size_t)c->n_voxels_local * sizeof(uint32_t), c->stream));
+                int rc = launch_voxelizer<true>(c);
+                if (rc) return rc;
+            }
             PayloadJob Pj;
             memset(&Pj, 0, sizeof Pj);
             Pj.tris = c->d_tris; Pj.owner = c->owner.as<uint32_t>();
@@ -1373,7 +1529,7 @@ static int build_phase_b(svo_ctx* c, const ull* table) {
                 for (int r = 0; r < c->world; r++) Pj.segs.ptr[r] = c->peer_slice[r];
                 Pj.segs.nslice = ((const SliceCtrl*)c->sl_ctrl.p)->nslice;
             }
-            Pj.data = c->data.as<float>() - c->data_lo * 8;
+            Pj.data = data_biased;
             Pj.unit_div = c->unit_div; Pj.gridsize_f = (float)c->prm.gridsize; Pj.color_mode = c->prm.color_mode;
             Pj.levels = levels ? 1 : 0;
             Pj.leaf_offset = c->leaf_offset;
@@ -1381,15 +1537,25 @@ static int build_phase_b(svo_ctx* c, const ull* table) {
             k_payload<<<blocks_for(L0.n, WARPS_PER_BLOCK), WARPS_PER_BLOCK * 32, 0, c->stream>>>(L0, Pj); LAUNCHED();
         }
     }
+    c->owner_ready = false;
     if (levels && c->n_voxels) {
-        // internal-node data records, bottom-up (needs the leaf records and the ibase values written above)
+        // internal-node data records, bottom-up (needs the leaf records and the ibase values written above); sharded: the
+        // local levels here, the shared upper levels' records come from the host-side merge
         E.is_top = 0; E.root_here = 0;
-        for (int j = 0; j < nl; j++) {
+        for (int j = 0; j < (host_merge ? J + 1 : nl); j++) {
             if (!c->lv[j].n) continue;
             const int real_node = !(j == top && !d_even);
             const Level L = (j == J) ? LJ : c->lv[j].view();
             const Level C = j == 0 ? L : (j - 1 == J ? (upper ? GJ : LJ) : c->lv[j - 1].view());
-            k_levels_data<<<blocks_for(L.n, 128), 128, 0, c->stream>>>(L, C, j, E, c->data.as<float>(), real_node); LAUNCHED();
+            k_levels_data<<<blocks_for(L.n, 128), 128, 0, c->stream>>>(L, C, j, E, data_biased, real_node, 0); LAUNCHED();
+        }
+        if (host_merge && !c->h_dpos.empty()) {
+            const size_t nrec = c->h_dpos.size();
+            CK(c->d_dpos.ensure(nrec * sizeof(ull)));
+            CK(c->d_drec.ensure(nrec * 6 * sizeof(float)));
+            CK(cudaMemcpyAsync(c->d_dpos.p, c->h_dpos.data(), nrec * sizeof(ull), cudaMemcpyHostToDevice, c->stream));
+            CK(cudaMemcpyAsync(c->d_drec.p, c->h_drec.data(), nrec * 6 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+            k_scatter_data_records<<<blocks_for(nrec, 256), 256, 0, c->stream>>>(c->d_dpos.as<ull>(), c->d_drec.as<float>(), nrec, data_biased); LAUNCHED();
         }
     }
     mark(c, EV_BUILD1);
@@ -1788,7 +1954,7 @@ int svo_build(svo_ctx* c, uint64_t* n_voxels, uint64_t* n_nodes, uint64_t* n_dat
 int svo_shard_table_size(svo_ctx* c, uint64_t* n_u64) {
     if (!c || !n_u64) return SVO_E_INVALID;
     if (!c->partitioned) return fail(c, SVO_E_INVALID, "svo_shard_table_size before svo_partition");
-    *n_u64 = c->WJ * 4;
+    *n_u64 = c->WJ * c->tstride;
     return SVO_OK;
 }
 
@@ -1796,7 +1962,7 @@ int svo_shard_count(svo_ctx* c, uint64_t* dev_table) {
     if (!c) return SVO_E_INVALID;
     if (!c->voxelized) return fail(c, SVO_E_INVALID, "svo_shard_count before svo_voxelize");
     CK(cudaSetDevice(c->device));
-    if (!dev_table) { CK(c->table_own.ensure((size_t)c->WJ * 4 * sizeof(ull))); dev_table = c->table_own.as<uint64_t>(); }      // library-owned table
+    if (!dev_table) { CK(c->table_own.ensure((size_t)c->WJ * c->tstride * sizeof(ull))); dev_table = c->table_own.as<uint64_t>(); }      // library-owned table
     c->fast = fast_path_applies(c);
     if (c->fast) return fast_phase_a(c, (ull*)dev_table, true, false);
     return build_phase_a(c, (ull*)dev_table);
@@ -1808,14 +1974,14 @@ int svo_shard_exchange(svo_ctx* c, uint64_t* dev_table) {
     if (!c->sliced) return fail(c, SVO_E_INVALID, "svo_shard_exchange needs the peer windows of svo_shard_slice_*; otherwise sum the table with your own collective");
     if (!dev_table) dev_table = c->table_own.as<uint64_t>();
     if (!dev_table) return fail(c, SVO_E_INVALID, "dev_table is NULL");
-    const size_t bytes = (size_t)c->WJ * 4 * sizeof(ull);
+    const size_t bytes = (size_t)c->WJ * c->tstride * sizeof(ull);
     if (bytes > XTABLE_BYTES) return fail(c, SVO_E_RANGE, "subtree table is larger than the exchange window; sum it with your own collective");
     CK(cudaSetDevice(c->device));
     // own entries = the level-J words of this rank's slab: a contiguous range of the table; the ranges of all ranks tile it
     XchgJob X;
     memset(&X, 0, sizeof X);
     X.src = (const ull*)dev_table;
-    X.lo = c->bias[c->J] * 4ULL; X.n = c->nwords[c->J] * 4ULL;
+    X.lo = c->bias[c->J] * (ull)c->tstride; X.n = c->nwords[c->J] * (ull)c->tstride;
     X.world = c->world; X.me = c->rank; X.epoch = ++c->xchg_epoch;      // every rank calls the exchange the same number of times
     X.info = c->fast ? c->info_buf.as<BuildInfo>() : nullptr;
     for (int r = 0; r < c->world; r++) { X.xtable[r] = c->peer_xtable[r]; X.ctrl[r] = c->peer_slctrl[r]; }
@@ -2231,7 +2397,7 @@ int svo_shard_layout_from_table(const svo_params* params, int rank, int world, c
     if (rc == SVO_OK) { c->world = world; c->rank = rank; rc = derive_grid(c, params); }
     if (rc == SVO_OK) rc = setup_geometry(c);
     if (rc != SVO_OK) return fail(nullptr, rc, tmp.err);
-    if (n_u64 != c->WJ * 4) return fail(nullptr, SVO_E_RANGE, "table size does not match svo_shard_table_size for this geometry");
+    if (n_u64 != c->WJ * c->tstride) return fail(nullptr, SVO_E_RANGE, "table size does not match svo_shard_table_size for this geometry");
     shard_merge_compute(c, (const ull*)host_table);
     out->n_voxels = c->n_voxels; out->n_nodes = c->n_nodes;
     out->node_lo = c->node_lo; out->node_hi = c->node_hi;

@@ -430,7 +430,6 @@ int main(int argc, char** argv) {
         if (!ok) { std::cout << "Error reading " << tridata << ": " << svo_last_error(ctx[0]) << std::endl; return 0; }
         if (svo_synchronize(ctx[0]) != SVO_OK) die(ctx[0], "svo_synchronize");
     } else {
-        if (opt.levels) { std::cout << "Error: -levels is not available with -gpus > 1" << std::endl; return 0; }
         for (int r = 0; r < world; r++) {
             if (svo_shard_configure(ctx[r], r, world) != SVO_OK) die(ctx[r], "svo_shard_configure");
             if (svo_shard_slice_create(ctx[r], per_rank, kFloatsPerTri, &windows[r]) != SVO_OK) die(ctx[r], "svo_shard_slice_create");

@@ -107,7 +107,7 @@ def slice_bounds(n_tris: int, world: int, rank: int) -> tuple[int, int]:
 
 def run_single_process(tris, length: float, gridsize: int, world: int, memory_limit_mb: int = 2048,
                        color: str = "model", device: int = 0, fetch: bool = True, dispatch: bool = False,
-                       slices: list | None = None, remote: bool = False) -> list[ShardResult]:
+                       slices: list | None = None, remote: bool = False, levels: bool = False) -> list[ShardResult]:
     """All `world` ranks as contexts of ONE process (sharing a GPU is fine): the table exchange is a
     host-side sum. Used by the single-GPU parity tests of the sharded path and by the CLI.
     dispatch=True: every rank starts with only its slice of the file and the triangle dispatch
@@ -119,7 +119,7 @@ def run_single_process(tris, length: float, gridsize: int, world: int, memory_li
     payload = tris.shape[1] == 21
     ctxs = [SvoBuilder(device) for _ in range(world)]
     try:
-        prm = SvoBuilder.make_params(length, gridsize, payload, memory_limit_mb, False, color)
+        prm = SvoBuilder.make_params(length, gridsize, payload, memory_limit_mb, levels, color)
         tables = []
         if dispatch:
             T = tris.shape[0]

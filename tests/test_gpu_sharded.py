@@ -10,10 +10,10 @@ from ooc_svo_builder_b200 import sharded
 pytestmark = pytest.mark.gpu
 
 
-def _check(oracle, mesh, g, world, limit=2048, color="model", **kw):
-    res = sharded.run_single_process(mesh.tris, mesh.length, g, world, memory_limit_mb=limit, color=color, **kw)
+def _check(oracle, mesh, g, world, limit=2048, color="model", levels=False, **kw):
+    res = sharded.run_single_process(mesh.tris, mesh.length, g, world, memory_limit_mb=limit, color=color, levels=levels, **kw)
     hdr, nodes, data = sharded.assemble(res, g)
-    want = oracle.build(mesh.tris, mesh.length, g, memory_limit_mb=limit, color=color)
+    want = oracle.build(mesh.tris, mesh.length, g, memory_limit_mb=limit, color=color, levels=levels)
     assert hdr == want.header
     gn = np.frombuffer(nodes.tobytes(), dtype=np.uint64).reshape(-1, 3)
     wn = np.frombuffer(want.nodes, dtype=np.uint64).reshape(-1, 3)
@@ -59,17 +59,22 @@ def test_sharded_payload(oracle, world):
     _check(oracle, mg.terrain(100, seed=2), 128, world, color="linear")
 
 
-def test_sharded_levels_is_rejected():
-    from ooc_svo_builder_b200 import SvoBuilder, SvoError
-    sb = SvoBuilder(0)
-    try:
-        sb.shard_configure(0, 2)
-        m = mg.icosphere(2)
-        sb.set_triangles(m.tris)
-        with pytest.raises(SvoError):
-            sb.partition(SvoBuilder.make_params(m.length, 64, False, levels=True))
-    finally:
-        sb.close()
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_sharded_levels(oracle, world):
+    """-levels across ranks (OctreeBuilder.cpp:82-99): the data caches of the top-of-shard tiles ride in the exchange table,
+    the shared upper levels are averaged from it, internal data records interleave with the leaf records in post-order
+    across the ranks' ranges of the data file. Payload (float averaging, bit-exact) and binary (index structure)."""
+    ico = mg.icosphere(4)
+    _check(oracle, mg.Mesh(mg.with_payload(ico.tris), ico.length), 128, world, levels=True)
+    _check(oracle, mg.terrain(90, seed=2), 256, world, limit=3, levels=True)                  # 8 partitions, odd depth
+    _check(oracle, mg.random_soup(900, seed=6, payload=True), 128, world, levels=True, color="normal")
+    _check(oracle, mg.random_soup(400, seed=3), 64, world, levels=True)                       # binary
+    _check(oracle, mg.empty_mesh(payload=True), 64, world, levels=True)
+
+
+def test_sharded_levels_remote_staging(oracle):
+    _check(oracle, mg.terrain(90, seed=2), 256, 4, limit=3, levels=True, remote=True)
+    _check(oracle, mg.icosphere(4), 128, 2, levels=True, remote=True)
 
 
 # ---- triangle dispatch over peer memory: every rank starts with a slice of the file only ----------------------
