@@ -3,8 +3,8 @@
 // point needs a compute-capability 10.x device.
 #include "../../include/svo_b200.h"
 #include "svo_kernels.cuh"
-#include "svo_build.cuh"
 #include "svo_dispatch.cuh"
+#include "svo_build.cuh"
 
 #include <cmath>
 #include <cstdio>
@@ -124,7 +124,10 @@ struct svo_ctx {
     bool fast = false, spec = false, fast_caps_ok = false;
     int jB = 1;                        // levels 1..jB are scanned by k_dense_scan, jB+1..J by k_small_levels
     int jE = 1;                        // levels jE+1..J are emitted by the single-block top kernel
-    int top_pending = 0;               // k_top stages of phase A whose launch was deferred to phase B (one GPU)
+    int top_pending = 0;               // k_top stages of phase A whose launch was deferred (one GPU: to phase B; sharded with the
+                                       // peer-memory exchange: to svo_shard_exchange, which adds the push of the table entries)
+    bool xwait_pending = false;        // the wait for the peers' table entries is folded into phase B's k_top
+    ull* xchg_user_table = nullptr;    // caller's table buffer: receives a copy of the complete table at the end of svo_shard_emit
     ull fcap[MAX_LEVELS];              // entries the tile lists of each level hold
 
     // outputs
@@ -369,6 +372,7 @@ VoxJob make_voxjob(svo_ctx* c) {
         J.pull_cap = c->sl_cap_blocks * 4;
         J.pull_counts = &own->count[0][c->rank];
         J.pull_first = c->rank;
+
     }
     return J;
 }
@@ -1667,6 +1671,16 @@ static int make_topjob(svo_ctx* c, ull* table, TopJob& P) {
     Mj.keyJ = c->lv[J].key.as<ull>(); Mj.baseJ = c->lv[J].base.as<ull>(); Mj.capJ = c->fcap[J];
     Mj.info = dinfo;
     Mj.nodes_cap = c->spec ? c->nodes.cap / SVO_NODE_BYTES : ~0ULL;
+    if (c->sliced && c->sl_attached) {
+        XchgJob& X = P.X;
+        X.src = table;
+        X.lo = c->bias[J] * (ull)c->tstride; X.n = c->nwords[J] * (ull)c->tstride;
+        X.world = c->world; X.me = c->rank; X.epoch = c->xchg_epoch;
+        X.info = dinfo;
+        for (int r = 0; r < c->world; r++) { X.xtable[r] = c->peer_xtable[r]; X.ctrl[r] = c->peer_slctrl[r]; }
+        P.own_ctrl = (SliceCtrl*)c->sl_ctrl.p;
+        if (c->xwait_pending) Mj.table = c->sl_xtable.as<ull>();      // the complete table lives in this rank's exchange window
+    }
     return SVO_OK;
 }
 static int launch_top(svo_ctx* c, ull* table, int stages) {
@@ -1768,7 +1782,10 @@ static int fast_phase_a(svo_ctx* c, ull* table, bool fill_table, bool force_sync
     // ---- everything one block does: small-level lists and sizes, this rank's table entries. On one GPU the launch is
     // deferred to phase B, where the merge, the scattered upper records and the top-level emission join it ----
     c->top_pending = TOP_LISTS | TOP_SIZES | (fill_table ? TOP_TABLE : 0);
-    if (c->world > 1) {
+    if (fill_table) c->xwait_pending = false;              // (a repeated build keeps reading the exchanged table from the window)
+    if (c->world > 1 && !(fill_table && c->sliced && c->uses_peer_exchange)) {
+        // (a context that exchanges over peer memory keeps the stages pending: svo_shard_exchange launches them together with
+        // the push of the table entries)
         if ((rc = launch_top(c, table, c->top_pending))) return rc;
         c->top_pending = 0;
     }
@@ -1784,9 +1801,12 @@ static int fast_phase_b(svo_ctx* c, ull* table) {
     BuildInfo* dinfo = c->info_buf.as<BuildInfo>();
     const bool spec = c->spec;
     int rc;
+    if (c->world > 1 && c->top_pending)
+        return fail(c, SVO_E_INVALID, "svo_shard_emit: this context exchanges its table with svo_shard_exchange, which was not called for this job");
+    const int xw = c->xwait_pending ? TOP_XWAIT : 0;
     if (!spec) {
         // ---- merged upper levels; read-back #2: record counts and this rank's range ----
-        if ((rc = launch_top(c, table, c->top_pending | TOP_MERGE))) return rc;
+        if ((rc = launch_top(c, table, c->top_pending | xw | TOP_MERGE))) return rc;
         c->top_pending = 0;
         if (c->world == 1) mark(c, EV_CMP1);
         if ((rc = read_info(c, "sync2_wait"))) return rc;
@@ -1800,7 +1820,7 @@ static int fast_phase_b(svo_ctx* c, ull* table) {
     } else {
         // ---- one launch: [small-level lists and sizes, table,] merge, scattered upper records, top-level emission ----
         mark(c, EV_EMIT0);
-        if ((rc = launch_top(c, table, c->top_pending | TOP_MERGE | TOP_SCATTER | TOP_EMIT))) return rc;
+        if ((rc = launch_top(c, table, c->top_pending | xw | TOP_MERGE | TOP_SCATTER | TOP_EMIT))) return rc;
         c->top_pending = 0;
     }
     EmitJob E;
@@ -1873,6 +1893,8 @@ static int fast_phase_b(svo_ctx* c, ull* table) {
     // launched no emitter and keeps its pyramid)
     mark(c, EV_CLR0);
     mark(c, EV_CLR1);
+    if (c->xwait_pending && c->xchg_user_table)      // the caller's table buffer ends up holding the complete table (off the critical path)
+        CK(cudaMemcpyAsync(c->xchg_user_table, c->sl_xtable.p, (size_t)c->WJ * c->tstride * sizeof(ull), cudaMemcpyDeviceToDevice, c->stream));
     CK(cudaMemcpyAsync(c->h_info, c->info_buf.p, sizeof(BuildInfo), cudaMemcpyDeviceToHost, c->stream));
     return SVO_OK;
 }
@@ -1977,6 +1999,19 @@ int svo_shard_exchange(svo_ctx* c, uint64_t* dev_table) {
     const size_t bytes = (size_t)c->WJ * c->tstride * sizeof(ull);
     if (bytes > XTABLE_BYTES) return fail(c, SVO_E_RANGE, "subtree table is larger than the exchange window; sum it with your own collective");
     CK(cudaSetDevice(c->device));
+    if (c->fast) {
+        // device-driven build: the push rides in the single-block top kernel (with the deferred stages of the local build, if
+        // any), the wait for the peers' entries rides in svo_shard_emit's: no kernel of its own, no copy of the table
+        ++c->xchg_epoch;                                    // every rank calls the exchange the same number of times
+        c->xchg_user_table = (ull*)dev_table;
+        int rc = launch_top(c, (ull*)dev_table, c->top_pending | TOP_XPUSH);
+        if (rc) return rc;
+        c->top_pending = 0;
+        c->xwait_pending = true;
+        c->exchanged_by_peer_memory = true;
+        c->uses_peer_exchange = true;
+        return SVO_OK;
+    }
     // own entries = the level-J words of this rank's slab: a contiguous range of the table; the ranges of all ranks tile it
     XchgJob X;
     memset(&X, 0, sizeof X);
@@ -2222,8 +2257,8 @@ int svo_shard_slice_create(svo_ctx* c, uint64_t capacity_tris, int fpt, void** d
     char* w = (char*)c->window.p;
     c->sl_ctrl.p = w + L.ctrl; c->sl_xtable.p = w + L.xtable; c->sl_list.p = w + L.list; c->slice.p = w + L.slice;
     CK(cudaMemset(c->sl_ctrl.p, 0, sizeof(SliceCtrl)));
-    CK(c->sl_cursor.ensure(MAX_WORLD * sizeof(ull)));
-    CK(cudaMemset(c->sl_cursor.p, 0, MAX_WORLD * sizeof(ull)));
+    CK(c->sl_cursor.ensure((MAX_WORLD + 1) * sizeof(ull)));
+    CK(cudaMemset(c->sl_cursor.p, 0, (MAX_WORLD + 1) * sizeof(ull)));
     c->slice_cap = capacity_tris;
     c->sl_world = c->world;
     c->slice_fpt = fpt;
@@ -2332,7 +2367,7 @@ int svo_shard_slice_publish(svo_ctx* c, const svo_params* params, uint64_t n_tot
     if (rc) return rc;
     const int dc = shard_chunk_depth(c);
     if (c->D - dc < 2) return fail(c, SVO_E_INVALID, "gridsize too small for this many shards");
-    rc = svo_shard_slice_fence(c);                          // the peers' list buffers are about to be rewritten
+    rc = svo_shard_slice_fence(c);                          // the peers' list buffers are about to be rewritten (one-block wait kernel)
     if (rc) return rc;
     const uint32_t launches_before = c->launches;
     mark(c, EV_DSP0);
@@ -2359,18 +2394,14 @@ int svo_shard_slice_publish(svo_ctx* c, const svo_params* params, uint64_t n_tot
     D.epoch = ++c->sl_epoch;
     S.cap = c->sl_cap_blocks * 4;
     S.cursor = c->sl_cursor.as<ull>();
-    if (D.nb) {
-        const size_t smem = (size_t)FILTER_WARPS * VOX_BLOCK * c->slice_fpt * sizeof(float);      // 36 / 84 KB
-        if (!c->filter_attr_set) {
-            CK(cudaFuncSetAttribute(k_slice_filter<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, FILTER_WARPS * VOX_BLOCK * 9 * (int)sizeof(float)));
-            CK(cudaFuncSetAttribute(k_slice_filter<21>, cudaFuncAttributeMaxDynamicSharedMemorySize, FILTER_WARPS * VOX_BLOCK * 21 * (int)sizeof(float)));
-            c->filter_attr_set = true;
-        }
-        const unsigned grid = (unsigned)std::min<ull>((D.nb + FILTER_WARPS - 1) / FILTER_WARPS, (ull)c->sm_count * 4);
-        if (c->slice_fpt == 9) { k_slice_filter<9><<<grid, FILTER_WARPS * 32, smem, c->stream>>>(S); LAUNCHED(); }
-        else { k_slice_filter<21><<<grid, FILTER_WARPS * 32, smem, c->stream>>>(S); LAUNCHED(); }
+    if (D.n_local) {
+        // one launch: list this slice's units per destination and (the block that finishes last) publish counts + flag
+        const ull n_units = (D.n_local + UNIT - 1) / UNIT;
+        const unsigned grid = (unsigned)std::min<ull>((n_units + FILTER_WARPS * 4 - 1) / (FILTER_WARPS * 4), (ull)c->sm_count * 8);
+        k_slice_filter<<<grid, FILTER_WARPS * 32, 0, c->stream>>>(S); LAUNCHED();
+    } else {
+        k_slice_post<<<1, MAX_WORLD, 0, c->stream>>>(S, 0); LAUNCHED();
     }
-    k_slice_post<<<1, MAX_WORLD, 0, c->stream>>>(S, 0); LAUNCHED();
     mark(c, EV_DSP1);
     c->dispatch_launches = c->launches - launches_before;
     // the triangle set of this context is now the union of all slices, addressed by file position

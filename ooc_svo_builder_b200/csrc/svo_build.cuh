@@ -17,6 +17,7 @@
 //                   (same arithmetic as the host-side svo_shard_layout_from_table)
 #pragma once
 #include "svo_kernels.cuh"
+#include "svo_dispatch.cuh"
 
 namespace svo {
 
@@ -415,19 +416,53 @@ __global__ void __launch_bounds__(1024) k_shard_merge(MergeJob Mj) {
 // all of them on one GPU; [lists, sizes, table] | exchange | [merge, scatter, emit] when sharded; the merge alone
 // when the node buffer still has to be sized on the host.
 // ---------------------------------------------------------------------------
-enum { TOP_LISTS = 1, TOP_SIZES = 2, TOP_TABLE = 4, TOP_MERGE = 8, TOP_SCATTER = 16, TOP_EMIT = 32 };
+enum { TOP_LISTS = 1, TOP_SIZES = 2, TOP_TABLE = 4, TOP_MERGE = 8, TOP_SCATTER = 16, TOP_EMIT = 32, TOP_XPUSH = 64, TOP_XWAIT = 128 };
 struct TopJob {
     int stages;
     SmallLevelsJob S;
     FusedJob F;                       // lv[jB..J] views; jf_up = first level of the size pass, jf = last level NOT emitted here
     TableFillJob T; unsigned long long table_words;
     MergeJob M;
+    XchgJob X; SliceCtrl* own_ctrl;   // sharded, peer-memory exchange of the table (svo_dispatch.cuh): push after TABLE, wait before MERGE
     BuildInfo* info;
 };
 __global__ void __launch_bounds__(1024) k_top(TopJob P) {
     if ((P.stages & TOP_LISTS) && !build_aborted(P.info)) small_levels_body(P.S);
     if ((P.stages & TOP_SIZES) && !build_aborted(P.info)) fused_up_body(P.F, P.F.jf_up);
     if ((P.stages & TOP_TABLE) && !build_aborted(P.info)) table_fill_body(P.T, P.table_words);
+    if (P.stages & TOP_XPUSH) {
+        // this rank's entries into every peer's exchange table, then the flag. Runs for an aborted build as well: the
+        // peers must learn that this rank has nothing to offer (poisoned flag -> SVO_E_RETRY on every rank)
+        const bool poisoned = build_aborted(P.info);
+        if (!poisoned)
+            for (int p = 0; p < P.X.world; p++) {
+                unsigned long long* dst = P.X.xtable[p];
+                for (unsigned long long i = threadIdx.x; i < P.X.n; i += blockDim.x) dst[P.X.lo + i] = P.X.src[P.X.lo + i];
+            }
+        __threadfence_system();
+        __syncthreads();
+        if ((int)threadIdx.x < P.X.world) {
+            __threadfence_system();
+            *(volatile unsigned long long*)&P.X.ctrl[threadIdx.x]->flag[2][P.X.me] = 2ULL * P.X.epoch + (poisoned ? 1ULL : 0ULL);
+        }
+        __syncthreads();
+    }
+    if (P.stages & TOP_XWAIT) {
+        // ONE block spins here (like the k_xchg_wait launch it replaces): it cannot keep a peer's kernels off this GPU
+        if ((int)threadIdx.x < P.X.world) {
+            const volatile unsigned long long* f = &P.own_ctrl->flag[2][threadIdx.x];
+            const long long t0 = clock64();
+            unsigned long long v;
+            while (((v = *f) >> 1) < P.X.epoch) {
+                if (clock64() - t0 > 8000000000LL) { P.own_ctrl->error = 3ULL; break; }
+                __nanosleep(100);
+            }
+            if ((v >> 1) == P.X.epoch && (v & 1ULL)) atomicOr(&P.info->overflow, 1ULL << 43);
+            __threadfence_system();
+        }
+        __threadfence();
+        __syncthreads();
+    }
     if ((P.stages & TOP_MERGE) && !build_aborted(P.info)) shard_merge_body(P.M);
     if ((P.stages & TOP_SCATTER) && !build_aborted(P.info)) {
         scatter_records_body(P.M.rpos, P.M.rrec, P.M.rcap, &P.info->n_upper, P.F.E, threadIdx.x, blockDim.x);

@@ -187,101 +187,104 @@ struct SliceJob {
     uint32_t* list[MAX_WORLD];                  // peer list buffers: region [src * cap, (src + 1) * cap) belongs to source src
     SliceCtrl* ctrl[MAX_WORLD];
     unsigned long long cap;                     // list entries (32-triangle units) per region
-    unsigned long long* cursor;                 // local, MAX_WORLD counters (zeroed by k_slice_post)
+    unsigned long long* cursor;                 // local: MAX_WORLD list cursors + [MAX_WORLD] the count of finished blocks (all zeroed by the posting block)
 };
-
 constexpr int FILTER_WARPS = 8;
 // order-preserving float <-> int maps (for the integer warp reductions): a < b  <=>  ord(a) < ord(b) for non-NaN floats
 __device__ __forceinline__ int float_to_ord(float f) { const int i = __float_as_int(f); return i ^ ((i >> 31) & 0x7fffffff); }
 __device__ __forceinline__ float ord_to_float(int i) { return __int_as_float(i ^ ((i >> 31) & 0x7fffffff)); }
-// One WARP per staging block (4 x 32 triangles): the block's 4608 / 10752 bytes are read with coalesced float4 loads
-// into the warp's shared-memory tile. Every warp owns a contiguous run of staging blocks and reserves list space once
-// per 16 of them (lane d keeps the hit mask of destination d), so the list cursors see a fraction of the atomics a
-// per-block append would issue (same-address atomics were the bottleneck of the first version).
-template <int FPT>
+// One WARP per 32-triangle unit, one triangle per lane (nine direct loads of the lane's vertices: a unit is 1152 / 2688
+// contiguous bytes, every line is used by the warp), several units in flight. One test per UNIT and destination instead of
+// one per triangle: the unit's bounding box (six warp reductions) against the destination box, lane d testing destination
+// d. A superset of the union of the per-triangle tests (per axis it is exactly their union), which is all the list needs:
+// the voxelizer on the destination applies the exact per-partition rule to every triangle. Units with a NaN or an
+// absurdly large coordinate (float -> int conversion no longer monotone) go to every destination. Every warp owns a
+// contiguous run of units and reserves list space once per 64 of them (lane d keeps the hit mask of destination d), so the
+// list cursors see a fraction of the atomics a per-unit append would issue.
 __global__ void __launch_bounds__(FILTER_WARPS * 32) k_slice_filter(SliceJob S) {
-    extern __shared__ float4 s_f4[];
+    __shared__ int s_last;
+    // (The wait for the peers to have finished reading the previous job's lists stays a ONE-block kernel in front of this
+    // one, k_slice_wait: a whole grid that spins for a peer can fill the GPU, and with several contexts per device -- two
+    // steps in flight, or all ranks of a test on one GPU -- the kernel it is waiting for might never get an SM.)
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    constexpr uint32_t fpt = FPT;
-    float4* tile4 = s_f4 + (size_t)wid * (VOX_BLOCK * fpt / 4);
-    const float* tile = reinterpret_cast<const float*>(tile4);
+    const uint32_t fpt = S.D.fpt;
+    const unsigned long long n = S.D.n_local;
+    const unsigned long long n_units = (n + UNIT - 1) / UNIT;
     const unsigned long long nwarps = (unsigned long long)gridDim.x * FILTER_WARPS;
-    const unsigned long long per = (S.D.nb + nwarps - 1) / nwarps;
+    const unsigned long long per = (n_units + nwarps - 1) / nwarps;
     const unsigned long long gw = (unsigned long long)blockIdx.x * FILTER_WARPS + wid;
-    const unsigned long long b1 = min(S.D.nb, (gw + 1) * per);
-    constexpr int PER_LANE = VOX_BLOCK * FPT / 4 / 32;          // float4 loads per lane and staging block: 9 or 21
-    static_assert(VOX_BLOCK == 128 && UNIT == 32, "a staging block is four 32-triangle units");
+    const unsigned long long u1 = min(n_units, (gw + 1) * per);
     // lane d tests destination d: its box, once, in registers
     const int dd = lane < S.D.world ? lane : 0;
     float d_lof[3], d_hif[3];
     int d_lo[3], d_hi[3];
 #pragma unroll
     for (int a = 0; a < 3; a++) { d_lof[a] = S.D.lof[dd][a]; d_hif[a] = S.D.hif[dd][a]; d_lo[a] = S.D.lo[dd][a]; d_hi[a] = S.D.hi[dd][a]; }
-    for (unsigned long long base = gw * per; base < b1; base += 16) {
-        unsigned long long hits = 0;                            // lane d: nibble j = warps of block base + j that touch destination d
-        const int nj = (int)min(16ULL, b1 - base);
+    for (unsigned long long base = gw * per; base < u1; base += 64) {
+        unsigned long long hits = 0;                            // lane d: bit j = unit base + j touches destination d
+        const int nj = (int)min(64ULL, u1 - base);
+#pragma unroll 4
         for (int j = 0; j < nj; j++) {
-            const unsigned long long q0 = (base + j) * VOX_BLOCK;
-            const unsigned nrec = (unsigned)(S.D.n_local - q0 < VOX_BLOCK ? S.D.n_local - q0 : VOX_BLOCK);
-            const float4* src4 = reinterpret_cast<const float4*>(S.D.tris + q0 * fpt);   // the slice buffer is padded to whole blocks
-            {   // all loads of the block in flight before the first store (a rolled loop would serialise nine DRAM latencies)
-                float4 r[PER_LANE];
+            const unsigned long long t = (base + j) * UNIT + lane;
+            float mn[3], mx[3];
+            bool odd = false;
+            if (t < n) {
+                const float* c = S.D.tris + t * fpt;
+                float v[9];
 #pragma unroll
-                for (int i = 0; i < PER_LANE; i++) r[i] = __ldg(src4 + lane + 32 * i);
-#pragma unroll
-                for (int i = 0; i < PER_LANE; i++) tile4[lane + 32 * i] = r[i];
-            }
-            __syncwarp();
-#pragma unroll
-            for (int k = 0; k < 4; k++) {                       // triangles 32k .. 32k + 31 are unit k of the block
-                // One test per UNIT and destination instead of one per triangle: the unit's bounding box (six warp
-                // reductions) against the destination box, lane d testing destination d. A superset of the union of the
-                // per-triangle tests (per axis it is exactly their union), which is all the list needs: the voxelizer on
-                // the destination applies the exact per-partition rule to every triangle. Units with a NaN or an
-                // absurdly large coordinate (float -> int conversion no longer monotone) go to every destination.
-                const unsigned t = lane + 32u * k;
-                float mn[3], mx[3];
-                bool odd = false;
-                if (t < nrec) {
-                    const float* c = tile + (size_t)t * fpt;
-#pragma unroll
-                    for (int a = 0; a < 3; a++) {
-                        mn[a] = stdmin(c[a], stdmin(c[3 + a], c[6 + a])); mx[a] = stdmax(c[a], stdmax(c[3 + a], c[6 + a]));
-                        odd = odd || !(fabsf(fmul(mn[a], S.D.unit_div)) < 1.0e9f) || !(fabsf(fmul(mx[a], S.D.unit_div)) < 1.0e9f);   // NaN compares false
-                    }
-                } else {
-#pragma unroll
-                    for (int a = 0; a < 3; a++) { mn[a] = __int_as_float(0x7f800000); mx[a] = __int_as_float(0xff800000); }
-                }
-                const bool any_odd = __any_sync(0xffffffffu, odd);
-                const bool any_tri = __any_sync(0xffffffffu, t < nrec);
-                bool touch = true;
+                for (int i = 0; i < 9; i++) v[i] = __ldg(c + i);
 #pragma unroll
                 for (int a = 0; a < 3; a++) {
-                    const float umn = ord_to_float(__reduce_min_sync(0xffffffffu, float_to_ord(mn[a])));
-                    const float umx = ord_to_float(__reduce_max_sync(0xffffffffu, float_to_ord(mx[a])));
-                    if (lane < S.D.world) {
-                        if (S.D.use_partitions) {
-                            touch = touch && !(umx < d_lof[a]) && !(umn > d_hif[a]);
-                        } else {
-                            const int l = clampi(f2i(fmul(umn, S.D.unit_div)), 0, S.D.gmax), h = clampi(f2i(fmul(umx, S.D.unit_div)), 0, S.D.gmax);
-                            touch = touch && !(h < d_lo[a] || l > d_hi[a]);
-                        }
+                    mn[a] = stdmin(v[a], stdmin(v[3 + a], v[6 + a])); mx[a] = stdmax(v[a], stdmax(v[3 + a], v[6 + a]));
+                    odd = odd || !(fabsf(fmul(mn[a], S.D.unit_div)) < 1.0e9f) || !(fabsf(fmul(mx[a], S.D.unit_div)) < 1.0e9f);   // NaN compares false
+                }
+            } else {
+#pragma unroll
+                for (int a = 0; a < 3; a++) { mn[a] = __int_as_float(0x7f800000); mx[a] = __int_as_float(0xff800000); }
+            }
+            const bool any_odd = __any_sync(0xffffffffu, odd);
+            bool touch = true;
+#pragma unroll
+            for (int a = 0; a < 3; a++) {
+                const float umn = ord_to_float(__reduce_min_sync(0xffffffffu, float_to_ord(mn[a])));
+                const float umx = ord_to_float(__reduce_max_sync(0xffffffffu, float_to_ord(mx[a])));
+                if (lane < S.D.world) {
+                    if (S.D.use_partitions) {
+                        touch = touch && !(umx < d_lof[a]) && !(umn > d_hif[a]);
+                    } else {
+                        const int l = clampi(f2i(fmul(umn, S.D.unit_div)), 0, S.D.gmax), h = clampi(f2i(fmul(umx, S.D.unit_div)), 0, S.D.gmax);
+                        touch = touch && !(h < d_lo[a] || l > d_hi[a]);
                     }
                 }
-                if (lane < S.D.world && any_tri && (touch || any_odd)) hits |= 1ULL << (4 * j + k);
             }
-            __syncwarp();
+            if (lane < S.D.world && (touch || any_odd)) hits |= 1ULL << j;      // (a unit of the run holds at least one triangle)
         }
         if (lane < S.D.world && hits) {
             unsigned long long pos = atomicAdd(&S.cursor[lane], (unsigned long long)__popcll(hits));
             uint32_t* out = S.list[lane] + (unsigned long long)S.D.me * S.cap;
-            for (int j = 0; j < 16; j++) {
-                const uint32_t w = (uint32_t)((hits >> (4 * j)) & 15ULL);
-                for (uint32_t k = 0; k < 4; k++)
-                    if ((w >> k) & 1u) out[pos++] = (uint32_t)((base + j) * 4 + k);      // 32-triangle unit index; pos < 4 * nb <= cap
+            while (hits) {
+                const int j = __ffsll((long long)hits) - 1;
+                hits &= hits - 1;
+                out[pos++] = (uint32_t)(base + j);              // 32-triangle unit index; pos < n_units <= cap
             }
         }
+    }
+    // the block that finishes last publishes: counts + slice size to every peer, then flag 0 behind a system-scope fence
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(&S.cursor[MAX_WORLD], 1ULL) == (unsigned long long)gridDim.x - 1ULL;
+    __syncthreads();
+    if (s_last) {
+        __threadfence_system();
+        const int p = threadIdx.x;
+        if (p < S.D.world) {
+            *(volatile unsigned long long*)&S.ctrl[p]->count[S.D.me][p] = *(volatile unsigned long long*)&S.cursor[p];
+            *(volatile unsigned long long*)&S.ctrl[p]->nslice[S.D.me] = S.D.n_local;
+            S.cursor[p] = 0ULL;
+            __threadfence_system();
+            *(volatile unsigned long long*)&S.ctrl[p]->flag[0][S.D.me] = S.D.epoch;
+        }
+        if (threadIdx.x == 0) S.cursor[MAX_WORLD] = 0ULL;
     }
 }
 

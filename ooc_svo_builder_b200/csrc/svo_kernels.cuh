@@ -87,6 +87,7 @@ struct VoxJob {
     unsigned long long pull_cap;
     const unsigned long long* pull_counts;
     int pull_first;                       // this rank walks the sources in the order pull_first, pull_first + 1, ... (mod n)
+
     // sharding: level-0 word range owned by this context and the voxel bounding box of its slab.
     // lvl[] / tileidx are biased so that they are indexed with GLOBAL word indices.
     unsigned long long w_lo, w_hi;
