@@ -1714,7 +1714,9 @@ static int fast_phase_a(svo_ctx* c, ull* table, bool fill_table, bool force_sync
     CK(cudaMemsetAsync(dinfo, 0, sizeof(BuildInfo), c->stream));
     auto dense_pass = [&](int count_only) -> int {
         for (int j = 1; j <= jB; j++) {
-            const ull nt = (c->nwords[j] + DS_TILE - 1) / DS_TILE;
+            const bool big = c->nwords[j] > (4ULL << 20);                     // > 32 MiB of words: four sub-tiles per block
+            const ull tile_words = (ull)DS_THREADS * DS_ITEMS * (big ? 4 : 1);
+            const ull nt = (c->nwords[j] + tile_words - 1) / tile_words;
             int rc = lookback_prepare(c, nt);
             if (rc) return rc;
             DenseScanJob Dj;
@@ -1725,7 +1727,8 @@ static int fast_phase_a(svo_ctx* c, ull* table, bool fill_table, bool force_sync
             Dj.cap = c->fcap[j]; Dj.cap_child = c->fcap[j - 1];
             Dj.j = j; Dj.count_only = count_only; Dj.info = dinfo;
             Dj.state = c->lb_state.as<ull>(); Dj.ticket = c->lb_ticket.as<ull>(); Dj.ticket_base = c->lb_tickets; Dj.epoch = c->lb_epoch;
-            k_dense_scan<<<(unsigned)nt, DS_THREADS, 0, c->stream>>>(Dj); LAUNCHED();
+            if (big) { k_dense_scan<4><<<(unsigned)nt, DS_THREADS, 0, c->stream>>>(Dj); LAUNCHED(); }
+            else { k_dense_scan<1><<<(unsigned)nt, DS_THREADS, 0, c->stream>>>(Dj); LAUNCHED(); }
             c->lb_tickets += nt;
         }
         if (count_only && jB < J) {
@@ -1843,7 +1846,8 @@ static int fast_phase_b(svo_ctx* c, ull* table) {
     E.is_top = 0; E.root_here = 0;
     mark(c, EV_EL0);
     if (launch_n(0)) {
-        const unsigned grid = blocks_for(launch_n(0), WARPS_PER_BLOCK * EMIT_TILES_PER_WARP);
+        // persistent warps: at most the resident set (5 blocks of 256 threads per SM at 46 registers)
+        const unsigned grid = (unsigned)std::min<ull>(blocks_for(launch_n(0), WARPS_PER_BLOCK * EMIT_TILES_PER_WARP), (ull)c->sm_count * 5);
         if (payload) { k_emit_leaf<true><<<grid, WARPS_PER_BLOCK * 32, 0, c->stream>>>(fast_view(c, 0), E); LAUNCHED(); }
         else { k_emit_leaf<false><<<grid, WARPS_PER_BLOCK * 32, 0, c->stream>>>(fast_view(c, 0), E); LAUNCHED(); }
     }

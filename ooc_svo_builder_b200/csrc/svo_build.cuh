@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(256) k_pyramid_up(const unsigned long long* sr
 // ---------------------------------------------------------------------------
 // k_dense_scan
 // ---------------------------------------------------------------------------
-constexpr int DS_THREADS = 256, DS_ITEMS = 8, DS_TILE = DS_THREADS * DS_ITEMS;
+constexpr int DS_THREADS = 256, DS_ITEMS = 8;              // a thread reads 8 consecutive words (64 bytes) per sub-tile
 constexpr unsigned long long SMALL_LEVEL_WORDS = 4096;     // dense levels up to this size are walked by k_small_levels
 
 struct DenseScanJob {
@@ -49,50 +49,78 @@ struct DenseScanJob {
     unsigned long long* state; unsigned long long* ticket; unsigned long long ticket_base, epoch;
 };
 
+// K sub-tiles of 2048 words per block (K = 1 for small levels, 4 for the 10^8-word levels of the big grids: the look-back
+// costs a block a fixed latency, so a block must bring enough bytes along -- at K = 1 the 1 GiB level 1 of an 8192^3 grid
+// was scanned at 1 TB/s). Sweep 1 keeps only counts and one "non-zero" bit per word (the levels are > 99 % zeros); after the
+// look-back, sweep 2 reads the few non-zero words again (L1 / L2 hits) and writes the list.
+template <int K>
 __global__ void __launch_bounds__(DS_THREADS) k_dense_scan(DenseScanJob Dj) {
+    constexpr unsigned long long TILE = (unsigned long long)DS_THREADS * DS_ITEMS * K;
     __shared__ unsigned long long s_tile, s_prefix[2];
     if (threadIdx.x == 0) s_tile = atomicAdd(Dj.ticket, 1ULL) - Dj.ticket_base;
     __syncthreads();
     const unsigned long long tile = s_tile;
-    if (tile * DS_TILE >= Dj.n || build_aborted(Dj.info)) return;
-    const unsigned long long base = tile * DS_TILE + (unsigned long long)threadIdx.x * DS_ITEMS;
-    unsigned long long w[DS_ITEMS];
-    if (base + DS_ITEMS <= Dj.n) {
-        const ulonglong2* p = reinterpret_cast<const ulonglong2*>(Dj.dense + base);      // base is a multiple of 8 words
+    if (tile * TILE >= Dj.n || build_aborted(Dj.info)) return;
+    // chunk-major: sub-tile k is 2048 consecutive words, thread t owns its words [8 t, 8 t + 8) (64 bytes; a warp reads 2 KB
+    // per sub-tile). Element order of the scan = (sub-tile, thread, word).
+    const unsigned long long tile0 = tile * TILE;
+    unsigned nzbits = 0;
+    unsigned long long ex[K], run_before[K];
+    unsigned long long run = 0;
 #pragma unroll
-        for (int i = 0; i < DS_ITEMS / 2; i++) { const ulonglong2 v = __ldcg(p + i); w[2 * i] = v.x; w[2 * i + 1] = v.y; }
-    } else {
+    for (int k = 0; k < K; k++) {
+        const unsigned long long b0 = tile0 + (unsigned long long)k * (DS_THREADS * DS_ITEMS) + (unsigned long long)threadIdx.x * DS_ITEMS;
+        unsigned long long w[DS_ITEMS];
+        if (b0 + DS_ITEMS <= Dj.n) {
+            const ulonglong2* p = reinterpret_cast<const ulonglong2*>(Dj.dense + b0);      // b0 is a multiple of 8 words
 #pragma unroll
-        for (int i = 0; i < DS_ITEMS; i++) w[i] = base + i < Dj.n ? __ldcg(Dj.dense + base + i) : 0ULL;
+            for (int i = 0; i < DS_ITEMS / 2; i++) { const ulonglong2 v = __ldg(p + i); w[2 * i] = v.x; w[2 * i + 1] = v.y; }
+        } else {
+#pragma unroll
+            for (int i = 0; i < DS_ITEMS; i++) w[i] = b0 + i < Dj.n ? __ldg(Dj.dense + b0 + i) : 0ULL;
+        }
+        unsigned nz = 0, pc = 0;
+#pragma unroll
+        for (int i = 0; i < DS_ITEMS; i++) {
+            if (w[i] != 0ULL) { nzbits |= 1u << (k * DS_ITEMS + i); nz++; pc += (unsigned)__popcll(w[i]); }
+        }
+        unsigned long long total;
+        ex[k] = block_excl_scan(((unsigned long long)pc << 16) | nz, total);    // nz <= 2048 per sub-tile
+        run_before[k] = run;
+        run += total;                                                            // (counts of different sub-tiles add without carry: 4 * 2048 < 65536)
     }
-    unsigned nz = 0, pc = 0;
-#pragma unroll
-    for (int i = 0; i < DS_ITEMS; i++) { nz += w[i] != 0ULL ? 1u : 0u; pc += (unsigned)__popcll(w[i]); }
-    unsigned long long total;
-    const unsigned long long ex = block_excl_scan(((unsigned long long)pc << 16) | nz, total);    // nz <= 2048 per block
     if (threadIdx.x < 32) {
-        const unsigned long long tot[2] = { total & 0xffffULL, total >> 16 };
+        const unsigned long long tot[2] = { run & 0xffffULL, run >> 16 };
         unsigned long long pre[2];
         lookback<2>(Dj.state, Dj.epoch, tile, tot, pre, &Dj.info->overflow);
         if (threadIdx.x == 0) { s_prefix[0] = pre[0]; s_prefix[1] = pre[1]; }
     }
     __syncthreads();
-    unsigned long long at = s_prefix[0] + (ex & 0xffffULL), cp = s_prefix[1] + (ex >> 16);
     unsigned long long up_word = ~0ULL, up_bits = 0ULL;
 #pragma unroll
-    for (int i = 0; i < DS_ITEMS; i++) {
-        if (w[i] == 0ULL) continue;
-        const unsigned long long g = Dj.bias + base + i;
-        if (!Dj.count_only && at < Dj.cap) { Dj.key[at] = g; Dj.mask[at] = w[i]; Dj.fc[at] = cp; }
-        at++;
-        cp += (unsigned)__popcll(w[i]);
-        if (Dj.next) {
-            if ((g >> 6) != up_word) { if (up_bits) red_or(Dj.next + up_word, up_bits); up_word = g >> 6; up_bits = 0ULL; }
-            up_bits |= 1ULL << (g & 63);
+    for (int k = 0; k < K; k++) {
+        unsigned bits = (nzbits >> (k * DS_ITEMS)) & 0xffu;
+        if (!bits) continue;
+        const unsigned long long b0 = tile0 + (unsigned long long)k * (DS_THREADS * DS_ITEMS) + (unsigned long long)threadIdx.x * DS_ITEMS;
+        const unsigned long long pk = run_before[k] + ex[k];
+        unsigned long long at = s_prefix[0] + (pk & 0xffffULL), cp = s_prefix[1] + (pk >> 16);
+        while (bits) {
+            const int i = __ffs(bits) - 1;
+            bits &= bits - 1;
+            const unsigned long long w = __ldg(Dj.dense + b0 + i);
+            const unsigned long long g = Dj.bias + b0 + i;
+            if (!Dj.count_only && at < Dj.cap) { Dj.key[at] = g; Dj.mask[at] = w; Dj.fc[at] = cp; }
+            at++;
+            cp += (unsigned)__popcll(w);
+            if (Dj.next) {
+                if ((g >> 6) != up_word) { if (up_bits) red_or(Dj.next + up_word, up_bits); up_word = g >> 6; up_bits = 0ULL; }
+                up_bits |= 1ULL << (g & 63);
+            }
         }
     }
     if (up_bits) red_or(Dj.next + up_word, up_bits);
-    if (threadIdx.x == 0 && (tile + 1) * DS_TILE >= Dj.n) {       // the last tile: totals
+    const unsigned long long total = run;
+    if (threadIdx.x == 0 && (tile + 1) * TILE >= Dj.n) {       // the last tile: totals
         const unsigned long long n_tiles = s_prefix[0] + (total & 0xffffULL), n_children = s_prefix[1] + (total >> 16);
         Dj.info->count[Dj.j] = n_tiles;
         if (Dj.j == 1) Dj.info->count[0] = n_children;
@@ -175,12 +203,14 @@ __device__ __forceinline__ void brick_pair(const unsigned long long* dense0, uns
         v[h] = leaves | ((leaves + (unsigned)__popc(nonzero_bytes(m[h]))) << 16);
     }
 }
-// Two sweeps over the block's tiles: totals first (nothing is kept in registers, so that several blocks fit an SM and
-// the whole look-back chain runs in one wave), then -- with the block's prefix known -- the bricks are gathered again
-// (L1 / L2 hits) and written.
+// Two sweeps over the block's tiles: totals first, then -- with the block's prefix known -- the bricks are written. The
+// Morton-converted brick words wait in shared memory in between (16 KB per block), not in registers: several blocks fit an
+// SM, the whole look-back chain runs in one wave, and dense level 0 (64 GiB at 8192^3: every gather is a DRAM sector)
+// is read exactly once.
 __global__ void __launch_bounds__(BP_WARPS * 32) k_brick_pass(BrickJob B) {
     __shared__ unsigned long long s_tile, s_prefix[3];
     __shared__ unsigned s_tot[BP_TILE][3], s_ex[BP_TILE][3];
+    __shared__ unsigned long long s_m[BP_TILE][64];
     if (threadIdx.x == 0) s_tile = atomicAdd(B.ticket, 1ULL) - B.ticket_base;
     __syncthreads();
     if (build_aborted(B.info)) return;
@@ -201,6 +231,7 @@ __global__ void __launch_bounds__(BP_WARPS * 32) k_brick_pass(BrickJob B) {
         const unsigned long long W1 = __shfl_sync(0xffffffffu, myW1, q), K1 = __shfl_sync(0xffffffffu, myK1, q);
         unsigned long long m[2]; unsigned v[2];
         brick_pair(B.dense0, W1, K1, lane, m, v);
+        s_m[wid * BP_PER_WARP + q][lane] = m[0]; s_m[wid * BP_PER_WARP + q][lane + 32] = m[1];
         unsigned tot = v[0] + v[1];                    // leaves <= 4096, sizes <= 4608 per tile: no carry between the halves
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, d);
@@ -245,7 +276,12 @@ __global__ void __launch_bounds__(BP_WARPS * 32) k_brick_pass(BrickJob B) {
         const unsigned long long W1 = __shfl_sync(0xffffffffu, myW1, q), K1 = __shfl_sync(0xffffffffu, myK1, q), F1 = __shfl_sync(0xffffffffu, myF1, q);
         if (W1 == 0ULL) continue;                          // (warp-uniform) beyond the list
         unsigned long long m[2]; unsigned v[2];
-        brick_pair(B.dense0, W1, K1, lane, m, v);
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            m[h] = s_m[wid * BP_PER_WARP + q][lane + 32 * h];
+            const unsigned leaves = (unsigned)__popcll(m[h]);
+            v[h] = leaves | ((leaves + (unsigned)__popc(nonzero_bytes(m[h]))) << 16);
+        }
         unsigned i0 = v[0], i1 = v[1];                     // exclusive prefix over the 64 children in bit order (bits 0..31 = half 0)
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
