@@ -69,6 +69,7 @@ struct svo_ctx {
     Timeline tl;
     int device = 0;
     int sm_count = 148;
+    int res_emit_leaf[2] = {4, 4}, res_emit_upper = 4;      // resident blocks per SM of the persistent emitters (occupancy API)
     cudaStream_t stream = nullptr;
     cudaStream_t own_stream = nullptr;
     std::string err;
@@ -120,6 +121,7 @@ struct svo_ctx {
     // device-driven build (svo_build.cuh): counts live in a device-resident BuildInfo; list capacities are remembered
     // from the previous build so that a steady-state build needs no host read-back before the final one
     DevBuf info_buf, merge_scratch, merge_rpos, merge_rrec;
+    DevBuf brick_lp, brick_sp;                 // per level-1 tile: leaf / brick-record prefixes (brick pass)
     BuildInfo* h_info = nullptr;       // pinned copy
     bool fast = false, spec = false, fast_caps_ok = false;
     int jB = 1;                        // levels 1..jB are scanned by k_dense_scan, jB+1..J by k_small_levels
@@ -262,7 +264,7 @@ int exscan(svo_ctx* c, F f, ull n, ull* out, const ull* np = nullptr, BuildInfo*
     int rc = lookback_prepare(c, nt);
     if (rc) return rc;
     OneValue<F> g{ f };
-    k_scan_lookback<1><<<(unsigned)nt, LB_THREADS, 0, c->stream>>>(g, n, np, out, (ull*)nullptr, c->lb_state.as<ull>(), c->lb_ticket.as<ull>(), c->lb_tickets, c->lb_epoch, info); LAUNCHED();
+    k_scan_lookback<1><<<(unsigned)nt, LB_THREADS, 0, c->stream>>>(g, n, np, out, (ull*)nullptr, (ull*)nullptr, c->lb_state.as<ull>(), c->lb_ticket.as<ull>(), c->lb_tickets, c->lb_epoch, info); LAUNCHED();
     c->lb_tickets += nt;
     return SVO_OK;
 }
@@ -278,7 +280,7 @@ int exscan_level0(svo_ctx* c, const ull* mask, ull n, ull* fc, ull* ps) {
     int rc = lookback_prepare(c, nt);
     if (rc) return rc;
     BrickPrefixes g{ mask };
-    k_scan_lookback<2><<<(unsigned)nt, LB_THREADS, 0, c->stream>>>(g, n, (const ull*)nullptr, fc, ps, c->lb_state.as<ull>(), c->lb_ticket.as<ull>(), c->lb_tickets, c->lb_epoch, (BuildInfo*)nullptr); LAUNCHED();
+    k_scan_lookback<2><<<(unsigned)nt, LB_THREADS, 0, c->stream>>>(g, n, (const ull*)nullptr, fc, ps, (ull*)nullptr, c->lb_state.as<ull>(), c->lb_ticket.as<ull>(), c->lb_tickets, c->lb_epoch, (BuildInfo*)nullptr); LAUNCHED();
     c->lb_tickets += nt;
     return SVO_OK;
 }
@@ -486,6 +488,12 @@ int svo_ctx_create(int device, svo_ctx** out) {
     svo_ctx* n = new svo_ctx();
     n->device = device;
     n->sm_count = prop.multiProcessorCount;
+    {
+        int r = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r, k_emit_leaf<false, 5>, WARPS_PER_BLOCK * 32, 0) == cudaSuccess && r > 0) n->res_emit_leaf[0] = r;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r, k_emit_leaf<true, 5>, WARPS_PER_BLOCK * 32, 0) == cudaSuccess && r > 0) n->res_emit_leaf[1] = r;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r, k_emit_upper_fast, WARPS_PER_BLOCK * 32, 0) == cudaSuccess && r > 0) n->res_emit_upper = r;
+    }
     memset(&n->stats, 0, sizeof n->stats);
     memset(&n->prm, 0, sizeof n->prm);
     memset(n->nwords, 0, sizeof n->nwords);
@@ -533,7 +541,7 @@ void svo_ctx_destroy(svo_ctx* c) {
     for (int i = 0; i < 2; i++) if (c->up_ev[i]) cudaEventDestroy(c->up_ev[i]);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     if (c->h_info) cudaFreeHost(c->h_info);
-    c->info_buf.release(); c->merge_scratch.release(); c->merge_rpos.release(); c->merge_rrec.release();
+    c->info_buf.release(); c->merge_scratch.release(); c->merge_rpos.release(); c->merge_rrec.release(); c->brick_lp.release(); c->brick_sp.release();
     c->d_rpos.release(); c->d_rrec.release(); c->d_dpos.release(); c->d_drec.release(); c->stage_data.release();
     cudaStreamDestroy(c->own_stream);
     delete c;
@@ -1490,8 +1498,8 @@ static int build_phase_b(svo_ctx* c, const ull* table) {
             const Level L0 = (J == 0) ? LJ : c->lv[0].view();
             mark(c, EV_EL0);
             if (levels) { k_emit_leaf_levels<<<blocks_for(L0.n, WARPS_PER_BLOCK), WARPS_PER_BLOCK * 32, 0, c->stream>>>(L0, E); LAUNCHED(); }
-            else if (payload) { k_emit_leaf<true><<<blocks_for(L0.n, WARPS_PER_BLOCK * EMIT_TILES_PER_WARP), WARPS_PER_BLOCK * 32, 0, c->stream>>>(L0, E); LAUNCHED(); }
-            else { k_emit_leaf<false><<<blocks_for(L0.n, WARPS_PER_BLOCK * EMIT_TILES_PER_WARP), WARPS_PER_BLOCK * 32, 0, c->stream>>>(L0, E); LAUNCHED(); }
+            else if (payload) { k_emit_leaf<true, 5><<<blocks_for(L0.n, WARPS_PER_BLOCK * EMIT_TILES_PER_WARP), WARPS_PER_BLOCK * 32, 0, c->stream>>>(L0, E); LAUNCHED(); }
+            else { k_emit_leaf<false, 5><<<blocks_for(L0.n, WARPS_PER_BLOCK * EMIT_TILES_PER_WARP), WARPS_PER_BLOCK * 32, 0, c->stream>>>(L0, E); LAUNCHED(); }
             mark(c, EV_EL1);
         }
     }
@@ -1764,17 +1772,23 @@ static int fast_phase_a(svo_ctx* c, ull* table, bool fill_table, bool force_sync
     if (rc) return rc;
     {   // bricks: lists, leaf ranks, subtree sizes of levels 0 and 1
         const ull n1 = spec ? std::min<ull>(c->fcap[1], c->nwords[1]) : c->h_info->count[1];
-        const ull nt = std::max<ull>((n1 + BP_TILE - 1) / BP_TILE, 1);
-        if ((rc = lookback_prepare(c, nt))) return rc;
+        CK(c->brick_lp.ensure((size_t)(c->fcap[1] + 2) * sizeof(ull)));
+        CK(c->brick_sp.ensure((size_t)(c->fcap[1] + 2) * sizeof(ull)));
         BrickJob B;
         memset(&B, 0, sizeof B);
         B.L1 = fast_view(c, 1); B.L0 = fast_view(c, 0);
         B.dense0 = c->dense[0].as<ull>() - c->bias[0];
         B.tileidx = payload ? c->tileidx.as<uint32_t>() - c->bias[0] : nullptr;
+        B.tile_lp = c->brick_lp.as<ull>(); B.tile_sp = c->brick_sp.as<ull>();
         B.info = dinfo;
-        B.state = c->lb_state.as<ull>(); B.ticket = c->lb_ticket.as<ull>(); B.ticket_base = c->lb_tickets; B.epoch = c->lb_epoch;
-        k_brick_pass<<<(unsigned)nt, BP_WARPS * 32, 0, c->stream>>>(B); LAUNCHED();
+        if (n1) { k_brick_gather<<<blocks_for(n1, BP_TILE), BP_WARPS * 32, 0, c->stream>>>(B); LAUNCHED(); }
+        const ull nt = std::max<ull>((n1 + LB_TILE - 1) / LB_TILE, 1);
+        if ((rc = lookback_prepare(c, nt))) return rc;
+        BrickTileTotals g{ B.tile_lp, c->lv[1].mask.as<ull>() };
+        k_scan_lookback<3><<<(unsigned)nt, LB_THREADS, 0, c->stream>>>(g, n1, &dinfo->count[1], B.tile_lp, B.tile_sp, c->lv[1].ps.as<ull>(),
+                                                                      c->lb_state.as<ull>(), c->lb_ticket.as<ull>(), c->lb_tickets, c->lb_epoch, dinfo); LAUNCHED();
         c->lb_tickets += nt;
+        k_brick_prefix<<<std::max(blocks_for(n1, BP_WARPS * 32), 1u), BP_WARPS * 32, 0, c->stream>>>(B); LAUNCHED();
     }
     // subtree sizes of the big levels above: look-back scans (the small levels follow in k_top)
     for (int j = 2; j <= jB; j++) {
@@ -1841,15 +1855,37 @@ static int fast_phase_b(svo_ctx* c, ull* table) {
         if (!n) continue;
         E.is_top = (j == top);
         E.root_here = (j == J) && root_level_here;
-        k_emit_upper<<<blocks_for(n, WARPS_PER_BLOCK), WARPS_PER_BLOCK * 32, 0, c->stream>>>(fast_view(c, j), fast_view(c, j - 1), E); LAUNCHED();
+        // persistent warps over batches of bs tiles: full batches once the level has more tiles than the GPU holds warps
+        const ull resident = (ull)c->sm_count * c->res_emit_upper;
+        int bs = 32;
+        while (bs > 1 && n / bs < resident * WARPS_PER_BLOCK) bs >>= 1;
+        const unsigned grid = (unsigned)std::min<ull>(blocks_for(blocks_for(n, bs), WARPS_PER_BLOCK), resident);
+        k_emit_upper_fast<<<grid, WARPS_PER_BLOCK * 32, 0, c->stream>>>(fast_view(c, j), fast_view(c, j - 1), E, bs); LAUNCHED();
     }
     E.is_top = 0; E.root_here = 0;
     mark(c, EV_EL0);
     if (launch_n(0)) {
-        // persistent warps: at most the resident set (5 blocks of 256 threads per SM at 46 registers)
-        const unsigned grid = (unsigned)std::min<ull>(blocks_for(launch_n(0), WARPS_PER_BLOCK * EMIT_TILES_PER_WARP), (ull)c->sm_count * 5);
-        if (payload) { k_emit_leaf<true><<<grid, WARPS_PER_BLOCK * 32, 0, c->stream>>>(fast_view(c, 0), E); LAUNCHED(); }
-        else { k_emit_leaf<false><<<grid, WARPS_PER_BLOCK * 32, 0, c->stream>>>(fast_view(c, 0), E); LAUNCHED(); }
+        // persistent warps: at most the resident set (a sixth block per SM would run alone after the others finished)
+        const unsigned grid = (unsigned)std::min<ull>(blocks_for(launch_n(0), WARPS_PER_BLOCK * EMIT_TILES_PER_WARP), (ull)c->sm_count * c->res_emit_leaf[payload ? 1 : 0]);
+        static const int var = getenv("SVO_LEAF_VARIANT") ? atoi(getenv("SVO_LEAF_VARIANT")) : 0;
+        const Level L0 = fast_view(c, 0);
+        const ull need = blocks_for(launch_n(0), WARPS_PER_BLOCK * EMIT_TILES_PER_WARP);
+#define LEAF_VARIANT(MINB, PER_SM) { \
+            int r = 4; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r, k_emit_leaf<false, MINB>, WARPS_PER_BLOCK * 32, 0); \
+            if (PER_SM < r) r = PER_SM; \
+            const unsigned gr = (unsigned)std::min<ull>(need, (ull)c->sm_count * r); \
+            if (payload) k_emit_leaf<true, MINB><<<gr, WARPS_PER_BLOCK * 32, 0, c->stream>>>(L0, E); \
+            else k_emit_leaf<false, MINB><<<gr, WARPS_PER_BLOCK * 32, 0, c->stream>>>(L0, E); }
+        (void)grid;
+        switch (var) {
+            case 1: LEAF_VARIANT(4, 4); break;
+            case 2: LEAF_VARIANT(4, 2); break;
+            case 3: LEAF_VARIANT(4, 3); break;
+            case 4: LEAF_VARIANT(6, 6); break;
+            case 5: LEAF_VARIANT(8, 8); break;
+            default: LEAF_VARIANT(5, 5); break;
+        }
+        LAUNCHED();
     }
     mark(c, EV_EL1);
     mark(c, EV_EMIT1);

@@ -9,9 +9,9 @@
 //                   and 1 with fire-and-forget reductions): compacts the non-zero words into the tile list
 //                   (key, mask, child prefix fc), sets the words' bits in dense level j+1, counts tiles and children
 //   k_small_levels  the same for all levels with <= 4096 dense words, in ONE block
-//   k_brick_pass    one warp per level-1 tile: gathers its <= 64 brick words from dense level 0, converts them to the
-//                   Morton layout, and scans (leaves, brick subtree sizes, level-1 subtree sizes) in one look-back
-//                   chain -> brick list (key, mask, leaf rank fc, size prefix ps) and the level-1 size prefix
+//   k_brick_gather / k_scan_lookback<3> / k_brick_prefix   the brick level: gathers the <= 64 brick words of every level-1
+//                   tile from dense level 0 into the brick list (Morton layout), scans (leaves, brick subtree sizes,
+//                   level-1 subtree sizes) over the level-1 tiles, writes leaf ranks fc and size prefixes ps of the bricks
 //   k_shard_merge   the shared upper levels from the exchanged subtree table, in one block: global counts, this
 //                   rank's file range, bases of its top tiles, the upper records inside its range
 //                   (same arithmetic as the host-side svo_shard_layout_from_table)
@@ -180,7 +180,18 @@ __global__ void __launch_bounds__(1024) k_small_levels(SmallLevelsJob S) {
 }
 
 // ---------------------------------------------------------------------------
-// k_brick_pass
+// The brick pass: three launches.
+//   k_brick_gather   one warp per level-1 tile (four tiles per warp, all gathers in flight together): reads the tile's
+//                    <= 64 brick words from dense level 0 (64 GiB at 8192^3: every gather is a DRAM sector, read exactly
+//                    once), converts them to the Morton layout and writes them -- with their keys -- at their final
+//                    positions of the brick list (the level-1 list's child prefix fc gives them: no scan needed);
+//                    leaves and brick-subtree records of the tile go to tile_tot[t]
+//   k_scan_lookback<3, BrickTileTotals>   exclusive prefixes per level-1 tile: leaves, brick records, level-1 subtree
+//                    sizes (L1.ps). 64 times fewer elements than bricks: the look-back chain is a few dozen tiles long
+//   k_brick_prefix   one warp per level-1 tile again: reads its bricks back (coalesced, L2 hits at the sizes that fit) and
+//                    writes their leaf ranks (fc) and size prefixes (ps)
+// An earlier single kernel held all this in one look-back chain over the level-1 tiles; at 8192^3 it spent half of its
+// time at the block barriers around the chain while the DRAM gathers of only one wave of blocks were in flight.
 // ---------------------------------------------------------------------------
 constexpr int BP_WARPS = 8, BP_PER_WARP = 4, BP_TILE = BP_WARPS * BP_PER_WARP;     // level-1 tiles per block
 struct BrickJob {
@@ -188,123 +199,98 @@ struct BrickJob {
     Level L0;                             // key, mask, fc, ps out
     const unsigned long long* dense0;     // pre-biased: indexed with global level-0 word indices
     uint32_t* tileidx;                    // pre-biased dense map word -> compact index (payload owner pass) or NULL
+    unsigned long long* tile_lp;          // n1 + 1: in: leaves | records << 32 per tile (gather); out: leaf prefix (scan)
+    unsigned long long* tile_sp;          // n1 + 1: brick-record prefix per level-1 tile
     BuildInfo* info;
-    unsigned long long* state; unsigned long long* ticket; unsigned long long ticket_base, epoch;
 };
-// this lane's two bricks (bits lane, lane + 32) of level-1 tile (W1, K1): Morton-layout words and leaves | sizes << 16
-__device__ __forceinline__ void brick_pair(const unsigned long long* dense0, unsigned long long W1, unsigned long long K1, int lane,
-                                           unsigned long long (&m)[2], unsigned (&v)[2]) {
-#pragma unroll
-    for (int h = 0; h < 2; h++) {
-        const int bit = lane + 32 * h;
-        m[h] = 0ULL;
-        if ((W1 >> bit) & 1ULL) m[h] = linear_to_morton64(__ldcg(dense0 + ((K1 << 6) | (unsigned long long)bit)));
-        const unsigned leaves = (unsigned)__popcll(m[h]);
-        v[h] = leaves | ((leaves + (unsigned)__popc(nonzero_bytes(m[h]))) << 16);
-    }
-}
-// Two sweeps over the block's tiles: totals first, then -- with the block's prefix known -- the bricks are written. The
-// Morton-converted brick words wait in shared memory in between (16 KB per block), not in registers: several blocks fit an
-// SM, the whole look-back chain runs in one wave, and dense level 0 (64 GiB at 8192^3: every gather is a DRAM sector)
-// is read exactly once.
-__global__ void __launch_bounds__(BP_WARPS * 32) k_brick_pass(BrickJob B) {
-    __shared__ unsigned long long s_tile, s_prefix[3];
-    __shared__ unsigned s_tot[BP_TILE][3], s_ex[BP_TILE][3];
-    __shared__ unsigned long long s_m[BP_TILE][64];
-    if (threadIdx.x == 0) s_tile = atomicAdd(B.ticket, 1ULL) - B.ticket_base;
-    __syncthreads();
+__global__ void __launch_bounds__(BP_WARPS * 32) k_brick_gather(BrickJob B) {
     if (build_aborted(B.info)) return;
-    const unsigned long long tile = s_tile;
     const unsigned long long n1 = level_n(B.L1);
-    if (tile * BP_TILE >= n1) {
-        if (tile == 0 && threadIdx.x == 0) { B.L0.fc[0] = 0ULL; B.L0.ps[0] = 0ULL; B.L1.ps[0] = 0ULL; B.info->n_leaves_local = 0ULL; B.info->n_brick_records = 0ULL; }
-        return;
-    }
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const unsigned long long tw0 = tile * BP_TILE + (unsigned long long)wid * BP_PER_WARP;
+    const unsigned long long tw0 = ((unsigned long long)blockIdx.x * BP_WARPS + wid) * BP_PER_WARP;
+    if (tw0 >= n1) return;
     // lane q of the warp holds the descriptor of the warp's q-th tile
     unsigned long long myW1 = 0ULL, myK1 = 0ULL, myF1 = 0ULL;
     if (lane < BP_PER_WARP && tw0 + lane < n1) { myW1 = B.L1.mask[tw0 + lane]; myK1 = B.L1.key[tw0 + lane]; myF1 = B.L1.fc[tw0 + lane]; }
-    // ---- sweep 1: totals of every tile (fully unrolled: the gathers of all the warp's tiles are in flight together) ----
+    unsigned long long m[BP_PER_WARP][2];
 #pragma unroll
-    for (int q = 0; q < BP_PER_WARP; q++) {
+    for (int q = 0; q < BP_PER_WARP; q++) {                   // all the gathers first
         const unsigned long long W1 = __shfl_sync(0xffffffffu, myW1, q), K1 = __shfl_sync(0xffffffffu, myK1, q);
-        unsigned long long m[2]; unsigned v[2];
-        brick_pair(B.dense0, W1, K1, lane, m, v);
-        s_m[wid * BP_PER_WARP + q][lane] = m[0]; s_m[wid * BP_PER_WARP + q][lane + 32] = m[1];
-        unsigned tot = v[0] + v[1];                    // leaves <= 4096, sizes <= 4608 per tile: no carry between the halves
 #pragma unroll
-        for (int d = 16; d > 0; d >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, d);
-        if (lane == 0) {
-            const int s = wid * BP_PER_WARP + q;
-            s_tot[s][0] = tot & 0xffffu;
-            s_tot[s][1] = tot >> 16;
-            s_tot[s][2] = W1 ? (tot >> 16) + (unsigned)__popcll(W1) + (unsigned)__popc(nonzero_bytes(W1)) : 0u;   // S of the level-1 tile
+        for (int h = 0; h < 2; h++) {
+            const int bit = lane + 32 * h;
+            m[q][h] = 0ULL;
+            if ((W1 >> bit) & 1ULL) m[q][h] = __ldcg(B.dense0 + ((K1 << 6) | (unsigned long long)bit));
         }
     }
-    __syncthreads();
-    if (wid == 0) {
-        // exclusive scan over the block's BP_TILE = 32 tiles (one per lane) and the look-back
-        static_assert(BP_TILE == 32, "one tile per lane of warp 0");
-        unsigned long long tot[3], prefix[3];
-#pragma unroll
-        for (int c = 0; c < 3; c++) {
-            const unsigned x = s_tot[lane][c];
-            unsigned inc = x;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { const unsigned a = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += a; }
-            s_ex[lane][c] = inc - x;
-            tot[c] = __shfl_sync(0xffffffffu, inc, 31);
-        }
-        lookback<3>(B.state, B.epoch, tile, tot, prefix, &B.info->overflow);
-        if (lane == 0) {
-#pragma unroll
-            for (int c = 0; c < 3; c++) s_prefix[c] = prefix[c];
-            if ((tile + 1) * BP_TILE >= n1) {         // the last tile: totals behind the lists
-                const unsigned long long n0 = B.info->count[0];
-                if (n0 <= B.L0.cap) { B.L0.fc[n0] = prefix[0] + tot[0]; B.L0.ps[n0] = prefix[1] + tot[1]; }
-                B.L1.ps[n1] = prefix[2] + tot[2];
-                B.info->n_leaves_local = prefix[0] + tot[0];
-                B.info->n_brick_records = prefix[1] + tot[1];
-            }
-        }
-    }
-    __syncthreads();
-    // ---- sweep 2: the bricks ----
 #pragma unroll
     for (int q = 0; q < BP_PER_WARP; q++) {
         const unsigned long long W1 = __shfl_sync(0xffffffffu, myW1, q), K1 = __shfl_sync(0xffffffffu, myK1, q), F1 = __shfl_sync(0xffffffffu, myF1, q);
-        if (W1 == 0ULL) continue;                          // (warp-uniform) beyond the list
-        unsigned long long m[2]; unsigned v[2];
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-            m[h] = s_m[wid * BP_PER_WARP + q][lane + 32 * h];
-            const unsigned leaves = (unsigned)__popcll(m[h]);
-            v[h] = leaves | ((leaves + (unsigned)__popc(nonzero_bytes(m[h]))) << 16);
-        }
-        unsigned i0 = v[0], i1 = v[1];                     // exclusive prefix over the 64 children in bit order (bits 0..31 = half 0)
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const unsigned a = __shfl_up_sync(0xffffffffu, i0, d), b = __shfl_up_sync(0xffffffffu, i1, d);
-            if (lane >= d) { i0 += a; i1 += b; }
-        }
-        const unsigned t0 = __shfl_sync(0xffffffffu, i0, 31);
-        const unsigned pre[2] = { i0 - v[0], t0 + i1 - v[1] };
-        const int s = wid * BP_PER_WARP + q;
-        const unsigned long long lp = s_prefix[0] + s_ex[s][0], sp = s_prefix[1] + s_ex[s][1];
-        if (lane == 0) B.L1.ps[tw0 + q] = s_prefix[2] + s_ex[s][2];
+        if (W1 == 0ULL) continue;                              // (warp-uniform) beyond the list
+        unsigned tot = 0;
 #pragma unroll
         for (int h = 0; h < 2; h++) {
             const int bit = lane + 32 * h;
             if (!((W1 >> bit) & 1ULL)) continue;
+            const unsigned long long w = linear_to_morton64(m[q][h]);
+            const unsigned leaves = (unsigned)__popcll(w);
+            tot += leaves | ((leaves + (unsigned)__popc(nonzero_bytes(w))) << 16);      // <= 4096 leaves, <= 4608 records per tile: no carry
             const unsigned long long c = F1 + __popcll(W1 & lowmask(bit));
-            if (c >= B.L0.cap) continue;                   // (the overflow flag is already set by the level-1 scan)
+            if (c >= B.L0.cap) continue;                       // (the overflow flag is already set by the level-1 scan)
             const unsigned long long ck = (K1 << 6) | (unsigned long long)bit;
             B.L0.key[c] = ck;
-            B.L0.mask[c] = m[h];
-            B.L0.fc[c] = lp + (pre[h] & 0xffffu);
-            B.L0.ps[c] = sp + (pre[h] >> 16);
+            B.L0.mask[c] = w;
             if (B.tileidx) B.tileidx[ck] = (uint32_t)c;
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, d);
+        if (lane == 0) B.tile_lp[tw0 + q] = (unsigned long long)(tot & 0xffffu) | ((unsigned long long)(tot >> 16) << 32);
+    }
+}
+struct BrickTileTotals {   // per level-1 tile: leaves, brick records, subtree size of the tile
+    const unsigned long long* tot; const unsigned long long* mask1;
+    __device__ void operator()(unsigned long long t, unsigned long long (&e)[3]) const {
+        const unsigned long long v = tot[t], W1 = mask1[t];
+        e[0] = v & 0xffffffffULL; e[1] = v >> 32;
+        e[2] = e[1] + (unsigned long long)(__popcll(W1) + __popc(nonzero_bytes(W1)));
+    }
+};
+// A warp takes 32 consecutive level-1 tiles: their bricks are one contiguous run of the brick list, and the prefixes of
+// the run's first tile seed a plain running sum -- no per-tile logic, all loads and stores coalesced.
+__global__ void __launch_bounds__(BP_WARPS * 32) k_brick_prefix(BrickJob B) {
+    if (build_aborted(B.info)) return;
+    const unsigned long long n1 = level_n(B.L1);
+    const int lane = threadIdx.x & 31;
+    const unsigned long long w = (unsigned long long)blockIdx.x * BP_WARPS + (threadIdx.x >> 5);
+    if (w == 0 && lane == 0) {                                 // totals behind the lists (the scan wrote lp[n1], sp[n1]; both 0 when n1 == 0)
+        const unsigned long long n0 = B.info->count[0], nl = B.tile_lp[n1], ns = B.tile_sp[n1];
+        if (n0 <= B.L0.cap) { B.L0.fc[n0] = nl; B.L0.ps[n0] = ns; }
+        B.info->n_leaves_local = nl;
+        B.info->n_brick_records = ns;
+    }
+    const unsigned long long t0 = w * 32;
+    if (t0 >= n1) return;
+    const unsigned long long t1 = min(t0 + 32, n1);
+    const unsigned long long c0 = B.L1.fc[t0];
+    const unsigned long long c1 = min(B.L1.fc[t1], B.L0.cap);
+    unsigned long long lp = B.tile_lp[t0], sp = B.tile_sp[t0];
+    constexpr int U = 4;                                       // rounds of 32 bricks whose loads are in flight together
+    for (unsigned long long cb = c0; cb < c1; cb += 32 * U) {
+        unsigned long long m[U];
+#pragma unroll
+        for (int k = 0; k < U; k++) { const unsigned long long c = cb + 32 * k + lane; m[k] = c < c1 ? B.L0.mask[c] : 0ULL; }
+#pragma unroll
+        for (int k = 0; k < U; k++) {
+            const unsigned long long c = cb + 32 * k + lane;
+            const unsigned leaves = (unsigned)__popcll(m[k]);
+            const unsigned v = leaves | ((leaves + (unsigned)__popc(nonzero_bytes(m[k]))) << 16);    // 32 bricks: <= 2048 leaves, <= 2304 records
+            unsigned inc = v;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const unsigned a = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += a; }
+            const unsigned ex = inc - v;
+            if (c < c1) { B.L0.fc[c] = lp + (ex & 0xffffu); B.L0.ps[c] = sp + (ex >> 16); }
+            const unsigned all = __shfl_sync(0xffffffffu, inc, 31);
+            lp += all & 0xffffu; sp += all >> 16;
         }
     }
 }

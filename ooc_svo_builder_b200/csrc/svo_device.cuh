@@ -103,6 +103,25 @@ __host__ __device__ __forceinline__ uint64_t child_offsets(uint32_t m) {
     return r;
 }
 
+// The same as a 256-entry table in global memory, built at compile time (one cached 8-byte load instead of ~40
+// instructions; the emitters look it up once per record).
+struct ChildOffsetTable { unsigned long long v[256]; };
+constexpr ChildOffsetTable make_child_offset_table() {
+    ChildOffsetTable t{};
+    for (unsigned m = 0; m < 256; m++) {
+        unsigned long long r = 0;
+        unsigned rank = 0;
+        for (int c = 0; c < 8; c++) {
+            const unsigned long long b = ((m >> c) & 1u) ? (unsigned long long)rank++ : 0xFFULL;
+            r |= b << (8 * c);
+        }
+        t.v[m] = r;
+    }
+    return t;
+}
+__device__ const ChildOffsetTable g_child_offsets = make_child_offset_table();
+__device__ __forceinline__ unsigned long long child_offsets_lut(uint32_t m) { return __ldg(&g_child_offsets.v[m & 0xffu]); }
+
 // ---------------------------------------------------------------------------
 // Schwarz-Seidel conservative test, voxelizer.cpp:206-254 (setup) and :266-287
 // ---------------------------------------------------------------------------

@@ -404,18 +404,29 @@ __global__ void __launch_bounds__(VOX_BLOCK, SVO_VOX_MINBLOCKS) k_vox_warp(VoxJo
     extern __shared__ float4 s_stage4[];
     __shared__ __align__(8) unsigned long long s_bar[VOX_BLOCK / 32][2];
     __shared__ unsigned long long s_base[MAX_WORLD + 1], s_pref[MAX_WORLD + 1];
+    __shared__ int s_order[MAX_WORLD];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const uint32_t unit_floats = UNIT * J.fpt;
     float* wbuf = reinterpret_cast<float*>(s_stage4) + (size_t)wid * 2 * unit_floats;
     unsigned long long count;
     if (MODE == 2) {
-        // Sources are walked in rotated order, starting with this rank's own slice: if every rank began with source 0,
-        // all of them would pull from the same GPU at the same time (its NVLink egress, ~750 GB/s, shared by N readers)
-        // and then move on together; rotated, each source serves about one reader at a time.
+        // Sources are walked in ROTATED order. If every rank began with the same source, all of them would pull from the
+        // same GPU at the same time (its NVLink egress, ~750 GB/s, shared by N readers) and then move on together. The
+        // rotation is taken among the sources that actually listed units for this rank, and it starts at (rank mod their
+        // number): with a lat-long mesh every octant needs the same four latitude bands, and a rotation that started at
+        // the rank's own (unneeded) slice made three ranks begin at the same source -- measured on 8 GPUs: 1.7 ms for
+        // those three against 1.2 ms for the rank that had a source to itself.
         segs_bases(J.segs, s_base);
         if (threadIdx.x == 0) {
+            int ne = 0, idx[MAX_WORLD];
+            for (int r = 0; r < J.segs.n; r++) if (J.pull_counts[(size_t)r * MAX_WORLD] > 0ULL) idx[ne++] = r;
             unsigned long long acc = 0;
-            for (int i = 0; i < J.segs.n; i++) { s_pref[i] = acc; acc += J.pull_counts[(size_t)((J.pull_first + i) % J.segs.n) * MAX_WORLD]; }
+            for (int i = 0; i < J.segs.n; i++) {
+                int r = 0;
+                unsigned long long cnt = 0ULL;
+                if (i < ne) { r = idx[(J.pull_first + i) % ne]; cnt = J.pull_counts[(size_t)r * MAX_WORLD]; }
+                s_order[i] = r; s_pref[i] = acc; acc += cnt;
+            }
             s_pref[J.segs.n] = acc;
         }
         __syncthreads();
@@ -437,7 +448,7 @@ __global__ void __launch_bounds__(VOX_BLOCK, SVO_VOX_MINBLOCKS) k_vox_warp(VoxJo
     auto locate = [&](unsigned long long u) {
         if (MODE == 2) {
             while (u >= s_pref[src + 1]) src++;             // a warp's tickets only grow: src (position in the rotated order) moves forward
-            const int r = (J.pull_first + src) % J.segs.n;  // the source rank
+            const int r = s_order[src];                     // the source rank
             const uint64_t q0 = (uint64_t)J.subset[(size_t)r * J.pull_cap + (u - s_pref[src])] * UNIT;
             const uint64_t nseg = s_base[r + 1] - s_base[r];
             uptr = J.segs.ptr[r] + q0 * J.fpt;
@@ -835,7 +846,7 @@ __device__ __forceinline__ void lookback(unsigned long long* state, unsigned lon
 // or from device memory (np != NULL: the launch grid was sized for `n` = the capacity, the real count is min(*np, n)).
 template <int NV, class F>
 __global__ void __launch_bounds__(LB_THREADS) k_scan_lookback(F f, unsigned long long n, const unsigned long long* np,
-                                                              unsigned long long* out0, unsigned long long* out1,
+                                                              unsigned long long* out0, unsigned long long* out1, unsigned long long* out2,
                                                               unsigned long long* state, unsigned long long* ticket,
                                                               unsigned long long ticket_base, unsigned long long epoch, BuildInfo* info) {
     __shared__ unsigned long long s_tile, s_prefix[NV];
@@ -845,7 +856,7 @@ __global__ void __launch_bounds__(LB_THREADS) k_scan_lookback(F f, unsigned long
     if (np) { const unsigned long long v = *np; n = v < n ? v : n; }
     const unsigned long long tile = s_tile;
     if (tile * LB_TILE >= n) {
-        if (tile == 0 && threadIdx.x == 0) { out0[0] = 0ULL; if (NV > 1) out1[0] = 0ULL; }      // empty input: out[n] = out[0] = 0
+        if (tile == 0 && threadIdx.x == 0) { out0[0] = 0ULL; if (NV > 1) out1[0] = 0ULL; if (NV > 2) out2[0] = 0ULL; }      // empty input: out[n] = out[0] = 0
         return;
     }
     const unsigned long long base = tile * LB_TILE + (unsigned long long)threadIdx.x * LB_ITEMS;
@@ -874,7 +885,7 @@ __global__ void __launch_bounds__(LB_THREADS) k_scan_lookback(F f, unsigned long
     __syncthreads();
 #pragma unroll
     for (int c = 0; c < NV; c++) {
-        unsigned long long* out = c == 0 ? out0 : out1;
+        unsigned long long* out = c == 0 ? out0 : (c == 1 ? out1 : out2);
         unsigned long long run = s_prefix[c] + ex[c];
 #pragma unroll
         for (int i = 0; i < LB_ITEMS; i++) {
@@ -1223,15 +1234,14 @@ __device__ __forceinline__ void emit_upper_tile(const Level& L, const Level& C, 
 }
 // 24-byte node record as 16 + 8 or 8 + 16 bytes, whichever is aligned
 __device__ __forceinline__ void store_record(unsigned long long* o, unsigned long long d0, unsigned long long d1, unsigned long long d2) {
-    if (((uintptr_t)o & 15) == 0) { asm volatile("st.global.v2.u64 [%0], {%1, %2};" :: "l"(o), "l"(d0), "l"(d1) : "memory"); o[2] = d2; }
-    else { o[0] = d0; asm volatile("st.global.v2.u64 [%0], {%1, %2};" :: "l"(o + 1), "l"(d1), "l"(d2) : "memory"); }
+    if (((uintptr_t)o & 15) == 0) { asm volatile("st.global.v2.u64 [%0], {%1, %2};" :: "l"(o), "l"(d0), "l"(d1)); o[2] = d2; }
+    else { o[0] = d0; asm volatile("st.global.v2.u64 [%0], {%1, %2};" :: "l"(o + 1), "l"(d1), "l"(d2)); }
 }
 // The same tile without -levels, trimmed for instruction count (the generic version spends ~400 warp instructions per
 // tile, and the level above the bricks holds 10^6 tiles at 8192^3): everything that only depends on the tile word is
 // computed once per warp -- per-byte child counts and their running sums with one SWAR popcount and one multiply --,
 // child_offsets comes from a shared-memory table, records go out as 16 + 8 byte stores.
-__device__ __forceinline__ void emit_upper_tile_fast(const Level& L, const Level& C, const EmitJob& E, const NodeRange& R, unsigned long long i, int lane,
-                                                     const unsigned long long* s_off) {
+__device__ __forceinline__ void emit_upper_tile_fast(const Level& L, const Level& C, const EmitJob& E, const NodeRange& R, unsigned long long i, int lane) {
     const unsigned long long W = L.mask[i], fc = L.fc[i], base = L.base[i];
     const unsigned long long S = L.ps[i + 1] - L.ps[i];
     if (L.clear && lane == 31) L.clear[L.key[i]] = 0ULL;
@@ -1256,7 +1266,7 @@ __device__ __forceinline__ void emit_upper_tile_fast(const Level& L, const Level
             const unsigned long long gbase = base + (psc - ps0) + before;         // subtree region of grandchild c
             C.base[c] = gbase;
             const unsigned long long pos = base + (pend - ps0) + before + inb;    // its record, in the children block of byte k
-            if (unsigned long long* o = node_slot(E, R, pos)) store_record(o, 0ULL, gbase + (psc1 - psc) - __popc(gnz), s_off[gnz]);
+            if (unsigned long long* o = node_slot(E, R, pos)) store_record(o, 0ULL, gbase + (psc1 - psc) - __popc(gnz), child_offsets_lut(gnz));
         }
     }
     if (lane < 8 && ((nzb >> lane) & 1u)) {
@@ -1265,24 +1275,118 @@ __device__ __forceinline__ void emit_upper_tile_fast(const Level& L, const Level
         const uint32_t through = (uint32_t)(cum >> (8 * k)) & 0xffu, before = through - (uint32_t)__popc(byte);
         const unsigned long long blk = base + (C.ps[fc + through] - ps0) + before;
         const unsigned long long pos = base + S - __popc(nzb) + __popc(nzb & ((1u << k) - 1u));
-        if (unsigned long long* o = node_slot(E, R, pos)) store_record(o, 0ULL, blk, s_off[byte]);
+        if (unsigned long long* o = node_slot(E, R, pos)) store_record(o, 0ULL, blk, child_offsets_lut(byte));
     }
     if (E.root_here && lane == 8) {
-        if (unsigned long long* o = node_slot(E, R, S)) store_record(o, 0ULL, base + S - __popc(nzb), s_off[nzb]);
+        if (unsigned long long* o = node_slot(E, R, S)) store_record(o, 0ULL, base + S - __popc(nzb), child_offsets_lut(nzb));
     }
 }
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_emit_upper(Level L, Level C, EmitJob E) {
-    __shared__ unsigned long long s_off[256];
-    if (!E.levels) {
-        for (int t = threadIdx.x; t < 256; t += blockDim.x) s_off[t] = child_offsets((uint32_t)t);
-        __syncthreads();
-    }
     if (build_aborted(E.info)) return;
     const unsigned long long i = (unsigned long long)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
     if (i >= level_n(L)) return;
     const NodeRange R = node_range(E);
     if (E.levels) emit_upper_tile(L, C, E, R, i, threadIdx.x & 31);
-    else emit_upper_tile_fast(L, C, E, R, i, threadIdx.x & 31, s_off);
+    else emit_upper_tile_fast(L, C, E, R, i, threadIdx.x & 31);
+}
+
+// The upper levels of the device-driven build (no -levels). PERSISTENT warps walk batches of `bs` tiles (bs = 32 for the
+// 10^6-tile levels of the big grids, smaller when the level has fewer tiles than the GPU has warps): lane q loads the
+// descriptor of the batch's q-th tile (coalesced), and inside the batch the child loads of tile q + 1 are issued before
+// the records of tile q are written -- one warp per tile spent three dependent memory latencies per tile (info -> tile ->
+// children) and nothing else. Lanes map to the tile's children by RANK (the children of a tile are consecutive in the
+// list below, so all loads are coalesced; 16 children per tile is typical and one round of 32 lanes covers it): the byte k
+// a child belongs to follows from the running per-byte counts with one SWAR compare, its position needs no bit index.
+struct UpperChild { unsigned long long psc, psc1, pend, gm; };
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_emit_upper_fast(Level L, Level C, EmitJob E, int bs) {
+    if (build_aborted(E.info)) return;
+    const int lane = threadIdx.x & 31;
+    const unsigned long long n = level_n(L);
+    const unsigned long long nbatch = (n + bs - 1) / bs;
+    const unsigned long long nwarps = (unsigned long long)gridDim.x * WARPS_PER_BLOCK;
+    const NodeRange R = node_range(E);
+    constexpr unsigned long long ONES = 0x0101010101010101ULL, HIGH = 0x8080808080808080ULL;
+    for (unsigned long long batch = (unsigned long long)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5); batch < nbatch; batch += nwarps) {
+        const unsigned long long t0 = batch * bs;
+        const int cnt = (int)min((unsigned long long)bs, n - t0);
+        unsigned long long myW = 0ULL, myFc = 0ULL, myBase = 0ULL, myS = 0ULL;
+        if (lane < cnt) {
+            const unsigned long long t = t0 + lane;
+            myW = L.mask[t]; myFc = L.fc[t]; myBase = L.base[t]; myS = L.ps[t + 1] - L.ps[t];
+            if (L.clear) L.clear[L.key[t]] = 0ULL;
+        }
+        // state of the tile whose loads are in flight
+        unsigned long long nW = 0ULL, nFc = 0ULL, nCum = 0ULL;
+        uint32_t nThrough = 0, nByte = 0;                       // of this lane's child (rank = lane)
+        UpperChild nx = {0ULL, 0ULL, 0ULL, 0ULL};
+        auto child_of = [&](unsigned long long W, unsigned long long cum, int r, uint32_t& through, uint32_t& byte) {
+            // bytes whose running count is <= r come before the child's byte: cum is monotone, every byte <= 64
+            const int k = 8 - __popcll(((cum | HIGH) - (unsigned long long)(r + 1) * ONES) & HIGH);
+            through = (uint32_t)(cum >> (8 * k)) & 0xffu;
+            byte = (uint32_t)(W >> (8 * k)) & 0xffu;
+        };
+        auto load_child = [&](unsigned long long fc, int r, uint32_t through, UpperChild& u) {
+            const unsigned long long c = fc + r;
+            u.psc = C.ps[c]; u.psc1 = C.ps[c + 1]; u.gm = C.mask[c]; u.pend = C.ps[fc + through];
+        };
+        auto prepare = [&](int q) {
+            nW = __shfl_sync(0xffffffffu, myW, q);
+            nFc = __shfl_sync(0xffffffffu, myFc, q);
+            unsigned long long bp = nW - ((nW >> 1) & 0x5555555555555555ULL);
+            bp = (bp & 0x3333333333333333ULL) + ((bp >> 2) & 0x3333333333333333ULL);
+            bp = (bp + (bp >> 4)) & 0x0f0f0f0f0f0f0f0fULL;
+            nCum = bp * ONES;                                    // inclusive running per-byte child counts
+            const int nchild = (int)(nCum >> 56);
+            nx.psc = 0ULL; nx.psc1 = 0ULL; nx.pend = 0ULL; nx.gm = 0ULL;
+            if (lane < nchild) { child_of(nW, nCum, lane, nThrough, nByte); load_child(nFc, lane, nThrough, nx); }
+        };
+        auto write_child = [&](unsigned long long base, unsigned long long ps0, int r, uint32_t through, uint32_t byte, const UpperChild& u, unsigned long long fc) {
+            const uint32_t before = through - (uint32_t)__popc(byte);                 // children in the bytes below
+            const unsigned long long gbase = base + (u.psc - ps0) + before;           // subtree region of this grandchild
+            C.base[fc + r] = gbase;
+            const unsigned long long pos = base + (u.pend - ps0) + r;                 // its record, in the children block of its byte
+            if (unsigned long long* o = node_slot(E, R, pos)) {
+                const uint32_t gnz = nonzero_bytes(u.gm);
+                store_record(o, 0ULL, gbase + (u.psc1 - u.psc) - __popc(gnz), child_offsets_lut(gnz));
+            }
+        };
+        prepare(0);
+        for (int q = 0; q < cnt; q++) {
+            const unsigned long long W = nW, fc = nFc, cum = nCum;
+            const uint32_t through = nThrough, byte = nByte;
+            const UpperChild u = nx;
+            const unsigned long long base = __shfl_sync(0xffffffffu, myBase, q), S = __shfl_sync(0xffffffffu, myS, q);
+            if (q + 1 < cnt) prepare(q + 1);
+            const int nchild = (int)(cum >> 56);
+            const unsigned long long ps0 = __shfl_sync(0xffffffffu, u.psc, 0);       // C.ps[fc]
+            if (lane < nchild) write_child(base, ps0, lane, through, byte, u, fc);
+            if (nchild > 32) {                                                        // second round (rare)
+                const int r = lane + 32;
+                if (r < nchild) {
+                    uint32_t th, by; UpperChild v;
+                    child_of(W, cum, r, th, by);
+                    load_child(fc, r, th, v);
+                    write_child(base, ps0, r, th, by, v, fc);
+                }
+            }
+            // the tile's own children: one record per non-zero byte, behind the subtrees
+            const uint32_t nzb = nonzero_bytes(W);
+            const int k = lane & 7;
+            const uint32_t by = (uint32_t)(W >> (8 * k)) & 0xffu;
+            const uint32_t th = (uint32_t)(cum >> (8 * k)) & 0xffu, before = th - (uint32_t)__popc(by);
+            // the end of byte k's subtrees: the value its last child (rank th - 1) already holds
+            const unsigned long long pend_sh = __shfl_sync(0xffffffffu, u.pend, (int)(th - 1u) & 31);
+            if (lane < 8 && by) {
+                const unsigned long long pend = th <= 32 ? pend_sh : C.ps[fc + th];
+                const unsigned long long blk = base + (pend - ps0) + before;
+                const unsigned long long pos = base + S - __popc(nzb) + __popc(nzb & ((1u << k) - 1u));
+                if (unsigned long long* o = node_slot(E, R, pos)) store_record(o, 0ULL, blk, child_offsets_lut(by));
+            }
+            if (E.root_here && lane == 8) {
+                if (unsigned long long* o = node_slot(E, R, S)) store_record(o, 0ULL, base + S - __popc(nzb), child_offsets_lut(nzb));
+            }
+        }
+    }
 }
 
 // Level 0 (bricks): the whole subtree region of a brick is contiguous in the file: popc(W) leaf records followed by
@@ -1297,106 +1401,164 @@ constexpr int EMIT_TILES_PER_WARP = 32;         // bricks per batch of a warp
 // 16-byte store to a 16-byte aligned address. Inline PTX on purpose: written as a C++ vector store, the two branches of
 // "aligned: 16 + 8, else 8 + 16" write the same bytes and the compiler folds them into ONE (then misaligned) form.
 __device__ __forceinline__ void st128(unsigned long long* p, unsigned long long a, unsigned long long b) {
-    asm volatile("st.global.v2.u64 [%0], {%1, %2};" :: "l"(p), "l"(a), "l"(b) : "memory");
+    asm volatile("st.global.v2.u64 [%0], {%1, %2};" :: "l"(p), "l"(a), "l"(b));
 }
 // PERSISTENT warps: every warp walks batches of 32 bricks with a stride of the whole grid; the descriptors (word, file
 // base, leaf rank) of the NEXT batch are loaded before the current one is written, so that no warp ever sits idle on
 // its loads (at 8192^3 the lists come from DRAM: without the prefetch the kernel ran at 44 % of the HBM peak).
-template <bool PAYLOAD>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_emit_leaf(Level L, EmitJob E) {
-    __shared__ unsigned long long s_off[256];
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_off[i] = child_offsets((uint32_t)i);
-    __syncthreads();
+// WHOLE SECTORS. Records are 24 bytes, so a brick's region starts anywhere on an 8-byte grid -- and a store instruction
+// that leaves a 32-byte sector half written costs the L2 a read-modify-write: tools/native/store_probe.cu measures the
+// bare store pattern of "eight lanes write 128 contiguous bytes of a brick" at 5.9 TB/s when the runs start on sector
+// boundaries and at 2.4 TB/s when they start 16 bytes off (the rate this kernel ran at before). So every store
+// instruction here covers whole sectors wherever the file allows it:
+//   interior   the leaf run between its first and last sector boundary, as aligned 16-byte pairs (lanes 2 j, 2 j + 1 of a
+//              group fill one sector)
+//   seam       what lies between the interiors of two consecutive bricks -- the last 0..3 words of this run, this brick's
+//              child records (<= 24 words), the first 0..3 words of the NEXT brick's run when it follows without a gap --
+//              is composed in shared memory (<= 30 words) and written as aligned pairs too: it starts and ends on sector
+//              boundaries by construction
+// Partial sectors remain only where another kernel's records follow a brick (the parent's children blocks, about every
+// second brick) and at the ends of a batch.
+// In geometry-only mode the leaf run is a constant pattern of period three words (data 1, children base 0, offsets ~0: the
+// word of field f is 1 - f).
+template <bool PAYLOAD, int MINB>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MINB) k_emit_leaf(Level L, EmitJob E) {
+    __shared__ unsigned long long s_seam[WARPS_PER_BLOCK][2][4][32];
     if (build_aborted(E.info)) return;
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const unsigned long long n = level_n(L);
     const unsigned long long nbatch = (n + 31) / 32;
     const unsigned long long nwarps = (unsigned long long)gridDim.x * WARPS_PER_BLOCK;
-    unsigned long long batch = (unsigned long long)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    unsigned long long batch = (unsigned long long)blockIdx.x * WARPS_PER_BLOCK + wid;
     if (batch >= nbatch) return;
     const NodeRange R = node_range(E);
+    unsigned long long* const nodes = E.nodes;
     const int g = lane >> 3, s = lane & 7;                                        // group (brick of the round), lane in the group
+    const unsigned gmask = 0xffu << (8 * g);
     const int s2 = (2 * s) % 3;
-    unsigned long long nW = 0ULL, nBase = 0ULL, nFc = 0ULL;
-    auto prefetch = [&](unsigned long long bt) {
+    constexpr unsigned REL_BITS = 25, REL_MASK = (1u << REL_BITS) - 1u;
+    unsigned long long nW = 0ULL, nBase = 0ULL, nFc = 0ULL, nKey = ~0ULL;
+    auto prefetch = [&](unsigned long long bt) {              // loads only: a store that depends on one of them would stall the warp here
         const unsigned long long t = bt * 32 + lane;
-        nW = 0ULL; nBase = 0ULL; nFc = 0ULL;
+        nW = 0ULL; nBase = 0ULL; nFc = 0ULL; nKey = ~0ULL;
         if (bt < nbatch && t < n) {
             nW = L.mask[t];
             nBase = L.base[t];
             if (PAYLOAD) nFc = L.fc[t];
-            if (L.clear) L.clear[L.key[t]] = 0ULL;
+            if (L.clear) nKey = L.key[t];
         }
     };
     prefetch(batch);
     while (batch < nbatch) {
         const int cnt = (int)min(32ULL, n - batch * 32);
-        unsigned long long myW = nW;
-        const unsigned long long myBase = nBase, myFc = nFc;
+        const unsigned long long myW = nW, myBase = nBase, myFc = nFc, myKey = nKey;
         batch += nwarps;
         prefetch(batch);                                                          // in flight while this batch is written
+        if (myKey != ~0ULL) L.clear[myKey] = 0ULL;                                // the brick's word in the bit-grid is consumed: leave it clean
+        const unsigned nleaf = (unsigned)__popcll(myW);
+        const uint32_t nzb = nonzero_bytes(myW);
+        const unsigned S = nleaf + (unsigned)__popc(nzb);                             // records of the brick's region
         // a rank's own bricks always lie inside its range; the capacity guard drops whole bricks
-        const bool ok = lane < cnt && E.write_records && myBase >= R.lo &&
-                        myBase + (unsigned long long)(__popcll(myW) + __popc(nonzero_bytes(myW)) + (E.root_here ? 1 : 0)) <= R.hi;
-        if (!ok) myW = 0ULL;                                                          // nothing is written for this brick
-        const unsigned long long myRel = ok ? (myBase - R.lo) * 3ULL : 0ULL;          // first word of the region in the buffer
+        const bool ok = lane < cnt && myW != 0ULL && E.write_records && myBase >= R.lo &&
+                        myBase + (unsigned long long)(S + (E.root_here ? 1u : 0u)) <= R.hi;
+        const unsigned okm = __ballot_sync(0xffffffffu, ok);
+        if (!okm) continue;
+        const unsigned long long rel = myBase - R.lo;                                 // first record of the region in the buffer
+        const unsigned long long ref = __shfl_sync(0xffffffffu, rel, __ffs(okm) - 1); // ... of the batch's first brick
         const unsigned long long leaf1 = 1ULL + R.leaf_offset + myFc;                 // payload: data index of the brick's first leaf
+        // (the gridsize-4 root brick and a brick further than 2^25 records from the batch's first -- no tree has one -- take the
+        // plain path below)
+        const bool in_group = ok && !E.root_here && (rel - ref) <= (unsigned long long)REL_MASK;
+        if (ok && !in_group) {
+            unsigned long long* const out = nodes + 3ULL * rel;
+            for (unsigned q = 0; q < nleaf; q++) { out[3 * q] = PAYLOAD ? leaf1 + q : 1ULL; out[3 * q + 1] = 0ULL; out[3 * q + 2] = ~0ULL; }
+            unsigned long long* o = out + 3u * nleaf;
+            unsigned long long cb = myBase;                                           // first leaf of the byte
+            for (uint32_t m = nzb; m; m &= m - 1u) {
+                const int k = __ffs(m) - 1;
+                const uint32_t byte = (uint32_t)(myW >> (8 * k)) & 0xffu;
+                o[0] = 0ULL; o[1] = cb; o[2] = child_offsets_lut(byte);
+                cb += (unsigned)__popc(byte);
+                o += 3;
+            }
+            if (E.root_here) { o[0] = 0ULL; o[1] = myBase + nleaf; o[2] = child_offsets(nzb); }   // gridsize 4: the single brick is the root
+        }
+        // does the next / previous brick of the batch follow without a gap?
+        const unsigned long long relN = __shfl_down_sync(0xffffffffu, rel, 1), relP = __shfl_up_sync(0xffffffffu, rel, 1);
+        const unsigned SP = __shfl_up_sync(0xffffffffu, S, 1);
+        const unsigned gm = __ballot_sync(0xffffffffu, in_group);
+        const bool contigN = in_group && lane < 31 && ((gm >> (lane + 1)) & 1u) && rel + S == relN;
+        const bool contigP = in_group && lane > 0 && ((gm >> (lane - 1)) & 1u) && relP + SP == rel;
+        const unsigned packed = in_group ? ((unsigned)(rel - ref) | (contigN ? 1u << REL_BITS : 0u) | (contigP ? 0u : 1u << (REL_BITS + 1)) | (1u << (REL_BITS + 2))) : 0u;
+        unsigned long long* const outref = nodes + 3ULL * ref;
+        const unsigned long long baseref = R.lo + ref;
+        const unsigned ref32 = (unsigned)ref;
+        __syncwarp();                                                                 // (the seam buffers of the previous batch are free)
         for (int r = 0; r < cnt; r += 4) {
-            const int t = r + g;                                                      // brick of this group (lanes beyond cnt hold W = 0)
-            const unsigned long long W = __shfl_sync(0xffffffffu, myW, t);
-            const unsigned long long w0 = __shfl_sync(0xffffffffu, myRel, t);
-            const unsigned long long base = __shfl_sync(0xffffffffu, myBase, t);
+            const unsigned pk = __shfl_sync(0xffffffffu, packed, r + g);              // (lanes beyond cnt hold 0)
+            const unsigned long long W = __shfl_sync(0xffffffffu, myW, r + g);
             unsigned long long d0 = 1ULL;
-            if (PAYLOAD) d0 = __shfl_sync(0xffffffffu, leaf1, t);
-            if (W == 0ULL) continue;
-            const int nleaf = __popcll(W), words = 3 * nleaf;
-            unsigned long long* out = E.nodes + w0;
-            const int odd = (int)(w0 & 1ULL);
-            // relative words [odd, last) are written as aligned pairs, q = odd + 2 * (s + 8 * i)
-            const int last = words - ((words - odd) & 1);
-            int f = odd + s2; if (f >= 3) f -= 3;               // field of word q: q % 3 (w0 = 3 * base: a multiple of three words)
+            if (PAYLOAD) d0 = __shfl_sync(0xffffffffu, leaf1, r + g);
+            if (!(pk >> (REL_BITS + 2))) continue;                                    // (uniform in the group)
+            const unsigned rel32 = pk & REL_MASK;
+            const bool next_follows = (pk >> REL_BITS) & 1u, own_head = (pk >> (REL_BITS + 1)) & 1u;
+            unsigned long long* const out = outref + 3ULL * rel32;                    // word 0 of the brick's region
+            const unsigned a0 = (3u * (ref32 + rel32)) & 3u;                          // position of word 0 inside its sector (the buffer is 256-byte aligned)
+            const unsigned nl = (unsigned)__popcll(W), words = 3u * nl;
+            const uint32_t nz8 = nonzero_bytes(W);
+            const unsigned head = (4u - a0) & 3u;                                     // words before the first sector boundary
+            const unsigned tail = (a0 + words) & 3u;                                  // words behind the last one
+            const unsigned iend = words - tail;                                       // interior: [head, iend), a multiple of four words long (possibly empty)
+            // ---- interior ----
+            int f = (head == 3u ? 0 : (int)head) + s2; if (f >= 3) f -= 3;            // field of this lane's first word, (head + 2 s) % 3
             if (!PAYLOAD) {
-                // the three pair patterns (1, 0) (0, ~0) (~0, 1) in the order this lane meets them: the field advances by
-                // 16 % 3 == 1 per step, so three steps are one period
-                const unsigned long long a0 = f == 0 ? 1ULL : (f == 1 ? 0ULL : ~0ULL), b0 = f == 0 ? 0ULL : (f == 1 ? ~0ULL : 1ULL);
-                const unsigned long long a1 = b0;                                                   // the pair one word further on
-                const unsigned long long b1 = a1 == 1ULL ? 0ULL : (a1 == 0ULL ? ~0ULL : 1ULL);
-                const unsigned long long a2 = b1;
-                const unsigned long long b2 = a2 == 1ULL ? 0ULL : (a2 == 0ULL ? ~0ULL : 1ULL);
-                unsigned long long* p = out + odd + 2 * s;
-                unsigned long long* const end = out + last;
-                for (; p < end; p += 48) {
-                    st128(p, a0, b0);
-                    if (p + 16 < end) st128(p + 16, a1, b1);
-                    if (p + 32 < end) st128(p + 32, a2, b2);
+                // the field advances by 16 % 3 == 1 per store: three stores are one period
+                const int f1 = f == 2 ? 0 : f + 1, f2 = f1 == 2 ? 0 : f1 + 1;
+                const unsigned long long x0 = (unsigned long long)(long long)(1 - f), x1 = (unsigned long long)(long long)(1 - f1),
+                                         x2 = (unsigned long long)(long long)(1 - f2);
+                for (unsigned q = head + 2u * s; q < iend; q += 48u) {
+                    st128(out + q, x0, x1);
+                    if (q + 16u < iend) st128(out + q + 16u, x1, x2);
+                    if (q + 32u < iend) st128(out + q + 32u, x2, x0);
                 }
             } else {
-                for (int q = odd + 2 * s; q < last; q += 16) {
+                for (unsigned q = head + 2u * s; q < iend; q += 16u) {
                     unsigned long long a, b;                    // the data index of the record in the data field
-                    if (f == 0) { a = d0 + (unsigned)(q / 3); b = 0ULL; }
+                    if (f == 0) { a = d0 + (q / 3u); b = 0ULL; }
                     else if (f == 1) { a = 0ULL; b = ~0ULL; }
-                    else { a = ~0ULL; b = d0 + (unsigned)((q + 1) / 3); }
+                    else { a = ~0ULL; b = d0 + ((q + 1u) / 3u); }
                     st128(out + q, a, b);
                     f = f == 2 ? 0 : f + 1;
                 }
             }
-            if (odd && s == 7) out[0] = d0;                     // word 0: the data field of the first record
-            if (last < words && s == 6) out[words - 1] = ~0ULL; // the run's last word: an offsets field
-            // child record of byte s
-            const uint32_t byte = (uint32_t)((W >> (8 * s)) & 0xffULL);
-            const uint32_t nzb = nonzero_bytes(W);
-            if (byte) {
-                unsigned long long* o = out + words + 3 * __popc(nzb & ((1u << s) - 1u));
-                const unsigned long long cb = base + __popcll(W & lowmask(8 * s));
-                const unsigned long long off = s_off[byte];
-                if (((uintptr_t)o & 15) == 0) { st128(o, 0ULL, cb); o[2] = off; }
-                else { o[0] = 0ULL; st128(o + 1, cb, off); }
+            // ---- head, when the brick before this one does not cover it ----
+            if (own_head && (unsigned)s < head) out[s] = s == 0 ? d0 : (unsigned long long)(long long)(1 - s);
+            // ---- seam ----
+            unsigned long long* const sb = s_seam[wid][(r >> 2) & 1][g];
+            if ((unsigned)s < tail) {                                                 // word iend + s of the run: field 3 - (tail - s), of the LAST leaf for field 0
+                const int fl = (int)(3u - (tail - (unsigned)s)) % 3;
+                sb[s] = fl == 0 ? (PAYLOAD ? d0 + (nl - 1u) : 1ULL) : (unsigned long long)(long long)(1 - fl);
             }
-            if (E.root_here && s == 0) {   // gridsize 4: the single brick is the root
-                unsigned long long* o = out + words + 3 * __popc(nzb);
-                o[0] = 0ULL;
-                o[1] = base + nleaf;
-                o[2] = child_offsets(nzb);
+            const uint32_t byte = (uint32_t)((W >> (8 * s)) & 0xffULL);
+            if (byte) {                                                               // child record of byte s
+                const unsigned j0 = tail + 3u * (unsigned)__popc(nz8 & ((1u << s) - 1u));
+                sb[j0] = 0ULL;
+                sb[j0 + 1] = baseref + rel32 + (unsigned)__popcll(W & lowmask(8 * s));
+                sb[j0 + 2] = child_offsets_lut(byte);
+            }
+            unsigned len = tail + 3u * (unsigned)__popc(nz8);
+            if (next_follows) {                                                       // up to the next brick's first sector boundary
+                const unsigned nh = (4u - (len & 3u)) & 3u;
+                if ((unsigned)s < nh) sb[len + s] = s == 0 ? (PAYLOAD ? d0 + nl : 1ULL) : (unsigned long long)(long long)(1 - s);
+                len += nh;
+            }
+            __syncwarp(gmask);
+            unsigned long long* const so = out + iend;
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+                const unsigned j = 2u * s + 16u * i;
+                if (j + 1u < len) st128(so + j, sb[j], sb[j + 1]);
+                else if (j < len) so[j] = sb[j];
             }
         }
     }
@@ -1618,9 +1780,6 @@ __global__ void __launch_bounds__(1024) k_fused_up(FusedJob F) {
 // top-down emission of levels J..jf+1 (each level writes the bases of the next); level jf itself is emitted
 // by the regular multi-block kernel afterwards. No -levels on this path.
 __device__ __forceinline__ void fused_emit_body(const FusedJob& F) {
-    __shared__ unsigned long long s_off[256];
-    for (int t = threadIdx.x; t < 256; t += blockDim.x) s_off[t] = child_offsets((uint32_t)t);
-    __syncthreads();
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const NodeRange R = node_range(F.E);
     for (int j = F.J; j > F.jf; j--) {
@@ -1628,7 +1787,7 @@ __device__ __forceinline__ void fused_emit_body(const FusedJob& F) {
         const unsigned long long n = level_n(L);
         EmitJob E = F.E;
         E.root_here = (j == F.J) ? F.E.root_here : 0;
-        for (unsigned long long i = wid; i < n; i += nw) emit_upper_tile_fast(L, C, E, R, i, lane, s_off);      // (no -levels on this path)
+        for (unsigned long long i = wid; i < n; i += nw) emit_upper_tile_fast(L, C, E, R, i, lane);      // (no -levels on this path)
         __threadfence();
         __syncthreads();
     }

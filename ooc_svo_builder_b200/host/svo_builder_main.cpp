@@ -233,13 +233,27 @@ bool pwrite_all(int fd, const char* src, size_t n, off_t off) {
 // pinned buffers and hands the chunks IN ORDER to `consume(ptr, bytes)`. consume's contract is the library's
 // double-buffer rule (svo_triangles_append): when it returns, every EARLIER chunk has been copied to the device, so a
 // slot is reusable once the chunk after it has been consumed (replaces TriReader's fread loop, TriReader.h:41-79).
+// Pinning host memory costs about as much as copying it: the chunks come from a small pool that is allocated ONCE per
+// rank and serves the input ring first and the output ring afterwards.
+struct PinnedPool {
+    std::vector<void*> slot;
+    size_t bytes = 0;                         // per slot
+    bool init(int n, size_t b) {
+        bytes = b;
+        for (int i = 0; i < n; i++) { void* p = svo_host_alloc(b); if (!p) return false; slot.push_back(p); }
+        return true;
+    }
+    ~PinnedPool() { for (auto p : slot) svo_host_free(p); }
+};
+
 template <class Consume>
-bool stream_in(int fd, off_t first, size_t total, size_t chunk, int n_threads, Consume consume) {
+bool stream_in(int fd, off_t first, size_t total, size_t chunk_unit, int n_threads, const PinnedPool& pool, Consume consume) {
     if (total == 0) return true;
+    const size_t chunk = std::max<size_t>(pool.bytes / chunk_unit, 1) * chunk_unit;      // whole records per chunk
+    if (chunk > pool.bytes) return false;
     const size_t n_chunks = (total + chunk - 1) / chunk;
-    const int R = (int)std::min<size_t>(n_chunks, (size_t)n_threads + 2);
-    std::vector<void*> slot(R, nullptr);
-    for (auto& p : slot) { p = svo_host_alloc(chunk); if (!p) return false; }
+    const int R = (int)std::min<size_t>(n_chunks, pool.slot.size());
+    const std::vector<void*>& slot = pool.slot;
     std::mutex mu;
     std::condition_variable cv;
     std::vector<char> ready(n_chunks, 0);
@@ -261,7 +275,7 @@ bool stream_in(int fd, off_t first, size_t total, size_t chunk, int n_threads, C
         }
     };
     std::vector<std::thread> th;
-    for (int t = 0; t < std::min<int>(n_threads, (int)n_chunks); t++) th.emplace_back(reader);
+    for (int t = 0; t < std::min<int>(std::min<int>(n_threads, R), (int)n_chunks); t++) th.emplace_back(reader);
     bool ok = true;
     for (size_t i = 0; i < n_chunks && ok; i++) {
         {
@@ -278,7 +292,6 @@ bool stream_in(int fd, off_t first, size_t total, size_t chunk, int n_threads, C
     { std::lock_guard<std::mutex> lk(mu); released = n_chunks; }
     cv.notify_all();
     for (auto& t : th) t.join();
-    for (auto p : slot) svo_host_free(p);
     return ok && !failed;
 }
 
@@ -287,14 +300,13 @@ bool stream_in(int fd, off_t first, size_t total, size_t chunk, int n_threads, C
 // Positional writes: the order in which chunks reach the file does not matter (replaces writeNode / writeVoxelData,
 // octree_io.h:49-66). Chunks stay inside `budget` bytes in total.
 bool stream_out(svo_ctx* ctx, int fd, uint64_t first, uint64_t count, uint64_t rec, int (*fetch)(svo_ctx*, uint64_t, uint64_t, void*),
-                size_t budget, int n_threads, std::string& err) {
+                const PinnedPool& pool, int n_threads, std::string& err) {
     if (count == 0) return true;
-    const int R = n_threads + 1;
-    const size_t chunk_bytes = std::max<size_t>(std::min<size_t>(budget / (size_t)R, 64u << 20) / rec * rec, rec);
-    const uint64_t per = chunk_bytes / rec;
+    const int R = (int)pool.slot.size();
+    n_threads = std::max(1, std::min(n_threads, R - 1));
+    const uint64_t per = std::max<uint64_t>(pool.bytes / rec, 1);
     const uint64_t n_chunks = (count + per - 1) / per;
-    std::vector<void*> slot(R, nullptr);
-    for (auto& p : slot) { p = svo_host_alloc(chunk_bytes); if (!p) { err = "cannot allocate pinned output buffers"; return false; } }
+    const std::vector<void*>& slot = pool.slot;
     std::mutex mu;
     std::condition_variable cv;
     std::vector<int> state(R, 0);             // 0 free, 1 filled (waiting for a writer), 2 being written
@@ -333,7 +345,6 @@ bool stream_out(svo_ctx* ctx, int fd, uint64_t first, uint64_t count, uint64_t r
     { std::lock_guard<std::mutex> lk(mu); done = true; }
     cv.notify_all();
     for (auto& t : th) t.join();
-    for (auto p : slot) svo_host_free(p);
     if (failed && err.empty()) err = "write error (disk full?)";
     return !failed;
 }
@@ -418,13 +429,17 @@ int main(int argc, char** argv) {
     for (int r = 0; r < world; r++) if (ctx_ready[r].get() != SVO_OK) die(nullptr, "svo_ctx_create");
 
     // Triangle records: the file is read by several threads (pread) into a ring of pinned chunks inside the -l budget
-    // and streamed to the device(s) in file order; the whole file is never resident on the host.
-    const size_t chunk_in = std::max<size_t>(std::min<size_t>(budget / (size_t)(n_io + 2) / (size_t)world, 32u << 20) / rec_bytes, 1) * rec_bytes;
+    // and streamed to the device(s) in file order; the whole file is never resident on the host. One pool of pinned
+    // chunks per rank (at most 4 x 16 MB, inside the budget), reused for the output.
+    const int pool_slots = 4;
+    const size_t pool_chunk = std::max<size_t>(std::min<size_t>(budget / (size_t)(pool_slots * world), 16u << 20), 2 * 84);
+    std::vector<PinnedPool> pools(world);
+    for (int r = 0; r < world; r++) if (!pools[r].init(pool_slots, pool_chunk)) { std::cout << "Error: cannot allocate pinned IO buffers" << std::endl; return 0; }
     const uint64_t per_rank = (hdr.n_triangles + (uint64_t)world - 1) / (uint64_t)world;       // rank r holds slice r of the file
     std::vector<void*> windows(world, nullptr);
     if (world == 1) {
         if (svo_triangles_begin(ctx[0], hdr.n_triangles, kFloatsPerTri) != SVO_OK) die(ctx[0], "svo_triangles_begin");
-        const bool ok = stream_in(in_fd, 0, tri_bytes, chunk_in, n_io, [&](void* p, size_t len) {
+        const bool ok = stream_in(in_fd, 0, tri_bytes, rec_bytes, n_io, pools[0], [&](void* p, size_t len) {
             return svo_triangles_append(ctx[0], static_cast<const float*>(p), len / rec_bytes) == SVO_OK;
         });
         if (!ok) { std::cout << "Error reading " << tridata << ": " << svo_last_error(ctx[0]) << std::endl; return 0; }
@@ -441,7 +456,7 @@ int main(int argc, char** argv) {
             up.push_back(std::async(std::launch::async, [&, r]() {
                 const uint64_t lo = std::min<uint64_t>((uint64_t)r * per_rank, hdr.n_triangles), hi = std::min<uint64_t>(lo + per_rank, hdr.n_triangles);
                 if (svo_shard_slice_begin(ctx[r], hi - lo) != SVO_OK) return false;
-                const bool ok = stream_in(in_fd, (off_t)(lo * rec_bytes), (size_t)(hi - lo) * rec_bytes, chunk_in, std::max(1, n_io / world), [&](void* p, size_t len) {
+                const bool ok = stream_in(in_fd, (off_t)(lo * rec_bytes), (size_t)(hi - lo) * rec_bytes, rec_bytes, std::max(1, n_io / world), pools[r], [&](void* p, size_t len) {
                     return svo_shard_slice_append(ctx[r], static_cast<const float*>(p), len / rec_bytes) == SVO_OK;
                 });
                 return ok && svo_synchronize(ctx[r]) == SVO_OK;
@@ -540,7 +555,7 @@ int main(int argc, char** argv) {
                     lo = nodes ? nlo : dlo; hi = nodes ? nhi : dhi;
                 }
                 std::string err;
-                stream_out(ctx[r], fd, lo, hi - lo, rec, nodes ? svo_fetch_nodes : svo_fetch_data, budget / (size_t)world, std::max(1, n_io / world / 2 + 1), err);
+                stream_out(ctx[r], fd, lo, hi - lo, rec, nodes ? svo_fetch_nodes : svo_fetch_data, pools[r], std::max(1, n_io / world), err);
                 return err;
             }));
         }

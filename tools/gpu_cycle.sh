@@ -17,5 +17,5 @@ except Exception as e:
     print("bench failed", e); print(open("gpurun_out/bench_$tag.err").read()[-2000:])
 PY
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches_$tag.csv python tools/profile_step.py c2 > /dev/null 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_vox_warp|k_emit_leaf|k_brick_pass|k_dense_scan|k_emit_upper" -s 10 -c 14 -o gpurun_out/prof_$tag -f python tools/profile_step.py c2 > gpurun_out/ncu_$tag.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_vox_warp|k_emit_leaf|k_brick|k_dense_scan|k_emit_upper" -s 10 -c 14 -o gpurun_out/prof_$tag -f python tools/profile_step.py c2 > gpurun_out/ncu_$tag.log 2>&1
 ls -la gpurun_out/prof_$tag.ncu-rep
