@@ -235,6 +235,12 @@ def load_profile():
         return {}
 
 
+def leaf_emitter_bytes(n_brick_records, n_bricks):
+    """Algorithmic bytes of k_emit_leaf: 24 B per record of the brick subtrees (leaves + depth D-1 nodes) and per brick
+    record (the parent's children blocks, written by the same kernel), 24 B read per brick (key, word, file base)."""
+    return 24 * (n_brick_records + n_bricks) + 24 * n_bricks
+
+
 def frac_entry(nbytes: float, ms: float, peak: float) -> dict:
     ach = nbytes / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
     return {"ms": ms, "algorithmic_bytes": int(nbytes), "achieved": ach, "unit": "GB/s", "frac": ach / peak}
@@ -301,7 +307,7 @@ def ours_single(args, peak, peak_src, sm_max_mhz):
     prof = load_profile()
     n_bricks, n_t1, n_brec = st["n_bricks"], st["n_tiles1"], st["n_brick_records"]
     vox_bytes = T * 36 + 8 * n_bricks + 8 * n_t1          # records read + one 64-bit word per touched brick / level-1 tile
-    leaf_bytes = 24 * n_brec + 16 * n_bricks              # records written + (mask, base) read per brick
+    leaf_bytes = leaf_emitter_bytes(n_brec, n_bricks)
     kernels = {
         "k_vox_warp": frac_entry(vox_bytes, avg("ms_vox_small"), peak),
         "k_emit_leaf": frac_entry(leaf_bytes, avg("ms_emit_leaf"), peak),
@@ -323,8 +329,8 @@ def ours_single(args, peak, peak_src, sm_max_mhz):
         "traffic": traffic, "traffic_source": "committed ncu --set full capture of the same step (%s); not measured in this run" % os.path.relpath(PROFILE_JSON, ROOT),
         "peak_source": peak_src, "algorithmic_bytes": kernels[dom]["algorithmic_bytes"], "kernel_ms": kernels[dom]["ms"],
         "note": "each kernel: its own algorithmic bytes / its own CUDA-event time. k_vox_warp: T*36 B records + 8 B per touched brick and level-1 "
-                "tile; it is instruction-issue bound (see `issue`), not HBM bound. k_emit_leaf: 24 B per record it writes (leaves + depth D-1 nodes) "
-                "+ 16 B read per brick. octree_build_stage: SURVEY.md 8d bytes (8*N + 24*N_nodes) / the whole build stage (ms_build).",
+                "tile; it is instruction-issue bound (see `issue`), not HBM bound. k_emit_leaf: 24 B per record it writes (leaves, depth D-1 nodes and the "
+                "bricks' own records) + 24 B read per brick (key, word, file base). octree_build_stage: SURVEY.md 8d bytes (8*N + 24*N_nodes) / the whole build stage (ms_build).",
         "issue": issue, "kernels": kernels,
         "octree_build_stage": frac_entry(8 * nv + 24 * nn, avg("ms_build"), peak),
     }
@@ -637,7 +643,7 @@ def ours_sharded(args, rank, world, local, dist, peak, peak_src):
         clocks = sampler.stop(t0, t1)
         value = T / (ms_per_step * 1e-3)
         lm = stage_max["ms_emit_leaf"]
-        leaf_bytes = 24 * st["n_brick_records"] + 16 * st["n_bricks"]                   # rank 0's own bricks
+        leaf_bytes = leaf_emitter_bytes(st["n_brick_records"], st["n_bricks"])         # rank 0's own bricks
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -654,7 +660,7 @@ def ours_sharded(args, rank, world, local, dist, peak, peak_src):
             "parity": parity,
             "roofline": {"bound": "hbm", "kernel": "k_emit_leaf (rank 0's bytes / slowest rank's time)", "achieved": leaf_bytes / max(lm, 1e-9) / 1e6, "peak": peak, "unit": "GB/s",
                          "frac": leaf_bytes / max(lm, 1e-9) / 1e6 / peak, "traffic": None, "peak_source": peak_src, "algorithmic_bytes": int(leaf_bytes), "kernel_ms": lm,
-                         "note": "k_emit_leaf: 24 B per record it writes + 16 B read per brick, its own time. octree_build_stage: rank 0's share of 8*N + 24*N_nodes "
+                         "note": "k_emit_leaf: 24 B per record it writes (brick subtrees + the bricks' own records) + 24 B read per brick, its own time. octree_build_stage: rank 0's share of 8*N + 24*N_nodes "
                                  "over the slowest rank's ms_build (includes the wait for the table exchange).",
                          "octree_build_stage": frac_entry((8 * nv + 24 * nn) / world, stage_max["ms_build"], peak)},
             "e2e": {"value": T / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(tris.nbytes),
@@ -764,7 +770,7 @@ def strong_scaling_record(torch, dist, db_unused, rank, world, local, stream, pe
         out.update({"ms_1_gpu": ms_1, "speedup": ms_1 / ms_n,
                     "one_gpu": {"ms_voxelize": st1["ms_voxelize"], "ms_build": st1["ms_build"], "ms_emit_leaf": st1["ms_emit_leaf"],
                                 "build_stage_hbm_frac": (8 * nv1 + 24 * nn1) / max(st1["ms_build"], 1e-9) / 1e6 / peak,
-                                "emit_leaf_hbm_frac": (24 * st1["n_brick_records"] + 16 * st1["n_bricks"]) / max(st1["ms_emit_leaf"], 1e-9) / 1e6 / peak,
+                                "emit_leaf_hbm_frac": leaf_emitter_bytes(st1["n_brick_records"], st1["n_bricks"]) / max(st1["ms_emit_leaf"], 1e-9) / 1e6 / peak,
                                 "nodes_filesum_ok": (None if not gold else [int(x) for x in one] == gold["nodes_filesum"])}})
         sb.close()
     dist.barrier()

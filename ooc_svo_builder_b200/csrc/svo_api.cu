@@ -490,9 +490,9 @@ int svo_ctx_create(int device, svo_ctx** out) {
     n->sm_count = prop.multiProcessorCount;
     {
         int r = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r, k_emit_leaf<false, 5>, WARPS_PER_BLOCK * 32, 0) == cudaSuccess && r > 0) n->res_emit_leaf[0] = r;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r, k_emit_leaf<true, 5>, WARPS_PER_BLOCK * 32, 0) == cudaSuccess && r > 0) n->res_emit_leaf[1] = r;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r, k_emit_upper_fast, WARPS_PER_BLOCK * 32, 0) == cudaSuccess && r > 0) n->res_emit_upper = r;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r, k_emit_leaf<false, 4, true>, WARPS_PER_BLOCK * 32, 0) == cudaSuccess && r > 0) n->res_emit_leaf[0] = r;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r, k_emit_leaf<true, 4, true>, WARPS_PER_BLOCK * 32, 0) == cudaSuccess && r > 0) n->res_emit_leaf[1] = r;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r, k_emit_upper_fast<true>, WARPS_PER_BLOCK * 32, 0) == cudaSuccess && r > 0) n->res_emit_upper = r;
     }
     memset(&n->stats, 0, sizeof n->stats);
     memset(&n->prm, 0, sizeof n->prm);
@@ -1498,8 +1498,8 @@ static int build_phase_b(svo_ctx* c, const ull* table) {
             const Level L0 = (J == 0) ? LJ : c->lv[0].view();
             mark(c, EV_EL0);
             if (levels) { k_emit_leaf_levels<<<blocks_for(L0.n, WARPS_PER_BLOCK), WARPS_PER_BLOCK * 32, 0, c->stream>>>(L0, E); LAUNCHED(); }
-            else if (payload) { k_emit_leaf<true, 5><<<blocks_for(L0.n, WARPS_PER_BLOCK * EMIT_TILES_PER_WARP), WARPS_PER_BLOCK * 32, 0, c->stream>>>(L0, E); LAUNCHED(); }
-            else { k_emit_leaf<false, 5><<<blocks_for(L0.n, WARPS_PER_BLOCK * EMIT_TILES_PER_WARP), WARPS_PER_BLOCK * 32, 0, c->stream>>>(L0, E); LAUNCHED(); }
+            else if (payload) { k_emit_leaf<true, 4, false><<<blocks_for(L0.n, WARPS_PER_BLOCK * EMIT_TILES_PER_WARP), WARPS_PER_BLOCK * 32, 0, c->stream>>>(L0, E); LAUNCHED(); }
+            else { k_emit_leaf<false, 4, false><<<blocks_for(L0.n, WARPS_PER_BLOCK * EMIT_TILES_PER_WARP), WARPS_PER_BLOCK * 32, 0, c->stream>>>(L0, E); LAUNCHED(); }
             mark(c, EV_EL1);
         }
     }
@@ -1860,31 +1860,19 @@ static int fast_phase_b(svo_ctx* c, ull* table) {
         int bs = 32;
         while (bs > 1 && n / bs < resident * WARPS_PER_BLOCK) bs >>= 1;
         const unsigned grid = (unsigned)std::min<ull>(blocks_for(blocks_for(n, bs), WARPS_PER_BLOCK), resident);
-        k_emit_upper_fast<<<grid, WARPS_PER_BLOCK * 32, 0, c->stream>>>(fast_view(c, j), fast_view(c, j - 1), E, bs); LAUNCHED();
+        // (the records of the bricks -- the children of level 1 -- are written by k_emit_leaf)
+        if (j == 1) { k_emit_upper_fast<false><<<grid, WARPS_PER_BLOCK * 32, 0, c->stream>>>(fast_view(c, j), fast_view(c, j - 1), E, bs); LAUNCHED(); }
+        else { k_emit_upper_fast<true><<<grid, WARPS_PER_BLOCK * 32, 0, c->stream>>>(fast_view(c, j), fast_view(c, j - 1), E, bs); LAUNCHED(); }
     }
     E.is_top = 0; E.root_here = 0;
     mark(c, EV_EL0);
     if (launch_n(0)) {
         // persistent warps: at most the resident set (a sixth block per SM would run alone after the others finished)
         const unsigned grid = (unsigned)std::min<ull>(blocks_for(launch_n(0), WARPS_PER_BLOCK * EMIT_TILES_PER_WARP), (ull)c->sm_count * c->res_emit_leaf[payload ? 1 : 0]);
-        static const int var = getenv("SVO_LEAF_VARIANT") ? atoi(getenv("SVO_LEAF_VARIANT")) : 0;
         const Level L0 = fast_view(c, 0);
-        const ull need = blocks_for(launch_n(0), WARPS_PER_BLOCK * EMIT_TILES_PER_WARP);
-#define LEAF_VARIANT(MINB, PER_SM) { \
-            int r = 4; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r, k_emit_leaf<false, MINB>, WARPS_PER_BLOCK * 32, 0); \
-            if (PER_SM < r) r = PER_SM; \
-            const unsigned gr = (unsigned)std::min<ull>(need, (ull)c->sm_count * r); \
-            if (payload) k_emit_leaf<true, MINB><<<gr, WARPS_PER_BLOCK * 32, 0, c->stream>>>(L0, E); \
-            else k_emit_leaf<false, MINB><<<gr, WARPS_PER_BLOCK * 32, 0, c->stream>>>(L0, E); }
-        (void)grid;
-        switch (var) {
-            case 1: LEAF_VARIANT(4, 4); break;
-            case 2: LEAF_VARIANT(4, 2); break;
-            case 3: LEAF_VARIANT(4, 3); break;
-            case 4: LEAF_VARIANT(6, 6); break;
-            case 5: LEAF_VARIANT(8, 8); break;
-            default: LEAF_VARIANT(5, 5); break;
-        }
+        E.ticket = &dinfo->leaf_ticket;          // (zeroed with the rest of the BuildInfo when the build began)
+        if (payload) k_emit_leaf<true, 4, true><<<grid, WARPS_PER_BLOCK * 32, 0, c->stream>>>(L0, E);
+        else k_emit_leaf<false, 4, true><<<grid, WARPS_PER_BLOCK * 32, 0, c->stream>>>(L0, E);
         LAUNCHED();
     }
     mark(c, EV_EL1);

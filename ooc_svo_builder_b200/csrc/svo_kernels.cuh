@@ -770,6 +770,7 @@ struct BuildInfo {
     unsigned long long leaf_offset;           // voxels in the slabs of lower ranks
     unsigned long long node_lo, node_hi;      // this rank's records of the node file
     unsigned long long n_upper;               // shared upper-level records inside [node_lo, node_hi)
+    unsigned long long leaf_ticket;           // k_emit_leaf hands out its batches in file order
     unsigned long long overflow;              // bit j: list of level j too small; bit 32: node buffer; bit 40: look-back timeout.
                                               // Once set, every later kernel of the build returns at once (the pyramid stays intact).
 };
@@ -1150,6 +1151,7 @@ struct EmitJob {
     unsigned long long cap;           // records the node buffer holds (speculative emission into an earlier build's buffer)
     const BuildInfo* info;
     int write_records;                // 0: only propagate the subtree bases
+    unsigned long long* ticket;       // k_emit_leaf: batches in ticket order (a counter that is zero at launch), or NULL: round-robin
 };
 struct NodeRange { unsigned long long lo, hi, leaf_offset; };
 __device__ __forceinline__ NodeRange node_range(const EmitJob& E) {
@@ -1297,7 +1299,11 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_emit_upper(Level L, Le
 // children) and nothing else. Lanes map to the tile's children by RANK (the children of a tile are consecutive in the
 // list below, so all loads are coalesced; 16 children per tile is typical and one round of 32 lanes covers it): the byte k
 // a child belongs to follows from the running per-byte counts with one SWAR compare, its position needs no bit index.
+// CHILD_RECS = false (level 1 of the device-driven build): the records of the children -- the bricks -- are written by
+// k_emit_leaf, which has them in the middle of the contiguous stream it writes; this kernel then only places the bricks
+// (C.base) and writes the tiles' own child records.
 struct UpperChild { unsigned long long psc, psc1, pend, gm; };
+template <bool CHILD_RECS>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_emit_upper_fast(Level L, Level C, EmitJob E, int bs) {
     if (build_aborted(E.info)) return;
     const int lane = threadIdx.x & 31;
@@ -1327,7 +1333,8 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_emit_upper_fast(Level 
         };
         auto load_child = [&](unsigned long long fc, int r, uint32_t through, UpperChild& u) {
             const unsigned long long c = fc + r;
-            u.psc = C.ps[c]; u.psc1 = C.ps[c + 1]; u.gm = C.mask[c]; u.pend = C.ps[fc + through];
+            u.psc = C.ps[c]; u.pend = C.ps[fc + through];
+            if (CHILD_RECS) { u.psc1 = C.ps[c + 1]; u.gm = C.mask[c]; }
         };
         auto prepare = [&](int q) {
             nW = __shfl_sync(0xffffffffu, myW, q);
@@ -1344,10 +1351,12 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_emit_upper_fast(Level 
             const uint32_t before = through - (uint32_t)__popc(byte);                 // children in the bytes below
             const unsigned long long gbase = base + (u.psc - ps0) + before;           // subtree region of this grandchild
             C.base[fc + r] = gbase;
-            const unsigned long long pos = base + (u.pend - ps0) + r;                 // its record, in the children block of its byte
-            if (unsigned long long* o = node_slot(E, R, pos)) {
-                const uint32_t gnz = nonzero_bytes(u.gm);
-                store_record(o, 0ULL, gbase + (u.psc1 - u.psc) - __popc(gnz), child_offsets_lut(gnz));
+            if (CHILD_RECS) {
+                const unsigned long long pos = base + (u.pend - ps0) + r;             // its record, in the children block of its byte
+                if (unsigned long long* o = node_slot(E, R, pos)) {
+                    const uint32_t gnz = nonzero_bytes(u.gm);
+                    store_record(o, 0ULL, gbase + (u.psc1 - u.psc) - __popc(gnz), child_offsets_lut(gnz));
+                }
             }
         };
         prepare(0);
@@ -1421,15 +1430,34 @@ __device__ __forceinline__ void st128(unsigned long long* p, unsigned long long 
 // second brick) and at the ends of a batch.
 // In geometry-only mode the leaf run is a constant pattern of period three words (data 1, children base 0, offsets ~0: the
 // word of field f is 1 - f).
-template <bool PAYLOAD, int MINB>
+//   BLOCKS (device-driven build): behind the last brick of a byte of the parent tile comes the parent's children block of
+//              that byte -- the records OF the bricks (data 0, base + leaves, offsets of the non-zero bytes), everything a
+//              lane needs is in the brick list. The seam carries it along (<= 8 more records), and all bricks of a
+//              level-1 tile become one uninterrupted stream.
+// What depends on the brick alone is computed ONCE, by the lane that holds the brick (32 bricks at a time), and left in
+// shared memory for the eight lanes that write it; batches are handed out in file order by a ticket (E.ticket), which keeps
+// the DRAM pages of the whole GPU's stores close together (store_probe: + 25 % over a fixed round-robin).
+struct LeafBrick { unsigned long long W, ab, cbase, off; };      // word | flags and counts | base + leaves | offsets of the non-zero bytes
+template <bool PAYLOAD, int MINB, bool BLOCKS>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MINB) k_emit_leaf(Level L, EmitJob E) {
-    __shared__ unsigned long long s_seam[WARPS_PER_BLOCK][2][4][32];
+    constexpr int SEAM = BLOCKS ? 64 : 32;
+    __shared__ __align__(16) unsigned long long s_seam[WARPS_PER_BLOCK][4][SEAM];
+    __shared__ __align__(16) LeafBrick s_brick[WARPS_PER_BLOCK][32];
+    __shared__ uint32_t s_kb[WARPS_PER_BLOCK][32];                                // key >> 3: (level-1 tile, byte) of the brick
+    __shared__ ulonglong2 s_prev[WARPS_PER_BLOCK][8];                             // the same two record words of the 7 bricks before the batch
+    __shared__ uint32_t s_pkb[WARPS_PER_BLOCK][8];
     if (build_aborted(E.info)) return;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const unsigned long long n = level_n(L);
     const unsigned long long nbatch = (n + 31) / 32;
     const unsigned long long nwarps = (unsigned long long)gridDim.x * WARPS_PER_BLOCK;
-    unsigned long long batch = (unsigned long long)blockIdx.x * WARPS_PER_BLOCK + wid;
+    // tickets are drawn two batches ahead (the atomic's round trip is hidden behind a whole batch)
+    auto draw = [&]() -> unsigned long long { return lane == 0 ? atomicAdd(E.ticket, 1ULL) : 0ULL; };
+    unsigned long long batch = (unsigned long long)blockIdx.x * WARPS_PER_BLOCK + wid, batch1 = batch + nwarps;
+    if (E.ticket) {
+        const unsigned long long a = draw(), b = draw();
+        batch = __shfl_sync(0xffffffffu, a, 0); batch1 = __shfl_sync(0xffffffffu, b, 0);
+    }
     if (batch >= nbatch) return;
     const NodeRange R = node_range(E);
     unsigned long long* const nodes = E.nodes;
@@ -1437,37 +1465,49 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MINB) k_emit_leaf(Level 
     const unsigned gmask = 0xffu << (8 * g);
     const int s2 = (2 * s) % 3;
     constexpr unsigned REL_BITS = 25, REL_MASK = (1u << REL_BITS) - 1u;
-    unsigned long long nW = 0ULL, nBase = 0ULL, nFc = 0ULL, nKey = ~0ULL;
+    constexpr unsigned F_NEXT = 1u << REL_BITS, F_HEAD = 2u << REL_BITS, F_VALID = 4u << REL_BITS, F_LOB = 8u << REL_BITS;
+    unsigned long long nW = 0ULL, nBase = 0ULL, nFc = 0ULL, nKey = ~0ULL, nKeyX = ~0ULL, pW = 0ULL, pBase = 0ULL, pKey = ~0ULL;
     auto prefetch = [&](unsigned long long bt) {              // loads only: a store that depends on one of them would stall the warp here
         const unsigned long long t = bt * 32 + lane;
-        nW = 0ULL; nBase = 0ULL; nFc = 0ULL; nKey = ~0ULL;
+        nW = 0ULL; nBase = 0ULL; nFc = 0ULL; nKey = ~0ULL; nKeyX = ~0ULL; pW = 0ULL; pBase = 0ULL; pKey = ~0ULL;
         if (bt < nbatch && t < n) {
             nW = L.mask[t];
             nBase = L.base[t];
             if (PAYLOAD) nFc = L.fc[t];
-            if (L.clear) nKey = L.key[t];
+            if (L.clear || BLOCKS) nKey = L.key[t];
+            if (BLOCKS && lane == 31 && t + 1 < n) nKeyX = L.key[t + 1];          // the brick behind the batch
+        }
+        // the seven bricks before the batch (a byte of the parent tile may begin there): lane l takes brick t0 - 1 - l
+        if (BLOCKS && bt < nbatch && lane < 7 && bt * 32 > (unsigned long long)lane) {
+            const unsigned long long u = bt * 32 - 1 - lane;
+            pKey = L.key[u]; pW = L.mask[u]; pBase = L.base[u];
         }
     };
     prefetch(batch);
     while (batch < nbatch) {
-        const int cnt = (int)min(32ULL, n - batch * 32);
-        const unsigned long long myW = nW, myBase = nBase, myFc = nFc, myKey = nKey;
-        batch += nwarps;
+        const unsigned long long t0 = batch * 32;
+        const int cnt = (int)min(32ULL, n - t0);
+        const unsigned long long myW = nW, myBase = nBase, myFc = nFc, myKey = nKey, myKeyX = nKeyX, prevW = pW, prevBase = pBase, prevKey = pKey;
+        unsigned long long drawn = 0ULL;
+        if (E.ticket) drawn = draw();
+        batch = batch1;
         prefetch(batch);                                                          // in flight while this batch is written
-        if (myKey != ~0ULL) L.clear[myKey] = 0ULL;                                // the brick's word in the bit-grid is consumed: leave it clean
+        if (L.clear && myKey != ~0ULL) L.clear[myKey] = 0ULL;                     // the brick's word in the bit-grid is consumed: leave it clean
         const unsigned nleaf = (unsigned)__popcll(myW);
         const uint32_t nzb = nonzero_bytes(myW);
-        const unsigned S = nleaf + (unsigned)__popc(nzb);                             // records of the brick's region
+        const unsigned nzc = (unsigned)__popc(nzb);
+        const unsigned S = nleaf + nzc;                                               // records of the brick's region
         // a rank's own bricks always lie inside its range; the capacity guard drops whole bricks
         const bool ok = lane < cnt && myW != 0ULL && E.write_records && myBase >= R.lo &&
                         myBase + (unsigned long long)(S + (E.root_here ? 1u : 0u)) <= R.hi;
         const unsigned okm = __ballot_sync(0xffffffffu, ok);
-        if (!okm) continue;
+        if (!okm) { batch1 = E.ticket ? __shfl_sync(0xffffffffu, drawn, 0) : batch + nwarps; continue; }
         const unsigned long long rel = myBase - R.lo;                                 // first record of the region in the buffer
         const unsigned long long ref = __shfl_sync(0xffffffffu, rel, __ffs(okm) - 1); // ... of the batch's first brick
         const unsigned long long leaf1 = 1ULL + R.leaf_offset + myFc;                 // payload: data index of the brick's first leaf
-        // (the gridsize-4 root brick and a brick further than 2^25 records from the batch's first -- no tree has one -- take the
-        // plain path below)
+        // (the gridsize-4 root brick takes the plain path below; so would a brick further than 2^25 records from the batch's
+        // first one, which no tree has: between two bricks that follow each other in the list lie at most the children blocks
+        // of their ancestors)
         const bool in_group = ok && !E.root_here && (rel - ref) <= (unsigned long long)REL_MASK;
         if (ok && !in_group) {
             unsigned long long* const out = nodes + 3ULL * rel;
@@ -1484,28 +1524,74 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MINB) k_emit_leaf(Level 
             if (E.root_here) { o[0] = 0ULL; o[1] = myBase + nleaf; o[2] = child_offsets(nzb); }   // gridsize 4: the single brick is the root
         }
         // does the next / previous brick of the batch follow without a gap?
-        const unsigned long long relN = __shfl_down_sync(0xffffffffu, rel, 1), relP = __shfl_up_sync(0xffffffffu, rel, 1);
-        const unsigned SP = __shfl_up_sync(0xffffffffu, S, 1);
         const unsigned gm = __ballot_sync(0xffffffffu, in_group);
-        const bool contigN = in_group && lane < 31 && ((gm >> (lane + 1)) & 1u) && rel + S == relN;
-        const bool contigP = in_group && lane > 0 && ((gm >> (lane - 1)) & 1u) && relP + SP == rel;
-        const unsigned packed = in_group ? ((unsigned)(rel - ref) | (contigN ? 1u << REL_BITS : 0u) | (contigP ? 0u : 1u << (REL_BITS + 1)) | (1u << (REL_BITS + 2))) : 0u;
+        bool contigN, contigP, last_of_byte = false;
+        if (BLOCKS) {
+            // bricks of one level-1 tile form one stream (this kernel writes the children blocks between them); the tile's
+            // own records follow its last brick
+            unsigned long long keyN = __shfl_down_sync(0xffffffffu, myKey, 1), keyP = __shfl_up_sync(0xffffffffu, myKey, 1);
+            if (lane == 31) keyN = myKeyX;
+            const unsigned long long key_before = __shfl_sync(0xffffffffu, prevKey, 0);
+            if (lane == 0) keyP = key_before;
+            last_of_byte = (keyN >> 3) != (myKey >> 3);
+            contigN = in_group && lane < 31 && ((gm >> (lane + 1)) & 1u) && (keyN >> 6) == (myKey >> 6);
+            contigP = in_group && lane > 0 && ((gm >> (lane - 1)) & 1u) && (keyP >> 6) == (myKey >> 6);
+        } else {
+            const unsigned long long relN = __shfl_down_sync(0xffffffffu, rel, 1), relP = __shfl_up_sync(0xffffffffu, rel, 1);
+            const unsigned SP = __shfl_up_sync(0xffffffffu, S, 1);
+            contigN = in_group && lane < 31 && ((gm >> (lane + 1)) & 1u) && rel + S == relN;
+            contigP = in_group && lane > 0 && ((gm >> (lane - 1)) & 1u) && relP + SP == rel;
+        }
+        const unsigned rel32o = (unsigned)(rel - ref);
+        const unsigned fa = in_group ? (rel32o | (contigN ? F_NEXT : 0u) | (contigP ? 0u : F_HEAD) | F_VALID | (last_of_byte ? F_LOB : 0u)) : 0u;
+        // leaves | non-zero bytes << 8 | their count << 16 | position of the region's first word inside its 32-byte sector << 20
+        // (the buffer is 256-byte aligned)
+        const unsigned fb = nleaf | (nzb << 8) | (nzc << 16) | (((3u * ((unsigned)ref + rel32o)) & 3u) << 20);
+        __syncwarp();                                                                 // (nobody still reads the previous batch)
+        {
+            LeafBrick B;
+            B.W = myW; B.ab = (unsigned long long)fa | ((unsigned long long)fb << 32);
+            B.cbase = myBase + nleaf; B.off = in_group ? child_offsets_lut(nzb) : 0ULL;
+            s_brick[wid][lane] = B;
+            if (BLOCKS) {
+                s_kb[wid][lane] = (uint32_t)(myKey >> 3);
+                if (lane < 7) {
+                    s_prev[wid][lane].x = prevBase + (unsigned)__popcll(prevW);
+                    s_prev[wid][lane].y = prevKey != ~0ULL ? child_offsets_lut(nonzero_bytes(prevW)) : 0ULL;
+                    s_pkb[wid][lane] = prevKey != ~0ULL ? (uint32_t)(prevKey >> 3) : 0xffffffffu;
+                }
+            }
+        }
+        __syncwarp();
         unsigned long long* const outref = nodes + 3ULL * ref;
         const unsigned long long baseref = R.lo + ref;
-        const unsigned ref32 = (unsigned)ref;
-        __syncwarp();                                                                 // (the seam buffers of the previous batch are free)
+        const unsigned long long room = (R.hi - R.lo) - ref;                          // records of the buffer from the batch's first brick on
         for (int r = 0; r < cnt; r += 4) {
-            const unsigned pk = __shfl_sync(0xffffffffu, packed, r + g);              // (lanes beyond cnt hold 0)
-            const unsigned long long W = __shfl_sync(0xffffffffu, myW, r + g);
+            const int bi = r + g;
+            const ulonglong2 bw = *reinterpret_cast<const ulonglong2*>(&s_brick[wid][bi].W);
+            const unsigned pk = (unsigned)bw.y, pb = (unsigned)(bw.y >> 32);
+            if (!(pk & F_VALID)) continue;                                            // (uniform in the group)
+            const unsigned long long W = bw.x;
             unsigned long long d0 = 1ULL;
-            if (PAYLOAD) d0 = __shfl_sync(0xffffffffu, leaf1, r + g);
-            if (!(pk >> (REL_BITS + 2))) continue;                                    // (uniform in the group)
             const unsigned rel32 = pk & REL_MASK;
-            const bool next_follows = (pk >> REL_BITS) & 1u, own_head = (pk >> (REL_BITS + 1)) & 1u;
+            const unsigned nl = pb & 0xffu, nz8 = (pb >> 8) & 0xffu, nzn = (pb >> 16) & 0xfu, a0 = (pb >> 20) & 3u;
+            // the children block behind the last brick of a byte: lane s takes the byte's s-th brick from the end
+            bool blk_on = false;
+            unsigned long long blk_cbase = 0ULL, blk_off = 0ULL;
+            if (BLOCKS && (pk & F_LOB)) {
+                const int u = bi - s;
+                if (u >= 0) {
+                    blk_on = s_kb[wid][u] == s_kb[wid][bi];
+                    if (blk_on) { const ulonglong2 rec = *reinterpret_cast<const ulonglong2*>(&s_brick[wid][u].cbase); blk_cbase = rec.x; blk_off = rec.y; }
+                } else {                                                              // the byte began in the batch before this one
+                    blk_on = s_pkb[wid][-u - 1] == s_kb[wid][bi];
+                    if (blk_on) { const ulonglong2 rec = s_prev[wid][-u - 1]; blk_cbase = rec.x; blk_off = rec.y; }
+                }
+            }
+            if (PAYLOAD) d0 = 1ULL + R.leaf_offset + L.fc[t0 + (unsigned)bi];
+            const bool next_follows = (pk & F_NEXT) != 0u, own_head = (pk & F_HEAD) != 0u;
             unsigned long long* const out = outref + 3ULL * rel32;                    // word 0 of the brick's region
-            const unsigned a0 = (3u * (ref32 + rel32)) & 3u;                          // position of word 0 inside its sector (the buffer is 256-byte aligned)
-            const unsigned nl = (unsigned)__popcll(W), words = 3u * nl;
-            const uint32_t nz8 = nonzero_bytes(W);
+            const unsigned words = 3u * nl;
             const unsigned head = (4u - a0) & 3u;                                     // words before the first sector boundary
             const unsigned tail = (a0 + words) & 3u;                                  // words behind the last one
             const unsigned iend = words - tail;                                       // interior: [head, iend), a multiple of four words long (possibly empty)
@@ -1534,7 +1620,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MINB) k_emit_leaf(Level 
             // ---- head, when the brick before this one does not cover it ----
             if (own_head && (unsigned)s < head) out[s] = s == 0 ? d0 : (unsigned long long)(long long)(1 - s);
             // ---- seam ----
-            unsigned long long* const sb = s_seam[wid][(r >> 2) & 1][g];
+            unsigned long long* const sb = s_seam[wid][g];
             if ((unsigned)s < tail) {                                                 // word iend + s of the run: field 3 - (tail - s), of the LAST leaf for field 0
                 const int fl = (int)(3u - (tail - (unsigned)s)) % 3;
                 sb[s] = fl == 0 ? (PAYLOAD ? d0 + (nl - 1u) : 1ULL) : (unsigned long long)(long long)(1 - fl);
@@ -1546,7 +1632,20 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MINB) k_emit_leaf(Level 
                 sb[j0 + 1] = baseref + rel32 + (unsigned)__popcll(W & lowmask(8 * s));
                 sb[j0 + 2] = child_offsets_lut(byte);
             }
-            unsigned len = tail + 3u * (unsigned)__popc(nz8);
+            unsigned len = tail + 3u * nzn;
+            if (BLOCKS && (pk & F_LOB)) {
+                const unsigned m = (unsigned)__popc(__ballot_sync(gmask, blk_on));    // bricks of the byte (its last s + 1 .. a prefix of the lanes)
+                const bool fits = (unsigned long long)rel32 + nl + nzn + m <= room;   // (speculative emission into a smaller buffer)
+                if (fits) {
+                    if (blk_on) {
+                        const unsigned j0 = len + 3u * (m - 1u - (unsigned)s);
+                        sb[j0] = 0ULL;
+                        sb[j0 + 1] = blk_cbase;
+                        sb[j0 + 2] = blk_off;
+                    }
+                    len += 3u * m;
+                }
+            }
             if (next_follows) {                                                       // up to the next brick's first sector boundary
                 const unsigned nh = (4u - (len & 3u)) & 3u;
                 if ((unsigned)s < nh) sb[len + s] = s == 0 ? (PAYLOAD ? d0 + nl : 1ULL) : (unsigned long long)(long long)(1 - s);
@@ -1555,12 +1654,17 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MINB) k_emit_leaf(Level 
             __syncwarp(gmask);
             unsigned long long* const so = out + iend;
 #pragma unroll
-            for (int i = 0; i < 2; i++) {
+            for (int i = 0; i < SEAM / 16; i++) {
                 const unsigned j = 2u * s + 16u * i;
-                if (j + 1u < len) st128(so + j, sb[j], sb[j + 1]);
-                else if (j < len) so[j] = sb[j];
+                if (16u * i < len) {                                                  // (uniform in the group)
+                    const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(sb + j);
+                    if (j + 1u < len) st128(so + j, v.x, v.y);
+                    else if (j < len) so[j] = v.x;
+                }
             }
+            __syncwarp(gmask);                                                        // (the seam buffer is free for the next round)
         }
+        if (E.ticket) batch1 = __shfl_sync(0xffffffffu, drawn, 0); else batch1 = batch + nwarps;
     }
 }
 
