@@ -1788,7 +1788,9 @@ static int fast_phase_a(svo_ctx* c, ull* table, bool fill_table, bool force_sync
         k_scan_lookback<3><<<(unsigned)nt, LB_THREADS, 0, c->stream>>>(g, n1, &dinfo->count[1], B.tile_lp, B.tile_sp, c->lv[1].ps.as<ull>(),
                                                                       c->lb_state.as<ull>(), c->lb_ticket.as<ull>(), c->lb_tickets, c->lb_epoch, dinfo); LAUNCHED();
         c->lb_tickets += nt;
-        k_brick_prefix<<<std::max(blocks_for(n1, BP_WARPS * 32), 1u), BP_WARPS * 32, 0, c->stream>>>(B); LAUNCHED();
+        int tpw = 32;                                  // tiles per warp: fewer when the level does not fill the GPU
+        while (tpw > 2 && n1 / tpw < (ull)c->sm_count * 32) tpw >>= 1;
+        k_brick_prefix<<<std::max(blocks_for(n1, BP_WARPS * tpw), 1u), BP_WARPS * 32, 0, c->stream>>>(B, tpw); LAUNCHED();
     }
     // subtree sizes of the big levels above: look-back scans (the small levels follow in k_top)
     for (int j = 2; j <= jB; j++) {

@@ -255,9 +255,9 @@ struct BrickTileTotals {   // per level-1 tile: leaves, brick records, subtree s
         e[2] = e[1] + (unsigned long long)(__popcll(W1) + __popc(nonzero_bytes(W1)));
     }
 };
-// A warp takes 32 consecutive level-1 tiles: their bricks are one contiguous run of the brick list, and the prefixes of
+// A warp takes tiles_per_warp (32; fewer when the level is small) consecutive level-1 tiles: their bricks are one contiguous run of the brick list, and the prefixes of
 // the run's first tile seed a plain running sum -- no per-tile logic, all loads and stores coalesced.
-__global__ void __launch_bounds__(BP_WARPS * 32) k_brick_prefix(BrickJob B) {
+__global__ void __launch_bounds__(BP_WARPS * 32) k_brick_prefix(BrickJob B, int tiles_per_warp) {
     if (build_aborted(B.info)) return;
     const unsigned long long n1 = level_n(B.L1);
     const int lane = threadIdx.x & 31;
@@ -268,9 +268,9 @@ __global__ void __launch_bounds__(BP_WARPS * 32) k_brick_prefix(BrickJob B) {
         B.info->n_leaves_local = nl;
         B.info->n_brick_records = ns;
     }
-    const unsigned long long t0 = w * 32;
+    const unsigned long long t0 = w * (unsigned long long)tiles_per_warp;
     if (t0 >= n1) return;
-    const unsigned long long t1 = min(t0 + 32, n1);
+    const unsigned long long t1 = min(t0 + (unsigned long long)tiles_per_warp, n1);
     const unsigned long long c0 = B.L1.fc[t0];
     const unsigned long long c1 = min(B.L1.fc[t1], B.L0.cap);
     unsigned long long lp = B.tile_lp[t0], sp = B.tile_sp[t0];

@@ -1441,23 +1441,23 @@ struct LeafBrick { unsigned long long W, ab, cbase, off; };      // word | flags
 template <bool PAYLOAD, int MINB, bool BLOCKS>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MINB) k_emit_leaf(Level L, EmitJob E) {
     constexpr int SEAM = BLOCKS ? 64 : 32;
-    __shared__ __align__(16) unsigned long long s_seam[WARPS_PER_BLOCK][4][SEAM];
+    __shared__ __align__(16) unsigned long long s_seam[WARPS_PER_BLOCK][2][4][SEAM];
+    __shared__ unsigned long long s_lut[256];                                     // child_offsets by byte
     __shared__ __align__(16) LeafBrick s_brick[WARPS_PER_BLOCK][32];
     __shared__ uint32_t s_kb[WARPS_PER_BLOCK][32];                                // key >> 3: (level-1 tile, byte) of the brick
     __shared__ ulonglong2 s_prev[WARPS_PER_BLOCK][8];                             // the same two record words of the 7 bricks before the batch
     __shared__ uint32_t s_pkb[WARPS_PER_BLOCK][8];
+    s_lut[threadIdx.x & 255] = g_child_offsets.v[threadIdx.x & 255];
+    __syncthreads();
     if (build_aborted(E.info)) return;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const unsigned long long n = level_n(L);
     const unsigned long long nbatch = (n + 31) / 32;
     const unsigned long long nwarps = (unsigned long long)gridDim.x * WARPS_PER_BLOCK;
-    // tickets are drawn two batches ahead (the atomic's round trip is hidden behind a whole batch)
-    auto draw = [&]() -> unsigned long long { return lane == 0 ? atomicAdd(E.ticket, 1ULL) : 0ULL; };
+    // the first two batches of a warp are fixed, the rest are tickets, drawn two batches ahead (the atomic's round trip is
+    // hidden behind a whole batch, and a small job -- two batches per warp at 1024^3 -- never waits for one)
+    auto draw = [&]() -> unsigned long long { return lane == 0 ? 2ULL * nwarps + atomicAdd(E.ticket, 1ULL) : 0ULL; };
     unsigned long long batch = (unsigned long long)blockIdx.x * WARPS_PER_BLOCK + wid, batch1 = batch + nwarps;
-    if (E.ticket) {
-        const unsigned long long a = draw(), b = draw();
-        batch = __shfl_sync(0xffffffffu, a, 0); batch1 = __shfl_sync(0xffffffffu, b, 0);
-    }
     if (batch >= nbatch) return;
     const NodeRange R = node_range(E);
     unsigned long long* const nodes = E.nodes;
@@ -1551,13 +1551,13 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MINB) k_emit_leaf(Level 
         {
             LeafBrick B;
             B.W = myW; B.ab = (unsigned long long)fa | ((unsigned long long)fb << 32);
-            B.cbase = myBase + nleaf; B.off = in_group ? child_offsets_lut(nzb) : 0ULL;
+            B.cbase = myBase + nleaf; B.off = s_lut[nzb];
             s_brick[wid][lane] = B;
             if (BLOCKS) {
                 s_kb[wid][lane] = (uint32_t)(myKey >> 3);
                 if (lane < 7) {
                     s_prev[wid][lane].x = prevBase + (unsigned)__popcll(prevW);
-                    s_prev[wid][lane].y = prevKey != ~0ULL ? child_offsets_lut(nonzero_bytes(prevW)) : 0ULL;
+                    s_prev[wid][lane].y = s_lut[nonzero_bytes(prevW)];
                     s_pkb[wid][lane] = prevKey != ~0ULL ? (uint32_t)(prevKey >> 3) : 0xffffffffu;
                 }
             }
@@ -1620,7 +1620,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MINB) k_emit_leaf(Level 
             // ---- head, when the brick before this one does not cover it ----
             if (own_head && (unsigned)s < head) out[s] = s == 0 ? d0 : (unsigned long long)(long long)(1 - s);
             // ---- seam ----
-            unsigned long long* const sb = s_seam[wid][g];
+            unsigned long long* const sb = s_seam[wid][(r >> 2) & 1][g];
             if ((unsigned)s < tail) {                                                 // word iend + s of the run: field 3 - (tail - s), of the LAST leaf for field 0
                 const int fl = (int)(3u - (tail - (unsigned)s)) % 3;
                 sb[s] = fl == 0 ? (PAYLOAD ? d0 + (nl - 1u) : 1ULL) : (unsigned long long)(long long)(1 - fl);
@@ -1630,7 +1630,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MINB) k_emit_leaf(Level 
                 const unsigned j0 = tail + 3u * (unsigned)__popc(nz8 & ((1u << s) - 1u));
                 sb[j0] = 0ULL;
                 sb[j0 + 1] = baseref + rel32 + (unsigned)__popcll(W & lowmask(8 * s));
-                sb[j0 + 2] = child_offsets_lut(byte);
+                sb[j0 + 2] = s_lut[byte];
             }
             unsigned len = tail + 3u * nzn;
             if (BLOCKS && (pk & F_LOB)) {
@@ -1662,7 +1662,6 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MINB) k_emit_leaf(Level 
                     else if (j < len) so[j] = v.x;
                 }
             }
-            __syncwarp(gmask);                                                        // (the seam buffer is free for the next round)
         }
         if (E.ticket) batch1 = __shfl_sync(0xffffffffu, drawn, 0); else batch1 = batch + nwarps;
     }
