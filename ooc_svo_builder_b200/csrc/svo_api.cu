@@ -384,6 +384,8 @@ int launch_voxelizer(svo_ctx* c) {
     if (c->q_end == c->q_begin) return SVO_OK;
     VoxJob J = make_voxjob(c);
     const size_t smem = J.pair_tri ? 0 : (size_t)VOX_BLOCK * c->fpt * sizeof(float);
+    if (OWNER)      // the owner pass has its own unit tickets; a build may be repeated on the same voxelization
+        CK(cudaMemsetAsync(c->qcount.as<ull>() + VOX_TICKET_BASE + VOX_TICKETS * VOX_TICKET_STRIDE, 0, (size_t)VOX_TICKETS * VOX_TICKET_STRIDE * sizeof(ull), c->stream));
     if (!OWNER) mark(c, EV_VS0);
     if (c->sliced) {
         // remote staging: wait (on the device) until every peer has published its block lists, then walk them
@@ -858,8 +860,8 @@ int svo_voxelize(svo_ctx* c) {
     CK(cudaSetDevice(c->device));
     int rc = ensure_pyramid(c);
     if (rc) return rc;
-    CK(c->qcount.ensure(8 * sizeof(ull)));
-    CK(cudaMemsetAsync(c->qcount.p, 0, 8 * sizeof(ull), c->stream));
+    CK(c->qcount.ensure(VOX_QCOUNT_WORDS * sizeof(ull)));
+    CK(cudaMemsetAsync(c->qcount.p, 0, VOX_QCOUNT_WORDS * sizeof(ull), c->stream));
     c->use_subset = c->world > 1 && !c->dispatched && !c->sliced && !(c->P > 1 && c->use_lists);
     { const char* e = getenv("SVO_VOX_KERNEL"); c->warp_kernel = !(e && strcmp(e, "block") == 0); }
     if (c->use_subset) CK(c->subset.ensure((size_t)(c->n_tris / VOX_BLOCK + 2) * sizeof(uint32_t)));

@@ -30,6 +30,8 @@ constexpr int MAX_LEVELS = 12;        // ceil(D/2), D <= 21 (libmorton's 21 bits
 #endif
 constexpr int VOX_BLOCK = SVO_VOX_BLOCK;   // threads per block of the small-bbox voxelizer
 constexpr int WARPS_PER_BLOCK = 8;
+// ticket counters of the voxelizer's unit scheduler: VoxJob::qcount[VOX_TICKET_BASE + (pass * VOX_TICKETS + c) * VOX_TICKET_STRIDE]
+constexpr int VOX_TICKETS = 8, VOX_TICKET_STRIDE = 16, VOX_TICKET_BASE = 16, VOX_QCOUNT_WORDS = VOX_TICKET_BASE + 2 * VOX_TICKETS * VOX_TICKET_STRIDE;
 
 constexpr int MAX_WORLD = 16;         // ranks of a sharded build that exchange through peer memory
 
@@ -436,9 +438,44 @@ __global__ void __launch_bounds__(VOX_BLOCK, SVO_VOX_MINBLOCKS) k_vox_warp(VoxJo
     }
     if (lane == 0) { mbar_init(&s_bar[wid][0], 1); mbar_init(&s_bar[wid][1], 1); mbar_fence_init(); }
     __syncwarp();
-    unsigned long long* ticket = J.qcount + (OWNER ? 6 : 5);
-    auto take = [&]() -> unsigned long long {               // lane 0 holds the value until it is broadcast
-        return lane == 0 ? atomicAdd(ticket, 1ULL) : 0ULL;
+    // Units are handed out by VOX_TICKETS counters, each on its own 128-byte line and each owning a contiguous 1/VOX_TICKETS of
+    // the units; a warp draws from its home counter and, when that is used up, from the one with the most work left. (ONE
+    // counter for the whole GPU was the kernel's real limit: returning atomics on a single address retire at ~370 M/s -- at
+    // 32 triangles per unit exactly the 12 G triangles/s the kernel ran at from 1024^3 to 8192^3, with 18 % of all warp
+    // stalls waiting for a ticket drawn a whole unit earlier.)
+    constexpr unsigned long long NONE = ~0ULL;
+    unsigned long long* const tk = J.qcount + VOX_TICKET_BASE + (OWNER ? VOX_TICKETS * VOX_TICKET_STRIDE : 0);
+    auto lo_of = [&](int c) -> unsigned long long { return count * (unsigned long long)c / VOX_TICKETS; };
+    int tc = (int)(((unsigned)blockIdx.x * (VOX_BLOCK / 32) + (unsigned)wid) % VOX_TICKETS);     // the counter this warp draws from
+    auto take = [&]() -> unsigned long long {               // raw ticket of counter tc; lane 0 holds the value until it is broadcast
+        return lane == 0 ? atomicAdd(tk + tc * VOX_TICKET_STRIDE, 1ULL) : 0ULL;
+    };
+    // the unit behind a raw ticket of counter c, or NONE when every counter is used up
+    auto resolve = [&](unsigned long long raw_lane0, int c) -> unsigned long long {
+        unsigned long long raw = __shfl_sync(0xffffffffu, raw_lane0, 0);
+        unsigned long long lo = lo_of(c), size = lo_of(c + 1) - lo;
+        if (raw < size) return lo + raw;
+        for (int tries = 0; tries < 4 * VOX_TICKETS; tries++) {
+            unsigned long long rem = 0ULL;
+            if (lane < VOX_TICKETS) {
+                const unsigned long long v = *(volatile const unsigned long long*)(tk + lane * VOX_TICKET_STRIDE);
+                const unsigned long long sz = lo_of(lane + 1) - lo_of(lane);
+                rem = v < sz ? sz - v : 0ULL;
+            }
+            int best = lane;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) {
+                const unsigned long long o = __shfl_xor_sync(0xffffffffu, rem, d);
+                const int ob = __shfl_xor_sync(0xffffffffu, best, d);
+                if (o > rem || (o == rem && ob < best)) { rem = o; best = ob; }
+            }
+            if (rem == 0ULL) return NONE;
+            tc = best;
+            raw = __shfl_sync(0xffffffffu, take(), 0);
+            lo = lo_of(tc); size = lo_of(tc + 1) - lo;
+            if (raw < size) return lo + raw;
+        }
+        return NONE;
     };
     // state of the unit that was located last
     int src = 0;
@@ -447,7 +484,8 @@ __global__ void __launch_bounds__(VOX_BLOCK, SVO_VOX_MINBLOCKS) k_vox_warp(VoxJo
     uint32_t uvalid = 0;                                    // triangles in it (<= 32)
     auto locate = [&](unsigned long long u) {
         if (MODE == 2) {
-            while (u >= s_pref[src + 1]) src++;             // a warp's tickets only grow: src (position in the rotated order) moves forward
+            if (u < s_pref[src]) src = 0;                   // (a unit of another counter's range)
+            while (u >= s_pref[src + 1]) src++;             // src: position in the rotated order
             const int r = s_order[src];                     // the source rank
             const uint64_t q0 = (uint64_t)J.subset[(size_t)r * J.pull_cap + (u - s_pref[src])] * UNIT;
             const uint64_t nseg = s_base[r + 1] - s_base[r];
@@ -466,18 +504,21 @@ __global__ void __launch_bounds__(VOX_BLOCK, SVO_VOX_MINBLOCKS) k_vox_warp(VoxJo
     auto stage = [&](int b) {
         if (uvalid == UNIT && lane == 0) bulk_load(wbuf + (size_t)b * unit_floats, uptr, unit_floats * 4u, &s_bar[wid][b]);
     };
-    unsigned long long cur = __shfl_sync(0xffffffffu, take(), 0);
-    unsigned long long next = __shfl_sync(0xffffffffu, take(), 0);
+    const int c0 = tc;
+    const unsigned long long r0 = take(), r1 = take();
+    unsigned long long cur = resolve(r0, c0);
+    unsigned long long next = cur != NONE ? resolve(r1, c0) : NONE;
     uint32_t phase = 0;
-    if (cur < count) { locate(cur); stage(0); }
+    if (cur != NONE) { locate(cur); stage(0); }
     float v[9];
-    for (int it = 0; cur < count; it++) {
+    for (int it = 0; cur != NONE; it++) {
         const int b = it & 1;
         const float* my_ptr = uptr;
         const uint32_t my_valid = uvalid;
         const uint32_t tri = (uint32_t)(ufirst + lane);
+        const int ca = tc;
         const unsigned long long ahead = take();            // ticket of iteration it + 2; consumed after the body
-        if (next < count) { locate(next); stage(b ^ 1); }   // buffer b^1 was last read in iteration it - 1 (before its __syncwarp)
+        if (next != NONE) { locate(next); stage(b ^ 1); }   // buffer b^1 was last read in iteration it - 1 (before its __syncwarp)
         const bool active = (uint32_t)lane < my_valid;
         if (my_valid == UNIT) {
             mbar_wait(&s_bar[wid][b], (phase >> b) & 1u);
@@ -492,7 +533,7 @@ __global__ void __launch_bounds__(VOX_BLOCK, SVO_VOX_MINBLOCKS) k_vox_warp(VoxJo
         __syncwarp();                                       // every lane has its vertices: the buffer may be refilled
         vox_small_body<OWNER, ENUM, BIG>(J, active, tri, 0u, v);
         cur = next;
-        next = __shfl_sync(0xffffffffu, ahead, 0);
+        next = cur != NONE ? resolve(ahead, ca) : NONE;
     }
 }
 
