@@ -220,43 +220,19 @@ __global__ void __launch_bounds__(FILTER_WARPS * 32) k_slice_filter(SliceJob S) 
     int d_lo[3], d_hi[3];
 #pragma unroll
     for (int a = 0; a < 3; a++) { d_lof[a] = S.D.lof[dd][a]; d_hif[a] = S.D.hif[dd][a]; d_lo[a] = S.D.lo[dd][a]; d_hi[a] = S.D.hi[dd][a]; }
-    // Geometry-only records (36 bytes): a unit is 1152 contiguous bytes, read as 72 coalesced 16-byte loads (the next unit's
-    // are in flight while this one is tested) and handed to the lanes through shared memory -- nine strided 4-byte loads per
-    // lane touched every cache line of the unit nine times and left the kernel bound by the load/store unit at 3 TB/s.
-    // (Payload records keep the strided loads: only 36 of their 84 bytes are needed. Slices are padded to whole units.)
-    __shared__ __align__(16) float s_unit[FILTER_WARPS][2][UNIT * 9];
-    const bool wide = fpt == 9 && (reinterpret_cast<uintptr_t>(S.D.tris) & 15) == 0;
-    float4 p0 = make_float4(0.f, 0.f, 0.f, 0.f), p1 = p0, p2 = p0;
-    auto fetch = [&](unsigned long long unit) {
-        const float4* q = reinterpret_cast<const float4*>(S.D.tris + unit * (UNIT * 9));
-        p0 = __ldg(q + lane); p1 = __ldg(q + 32 + lane);
-        if (lane < 8) p2 = __ldg(q + 64 + lane);
-    };
-    if (wide && gw * per < u1) fetch(gw * per);
     for (unsigned long long base = gw * per; base < u1; base += 64) {
         unsigned long long hits = 0;                            // lane d: bit j = unit base + j touches destination d
         const int nj = (int)min(64ULL, u1 - base);
-#pragma unroll 2
+#pragma unroll 4
         for (int j = 0; j < nj; j++) {
             const unsigned long long t = (base + j) * UNIT + lane;
             float mn[3], mx[3];
             bool odd = false;
-            float v[9];
-            if (wide) {
-                float4* sb = reinterpret_cast<float4*>(s_unit[wid][j & 1]);
-                sb[lane] = p0; sb[32 + lane] = p1;
-                if (lane < 8) sb[64 + lane] = p2;
-                if (base + j + 1 < u1) fetch(base + j + 1);
-                __syncwarp();
-#pragma unroll
-                for (int i = 0; i < 9; i++) v[i] = s_unit[wid][j & 1][lane * 9 + i];
-            }
             if (t < n) {
                 const float* c = S.D.tris + t * fpt;
-                if (!wide) {
+                float v[9];
 #pragma unroll
-                    for (int i = 0; i < 9; i++) v[i] = __ldg(c + i);
-                }
+                for (int i = 0; i < 9; i++) v[i] = __ldg(c + i);
 #pragma unroll
                 for (int a = 0; a < 3; a++) {
                     mn[a] = stdmin(v[a], stdmin(v[3 + a], v[6 + a])); mx[a] = stdmax(v[a], stdmax(v[3 + a], v[6 + a]));
