@@ -430,8 +430,8 @@ int main(int argc, char** argv) {
 
     // Triangle records: the file is read by several threads (pread) into a ring of pinned chunks inside the -l budget
     // and streamed to the device(s) in file order; the whole file is never resident on the host. One pool of pinned
-    // chunks per rank (at most 4 x 16 MB, inside the budget), reused for the output.
-    const int pool_slots = 4;
+    // chunks per rank (at most 8 x 16 MB, inside the budget), reused for the output.
+    const int pool_slots = 8;
     const size_t pool_chunk = std::max<size_t>(std::min<size_t>(budget / (size_t)(pool_slots * world), 16u << 20), 2 * 84);
     std::vector<PinnedPool> pools(world);
     for (int r = 0; r < world; r++) if (!pools[r].init(pool_slots, pool_chunk)) { std::cout << "Error: cannot allocate pinned IO buffers" << std::endl; return 0; }
