@@ -174,6 +174,8 @@ struct svo_ctx {
     DispatchJob dj;
 
     // remote staging of triangle slices (svo_dispatch.cuh)
+    DevBuf sl_ubox;                    // per-unit bounding boxes of this rank's slice (k_slice_boxes); valid until the slice changes
+    bool sl_boxes_valid = false;
     DevBuf window, sl_cursor;          // window = [SliceCtrl | exchange table | block lists | slice], one allocation peers map
     struct View { void* p = nullptr; template <class T> T* as() const { return static_cast<T*>(p); } } slice, sl_list, sl_ctrl, sl_xtable;
     ull* peer_xtable[MAX_WORLD];
@@ -534,7 +536,7 @@ void svo_ctx_destroy(svo_ctx* c) {
     c->d_lvlptrs.release(); c->d_nwords.release(); c->d_counts.release();
     c->part_counts.release(); c->part_cursor.release(); c->part_off.release(); c->pair_tri.release();
     c->queue[0].release(); c->queue[1].release(); c->qcount.release(); c->subset.release();
-    c->window.release(); c->sl_cursor.release();
+    c->window.release(); c->sl_cursor.release(); c->sl_ubox.release();
     c->inbox.release(); c->ctrl_buf.release(); c->blockcnt.release(); c->blockoff.release();
     if (c->h_ctrl) cudaFreeHost(c->h_ctrl);
     c->lb_state.release(); c->lb_ticket.release();
@@ -2328,7 +2330,7 @@ int svo_shard_slice_attach(svo_ctx* c, void* const* windows) {
     return SVO_OK;
 }
 
-int svo_shard_slice_fence(svo_ctx* c) {
+static int slice_fence(svo_ctx* c) {
     if (!c) return SVO_E_INVALID;
     if (!c->sl_attached) return fail(c, SVO_E_INVALID, "svo_shard_slice_fence before svo_shard_slice_attach");
     CK(cudaSetDevice(c->device));
@@ -2336,18 +2338,26 @@ int svo_shard_slice_fence(svo_ctx* c) {
     return SVO_OK;
 }
 
+// Public form: the caller is about to write into the slice itself, so the cached unit boxes go with the old contents.
+int svo_shard_slice_fence(svo_ctx* c) {
+    if (!c) return SVO_E_INVALID;
+    c->sl_boxes_valid = false;
+    return slice_fence(c);
+}
+
 int svo_shard_slice_upload(svo_ctx* c, const float* src, uint64_t n_local) {
     if (!c) return SVO_E_INVALID;
     if (!c->sl_attached) return fail(c, SVO_E_INVALID, "svo_shard_slice_upload before svo_shard_slice_attach");
     if (n_local > c->slice_cap) return fail(c, SVO_E_RANGE, "slice is larger than the capacity given to svo_shard_slice_create");
     if (n_local && !src) return fail(c, SVO_E_INVALID, "src is NULL");
-    int rc = svo_shard_slice_fence(c);                      // peers may still be reading the previous contents
+    int rc = slice_fence(c);                      // peers may still be reading the previous contents
     if (rc) return rc;
     for (int i = 0; i < EV_COUNT; i++) c->ev_set[i] = false;
     mark(c, EV_UP0);
     if (n_local) CK(cudaMemcpyAsync(c->slice.p, src, (size_t)n_local * c->slice_fpt * sizeof(float), cudaMemcpyDefault, c->stream));
     mark(c, EV_UP1);
     c->slice_n_local = n_local;
+    c->sl_boxes_valid = false;
     return SVO_OK;
 }
 
@@ -2355,7 +2365,7 @@ int svo_shard_slice_begin(svo_ctx* c, uint64_t n_local) {
     if (!c) return SVO_E_INVALID;
     if (!c->sl_attached) return fail(c, SVO_E_INVALID, "svo_shard_slice_begin before svo_shard_slice_attach");
     if (n_local > c->slice_cap) return fail(c, SVO_E_RANGE, "slice is larger than the capacity given to svo_shard_slice_create");
-    int rc = svo_shard_slice_fence(c);                      // peers may still be reading the previous contents
+    int rc = slice_fence(c);                      // peers may still be reading the previous contents
     if (rc) return rc;
     for (int i = 0; i < EV_COUNT; i++) c->ev_set[i] = false;
     mark(c, EV_UP0);
@@ -2363,6 +2373,7 @@ int svo_shard_slice_begin(svo_ctx* c, uint64_t n_local) {
     c->up_slot = 0; c->up_pending[0] = c->up_pending[1] = false;
     c->slice_n_local = n_local;
     c->stream_fill = 0;
+    c->sl_boxes_valid = false;                              // the slice is about to change
     if (n_local == 0) mark(c, EV_UP1);
     return SVO_OK;
 }
@@ -2382,6 +2393,7 @@ int svo_shard_slice_append(svo_ctx* c, const float* host_chunk, uint64_t n) {
     if (c->up_pending[slot ^ 1]) { CK(cudaEventSynchronize(c->up_ev[slot ^ 1])); c->up_pending[slot ^ 1] = false; }
     c->up_slot = slot ^ 1;
     c->stream_fill += n;
+    c->sl_boxes_valid = false;
     if (c->stream_fill == c->slice_n_local) mark(c, EV_UP1);
     return SVO_OK;
 }
@@ -2399,7 +2411,7 @@ int svo_shard_slice_publish(svo_ctx* c, const svo_params* params, uint64_t n_tot
     if (rc) return rc;
     const int dc = shard_chunk_depth(c);
     if (c->D - dc < 2) return fail(c, SVO_E_INVALID, "gridsize too small for this many shards");
-    rc = svo_shard_slice_fence(c);                          // the peers' list buffers are about to be rewritten (one-block wait kernel)
+    rc = slice_fence(c);                                    // the peers' list buffers are about to be rewritten (one-block wait kernel)
     if (rc) return rc;
     const uint32_t launches_before = c->launches;
     mark(c, EV_DSP0);
@@ -2427,9 +2439,23 @@ int svo_shard_slice_publish(svo_ctx* c, const svo_params* params, uint64_t n_tot
     S.cap = c->sl_cap_blocks * 4;
     S.cursor = c->sl_cursor.as<ull>();
     if (D.n_local) {
-        // one launch: list this slice's units per destination and (the block that finishes last) publish counts + flag
         const ull n_units = (D.n_local + UNIT - 1) / UNIT;
         const unsigned grid = (unsigned)std::min<ull>((n_units + FILTER_WARPS * 4 - 1) / (FILTER_WARPS * 4), (ull)c->sm_count * 8);
+        // The bounding boxes of the slice's 32-triangle units do not depend on the job: they are computed when the slice has
+        // changed (svo_shard_slice_begin / _append) and reused by every job on the same slice, whose filter then reads 32
+        // bytes per unit instead of the unit's 1152 / 2688. (SVO_SLICE_BOXES=0: test the triangles every time.)
+        static const bool use_boxes = !(getenv("SVO_SLICE_BOXES") && getenv("SVO_SLICE_BOXES")[0] == '0');
+        if (use_boxes) {
+            CK(c->sl_ubox.ensure((size_t)c->sl_cap_blocks * 4 * 2 * sizeof(float4)));
+            S.ubox = c->sl_ubox.as<float4>();
+            if (!c->sl_boxes_valid) {
+                S.ubox_mode = 1;
+                k_slice_boxes<<<grid, FILTER_WARPS * 32, 0, c->stream>>>(S); LAUNCHED();
+                c->sl_boxes_valid = true;
+            }
+            S.ubox_mode = 2;
+        }
+        // one launch: list this slice's units per destination and (the block that finishes last) publish counts + flag
         k_slice_filter<<<grid, FILTER_WARPS * 32, 0, c->stream>>>(S); LAUNCHED();
     } else {
         k_slice_post<<<1, MAX_WORLD, 0, c->stream>>>(S, 0); LAUNCHED();

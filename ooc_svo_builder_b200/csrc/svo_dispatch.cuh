@@ -188,6 +188,8 @@ struct SliceJob {
     SliceCtrl* ctrl[MAX_WORLD];
     unsigned long long cap;                     // list entries (32-triangle units) per region
     unsigned long long* cursor;                 // local: MAX_WORLD list cursors + [MAX_WORLD] the count of finished blocks (all zeroed by the posting block)
+    float4* ubox;                               // per 32-triangle unit of the slice, two float4: {min x, y, z, max x}, {max y, z, largest |coordinate|, NaN seen}
+    int ubox_mode;                              // 0: test the triangles (no cache), 1: fill the cache, nothing else (k_slice_boxes), 2: test the cached boxes
 };
 constexpr int FILTER_WARPS = 8;
 // order-preserving float <-> int maps (for the integer warp reductions): a < b  <=>  ord(a) < ord(b) for non-NaN floats
@@ -201,6 +203,59 @@ __device__ __forceinline__ float ord_to_float(int i) { return __int_as_float(i ^
 // absurdly large coordinate (float -> int conversion no longer monotone) go to every destination. Every warp owns a
 // contiguous run of units and reserves list space once per 64 of them (lane d keeps the hit mask of destination d), so the
 // list cursors see a fraction of the atomics a per-unit append would issue.
+// Bounding box of unit `u` of a slice (all 32 lanes; lane = triangle). any_odd: a triangle of the unit has a NaN or an
+// absurdly large coordinate. With `rec` != NULL lane 0 also writes the unit's cache record: the largest |coordinate| of the
+// unit decides the "absurdly large" test for ANY unit_div (|x| * unit_div is monotone in |x|), NaNs are flagged.
+__device__ __forceinline__ void unit_box(const float* tris, uint32_t fpt, unsigned long long n, unsigned long long u, int lane, float unit_div,
+                                         float (&umn)[3], float (&umx)[3], bool& any_odd, float4* rec) {
+    const unsigned long long t = u * UNIT + lane;
+    float mn[3], mx[3];
+    bool odd = false, nan = false;
+    float big = 0.0f;
+    if (t < n) {
+        const float* c = tris + t * fpt;
+        float v[9];
+#pragma unroll
+        for (int i = 0; i < 9; i++) v[i] = __ldg(c + i);
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            mn[a] = stdmin(v[a], stdmin(v[3 + a], v[6 + a])); mx[a] = stdmax(v[a], stdmax(v[3 + a], v[6 + a]));
+            odd = odd || !(fabsf(fmul(mn[a], unit_div)) < 1.0e9f) || !(fabsf(fmul(mx[a], unit_div)) < 1.0e9f);   // NaN compares false
+            nan = nan || mn[a] != mn[a] || mx[a] != mx[a];
+            if (mn[a] == mn[a]) big = fmaxf(big, fabsf(mn[a]));
+            if (mx[a] == mx[a]) big = fmaxf(big, fabsf(mx[a]));
+        }
+    } else {
+#pragma unroll
+        for (int a = 0; a < 3; a++) { mn[a] = __int_as_float(0x7f800000); mx[a] = __int_as_float(0xff800000); }
+    }
+    any_odd = __any_sync(0xffffffffu, odd);
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        umn[a] = ord_to_float(__reduce_min_sync(0xffffffffu, float_to_ord(mn[a])));
+        umx[a] = ord_to_float(__reduce_max_sync(0xffffffffu, float_to_ord(mx[a])));
+    }
+    if (rec) {
+        const bool any_nan = __any_sync(0xffffffffu, nan);
+        const float ubig = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(big)));     // big >= 0: the bit patterns order like the values
+        if (lane == 0) {
+            rec[0] = make_float4(umn[0], umn[1], umn[2], umx[0]);
+            rec[1] = make_float4(umx[1], umx[2], ubig, any_nan ? 1.0f : 0.0f);
+        }
+    }
+}
+// Fills the box cache of a slice: once per LOAD of the slice, not per job (svo_shard_slice_publish launches it when the slice
+// has changed since the last time).
+__global__ void __launch_bounds__(FILTER_WARPS * 32) k_slice_boxes(SliceJob S) {
+    const int lane = threadIdx.x & 31;
+    const unsigned long long n = S.D.n_local, n_units = (n + UNIT - 1) / UNIT;
+    const unsigned long long nwarps = (unsigned long long)gridDim.x * FILTER_WARPS;
+    for (unsigned long long u = (unsigned long long)blockIdx.x * FILTER_WARPS + (threadIdx.x >> 5); u < n_units; u += nwarps) {
+        float umn[3], umx[3];
+        bool any_odd;
+        unit_box(S.D.tris, S.D.fpt, n, u, lane, S.D.unit_div, umn, umx, any_odd, S.ubox + 2 * u);
+    }
+}
 __global__ void __launch_bounds__(FILTER_WARPS * 32) k_slice_filter(SliceJob S) {
     __shared__ int s_last;
     // (The wait for the peers to have finished reading the previous job's lists stays a ONE-block kernel in front of this
@@ -225,29 +280,20 @@ __global__ void __launch_bounds__(FILTER_WARPS * 32) k_slice_filter(SliceJob S) 
         const int nj = (int)min(64ULL, u1 - base);
 #pragma unroll 4
         for (int j = 0; j < nj; j++) {
-            const unsigned long long t = (base + j) * UNIT + lane;
-            float mn[3], mx[3];
-            bool odd = false;
-            if (t < n) {
-                const float* c = S.D.tris + t * fpt;
-                float v[9];
-#pragma unroll
-                for (int i = 0; i < 9; i++) v[i] = __ldg(c + i);
-#pragma unroll
-                for (int a = 0; a < 3; a++) {
-                    mn[a] = stdmin(v[a], stdmin(v[3 + a], v[6 + a])); mx[a] = stdmax(v[a], stdmax(v[3 + a], v[6 + a]));
-                    odd = odd || !(fabsf(fmul(mn[a], S.D.unit_div)) < 1.0e9f) || !(fabsf(fmul(mx[a], S.D.unit_div)) < 1.0e9f);   // NaN compares false
-                }
+            float umn_[3], umx_[3];
+            bool any_odd;
+            if (S.ubox_mode == 2) {
+                // the unit's box was computed when the slice was loaded (k_slice_boxes): it does not depend on the job
+                const float4 a = __ldg(S.ubox + 2 * (base + j)), b = __ldg(S.ubox + 2 * (base + j) + 1);
+                umn_[0] = a.x; umn_[1] = a.y; umn_[2] = a.z; umx_[0] = a.w; umx_[1] = b.x; umx_[2] = b.y;
+                any_odd = b.w != 0.0f || !(fmul(b.z, S.D.unit_div) < 1.0e9f);
             } else {
-#pragma unroll
-                for (int a = 0; a < 3; a++) { mn[a] = __int_as_float(0x7f800000); mx[a] = __int_as_float(0xff800000); }
+                unit_box(S.D.tris, fpt, n, base + j, lane, S.D.unit_div, umn_, umx_, any_odd, nullptr);
             }
-            const bool any_odd = __any_sync(0xffffffffu, odd);
             bool touch = true;
 #pragma unroll
             for (int a = 0; a < 3; a++) {
-                const float umn = ord_to_float(__reduce_min_sync(0xffffffffu, float_to_ord(mn[a])));
-                const float umx = ord_to_float(__reduce_max_sync(0xffffffffu, float_to_ord(mx[a])));
+                const float umn = umn_[a], umx = umx_[a];
                 if (lane < S.D.world) {
                     if (S.D.use_partitions) {
                         touch = touch && !(umx < d_lof[a]) && !(umn > d_hif[a]);
