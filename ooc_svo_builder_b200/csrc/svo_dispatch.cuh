@@ -278,18 +278,44 @@ __global__ void __launch_bounds__(FILTER_WARPS * 32) k_slice_filter(SliceJob S) 
     for (unsigned long long base = gw * per; base < u1; base += 64) {
         unsigned long long hits = 0;                            // lane d: bit j = unit base + j touches destination d
         const int nj = (int)min(64ULL, u1 - base);
+        if (S.ubox_mode == 2) {
+            // The units' boxes were computed when the slice was loaded (k_slice_boxes): they do not depend on the job. Here the
+            // roles are turned around: a lane holds the boxes of two units (coalesced loads, nothing waits for anything), the
+            // destinations are walked by the whole warp, and a ballot hands destination d's hit mask to lane d.
+            float4 bx[2][2];
+            bool valid[2], odd[2];
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                valid[h] = lane + 32 * h < nj;
+                bx[h][0] = bx[h][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (valid[h]) { bx[h][0] = __ldg(S.ubox + 2 * (base + lane + 32 * h)); bx[h][1] = __ldg(S.ubox + 2 * (base + lane + 32 * h) + 1); }
+                odd[h] = bx[h][1].w != 0.0f || !(fmul(bx[h][1].z, S.D.unit_div) < 1.0e9f);
+            }
+            for (int d = 0; d < S.D.world; d++) {
+                unsigned m[2];
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const float umn[3] = { bx[h][0].x, bx[h][0].y, bx[h][0].z }, umx[3] = { bx[h][0].w, bx[h][1].x, bx[h][1].y };
+                    bool touch = true;
+#pragma unroll
+                    for (int a = 0; a < 3; a++) {
+                        if (S.D.use_partitions) {
+                            touch = touch && !(umx[a] < S.D.lof[d][a]) && !(umn[a] > S.D.hif[d][a]);
+                        } else {
+                            const int l = clampi(f2i(fmul(umn[a], S.D.unit_div)), 0, S.D.gmax), hh = clampi(f2i(fmul(umx[a], S.D.unit_div)), 0, S.D.gmax);
+                            touch = touch && !(hh < S.D.lo[d][a] || l > S.D.hi[d][a]);
+                        }
+                    }
+                    m[h] = __ballot_sync(0xffffffffu, valid[h] && (touch || odd[h]));
+                }
+                if (lane == d) hits = (unsigned long long)m[0] | ((unsigned long long)m[1] << 32);
+            }
+        }
 #pragma unroll 4
-        for (int j = 0; j < nj; j++) {
+        for (int j = 0; j < (S.ubox_mode == 2 ? 0 : nj); j++) {
             float umn_[3], umx_[3];
             bool any_odd;
-            if (S.ubox_mode == 2) {
-                // the unit's box was computed when the slice was loaded (k_slice_boxes): it does not depend on the job
-                const float4 a = __ldg(S.ubox + 2 * (base + j)), b = __ldg(S.ubox + 2 * (base + j) + 1);
-                umn_[0] = a.x; umn_[1] = a.y; umn_[2] = a.z; umx_[0] = a.w; umx_[1] = b.x; umx_[2] = b.y;
-                any_odd = b.w != 0.0f || !(fmul(b.z, S.D.unit_div) < 1.0e9f);
-            } else {
-                unit_box(S.D.tris, fpt, n, base + j, lane, S.D.unit_div, umn_, umx_, any_odd, nullptr);
-            }
+            unit_box(S.D.tris, fpt, n, base + j, lane, S.D.unit_div, umn_, umx_, any_odd, nullptr);
             bool touch = true;
 #pragma unroll
             for (int a = 0; a < 3; a++) {
