@@ -296,7 +296,10 @@ int svo_ipc_close(void* dev_ptr);
  *             entries into the peers' windows with NVLink stores; no library collective on the path)
  *   svo_shard_slice_fence                    stream-ordered wait until every peer has finished reading this rank's
  *                                            slice for the last published job (call before writing into `slice`
- *                                            yourself; upload and publish do it for you)
+ *                                            yourself; upload and publish do it for you). The library keeps the bounding
+ *                                            boxes of the slice's 32-triangle units from one job to the next; they are
+ *                                            recomputed after svo_shard_slice_upload / _begin / _append / _fence, so a
+ *                                            caller that writes the slice itself MUST call svo_shard_slice_fence first.
  * Per-partition counts (svo_partition's part_tricounts) are not available in this mode. At most 16 ranks. */
 int svo_shard_slice_create(svo_ctx* ctx, uint64_t capacity_tris, int floats_per_tri, void** dev_window);
 int svo_shard_slice_attach(svo_ctx* ctx, void* const* windows);
