@@ -107,3 +107,22 @@ def test_cli_multi_gpu_files_match_oracle(tmp_path, oracle, gpus, payload):
     want = oracle.build(m.tris, m.length, 512, memory_limit_mb=100)
     got = oracle.read_outputs(str(tmp_path / "mesh") + "512_%d" % want.n_partitions)
     assert (got.header, got.nodes, got.data) == (want.header, want.nodes, want.data), out[-1500:]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("payload", [False, True])
+def test_cli_multi_gpu_levels_files_match_oracle(tmp_path, oracle, payload):
+    """-levels on the sharded path (internal nodes carry averaged data records; the ranks own contiguous ranges of BOTH files)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs, this box has %d" % torch.cuda.device_count())
+    m = mg.displaced_sphere(120, 120, seed=11)
+    if payload:
+        m = mg.Mesh(mg.with_payload(m.tris), m.length)
+    hdr = mg.write_tri(str(tmp_path / "mesh"), m)
+    exe = "svo_builder" if payload else "svo_builder_binary"
+    rc, out = run(exe, "-f", hdr, "-s", "256", "-l", "10", "-levels", "-gpus", "2")
+    assert rc == 0, out
+    want = oracle.build(m.tris, m.length, 256, memory_limit_mb=10, levels=True)
+    got = oracle.read_outputs(str(tmp_path / "mesh") + "256_%d" % want.n_partitions)
+    assert (got.header, got.nodes, got.data) == (want.header, want.nodes, want.data), out[-1500:]
